@@ -1,0 +1,205 @@
+/*
+ * spef_b200.h -- C ABI of libspef_b200.so: the B200 (sm_100a) implementation of SPEF's batched
+ * pose-inference hot path (Mobile-URSONet forward -> softmax -> soft-classification decode ->
+ * pose error / ESA score -> temporal pdf filter).
+ *
+ * The reference (possoj/Spacecraft-Pose-Estimation-Framework) is 100 % Python and has no FFI; its
+ * "back-end" boundary is a duck-typed object with predict(images) (src/spe/spe_torch.py:41-76,
+ * called from src/tools/evaluation.py:71 and src/temporal/inference.py:132).  Each entry point
+ * below names the reference function(s) it replaces; INTEGRATION.md shows the ctypes binding a
+ * reference maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 (SPEF_OK) or a spef_status code; nothing throws across the ABI;
+ *     spef_last_error(ctx) returns a human-readable message for the last failure on that ctx.
+ *   - *_dev pointers are caller-owned device memory on the ctx's device (e.g. torch
+ *     Tensor.data_ptr()); *_host pointers are caller-owned host memory (pinned memory makes the
+ *     copies asynchronous).  The library owns only weights, tables, workspaces and stream state
+ *     inside the ctx.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  All work is
+ *     stream-ordered; *_host variants synchronise the stream before returning.
+ *   - one ctx per device, not thread-safe, no global state.
+ *   - tensors: images [B,3,H,W] float32 NCHW in [0,1] (the reference's contract,
+ *     src/data/datasets/speed.py:66-69); quaternions scalar-first [B,4] float32; positions [B,3]
+ *     float32; logits / pdfs [B,n] float32 row-major.
+ */
+#ifndef SPEF_B200_H
+#define SPEF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPEF_ABI_VERSION 1
+
+typedef enum spef_status {
+  SPEF_OK = 0,
+  SPEF_ERR_INVALID = 1,     /* bad argument / shape / key */
+  SPEF_ERR_CUDA = 2,        /* CUDA runtime or driver error (message has the CUDA string) */
+  SPEF_ERR_STATE = 3,       /* call order violated (weights not finalised, histogram missing, ...) */
+  SPEF_ERR_UNSUPPORTED = 4, /* configuration the kernels do not implement */
+  SPEF_ERR_NUMERIC = 5      /* a reference ValueError condition (NaN in decode, zero pdf sum) */
+} spef_status;
+
+enum { SPEF_FP32 = 0, SPEF_BF16 = 1 };
+
+/* flag bits written per image by the decode / score kernels */
+enum {
+  SPEF_FLAG_ORI_NAN = 1u,      /* NaN in A: classification_utils.py:134-135 raises ValueError */
+  SPEF_FLAG_POS_ZERO_SUM = 2u, /* classification_utils.py:253-254 */
+  SPEF_FLAG_POS_NAN = 4u,      /* classification_utils.py:262-263 */
+  SPEF_FLAG_DOT_GT_1_01 = 8u   /* spe_utils.py:137-138 (dead code in the reference: diagnostic only) */
+};
+
+typedef struct spef_ctx spef_ctx;
+
+typedef struct spef_config {
+  int32_t struct_size; /* = sizeof(spef_config) */
+  int32_t device;      /* CUDA device ordinal */
+  int32_t img_h;       /* 240  (src/config/train/config.py:27) */
+  int32_t img_w;       /* 384 */
+  int32_t n_ori;       /* orientation head outputs (bins), e.g. 1728 */
+  int32_t n_pos;       /* position head outputs: 3 (regression) or bins (classification) */
+  int32_t pos_classification; /* 0: 'regression', 1: 'classification' */
+  int32_t precision;   /* SPEF_FP32 | SPEF_BF16: storage type of activations / GEMM operands */
+  int32_t max_batch;   /* largest B passed to forward/predict; sizes the workspaces */
+  int32_t pw_impl;     /* 0: default (tcgen05 GEMM for BF16, SIMT FP32 for FP32); 1: force SIMT (debug cross-check) */
+} spef_config;
+
+/* ---- lifecycle ------------------------------------------------------------------------------ */
+int spef_abi_version(void);
+/* replaces: SPETorch.__init__ (src/spe/spe_torch.py:24-39) + import_model's module construction
+ * (src/modeling/model.py:185-257) */
+int spef_create(spef_ctx** out, const spef_config* cfg);
+void spef_destroy(spef_ctx* ctx);
+const char* spef_last_error(const spef_ctx* ctx); /* ctx may be NULL: message of the last failed spef_create */
+
+/* ---- weights: replaces model.load_state_dict (src/modeling/model.py:261-266) --------------------
+ * `key` is a reference state_dict key (features.features.{i}..., head.ori.1.*,
+ * head.pos.0.*); data is the raw float32 tensor in PyTorch layout.  num_batches_tracked is ignored.
+ * spef_finalize_weights folds BatchNorm (eps 1e-5, src/modeling/common/pytorch_layers.py:55-56),
+ * repacks to kernel layouts, casts and uploads; it fails if any of the 315 float tensors is missing. */
+int spef_load_tensor(spef_ctx* ctx, const char* key, const float* data_host, const int64_t* shape, int32_t ndim);
+int spef_finalize_weights(spef_ctx* ctx);
+
+/* ---- histograms: replaces OrientationSoftClassification.histogram / .b and
+ * PositionSoftClassification.histogram (src/spe/classification_utils.py:39-83,168-176,201-216) -- */
+int spef_set_ori_histogram(spef_ctx* ctx, const double* quat_bins_host /*[n,4]*/, int32_t n);
+int spef_set_pos_histogram(spef_ctx* ctx, const double* pos_bins_host /*[n,3]*/, int32_t n);
+
+/* ---- network: replaces ModelWrapper.forward (src/modeling/common/pytorch_layers.py:29-32) ------ */
+int spef_forward(spef_ctx* ctx, const float* images_dev, int32_t batch,
+                 float* ori_out_dev /*[B,n_ori] logits*/, float* pos_out_dev /*[B,n_pos]*/, void* stream);
+
+/* teacher-forced single layer (parity harness; mirrors hooking one ConvBnAct of the reference):
+ * layer 0 = stem (input NCHW f32), 1..51 = the following conv layers in execution order
+ * (NHWC, ctx precision), 52 = global mean over H,W, 53 = head GEMM (in [B,1280], out f32 [B,n_ori+n_pos pad]).
+ * residual_dev may be NULL. */
+int spef_num_layers(const spef_ctx* ctx);
+int spef_layer_info(const spef_ctx* ctx, int32_t layer, int32_t* kind /*0 stem,1 pw,2 dw,3 pool,4 head*/,
+                    int32_t* cin, int32_t* cout, int32_t* hin, int32_t* win, int32_t* hout, int32_t* wout,
+                    int32_t* stride, int32_t* relu, int32_t* has_residual);
+int spef_layer_forward(spef_ctx* ctx, int32_t layer, const void* in_dev, const void* residual_dev,
+                       void* out_dev, int32_t batch, void* stream);
+
+/* ---- post-processing -------------------------------------------------------------------------
+ * spef_decode_ori replaces SPEUtils.last_activ (softmax, src/spe/spe_utils.py:75-76) when
+ * is_logits != 0, and OrientationSoftClassification.decode_batch
+ * (src/spe/classification_utils.py:113-166).  n must equal the histogram size.
+ * soft_out_dev [B,n], hinv_out_dev [B,16], argmax_out_dev [B] may be NULL.  flags_dev [B] is OR-ed. */
+int spef_decode_ori(spef_ctx* ctx, const float* in_dev, int32_t batch, int32_t n, int32_t is_logits,
+                    float* soft_out_dev, float* quat_out_dev, float* hinv_out_dev, int32_t* argmax_out_dev,
+                    uint32_t* flags_dev, void* stream);
+/* replaces softmax (spe_utils.py:77-79) + PositionSoftClassification.decode_batch
+ * (classification_utils.py:242-285) */
+int spef_decode_pos(spef_ctx* ctx, const float* in_dev, int32_t batch, int32_t n, int32_t is_logits,
+                    float* soft_out_dev, float* pos_out_dev, uint32_t* flags_dev, void* stream);
+/* replaces SPEUtils.get_score (src/spe/spe_utils.py:104-159) and the per-image error lists of
+ * evaluation() (src/tools/evaluation.py:82-85).  sums_dev[8] (double) is ACCUMULATED into:
+ *   [0] sum e_q (rad)  [1] sum e_t/|t|  [2] sum e_t (m)  [3] image count  [4] #images with |q.q^|>1.01
+ *   [5] #images with NaN error  [6],[7] reserved.  per_image_dev [B,2] = (e_q in degrees, e_t) may be NULL. */
+int spef_score(spef_ctx* ctx, const float* quat_pred_dev, const float* pos_pred_dev,
+               const float* quat_true_dev, const float* pos_true_dev, int32_t batch,
+               double* sums_dev, float* per_image_dev, void* stream);
+
+/* ---- fused predict: replaces SPETorch.predict (src/spe/spe_torch.py:41-76) ---------------------
+ * forward + softmax + decode on device.  ori_soft_out / pos_soft_out may be NULL.  When the ctx
+ * has pos_classification = 0, pos_out is the regressed position and pos_soft_out must be NULL. */
+int spef_predict(spef_ctx* ctx, const float* images_dev, int32_t batch,
+                 float* ori_soft_out_dev, float* quat_out_dev, float* pos_soft_out_dev, float* pos_out_dev,
+                 int32_t* argmax_out_dev, uint32_t* flags_dev, void* stream);
+/* same with HOST buffers: H2D of the images, predict, D2H of the results, stream synchronised. */
+int spef_predict_host(spef_ctx* ctx, const float* images_host, int32_t batch,
+                      float* ori_soft_out_host, float* quat_out_host, float* pos_soft_out_host, float* pos_out_host,
+                      int32_t* argmax_out_host, uint32_t* flags_out_host, void* stream);
+/* predict + score in one call (the body of evaluation()'s batch loop, src/tools/evaluation.py:69-85):
+ * targets come from the host, sums are accumulated in the ctx (spef_eval_reset / spef_eval_read). */
+int spef_eval_reset(spef_ctx* ctx, void* stream);
+int spef_eval_batch_host(spef_ctx* ctx, const float* images_host, const float* quat_true_host,
+                         const float* pos_true_host, int32_t batch, float* per_image_out_host /*[B,2] or NULL*/,
+                         void* stream);
+int spef_eval_batch(spef_ctx* ctx, const float* images_dev, const float* quat_true_dev,
+                    const float* pos_true_dev, int32_t batch, float* per_image_out_dev, void* stream);
+int spef_eval_read(spef_ctx* ctx, double* sums_host /*[8]*/, void* stream);
+double* spef_eval_sums_dev(spef_ctx* ctx); /* device pointer of the 8 accumulators (for an NCCL all-reduce) */
+
+/* host-buffer variants of the post-processing entry points (what SPEUtils.decode / get_score bind to) */
+int spef_decode_ori_host(spef_ctx* ctx, const float* in_host, int32_t batch, int32_t n, int32_t is_logits,
+                         float* soft_out_host, float* quat_out_host, float* hinv_out_host,
+                         int32_t* argmax_out_host, uint32_t* flags_out_host, void* stream);
+int spef_decode_pos_host(spef_ctx* ctx, const float* in_host, int32_t batch, int32_t n, int32_t is_logits,
+                         float* soft_out_host, float* pos_out_host, uint32_t* flags_out_host, void* stream);
+int spef_score_host(spef_ctx* ctx, const float* quat_pred_host, const float* pos_pred_host,
+                    const float* quat_true_host, const float* pos_true_host, int32_t batch,
+                    double* sums_out_host /*[8], overwritten*/, float* per_image_out_host, void* stream);
+
+/* ---- temporal: replaces Inference.predict(..., 'Adaptative') / Inference.reset
+ * (src/temporal/inference.py:92-99, 131-180) and TemporalPDF.update_pdf
+ * (src/temporal/pdf_compare.py:94-133) for n_streams independent videos (one frame each per call).
+ * Requires pos_classification = 1.  Outputs are [n_streams, ...]; any *_out pointer may be NULL. */
+typedef struct spef_temporal_out {
+  float* still_ori_soft;  /* [S,n_ori] */
+  float* still_pos_soft;  /* [S,n_pos] */
+  float* still_quat;      /* [S,4]  sign-continuous */
+  float* still_pos;       /* [S,3] */
+  float* video_ori_soft;  /* [S,n_ori] filtered pdf */
+  float* video_pos_soft;  /* [S,n_pos] */
+  float* video_quat;      /* [S,4] */
+  float* video_pos;       /* [S,3] */
+  float* ori_distance;    /* [S] */
+  float* pos_distance;    /* [S] */
+  uint32_t* flags;        /* [S] */
+} spef_temporal_out;
+int spef_temporal_reset(spef_ctx* ctx, int32_t n_streams, void* stream);
+/* from logits already on the device (filter + decode only) */
+int spef_temporal_step_logits(spef_ctx* ctx, const float* ori_logits_dev, const float* pos_logits_dev,
+                              int32_t n_streams, const spef_temporal_out* out_dev, void* stream);
+/* from images on the device: forward + the above.  apply_filter = 0 reproduces Inference.predict(image, None):
+ * still pose + sign continuity only, the filter state is left untouched and video_* outputs are not written. */
+int spef_temporal_step(spef_ctx* ctx, const float* images_dev, int32_t n_streams, int32_t apply_filter,
+                       const spef_temporal_out* out_dev, void* stream);
+/* TemporalPDF.update_pdf (src/temporal/pdf_compare.py:94-133, 'l2' metric) on caller-owned state:
+ * state_dev [S,n] previous filtered pdf, has_state_dev [S] (0 = first frame; set to 1 by the call). */
+int spef_pdf_filter(spef_ctx* ctx, const float* cur_dev /*[S,n]*/, int32_t n_streams, int32_t n, float* state_dev,
+                    int32_t* has_state_dev, float n_coef, float alpha, float* out_dev /*[S,n]*/,
+                    float* distance_dev /*[S]*/, void* stream);
+
+/* ---- introspection (bench / roofline bookkeeping) --------------------------------------------- */
+/* number of kernel launches this ctx has issued since creation */
+int64_t spef_launch_count(const spef_ctx* ctx);
+/* algorithmic bytes / flops of one forward at batch B under the ctx precision */
+int spef_forward_cost(const spef_ctx* ctx, int32_t batch, double* bytes_out, double* flops_out);
+/* per-layer device time of the most recent spef_forward_timed call, milliseconds [spef_num_layers] */
+int spef_forward_timed(spef_ctx* ctx, const float* images_dev, int32_t batch, float* ori_out_dev,
+                       float* pos_out_dev, float* layer_ms_host, void* stream);
+
+/* debug: the device-side 4x4 Jacobi eigen-solver compiled for the host (no GPU needed), so that the CPU
+ * test-suite can pin it against LAPACK.  a_in row-major symmetric; evecs row-major with eigenvectors as columns. */
+int spef_debug_jacobi4_host(const double* a_in, double* evals, double* evecs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPEF_B200_H */

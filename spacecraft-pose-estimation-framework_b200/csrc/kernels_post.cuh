@@ -1,0 +1,427 @@
+// Post-processing kernels: softmax + soft-classification decode (orientation: dominant eigenvector of
+// sum_b p_b q_b q_b^T; position: pdf-weighted mean), pose error / ESA score partial sums, the temporal
+// adaptive pdf filter and quaternion sign continuity.
+// Reference semantics: src/spe/spe_utils.py:56-159, src/spe/classification_utils.py:113-166,242-285,
+// src/tools/evaluation.py:82-85, src/temporal/pdf_compare.py:94-133, src/temporal/inference.py:136-180.
+#pragma once
+#include "common.cuh"
+#include <math.h>
+
+namespace spef {
+
+// ---- row iteration helper: lane-strided float4 when the row is 16-byte aligned, scalar otherwise -----
+template <typename F>
+__device__ __forceinline__ void for_each_in_row(const float* __restrict__ row, int n, bool vec_ok, int lane, F&& f) {
+  if (vec_ok) {
+    const float4* r4 = reinterpret_cast<const float4*>(row);
+    const int n4 = n >> 2;
+    for (int i = lane; i < n4; i += 32) {
+      const float4 v = r4[i];
+      f(i * 4, v.x, v.y, v.z, v.w, 4);
+    }
+    for (int i = (n4 << 2) + lane; i < n; i += 32) f(i, row[i], 0.f, 0.f, 0.f, 1);
+  } else {
+    for (int i = lane; i < n; i += 32) f(i, row[i], 0.f, 0.f, 0.f, 1);
+  }
+}
+
+// Cyclic Jacobi eigen-solver for a symmetric 4x4 (double).  a is destroyed (diagonal = eigenvalues),
+// v receives the eigenvectors as columns.
+__host__ __device__ inline void jacobi4(double (&a)[4][4], double (&v)[4][4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[i][j] = (i == j) ? 1.0 : 0.0;
+  for (int sweep = 0; sweep < 16; ++sweep) {
+    double off = 0.0, diag = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      diag += a[i][i] * a[i][i];
+#pragma unroll
+      for (int j = i + 1; j < 4; ++j) off += a[i][j] * a[i][j];
+    }
+    if (!(off > 1e-30 * diag)) break;
+#pragma unroll
+    for (int p = 0; p < 3; ++p) {
+#pragma unroll
+      for (int q = p + 1; q < 4; ++q) {
+        const double apq = a[p][q];
+        if (apq == 0.0) continue;
+        const double theta = (a[q][q] - a[p][p]) / (2.0 * apq);
+        const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {  // A <- A J  (columns p, q)
+          const double akp = a[k][p], akq = a[k][q];
+          a[k][p] = c * akp - s * akq;
+          a[k][q] = s * akp + c * akq;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {  // A <- J^T A  (rows p, q)
+          const double apk = a[p][k], aqk = a[q][k];
+          a[p][k] = c * apk - s * aqk;
+          a[q][k] = s * apk + c * aqk;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const double vkp = v[k][p], vkq = v[k][q];
+          v[k][p] = c * vkp - s * vkq;
+          v[k][q] = s * vkp + c * vkq;
+        }
+      }
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------------------------
+// Orientation: softmax (spe_utils.py:75-76) + decode (classification_utils.py:131-147), one warp per image.
+//   pass 1: row max + first-max argmax (np.argmax tie rule)
+//   pass 2: w = exp(z - max) (or w = p when the input is already a pdf); S = sum w; A = sum w q q^T
+//           (10 unique entries; 4-bin f32 partial sums flushed into f64 accumulators, f64 warp reduction)
+//   then cyclic Jacobi in f64 on the 4x4, dominant eigenvector, renormalise, cast to f32.
+//   pass 3 (optional): ori_soft = w / S.
+// The eigenvector sign is unspecified in the reference (LAPACK geev); we return scalar part >= 0.
+// qtab: [n] float4 (scalar-first quaternion bins).  ld = row pitch of `in` in floats.
+// --------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) decode_ori_kernel(const float* __restrict__ in, int ld, int B, int n, int is_logits,
+                                                         const float4* __restrict__ qtab, float* __restrict__ soft_out,
+                                                         float* __restrict__ quat_out, float* __restrict__ hinv_out,
+                                                         int* __restrict__ argmax_out, uint32_t* __restrict__ flags) {
+  const int lane = threadIdx.x & 31;
+  const int img = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (img >= B) return;
+  const float* row = in + (size_t)img * ld;
+  const bool vec_ok = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(in) & 15) == 0);
+
+  float mx = -INFINITY;
+  int amax = 0x7fffffff;
+  if (is_logits || argmax_out != nullptr) {
+    for_each_in_row(row, n, vec_ok, lane, [&](int i, float a, float b, float c, float d, int cnt) {
+      if (a > mx) { mx = a; amax = i; }
+      if (cnt == 4) {
+        if (b > mx) { mx = b; amax = i + 1; }
+        if (c > mx) { mx = c; amax = i + 2; }
+        if (d > mx) { mx = d; amax = i + 3; }
+      }
+    });
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float om = __shfl_xor_sync(0xffffffffu, mx, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, amax, o);
+      if (om > mx || (om == mx && oi < amax)) { mx = om; amax = oi; }
+    }
+    if (argmax_out != nullptr && lane == 0) argmax_out[img] = amax;
+  }
+
+  // accumulators: S, then a00 a01 a02 a03 a11 a12 a13 a22 a23 a33
+  double acc[11];
+#pragma unroll
+  for (int k = 0; k < 11; ++k) acc[k] = 0.0;
+  for_each_in_row(row, n, vec_ok, lane, [&](int i, float a, float b, float c, float d, int cnt) {
+    const float z[4] = {a, b, c, d};
+    float part[11];
+#pragma unroll
+    for (int k = 0; k < 11; ++k) part[k] = 0.f;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (e < cnt) {
+        const float w = is_logits ? expf(z[e] - mx) : z[e];
+        const float4 q = __ldg(qtab + i + e);
+        const float w0 = w * q.x, w1 = w * q.y, w2 = w * q.z, w3 = w * q.w;
+        part[0] += w;
+        part[1] = fmaf(w0, q.x, part[1]); part[2] = fmaf(w0, q.y, part[2]);
+        part[3] = fmaf(w0, q.z, part[3]); part[4] = fmaf(w0, q.w, part[4]);
+        part[5] = fmaf(w1, q.y, part[5]); part[6] = fmaf(w1, q.z, part[6]);
+        part[7] = fmaf(w1, q.w, part[7]); part[8] = fmaf(w2, q.z, part[8]);
+        part[9] = fmaf(w2, q.w, part[9]); part[10] = fmaf(w3, q.w, part[10]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 11; ++k) acc[k] += (double)part[k];
+  });
+#pragma unroll
+  for (int k = 0; k < 11; ++k) acc[k] = warp_sum(acc[k]);
+
+  const double S = acc[0];
+  if (soft_out != nullptr && is_logits) {
+    const float sf = (float)S;
+    float* orow = soft_out + (size_t)img * n;
+    const bool ovec = vec_ok && ((n & 3) == 0) && ((reinterpret_cast<uintptr_t>(soft_out) & 15) == 0);
+    if (ovec) {
+      const float4* r4 = reinterpret_cast<const float4*>(row);
+      float4* o4 = reinterpret_cast<float4*>(orow);
+      for (int i = lane; i < (n >> 2); i += 32) {
+        const float4 v = r4[i];
+        o4[i] = make_float4(expf(v.x - mx) / sf, expf(v.y - mx) / sf, expf(v.z - mx) / sf, expf(v.w - mx) / sf);
+      }
+    } else {
+      for (int i = lane; i < n; i += 32) orow[i] = expf(row[i] - mx) / sf;
+    }
+  }
+
+  // every lane solves the same 4x4 redundantly (no divergence, no broadcast needed)
+  double a[4][4], v[4][4];
+  a[0][0] = acc[1]; a[0][1] = a[1][0] = acc[2]; a[0][2] = a[2][0] = acc[3]; a[0][3] = a[3][0] = acc[4];
+  a[1][1] = acc[5]; a[1][2] = a[2][1] = acc[6]; a[1][3] = a[3][1] = acc[7];
+  a[2][2] = acc[8]; a[2][3] = a[3][2] = acc[9]; a[3][3] = acc[10];
+  if (is_logits) {  // normalise like the reference (A is built from the softmax output)
+    const double inv = 1.0 / S;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) a[i][j] *= inv;
+  }
+  bool bad = false;
+#pragma unroll
+  for (int k = 1; k < 11; ++k) bad = bad || isnan(acc[k]);
+  bad = bad || (is_logits && isnan(S));
+  if (bad) {
+    if (lane == 0) {
+      if (flags != nullptr) atomicOr(flags + img, 1u);
+      const float qn = __int_as_float(0x7fc00000);
+      reinterpret_cast<float4*>(quat_out)[img] = make_float4(qn, qn, qn, qn);
+    }
+    return;
+  }
+  jacobi4(a, v);
+  int best = 0;
+  double best_val = a[0][0];
+#pragma unroll
+  for (int k = 1; k < 4; ++k) {
+    if (a[k][k] > best_val) { best_val = a[k][k]; best = k; }
+  }
+  double q[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) q[k] = (best == 0) ? v[k][0] : (best == 1) ? v[k][1] : (best == 2) ? v[k][2] : v[k][3];
+  double nrm = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  double sgn = (q[0] < 0.0) ? -1.0 : 1.0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) q[k] = sgn * q[k] / nrm;
+  if (lane == 0) {
+    reinterpret_cast<float4*>(quat_out)[img] = make_float4((float)q[0], (float)q[1], (float)q[2], (float)q[3]);
+  }
+  if (hinv_out != nullptr) {
+    // h_inv = A^-1 = V diag(1/lambda) V^T  (classification_utils.py:142); static indexing keeps a, v in registers
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+      const int r = e >> 2, c = e & 3;
+      double h = 0.0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) h += v[r][k] * v[c][k] / a[k][k];
+      if (lane == e) hinv_out[(size_t)img * 16 + e] = (float)h;
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------------------------
+// Position: softmax (spe_utils.py:77-79) + weighted mean of the bin centres (classification_utils.py:253-265).
+// ptab: [n] float4 (x, y, z, 0).
+// --------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) decode_pos_kernel(const float* __restrict__ in, int ld, int B, int n, int is_logits,
+                                                         const float4* __restrict__ ptab, float* __restrict__ soft_out,
+                                                         float* __restrict__ pos_out, uint32_t* __restrict__ flags) {
+  const int lane = threadIdx.x & 31;
+  const int img = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (img >= B) return;
+  const float* row = in + (size_t)img * ld;
+  const bool vec_ok = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(in) & 15) == 0);
+  float mx = -INFINITY;
+  if (is_logits) {
+    for_each_in_row(row, n, vec_ok, lane, [&](int, float a, float b, float c, float d, int cnt) {
+      mx = fmaxf(mx, a);
+      if (cnt == 4) mx = fmaxf(mx, fmaxf(b, fmaxf(c, d)));
+    });
+    mx = warp_max(mx);
+  }
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  for_each_in_row(row, n, vec_ok, lane, [&](int i, float a, float b, float c, float d, int cnt) {
+    const float z[4] = {a, b, c, d};
+    float part[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (e < cnt) {
+        const float w = is_logits ? expf(z[e] - mx) : z[e];
+        const float4 x = __ldg(ptab + i + e);
+        part[0] += w;
+        part[1] = fmaf(w, x.x, part[1]); part[2] = fmaf(w, x.y, part[2]); part[3] = fmaf(w, x.z, part[3]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc[k] += (double)part[k];
+  });
+#pragma unroll
+  for (int k = 0; k < 4; ++k) acc[k] = warp_sum(acc[k]);
+  const double S = acc[0];
+  if (soft_out != nullptr && is_logits) {
+    const float sf = (float)S;
+    float* orow = soft_out + (size_t)img * n;
+    for (int i = lane; i < n; i += 32) orow[i] = expf(row[i] - mx) / sf;
+  }
+  if (lane == 0) {
+    uint32_t fl = 0;
+    if (S == 0.0) fl |= 2u;
+    const float x = (float)(acc[1] / S), y = (float)(acc[2] / S), z = (float)(acc[3] / S);
+    if (isnan(x) || isnan(y) || isnan(z)) fl |= 4u;
+    pos_out[(size_t)img * 3 + 0] = x;
+    pos_out[(size_t)img * 3 + 1] = y;
+    pos_out[(size_t)img * 3 + 2] = z;
+    if (fl && flags != nullptr) atomicOr(flags + img, fl);
+  }
+}
+
+// --------------------------------------------------------------------------------------------------
+// Score (spe_utils.py:119-157): per image, float32 with NumPy's operation order and no FMA contraction:
+//   e_t = sqrt(dx^2 + dy^2 + dz^2); e_tn = e_t / |t|; c = |sum q^ q|; c = min(c, 1); e_q = 2 acos(c).
+// Block-reduced in f64 and atomically accumulated into sums[0..5] (see spef_b200.h).  per_image [B,2]
+// = (e_q in degrees, e_t) as evaluation.py:82-85.
+// --------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) score_kernel(const float* __restrict__ qp, const float* __restrict__ tp,
+                                                    const float* __restrict__ qt, const float* __restrict__ tt, int B,
+                                                    double* __restrict__ sums, float* __restrict__ per_image) {
+  double s[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B; i += gridDim.x * blockDim.x) {
+    const float dx = __fsub_rn(tt[i * 3 + 0], tp[i * 3 + 0]);
+    const float dy = __fsub_rn(tt[i * 3 + 1], tp[i * 3 + 1]);
+    const float dz = __fsub_rn(tt[i * 3 + 2], tp[i * 3 + 2]);
+    const float e_t = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+    const float tx = tt[i * 3 + 0], ty = tt[i * 3 + 1], tz = tt[i * 3 + 2];
+    const float nt = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(tx, tx), __fmul_rn(ty, ty)), __fmul_rn(tz, tz)));
+    const float e_tn = __fdiv_rn(e_t, nt);
+    float d = __fmul_rn(qp[i * 4 + 0], qt[i * 4 + 0]);
+    d = __fadd_rn(d, __fmul_rn(qp[i * 4 + 1], qt[i * 4 + 1]));
+    d = __fadd_rn(d, __fmul_rn(qp[i * 4 + 2], qt[i * 4 + 2]));
+    d = __fadd_rn(d, __fmul_rn(qp[i * 4 + 3], qt[i * 4 + 3]));
+    float c = fabsf(d);
+    const bool over = c > 1.01f;
+    if (c > 1.f) c = 1.f;
+    const float e_q = __fmul_rn(2.f, acosf(c));
+    s[0] += (double)e_q;
+    s[1] += (double)e_tn;
+    s[2] += (double)e_t;
+    s[3] += 1.0;
+    if (over) s[4] += 1.0;
+    if (isnan(e_q) || isnan(e_tn)) s[5] += 1.0;
+    if (per_image != nullptr) {
+      per_image[i * 2 + 0] = __fdiv_rn(__fmul_rn(e_q, 180.f), 3.14159265358979323846f);
+      per_image[i * 2 + 1] = e_t;
+    }
+  }
+  __shared__ double red[8][6];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) s[k] = warp_sum(s[k]);
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) red[warp][k] = s[k];
+  }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w][threadIdx.x];
+    if (t != 0.0) atomicAdd(sums + threadIdx.x, t);
+  }
+}
+
+// --------------------------------------------------------------------------------------------------
+// Temporal adaptive pdf filter, TemporalPDF.update_pdf with the 'l2' metric (pdf_compare.py:94-133),
+// one CTA per stream.  state [S,n] = previous filtered pdf, has_state [S].
+//   cur <- cur / sum(cur);  first frame: state = out = cur, d = 0
+//   else d = || cur/sum(cur) - state/sum(state) ||_2 ; w = clip(exp(-alpha d), 0, 1)
+//        upd = (w n_coef) cur + (1 - w) state ; upd /= sum(upd) ; state = out = upd
+// Array arithmetic is float32 like NumPy's (NEP 50: python-float scalars do not promote f32 arrays);
+// reductions are accumulated in f64 and rounded to f32.
+// --------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double block_sum_256(double v, double* red) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  double t = 0.0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) t += red[w];
+  return t;
+}
+
+__global__ void __launch_bounds__(256) temporal_filter_kernel(const float* __restrict__ cur, int n, float* __restrict__ state,
+                                                              int* __restrict__ has_state, float n_coef, float alpha,
+                                                              float* __restrict__ out, float* __restrict__ distance) {
+  __shared__ double red[8];
+  const int s = blockIdx.x;
+  const float* c = cur + (size_t)s * n;
+  float* st = state + (size_t)s * n;
+  float* o = out + (size_t)s * n;
+  const int had = has_state[s];  // read before the first barrier: thread 0 rewrites it at the end
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) acc += (double)c[i];
+  const float s_cur = (float)block_sum_256(acc, red);
+  if (!had) {
+    for (int i = threadIdx.x; i < n; i += 256) {
+      const float v = __fdiv_rn(c[i], s_cur);
+      st[i] = v;
+      o[i] = v;
+    }
+    if (threadIdx.x == 0) {
+      distance[s] = 0.f;
+      has_state[s] = 1;
+    }
+    return;
+  }
+  // compute_distance re-normalises both pdfs (pdf_compare.py:47-48)
+  double a1 = 0.0, a2 = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) {
+    a1 += (double)__fdiv_rn(c[i], s_cur);
+    a2 += (double)st[i];
+  }
+  const float s1 = (float)block_sum_256(a1, red);
+  const float s2 = (float)block_sum_256(a2, red);
+  double dd = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) {
+    const float p1 = __fdiv_rn(__fdiv_rn(c[i], s_cur), s1);
+    const float p2 = __fdiv_rn(st[i], s2);
+    const float df = __fsub_rn(p1, p2);
+    dd += (double)__fmul_rn(df, df);
+  }
+  const float d = sqrtf((float)block_sum_256(dd, red));
+  float w = expf(__fmul_rn(-alpha, d));
+  w = fminf(fmaxf(w, 0.f), 1.f);
+  const float wn = __fmul_rn(w, n_coef);
+  const float w1 = __fsub_rn(1.f, w);
+  double au = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) {
+    const float u = __fadd_rn(__fmul_rn(wn, __fdiv_rn(c[i], s_cur)), __fmul_rn(w1, st[i]));
+    o[i] = u;  // unnormalised, same thread re-reads it below
+    au += (double)u;
+  }
+  const float su = (float)block_sum_256(au, red);
+  for (int i = threadIdx.x; i < n; i += 256) {
+    const float u = __fdiv_rn(o[i], su);
+    o[i] = u;
+    st[i] = u;
+  }
+  if (threadIdx.x == 0) distance[s] = d;
+}
+
+// Quaternion sign continuity (inference.py:136-144, 173-180): one thread per stream.
+__global__ void quat_continuity_kernel(float* __restrict__ quat, float* __restrict__ prev, int* __restrict__ has_prev, int S) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  float4 q = reinterpret_cast<float4*>(quat)[s];
+  if (!has_prev[s]) {
+    reinterpret_cast<float4*>(prev)[s] = q;
+    has_prev[s] = 1;
+    return;
+  }
+  const float4 p = reinterpret_cast<float4*>(prev)[s];
+  float dot = __fmul_rn(p.x, q.x);
+  dot = __fadd_rn(dot, __fmul_rn(p.y, q.y));
+  dot = __fadd_rn(dot, __fmul_rn(p.z, q.z));
+  dot = __fadd_rn(dot, __fmul_rn(p.w, q.w));
+  if (dot < 0.f) {
+    q = make_float4(-q.x, -q.y, -q.z, -q.w);
+    reinterpret_cast<float4*>(quat)[s] = q;
+  }
+  if (fabsf(dot) > 0.5f) reinterpret_cast<float4*>(prev)[s] = q;
+}
+
+}  // namespace spef

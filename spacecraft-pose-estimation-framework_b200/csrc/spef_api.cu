@@ -1,0 +1,1007 @@
+// libspef_b200.so -- C ABI (include/spef_b200.h): context, weight packer (BN fold), layer plan, launches.
+// The network topology follows src/modeling/backbone/mobilenet_v2.py:232-271 and
+// src/modeling/common/pytorch_layers.py:65-98 of the reference; state_dict keys follow SURVEY Appendix B.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <cmath>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/spef_b200.h"
+#include "common.cuh"
+#include "gemm_tcgen05.cuh"
+#include "kernels_conv.cuh"
+#include "kernels_post.cuh"
+
+using namespace spef;
+
+namespace {
+
+enum LayerKind { K_STEM = 0, K_PW = 1, K_DW = 2, K_POOL = 3, K_HEAD = 4 };
+enum BufId { BUF_IMG = -1, BUF_P = 0, BUF_Q = 1, BUF_H1 = 2, BUF_H2 = 3, BUF_POOL = 4, BUF_HEAD = 5 };
+
+struct HostTensor {
+  std::vector<int64_t> shape;
+  std::vector<float> data;
+};
+
+struct Layer {
+  int kind = 0;
+  std::string prefix;  // state_dict prefix of the ConvBnAct ("features.features.3.conv.1"), empty for pool/head
+  int cin = 0, cout = 0, hin = 0, win = 0, hout = 0, wout = 0, stride = 1, relu = 0;
+  int residual = 0;    // project conv of a residual block: D += block input
+  int src = 0, dst = 0, res_buf = -1;
+  float* w_f32 = nullptr;   // stem [27][32] | dw [9][C] | pw/head Wt [K][Npad] (SIMT operand)
+  bf16* w_bf16 = nullptr;   // pw/head [Npad][K] (tcgen05 operand, PyTorch layout)
+  float* bias = nullptr;    // zero padded
+  int n_pad = 0;            // head: n_ori + n_pos rounded up to 8; else cout
+  // tcgen05 plan
+  int block_n = 0, stages = 0;
+  size_t smem = 0;
+  CUtensorMap tmA, tmW, tmD;
+  bool tmW_ready = false;
+};
+
+const double kBnEps = 1e-5;  // torch.nn.BatchNorm2d default (pytorch_layers.py:55-56)
+
+}  // namespace
+
+struct spef_ctx {
+  spef_config cfg;
+  std::string err;
+  std::map<std::string, HostTensor> host_tensors;
+  std::vector<Layer> layers;
+  bool finalized = false;
+  int num_sms = 148;
+  size_t smem_optin = 0;
+  tc::EncodeTiledFn encode = nullptr;
+  size_t esz = 2;
+  // activations
+  void* act[4] = {nullptr, nullptr, nullptr, nullptr};
+  size_t act_elems[4] = {0, 0, 0, 0};
+  void* pooled = nullptr;      // [max_batch, 1280] activation type
+  float* head_out = nullptr;   // [max_batch, n_pad] f32
+  int head_pad = 0;
+  int plan_batch = -1;
+  // tables
+  float4* ori_tab = nullptr;
+  int ori_n = 0;
+  float4* pos_tab = nullptr;
+  int pos_n = 0;
+  // evaluation accumulators
+  double* eval_sums = nullptr;  // [8]
+  // workspaces for the *_host entry points and fused predict
+  float* ws_images = nullptr;
+  float* ws_quat = nullptr;     // [max_batch,4]
+  float* ws_pos = nullptr;      // [max_batch,3]
+  float* ws_qt = nullptr;       // [max_batch,4]
+  float* ws_tt = nullptr;       // [max_batch,3]
+  float* ws_soft = nullptr;     // [max_batch, max(n_ori,n_pos)] generic pdf/logit staging (lazily grown)
+  size_t ws_soft_elems = 0;
+  float* ws_soft2 = nullptr;
+  size_t ws_soft2_elems = 0;
+  float* ws_hinv = nullptr;
+  float* ws_per_image = nullptr;  // [max_batch,2]
+  int32_t* ws_argmax = nullptr;
+  uint32_t* ws_flags = nullptr;
+  double* ws_sums = nullptr;      // [8]
+  // temporal state
+  int t_streams = 0;
+  float* t_ori_state = nullptr;
+  float* t_pos_state = nullptr;
+  int* t_has = nullptr;          // [4][S]: ori filter, pos filter, prev still, prev video
+  float* t_prev_still = nullptr; // [S,4]
+  float* t_prev_video = nullptr;
+  float* t_ws[8] = {nullptr};    // scratch outputs when the caller passes NULL
+  // bookkeeping
+  int64_t launches = 0;
+  std::vector<cudaEvent_t> events;
+};
+
+static std::string g_create_err;
+
+static int fail(spef_ctx* c, int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf; else g_create_err = buf;
+  return code;
+}
+
+#define CK(call)                                                                                        \
+  do {                                                                                                  \
+    cudaError_t e_ = (call);                                                                            \
+    if (e_ != cudaSuccess) return fail(ctx, SPEF_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+#define CK_LAUNCH(name)                                                                                 \
+  do {                                                                                                  \
+    cudaError_t e_ = cudaGetLastError();                                                                \
+    if (e_ != cudaSuccess) return fail(ctx, SPEF_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(e_)); \
+    ctx->launches++;                                                                                    \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------------
+// topology
+// ------------------------------------------------------------------------------------------------------
+static void build_layers(spef_ctx* ctx) {
+  const int settings[7][4] = {{1, 16, 1, 1}, {6, 24, 2, 2}, {6, 32, 3, 2}, {6, 64, 4, 2}, {6, 96, 3, 1}, {6, 160, 3, 2}, {6, 320, 1, 1}};
+  std::vector<Layer>& L = ctx->layers;
+  L.clear();
+  int H = ctx->cfg.img_h, W = ctx->cfg.img_w;
+  auto down = [](int x) { return (x + 2 - 3) / 2 + 1; };
+  {
+    Layer s;
+    s.kind = K_STEM; s.prefix = "features.features.0"; s.cin = 3; s.cout = 32; s.hin = H; s.win = W;
+    s.hout = down(H); s.wout = down(W); s.stride = 2; s.relu = 1; s.src = BUF_IMG; s.dst = BUF_P;
+    L.push_back(s);
+    H = s.hout; W = s.wout;
+  }
+  int cur = BUF_P, cin = 32, idx = 1;
+  for (int g = 0; g < 7; ++g) {
+    const int t = settings[g][0], c = settings[g][1], n = settings[g][2], s = settings[g][3];
+    for (int i = 0; i < n; ++i, ++idx) {
+      const int stride = (i == 0) ? s : 1;
+      const int hidden = cin * t;
+      const bool res = (stride == 1 && cin == c);
+      char pre[64];
+      int j = 0, src = cur;
+      if (t != 1) {
+        Layer e;
+        snprintf(pre, sizeof(pre), "features.features.%d.conv.%d", idx, j++);
+        e.kind = K_PW; e.prefix = pre; e.cin = cin; e.cout = hidden; e.hin = e.hout = H; e.win = e.wout = W;
+        e.relu = 1; e.src = src; e.dst = BUF_H1;
+        L.push_back(e);
+        src = BUF_H1;
+      }
+      Layer d;
+      snprintf(pre, sizeof(pre), "features.features.%d.conv.%d", idx, j++);
+      d.kind = K_DW; d.prefix = pre; d.cin = d.cout = hidden; d.hin = H; d.win = W; d.stride = stride;
+      d.hout = (stride == 2) ? down(H) : H; d.wout = (stride == 2) ? down(W) : W; d.relu = 1; d.src = src; d.dst = BUF_H2;
+      L.push_back(d);
+      H = d.hout; W = d.wout;
+      Layer p;
+      snprintf(pre, sizeof(pre), "features.features.%d.conv.%d", idx, j++);
+      p.kind = K_PW; p.prefix = pre; p.cin = hidden; p.cout = c; p.hin = p.hout = H; p.win = p.wout = W; p.relu = 0;
+      p.residual = res ? 1 : 0; p.src = BUF_H2; p.dst = (cur == BUF_P) ? BUF_Q : BUF_P; p.res_buf = res ? cur : -1;
+      L.push_back(p);
+      cur = p.dst;
+      cin = c;
+    }
+  }
+  {
+    Layer l;
+    l.kind = K_PW; l.prefix = "features.features.18"; l.cin = cin; l.cout = 1280; l.hin = l.hout = H; l.win = l.wout = W;
+    l.relu = 1; l.src = cur; l.dst = BUF_H1;
+    L.push_back(l);
+  }
+  {
+    Layer pl;
+    pl.kind = K_POOL; pl.cin = pl.cout = 1280; pl.hin = H; pl.win = W; pl.hout = pl.wout = 1; pl.src = BUF_H1; pl.dst = BUF_POOL;
+    L.push_back(pl);
+  }
+  {
+    Layer h;
+    h.kind = K_HEAD; h.cin = 1280; h.cout = ctx->cfg.n_ori + ctx->cfg.n_pos; h.hin = h.win = h.hout = h.wout = 1;
+    h.src = BUF_POOL; h.dst = BUF_HEAD;
+    L.push_back(h);
+  }
+  for (Layer& l : L) l.n_pad = (l.kind == K_HEAD) ? ((l.cout + 7) / 8) * 8 : l.cout;
+}
+
+static void* buf_ptr(spef_ctx* ctx, int id) {
+  if (id >= 0 && id < 4) return ctx->act[id];
+  if (id == BUF_POOL) return ctx->pooled;
+  if (id == BUF_HEAD) return ctx->head_out;
+  return nullptr;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// lifecycle
+// ------------------------------------------------------------------------------------------------------
+extern "C" int spef_abi_version(void) { return SPEF_ABI_VERSION; }
+
+extern "C" const char* spef_last_error(const spef_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+extern "C" int spef_create(spef_ctx** out, const spef_config* cfg) {
+  spef_ctx* ctx = nullptr;  // for CK(): errors go to g_create_err until the ctx exists
+  if (!out || !cfg) return fail(nullptr, SPEF_ERR_INVALID, "spef_create: null argument");
+  if (cfg->struct_size != (int32_t)sizeof(spef_config)) return fail(nullptr, SPEF_ERR_INVALID, "spef_create: struct_size %d != %d", cfg->struct_size, (int)sizeof(spef_config));
+  if (cfg->img_h < 32 || cfg->img_w < 32 || cfg->n_ori < 1 || cfg->n_pos < 1 || cfg->max_batch < 1)
+    return fail(nullptr, SPEF_ERR_INVALID, "spef_create: bad geometry (img %dx%d, n_ori %d, n_pos %d, max_batch %d)", cfg->img_h, cfg->img_w, cfg->n_ori, cfg->n_pos, cfg->max_batch);
+  if (cfg->precision != SPEF_FP32 && cfg->precision != SPEF_BF16) return fail(nullptr, SPEF_ERR_INVALID, "spef_create: precision must be SPEF_FP32 or SPEF_BF16");
+  if (!cfg->pos_classification && cfg->n_pos != 3) return fail(nullptr, SPEF_ERR_INVALID, "spef_create: regression position head must have n_pos = 3");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(nullptr, SPEF_ERR_CUDA, "spef_create: no CUDA device (%s); libspef_b200 has no CPU fallback", cudaGetErrorString(e));
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, SPEF_ERR_INVALID, "spef_create: device %d out of range (%d devices)", cfg->device, ndev);
+  CK(cudaSetDevice(cfg->device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major != 10) return fail(nullptr, SPEF_ERR_UNSUPPORTED, "spef_create: device is sm_%d%d; this library is built for sm_100a (B200) only", prop.major, prop.minor);
+
+  ctx = new spef_ctx();
+  ctx->cfg = *cfg;
+  ctx->num_sms = prop.multiProcessorCount;
+  ctx->smem_optin = prop.sharedMemPerBlockOptin;
+  ctx->esz = (cfg->precision == SPEF_BF16) ? 2 : 4;
+  build_layers(ctx);
+
+  // cuTensorMapEncodeTiled through the runtime (no link-time dependency on libcuda)
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+    delete ctx;
+    return fail(nullptr, SPEF_ERR_CUDA, "spef_create: cuTensorMapEncodeTiled not available from the driver");
+  }
+  ctx->encode = (tc::EncodeTiledFn)fn;
+
+  // activation buffers (elements per image): P/Q = block in/out, H1 = expand out / last conv out, H2 = depthwise out
+  size_t need[4] = {0, 0, 0, 0};
+  for (const Layer& l : ctx->layers) {
+    if (l.dst >= 0 && l.dst < 4) {
+      size_t n = (size_t)l.hout * l.wout * l.cout;
+      if (n > need[l.dst]) need[l.dst] = n;
+    }
+  }
+  const size_t B = (size_t)cfg->max_batch;
+  auto dalloc = [&](void** p, size_t bytes) -> bool { return cudaMalloc(p, bytes ? bytes : 16) == cudaSuccess; };
+  bool ok = true;
+  for (int i = 0; i < 4; ++i) {
+    ctx->act_elems[i] = need[i] * B;
+    ok = ok && dalloc(&ctx->act[i], ctx->act_elems[i] * ctx->esz);
+  }
+  ctx->head_pad = ctx->layers.back().n_pad;
+  ok = ok && dalloc(&ctx->pooled, B * 1280 * ctx->esz);
+  ok = ok && dalloc((void**)&ctx->head_out, B * ctx->head_pad * sizeof(float));
+  ok = ok && dalloc((void**)&ctx->eval_sums, 8 * sizeof(double));
+  ok = ok && dalloc((void**)&ctx->ws_quat, B * 4 * sizeof(float));
+  ok = ok && dalloc((void**)&ctx->ws_pos, B * 3 * sizeof(float));
+  ok = ok && dalloc((void**)&ctx->ws_qt, B * 4 * sizeof(float));
+  ok = ok && dalloc((void**)&ctx->ws_tt, B * 3 * sizeof(float));
+  ok = ok && dalloc((void**)&ctx->ws_hinv, B * 16 * sizeof(float));
+  ok = ok && dalloc((void**)&ctx->ws_per_image, B * 2 * sizeof(float));
+  ok = ok && dalloc((void**)&ctx->ws_argmax, B * sizeof(int32_t));
+  ok = ok && dalloc((void**)&ctx->ws_flags, B * sizeof(uint32_t));
+  ok = ok && dalloc((void**)&ctx->ws_sums, 8 * sizeof(double));
+  if (!ok) {
+    std::string m = std::string("spef_create: cudaMalloc failed: ") + cudaGetErrorString(cudaGetLastError());
+    spef_destroy(ctx);
+    return fail(nullptr, SPEF_ERR_CUDA, "%s", m.c_str());
+  }
+  cudaMemset(ctx->eval_sums, 0, 8 * sizeof(double));
+  *out = ctx;
+  return SPEF_OK;
+}
+
+extern "C" void spef_destroy(spef_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->cfg.device);
+  for (Layer& l : ctx->layers) {
+    cudaFree(l.w_f32);
+    cudaFree(l.w_bf16);
+    cudaFree(l.bias);
+  }
+  for (int i = 0; i < 4; ++i) cudaFree(ctx->act[i]);
+  void* ptrs[] = {ctx->pooled, ctx->head_out, ctx->ori_tab, ctx->pos_tab, ctx->eval_sums, ctx->ws_images, ctx->ws_quat,
+                  ctx->ws_pos, ctx->ws_qt, ctx->ws_tt, ctx->ws_soft, ctx->ws_soft2, ctx->ws_hinv, ctx->ws_per_image,
+                  ctx->ws_argmax, ctx->ws_flags, ctx->ws_sums, ctx->t_ori_state, ctx->t_pos_state, ctx->t_has,
+                  ctx->t_prev_still, ctx->t_prev_video};
+  for (void* p : ptrs) cudaFree(p);
+  for (int i = 0; i < 8; ++i) cudaFree(ctx->t_ws[i]);
+  for (cudaEvent_t ev : ctx->events) cudaEventDestroy(ev);
+  delete ctx;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// weights
+// ------------------------------------------------------------------------------------------------------
+extern "C" int spef_load_tensor(spef_ctx* ctx, const char* key, const float* data, const int64_t* shape, int32_t ndim) {
+  if (!ctx) return SPEF_ERR_INVALID;
+  if (!key || !data || ndim < 0 || ndim > 4 || (ndim > 0 && !shape)) return fail(ctx, SPEF_ERR_INVALID, "spef_load_tensor: bad argument");
+  HostTensor t;
+  size_t n = 1;
+  for (int i = 0; i < ndim; ++i) {
+    if (shape[i] < 0) return fail(ctx, SPEF_ERR_INVALID, "spef_load_tensor(%s): negative dimension", key);
+    t.shape.push_back(shape[i]);
+    n *= (size_t)shape[i];
+  }
+  t.data.assign(data, data + n);
+  ctx->host_tensors[key] = std::move(t);
+  ctx->finalized = false;
+  return SPEF_OK;
+}
+
+static const HostTensor* find_tensor(spef_ctx* ctx, const std::string& key, std::initializer_list<int64_t> shape) {
+  auto it = ctx->host_tensors.find(key);
+  if (it == ctx->host_tensors.end()) {
+    fail(ctx, SPEF_ERR_STATE, "spef_finalize_weights: missing state_dict tensor '%s'", key.c_str());
+    return nullptr;
+  }
+  if (it->second.shape != std::vector<int64_t>(shape)) {
+    std::string got;
+    for (int64_t d : it->second.shape) got += std::to_string(d) + ",";
+    std::string want;
+    for (int64_t d : shape) want += std::to_string(d) + ",";
+    fail(ctx, SPEF_ERR_INVALID, "spef_finalize_weights: tensor '%s' has shape [%s], expected [%s]", key.c_str(), got.c_str(), want.c_str());
+    return nullptr;
+  }
+  return &it->second;
+}
+
+static inline float bf16_round_host(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+template <typename T>
+static bool upload(T** dst, const std::vector<T>& src) {
+  if (*dst) { cudaFree(*dst); *dst = nullptr; }
+  if (cudaMalloc((void**)dst, src.size() * sizeof(T)) != cudaSuccess) return false;
+  return cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice) == cudaSuccess;
+}
+
+extern "C" int spef_finalize_weights(spef_ctx* ctx) {
+  if (!ctx) return SPEF_ERR_INVALID;
+  CK(cudaSetDevice(ctx->cfg.device));
+  const bool use_bf16 = ctx->cfg.precision == SPEF_BF16;
+  for (Layer& l : ctx->layers) {
+    if (l.kind == K_POOL) continue;
+    std::vector<float> wf, bias;
+    int N = l.cout, K = l.cin;
+    if (l.kind == K_HEAD) {
+      const int n_ori = ctx->cfg.n_ori, n_pos = ctx->cfg.n_pos;
+      const HostTensor* wo = find_tensor(ctx, "head.ori.1.weight", {n_ori, 1280});
+      const HostTensor* bo = wo ? find_tensor(ctx, "head.ori.1.bias", {n_ori}) : nullptr;
+      const HostTensor* wp = bo ? find_tensor(ctx, "head.pos.0.weight", {n_pos, 1280}) : nullptr;
+      const HostTensor* bp = wp ? find_tensor(ctx, "head.pos.0.bias", {n_pos}) : nullptr;
+      if (!bp) return ctx->err.find("missing") != std::string::npos ? SPEF_ERR_STATE : SPEF_ERR_INVALID;
+      wf.assign((size_t)l.n_pad * K, 0.f);
+      bias.assign(l.n_pad, 0.f);
+      memcpy(wf.data(), wo->data.data(), wo->data.size() * 4);
+      memcpy(wf.data() + (size_t)n_ori * K, wp->data.data(), wp->data.size() * 4);
+      memcpy(bias.data(), bo->data.data(), n_ori * 4);
+      memcpy(bias.data() + n_ori, bp->data.data(), n_pos * 4);
+    } else {
+      const int64_t kk = (l.kind == K_PW) ? 1 : 3;
+      const int64_t cin_w = (l.kind == K_DW) ? 1 : l.cin;
+      const HostTensor* w = find_tensor(ctx, l.prefix + ".0.weight", {l.cout, cin_w, kk, kk});
+      const HostTensor* g = w ? find_tensor(ctx, l.prefix + ".1.weight", {l.cout}) : nullptr;
+      const HostTensor* b = g ? find_tensor(ctx, l.prefix + ".1.bias", {l.cout}) : nullptr;
+      const HostTensor* m = b ? find_tensor(ctx, l.prefix + ".1.running_mean", {l.cout}) : nullptr;
+      const HostTensor* v = m ? find_tensor(ctx, l.prefix + ".1.running_var", {l.cout}) : nullptr;
+      if (!v) return ctx->err.find("missing") != std::string::npos ? SPEF_ERR_STATE : SPEF_ERR_INVALID;
+      const size_t per = (size_t)cin_w * kk * kk;
+      wf.resize((size_t)l.cout * per);
+      bias.resize(l.cout);
+      for (int co = 0; co < l.cout; ++co) {  // BN fold in double
+        const double s = (double)g->data[co] / std::sqrt((double)v->data[co] + kBnEps);
+        for (size_t i = 0; i < per; ++i) wf[co * per + i] = (float)((double)w->data[co * per + i] * s);
+        bias[co] = (float)((double)b->data[co] - (double)m->data[co] * s);
+      }
+    }
+    std::vector<float> packed;
+    if (l.kind == K_STEM) {  // [32,3,3,3] -> [27][32]
+      packed.resize(27 * 32);
+      for (int co = 0; co < 32; ++co)
+        for (int k = 0; k < 27; ++k) packed[k * 32 + co] = wf[co * 27 + k];
+    } else if (l.kind == K_DW) {  // [C,1,3,3] -> [9][C]
+      packed.resize((size_t)9 * l.cout);
+      for (int c = 0; c < l.cout; ++c)
+        for (int k = 0; k < 9; ++k) packed[(size_t)k * l.cout + c] = wf[(size_t)c * 9 + k];
+    } else {  // pw / head: [Npad][K]; SIMT operand is the transpose [K][Npad]
+      const int Np = l.n_pad;
+      if (use_bf16) {
+        std::vector<bf16> wb((size_t)Np * K);
+        for (size_t i = 0; i < wb.size(); ++i) {
+          wb[i] = __float2bfloat16_rn(wf[i]);
+          wf[i] = __bfloat162float(wb[i]);  // SIMT cross-check sees exactly the tensor-core operand
+        }
+        if (!upload(&l.w_bf16, wb)) return fail(ctx, SPEF_ERR_CUDA, "spef_finalize_weights: upload failed");
+        l.tmW_ready = false;
+      }
+      packed.resize((size_t)K * Np);
+      for (int n = 0; n < Np; ++n)
+        for (int k = 0; k < K; ++k) packed[(size_t)k * Np + n] = wf[(size_t)n * K + k];
+      (void)N;
+    }
+    bias.resize(tc::bias_floats(l.n_pad), 0.f);
+    if (!upload(&l.w_f32, packed) || !upload(&l.bias, bias)) return fail(ctx, SPEF_ERR_CUDA, "spef_finalize_weights: upload failed");
+    if (l.kind == K_PW || l.kind == K_HEAD) {
+      l.block_n = tc::pick_block_n(l.n_pad);
+      l.stages = tc::pick_stages(l.block_n, l.n_pad, ctx->smem_optin);
+      l.smem = tc::smem_bytes(l.block_n, l.stages, l.n_pad);
+    }
+  }
+  if (use_bf16) {
+    CK(cudaFuncSetAttribute(tc::pw_gemm_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
+    CK(cudaFuncSetAttribute(tc::pw_gemm_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
+  }
+  ctx->host_tensors.clear();
+  ctx->plan_batch = -1;
+  ctx->finalized = true;
+  return SPEF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// histograms
+// ------------------------------------------------------------------------------------------------------
+extern "C" int spef_set_ori_histogram(spef_ctx* ctx, const double* q, int32_t n) {
+  if (!ctx) return SPEF_ERR_INVALID;
+  if (!q || n < 1) return fail(ctx, SPEF_ERR_INVALID, "spef_set_ori_histogram: bad argument");
+  CK(cudaSetDevice(ctx->cfg.device));
+  std::vector<float4> t(n);
+  for (int i = 0; i < n; ++i) t[i] = make_float4((float)q[i * 4], (float)q[i * 4 + 1], (float)q[i * 4 + 2], (float)q[i * 4 + 3]);
+  if (!upload(&ctx->ori_tab, t)) return fail(ctx, SPEF_ERR_CUDA, "spef_set_ori_histogram: upload failed");
+  ctx->ori_n = n;
+  return SPEF_OK;
+}
+
+extern "C" int spef_set_pos_histogram(spef_ctx* ctx, const double* x, int32_t n) {
+  if (!ctx) return SPEF_ERR_INVALID;
+  if (!x || n < 1) return fail(ctx, SPEF_ERR_INVALID, "spef_set_pos_histogram: bad argument");
+  CK(cudaSetDevice(ctx->cfg.device));
+  std::vector<float4> t(n);
+  for (int i = 0; i < n; ++i) t[i] = make_float4((float)x[i * 3], (float)x[i * 3 + 1], (float)x[i * 3 + 2], 0.f);
+  if (!upload(&ctx->pos_tab, t)) return fail(ctx, SPEF_ERR_CUDA, "spef_set_pos_histogram: upload failed");
+  ctx->pos_n = n;
+  return SPEF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// layer launches
+// ------------------------------------------------------------------------------------------------------
+template <typename T>
+static int launch_cuda_core_layer(spef_ctx* ctx, const Layer& l, const void* in, const void* res, void* out, int B, cudaStream_t st) {
+  if (l.kind == K_STEM) {
+    const long long total = (long long)B * l.hout * l.wout * 4;
+    stem_conv3x3s2_kernel<T><<<(unsigned)cdivll(total, 256), 256, 0, st>>>((const float*)in, l.w_f32, l.bias, (T*)out, B, l.hin, l.win, l.hout, l.wout);
+    CK_LAUNCH("stem_conv3x3s2_kernel");
+  } else if (l.kind == K_DW) {
+    const int CG = l.cin / 8;
+    if (l.stride == 1) {
+      const long long total = (long long)B * l.hout * cdiv(l.wout, 4) * CG;
+      dwconv3x3_kernel<T, 1, 4><<<(unsigned)cdivll(total, 256), 256, 0, st>>>((const T*)in, l.w_f32, l.bias, (T*)out, B, l.hin, l.win, l.cin, l.hout, l.wout, l.relu);
+    } else {
+      const long long total = (long long)B * l.hout * cdiv(l.wout, 2) * CG;
+      dwconv3x3_kernel<T, 2, 2><<<(unsigned)cdivll(total, 256), 256, 0, st>>>((const T*)in, l.w_f32, l.bias, (T*)out, B, l.hin, l.win, l.cin, l.hout, l.wout, l.relu);
+    }
+    CK_LAUNCH("dwconv3x3_kernel");
+  } else if (l.kind == K_POOL) {
+    const int total = B * (l.cin / 8);
+    global_mean_kernel<T><<<cdiv(total, 256), 256, 0, st>>>((const T*)in, (T*)out, B, l.hin * l.win, l.cin);
+    CK_LAUNCH("global_mean_kernel");
+  } else {  // K_PW / K_HEAD on CUDA cores
+    const int M = B * l.hout * l.wout, N = l.n_pad, K = l.cin;
+    dim3 grid(cdiv(M, 64), cdiv(N, 64));
+    if (l.kind == K_HEAD) {
+      pw_gemm_simt_kernel<T, float><<<grid, 256, 0, st>>>((const T*)in, l.w_f32, l.bias, nullptr, (float*)out, M, N, K, N, 0);
+    } else {
+      pw_gemm_simt_kernel<T, T><<<grid, 256, 0, st>>>((const T*)in, l.w_f32, l.bias, (const T*)res, (T*)out, M, N, K, N, l.relu);
+    }
+    CK_LAUNCH("pw_gemm_simt_kernel");
+  }
+  return SPEF_OK;
+}
+
+static int launch_tcgen05_layer(spef_ctx* ctx, Layer& l, const void* in, const void* res, void* out, int B, cudaStream_t st, bool cached_maps) {
+  const int M = B * l.hout * l.wout, N = l.n_pad, K = l.cin;
+  const bool f32out = (l.kind == K_HEAD);
+  if (!l.tmW_ready) {
+    if (!tc::make_tmap_2d(ctx->encode, &l.tmW, l.w_bf16, false, N, K, K, l.block_n)) return fail(ctx, SPEF_ERR_CUDA, "cuTensorMapEncodeTiled(W) failed for %s", l.prefix.c_str());
+    l.tmW_ready = true;
+  }
+  CUtensorMap tA_local, tD_local;
+  CUtensorMap* tA = cached_maps ? &l.tmA : &tA_local;
+  CUtensorMap* tD = cached_maps ? &l.tmD : &tD_local;
+  if (!cached_maps || ctx->plan_batch != B) {
+    if (!tc::make_tmap_2d(ctx->encode, tA, in, false, M, K, K, tc::BLOCK_M)) return fail(ctx, SPEF_ERR_CUDA, "cuTensorMapEncodeTiled(A) failed for %s (M=%d K=%d)", l.prefix.c_str(), M, K);
+    if (!tc::make_tmap_2d(ctx->encode, tD, out, f32out, M, N, N, tc::BLOCK_M)) return fail(ctx, SPEF_ERR_CUDA, "cuTensorMapEncodeTiled(D) failed for %s (M=%d N=%d)", l.prefix.c_str(), M, N);
+  }
+  tc::GemmParams p;
+  p.bias = l.bias; p.residual = (const bf16*)res; p.M = M; p.N = N; p.K = K; p.block_n = l.block_n; p.num_stages = l.stages; p.relu = l.relu;
+  const int tiles = cdiv(M, tc::BLOCK_M) * cdiv(N, l.block_n);
+  const int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
+  if (f32out) tc::pw_gemm_tcgen05_kernel<true><<<grid, tc::NUM_THREADS, l.smem, st>>>(*tA, l.tmW, *tD, p);
+  else tc::pw_gemm_tcgen05_kernel<false><<<grid, tc::NUM_THREADS, l.smem, st>>>(*tA, l.tmW, *tD, p);
+  CK_LAUNCH("pw_gemm_tcgen05_kernel");
+  return SPEF_OK;
+}
+
+static int run_layer(spef_ctx* ctx, Layer& l, const void* in, const void* res, void* out, int B, cudaStream_t st, bool cached_maps) {
+  const bool use_bf16 = ctx->cfg.precision == SPEF_BF16;
+  if (use_bf16 && (l.kind == K_PW || l.kind == K_HEAD) && ctx->cfg.pw_impl == 0) return launch_tcgen05_layer(ctx, l, in, res, out, B, st, cached_maps);
+  if (use_bf16) return launch_cuda_core_layer<bf16>(ctx, l, in, res, out, B, st);
+  return launch_cuda_core_layer<float>(ctx, l, in, res, out, B, st);
+}
+
+static int check_ready(spef_ctx* ctx, int B, const char* who) {
+  if (!ctx) return SPEF_ERR_INVALID;
+  if (!ctx->finalized) return fail(ctx, SPEF_ERR_STATE, "%s: weights not finalised (spef_load_tensor + spef_finalize_weights first)", who);
+  if (B < 1 || B > ctx->cfg.max_batch) return fail(ctx, SPEF_ERR_INVALID, "%s: batch %d outside [1, max_batch=%d]", who, B, ctx->cfg.max_batch);
+  return SPEF_OK;
+}
+
+static int forward_internal(spef_ctx* ctx, const float* images, int B, cudaStream_t st, float* layer_ms) {
+  cudaEvent_t* ev = nullptr;
+  const int nl = (int)ctx->layers.size();
+  if (layer_ms) {
+    while ((int)ctx->events.size() < nl + 1) {
+      cudaEvent_t e;
+      CK(cudaEventCreate(&e));
+      ctx->events.push_back(e);
+    }
+    ev = ctx->events.data();
+    CK(cudaEventRecord(ev[0], st));
+  }
+  for (int i = 0; i < nl; ++i) {
+    Layer& l = ctx->layers[i];
+    const void* in = (l.src == BUF_IMG) ? (const void*)images : buf_ptr(ctx, l.src);
+    const void* res = (l.res_buf >= 0) ? buf_ptr(ctx, l.res_buf) : nullptr;
+    int rc = run_layer(ctx, l, in, res, buf_ptr(ctx, l.dst), B, st, true);
+    if (rc) return rc;
+    if (ev) CK(cudaEventRecord(ev[i + 1], st));
+  }
+  ctx->plan_batch = B;
+  if (layer_ms) {
+    CK(cudaEventSynchronize(ev[nl]));
+    for (int i = 0; i < nl; ++i) CK(cudaEventElapsedTime(&layer_ms[i], ev[i], ev[i + 1]));
+  }
+  return SPEF_OK;
+}
+
+static int copy_head_out(spef_ctx* ctx, int B, float* ori_out, float* pos_out, cudaStream_t st) {
+  const size_t pitch = (size_t)ctx->head_pad * sizeof(float);
+  if (ori_out) CK(cudaMemcpy2DAsync(ori_out, (size_t)ctx->cfg.n_ori * 4, ctx->head_out, pitch, (size_t)ctx->cfg.n_ori * 4, B, cudaMemcpyDeviceToDevice, st));
+  if (pos_out) CK(cudaMemcpy2DAsync(pos_out, (size_t)ctx->cfg.n_pos * 4, ctx->head_out + ctx->cfg.n_ori, pitch, (size_t)ctx->cfg.n_pos * 4, B, cudaMemcpyDeviceToDevice, st));
+  return SPEF_OK;
+}
+
+extern "C" int spef_forward(spef_ctx* ctx, const float* images_dev, int32_t B, float* ori_out, float* pos_out, void* stream) {
+  int rc = check_ready(ctx, B, "spef_forward");
+  if (rc) return rc;
+  if (!images_dev) return fail(ctx, SPEF_ERR_INVALID, "spef_forward: images_dev is NULL");
+  CK(cudaSetDevice(ctx->cfg.device));
+  rc = forward_internal(ctx, images_dev, B, (cudaStream_t)stream, nullptr);
+  if (rc) return rc;
+  return copy_head_out(ctx, B, ori_out, pos_out, (cudaStream_t)stream);
+}
+
+extern "C" int spef_forward_timed(spef_ctx* ctx, const float* images_dev, int32_t B, float* ori_out, float* pos_out, float* layer_ms, void* stream) {
+  int rc = check_ready(ctx, B, "spef_forward_timed");
+  if (rc) return rc;
+  if (!images_dev || !layer_ms) return fail(ctx, SPEF_ERR_INVALID, "spef_forward_timed: NULL argument");
+  CK(cudaSetDevice(ctx->cfg.device));
+  rc = forward_internal(ctx, images_dev, B, (cudaStream_t)stream, layer_ms);
+  if (rc) return rc;
+  return copy_head_out(ctx, B, ori_out, pos_out, (cudaStream_t)stream);
+}
+
+extern "C" int spef_num_layers(const spef_ctx* ctx) { return ctx ? (int)ctx->layers.size() : 0; }
+
+extern "C" int spef_layer_info(const spef_ctx* ctx, int32_t i, int32_t* kind, int32_t* cin, int32_t* cout, int32_t* hin, int32_t* win,
+                               int32_t* hout, int32_t* wout, int32_t* stride, int32_t* relu, int32_t* has_res) {
+  if (!ctx || i < 0 || i >= (int)ctx->layers.size()) return SPEF_ERR_INVALID;
+  const Layer& l = ctx->layers[i];
+  if (kind) *kind = l.kind;
+  if (cin) *cin = l.cin;
+  if (cout) *cout = (l.kind == K_HEAD) ? l.n_pad : l.cout;
+  if (hin) *hin = l.hin;
+  if (win) *win = l.win;
+  if (hout) *hout = l.hout;
+  if (wout) *wout = l.wout;
+  if (stride) *stride = l.stride;
+  if (relu) *relu = l.relu;
+  if (has_res) *has_res = l.residual;
+  return SPEF_OK;
+}
+
+extern "C" int spef_layer_forward(spef_ctx* ctx, int32_t i, const void* in, const void* res, void* out, int32_t B, void* stream) {
+  int rc = check_ready(ctx, B, "spef_layer_forward");
+  if (rc) return rc;
+  if (i < 0 || i >= (int)ctx->layers.size() || !in || !out) return fail(ctx, SPEF_ERR_INVALID, "spef_layer_forward: bad argument");
+  CK(cudaSetDevice(ctx->cfg.device));
+  Layer& l = ctx->layers[i];
+  return run_layer(ctx, l, in, l.residual ? res : nullptr, out, B, (cudaStream_t)stream, false);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// post-processing
+// ------------------------------------------------------------------------------------------------------
+static int decode_ori_ld(spef_ctx* ctx, const float* in, int ld, int B, int n, int is_logits, float* soft, float* quat, float* hinv,
+                         int32_t* amax, uint32_t* flags, cudaStream_t st) {
+  if (!ctx->ori_tab) return fail(ctx, SPEF_ERR_STATE, "decode_ori: orientation histogram not set (spef_set_ori_histogram)");
+  if (n != ctx->ori_n) return fail(ctx, SPEF_ERR_INVALID, "decode_ori: n = %d but the histogram has %d bins", n, ctx->ori_n);
+  if (!in || !quat || B < 1) return fail(ctx, SPEF_ERR_INVALID, "decode_ori: bad argument");
+  decode_ori_kernel<<<cdiv(B, 4), 128, 0, st>>>(in, ld, B, n, is_logits, ctx->ori_tab, soft, quat, hinv, amax, flags);
+  CK_LAUNCH("decode_ori_kernel");
+  return SPEF_OK;
+}
+
+static int decode_pos_ld(spef_ctx* ctx, const float* in, int ld, int B, int n, int is_logits, float* soft, float* pos, uint32_t* flags, cudaStream_t st) {
+  if (!ctx->pos_tab) return fail(ctx, SPEF_ERR_STATE, "decode_pos: position histogram not set (spef_set_pos_histogram)");
+  if (n != ctx->pos_n) return fail(ctx, SPEF_ERR_INVALID, "decode_pos: n = %d but the histogram has %d bins", n, ctx->pos_n);
+  if (!in || !pos || B < 1) return fail(ctx, SPEF_ERR_INVALID, "decode_pos: bad argument");
+  decode_pos_kernel<<<cdiv(B, 4), 128, 0, st>>>(in, ld, B, n, is_logits, ctx->pos_tab, soft, pos, flags);
+  CK_LAUNCH("decode_pos_kernel");
+  return SPEF_OK;
+}
+
+extern "C" int spef_decode_ori(spef_ctx* ctx, const float* in, int32_t B, int32_t n, int32_t is_logits, float* soft, float* quat,
+                               float* hinv, int32_t* amax, uint32_t* flags, void* stream) {
+  if (!ctx) return SPEF_ERR_INVALID;
+  CK(cudaSetDevice(ctx->cfg.device));
+  return decode_ori_ld(ctx, in, n, B, n, is_logits, soft, quat, hinv, amax, flags, (cudaStream_t)stream);
+}
+
+extern "C" int spef_decode_pos(spef_ctx* ctx, const float* in, int32_t B, int32_t n, int32_t is_logits, float* soft, float* pos,
+                               uint32_t* flags, void* stream) {
+  if (!ctx) return SPEF_ERR_INVALID;
+  CK(cudaSetDevice(ctx->cfg.device));
+  return decode_pos_ld(ctx, in, n, B, n, is_logits, soft, pos, flags, (cudaStream_t)stream);
+}
+
+extern "C" int spef_score(spef_ctx* ctx, const float* qp, const float* tp, const float* qt, const float* tt, int32_t B, double* sums,
+                          float* per_image, void* stream) {
+  if (!ctx) return SPEF_ERR_INVALID;
+  if (!qp || !tp || !qt || !tt || !sums || B < 1) return fail(ctx, SPEF_ERR_INVALID, "spef_score: bad argument");
+  CK(cudaSetDevice(ctx->cfg.device));
+  int grid = cdiv(B, 256);
+  if (grid > 4 * ctx->num_sms) grid = 4 * ctx->num_sms;
+  score_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(qp, tp, qt, tt, B, sums, per_image);
+  CK_LAUNCH("score_kernel");
+  return SPEF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// fused predict / evaluation
+// ------------------------------------------------------------------------------------------------------
+static int predict_internal(spef_ctx* ctx, const float* images, int B, float* ori_soft, float* quat, float* pos_soft, float* pos,
+                            int32_t* amax, uint32_t* flags, cudaStream_t st) {
+  int rc = forward_internal(ctx, images, B, st, nullptr);
+  if (rc) return rc;
+  if (flags) CK(cudaMemsetAsync(flags, 0, (size_t)B * sizeof(uint32_t), st));
+  rc = decode_ori_ld(ctx, ctx->head_out, ctx->head_pad, B, ctx->cfg.n_ori, 1, ori_soft, quat, nullptr, amax, flags, st);
+  if (rc) return rc;
+  if (ctx->cfg.pos_classification) {
+    rc = decode_pos_ld(ctx, ctx->head_out + ctx->cfg.n_ori, ctx->head_pad, B, ctx->cfg.n_pos, 1, pos_soft, pos, flags, st);
+    if (rc) return rc;
+  } else {
+    if (pos_soft) return fail(ctx, SPEF_ERR_INVALID, "predict: pos_soft requested but the position head is a regression head");
+    rc = copy_head_out(ctx, B, nullptr, pos, st);
+    if (rc) return rc;
+  }
+  return SPEF_OK;
+}
+
+extern "C" int spef_predict(spef_ctx* ctx, const float* images_dev, int32_t B, float* ori_soft, float* quat, float* pos_soft, float* pos,
+                            int32_t* amax, uint32_t* flags, void* stream) {
+  int rc = check_ready(ctx, B, "spef_predict");
+  if (rc) return rc;
+  if (!images_dev || !quat || !pos) return fail(ctx, SPEF_ERR_INVALID, "spef_predict: NULL argument");
+  CK(cudaSetDevice(ctx->cfg.device));
+  return predict_internal(ctx, images_dev, B, ori_soft, quat, pos_soft, pos, amax, flags, (cudaStream_t)stream);
+}
+
+static int grow(spef_ctx* ctx, float** p, size_t* have, size_t need) {
+  if (*have >= need) return SPEF_OK;
+  if (*p) cudaFree(*p);
+  *p = nullptr;
+  *have = 0;
+  CK(cudaMalloc((void**)p, need * sizeof(float)));
+  *have = need;
+  return SPEF_OK;
+}
+
+static int ensure_ws_images(spef_ctx* ctx) {
+  if (ctx->ws_images) return SPEF_OK;
+  CK(cudaMalloc((void**)&ctx->ws_images, (size_t)ctx->cfg.max_batch * 3 * ctx->cfg.img_h * ctx->cfg.img_w * sizeof(float)));
+  return SPEF_OK;
+}
+
+extern "C" int spef_predict_host(spef_ctx* ctx, const float* images_host, int32_t B, float* ori_soft_h, float* quat_h, float* pos_soft_h,
+                                 float* pos_h, int32_t* amax_h, uint32_t* flags_h, void* stream) {
+  int rc = check_ready(ctx, B, "spef_predict_host");
+  if (rc) return rc;
+  if (!images_host || !quat_h || !pos_h) return fail(ctx, SPEF_ERR_INVALID, "spef_predict_host: NULL argument");
+  CK(cudaSetDevice(ctx->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if ((rc = ensure_ws_images(ctx))) return rc;
+  const size_t img_bytes = (size_t)B * 3 * ctx->cfg.img_h * ctx->cfg.img_w * sizeof(float);
+  CK(cudaMemcpyAsync(ctx->ws_images, images_host, img_bytes, cudaMemcpyHostToDevice, st));
+  float* soft_d = nullptr;
+  float* psoft_d = nullptr;
+  if (ori_soft_h) {
+    if ((rc = grow(ctx, &ctx->ws_soft, &ctx->ws_soft_elems, (size_t)ctx->cfg.max_batch * ctx->cfg.n_ori))) return rc;
+    soft_d = ctx->ws_soft;
+  }
+  if (pos_soft_h) {
+    if ((rc = grow(ctx, &ctx->ws_soft2, &ctx->ws_soft2_elems, (size_t)ctx->cfg.max_batch * ctx->cfg.n_pos))) return rc;
+    psoft_d = ctx->ws_soft2;
+  }
+  rc = predict_internal(ctx, ctx->ws_images, B, soft_d, ctx->ws_quat, psoft_d, ctx->ws_pos, amax_h ? ctx->ws_argmax : nullptr, ctx->ws_flags, st);
+  if (rc) return rc;
+  if (ori_soft_h) CK(cudaMemcpyAsync(ori_soft_h, soft_d, (size_t)B * ctx->cfg.n_ori * 4, cudaMemcpyDeviceToHost, st));
+  if (pos_soft_h) CK(cudaMemcpyAsync(pos_soft_h, psoft_d, (size_t)B * ctx->cfg.n_pos * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(quat_h, ctx->ws_quat, (size_t)B * 16, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(pos_h, ctx->ws_pos, (size_t)B * 12, cudaMemcpyDeviceToHost, st));
+  if (amax_h) CK(cudaMemcpyAsync(amax_h, ctx->ws_argmax, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+  if (flags_h) CK(cudaMemcpyAsync(flags_h, ctx->ws_flags, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return SPEF_OK;
+}
+
+extern "C" int spef_eval_reset(spef_ctx* ctx, void* stream) {
+  if (!ctx) return SPEF_ERR_INVALID;
+  CK(cudaSetDevice(ctx->cfg.device));
+  CK(cudaMemsetAsync(ctx->eval_sums, 0, 8 * sizeof(double), (cudaStream_t)stream));
+  return SPEF_OK;
+}
+
+extern "C" double* spef_eval_sums_dev(spef_ctx* ctx) { return ctx ? ctx->eval_sums : nullptr; }
+
+extern "C" int spef_eval_batch(spef_ctx* ctx, const float* images_dev, const float* qt, const float* tt, int32_t B, float* per_image, void* stream) {
+  int rc = check_ready(ctx, B, "spef_eval_batch");
+  if (rc) return rc;
+  if (!images_dev || !qt || !tt) return fail(ctx, SPEF_ERR_INVALID, "spef_eval_batch: NULL argument");
+  CK(cudaSetDevice(ctx->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = predict_internal(ctx, images_dev, B, nullptr, ctx->ws_quat, nullptr, ctx->ws_pos, nullptr, ctx->ws_flags, st);
+  if (rc) return rc;
+  return spef_score(ctx, ctx->ws_quat, ctx->ws_pos, qt, tt, B, ctx->eval_sums, per_image, stream);
+}
+
+extern "C" int spef_eval_batch_host(spef_ctx* ctx, const float* images_host, const float* qt_h, const float* tt_h, int32_t B,
+                                    float* per_image_h, void* stream) {
+  int rc = check_ready(ctx, B, "spef_eval_batch_host");
+  if (rc) return rc;
+  if (!images_host || !qt_h || !tt_h) return fail(ctx, SPEF_ERR_INVALID, "spef_eval_batch_host: NULL argument");
+  CK(cudaSetDevice(ctx->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if ((rc = ensure_ws_images(ctx))) return rc;
+  CK(cudaMemcpyAsync(ctx->ws_images, images_host, (size_t)B * 3 * ctx->cfg.img_h * ctx->cfg.img_w * sizeof(float), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->ws_qt, qt_h, (size_t)B * 16, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->ws_tt, tt_h, (size_t)B * 12, cudaMemcpyHostToDevice, st));
+  rc = spef_eval_batch(ctx, ctx->ws_images, ctx->ws_qt, ctx->ws_tt, B, per_image_h ? ctx->ws_per_image : nullptr, stream);
+  if (rc) return rc;
+  if (per_image_h) {
+    CK(cudaMemcpyAsync(per_image_h, ctx->ws_per_image, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+  }
+  return SPEF_OK;
+}
+
+extern "C" int spef_eval_read(spef_ctx* ctx, double* sums_host, void* stream) {
+  if (!ctx || !sums_host) return SPEF_ERR_INVALID;
+  CK(cudaSetDevice(ctx->cfg.device));
+  CK(cudaMemcpyAsync(sums_host, ctx->eval_sums, 8 * sizeof(double), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  CK(cudaStreamSynchronize((cudaStream_t)stream));
+  return SPEF_OK;
+}
+
+// ---- host-buffer post-processing -----------------------------------------------------------------------
+extern "C" int spef_decode_ori_host(spef_ctx* ctx, const float* in_h, int32_t B, int32_t n, int32_t is_logits, float* soft_h, float* quat_h,
+                                    float* hinv_h, int32_t* amax_h, uint32_t* flags_h, void* stream) {
+  if (!ctx) return SPEF_ERR_INVALID;
+  if (!in_h || !quat_h || B < 1 || n < 1) return fail(ctx, SPEF_ERR_INVALID, "spef_decode_ori_host: bad argument");
+  CK(cudaSetDevice(ctx->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+  const size_t elems = (size_t)B * n;
+  if ((rc = grow(ctx, &ctx->ws_soft, &ctx->ws_soft_elems, elems))) return rc;
+  if (soft_h && (rc = grow(ctx, &ctx->ws_soft2, &ctx->ws_soft2_elems, elems))) return rc;
+  float* quat_d; float* hinv_d = nullptr; int32_t* amax_d = nullptr; uint32_t* flags_d;
+  CK(cudaMallocAsync((void**)&quat_d, (size_t)B * 16, st));
+  CK(cudaMallocAsync((void**)&flags_d, (size_t)B * 4, st));
+  if (hinv_h) CK(cudaMallocAsync((void**)&hinv_d, (size_t)B * 64, st));
+  if (amax_h) CK(cudaMallocAsync((void**)&amax_d, (size_t)B * 4, st));
+  CK(cudaMemsetAsync(flags_d, 0, (size_t)B * 4, st));
+  CK(cudaMemcpyAsync(ctx->ws_soft, in_h, elems * 4, cudaMemcpyHostToDevice, st));
+  rc = decode_ori_ld(ctx, ctx->ws_soft, n, B, n, is_logits, soft_h ? ctx->ws_soft2 : nullptr, quat_d, hinv_d, amax_d, flags_d, st);
+  if (rc == SPEF_OK) {
+    if (soft_h) cudaMemcpyAsync(soft_h, ctx->ws_soft2, elems * 4, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(quat_h, quat_d, (size_t)B * 16, cudaMemcpyDeviceToHost, st);
+    if (hinv_h) cudaMemcpyAsync(hinv_h, hinv_d, (size_t)B * 64, cudaMemcpyDeviceToHost, st);
+    if (amax_h) cudaMemcpyAsync(amax_h, amax_d, (size_t)B * 4, cudaMemcpyDeviceToHost, st);
+    if (flags_h) cudaMemcpyAsync(flags_h, flags_d, (size_t)B * 4, cudaMemcpyDeviceToHost, st);
+  }
+  cudaFreeAsync(quat_d, st);
+  cudaFreeAsync(flags_d, st);
+  if (hinv_d) cudaFreeAsync(hinv_d, st);
+  if (amax_d) cudaFreeAsync(amax_d, st);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(st));
+  return SPEF_OK;
+}
+
+extern "C" int spef_decode_pos_host(spef_ctx* ctx, const float* in_h, int32_t B, int32_t n, int32_t is_logits, float* soft_h, float* pos_h,
+                                    uint32_t* flags_h, void* stream) {
+  if (!ctx) return SPEF_ERR_INVALID;
+  if (!in_h || !pos_h || B < 1 || n < 1) return fail(ctx, SPEF_ERR_INVALID, "spef_decode_pos_host: bad argument");
+  CK(cudaSetDevice(ctx->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+  const size_t elems = (size_t)B * n;
+  if ((rc = grow(ctx, &ctx->ws_soft, &ctx->ws_soft_elems, elems))) return rc;
+  if (soft_h && (rc = grow(ctx, &ctx->ws_soft2, &ctx->ws_soft2_elems, elems))) return rc;
+  float* pos_d; uint32_t* flags_d;
+  CK(cudaMallocAsync((void**)&pos_d, (size_t)B * 12, st));
+  CK(cudaMallocAsync((void**)&flags_d, (size_t)B * 4, st));
+  CK(cudaMemsetAsync(flags_d, 0, (size_t)B * 4, st));
+  CK(cudaMemcpyAsync(ctx->ws_soft, in_h, elems * 4, cudaMemcpyHostToDevice, st));
+  rc = decode_pos_ld(ctx, ctx->ws_soft, n, B, n, is_logits, soft_h ? ctx->ws_soft2 : nullptr, pos_d, flags_d, st);
+  if (rc == SPEF_OK) {
+    if (soft_h) cudaMemcpyAsync(soft_h, ctx->ws_soft2, elems * 4, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(pos_h, pos_d, (size_t)B * 12, cudaMemcpyDeviceToHost, st);
+    if (flags_h) cudaMemcpyAsync(flags_h, flags_d, (size_t)B * 4, cudaMemcpyDeviceToHost, st);
+  }
+  cudaFreeAsync(pos_d, st);
+  cudaFreeAsync(flags_d, st);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(st));
+  return SPEF_OK;
+}
+
+extern "C" int spef_score_host(spef_ctx* ctx, const float* qp_h, const float* tp_h, const float* qt_h, const float* tt_h, int32_t B,
+                               double* sums_h, float* per_image_h, void* stream) {
+  if (!ctx) return SPEF_ERR_INVALID;
+  if (!qp_h || !tp_h || !qt_h || !tt_h || !sums_h || B < 1) return fail(ctx, SPEF_ERR_INVALID, "spef_score_host: bad argument");
+  CK(cudaSetDevice(ctx->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  float* buf;  // qp | qt | tp | tt | per_image
+  const size_t nB = (size_t)B;
+  CK(cudaMallocAsync((void**)&buf, nB * (4 + 4 + 3 + 3 + 2) * sizeof(float), st));
+  float* qp = buf; float* qt = qp + nB * 4; float* tp = qt + nB * 4; float* tt = tp + nB * 3; float* pi = tt + nB * 3;
+  CK(cudaMemcpyAsync(qp, qp_h, nB * 16, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(qt, qt_h, nB * 16, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(tp, tp_h, nB * 12, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(tt, tt_h, nB * 12, cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(ctx->ws_sums, 0, 8 * sizeof(double), st));
+  int rc = spef_score(ctx, qp, tp, qt, tt, B, ctx->ws_sums, per_image_h ? pi : nullptr, stream);
+  if (rc == SPEF_OK) {
+    cudaMemcpyAsync(sums_h, ctx->ws_sums, 8 * sizeof(double), cudaMemcpyDeviceToHost, st);
+    if (per_image_h) cudaMemcpyAsync(per_image_h, pi, nB * 8, cudaMemcpyDeviceToHost, st);
+  }
+  cudaFreeAsync(buf, st);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(st));
+  return SPEF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// temporal
+// ------------------------------------------------------------------------------------------------------
+extern "C" int spef_temporal_reset(spef_ctx* ctx, int32_t S, void* stream) {
+  if (!ctx) return SPEF_ERR_INVALID;
+  if (S < 1 || S > ctx->cfg.max_batch) return fail(ctx, SPEF_ERR_INVALID, "spef_temporal_reset: n_streams %d outside [1, max_batch=%d]", S, ctx->cfg.max_batch);
+  if (!ctx->cfg.pos_classification) return fail(ctx, SPEF_ERR_UNSUPPORTED, "temporal filtering requires a classification position head (src/temporal/inference.py:160-161)");
+  CK(cudaSetDevice(ctx->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (S != ctx->t_streams) {
+    void** ptrs[] = {(void**)&ctx->t_ori_state, (void**)&ctx->t_pos_state, (void**)&ctx->t_has, (void**)&ctx->t_prev_still, (void**)&ctx->t_prev_video};
+    for (void** p : ptrs) { if (*p) cudaFree(*p); *p = nullptr; }
+    for (int i = 0; i < 8; ++i) { if (ctx->t_ws[i]) cudaFree(ctx->t_ws[i]); ctx->t_ws[i] = nullptr; }
+    const size_t no = ctx->cfg.n_ori, np = ctx->cfg.n_pos, s = S;
+    CK(cudaMalloc((void**)&ctx->t_ori_state, s * no * 4));
+    CK(cudaMalloc((void**)&ctx->t_pos_state, s * np * 4));
+    CK(cudaMalloc((void**)&ctx->t_has, s * 4 * sizeof(int)));
+    CK(cudaMalloc((void**)&ctx->t_prev_still, s * 16));
+    CK(cudaMalloc((void**)&ctx->t_prev_video, s * 16));
+    const size_t sz[8] = {s * no * 4, s * np * 4, s * 16, s * 12, s * no * 4, s * np * 4, s * 16, s * 12};
+    for (int i = 0; i < 8; ++i) CK(cudaMalloc((void**)&ctx->t_ws[i], sz[i]));
+    ctx->t_streams = S;
+  }
+  CK(cudaMemsetAsync(ctx->t_has, 0, (size_t)S * 4 * sizeof(int), st));
+  return SPEF_OK;
+}
+
+static int temporal_from_logits(spef_ctx* ctx, const float* ori_logits, int ld_o, const float* pos_logits, int ld_p, int S,
+                                int apply_filter, const spef_temporal_out* o, cudaStream_t st) {
+  if (S != ctx->t_streams) return fail(ctx, SPEF_ERR_STATE, "temporal step: n_streams %d != %d set by spef_temporal_reset", S, ctx->t_streams);
+  spef_temporal_out z;
+  memset(&z, 0, sizeof(z));
+  if (o) z = *o;
+  float* still_os = z.still_ori_soft ? z.still_ori_soft : ctx->t_ws[0];
+  float* still_ps = z.still_pos_soft ? z.still_pos_soft : ctx->t_ws[1];
+  float* still_q = z.still_quat ? z.still_quat : ctx->t_ws[2];
+  float* still_p = z.still_pos ? z.still_pos : ctx->t_ws[3];
+  float* vid_os = z.video_ori_soft ? z.video_ori_soft : ctx->t_ws[4];
+  float* vid_ps = z.video_pos_soft ? z.video_pos_soft : ctx->t_ws[5];
+  float* vid_q = z.video_quat ? z.video_quat : ctx->t_ws[6];
+  float* vid_p = z.video_pos ? z.video_pos : ctx->t_ws[7];
+  float* d_o = z.ori_distance ? z.ori_distance : (float*)ctx->ws_per_image;          // [S] scratch
+  float* d_p = z.pos_distance ? z.pos_distance : (float*)ctx->ws_per_image + S;
+  const int no = ctx->cfg.n_ori, np = ctx->cfg.n_pos;
+  int* has = ctx->t_has;
+  if (z.flags) CK(cudaMemsetAsync(z.flags, 0, (size_t)S * 4, st));
+  int rc;
+  // still pose: softmax + decode (inference.py:131-133 -> spe_torch.py:75-76)
+  if ((rc = decode_ori_ld(ctx, ori_logits, ld_o, S, no, 1, still_os, still_q, nullptr, nullptr, z.flags, st))) return rc;
+  if ((rc = decode_pos_ld(ctx, pos_logits, ld_p, S, np, 1, still_ps, still_p, z.flags, st))) return rc;
+  quat_continuity_kernel<<<cdiv(S, 128), 128, 0, st>>>(still_q, ctx->t_prev_still, has + 2 * S, S);  // inference.py:136-144
+  CK_LAUNCH("quat_continuity_kernel");
+  if (!apply_filter) return SPEF_OK;
+  // adaptive pdf filters (inference.py:38-39, 164-165)
+  temporal_filter_kernel<<<S, 256, 0, st>>>(still_os, no, ctx->t_ori_state, has, 0.8f, 16.49f, vid_os, d_o);
+  CK_LAUNCH("temporal_filter_kernel");
+  temporal_filter_kernel<<<S, 256, 0, st>>>(still_ps, np, ctx->t_pos_state, has + S, 0.5f, 48.64f, vid_ps, d_p);
+  CK_LAUNCH("temporal_filter_kernel");
+  // decode of the filtered pdfs (inference.py:167-168)
+  if ((rc = decode_ori_ld(ctx, vid_os, no, S, no, 0, nullptr, vid_q, nullptr, nullptr, z.flags, st))) return rc;
+  if ((rc = decode_pos_ld(ctx, vid_ps, np, S, np, 0, nullptr, vid_p, z.flags, st))) return rc;
+  quat_continuity_kernel<<<cdiv(S, 128), 128, 0, st>>>(vid_q, ctx->t_prev_video, has + 3 * S, S);  // inference.py:173-180
+  CK_LAUNCH("quat_continuity_kernel");
+  return SPEF_OK;
+}
+
+extern "C" int spef_temporal_step_logits(spef_ctx* ctx, const float* ori_logits, const float* pos_logits, int32_t S,
+                                         const spef_temporal_out* out, void* stream) {
+  if (!ctx) return SPEF_ERR_INVALID;
+  if (!ori_logits || !pos_logits) return fail(ctx, SPEF_ERR_INVALID, "spef_temporal_step_logits: NULL argument");
+  CK(cudaSetDevice(ctx->cfg.device));
+  return temporal_from_logits(ctx, ori_logits, ctx->cfg.n_ori, pos_logits, ctx->cfg.n_pos, S, 1, out, (cudaStream_t)stream);
+}
+
+extern "C" int spef_temporal_step(spef_ctx* ctx, const float* images_dev, int32_t S, int32_t apply_filter, const spef_temporal_out* out, void* stream) {
+  int rc = check_ready(ctx, S, "spef_temporal_step");
+  if (rc) return rc;
+  if (!images_dev) return fail(ctx, SPEF_ERR_INVALID, "spef_temporal_step: NULL argument");
+  CK(cudaSetDevice(ctx->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if ((rc = forward_internal(ctx, images_dev, S, st, nullptr))) return rc;
+  return temporal_from_logits(ctx, ctx->head_out, ctx->head_pad, ctx->head_out + ctx->cfg.n_ori, ctx->head_pad, S, apply_filter, out, st);
+}
+
+extern "C" int spef_pdf_filter(spef_ctx* ctx, const float* cur, int32_t S, int32_t n, float* state, int32_t* has_state, float n_coef,
+                               float alpha, float* out, float* distance, void* stream) {
+  if (!ctx) return SPEF_ERR_INVALID;
+  if (!cur || !state || !has_state || !out || !distance || S < 1 || n < 1) return fail(ctx, SPEF_ERR_INVALID, "spef_pdf_filter: bad argument");
+  if (cur == out) return fail(ctx, SPEF_ERR_INVALID, "spef_pdf_filter: cur and out must not alias");
+  CK(cudaSetDevice(ctx->cfg.device));
+  temporal_filter_kernel<<<S, 256, 0, (cudaStream_t)stream>>>(cur, n, state, has_state, n_coef, alpha, out, distance);
+  CK_LAUNCH("temporal_filter_kernel");
+  return SPEF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// introspection
+// ------------------------------------------------------------------------------------------------------
+extern "C" int64_t spef_launch_count(const spef_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int spef_forward_cost(const spef_ctx* ctx, int32_t B, double* bytes_out, double* flops_out) {
+  if (!ctx) return SPEF_ERR_INVALID;
+  double bytes = 0.0, flops = 0.0;
+  const double e = (double)ctx->esz;
+  for (const Layer& l : ctx->layers) {
+    const double in_el = (double)l.hin * l.win * l.cin, out_el = (double)l.hout * l.wout * ((l.kind == K_HEAD) ? l.cout : l.cout);
+    switch (l.kind) {
+      case K_STEM: bytes += in_el * 4 + out_el * e; flops += 2.0 * 27 * out_el; break;
+      case K_DW: bytes += (in_el + out_el) * e; flops += 2.0 * 9 * out_el; break;
+      case K_PW: bytes += (in_el + out_el + (l.residual ? out_el : 0.0)) * e; flops += 2.0 * l.cin * out_el; break;
+      case K_POOL: bytes += (in_el + out_el) * e; flops += in_el; break;
+      case K_HEAD: bytes += in_el * e + out_el * 4; flops += 2.0 * l.cin * out_el; break;
+    }
+  }
+  if (bytes_out) *bytes_out = bytes * B;
+  if (flops_out) *flops_out = flops * B;
+  return SPEF_OK;
+}
+
+// debug: the device Jacobi solver compiled for the host, so that the CPU test-suite can pin it against LAPACK
+extern "C" int spef_debug_jacobi4_host(const double* a_in /*[16]*/, double* evals /*[4]*/, double* evecs /*[16], columns*/) {
+  if (!a_in || !evals || !evecs) return SPEF_ERR_INVALID;
+  double a[4][4], v[4][4];
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) a[i][j] = a_in[i * 4 + j];
+  jacobi4(a, v);
+  for (int i = 0; i < 4; ++i) {
+    evals[i] = a[i][i];
+    for (int j = 0; j < 4; ++j) evecs[i * 4 + j] = v[i][j];
+  }
+  return SPEF_OK;
+}

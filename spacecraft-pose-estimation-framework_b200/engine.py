@@ -1,0 +1,338 @@
+"""Thin Python owner of one ``spef_ctx`` (include/spef_b200.h).  PyTorch is used only for device memory
+and stream handles; every computation is a call into libspef_b200.so."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _ffi
+from ._ffi import SpefConfig, SpefTemporalOut, check, ptr
+
+_PRECISIONS = {"fp32": _ffi.SPEF_FP32, "float32": _ffi.SPEF_FP32, "bf16": _ffi.SPEF_BF16, "bfloat16": _ffi.SPEF_BF16}
+
+
+def _require_cuda(device) -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("spef_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    dev = torch.device(device if device is not None else "cuda:0")
+    if dev.type != "cuda":
+        raise RuntimeError(f"spef_b200 runs on CUDA devices only, got {dev}")
+    return torch.device("cuda", dev.index if dev.index is not None else torch.cuda.current_device())
+
+
+def _stream(dev: torch.device) -> Optional[int]:
+    return torch.cuda.current_stream(dev).cuda_stream or None
+
+
+class Engine:
+    """One device context: weights, histograms, workspaces, temporal state."""
+
+    def __init__(self, img_h: int = 240, img_w: int = 384, n_ori: int = 1728, n_pos: int = 3,
+                 pos_classification: bool = False, precision: str = "bf16", max_batch: int = 32,
+                 device=None, pw_impl: int = 0):
+        if precision not in _PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(_PRECISIONS)}")
+        self.device = _require_cuda(device)
+        self.lib = _ffi.lib()
+        self.cfg = SpefConfig(C.sizeof(SpefConfig), self.device.index, img_h, img_w, n_ori, n_pos,
+                              int(bool(pos_classification)), _PRECISIONS[precision], max_batch, pw_impl)
+        self.precision = "bf16" if _PRECISIONS[precision] == _ffi.SPEF_BF16 else "fp32"
+        self.act_dtype = torch.bfloat16 if self.precision == "bf16" else torch.float32
+        handle = C.c_void_p()
+        check(None, self.lib.spef_create(C.byref(handle), C.byref(self.cfg)))
+        self._h = handle.value
+        self.n_ori, self.n_pos, self.pos_classification = n_ori, n_pos, bool(pos_classification)
+        self.max_batch, self.img_h, self.img_w = max_batch, img_h, img_w
+        self.weights_ready = False
+        self.ori_hist_n = self.pos_hist_n = 0
+
+    # ---- lifecycle -------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.spef_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc: int):
+        check(self._h, rc)
+
+    # ---- weights / tables ------------------------------------------------------------------------
+    def load_state_dict(self, state_dict: Dict[str, torch.Tensor]):
+        """Feed the reference's 316-key state_dict (src/modeling/model.py:261-266); BN folding, repacking and
+        casting happen inside the library."""
+        for key, t in state_dict.items():
+            if key.endswith("num_batches_tracked"):
+                continue
+            a = t.detach().to("cpu", torch.float32).contiguous().numpy()
+            shape = (C.c_int64 * max(a.ndim, 1))(*a.shape)
+            self._ck(self.lib.spef_load_tensor(self._h, key.encode(), a.ctypes.data, shape, a.ndim))
+        self._ck(self.lib.spef_finalize_weights(self._h))
+        self.weights_ready = True
+
+    def set_ori_histogram(self, hist: np.ndarray):
+        h = np.ascontiguousarray(hist, dtype=np.float64)
+        assert h.ndim == 2 and h.shape[1] == 4
+        self._ck(self.lib.spef_set_ori_histogram(self._h, h.ctypes.data, h.shape[0]))
+        self.ori_hist_n = h.shape[0]
+
+    def set_pos_histogram(self, hist: np.ndarray):
+        h = np.ascontiguousarray(hist, dtype=np.float64)
+        assert h.ndim == 2 and h.shape[1] == 3
+        self._ck(self.lib.spef_set_pos_histogram(self._h, h.ctypes.data, h.shape[0]))
+        self.pos_hist_n = h.shape[0]
+
+    # ---- helpers ---------------------------------------------------------------------------------
+    def _dev_f32(self, x, shape=None) -> torch.Tensor:
+        t = torch.as_tensor(x)
+        t = t.to(self.device, torch.float32, non_blocking=True).contiguous()
+        if shape is not None:
+            assert tuple(t.shape) == tuple(shape), f"expected shape {shape}, got {tuple(t.shape)}"
+        return t
+
+    def _empty(self, *shape, dtype=torch.float32) -> torch.Tensor:
+        return torch.empty(*shape, dtype=dtype, device=self.device)
+
+    def _check_images(self, images: torch.Tensor) -> int:
+        if images.dim() != 4 or images.shape[1] != 3 or images.shape[2] != self.img_h or images.shape[3] != self.img_w:
+            raise ValueError(f"images must be [B,3,{self.img_h},{self.img_w}], got {tuple(images.shape)}")
+        if images.shape[0] > self.max_batch:
+            raise ValueError(f"batch {images.shape[0]} exceeds the engine's max_batch {self.max_batch}")
+        return images.shape[0]
+
+    # ---- network ---------------------------------------------------------------------------------
+    def forward(self, images: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """ModelWrapper.forward: images [B,3,H,W] f32 on this device -> (ori logits [B,n_ori], pos [B,n_pos])."""
+        B = self._check_images(images)
+        x = self._dev_f32(images)
+        ori, pos = self._empty(B, self.n_ori), self._empty(B, self.n_pos)
+        self._ck(self.lib.spef_forward(self._h, ptr(x), B, ptr(ori), ptr(pos), _stream(self.device)))
+        return ori, pos
+
+    def forward_timed(self, images: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, np.ndarray]:
+        B = self._check_images(images)
+        x = self._dev_f32(images)
+        ori, pos = self._empty(B, self.n_ori), self._empty(B, self.n_pos)
+        ms = np.zeros(self.num_layers(), np.float32)
+        self._ck(self.lib.spef_forward_timed(self._h, ptr(x), B, ptr(ori), ptr(pos), ms.ctypes.data, _stream(self.device)))
+        return ori, pos, ms
+
+    def num_layers(self) -> int:
+        return self.lib.spef_num_layers(self._h)
+
+    def layer_info(self, i: int) -> dict:
+        v = [C.c_int32() for _ in range(10)]
+        self._ck(self.lib.spef_layer_info(self._h, i, *[C.byref(x) for x in v]))
+        names = ("kind", "cin", "cout", "hin", "win", "hout", "wout", "stride", "relu", "residual")
+        return {n: x.value for n, x in zip(names, v)}
+
+    def layer_forward(self, i: int, x: torch.Tensor, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Teacher-forced single layer.  x: stem -> [B,3,H,W] f32; otherwise NHWC [B,H,W,C] in the activation dtype
+        (pool/head: [B,HW,C] / [B,C]).  Returns the layer output (NHWC, activation dtype; head: f32 [B,n_pad])."""
+        info = self.layer_info(i)
+        B = x.shape[0]
+        x = x.to(self.device).contiguous()
+        if info["kind"] == _ffi.KIND_HEAD:
+            out = self._empty(B, info["cout"])
+        elif info["kind"] == _ffi.KIND_POOL:
+            out = self._empty(B, info["cout"], dtype=self.act_dtype)
+        else:
+            out = self._empty(B, info["hout"], info["wout"], info["cout"], dtype=self.act_dtype)
+        want = torch.float32 if info["kind"] == _ffi.KIND_STEM else self.act_dtype
+        assert x.dtype == want, f"layer {i} expects {want}, got {x.dtype}"
+        r = None
+        if residual is not None:
+            r = residual.to(self.device).contiguous()
+            assert r.dtype == self.act_dtype and r.shape == out.shape
+        self._ck(self.lib.spef_layer_forward(self._h, i, ptr(x), ptr(r), ptr(out), B, _stream(self.device)))
+        return out
+
+    # ---- post-processing (device tensors) --------------------------------------------------------
+    def decode_ori(self, x: torch.Tensor, is_logits: bool, want_soft=False, want_hinv=False, want_argmax=False):
+        x = self._dev_f32(x)
+        B, n = x.shape
+        soft = self._empty(B, n) if (want_soft and is_logits) else None
+        quat = self._empty(B, 4)
+        hinv = self._empty(B, 4, 4) if want_hinv else None
+        amax = self._empty(B, dtype=torch.int32) if want_argmax else None
+        flags = torch.zeros(B, dtype=torch.int32, device=self.device)
+        self._ck(self.lib.spef_decode_ori(self._h, ptr(x), B, n, int(is_logits), ptr(soft), ptr(quat), ptr(hinv),
+                                          ptr(amax), ptr(flags), _stream(self.device)))
+        return {"soft": soft if is_logits else x, "quat": quat, "hinv": hinv, "argmax": amax, "flags": flags}
+
+    def decode_pos(self, x: torch.Tensor, is_logits: bool, want_soft=False):
+        x = self._dev_f32(x)
+        B, n = x.shape
+        soft = self._empty(B, n) if (want_soft and is_logits) else None
+        pos = self._empty(B, 3)
+        flags = torch.zeros(B, dtype=torch.int32, device=self.device)
+        self._ck(self.lib.spef_decode_pos(self._h, ptr(x), B, n, int(is_logits), ptr(soft), ptr(pos), ptr(flags),
+                                          _stream(self.device)))
+        return {"soft": soft if is_logits else x, "pos": pos, "flags": flags}
+
+    def score(self, quat_pred, pos_pred, quat_true, pos_true, sums: Optional[torch.Tensor] = None, want_per_image=False):
+        qp, tp = self._dev_f32(quat_pred), self._dev_f32(pos_pred)
+        qt, tt = self._dev_f32(quat_true), self._dev_f32(pos_true)
+        B = qp.shape[0]
+        if sums is None:
+            sums = torch.zeros(8, dtype=torch.float64, device=self.device)
+        per = self._empty(B, 2) if want_per_image else None
+        self._ck(self.lib.spef_score(self._h, ptr(qp), ptr(tp), ptr(qt), ptr(tt), B, ptr(sums), ptr(per), _stream(self.device)))
+        return sums, per
+
+    # ---- fused predict ---------------------------------------------------------------------------
+    def predict(self, images: torch.Tensor, want_soft=True, want_argmax=False) -> Dict[str, torch.Tensor]:
+        """forward + softmax + decode on device tensors (spef_predict)."""
+        B = self._check_images(images)
+        x = self._dev_f32(images)
+        out = {"ori": self._empty(B, 4), "pos": self._empty(B, 3), "flags": torch.zeros(B, dtype=torch.int32, device=self.device)}
+        if want_soft:
+            out["ori_soft"] = self._empty(B, self.n_ori)
+            if self.pos_classification:
+                out["pos_soft"] = self._empty(B, self.n_pos)
+        if want_argmax:
+            out["argmax"] = self._empty(B, dtype=torch.int32)
+        self._ck(self.lib.spef_predict(self._h, ptr(x), B, ptr(out.get("ori_soft")), ptr(out["ori"]), ptr(out.get("pos_soft")),
+                                       ptr(out["pos"]), ptr(out.get("argmax")), ptr(out["flags"]), _stream(self.device)))
+        return out
+
+    def predict_host(self, images: torch.Tensor, want_soft=True, want_argmax=False) -> Dict[str, np.ndarray]:
+        """Host buffers in, host buffers out (spef_predict_host): the call SPETorch.predict maps to."""
+        B = self._check_images(images)
+        x = images.detach()
+        if x.dtype != torch.float32 or not x.is_contiguous() or x.device.type != "cpu":
+            x = x.to("cpu", torch.float32).contiguous()
+        out = {"ori": np.empty((B, 4), np.float32), "pos": np.empty((B, 3), np.float32), "flags": np.zeros(B, np.uint32)}
+        if want_soft:
+            out["ori_soft"] = np.empty((B, self.n_ori), np.float32)
+            if self.pos_classification:
+                out["pos_soft"] = np.empty((B, self.n_pos), np.float32)
+        if want_argmax:
+            out["argmax"] = np.empty(B, np.int32)
+        self._ck(self.lib.spef_predict_host(self._h, x.data_ptr(), B, ptr(out.get("ori_soft")), ptr(out["ori"]),
+                                            ptr(out.get("pos_soft")), ptr(out["pos"]), ptr(out.get("argmax")),
+                                            ptr(out["flags"]), _stream(self.device)))
+        return out
+
+    # ---- evaluation accumulators -----------------------------------------------------------------
+    def eval_reset(self):
+        self._ck(self.lib.spef_eval_reset(self._h, _stream(self.device)))
+
+    def eval_batch(self, images: torch.Tensor, quat_true, pos_true, want_per_image=False):
+        B = self._check_images(images)
+        if images.device.type == "cpu":
+            x = images.detach().to(torch.float32).contiguous()
+            qt = np.ascontiguousarray(torch.as_tensor(quat_true).cpu().numpy(), np.float32)
+            tt = np.ascontiguousarray(torch.as_tensor(pos_true).cpu().numpy(), np.float32)
+            per = np.empty((B, 2), np.float32) if want_per_image else None
+            self._ck(self.lib.spef_eval_batch_host(self._h, x.data_ptr(), qt.ctypes.data, tt.ctypes.data, B, ptr(per),
+                                                   _stream(self.device)))
+            return per
+        x, qt, tt = self._dev_f32(images), self._dev_f32(quat_true, (B, 4)), self._dev_f32(pos_true, (B, 3))
+        per = self._empty(B, 2) if want_per_image else None
+        self._ck(self.lib.spef_eval_batch(self._h, ptr(x), ptr(qt), ptr(tt), B, ptr(per), _stream(self.device)))
+        return per
+
+    def eval_read(self) -> np.ndarray:
+        s = np.zeros(8, np.float64)
+        self._ck(self.lib.spef_eval_read(self._h, s.ctypes.data, _stream(self.device)))
+        return s
+
+    def eval_sums_tensor(self) -> torch.Tensor:
+        """The 8 device accumulators as a torch view-free copy target for collectives: returns a fresh
+        tensor holding the current sums (float64 [8])."""
+        return torch.from_numpy(self.eval_read()).to(self.device)
+
+    # ---- host-buffer post-processing (what SPEUtils binds to) ------------------------------------
+    def decode_ori_host(self, x: np.ndarray, is_logits: bool, want_soft=False, want_hinv=False, want_argmax=False):
+        x = np.ascontiguousarray(x, np.float32)
+        B, n = x.shape
+        soft = np.empty((B, n), np.float32) if (want_soft and is_logits) else None
+        quat = np.empty((B, 4), np.float32)
+        hinv = np.empty((B, 4, 4), np.float32) if want_hinv else None
+        amax = np.empty(B, np.int32) if want_argmax else None
+        flags = np.zeros(B, np.uint32)
+        self._ck(self.lib.spef_decode_ori_host(self._h, x.ctypes.data, B, n, int(is_logits), ptr(soft), ptr(quat), ptr(hinv),
+                                               ptr(amax), ptr(flags), _stream(self.device)))
+        return {"soft": soft if is_logits else x, "quat": quat, "hinv": hinv, "argmax": amax, "flags": flags}
+
+    def decode_pos_host(self, x: np.ndarray, is_logits: bool, want_soft=False):
+        x = np.ascontiguousarray(x, np.float32)
+        B, n = x.shape
+        soft = np.empty((B, n), np.float32) if (want_soft and is_logits) else None
+        pos = np.empty((B, 3), np.float32)
+        flags = np.zeros(B, np.uint32)
+        self._ck(self.lib.spef_decode_pos_host(self._h, x.ctypes.data, B, n, int(is_logits), ptr(soft), ptr(pos), ptr(flags),
+                                               _stream(self.device)))
+        return {"soft": soft if is_logits else x, "pos": pos, "flags": flags}
+
+    def score_host(self, quat_pred, pos_pred, quat_true, pos_true, want_per_image=False):
+        qp, tp = np.ascontiguousarray(quat_pred, np.float32), np.ascontiguousarray(pos_pred, np.float32)
+        qt, tt = np.ascontiguousarray(quat_true, np.float32), np.ascontiguousarray(pos_true, np.float32)
+        B = qp.shape[0]
+        assert qp.shape == (B, 4) and qt.shape == (B, 4) and tp.shape == (B, 3) and tt.shape == (B, 3)
+        sums = np.zeros(8, np.float64)
+        per = np.empty((B, 2), np.float32) if want_per_image else None
+        self._ck(self.lib.spef_score_host(self._h, qp.ctypes.data, tp.ctypes.data, qt.ctypes.data, tt.ctypes.data, B,
+                                          sums.ctypes.data, ptr(per), _stream(self.device)))
+        return sums, per
+
+    # ---- temporal --------------------------------------------------------------------------------
+    def temporal_reset(self, n_streams: int = 1):
+        self._ck(self.lib.spef_temporal_reset(self._h, n_streams, _stream(self.device)))
+        self._t_streams = n_streams
+
+    def _temporal_out(self, S: int):
+        t = {
+            "still_ori_soft": self._empty(S, self.n_ori), "still_pos_soft": self._empty(S, self.n_pos),
+            "still_quat": self._empty(S, 4), "still_pos": self._empty(S, 3),
+            "video_ori_soft": self._empty(S, self.n_ori), "video_pos_soft": self._empty(S, self.n_pos),
+            "video_quat": self._empty(S, 4), "video_pos": self._empty(S, 3),
+            "ori_distance": self._empty(S), "pos_distance": self._empty(S),
+            "flags": torch.zeros(S, dtype=torch.int32, device=self.device),
+        }
+        st = SpefTemporalOut(*[t[n].data_ptr() for n, _ in SpefTemporalOut._fields_])
+        return t, st
+
+    def temporal_step_logits(self, ori_logits, pos_logits) -> Dict[str, torch.Tensor]:
+        o, p = self._dev_f32(ori_logits), self._dev_f32(pos_logits)
+        S = o.shape[0]
+        t, st = self._temporal_out(S)
+        self._ck(self.lib.spef_temporal_step_logits(self._h, ptr(o), ptr(p), S, C.byref(st), _stream(self.device)))
+        return t
+
+    def temporal_step(self, images: torch.Tensor, apply_filter: bool = True) -> Dict[str, torch.Tensor]:
+        S = self._check_images(images)
+        x = self._dev_f32(images)
+        t, st = self._temporal_out(S)
+        self._ck(self.lib.spef_temporal_step(self._h, ptr(x), S, int(apply_filter), C.byref(st), _stream(self.device)))
+        if not apply_filter:
+            t = {k: v for k, v in t.items() if not k.startswith("video_") and not k.endswith("_distance")}
+        return t
+
+    def pdf_filter(self, cur: torch.Tensor, state: torch.Tensor, has_state: torch.Tensor, n_coef: float, alpha: float):
+        """TemporalPDF.update_pdf on caller-owned device state; returns (filtered pdf [S,n], distance [S])."""
+        cur = self._dev_f32(cur)
+        S, n = cur.shape
+        assert state.shape == (S, n) and state.dtype == torch.float32 and state.is_cuda
+        assert has_state.shape == (S,) and has_state.dtype == torch.int32 and has_state.is_cuda
+        out, dist = self._empty(S, n), self._empty(S)
+        self._ck(self.lib.spef_pdf_filter(self._h, ptr(cur), S, n, ptr(state), ptr(has_state), float(n_coef), float(alpha),
+                                          ptr(out), ptr(dist), _stream(self.device)))
+        return out, dist
+
+    # ---- introspection ---------------------------------------------------------------------------
+    def launch_count(self) -> int:
+        return int(self.lib.spef_launch_count(self._h))
+
+    def forward_cost(self, batch: int) -> Tuple[float, float]:
+        b, f = C.c_double(), C.c_double()
+        self._ck(self.lib.spef_forward_cost(self._h, batch, C.byref(b), C.byref(f)))
+        return b.value, f.value

@@ -1,0 +1,108 @@
+"""evaluation() (reference: src/tools/evaluation.py:35-102) with on-device score accumulation.
+
+For a spef_b200 plug-in (SPEB200) the whole batch step -- H2D, forward, softmax, decode, pose error -- is one
+C-ABI call (spef_eval_batch_host); the five ESA sums stay on the device as float64 and are read once per phase.
+When torch.distributed is initialised (one process per GPU, each holding a shard of the loader) the 8 sums are
+all-reduced (SUM) once per phase -- the only collective on the path -- and the per-image errors are all-gathered
+for std / MAD.  Any other duck-typed back-end with predict() takes the reference's per-batch route.
+"""
+from __future__ import annotations
+
+from typing import Any, Dict, List, Tuple
+
+import numpy as np
+import torch
+
+from ..spe.spe_b200 import SPEB200
+from ..spe.spe_utils import SPEUtils
+from .utils import RunningAverage
+
+
+def mad(data) -> float:
+    """Median absolute deviation (evaluation.py:16-32)."""
+    median = np.median(data)
+    return np.median(np.abs(np.array(data) - median)).tolist()
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist if (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1) else None
+
+
+def reduce_eval_sums(sums: np.ndarray, device=None) -> np.ndarray:
+    """SUM all-reduce of the 8 float64 accumulators across ranks (NCCL on GPU tensors, gloo on CPU tensors).
+    Linear, so it reproduces RunningAverage's sum_b(mean_b * n_b) / sum_b n_b over the union of the shards."""
+    dist = _dist()
+    if dist is None:
+        return sums
+    t = torch.from_numpy(np.ascontiguousarray(sums, np.float64))
+    if dist.get_backend() == "nccl":
+        t = t.to(device if device is not None else torch.device("cuda", torch.cuda.current_device()))
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t.cpu().numpy()
+
+
+def gather_per_image(err: np.ndarray, device=None) -> np.ndarray:
+    """All-gather of the per-image error rows [n_local, 2] (ragged across ranks)."""
+    dist = _dist()
+    if dist is None:
+        return err
+    parts = [None] * dist.get_world_size()
+    dist.all_gather_object(parts, err)
+    return np.concatenate(parts, axis=0)
+
+
+def _finish(rec_score, rec_error, phase, sums, per_image, device=None):
+    sums = reduce_eval_sums(sums, device)
+    per_image = gather_per_image(per_image, device)
+    m = SPEUtils.metrics_from_sums(sums)
+    rec_score[phase]['ori'].append(float(m['ori_score']))
+    rec_score[phase]['pos'].append(float(m['pos_score']))
+    rec_score[phase]['esa'].append(float(m['esa_score']))
+    rec_error[phase]['ori'].append(float(m['ori_error']))
+    rec_error[phase]['pos'].append(float(m['pos_error']))
+    rec_error[phase]['ori_std'].append(np.std(per_image[:, 0]).tolist())
+    rec_error[phase]['pos_std'].append(np.std(per_image[:, 1]).tolist())
+    rec_error[phase]['ori_mad'].append(mad(per_image[:, 0]))
+    rec_error[phase]['pos_mad'].append(mad(per_image[:, 1]))
+
+
+def evaluation(
+    spe_model: Any,
+    dataloader: Dict[str, Any],
+    spe_utils: SPEUtils,
+    split: Tuple[str, ...] = ('test', 'valid'),
+) -> Tuple[Dict[str, Dict[str, List[float]]], Dict[str, Dict[str, List[float]]]]:
+    """Same arguments and return structure as the reference: rec_score[phase] = {'ori','pos','esa'},
+    rec_error[phase] = {'ori','pos','ori_std','pos_std','ori_mad','pos_mad'}, each a list of length 1."""
+    rec_score = {x: {'ori': [], 'pos': [], 'esa': []} for x in split}
+    rec_error = {x: {'ori': [], 'pos': [], 'ori_std': [], 'pos_std': [], 'ori_mad': [], 'pos_mad': []} for x in split}
+
+    for phase in split:
+        if isinstance(spe_model, SPEB200):
+            eng = spe_model.engine
+            eng.eval_reset()
+            per = []
+            for images, targets in dataloader[phase]:
+                per.append(eng.eval_batch(images['torch'], targets['ori'], targets['pos'], want_per_image=True))
+            sums = eng.eval_read()
+            per = [p.cpu().numpy() if isinstance(p, torch.Tensor) else p for p in per]
+            per_image = np.concatenate(per, axis=0) if per else np.zeros((0, 2), np.float32)
+            _finish(rec_score, rec_error, phase, sums, per_image, eng.device)
+        else:
+            # any other back-end with predict(): per-batch route of the reference (evaluation.py:69-85); the score
+            # itself still runs in libspef_b200.so through SPEUtils.get_score
+            sums = np.zeros(8, np.float64)
+            per = []
+            running_avg = RunningAverage(keys=('esa_score', 'ori_score', 'pos_score', 'ori_error', 'pos_error'))
+            from ..spe.spe_utils import _get_score_engine
+            for images, targets in dataloader[phase]:
+                pose, _ = spe_model.predict(images['torch'])
+                tgt = {k: (v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)) for k, v in targets.items()}
+                s, p = _get_score_engine().score_host(pose['ori'], pose['pos'], tgt['ori'], tgt['pos'], want_per_image=True)
+                running_avg.update(SPEUtils.metrics_from_sums(s), images['torch'].size(0))
+                sums += s
+                per.append(p)
+            per_image = np.concatenate(per, axis=0) if per else np.zeros((0, 2), np.float32)
+            _finish(rec_score, rec_error, phase, sums, per_image)
+    return rec_score, rec_error
