@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""bench.py -- SPEF pose-inference hot path on B200: images/sec, roofline fraction, CPU baseline.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one process per GPU)
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path (oracle port), rank 0 only
+
+A "step" is one pass of the hot path over one batch of synthetic SPEED-shaped images: Mobile-URSONet forward
+(BF16 activations, tcgen05 pointwise GEMMs) -> softmax -> soft-classification decode -> pose error / ESA sums.
+Workload at every N: BASELINE.json configs[1]/[2] -- batch 256 per GPU (weak scaling: images are independent, no
+data-path collective; one NCCL all-reduce of the 8 float64 ESA accumulators at the end of the timed region).
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "images/sec (device-timed, max over ranks)"
+UNIT = "images/s"
+IMG = (240, 384)
+N_ORI = 1728
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--pw-impl", type=int, default=0, help="0 tcgen05 (default), 1 SIMT cross-check")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--layers", action="store_true", help="also print the per-layer table to stderr")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(", ") for r in open(self.f.name) if r.strip()]
+        os.unlink(self.f.name)
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1])); smax = float(r[2])
+            except ValueError:
+                continue
+            for n, v in zip(names, r[5:9]):
+                if v.strip().lower() == "active":
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the oracle port of the reference's PyTorch + NumPy path on the host cores
+# ------------------------------------------------------------------------------------------------------
+def cpu_hot_path_factory():
+    """One step of the reference's hot path on the CPU (SPETorch.predict + get_score, spe_torch.py:41-76,
+    spe_utils.py:104-159) as restated by oracle/spef_oracle.py -- the only place bench.py executes oracle/."""
+    from oracle import spef_oracle as O
+    from spef_b200.tools import synthetic
+    sd = synthetic.synthetic_state_dict(N_ORI, 3)
+    hist = O.ori_histogram(12)[0]
+
+    def step(images, targets):
+        ori, pos = O.forward_fp32(sd, images)
+        soft = O.softmax(ori.numpy())
+        q, _ = O.ori_decode_batch(soft, hist)
+        return O.get_score(targets, {"ori": q, "pos": pos.numpy()})
+    return step
+
+
+def time_cpu(seconds, sample_batch=32):
+    from spef_b200.tools import synthetic
+    cores = len(os.sched_getaffinity(0))
+    torch.set_num_threads(cores)
+    step = cpu_hot_path_factory()
+    x = synthetic.synthetic_images(sample_batch)
+    tg = synthetic.synthetic_targets(sample_batch)
+    step(x[:4], {k: v[:4] for k, v in tg.items()})  # warm-up
+    n, t0 = 0, time.perf_counter()
+    while True:
+        step(x, tg)
+        n += sample_batch
+        el = time.perf_counter() - t0
+        if el >= seconds:
+            break
+    return n / el, cores, f"{n} images in batches of {sample_batch} ({el:.1f} s), FP32, torch {torch.__version__} CPU + NumPy, {cores} threads"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from spef_b200.tools import synthetic
+    cores = len(os.sched_getaffinity(0))
+    torch.set_num_threads(cores)
+    step = cpu_hot_path_factory()
+    sample = 32  # bounded sample of the 256-image batch per step (the full batch takes ~10 s on a host CPU)
+    x = synthetic.synthetic_images(sample)
+    tg = synthetic.synthetic_targets(sample)
+    for _ in range(max(args.warmup, 1)):
+        step(x[:8], {k: v[:8] for k, v in tg.items()})
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step(x, tg)
+    el = time.perf_counter() - t0
+    v = sample * args.steps / el
+    desc = f"{sample}-image sample of the {args.batch}-image batch per step, FP32, {cores} host threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000 * el / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "Mobile-URSONet batched inference (forward + softmax + decode + ESA score), batch 256 per GPU, 240x384, 1728 orientation bins",
+                   "note": "reference = the reference's own PyTorch/NumPy CPU path as restated by oracle/ (the reference is pure Python and has no pip-installable package); rank 0 only"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ------------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------------
+def layer_table(eng, batch, ms):
+    """Per-launch algorithmic bytes / flops next to the measured device time."""
+    kinds = {0: "stem_conv3x3s2_kernel", 1: "pw_gemm", 2: "dwconv3x3_kernel", 3: "global_mean_kernel", 4: "pw_gemm"}
+    esz = 2 if eng.precision == "bf16" else 4
+    rows = []
+    for i in range(eng.num_layers()):
+        li = eng.layer_info(i)
+        ein = li["hin"] * li["win"] * li["cin"] * batch
+        eout = li["hout"] * li["wout"] * li["cout"] * batch
+        k = li["kind"]
+        if k == 0:
+            by, fl = ein * 4 + eout * esz, 2 * 27 * eout
+        elif k == 2:
+            by, fl = (ein + eout) * esz, 2 * 9 * eout
+        elif k == 1:
+            by, fl = (ein + eout * (2 if li["residual"] else 1)) * esz, 2 * li["cin"] * eout
+        elif k == 3:
+            by, fl = (ein + eout) * esz, ein
+        else:
+            by, fl = ein * esz + eout * 4 + li["cin"] * li["cout"] * esz, 2 * li["cin"] * eout
+        rows.append({"layer": i, "kernel": kinds[k], "cin": li["cin"], "cout": li["cout"], "hw": f"{li['hout']}x{li['wout']}",
+                     "stride": li["stride"], "bytes": by, "flops": fl, "ms": float(ms[i])})
+    return rows
+
+
+def run_b200(args):
+    from spef_b200.engine import Engine
+    from spef_b200.tools import synthetic
+    from spef_b200.tools.evaluation import reduce_eval_sums
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch multi-GPU runs with torch.distributed.run (one process per GPU)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    B = args.batch
+    eng = Engine(IMG[0], IMG[1], N_ORI, 3, False, args.precision, B, dev, args.pw_impl)
+    eng.load_state_dict(synthetic.synthetic_state_dict(N_ORI, 3))
+    from spef_b200.spe.classification_utils import OrientationSoftClassification
+    eng.set_ori_histogram(OrientationSoftClassification(12, 3, False).histogram)
+
+    # synthetic batch: 32 distinct seeded images tiled to B (283 MB of f32 at B = 256 > 126 MB L2), per-rank seed
+    base = synthetic.synthetic_images(min(B, 32), IMG, synthetic.IMAGE_SEED + rank)
+    host_images = base.repeat((B + base.shape[0] - 1) // base.shape[0], 1, 1, 1)[:B].contiguous().pin_memory()
+    tg = synthetic.synthetic_targets(B, 2024 + rank)
+    qt_h, tt_h = torch.from_numpy(tg["ori"]).pin_memory(), torch.from_numpy(tg["pos"]).pin_memory()
+    images = host_images.to(dev)
+    qt, tt = qt_h.to(dev), tt_h.to(dev)
+    stream = torch.cuda.current_stream(dev)
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    # ---- warm-up -------------------------------------------------------------------------------------
+    eng.eval_reset()
+    for _ in range(max(args.warmup, 3)):
+        eng.eval_batch(images, qt, tt)
+    sync_all()
+
+    # ---- timed region: K steps, inputs resident in HBM, CUDA events on the launching stream ----------
+    sampler = ClockSampler(local)
+    sampler.start()
+    eng.eval_reset()
+    launches0 = eng.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    e0.record(stream)
+    for _ in range(args.steps):
+        eng.eval_batch(images, qt, tt)
+    sums = eng.eval_sums_tensor() if dist is None else None
+    if dist is not None:  # the path's one exchange step: SUM all-reduce of the 8 ESA accumulators over NVLink
+        sums = torch.from_numpy(eng.eval_read()).to(dev)
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    e1.record(stream)
+    sync_all()
+    ms_total = e0.elapsed_time(e1)
+    launches = eng.launch_count() - launches0
+    clocks = sampler.stop()
+    if dist is not None:
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    value = world * B * args.steps / (ms_total / 1000)
+    s = sums.cpu().numpy()
+
+    # ---- end to end: host buffers through the C ABI (spef_eval_batch_host): H2D of the pinned images and targets,
+    # forward + decode + score, D2H of the per-image errors, every step ------------------------------------------
+    for _ in range(2):
+        eng.eval_batch(host_images, qt_h, tt_h, want_per_image=True)
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        per = eng.eval_batch(host_images, qt_h, tt_h, want_per_image=True)
+    eng.eval_read()
+    sync_all()
+    e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e = {"value": world * B * args.steps / e2e_s, "unit": UNIT,
+           "h2d_bytes_per_step": int(host_images.numel() * 4 + B * 28), "d2h_bytes_per_step": int(B * 8),
+           "api": "spef_eval_batch_host (pinned host images + targets in, per-image errors out)"}
+
+    # ---- per-kernel roofline: per-layer CUDA events on the same stream, same inputs, K steps -------------------
+    nl = eng.num_layers()
+    ms_layers = np.zeros(nl)
+    reps = max(3, min(args.steps, 10))
+    for _ in range(reps):
+        _, _, ms = eng.forward_timed(images)
+        ms_layers += ms
+    ms_layers /= reps
+    pk = peaks()
+    rows = layer_table(eng, B, ms_layers)
+    fam = {}
+    for r in rows:
+        name = r["kernel"] if r["kernel"] != "pw_gemm" else ("pw_gemm_tcgen05_kernel" if (args.precision == "bf16" and args.pw_impl == 0) else "pw_gemm_simt_kernel")
+        f = fam.setdefault(name, {"launches": 0, "bytes": 0.0, "flops": 0.0, "ms": 0.0})
+        f["launches"] += 1; f["bytes"] += r["bytes"]; f["flops"] += r["flops"]; f["ms"] += r["ms"]
+    kernels = []
+    for name, f in fam.items():
+        gbs = f["bytes"] / (f["ms"] * 1e-3) / 1e9 if f["ms"] > 0 else 0.0
+        kernels.append({"kernel": name, "launches_per_step": f["launches"], "ms_per_step": f["ms"], "share": f["ms"] / ms_layers.sum(),
+                        "achieved_GBps": gbs, "hbm_frac": gbs / pk["hbm_gbs"], "achieved_TFLOPs": f["flops"] / (f["ms"] * 1e-3) / 1e12 if f["ms"] > 0 else 0.0})
+    kernels.sort(key=lambda k: -k["ms_per_step"])
+    top = kernels[0]
+    ftop = fam[top["kernel"]]
+    roofline = {"kernel": top["kernel"], "bound": "hbm", "achieved": top["achieved_GBps"], "peak": pk["hbm_gbs"], "unit": "GB/s",
+                "frac": top["hbm_frac"], "traffic": None, "peak_source": pk["source"],
+                "algorithmic_bytes_per_launch": ftop["bytes"] / ftop["launches"], "avg_launch_ms": ftop["ms"] / ftop["launches"],
+                "share_of_step": top["share"],
+                "how": f"algorithmic bytes (DESIGN.md section 5) / per-layer CUDA-event time on the launch stream, mean of {reps} passes after the timed region, same inputs"}
+    tot_bytes, tot_flops = eng.forward_cost(B)
+    step_ms = ms_total / args.steps
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+        "config": {"workload": f"Mobile-URSONet {args.precision.upper()} batched inference (forward + softmax + soft-classification decode + ESA score), "
+                               f"batch {B} per GPU, 3x240x384 f32 NCHW images, 1728 orientation bins, regression position head (BASELINE.json configs[1]"
+                               + ("/[2]" if world > 1 else "") + ")",
+                   "weights": "calibrated random init (seed 7)", "l2": "inputs larger than L2 (283 MB image batch, GB-scale activations)",
+                   "parallelism": f"batch-sharded x{world}, one NCCL all-reduce of 8 f64 at the end" if world > 1 else "single GPU",
+                   "pw_impl": "tcgen05" if (args.precision == "bf16" and args.pw_impl == 0) else "simt"},
+        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+        "step_roofline": {"algorithmic_bytes_per_step": tot_bytes, "flops_per_step": tot_flops,
+                          "achieved_GBps": tot_bytes / (step_ms * 1e-3) / 1e9, "hbm_frac": tot_bytes / (step_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
+                          "achieved_TFLOPs": tot_flops / (step_ms * 1e-3) / 1e12},
+        "kernels": kernels,
+        "esa": {"images": float(s[3]), "esa_score": float((s[0] + s[1]) / s[3]), "flagged": float(s[4] + s[5])},
+    }
+    if rank == 0 and not args.no_cpu_baseline and world >= 1:
+        v, cores, desc = time_cpu(args.cpu_seconds)
+        out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
+    if rank == 0:
+        if args.layers:
+            for r in rows:
+                gb = r["bytes"] / (r["ms"] * 1e-3) / 1e9 if r["ms"] > 0 else 0
+                print(f"L{r['layer']:02d} {r['kernel']:24s} {r['cin']:5d}->{r['cout']:5d} {r['hw']:>8s} s{r['stride']} {r['ms']*1000:9.1f} us "
+                      f"{gb:8.0f} GB/s {r['flops']/(r['ms']*1e-3)/1e12 if r['ms'] > 0 else 0:7.1f} TF/s", file=sys.stderr)
+        print(json.dumps(out))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -35,7 +35,7 @@ def reduce_eval_sums(sums: np.ndarray, device=None) -> np.ndarray:
     dist = _dist()
     if dist is None:
         return sums
-    t = torch.from_numpy(np.ascontiguousarray(sums, np.float64))
+    t = torch.from_numpy(np.array(sums, dtype=np.float64, copy=True))  # never reduce into the caller's array
     if dist.get_backend() == "nccl":
         t = t.to(device if device is not None else torch.device("cuda", torch.cuda.current_device()))
     dist.all_reduce(t, op=dist.ReduceOp.SUM)

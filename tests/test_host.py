@@ -1,0 +1,172 @@
+"""CPU-side tests: the C-ABI library loads and exports every declared symbol, host logic of the Python mirror,
+and the device Jacobi solver compiled for the host.  No compute call needs a GPU here."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import spef_oracle as O
+from spef_b200 import _ffi
+from spef_b200.modeling import arch, import_model, copy_state_dict
+from spef_b200.spe import OrientationSoftClassification, PositionSoftClassification, SPEUtils
+from spef_b200.tools import RunningAverage, synthetic
+from spef_b200.tools.evaluation import mad
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+NO_GPU = not torch.cuda.is_available()
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "spef_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(spef_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _ffi.lib()
+    names = _declared_symbols()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(lib, n), f"libspef_b200.so does not export {n}"
+        assert n in _ffi.SIGNATURES, f"{n} is declared in the header but has no ctypes signature"
+    assert set(_ffi.SIGNATURES) == set(names)
+    assert lib.spef_abi_version() == 1
+
+
+def test_config_struct_matches_header():
+    text = open(os.path.join(ROOT, "include", "spef_b200.h")).read()
+    body = text[text.index("typedef struct spef_config {"):text.index("} spef_config;")]
+    fields = re.findall(r"int32_t\s+(\w+);", body)
+    assert fields == [f for f, _ in _ffi.SpefConfig._fields_]
+    body = text[text.index("typedef struct spef_temporal_out {"):text.index("} spef_temporal_out;")]
+    fields = re.findall(r"\*\s*(\w+);", body)
+    assert fields == [f for f, _ in _ffi.SpefTemporalOut._fields_]
+
+
+@pytest.mark.skipif(not NO_GPU, reason="checks the no-GPU failure mode")
+def test_create_fails_loudly_without_gpu():
+    lib = _ffi.lib()
+    cfg = _ffi.SpefConfig(ctypes.sizeof(_ffi.SpefConfig), 0, 240, 384, 1728, 3, 0, 1, 4, 0)
+    h = ctypes.c_void_p()
+    rc = lib.spef_create(ctypes.byref(h), ctypes.byref(cfg))
+    assert rc == 2 and not h.value
+    assert b"no CPU fallback" in lib.spef_last_error(None)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        from spef_b200.engine import Engine
+        Engine()
+
+
+def test_create_rejects_bad_config():
+    lib = _ffi.lib()
+    h = ctypes.c_void_p()
+    cfg = _ffi.SpefConfig(4, 0, 240, 384, 1728, 3, 0, 1, 4, 0)  # wrong struct_size
+    assert lib.spef_create(ctypes.byref(h), ctypes.byref(cfg)) == 1
+    cfg = _ffi.SpefConfig(ctypes.sizeof(_ffi.SpefConfig), 0, 240, 384, 1728, 5, 0, 1, 4, 0)  # regression head with n_pos != 3
+    assert lib.spef_create(ctypes.byref(h), ctypes.byref(cfg)) == 1
+    assert lib.spef_create(None, None) == 1
+
+
+def test_device_jacobi_solver_matches_lapack():
+    """The 4x4 cyclic Jacobi used by the decode kernel, compiled for the host, against np.linalg.eigh."""
+    lib = _ffi.lib()
+    rs = np.random.RandomState(0)
+    hist, _ = O.ori_histogram(12)
+    mats = []
+    for sigma in (1e-9, 1.0, 3.0, 10.0):
+        p = O.softmax((rs.randn(4, 1728) * sigma).astype(np.float32)).astype(np.float64)
+        for i in range(4):
+            mats.append(np.einsum("b,bi,bj->ij", p[i], hist, hist))
+    mats.append(np.diag([0.1, 0.2, 0.3, 0.4]))
+    mats.append(np.outer(hist[5], hist[5]))  # rank 1
+    for a in mats:
+        ev, evec = np.zeros(4), np.zeros((4, 4))
+        a = np.ascontiguousarray(a)
+        assert lib.spef_debug_jacobi4_host(a.ctypes.data, ev.ctypes.data, evec.ctypes.data) == 0
+        w, v = np.linalg.eigh(a)
+        np.testing.assert_allclose(np.sort(ev), w, rtol=1e-12, atol=1e-15)
+        q = evec[:, np.argmax(ev)]
+        assert O.quat_angle_deg(q / np.linalg.norm(q), v[:, -1]) < 1e-6
+        np.testing.assert_allclose(evec @ np.diag(ev) @ evec.T, a, atol=1e-14)
+
+
+def test_arch_and_state_dict_spec(golden):
+    spec = arch.state_dict_spec(1728, 3)
+    assert len(spec) == 316 and len(arch.conv_layers()) == 52
+    n_param = sum(int(np.prod(s)) for k, s, r in spec if r in ("conv", "bn_weight", "bn_bias", "linear_weight", "linear_bias"))
+    assert n_param == 4441283
+    assert [b["idx"] for b in arch.block_table() if b["residual"]] == [3, 5, 6, 8, 9, 10, 12, 13, 15, 16]
+    assert arch.output_hw(240, 384) == (8, 12)
+    # oracle and package agree on the topology
+    assert [(b["cin"], b["cout"], b["stride"]) for b in arch.block_table()] == [(b["cin"], b["cout"], b["stride"]) for b in O.block_table()]
+
+
+def test_synthetic_inputs_are_deterministic():
+    a, b = synthetic.synthetic_state_dict(1728, 3), synthetic.synthetic_state_dict(1728, 3)
+    assert list(a.keys()) == [k for k, _, _ in arch.state_dict_spec(1728, 3)]
+    assert all(torch.equal(a[k], b[k]) for k in a)
+    assert float(a["features.features.0.1.running_var"].min()) > 0
+    assert torch.equal(synthetic.synthetic_images(2), synthetic.synthetic_images(2))
+    t = synthetic.synthetic_targets(64)
+    np.testing.assert_allclose(np.linalg.norm(t["ori"], axis=1), 1, atol=1e-6)
+    assert t["pos"][:, 2].min() >= 3 and t["pos"][:, 2].max() <= 35
+
+
+def test_facade_histograms_and_encode_match_reference(golden):
+    g, ed = golden("histograms"), golden("encode_decode")
+    for n in (8, 12, 16):
+        for delete in (False, True):
+            o = OrientationSoftClassification(n, 3, delete)
+            tag = f"ori{n}_{'del' if delete else 'all'}"
+            np.testing.assert_allclose(o.histogram, g[tag + "_hist"], rtol=0, atol=1e-15)
+            np.testing.assert_array_equal(o.redundant_flags, g[tag + "_red"])
+            assert o.n_bins == g[tag + "_hist"].shape[0]
+    o = OrientationSoftClassification(12, 3, False)
+    assert o.b.shape == (1728, 4, 4)
+    p = PositionSoftClassification(10, 100, np.array([-16, -12, -2]), np.array([16, 12, 40]))
+    np.testing.assert_array_equal(p.histogram, g["pos10_hist"])
+    for i in range(4):
+        np.testing.assert_allclose(o.encode(ed["labels_q"][i]), ed["enc_ori"][i], rtol=1e-5, atol=1e-12)
+        np.testing.assert_allclose(p.encode(ed["labels_t"][i]), ed["enc_pos"][i], rtol=1e-5, atol=1e-12)
+
+
+def test_speutils_surface():
+    su = SPEUtils(None, 'classification', 12, 3, False, 'regression', 10, 100, None)
+    assert su.orientation.n_bins == 1728 and su.position.n_bins == 1000 and su.keypoints is None
+    with pytest.raises(NotImplementedError):
+        SPEUtils(None, 'keypoints', pos_mode='keypoints', keypoints_path='x.mat')
+    m = SPEUtils.metrics_from_sums(np.array([2.0, 1.0, 8.0, 4.0, 0, 0, 0, 0]))
+    assert m["ori_score"] == np.float32(0.5) and m["pos_score"] == np.float32(0.25) and m["pos_error"] == 2.0
+    assert m["esa_score"] == np.float32(0.75) and abs(m["ori_error"] - 0.5 * 180 / np.pi) < 1e-5
+
+
+def test_import_model_api_on_cpu():
+    data = {"valid": [({"torch": torch.rand(2, 3, 240, 384)}, {})]}
+    model, bit_width = import_model(data, 'mobilenet_v2_pytorch', 'ursonet_pytorch', ori_mode='classification',
+                                    n_ori_bins=1728, pos_mode='regression')
+    assert bit_width is None and not model.training
+    sd = model.state_dict()
+    assert list(sd.keys()) == [k for k, _, _ in arch.state_dict_spec(1728, 3)] and len(sd) == 316
+    assert hasattr(model, "features") and hasattr(model, "head")
+    model.load_state_dict(synthetic.synthetic_state_dict(1728, 3))
+    assert torch.equal(model.state_dict()["head.pos.0.bias"], torch.tensor([0.0, 0.0, 10.0]))
+    assert set(copy_state_dict(sd, model.state_dict()).keys()) == set(sd.keys())
+    with pytest.raises(NotImplementedError):
+        import_model(data, 'mobilenet_v2_brevitas', 'ursonet_brevitas', n_ori_bins=1728)
+    with pytest.raises(AssertionError):
+        import_model(data, 'mobilenet_v2_pytorch', 'ursonet_pytorch', ori_mode='classification')  # n_ori_bins missing
+    with pytest.raises(NotImplementedError):
+        model.train()
+    if NO_GPU:  # the forward must fail loudly, never fall back to torch ops
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            model(torch.rand(1, 3, 240, 384))
+
+
+def test_running_average_and_mad():
+    ra = RunningAverage(keys=("a",))
+    ra.update({"a": 1.0}, 3)
+    ra.update({"a": 5.0}, 1)
+    assert ra.get("a") == 2.0 and ra.get_multiple(("a",)) == {"a": 2.0}
+    assert mad([1.0, 2.0, 3.0, 4.0, 100.0]) == 1.0
