@@ -1,0 +1,173 @@
+// Depthwise ConvBnAct(C->C, k3, p1, stride S, groups=C) for BF16 NHWC activations, TMA-tiled.
+// (reference semantics: src/modeling/common/pytorch_layers.py:82-83 with BN folded, ReLU)
+//
+// Persistent CTAs loop over (channel chunk, image, tile_y, tile_x) tiles.  One thread issues a 4-D TMA box
+// {CV*8 channels, TWI cols, THI rows, 1 image} of the input into shared memory (double buffered, mbarrier
+// complete_tx); the 1-pixel halo and the image border come for free from TMA out-of-bounds zero fill (box start
+// at x0-1, y0-1), so the SM executes no address / bounds logic for loads.  Each thread owns one 8-channel vector
+// (fixed for the whole kernel => its 9x8 folded weights live in registers) and computes runs of 4 output pixels
+// along x with a register sliding window over the smem tile: (3S+3) x 3 LDS.128 per 4 outputs instead of 36.
+// Outputs go straight from registers to global memory: 8 lanes x 16 B = one full 128-byte line per pixel.
+#pragma once
+#include <cuda.h>
+#include "common.cuh"
+#include "gemm_tcgen05.cuh"  // mbarrier / TMA PTX wrappers
+
+namespace spef {
+namespace dw {
+
+constexpr int TX = 4;  // outputs per thread along x
+
+struct DwParams {
+  int B, H, W, C, Ho, Wo;
+  int TH, TW;        // output tile (TW multiple of TX)
+  int THI, TWI;      // input box rows / cols = (T-1)*S + 3
+  int tiles_y, tiles_x, nchunks;
+  int relu;
+};
+
+__device__ __forceinline__ void tma_load_4d(uint32_t smem_dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+__host__ __device__ inline int stage_stride(int thi, int twi, int cv) { return ((thi * twi * cv * 16 + 127) / 128) * 128; }
+inline size_t smem_bytes(const DwParams& p, int cv) { return 2 * (size_t)stage_stride(p.THI, p.TWI, cv) + 128 + 64; }
+
+template <int S, int CV>
+__global__ void __launch_bounds__(32 * CV, (CV == 4) ? 4 : 2)
+dwconv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__ w, const float* __restrict__ bias,
+                     bf16* __restrict__ out, const DwParams p) {
+  constexpr int NT = 32 * CV;
+  constexpr int NCOLS = (TX - 1) * S + 3;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+  const int tile_bytes = p.THI * p.TWI * CV * 16;               // TMA transaction size (full box, OOB included)
+  const int sstride = stage_stride(p.THI, p.TWI, CV);           // stage pitch, 128-byte aligned
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + 2 * (size_t)sstride);
+
+  const int tid = threadIdx.x;
+  const int cv = tid % CV;
+  const int nxs = p.TW / TX;
+  const int tasks = nxs * p.TH;            // (x strip, row) pairs per tile; each is done by CV threads
+  const int task0 = tid / CV, task_step = NT / CV;
+  const long long spatial_tiles = (long long)p.B * p.tiles_y * p.tiles_x;
+  const long long num_tiles = spatial_tiles * p.nchunks;
+
+  if (tid == 0) {
+    tc::tma_prefetch_desc(&tmX);
+    tc::mbar_init(tc::smem_u32(&full_bar[0]), 1);
+    tc::mbar_init(tc::smem_u32(&full_bar[1]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  auto issue = [&](long long tile, int stage) {
+    const int chunk = (int)(tile / spatial_tiles);
+    long long r = tile - (long long)chunk * spatial_tiles;
+    const int tx = (int)(r % p.tiles_x); r /= p.tiles_x;
+    const int ty = (int)(r % p.tiles_y);
+    const int b = (int)(r / p.tiles_y);
+    const uint32_t bar = tc::smem_u32(&full_bar[stage]);
+    tc::mbar_arrive_expect_tx(bar, (uint32_t)tile_bytes);
+    tma_load_4d(tc::smem_u32(smem + (size_t)stage * sstride), &tmX, chunk * CV * 8, tx * p.TW * S - 1, ty * p.TH * S - 1, b, bar);
+  };
+
+  long long tile = blockIdx.x;
+  if (tid == 0) {
+    if (tile < num_tiles) issue(tile, 0);
+    if (tile + gridDim.x < num_tiles) issue(tile + gridDim.x, 1);
+  }
+
+  float wr[9][8];
+  float bv[8];
+  int cur_chunk = -1;
+  uint32_t phases = 0;  // bit s = parity of stage s
+  int stage = 0;
+  for (; tile < num_tiles; tile += gridDim.x) {
+    const int chunk = (int)(tile / spatial_tiles);
+    long long r = tile - (long long)chunk * spatial_tiles;
+    const int tx = (int)(r % p.tiles_x); r /= p.tiles_x;
+    const int ty = (int)(r % p.tiles_y);
+    const int b = (int)(r / p.tiles_y);
+    const int c0 = chunk * CV * 8 + cv * 8;
+    const bool c_ok = c0 < p.C;
+    if (chunk != cur_chunk) {  // tiles are chunk-major, so this happens ~nchunks times per CTA
+      cur_chunk = chunk;
+      if (c_ok) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) Vec8<float>::load(w + (size_t)k * p.C + c0, wr[k]);
+        Vec8<float>::load(bias + c0, bv);
+      }
+    }
+    tc::mbar_wait(tc::smem_u32(&full_bar[stage]), (phases >> stage) & 1u);
+    phases ^= 1u << stage;
+    const uint8_t* tile_s = smem + (size_t)stage * sstride + cv * 16;
+
+    if (c_ok) {
+      for (int task = task0; task < tasks; task += task_step) {
+        const int xs = task % nxs, ry = task / nxs;
+        const int oy = ty * p.TH + ry;
+        const int ox0 = tx * p.TW + xs * TX;
+        if (oy >= p.Ho || ox0 >= p.Wo) continue;
+        float acc[TX][8];
+#pragma unroll
+        for (int t = 0; t < TX; ++t)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[t][e] = bv[e];
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+          const uint8_t* row = tile_s + ((size_t)(ry * S + ky) * p.TWI + xs * TX * S) * (CV * 16);
+#pragma unroll
+          for (int j = 0; j < NCOLS; ++j) {
+            const uint4 u = *reinterpret_cast<const uint4*>(row + (size_t)j * (CV * 16));
+            float v[8];
+            Vec8<bf16>::unpack(u, v);
+#pragma unroll
+            for (int t = 0; t < TX; ++t) {
+              const int kx = j - t * S;
+              if (kx >= 0 && kx <= 2) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) acc[t][e] = fmaf(v[e], wr[ky * 3 + kx][e], acc[t][e]);
+              }
+            }
+          }
+        }
+        bf16* op = out + (((size_t)b * p.Ho + oy) * p.Wo + ox0) * p.C + c0;
+#pragma unroll
+        for (int t = 0; t < TX; ++t) {
+          if (ox0 + t < p.Wo) {
+            if (p.relu) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) acc[t][e] = fmaxf(acc[t][e], 0.f);
+            }
+            Vec8<bf16>::store(op + (size_t)t * p.C, acc[t]);
+          }
+        }
+      }
+    }
+    __syncthreads();  // everyone is done reading this stage
+    if (tid == 0) {
+      const long long next = tile + 2LL * gridDim.x;
+      if (next < num_tiles) issue(next, stage);
+    }
+    stage ^= 1;
+  }
+}
+
+// 4-D NHWC tensor map {C, W, H, B}, box {cv*8, twi, thi, 1}, no swizzle, zero OOB fill.
+inline bool make_tmap_nhwc(tc::EncodeTiledFn fn, CUtensorMap* out, const void* ptr, int B, int H, int W, int C, int cv, int twi, int thi) {
+  const cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  const cuuint64_t gstride[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  const cuuint32_t box[4] = {(cuuint32_t)(cv * 8), (cuuint32_t)twi, (cuuint32_t)thi, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+}  // namespace dw
+}  // namespace spef

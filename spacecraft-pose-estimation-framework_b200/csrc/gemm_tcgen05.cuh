@@ -6,7 +6,7 @@
 //   warp 1   MMA issuer        one thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=block_n, K=16),
 //                              accumulators in TMEM (2 stages x block_n columns), tcgen05.commit -> mbarriers
 //   warp 2   TMEM allocator
-//   warps 4-7 epilogue         tcgen05.ld 32x32b -> +bias -> ReLU -> +residual -> bf16 -> swizzled smem -> TMA store
+//   warps 4.. epilogue (NG groups of 4 warps)  tcgen05.ld 32x32b -> +bias -> ReLU -> +residual -> bf16 -> swizzled smem -> TMA store
 // K is tiled in 64-element (128-byte) chunks; K tails (16, 24, 32, 96, 144, 160) and M/N tails rely on TMA
 // out-of-bounds zero fill on loads and clipping on stores, so no layer needs padding in HBM.
 // Reference semantics: src/modeling/common/pytorch_layers.py:78-79,85-86,93-98; mobilenet_v2.py:264; ursonet.py:31-32.
@@ -20,8 +20,8 @@ namespace tc {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;                       // bf16 elements = 128 bytes = one swizzle row
 constexpr int A_STAGE_BYTES = BLOCK_M * 128;      // 16 KB
-constexpr int STAGING_BYTES = BLOCK_M * 128;      // one 128-row x 128-byte output box
-constexpr int NUM_THREADS = 256;
+constexpr int STAGING_PITCH = 144;                // copy-out mode: 128-byte box row + 16-byte pad (conflict-free)
+constexpr int STAGING_BYTES = BLOCK_M * STAGING_PITCH;  // 18 KB (multiple of 1024); TMA-store mode uses the first 16 KB
 constexpr int TMEM_COLS = 512;
 constexpr int MAX_STAGES = 8;
 
@@ -32,6 +32,10 @@ struct GemmParams {
   int block_n;         // MMA N (multiple of 16, <= 256; multiple of 64 when N > block_n)
   int num_stages;      // smem pipeline depth
   int relu;
+  int store_mode;      // 0: padded smem staging + coalesced st.global by the epilogue threads; 1: swizzled staging + TMA store
+  void* out;           // D (copy-out mode)
+  int ldd;             // row pitch of D in elements
+  long long* trace;    // debug: clock64 timestamps of CTA 0 (nullptr in production)
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
@@ -108,6 +112,19 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ float4 lds_f4(uint32_t saddr) {
+  float4 r;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(saddr));
+  return r;
+}
+__device__ __forceinline__ uint4 lds_u4(uint32_t saddr) {
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(saddr));
+  return r;
+}
+__device__ __forceinline__ void sts_u4(uint32_t saddr, const uint4& v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // UMMA shared-memory descriptor, K-major operand, SWIZZLE_128B: rows of 128 B, 8-row groups 1024 B apart.
@@ -130,8 +147,8 @@ __host__ __device__ inline uint32_t make_idesc_bf16(int m, int n) {
 // ---- shared-memory plan (host and device agree through these helpers) -------------------------------
 __host__ __device__ inline int stage_bytes(int block_n) { return A_STAGE_BYTES + block_n * 128; }
 __host__ __device__ inline int bias_floats(int N) { return ((N + 63) / 64) * 64 + 256; }
-inline size_t smem_bytes(int block_n, int num_stages, int N) {
-  return 1024 /*align slack*/ + (size_t)num_stages * stage_bytes(block_n) + 2 * STAGING_BYTES +
+inline size_t smem_bytes(int block_n, int num_stages, int N, int ng) {
+  return 1024 /*align slack*/ + (size_t)num_stages * stage_bytes(block_n) + (size_t)ng * 2 * STAGING_BYTES +
          (size_t)bias_floats(N) * 4 + 256 /*barriers + tmem ptr*/;
 }
 inline int pick_block_n(int N) {
@@ -144,14 +161,14 @@ inline int pick_block_n(int N) {
   }
   return best;
 }
-inline int pick_stages(int block_n, int N, size_t smem_limit) {
+inline int pick_stages(int block_n, int N, size_t smem_limit, int ng) {
   int s = MAX_STAGES;
-  while (s > 2 && smem_bytes(block_n, s, N) > smem_limit) --s;
+  while (s > 2 && smem_bytes(block_n, s, N, ng) > smem_limit) --s;
   return s;
 }
 
-template <bool OUT_F32>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+template <bool OUT_F32, int NG>
+__global__ void __launch_bounds__(128 + 128 * NG, 1)
 pw_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                        const __grid_constant__ CUtensorMap tmD, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -161,8 +178,8 @@ pw_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   const int nstages = p.num_stages;
   const int sbytes = stage_bytes(block_n);
   uint8_t* stage_base = smem;
-  uint8_t* staging = stage_base + (size_t)nstages * sbytes;  // 2 x 16 KB, 1024-aligned (sbytes % 1024 == 0)
-  float* bias_s = reinterpret_cast<float*>(staging + 2 * STAGING_BYTES);
+  uint8_t* staging = stage_base + (size_t)nstages * sbytes;  // NG x 2 x 16 KB, 1024-aligned (sbytes % 1024 == 0)
+  float* bias_s = reinterpret_cast<float*>(staging + (size_t)NG * 2 * STAGING_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + bias_floats(p.N));
   uint64_t* full_bar = bars;                       // [MAX_STAGES]
   uint64_t* empty_bar = bars + MAX_STAGES;         // [MAX_STAGES]
@@ -178,7 +195,7 @@ pw_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   const int k_chunks = (p.K + BLOCK_K - 1) / BLOCK_K;
 
   // ---- one-time setup ----
-  for (int i = threadIdx.x; i < bias_floats(p.N); i += NUM_THREADS) bias_s[i] = (i < p.N) ? p.bias[i] : 0.f;
+  for (int i = threadIdx.x; i < bias_floats(p.N); i += (int)blockDim.x) bias_s[i] = (i < p.N) ? p.bias[i] : 0.f;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmW);
@@ -191,7 +208,7 @@ pw_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&tmem_full_bar[i]), 1);
-      mbar_init(smem_u32(&tmem_empty_bar[i]), 4);  // one arrive per epilogue warp
+      mbar_init(smem_u32(&tmem_empty_bar[i]), 4 * NG);  // one arrive per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -236,6 +253,8 @@ pw_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         mbar_wait(smem_u32(&tmem_empty_bar[acc]), acc_phase ^ 1);
         tcgen05_fence_after();
+        const int lt = (tile - (int)blockIdx.x) / (int)gridDim.x;
+        if (p.trace && blockIdx.x == 0 && lt < 256) p.trace[lt * 8 + 0] = clock64();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);  // accumulator stages at columns 0 / 256
         for (int kc = 0; kc < k_chunks; ++kc) {
           mbar_wait(smem_u32(&full_bar[stage]), phase);
@@ -254,42 +273,75 @@ pw_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
         tcgen05_commit(smem_u32(&tmem_full_bar[acc]));  // accumulator complete -> epilogue
+        if (p.trace && blockIdx.x == 0 && lt < 256) p.trace[lt * 8 + 1] = clock64();
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
     __syncwarp();
   } else if (warp >= 4) {
-    // ===================== epilogue =====================
+    // ===================== epilogue: NG groups of 4 warps =====================
+    // Each group owns two staging boxes and a named barrier; 128-byte column boxes of the accumulator stream are
+    // dealt round-robin to the groups, so TMEM loads, the bias/ReLU/residual math, the smem staging and the TMA
+    // stores of different groups overlap (one epilogue warp per SM sub-partition cannot hide its own latencies).
     constexpr int COLS_PER_BOX = OUT_F32 ? 32 : 64;   // one 128-byte staging row
     const int q = warp & 3;                           // TMEM lane quarter this warp may access
+    const int grp = (warp - 4) >> 2;                  // epilogue group
     const int row = q * 32 + lane;                    // row of the 128-row tile == TMEM lane
-    const bool leader = (threadIdx.x == 128);
+    const bool leader = (q == 0 && lane == 0);
+    const uint32_t bar_id = 1 + grp;
+    uint8_t* my_staging = staging + (size_t)grp * 2 * STAGING_BYTES;
     int acc = 0;
     uint32_t acc_phase = 0;
     int buf = 0;
+    uint32_t box_counter = 0;                         // identical sequence in every group
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_idx = (tile / n_tiles) * BLOCK_M;
       const int n_idx = (tile % n_tiles) * block_n;
       mbar_wait(smem_u32(&tmem_full_bar[acc]), acc_phase);
       tcgen05_fence_after();
+      const int lt = (tile - (int)blockIdx.x) / (int)gridDim.x;
+      const bool tr = (p.trace != nullptr) && blockIdx.x == 0 && lt < 256 && leader && grp == 0;
+      if (tr) p.trace[lt * 8 + 2] = clock64();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256);
       const int m = m_idx + row;
-      for (int c0 = 0; c0 < block_n && n_idx + c0 < p.N; c0 += COLS_PER_BOX) {
-        // staging buffer `buf` is free once the TMA store issued two boxes ago has read it
-        if (leader) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        uint8_t* sb = staging + (size_t)buf * STAGING_BYTES + (size_t)row * 128;
+      for (int c0 = 0; c0 < block_n && n_idx + c0 < p.N; c0 += COLS_PER_BOX, ++box_counter) {
+        if ((int)(box_counter % NG) != grp) continue;
+        uint32_t v[COLS_PER_BOX];
+        {
+          uint32_t(&v0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[0]);
+          tmem_ld_32x32b_x32(t_row + (uint32_t)c0, v0);
+          if constexpr (!OUT_F32) {
+            uint32_t(&v1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[32]);
+            tmem_ld_32x32b_x32(t_row + (uint32_t)(c0 + 32), v1);
+          }
+        }
+        const bool tma_store = (p.store_mode != 0);
+        // TMA mode: staging buffer `buf` is free once the TMA store this group issued two boxes ago has read it.
+        // Copy-out mode: it is free because every thread passed the barrier of the previous box after finishing the
+        // copy-out of the box before that (program order), so no extra wait is needed.
+        if (tma_store && leader) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        tmem_ld_wait();
+        if (tr) p.trace[lt * 8 + 3] = clock64();
+        if (tma_store) asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        const uint32_t sbuf = smem_u32(my_staging + (size_t)buf * STAGING_BYTES);
+        const uint32_t sb = sbuf + (uint32_t)row * (tma_store ? 128u : (uint32_t)STAGING_PITCH);
+        const uint32_t swz = tma_store ? (uint32_t)(row & 7) : 0u;
+        const uint32_t bias_sa = smem_u32(bias_s + n_idx + c0);
 #pragma unroll
         for (int h = 0; h < COLS_PER_BOX / 32; ++h) {
           const int cc = c0 + h * 32;  // column offset inside the tile
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(t_row + (uint32_t)cc, v);
-          tmem_ld_wait();
           float f[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            f[j] = __uint_as_float(v[j]) + bias_s[n_idx + cc + j];
-            if (p.relu) f[j] = fmaxf(f[j], 0.f);
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 b4 = lds_f4(bias_sa + (uint32_t)(h * 32 + j4 * 4) * 4u);
+            f[j4 * 4 + 0] = __uint_as_float(v[h * 32 + j4 * 4 + 0]) + b4.x;
+            f[j4 * 4 + 1] = __uint_as_float(v[h * 32 + j4 * 4 + 1]) + b4.y;
+            f[j4 * 4 + 2] = __uint_as_float(v[h * 32 + j4 * 4 + 2]) + b4.z;
+            f[j4 * 4 + 3] = __uint_as_float(v[h * 32 + j4 * 4 + 3]) + b4.w;
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
           }
           if constexpr (!OUT_F32) {
             if (p.residual != nullptr && m < p.M) {
@@ -309,29 +361,54 @@ pw_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
               float t8[8];
 #pragma unroll
               for (int e = 0; e < 8; ++e) t8[e] = f[g * 8 + e];
-              const int chunk = h * 4 + g;  // 0..7 inside the 128-byte row
-              *reinterpret_cast<uint4*>(sb + ((chunk ^ (row & 7)) << 4)) = Vec8<bf16>::pack(t8);
+              const uint32_t chunk = (uint32_t)(h * 4 + g);  // 0..7 inside the 128-byte row
+              sts_u4(sb + ((chunk ^ swz) << 4), Vec8<bf16>::pack(t8));
             }
           } else {
 #pragma unroll
             for (int g = 0; g < 8; ++g) {  // eight 16-byte chunks = 32 f32 columns
-              const float4 o = make_float4(f[g * 4], f[g * 4 + 1], f[g * 4 + 2], f[g * 4 + 3]);
-              *reinterpret_cast<float4*>(sb + ((g ^ (row & 7)) << 4)) = o;
+              uint4 o;
+              o.x = __float_as_uint(f[g * 4]); o.y = __float_as_uint(f[g * 4 + 1]);
+              o.z = __float_as_uint(f[g * 4 + 2]); o.w = __float_as_uint(f[g * 4 + 3]);
+              sts_u4(sb + (((uint32_t)g ^ swz) << 4), o);
             }
           }
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to TMA
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (leader) {
-          tma_store_2d(&tmD, smem_u32(staging + (size_t)buf * STAGING_BYTES), n_idx + c0, m_idx);
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        if (tr) p.trace[lt * 8 + 4] = clock64();  // math + STS done
+        if (tma_store) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to TMA
+          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+          if (leader) {
+            tma_store_2d(&tmD, sbuf, n_idx + c0, m_idx);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        } else {
+          // coalesced copy-out: 8 consecutive threads write one 128-byte row segment of D
+          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+          if (tr) p.trace[lt * 8 + 5] = clock64();  // barrier passed
+          constexpr int ELEMS_PER_PIECE = OUT_F32 ? 4 : 8;
+          constexpr int ESZ = OUT_F32 ? 4 : 2;
+          const int tg = (int)threadIdx.x - 128 - grp * 128;  // 0..127 inside the group
+          uint8_t* outb = reinterpret_cast<uint8_t*>(p.out);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int i = tg + k * 128;
+            const int r = i >> 3, pc = i & 7;
+            const int gm = m_idx + r, gcol = n_idx + c0 + pc * ELEMS_PER_PIECE;
+            if (gm < p.M && gcol < p.N) {
+              const uint4 val = lds_u4(sbuf + (uint32_t)(r * STAGING_PITCH + pc * 16));
+              *reinterpret_cast<uint4*>(outb + ((size_t)gm * p.ldd + gcol) * ESZ) = val;
+            }
+          }
         }
+        if (tr) p.trace[lt * 8 + 6] = clock64();  // copy-out / store issue done
         buf ^= 1;
       }
-      // all tcgen05.ld of this accumulator have completed (wait::ld above): hand TMEM back to the MMA warp
+      // all tcgen05.ld of this warp on this accumulator have completed (wait::ld above): hand TMEM back
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
+      if (tr) p.trace[lt * 8 + 7] = clock64();
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");

@@ -1,0 +1,362 @@
+// Pointwise 1x1 conv / Linear on tcgen05, second-generation pipeline (see gemm_tcgen05.cuh for the operand layouts).
+//
+// What the clock64 traces of v1 on B200 showed (profiles/r01_gemm_trace.txt):
+//   * every mbarrier hand-off between roles costs 300-1000 cycles (MMA commit -> epilogue wake-up ~1000, epilogue
+//     release -> MMA wake-up ~700), so with two TMEM accumulator stages the MMA <-> epilogue round trip (~2900 cycles)
+//     caps the kernel at two tiles per round trip no matter how fast the epilogue is;
+//   * per 128x64 output box the epilogue spends ~150-270 cycles in tcgen05.ld, ~500 in FP32 math + staging and ~850 in
+//     coalesced st.global, serialised in the same four warps; a TMA store of the box keeps the TMA unit busy for
+//     ~2000 cycles (16 cycles per 128-byte row) and is no faster.
+// v2 therefore
+//   * uses up to 8 accumulator stages (512 TMEM columns / 64, 128 or 256 columns per stage) so that 4-8 tiles are in
+//     flight across the MMA <-> drain hand-off,
+//   * splits the epilogue into "drain" warps (tcgen05.ld -> packed f32x2 bias add -> cvt.bf16x2 -> packed bf16x2 ReLU,
+//     or the f32 residual add -> padded smem staging; NDG groups of 4 warps take boxes round-robin and hand the TMEM
+//     stage back right after their last tcgen05.ld) and "store" warps (staging ring -> 16-byte coalesced st.global,
+//     8 lanes = one 128-byte row segment), connected by a ring of staging buffers,
+// so the store stream of box i overlaps the drain of box i+1 and the MMAs of the following tiles.
+#pragma once
+#include "gemm_tcgen05.cuh"
+
+namespace spef {
+namespace tc {
+
+constexpr int V2_RING = 4;        // staging buffers between drain and store warps
+constexpr int V2_MAX_ACC = 8;     // TMEM accumulator stages
+
+__host__ __device__ inline int acc_stride_cols(int block_n) { return block_n <= 64 ? 64 : (block_n <= 128 ? 128 : 256); }
+
+constexpr int V2_W_RESIDENT_MAX = 80 * 1024;  // weights stay in shared memory for the whole kernel when they fit in this
+
+// bytes of the complete (all n-tiles, all K chunks) weight matrix as 128B-swizzled smem tiles
+__host__ __device__ inline int w_region_bytes(int N, int K, int block_n) {
+  return ((N + block_n - 1) / block_n) * ((K + BLOCK_K - 1) / BLOCK_K) * block_n * 128;
+}
+__host__ __device__ inline bool w_is_resident(int N, int K, int block_n) { return w_region_bytes(N, K, block_n) <= V2_W_RESIDENT_MAX; }
+// per-stage bytes: activations only when the weights are resident
+__host__ __device__ inline int stage_bytes_v2(int N, int K, int block_n) {
+  return w_is_resident(N, K, block_n) ? A_STAGE_BYTES : stage_bytes(block_n);
+}
+inline size_t smem_bytes_v2(int block_n, int num_stages, int N, int K) {
+  return 1024 + (w_is_resident(N, K, block_n) ? (size_t)w_region_bytes(N, K, block_n) : 0) +
+         (size_t)num_stages * stage_bytes_v2(N, K, block_n) + (size_t)V2_RING * STAGING_BYTES + (size_t)bias_floats(N) * 4 + 512;
+}
+inline int pick_stages_v2(int block_n, int N, int K, size_t smem_limit) {
+  int s = MAX_STAGES;
+  while (s > 2 && smem_bytes_v2(block_n, s, N, K) > smem_limit) --s;
+  return s;
+}
+
+__device__ __forceinline__ uint64_t pack_f32x2(uint32_t lo, uint32_t hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// two f32 (packed in a b64) -> bf16x2 (low half = first element)
+__device__ __forceinline__ uint32_t cvt_bf16x2(uint64_t v) {
+  uint32_t lo, hi, r;
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(__uint_as_float(hi)), "f"(__uint_as_float(lo)));
+  return r;
+}
+__device__ __forceinline__ uint32_t relu_bf16x2(uint32_t v) {
+  uint32_t r;
+  asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(0u));
+  return r;
+}
+
+// Thread layout: warps 0-3 control (TMA, MMA, TMEM alloc, spare), warps 4 .. 4+4*NDG-1 drain, then NSW store warps.
+template <bool OUT_F32, int NDG, int NSW>
+__global__ void __launch_bounds__(128 + 128 * NDG + 32 * NSW, 1)
+pw_gemm_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int block_n = p.block_n;
+  const int nstages = p.num_stages;
+  const bool w_resident = w_is_resident(p.N, p.K, block_n);
+  const int sbytes = stage_bytes_v2(p.N, p.K, block_n);
+  const int acc_stride = acc_stride_cols(block_n);
+  const int acc_stages = min(V2_MAX_ACC, TMEM_COLS / acc_stride);
+  uint8_t* w_region = smem;                                     // resident weights: [n_tile][k_chunk][block_n rows x 128 B]
+  uint8_t* stage_base = smem + (w_resident ? w_region_bytes(p.N, p.K, block_n) : 0);
+  uint8_t* staging = stage_base + (size_t)nstages * sbytes;
+  float* bias_s = reinterpret_cast<float*>(staging + (size_t)V2_RING * STAGING_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + bias_floats(p.N));
+  uint64_t* full_bar = bars;                                   // [MAX_STAGES]  TMA -> MMA
+  uint64_t* empty_bar = full_bar + MAX_STAGES;                 // [MAX_STAGES]  MMA -> TMA
+  uint64_t* tmem_full_bar = empty_bar + MAX_STAGES;            // [V2_MAX_ACC]  MMA -> drain
+  uint64_t* tmem_empty_bar = tmem_full_bar + V2_MAX_ACC;       // [V2_MAX_ACC]  drain -> MMA
+  uint64_t* sfull_bar = tmem_empty_bar + V2_MAX_ACC;           // [V2_RING]     drain -> store
+  uint64_t* sempty_bar = sfull_bar + V2_RING;                  // [V2_RING]     store -> drain
+  uint64_t* w_bar = sempty_bar + V2_RING;                      // [1]           resident weights landed
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(w_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
+  const int n_tiles = (p.N + block_n - 1) / block_n;
+  const int num_tiles = m_tiles * n_tiles;
+  const int k_chunks = (p.K + BLOCK_K - 1) / BLOCK_K;
+  constexpr int COLS_PER_BOX = OUT_F32 ? 32 : 64;  // one 128-byte staging row
+  constexpr int FIRST_STORE_WARP = 4 + 4 * NDG;
+
+  for (int i = threadIdx.x; i < bias_floats(p.N); i += (int)blockDim.x) bias_s[i] = (i < p.N) ? p.bias[i] : 0.f;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmW);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < nstages; ++i) {
+      mbar_init(smem_u32(&full_bar[i]), 1);
+      mbar_init(smem_u32(&empty_bar[i]), 1);
+    }
+    for (int i = 0; i < V2_MAX_ACC; ++i) {
+      mbar_init(smem_u32(&tmem_full_bar[i]), 1);
+      mbar_init(smem_u32(&tmem_empty_bar[i]), 4 * NDG);   // one arrive per drain warp
+    }
+    for (int i = 0; i < V2_RING; ++i) {
+      mbar_init(smem_u32(&sfull_bar[i]), 4);              // the four warps of the group that filled the slot
+      mbar_init(smem_u32(&sempty_bar[i]), NSW);           // one arrive per store warp
+    }
+    mbar_init(smem_u32(w_bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_s)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_s;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx_bytes = (uint32_t)sbytes;
+      int tm = (int)blockIdx.x / n_tiles, tn = (int)blockIdx.x % n_tiles;
+      const int w_tile_bytes = block_n * 128;
+      if (w_resident) {  // the whole weight matrix is fetched once per CTA and stays in shared memory
+        const uint32_t wb = smem_u32(w_bar);
+        mbar_arrive_expect_tx(wb, (uint32_t)w_region_bytes(p.N, p.K, block_n));
+        for (int j = 0; j < n_tiles; ++j)
+          for (int kc = 0; kc < k_chunks; ++kc)
+            tma_load_2d(smem_u32(w_region + (size_t)(j * k_chunks + kc) * w_tile_bytes), &tmW, kc * BLOCK_K, j * block_n, wb);
+      }
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_idx = tm * BLOCK_M, n_idx = tn * block_n;
+        for (int kc = 0; kc < k_chunks; ++kc) {
+          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+          const uint32_t fb = smem_u32(&full_bar[stage]);
+          mbar_arrive_expect_tx(fb, tx_bytes);
+          uint8_t* sa = stage_base + (size_t)stage * sbytes;
+          tma_load_2d(smem_u32(sa), &tmA, kc * BLOCK_K, m_idx, fb);
+          if (!w_resident) tma_load_2d(smem_u32(sa + A_STAGE_BYTES), &tmW, kc * BLOCK_K, n_idx, fb);
+          if (++stage == nstages) { stage = 0; phase ^= 1; }
+        }
+        if (n_tiles == 1) { tm += gridDim.x; } else { const int t2 = tile + (int)gridDim.x; tm = t2 / n_tiles; tn = t2 % n_tiles; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(BLOCK_M, block_n);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      int tn = (int)blockIdx.x % n_tiles;
+      if (w_resident) mbar_wait(smem_u32(w_bar), 0);
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(smem_u32(&tmem_empty_bar[acc]), acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * acc_stride);
+        for (int kc = 0; kc < k_chunks; ++kc) {
+          mbar_wait(smem_u32(&full_bar[stage]), phase);
+          tcgen05_fence_after();
+          uint8_t* sa = stage_base + (size_t)stage * sbytes;
+          const uint64_t a_desc = make_smem_desc_sw128(smem_u32(sa));
+          const uint64_t b_desc = make_smem_desc_sw128(w_resident ? smem_u32(w_region + (size_t)(tn * k_chunks + kc) * (block_n * 128))
+                                                                  : smem_u32(sa + A_STAGE_BYTES));
+          const int k_rem = p.K - kc * BLOCK_K;
+          const int ksteps = k_rem >= BLOCK_K ? 4 : (k_rem + 15) / 16;
+          for (int k = 0; k < ksteps; ++k)
+            tcgen05_mma_bf16(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kc > 0 || k > 0) ? 1u : 0u);
+          tcgen05_commit(smem_u32(&empty_bar[stage]));
+          if (++stage == nstages) { stage = 0; phase ^= 1; }
+        }
+        tcgen05_commit(smem_u32(&tmem_full_bar[acc]));
+        if (++acc == acc_stages) { acc = 0; acc_phase ^= 1; }
+        if (n_tiles > 1) tn = (tile + (int)gridDim.x) % n_tiles;
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4 && warp < FIRST_STORE_WARP) {
+    // ===================== drain warps: TMEM -> registers -> bf16 -> staging ring =====================
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int grp = (warp - 4) >> 2;        // drain group
+    const int row = q * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    uint32_t box = 0;                       // global box counter: identical sequence in every drain / store warp
+    int tm = (int)blockIdx.x / n_tiles, tn = (int)blockIdx.x % n_tiles;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_idx = tm * BLOCK_M, n_idx = tn * block_n;
+      const int m = m_idx + row;
+      const int ncols = min(block_n, p.N - n_idx);
+      const int nboxes = (ncols + COLS_PER_BOX - 1) / COLS_PER_BOX;
+      // index of the last box of this tile that belongs to this group (-1: none)
+      int last_mine = -1;
+      for (int b = nboxes - 1; b >= 0; --b) {
+        if ((int)((box + (uint32_t)b) % NDG) == grp) { last_mine = b; break; }
+      }
+      mbar_wait(smem_u32(&tmem_full_bar[acc]), acc_phase);
+      tcgen05_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * acc_stride);
+      if (last_mine < 0) {
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
+      }
+      for (int b = 0; b < nboxes; ++b, ++box) {
+        if ((int)(box % NDG) != grp) continue;
+        const int c0 = b * COLS_PER_BOX;
+        const int slot = (int)(box % V2_RING);
+        const uint32_t ring_phase = (box / V2_RING) & 1u;
+        uint32_t v[COLS_PER_BOX];
+        {
+          uint32_t(&v0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[0]);
+          tmem_ld_32x32b_x32(t_row + (uint32_t)c0, v0);
+          if constexpr (!OUT_F32) {
+            uint32_t(&v1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[32]);
+            tmem_ld_32x32b_x32(t_row + (uint32_t)(c0 + 32), v1);
+          }
+        }
+        mbar_wait(smem_u32(&sempty_bar[slot]), ring_phase ^ 1);  // staging slot drained by the store warps
+        tmem_ld_wait();
+        if (b == last_mine) {
+          // every tcgen05.ld of this warp on this accumulator has completed -> hand the TMEM stage back now
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
+        }
+        const uint32_t sb = smem_u32(staging + (size_t)slot * STAGING_BYTES) + (uint32_t)row * (uint32_t)STAGING_PITCH;
+        const uint32_t bias_sa = smem_u32(bias_s + n_idx + c0);
+        if constexpr (OUT_F32) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const float4 b4 = lds_f4(bias_sa + (uint32_t)g * 16u);
+            uint4 o;
+            o.x = __float_as_uint(__uint_as_float(v[g * 4 + 0]) + b4.x);
+            o.y = __float_as_uint(__uint_as_float(v[g * 4 + 1]) + b4.y);
+            o.z = __float_as_uint(__uint_as_float(v[g * 4 + 2]) + b4.z);
+            o.w = __float_as_uint(__uint_as_float(v[g * 4 + 3]) + b4.w);
+            sts_u4(sb + (uint32_t)g * 16u, o);
+          }
+        } else if (p.residual == nullptr) {
+          // packed path: f32x2 bias add, cvt to bf16x2, ReLU on the packed pair (round(max(x,0)) == max(round(x),0))
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {  // eight 16-byte pieces = 64 bf16 columns
+            const float4 b0 = lds_f4(bias_sa + (uint32_t)g * 32u);
+            const float4 b1 = lds_f4(bias_sa + (uint32_t)g * 32u + 16u);
+            uint32_t o[4];
+            o[0] = cvt_bf16x2(add_f32x2(pack_f32x2(v[g * 8 + 0], v[g * 8 + 1]), pack_f32x2(__float_as_uint(b0.x), __float_as_uint(b0.y))));
+            o[1] = cvt_bf16x2(add_f32x2(pack_f32x2(v[g * 8 + 2], v[g * 8 + 3]), pack_f32x2(__float_as_uint(b0.z), __float_as_uint(b0.w))));
+            o[2] = cvt_bf16x2(add_f32x2(pack_f32x2(v[g * 8 + 4], v[g * 8 + 5]), pack_f32x2(__float_as_uint(b1.x), __float_as_uint(b1.y))));
+            o[3] = cvt_bf16x2(add_f32x2(pack_f32x2(v[g * 8 + 6], v[g * 8 + 7]), pack_f32x2(__float_as_uint(b1.z), __float_as_uint(b1.w))));
+            if (p.relu) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) o[e] = relu_bf16x2(o[e]);
+            }
+            sts_u4(sb + (uint32_t)g * 16u, make_uint4(o[0], o[1], o[2], o[3]));
+          }
+        } else {
+          // linear bottleneck with skip connection: y = x + (acc + bias), one rounding (pytorch_layers.py:93-98)
+          const bf16* rp = p.residual + (size_t)m * p.N + n_idx + c0;
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const float4 b0 = lds_f4(bias_sa + (uint32_t)g * 32u);
+            const float4 b1 = lds_f4(bias_sa + (uint32_t)g * 32u + 16u);
+            float f[8] = {__uint_as_float(v[g * 8 + 0]) + b0.x, __uint_as_float(v[g * 8 + 1]) + b0.y,
+                          __uint_as_float(v[g * 8 + 2]) + b0.z, __uint_as_float(v[g * 8 + 3]) + b0.w,
+                          __uint_as_float(v[g * 8 + 4]) + b1.x, __uint_as_float(v[g * 8 + 5]) + b1.y,
+                          __uint_as_float(v[g * 8 + 6]) + b1.z, __uint_as_float(v[g * 8 + 7]) + b1.w};
+            if (p.relu) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
+            }
+            if (m < p.M && n_idx + c0 + g * 8 < p.N) {
+              float r[8];
+              Vec8<bf16>::load(rp + g * 8, r);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] += r[e];
+            }
+            sts_u4(sb + (uint32_t)g * 16u, Vec8<bf16>::pack(f));
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&sfull_bar[slot]));
+      }
+      if (++acc == acc_stages) { acc = 0; acc_phase ^= 1; }
+      if (n_tiles == 1) { tm += gridDim.x; } else { const int t2 = tile + (int)gridDim.x; tm = t2 / n_tiles; tn = t2 % n_tiles; }
+    }
+  } else if (warp >= FIRST_STORE_WARP) {
+    // ===================== store warps: staging ring -> coalesced st.global =====================
+    constexpr int ELEMS_PER_PIECE = OUT_F32 ? 4 : 8;
+    constexpr int ESZ = OUT_F32 ? 4 : 2;
+    constexpr int NST = 32 * NSW;
+    const int ts = (int)threadIdx.x - 32 * FIRST_STORE_WARP;
+    const int pc = ts & 7;            // 16-byte piece inside the 128-byte row segment (fixed per thread)
+    const int r0 = ts >> 3;           // first row handled by this thread; then += NST / 8
+    uint8_t* outb = reinterpret_cast<uint8_t*>(p.out);
+    uint32_t box = 0;
+    int tm = (int)blockIdx.x / n_tiles, tn = (int)blockIdx.x % n_tiles;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_idx = tm * BLOCK_M, n_idx = tn * block_n;
+      const int ncols = min(block_n, p.N - n_idx);
+      const int rows_here = min(BLOCK_M, p.M - m_idx);
+      for (int c0 = 0; c0 < ncols; c0 += COLS_PER_BOX, ++box) {
+        const int slot = (int)(box % V2_RING);
+        const uint32_t ring_phase = (box / V2_RING) & 1u;
+        const int gcol = n_idx + c0 + pc * ELEMS_PER_PIECE;
+        const bool col_ok = gcol < p.N;
+        mbar_wait(smem_u32(&sfull_bar[slot]), ring_phase);
+        const uint32_t sbuf = smem_u32(staging + (size_t)slot * STAGING_BYTES) + (uint32_t)(pc * 16);
+        uint8_t* gp = outb + ((size_t)(m_idx + r0) * p.ldd + gcol) * ESZ;
+        const size_t gstep = (size_t)(NST / 8) * p.ldd * ESZ;
+        if (col_ok) {
+#pragma unroll
+          for (int k = 0; k < 1024 / NST; ++k) {
+            const int r = r0 + k * (NST / 8);
+            if (r < rows_here) {
+              const uint4 val = lds_u4(sbuf + (uint32_t)(r * STAGING_PITCH));
+              *reinterpret_cast<uint4*>(gp + (size_t)k * gstep) = val;
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&sempty_bar[slot]));
+      }
+      if (n_tiles == 1) { tm += gridDim.x; } else { const int t2 = tile + (int)gridDim.x; tm = t2 / n_tiles; tn = t2 % n_tiles; }
+    }
+  }
+
+  // ---- teardown ----
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+}  // namespace tc
+}  // namespace spef

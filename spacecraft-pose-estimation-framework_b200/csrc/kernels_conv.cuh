@@ -10,9 +10,9 @@ namespace spef {
 
 // --------------------------------------------------------------------------------------------------
 // Stem: ConvBnAct(3->32, k3, s2, p1) (mobilenet_v2.py:252-254).  Reads the reference's own tensor
-// contract ([B,3,H,W] f32 NCHW), writes NHWC.  4 threads per output pixel, 8 output channels each:
-// the 27 taps are shared through L1, the 64-byte (bf16) pixel is written by 4 adjacent lanes so a
-// warp writes 512 contiguous bytes.  Weights [27][32] + bias in shared memory.
+// contract ([B,3,H,W] f32 NCHW), writes NHWC.  4 threads per pair of adjacent output pixels, 8 output channels each: the
+// 45 taps of the pair are loaded up front (memory-level parallelism), shared between the 4 lanes through L1, and
+// each 64-byte (bf16) pixel is written by 4 adjacent lanes.  Weights [27][32] + bias in shared memory.
 // --------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256) stem_conv3x3s2_kernel(const float* __restrict__ img, const float* __restrict__ w,
@@ -24,43 +24,69 @@ __global__ void __launch_bounds__(256) stem_conv3x3s2_kernel(const float* __rest
   if (threadIdx.x < 32) bs[threadIdx.x] = bias[threadIdx.x];
   __syncthreads();
 
-  const long long total = (long long)B * Ho * Wo * 4;
+  // one thread = 2 horizontally adjacent output pixels x 8 output channels
+  const int Wp = (Wo + 1) >> 1;
+  const long long total = (long long)B * Ho * Wp * 4;
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (tid >= total) return;
   const int cg = (int)(tid & 3);
   long long p = tid >> 2;
-  const int ox = (int)(p % Wo); p /= Wo;
+  const int oxp = (int)(p % Wp); p /= Wp;
   const int oy = (int)(p % Ho);
   const int b = (int)(p / Ho);
+  const int ox = oxp * 2;
 
-  float acc[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = bs[cg * 8 + j];
-
+  // all 45 taps are loaded up front (branch-free: clamped address, zero mask) so the loads overlap
+  float in[3][3][5];
   const float* ib = img + (size_t)b * 3 * H * W;
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    const int iy = oy * 2 - 1 + ky;
+    const bool yok = (iy >= 0) && (iy < H);
+    const int iyc = min(max(iy, 0), H - 1);
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      const int ix = ox * 2 - 1 + j;
+      const bool ok = yok && (ix >= 0) && (ix < W);
+      const int ixc = min(max(ix, 0), W - 1);
+#pragma unroll
+      for (int ci = 0; ci < 3; ++ci) {
+        const float v = __ldg(ib + ((size_t)ci * H + iyc) * W + ixc);
+        in[ci][ky][j] = ok ? v : 0.f;
+      }
+    }
+  }
+  float acc[2][8];
+#pragma unroll
+  for (int t = 0; t < 2; ++t)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[t][j] = bs[cg * 8 + j];
 #pragma unroll
   for (int ci = 0; ci < 3; ++ci) {
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
-      const int iy = oy * 2 - 1 + ky;
-      const bool yok = (iy >= 0) && (iy < H);
 #pragma unroll
       for (int kx = 0; kx < 3; ++kx) {
-        const int ix = ox * 2 - 1 + kx;
-        float v = 0.f;
-        if (yok && ix >= 0 && ix < W) v = __ldg(ib + ((size_t)ci * H + iy) * W + ix);
         const float4* wp = reinterpret_cast<const float4*>(ws + ((ci * 3 + ky) * 3 + kx) * 32 + cg * 8);
         const float4 w0 = wp[0], w1 = wp[1];
-        acc[0] = fmaf(v, w0.x, acc[0]); acc[1] = fmaf(v, w0.y, acc[1]);
-        acc[2] = fmaf(v, w0.z, acc[2]); acc[3] = fmaf(v, w0.w, acc[3]);
-        acc[4] = fmaf(v, w1.x, acc[4]); acc[5] = fmaf(v, w1.y, acc[5]);
-        acc[6] = fmaf(v, w1.z, acc[6]); acc[7] = fmaf(v, w1.w, acc[7]);
+        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const float v = in[ci][ky][kx + 2 * t];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[t][e] = fmaf(v, wv[e], acc[t][e]);
+        }
       }
     }
   }
 #pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j], 0.f);
-  Vec8<T>::store(out + (((size_t)b * Ho + oy) * Wo + ox) * 32 + cg * 8, acc);
+  for (int t = 0; t < 2; ++t) {
+    if (ox + t < Wo) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[t][j] = fmaxf(acc[t][j], 0.f);
+      Vec8<T>::store(out + (((size_t)b * Ho + oy) * Wo + ox + t) * 32 + cg * 8, acc[t]);
+    }
+  }
 }
 
 // --------------------------------------------------------------------------------------------------

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <cmath>
@@ -15,6 +16,8 @@
 #include "../../include/spef_b200.h"
 #include "common.cuh"
 #include "gemm_tcgen05.cuh"
+#include "gemm_tcgen05_v2.cuh"
+#include "dwconv_tma.cuh"
 #include "kernels_conv.cuh"
 #include "kernels_post.cuh"
 
@@ -45,6 +48,10 @@ struct Layer {
   size_t smem = 0;
   CUtensorMap tmA, tmW, tmD;
   bool tmW_ready = false;
+  // TMA depthwise plan
+  int dw_cv = 0;
+  dw::DwParams dwp;
+  CUtensorMap tmX;
 };
 
 const double kBnEps = 1e-5;  // torch.nn.BatchNorm2d default (pytorch_layers.py:55-56)
@@ -60,6 +67,13 @@ struct spef_ctx {
   int num_sms = 148;
   size_t smem_optin = 0;
   tc::EncodeTiledFn encode = nullptr;
+  int gemm_ng = 2;  // epilogue groups of the tcgen05 GEMM (SPEF_GEMM_NG = 1 | 2)
+  long long* trace_dev = nullptr;  // SPEF_GEMM_TRACE=<layer index>: dump CTA-0 timestamps of that layer to stderr
+  int trace_layer = -1;
+  int gemm_impl = 2;   // 2: drain/store warp-specialised epilogue (default); 1: v1 epilogue (SPEF_GEMM_IMPL=1)
+  int gemm_nsw = 4;    // store warps of the v2 epilogue (SPEF_GEMM_NSW = 4 | 8; 8 only with one drain group)
+  int gemm_ndg = 2;    // drain groups of the v2 epilogue (SPEF_GEMM_NDG = 1 | 2)
+  int gemm_store = 0;  // 0 coalesced copy-out (default), 1 TMA store (SPEF_GEMM_STORE=tma)
   size_t esz = 2;
   // activations
   void* act[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -232,6 +246,12 @@ extern "C" int spef_create(spef_ctx** out, const spef_config* cfg) {
   ctx->num_sms = prop.multiProcessorCount;
   ctx->smem_optin = prop.sharedMemPerBlockOptin;
   ctx->esz = (cfg->precision == SPEF_BF16) ? 2 : 4;
+  if (const char* e4 = getenv("SPEF_GEMM_TRACE")) { ctx->trace_layer = atoi(e4); cudaMalloc((void**)&ctx->trace_dev, 256 * 8 * sizeof(long long)); }
+  if (const char* e5 = getenv("SPEF_GEMM_IMPL")) ctx->gemm_impl = (atoi(e5) == 1) ? 1 : 2;
+  if (const char* e7 = getenv("SPEF_GEMM_NDG")) ctx->gemm_ndg = (atoi(e7) == 1) ? 1 : 2;
+  if (const char* e6 = getenv("SPEF_GEMM_NSW")) ctx->gemm_nsw = (atoi(e6) == 8 && ctx->gemm_ndg == 1) ? 8 : 4;
+  if (const char* e3 = getenv("SPEF_GEMM_STORE")) ctx->gemm_store = (strcmp(e3, "tma") == 0) ? 1 : 0;
+  if (const char* e2 = getenv("SPEF_GEMM_NG")) { int v = atoi(e2); if (v == 1 || v == 2) ctx->gemm_ng = v; }
   build_layers(ctx);
 
   // cuTensorMapEncodeTiled through the runtime (no link-time dependency on libcuda)
@@ -412,15 +432,51 @@ extern "C" int spef_finalize_weights(spef_ctx* ctx) {
     }
     bias.resize(tc::bias_floats(l.n_pad), 0.f);
     if (!upload(&l.w_f32, packed) || !upload(&l.bias, bias)) return fail(ctx, SPEF_ERR_CUDA, "spef_finalize_weights: upload failed");
+    if (l.kind == K_DW) {  // TMA tile plan (BF16 path)
+      l.dw_cv = (l.cin % 64 == 0) ? 8 : ((l.cin % 48 == 0) ? 6 : 4);
+      dw::DwParams& d = l.dwp;
+      d.B = 0; d.H = l.hin; d.W = l.win; d.C = l.cin; d.Ho = l.hout; d.Wo = l.wout; d.relu = l.relu;
+      const int wo4 = ((l.wout + 3) / 4) * 4;
+      d.TH = (l.stride == 1) ? 8 : 4;
+      d.TW = (l.stride == 1) ? (wo4 < 32 ? wo4 : 32) : (wo4 < 16 ? wo4 : 16);
+      d.THI = (d.TH - 1) * l.stride + 3;
+      d.TWI = (d.TW - 1) * l.stride + 3;
+      d.tiles_y = cdiv(l.hout, d.TH);
+      d.tiles_x = cdiv(l.wout, d.TW);
+      d.nchunks = cdiv(l.cin, l.dw_cv * 8);
+    }
     if (l.kind == K_PW || l.kind == K_HEAD) {
       l.block_n = tc::pick_block_n(l.n_pad);
-      l.stages = tc::pick_stages(l.block_n, l.n_pad, ctx->smem_optin);
-      l.smem = tc::smem_bytes(l.block_n, l.stages, l.n_pad);
+      if (ctx->gemm_impl == 2) {
+        l.stages = tc::pick_stages_v2(l.block_n, l.n_pad, l.cin, ctx->smem_optin);
+        l.smem = tc::smem_bytes_v2(l.block_n, l.stages, l.n_pad, l.cin);
+      } else {
+        l.stages = tc::pick_stages(l.block_n, l.n_pad, ctx->smem_optin, ctx->gemm_ng);
+        l.smem = tc::smem_bytes(l.block_n, l.stages, l.n_pad, ctx->gemm_ng);
+      }
     }
   }
   if (use_bf16) {
-    CK(cudaFuncSetAttribute(tc::pw_gemm_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
-    CK(cudaFuncSetAttribute(tc::pw_gemm_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
+    const int so = (int)ctx->smem_optin;
+    CK(cudaFuncSetAttribute(tc::pw_gemm_tcgen05_v2_kernel<false, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, so));
+    CK(cudaFuncSetAttribute(tc::pw_gemm_tcgen05_v2_kernel<true, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, so));
+    CK(cudaFuncSetAttribute(tc::pw_gemm_tcgen05_v2_kernel<false, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, so));
+    CK(cudaFuncSetAttribute(tc::pw_gemm_tcgen05_v2_kernel<true, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, so));
+    CK(cudaFuncSetAttribute(tc::pw_gemm_tcgen05_v2_kernel<false, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, so));
+    CK(cudaFuncSetAttribute(tc::pw_gemm_tcgen05_v2_kernel<true, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, so));
+    CK(cudaFuncSetAttribute(tc::pw_gemm_tcgen05_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, so));
+    CK(cudaFuncSetAttribute(tc::pw_gemm_tcgen05_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, so));
+    CK(cudaFuncSetAttribute(tc::pw_gemm_tcgen05_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, so));
+    CK(cudaFuncSetAttribute(tc::pw_gemm_tcgen05_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, so));
+    CK(cudaFuncSetAttribute(tc::pw_gemm_tcgen05_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, so));
+    CK(cudaFuncSetAttribute(tc::pw_gemm_tcgen05_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, so));
+    const int dw_smem = 100 * 1024;
+    CK(cudaFuncSetAttribute(dw::dwconv3x3_tma_kernel<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem));
+    CK(cudaFuncSetAttribute(dw::dwconv3x3_tma_kernel<1, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem));
+    CK(cudaFuncSetAttribute(dw::dwconv3x3_tma_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem));
+    CK(cudaFuncSetAttribute(dw::dwconv3x3_tma_kernel<2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem));
+    CK(cudaFuncSetAttribute(dw::dwconv3x3_tma_kernel<2, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem));
+    CK(cudaFuncSetAttribute(dw::dwconv3x3_tma_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem));
   }
   ctx->host_tensors.clear();
   ctx->plan_batch = -1;
@@ -459,7 +515,7 @@ extern "C" int spef_set_pos_histogram(spef_ctx* ctx, const double* x, int32_t n)
 template <typename T>
 static int launch_cuda_core_layer(spef_ctx* ctx, const Layer& l, const void* in, const void* res, void* out, int B, cudaStream_t st) {
   if (l.kind == K_STEM) {
-    const long long total = (long long)B * l.hout * l.wout * 4;
+    const long long total = (long long)B * l.hout * ((l.wout + 1) / 2) * 4;
     stem_conv3x3s2_kernel<T><<<(unsigned)cdivll(total, 256), 256, 0, st>>>((const float*)in, l.w_f32, l.bias, (T*)out, B, l.hin, l.win, l.hout, l.wout);
     CK_LAUNCH("stem_conv3x3s2_kernel");
   } else if (l.kind == K_DW) {
@@ -489,6 +545,37 @@ static int launch_cuda_core_layer(spef_ctx* ctx, const Layer& l, const void* in,
   return SPEF_OK;
 }
 
+template <int S, int CV>
+static void launch_dw_inst(const CUtensorMap& tm, const Layer& l, bf16* out, int grid, size_t smem, cudaStream_t st) {
+  dw::dwconv3x3_tma_kernel<S, CV><<<grid, 32 * CV, smem, st>>>(tm, l.w_f32, l.bias, out, l.dwp);
+}
+
+static int launch_dw_tma_layer(spef_ctx* ctx, Layer& l, const void* in, void* out, int B, cudaStream_t st, bool cached_maps) {
+  CUtensorMap local;
+  CUtensorMap* tm = cached_maps ? &l.tmX : &local;
+  if (!cached_maps || ctx->plan_batch != B) {
+    if (!dw::make_tmap_nhwc(ctx->encode, tm, in, B, l.hin, l.win, l.cin, l.dw_cv, l.dwp.TWI, l.dwp.THI))
+      return fail(ctx, SPEF_ERR_CUDA, "cuTensorMapEncodeTiled(X) failed for %s", l.prefix.c_str());
+  }
+  l.dwp.B = B;
+  const long long tiles = (long long)B * l.dwp.tiles_y * l.dwp.tiles_x * l.dwp.nchunks;
+  const int per_sm = (l.dw_cv == 4) ? 4 : 2;
+  const int grid = (int)(tiles < (long long)per_sm * ctx->num_sms ? tiles : (long long)per_sm * ctx->num_sms);
+  const size_t smem = dw::smem_bytes(l.dwp, l.dw_cv);
+  bf16* o = (bf16*)out;
+  if (l.stride == 1) {
+    if (l.dw_cv == 8) launch_dw_inst<1, 8>(*tm, l, o, grid, smem, st);
+    else if (l.dw_cv == 6) launch_dw_inst<1, 6>(*tm, l, o, grid, smem, st);
+    else launch_dw_inst<1, 4>(*tm, l, o, grid, smem, st);
+  } else {
+    if (l.dw_cv == 8) launch_dw_inst<2, 8>(*tm, l, o, grid, smem, st);
+    else if (l.dw_cv == 6) launch_dw_inst<2, 6>(*tm, l, o, grid, smem, st);
+    else launch_dw_inst<2, 4>(*tm, l, o, grid, smem, st);
+  }
+  CK_LAUNCH("dwconv3x3_tma_kernel");
+  return SPEF_OK;
+}
+
 static int launch_tcgen05_layer(spef_ctx* ctx, Layer& l, const void* in, const void* res, void* out, int B, cudaStream_t st, bool cached_maps) {
   const int M = B * l.hout * l.wout, N = l.n_pad, K = l.cin;
   const bool f32out = (l.kind == K_HEAD);
@@ -505,17 +592,54 @@ static int launch_tcgen05_layer(spef_ctx* ctx, Layer& l, const void* in, const v
   }
   tc::GemmParams p;
   p.bias = l.bias; p.residual = (const bf16*)res; p.M = M; p.N = N; p.K = K; p.block_n = l.block_n; p.num_stages = l.stages; p.relu = l.relu;
+  p.store_mode = ctx->gemm_store; p.out = out; p.ldd = N;
+  const bool trace = ctx->trace_dev && (&l == &ctx->layers[ctx->trace_layer < (int)ctx->layers.size() && ctx->trace_layer >= 0 ? ctx->trace_layer : 0]) && ctx->trace_layer >= 0;
+  p.trace = (trace && ctx->gemm_impl == 1) ? ctx->trace_dev : nullptr;
+  if (trace) cudaMemsetAsync(ctx->trace_dev, 0, 256 * 8 * sizeof(long long), st);
   const int tiles = cdiv(M, tc::BLOCK_M) * cdiv(N, l.block_n);
   const int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
-  if (f32out) tc::pw_gemm_tcgen05_kernel<true><<<grid, tc::NUM_THREADS, l.smem, st>>>(*tA, l.tmW, *tD, p);
-  else tc::pw_gemm_tcgen05_kernel<false><<<grid, tc::NUM_THREADS, l.smem, st>>>(*tA, l.tmW, *tD, p);
+  const int ng = ctx->gemm_ng, nthr = 128 + 128 * ng;
+  if (ctx->gemm_impl == 2) {
+    const int nsw = ctx->gemm_nsw, ndg = ctx->gemm_ndg, nt2 = 128 + 128 * ndg + 32 * nsw;
+#define SPEF_V2_LAUNCH(F32, NDG_, NSW_) tc::pw_gemm_tcgen05_v2_kernel<F32, NDG_, NSW_><<<grid, nt2, l.smem, st>>>(*tA, l.tmW, p)
+    if (f32out) {
+      if (ndg == 2) SPEF_V2_LAUNCH(true, 2, 4); else if (nsw == 8) SPEF_V2_LAUNCH(true, 1, 8); else SPEF_V2_LAUNCH(true, 1, 4);
+    } else {
+      if (ndg == 2) SPEF_V2_LAUNCH(false, 2, 4); else if (nsw == 8) SPEF_V2_LAUNCH(false, 1, 8); else SPEF_V2_LAUNCH(false, 1, 4);
+    }
+#undef SPEF_V2_LAUNCH
+  } else if (f32out) {
+    if (ng == 1) tc::pw_gemm_tcgen05_kernel<true, 1><<<grid, nthr, l.smem, st>>>(*tA, l.tmW, *tD, p);
+    else if (ng == 2) tc::pw_gemm_tcgen05_kernel<true, 2><<<grid, nthr, l.smem, st>>>(*tA, l.tmW, *tD, p);
+    else tc::pw_gemm_tcgen05_kernel<true, 4><<<grid, nthr, l.smem, st>>>(*tA, l.tmW, *tD, p);
+  } else {
+    if (ng == 1) tc::pw_gemm_tcgen05_kernel<false, 1><<<grid, nthr, l.smem, st>>>(*tA, l.tmW, *tD, p);
+    else if (ng == 2) tc::pw_gemm_tcgen05_kernel<false, 2><<<grid, nthr, l.smem, st>>>(*tA, l.tmW, *tD, p);
+    else tc::pw_gemm_tcgen05_kernel<false, 4><<<grid, nthr, l.smem, st>>>(*tA, l.tmW, *tD, p);
+  }
   CK_LAUNCH("pw_gemm_tcgen05_kernel");
+  if (trace) {
+    static int dumped = 0;
+    if (dumped++ == 3) {  // 4th call: warmed up
+      std::vector<long long> h(256 * 8);
+      cudaStreamSynchronize(st);
+      cudaMemcpy(h.data(), ctx->trace_dev, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+      const long long t0 = h[0];
+      fprintf(stderr, "TRACE layer %s M=%d N=%d K=%d block_n=%d stages=%d (cycles rel. to first MMA start)\n tile: mma_start mma_commit | drain: tmem_full ld_done staged | store: sfull copied | mma: first smem stage ready (v2 layout; last box of the tile)\n", l.prefix.c_str(), M, N, K, l.block_n, l.stages);
+      for (int t = 0; t < 40; ++t) {
+        fprintf(stderr, "%3d:", t);
+        for (int j = 0; j < 8; ++j) fprintf(stderr, " %8lld", h[t * 8 + j] ? h[t * 8 + j] - t0 : -1);
+        fprintf(stderr, "\n");
+      }
+    }
+  }
   return SPEF_OK;
 }
 
 static int run_layer(spef_ctx* ctx, Layer& l, const void* in, const void* res, void* out, int B, cudaStream_t st, bool cached_maps) {
   const bool use_bf16 = ctx->cfg.precision == SPEF_BF16;
   if (use_bf16 && (l.kind == K_PW || l.kind == K_HEAD) && ctx->cfg.pw_impl == 0) return launch_tcgen05_layer(ctx, l, in, res, out, B, st, cached_maps);
+  if (use_bf16 && l.kind == K_DW && ctx->cfg.pw_impl == 0) return launch_dw_tma_layer(ctx, l, in, out, B, st, cached_maps);
   if (use_bf16) return launch_cuda_core_layer<bf16>(ctx, l, in, res, out, B, st);
   return launch_cuda_core_layer<float>(ctx, l, in, res, out, B, st);
 }
