@@ -54,7 +54,12 @@ dwconv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmX, const float* __res
   const int tasks = nxs * p.TH;            // (x strip, row) pairs per tile; each is done by CV threads
   const int task0 = tid / CV, task_step = NT / CV;
   const long long spatial_tiles = (long long)p.B * p.tiles_y * p.tiles_x;
-  const long long num_tiles = spatial_tiles * p.nchunks;
+  // Channel chunk fixed per CTA (weights stay in registers); CTAs b, b+1, ... b+nchunks-1 walk the same spatial tiles at
+  // the same time, so the partially used 128-byte lines of a pixel (CV*16 of C*2 bytes) are consumed out of L2 instead of
+  // being fetched from HBM once per chunk.  gridDim.x is a multiple of nchunks (host).
+  const int chunk = (int)(blockIdx.x % p.nchunks);
+  const long long sp0 = blockIdx.x / p.nchunks;
+  const long long sp_step = gridDim.x / p.nchunks;
 
   if (tid == 0) {
     tc::tma_prefetch_desc(&tmX);
@@ -64,9 +69,8 @@ dwconv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmX, const float* __res
   }
   __syncthreads();
 
-  auto issue = [&](long long tile, int stage) {
-    const int chunk = (int)(tile / spatial_tiles);
-    long long r = tile - (long long)chunk * spatial_tiles;
+  auto issue = [&](long long sp, int stage) {
+    long long r = sp;
     const int tx = (int)(r % p.tiles_x); r /= p.tiles_x;
     const int ty = (int)(r % p.tiles_y);
     const int b = (int)(r / p.tiles_y);
@@ -75,62 +79,73 @@ dwconv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmX, const float* __res
     tma_load_4d(tc::smem_u32(smem + (size_t)stage * sstride), &tmX, chunk * CV * 8, tx * p.TW * S - 1, ty * p.TH * S - 1, b, bar);
   };
 
-  long long tile = blockIdx.x;
+  long long sp = sp0;
   if (tid == 0) {
-    if (tile < num_tiles) issue(tile, 0);
-    if (tile + gridDim.x < num_tiles) issue(tile + gridDim.x, 1);
+    if (sp < spatial_tiles) issue(sp, 0);
+    if (sp + sp_step < spatial_tiles) issue(sp + sp_step, 1);
   }
 
-  float wr[9][8];
-  float bv[8];
-  int cur_chunk = -1;
+  uint64_t wr[9][4];   // folded weights of this thread's 8 channels as packed FP32 pairs (FFMA2 operands)
+  uint64_t bv[4];
+  const int c0 = chunk * CV * 8 + cv * 8;
+  const bool c_ok = c0 < p.C;
+  if (c_ok) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      float t8[8];
+      Vec8<float>::load(w + (size_t)k * p.C + c0, t8);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) wr[k][e] = f32x2(t8[2 * e], t8[2 * e + 1]);
+    }
+    float b8[8];
+    Vec8<float>::load(bias + c0, b8);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) bv[e] = f32x2(b8[2 * e], b8[2 * e + 1]);
+  }
   uint32_t phases = 0;  // bit s = parity of stage s
   int stage = 0;
-  for (; tile < num_tiles; tile += gridDim.x) {
-    const int chunk = (int)(tile / spatial_tiles);
-    long long r = tile - (long long)chunk * spatial_tiles;
+  for (; sp < spatial_tiles; sp += sp_step) {
+    long long r = sp;
     const int tx = (int)(r % p.tiles_x); r /= p.tiles_x;
     const int ty = (int)(r % p.tiles_y);
     const int b = (int)(r / p.tiles_y);
-    const int c0 = chunk * CV * 8 + cv * 8;
-    const bool c_ok = c0 < p.C;
-    if (chunk != cur_chunk) {  // tiles are chunk-major, so this happens ~nchunks times per CTA
-      cur_chunk = chunk;
-      if (c_ok) {
-#pragma unroll
-        for (int k = 0; k < 9; ++k) Vec8<float>::load(w + (size_t)k * p.C + c0, wr[k]);
-        Vec8<float>::load(bias + c0, bv);
-      }
-    }
     tc::mbar_wait(tc::smem_u32(&full_bar[stage]), (phases >> stage) & 1u);
     phases ^= 1u << stage;
     const uint8_t* tile_s = smem + (size_t)stage * sstride + cv * 16;
 
     if (c_ok) {
       for (int task = task0; task < tasks; task += task_step) {
-        const int xs = task % nxs, ry = task / nxs;
+        // S == 1 with 64/96-byte pixels: consecutive lanes groups take vertically adjacent rows and the host picks the
+        // box width so that the row pitch is 64 resp. 96 (mod 128) bytes => the 8 lanes of a quarter-warp hit 8 distinct
+        // 16-byte bank groups.  Otherwise strips along x are adjacent.
+        const bool rows_fastest = (S == 1 && CV != 8);
+        const int xs = rows_fastest ? task / p.TH : task % nxs;
+        const int ry = rows_fastest ? task % p.TH : task / nxs;
         const int oy = ty * p.TH + ry;
         const int ox0 = tx * p.TW + xs * TX;
         if (oy >= p.Ho || ox0 >= p.Wo) continue;
-        float acc[TX][8];
+        uint64_t acc[TX][4];
 #pragma unroll
         for (int t = 0; t < TX; ++t)
 #pragma unroll
-          for (int e = 0; e < 8; ++e) acc[t][e] = bv[e];
+          for (int e = 0; e < 4; ++e) acc[t][e] = bv[e];
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
           const uint8_t* row = tile_s + ((size_t)(ry * S + ky) * p.TWI + xs * TX * S) * (CV * 16);
 #pragma unroll
           for (int j = 0; j < NCOLS; ++j) {
             const uint4 u = *reinterpret_cast<const uint4*>(row + (size_t)j * (CV * 16));
-            float v[8];
-            Vec8<bf16>::unpack(u, v);
+            // bf16 pair -> packed f32 pair: low half << 16, high half masked
+            const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
+            uint64_t v[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[e] = f32x2(__uint_as_float(uw[e] << 16), __uint_as_float(uw[e] & 0xffff0000u));
 #pragma unroll
             for (int t = 0; t < TX; ++t) {
               const int kx = j - t * S;
               if (kx >= 0 && kx <= 2) {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) acc[t][e] = fmaf(v[e], wr[ky * 3 + kx][e], acc[t][e]);
+                for (int e = 0; e < 4; ++e) acc[t][e] = fma_f32x2(v[e], wr[ky * 3 + kx][e], acc[t][e]);
               }
             }
           }
@@ -139,19 +154,22 @@ dwconv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmX, const float* __res
 #pragma unroll
         for (int t = 0; t < TX; ++t) {
           if (ox0 + t < p.Wo) {
+            float o[8];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) f32x2_unpack(acc[t][e], o[2 * e], o[2 * e + 1]);
             if (p.relu) {
 #pragma unroll
-              for (int e = 0; e < 8; ++e) acc[t][e] = fmaxf(acc[t][e], 0.f);
+              for (int e = 0; e < 8; ++e) o[e] = fmaxf(o[e], 0.f);
             }
-            Vec8<bf16>::store(op + (size_t)t * p.C, acc[t]);
+            Vec8<bf16>::store(op + (size_t)t * p.C, o);
           }
         }
       }
     }
     __syncthreads();  // everyone is done reading this stage
     if (tid == 0) {
-      const long long next = tile + 2LL * gridDim.x;
-      if (next < num_tiles) issue(next, stage);
+      const long long next = sp + 2 * sp_step;
+      if (next < spatial_tiles) issue(next, stage);
     }
     stage ^= 1;
   }

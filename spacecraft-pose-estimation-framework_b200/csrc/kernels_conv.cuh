@@ -56,11 +56,12 @@ __global__ void __launch_bounds__(256) stem_conv3x3s2_kernel(const float* __rest
       }
     }
   }
-  float acc[2][8];
+  // packed FP32 pairs: 4 FFMA2 per tap and pixel instead of 8 FFMA
+  uint64_t acc[2][4];
 #pragma unroll
   for (int t = 0; t < 2; ++t)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[t][j] = bs[cg * 8 + j];
+    for (int j = 0; j < 4; ++j) acc[t][j] = f32x2(bs[cg * 8 + 2 * j], bs[cg * 8 + 2 * j + 1]);
 #pragma unroll
   for (int ci = 0; ci < 3; ++ci) {
 #pragma unroll
@@ -69,12 +70,13 @@ __global__ void __launch_bounds__(256) stem_conv3x3s2_kernel(const float* __rest
       for (int kx = 0; kx < 3; ++kx) {
         const float4* wp = reinterpret_cast<const float4*>(ws + ((ci * 3 + ky) * 3 + kx) * 32 + cg * 8);
         const float4 w0 = wp[0], w1 = wp[1];
-        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+        const uint64_t wv[4] = {f32x2(w0.x, w0.y), f32x2(w0.z, w0.w), f32x2(w1.x, w1.y), f32x2(w1.z, w1.w)};
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
           const float v = in[ci][ky][kx + 2 * t];
+          const uint64_t vv = f32x2(v, v);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) acc[t][e] = fmaf(v, wv[e], acc[t][e]);
+          for (int e = 0; e < 4; ++e) acc[t][e] = fma_f32x2(vv, wv[e], acc[t][e]);
         }
       }
     }
@@ -82,9 +84,14 @@ __global__ void __launch_bounds__(256) stem_conv3x3s2_kernel(const float* __rest
 #pragma unroll
   for (int t = 0; t < 2; ++t) {
     if (ox + t < Wo) {
+      float o[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[t][j] = fmaxf(acc[t][j], 0.f);
-      Vec8<T>::store(out + (((size_t)b * Ho + oy) * Wo + ox + t) * 32 + cg * 8, acc[t]);
+      for (int j = 0; j < 4; ++j) {
+        f32x2_unpack(acc[t][j], o[2 * j], o[2 * j + 1]);
+        o[2 * j] = fmaxf(o[2 * j], 0.f);
+        o[2 * j + 1] = fmaxf(o[2 * j + 1], 0.f);
+      }
+      Vec8<T>::store(out + (((size_t)b * Ho + oy) * Wo + ox + t) * 32 + cg * 8, o);
     }
   }
 }

@@ -439,8 +439,13 @@ extern "C" int spef_finalize_weights(spef_ctx* ctx) {
       const int wo4 = ((l.wout + 3) / 4) * 4;
       d.TH = (l.stride == 1) ? 8 : 4;
       d.TW = (l.stride == 1) ? (wo4 < 32 ? wo4 : 32) : (wo4 < 16 ? wo4 : 16);
+      if (l.stride == 1 && l.dw_cv == 6 && d.TW > 24) d.TW = 24;
       d.THI = (d.TH - 1) * l.stride + 3;
       d.TWI = (d.TW - 1) * l.stride + 3;
+      // bank-conflict-free row pitch for the rows-fastest lane order (dwconv_tma.cuh): 64-byte pixels need an odd box
+      // width, 96-byte pixels a width = 1 (mod 4); the extra columns are in-bounds neighbours (L2 hits) or OOB zeros
+      if (l.stride == 1 && l.dw_cv == 4) d.TWI |= 1;
+      if (l.stride == 1 && l.dw_cv == 6) d.TWI += (5 - d.TWI % 4) % 4;
       d.tiles_y = cdiv(l.hout, d.TH);
       d.tiles_x = cdiv(l.wout, d.TW);
       d.nchunks = cdiv(l.cin, l.dw_cv * 8);
@@ -558,9 +563,13 @@ static int launch_dw_tma_layer(spef_ctx* ctx, Layer& l, const void* in, void* ou
       return fail(ctx, SPEF_ERR_CUDA, "cuTensorMapEncodeTiled(X) failed for %s", l.prefix.c_str());
   }
   l.dwp.B = B;
-  const long long tiles = (long long)B * l.dwp.tiles_y * l.dwp.tiles_x * l.dwp.nchunks;
+  const long long sp_tiles = (long long)B * l.dwp.tiles_y * l.dwp.tiles_x;
   const int per_sm = (l.dw_cv == 4) ? 4 : 2;
-  const int grid = (int)(tiles < (long long)per_sm * ctx->num_sms ? tiles : (long long)per_sm * ctx->num_sms);
+  // grid = nchunks * (CTAs per chunk): every chunk gets the same number of CTAs, at most the resident capacity
+  long long per_chunk = ((long long)per_sm * ctx->num_sms) / l.dwp.nchunks;
+  if (per_chunk < 1) per_chunk = 1;
+  if (per_chunk > sp_tiles) per_chunk = sp_tiles;
+  const int grid = (int)(per_chunk * l.dwp.nchunks);
   const size_t smem = dw::smem_bytes(l.dwp, l.dw_cv);
   bf16* o = (bf16*)out;
   if (l.stride == 1) {
