@@ -142,11 +142,13 @@ def folded_layers(sd) -> List[dict]:
 
 def apply_layer(layer: dict, x: torch.Tensor, res: Optional[torch.Tensor], bf16: bool) -> torch.Tensor:
     """One folded conv layer on NCHW float32 tensors, optionally with BF16 rounding points:
-    pointwise weights rounded to bf16 (tensor-core operand), stem/depthwise weights kept f32,
-    fp32 accumulate, +bias, ReLU, (+residual), output rounded to bf16."""
+    pointwise and stem weights (and the stem's image taps) rounded to bf16 (tensor-core operands), depthwise weights kept
+    f32, fp32 accumulate, +bias, ReLU, (+residual), output rounded to bf16."""
     w, b = layer["w"], layer["b"]
-    if layer["kind"] == "pw" and bf16:
-        w = bf16_round(w)
+    if layer["kind"] in ("pw", "stem") and bf16:
+        w = bf16_round(w)  # tensor-core operands (the stem runs as an implicit GEMM: image taps and weights in BF16)
+    if layer["kind"] == "stem" and bf16:
+        x = bf16_round(x)
     groups = w.shape[0] if layer["kind"] == "dw" else 1
     k = w.shape[-1]
     y = F.conv2d(x, w, b, layer["stride"], (k - 1) // 2, 1, groups)

@@ -36,6 +36,9 @@ struct GemmParams {
   void* out;           // D (copy-out mode)
   int ldd;             // row pitch of D in elements
   long long* trace;    // debug: clock64 timestamps of CTA 0 (nullptr in production)
+  // im2col producer (stem as an implicit GEMM): image [B,3,H,W] f32 NCHW, output pixels [B,Ho,Wo]
+  const float* img;
+  int img_h, img_w, out_h, out_w;
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------

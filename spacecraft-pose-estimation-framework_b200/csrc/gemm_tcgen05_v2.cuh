@@ -71,8 +71,10 @@ __device__ __forceinline__ uint32_t relu_bf16x2(uint32_t v) {
 }
 
 // Thread layout: warps 0-3 control (TMA, MMA, TMEM alloc, spare), warps 4 .. 4+4*NDG-1 drain, then NSW store warps.
-template <bool OUT_F32, int NDG, int NSW>
-__global__ void __launch_bounds__(128 + 128 * NDG + 32 * NSW, 1)
+// PROD = 0: activations arrive by TMA (1x1 conv / Linear).  PROD = 1: four producer warps build the A tile by im2col from
+// the NCHW f32 image (stem 3x3 s2 as an implicit GEMM, K = 27 padded to 32); they sit between the control and drain warps.
+template <bool OUT_F32, int NDG, int NSW, int PROD>
+__global__ void __launch_bounds__(128 + 128 * PROD + 128 * NDG + 32 * NSW, 1)
 pw_gemm_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -103,7 +105,8 @@ pw_gemm_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
   const int num_tiles = m_tiles * n_tiles;
   const int k_chunks = (p.K + BLOCK_K - 1) / BLOCK_K;
   constexpr int COLS_PER_BOX = OUT_F32 ? 32 : 64;  // one 128-byte staging row
-  constexpr int FIRST_STORE_WARP = 4 + 4 * NDG;
+  constexpr int FIRST_DRAIN_WARP = 4 + 4 * PROD;
+  constexpr int FIRST_STORE_WARP = FIRST_DRAIN_WARP + 4 * NDG;
 
   for (int i = threadIdx.x; i < bias_floats(p.N); i += (int)blockDim.x) bias_s[i] = (i < p.N) ? p.bias[i] : 0.f;
   if (warp == 0 && lane == 0) {
@@ -112,7 +115,7 @@ pw_gemm_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < nstages; ++i) {
-      mbar_init(smem_u32(&full_bar[i]), 1);
+      mbar_init(smem_u32(&full_bar[i]), PROD ? 128 : 1);   // TMA: one arrive + tx bytes; im2col: every producer thread
       mbar_init(smem_u32(&empty_bar[i]), 1);
     }
     for (int i = 0; i < V2_MAX_ACC; ++i) {
@@ -150,7 +153,7 @@ pw_gemm_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
           for (int kc = 0; kc < k_chunks; ++kc)
             tma_load_2d(smem_u32(w_region + (size_t)(j * k_chunks + kc) * w_tile_bytes), &tmW, kc * BLOCK_K, j * block_n, wb);
       }
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x; PROD == 0 && tile < num_tiles; tile += gridDim.x) {
         const int m_idx = tm * BLOCK_M, n_idx = tn * block_n;
         for (int kc = 0; kc < k_chunks; ++kc) {
           mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
@@ -199,10 +202,68 @@ pw_gemm_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
       }
     }
     __syncwarp();
-  } else if (warp >= 4 && warp < FIRST_STORE_WARP) {
+  } else if (PROD == 1 && warp >= 4 && warp < FIRST_DRAIN_WARP) {
+    // ===================== im2col producer warps (stem): thread t builds row t of the A tile =====================
+    // A row = the 27 taps (ci, ky, kx) of one output pixel as bf16, k = (ci*3 + ky)*3 + kx, zero padded to 32; written in
+    // the 128B-swizzled K-major layout the UMMA descriptor expects (16-byte chunk c of row r at r*128 + ((c ^ (r & 7)) << 4)).
+    const int t = (int)threadIdx.x - 128;
+    const int H = p.img_h, W = p.img_w, Ho = p.out_h, Wo = p.out_w;
+    auto gather = [&](int tile, float (&tap)[27]) {
+      const int m = tile * BLOCK_M + t;
+      const bool m_ok = m < p.M;
+      const int mm = m_ok ? m : 0;
+      const int ox = mm % Wo;
+      const int oy = (mm / Wo) % Ho;
+      const int b = mm / (Wo * Ho);
+      const float* ib = p.img + (size_t)b * 3 * H * W;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int iy = oy * 2 - 1 + ky;
+        const bool yok = m_ok && (iy >= 0) && (iy < H);
+        const int iyc = min(max(iy, 0), H - 1);
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int ix = ox * 2 - 1 + kx;
+          const bool ok = yok && (ix >= 0) && (ix < W);
+          const int ixc = min(max(ix, 0), W - 1);
+#pragma unroll
+          for (int ci = 0; ci < 3; ++ci) {
+            const float v = __ldg(ib + ((size_t)ci * H + iyc) * W + ixc);
+            tap[(ci * 3 + ky) * 3 + kx] = ok ? v : 0.f;
+          }
+        }
+      }
+    };
+    int stage = 0;
+    uint32_t phase = 0;
+    float cur[27], nxt[27];
+    if ((int)blockIdx.x < num_tiles) gather(blockIdx.x, cur);
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      // software pipeline: the taps of the next tile are in flight while this one is converted and staged
+      const int next = tile + (int)gridDim.x;
+      if (next < num_tiles) gather(next, nxt);
+      uint32_t pk[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const float lo = (2 * k < 27) ? cur[2 * k] : 0.f;
+        const float hi = (2 * k + 1 < 27) ? cur[2 * k + 1] : 0.f;
+        pk[k] = Vec8<bf16>::pack2(lo, hi);
+      }
+      mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+      const uint32_t sa = smem_u32(stage_base + (size_t)stage * sbytes) + (uint32_t)t * 128u;
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        sts_u4(sa + (((uint32_t)c ^ ((uint32_t)t & 7u)) << 4), make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]));
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
+      mbar_arrive(smem_u32(&full_bar[stage]));
+      if (++stage == nstages) { stage = 0; phase ^= 1; }
+#pragma unroll
+      for (int k = 0; k < 27; ++k) cur[k] = nxt[k];
+    }
+  } else if (warp >= FIRST_DRAIN_WARP && warp < FIRST_STORE_WARP) {
     // ===================== drain warps: TMEM -> registers -> bf16 -> staging ring =====================
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
-    const int grp = (warp - 4) >> 2;        // drain group
+    const int grp = (warp - FIRST_DRAIN_WARP) >> 2;        // drain group
     const int row = q * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -236,8 +297,10 @@ pw_gemm_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
           uint32_t(&v0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[0]);
           tmem_ld_32x32b_x32(t_row + (uint32_t)c0, v0);
           if constexpr (!OUT_F32) {
-            uint32_t(&v1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[32]);
-            tmem_ld_32x32b_x32(t_row + (uint32_t)(c0 + 32), v1);
+            if (c0 + 32 < ncols) {  // second 32-column half only when it holds real columns
+              uint32_t(&v1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[32]);
+              tmem_ld_32x32b_x32(t_row + (uint32_t)(c0 + 32), v1);
+            }
           }
         }
         mbar_wait(smem_u32(&sempty_bar[slot]), ring_phase ^ 1);  // staging slot drained by the store warps
@@ -265,6 +328,7 @@ pw_gemm_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
           // packed path: f32x2 bias add, cvt to bf16x2, ReLU on the packed pair (round(max(x,0)) == max(round(x),0))
 #pragma unroll
           for (int g = 0; g < 8; ++g) {  // eight 16-byte pieces = 64 bf16 columns
+            if (c0 + g * 8 >= ncols) break;
             const float4 b0 = lds_f4(bias_sa + (uint32_t)g * 32u);
             const float4 b1 = lds_f4(bias_sa + (uint32_t)g * 32u + 16u);
             uint32_t o[4];
@@ -283,6 +347,7 @@ pw_gemm_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
           const bf16* rp = p.residual + (size_t)m * p.N + n_idx + c0;
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
+            if (c0 + g * 8 >= ncols) break;
             const float4 b0 = lds_f4(bias_sa + (uint32_t)g * 32u);
             const float4 b1 = lds_f4(bias_sa + (uint32_t)g * 32u + 16u);
             float f[8] = {__uint_as_float(v[g * 8 + 0]) + b0.x, __uint_as_float(v[g * 8 + 1]) + b0.y,

@@ -51,7 +51,9 @@ __global__ void __launch_bounds__(256) stem_conv3x3s2_kernel(const float* __rest
       const int ixc = min(max(ix, 0), W - 1);
 #pragma unroll
       for (int ci = 0; ci < 3; ++ci) {
-        const float v = __ldg(ib + ((size_t)ci * H + iyc) * W + ixc);
+        float v = __ldg(ib + ((size_t)ci * H + iyc) * W + ixc);
+        // BF16 engine: the image is a tensor-core operand on the default path, so the cross-check rounds it the same way
+        if constexpr (sizeof(T) == 2) v = __bfloat162float(__float2bfloat16_rn(v));
         in[ci][ky][j] = ok ? v : 0.f;
       }
     }

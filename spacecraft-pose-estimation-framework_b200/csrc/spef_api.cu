@@ -407,6 +407,16 @@ extern "C" int spef_finalize_weights(spef_ctx* ctx) {
     }
     std::vector<float> packed;
     if (l.kind == K_STEM) {  // [32,3,3,3] -> [27][32]
+      if (use_bf16) {  // implicit-GEMM operand [N=32][K=32] (27 taps + 5 zero columns), and the same rounded values for SIMT
+        std::vector<bf16> wb(32 * 32, __float2bfloat16_rn(0.f));
+        for (int co = 0; co < 32; ++co)
+          for (int k = 0; k < 27; ++k) {
+            wb[co * 32 + k] = __float2bfloat16_rn(wf[co * 27 + k]);
+            wf[co * 27 + k] = __bfloat162float(wb[co * 32 + k]);
+          }
+        if (!upload(&l.w_bf16, wb)) return fail(ctx, SPEF_ERR_CUDA, "spef_finalize_weights: upload failed");
+        l.tmW_ready = false;
+      }
       packed.resize(27 * 32);
       for (int co = 0; co < 32; ++co)
         for (int k = 0; k < 27; ++k) packed[k * 32 + co] = wf[co * 27 + k];
@@ -450,6 +460,11 @@ extern "C" int spef_finalize_weights(spef_ctx* ctx) {
       d.tiles_x = cdiv(l.wout, d.TW);
       d.nchunks = cdiv(l.cin, l.dw_cv * 8);
     }
+    if (l.kind == K_STEM) {  // stem as an implicit GEMM: M = B*Ho*Wo, N = 32, K = 27 -> 32
+      l.block_n = 32;
+      l.stages = tc::pick_stages_v2(32, 32, 32, ctx->smem_optin);
+      l.smem = tc::smem_bytes_v2(32, l.stages, 32, 32);
+    }
     if (l.kind == K_PW || l.kind == K_HEAD) {
       l.block_n = tc::pick_block_n(l.n_pad);
       if (ctx->gemm_impl == 2) {
@@ -463,12 +478,13 @@ extern "C" int spef_finalize_weights(spef_ctx* ctx) {
   }
   if (use_bf16) {
     const int so = (int)ctx->smem_optin;
-    CK(cudaFuncSetAttribute(tc::pw_gemm_tcgen05_v2_kernel<false, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, so));
-    CK(cudaFuncSetAttribute(tc::pw_gemm_tcgen05_v2_kernel<true, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, so));
-    CK(cudaFuncSetAttribute(tc::pw_gemm_tcgen05_v2_kernel<false, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, so));
-    CK(cudaFuncSetAttribute(tc::pw_gemm_tcgen05_v2_kernel<true, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, so));
-    CK(cudaFuncSetAttribute(tc::pw_gemm_tcgen05_v2_kernel<false, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, so));
-    CK(cudaFuncSetAttribute(tc::pw_gemm_tcgen05_v2_kernel<true, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, so));
+    CK(cudaFuncSetAttribute(tc::pw_gemm_tcgen05_v2_kernel<false, 1, 4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, so));
+    CK(cudaFuncSetAttribute(tc::pw_gemm_tcgen05_v2_kernel<true, 1, 4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, so));
+    CK(cudaFuncSetAttribute(tc::pw_gemm_tcgen05_v2_kernel<false, 1, 8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, so));
+    CK(cudaFuncSetAttribute(tc::pw_gemm_tcgen05_v2_kernel<true, 1, 8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, so));
+    CK(cudaFuncSetAttribute(tc::pw_gemm_tcgen05_v2_kernel<false, 2, 4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, so));
+    CK(cudaFuncSetAttribute(tc::pw_gemm_tcgen05_v2_kernel<true, 2, 4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, so));
+    CK(cudaFuncSetAttribute(tc::pw_gemm_tcgen05_v2_kernel<false, 1, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, so));
     CK(cudaFuncSetAttribute(tc::pw_gemm_tcgen05_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, so));
     CK(cudaFuncSetAttribute(tc::pw_gemm_tcgen05_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, so));
     CK(cudaFuncSetAttribute(tc::pw_gemm_tcgen05_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, so));
@@ -585,6 +601,23 @@ static int launch_dw_tma_layer(spef_ctx* ctx, Layer& l, const void* in, void* ou
   return SPEF_OK;
 }
 
+static int launch_stem_tcgen05(spef_ctx* ctx, Layer& l, const void* images, void* out, int B, cudaStream_t st) {
+  if (!l.tmW_ready) {
+    if (!tc::make_tmap_2d(ctx->encode, &l.tmW, l.w_bf16, false, 32, 32, 32, 32)) return fail(ctx, SPEF_ERR_CUDA, "cuTensorMapEncodeTiled(W) failed for the stem");
+    l.tmW_ready = true;
+  }
+  tc::GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.bias = l.bias; p.residual = nullptr; p.M = B * l.hout * l.wout; p.N = 32; p.K = 32; p.block_n = 32; p.num_stages = l.stages; p.relu = 1;
+  p.store_mode = 0; p.out = out; p.ldd = 32; p.trace = nullptr;
+  p.img = (const float*)images; p.img_h = l.hin; p.img_w = l.win; p.out_h = l.hout; p.out_w = l.wout;
+  const int tiles = cdiv(p.M, tc::BLOCK_M);
+  const int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
+  tc::pw_gemm_tcgen05_v2_kernel<false, 1, 4, 1><<<grid, 128 + 128 + 128 + 128, l.smem, st>>>(l.tmW, l.tmW, p);
+  CK_LAUNCH("pw_gemm_tcgen05_v2_kernel<im2col stem>");
+  return SPEF_OK;
+}
+
 static int launch_tcgen05_layer(spef_ctx* ctx, Layer& l, const void* in, const void* res, void* out, int B, cudaStream_t st, bool cached_maps) {
   const int M = B * l.hout * l.wout, N = l.n_pad, K = l.cin;
   const bool f32out = (l.kind == K_HEAD);
@@ -602,6 +635,7 @@ static int launch_tcgen05_layer(spef_ctx* ctx, Layer& l, const void* in, const v
   tc::GemmParams p;
   p.bias = l.bias; p.residual = (const bf16*)res; p.M = M; p.N = N; p.K = K; p.block_n = l.block_n; p.num_stages = l.stages; p.relu = l.relu;
   p.store_mode = ctx->gemm_store; p.out = out; p.ldd = N;
+  p.img = nullptr; p.img_h = p.img_w = p.out_h = p.out_w = 0;
   const bool trace = ctx->trace_dev && (&l == &ctx->layers[ctx->trace_layer < (int)ctx->layers.size() && ctx->trace_layer >= 0 ? ctx->trace_layer : 0]) && ctx->trace_layer >= 0;
   p.trace = (trace && ctx->gemm_impl == 1) ? ctx->trace_dev : nullptr;
   if (trace) cudaMemsetAsync(ctx->trace_dev, 0, 256 * 8 * sizeof(long long), st);
@@ -610,7 +644,7 @@ static int launch_tcgen05_layer(spef_ctx* ctx, Layer& l, const void* in, const v
   const int ng = ctx->gemm_ng, nthr = 128 + 128 * ng;
   if (ctx->gemm_impl == 2) {
     const int nsw = ctx->gemm_nsw, ndg = ctx->gemm_ndg, nt2 = 128 + 128 * ndg + 32 * nsw;
-#define SPEF_V2_LAUNCH(F32, NDG_, NSW_) tc::pw_gemm_tcgen05_v2_kernel<F32, NDG_, NSW_><<<grid, nt2, l.smem, st>>>(*tA, l.tmW, p)
+#define SPEF_V2_LAUNCH(F32, NDG_, NSW_) tc::pw_gemm_tcgen05_v2_kernel<F32, NDG_, NSW_, 0><<<grid, nt2, l.smem, st>>>(*tA, l.tmW, p)
     if (f32out) {
       if (ndg == 2) SPEF_V2_LAUNCH(true, 2, 4); else if (nsw == 8) SPEF_V2_LAUNCH(true, 1, 8); else SPEF_V2_LAUNCH(true, 1, 4);
     } else {
@@ -649,6 +683,7 @@ static int run_layer(spef_ctx* ctx, Layer& l, const void* in, const void* res, v
   const bool use_bf16 = ctx->cfg.precision == SPEF_BF16;
   if (use_bf16 && (l.kind == K_PW || l.kind == K_HEAD) && ctx->cfg.pw_impl == 0) return launch_tcgen05_layer(ctx, l, in, res, out, B, st, cached_maps);
   if (use_bf16 && l.kind == K_DW && ctx->cfg.pw_impl == 0) return launch_dw_tma_layer(ctx, l, in, out, B, st, cached_maps);
+  if (use_bf16 && l.kind == K_STEM && ctx->cfg.pw_impl == 0 && ctx->gemm_impl == 2 && !getenv("SPEF_STEM_SIMT")) return launch_stem_tcgen05(ctx, l, in, out, B, st);
   if (use_bf16) return launch_cuda_core_layer<bf16>(ctx, l, in, res, out, B, st);
   return launch_cuda_core_layer<float>(ctx, l, in, res, out, B, st);
 }
