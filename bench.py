@@ -25,6 +25,16 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# Anything a library prints to fd 1 (e.g. the NCCL version banner) goes to stderr; the JSON line uses the saved descriptor.
+_REAL_STDOUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(obj):
+    _REAL_STDOUT.write(json.dumps(obj) + "\n")
+    _REAL_STDOUT.flush()
+
+
 METRIC = "images/sec (device-timed, max over ranks)"
 UNIT = "images/s"
 IMG = (240, 384)
@@ -43,6 +53,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--layers", action="store_true", help="also print the per-layer table to stderr")
+    ap.add_argument("--workload", default="forward", choices=["forward", "decode", "temporal"],
+                    help="forward: BASELINE configs[1]/[2] (default, the driver's line); decode: configs[3] bins-per-axis sweep of the "
+                         "decode kernel alone; temporal: configs[4] D-SPEED-shaped stream, batch-1 latency and 64-stream throughput")
     return ap.parse_args()
 
 
@@ -66,7 +79,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "25", "-i", str(self.gpu)],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
@@ -74,7 +87,7 @@ class ClockSampler:
     def stop(self):
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.12)
+        time.sleep(0.05)
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
@@ -154,7 +167,7 @@ def run_reference(args):
     el = time.perf_counter() - t0
     v = sample * args.steps / el
     desc = f"{sample}-image sample of the {args.batch}-image batch per step, FP32, {cores} host threads"
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000 * el / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -163,7 +176,7 @@ def run_reference(args):
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    })
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -341,16 +354,128 @@ def run_b200(args):
                 gb = r["bytes"] / (r["ms"] * 1e-3) / 1e9 if r["ms"] > 0 else 0
                 print(f"L{r['layer']:02d} {r['kernel']:24s} {r['cin']:5d}->{r['cout']:5d} {r['hw']:>8s} s{r['stride']} {r['ms']*1000:9.1f} us "
                       f"{gb:8.0f} GB/s {r['flops']/(r['ms']*1e-3)/1e12 if r['ms'] > 0 else 0:7.1f} TF/s", file=sys.stderr)
-        print(json.dumps(out))
+        emit(out)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def run_decode_sweep(args):
+    """BASELINE configs[3]: soft-classification decode kernel isolated, orientation bins per axis 8..32."""
+    from spef_b200.engine import Engine
+    from spef_b200.spe.classification_utils import OrientationSoftClassification
+    dev = torch.device("cuda", 0)
+    eng = Engine(32, 32, 8, 3, False, "fp32", 1, dev)
+    pk = peaks()
+    rows = []
+    for n_dim in (8, 12, 16, 24, 32):
+        hist = OrientationSoftClassification(n_dim, 3, False).histogram
+        n = hist.shape[0]
+        eng.set_ori_histogram(hist)
+        B = int(max(4096, min(262144, (1 << 29) // (4 * n))))     # >= 512 MB of logits: larger than L2
+        logits = torch.randn((B, n), device=dev) * 3
+        # pre-allocated outputs and the bare C-ABI call in the timed loop: the Python wrapper's allocations would make the
+        # GPU wait for the host at these kernel durations
+        from spef_b200._ffi import ptr
+        quat = torch.empty((B, 4), device=dev)
+        flags = torch.zeros(B, dtype=torch.int32, device=dev)
+        st = torch.cuda.current_stream(dev).cuda_stream or None
+
+        def call():
+            rc = eng.lib.spef_decode_ori(eng._h, ptr(logits), B, n, 1, None, ptr(quat), None, None, ptr(flags), st)
+            assert rc == 0
+        for _ in range(3):
+            call()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            call()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        gbs = B * (4 * n + 16) / (ms * 1e-3) / 1e9
+        rows.append({"bins_per_axis": n_dim, "n_bins": n, "batch": B, "ms": ms, "images_per_s": B / (ms * 1e-3),
+                     "achieved_GBps": gbs, "hbm_frac": gbs / pk["hbm_gbs"]})
+        del logits
+    emit({"metric": "decode images/sec (softmax + weighted quaternion average, kernel isolated)", "unit": UNIT, "n_gpus": 1,
+          "steps": args.steps, "warmup": 3, "dtype": "f32", "data": "synthetic", "higher_is_better": True,
+          "value": rows[1]["images_per_s"], "config": {"workload": "BASELINE configs[3]: decode sweep, bins per axis 8..32, logits ~ 3*N(0,1), inputs larger than L2"},
+          "algorithmic_bytes": "4*n_bins + 16 per image", "peak_GBps": pk["hbm_gbs"], "sweep": rows})
+
+
+def run_temporal(args):
+    """BASELINE configs[4]: Mobile-URSONet+ (1728 + 1000 bins) frame stream through spef_temporal_step:
+    batch-1 latency (plain launches and one CUDA graph per frame) and 64 parallel streams throughput."""
+    from spef_b200.engine import Engine
+    from spef_b200.tools import synthetic
+    from spef_b200.spe.classification_utils import OrientationSoftClassification, PositionSoftClassification
+    dev = torch.device("cuda", 0)
+    sd = synthetic.synthetic_state_dict(N_ORI, 1000)
+    ori_hist = OrientationSoftClassification(12, 3, False).histogram
+    pos_hist = PositionSoftClassification(10, 100, np.array([-16, -12, -2]), np.array([16, 12, 40])).histogram
+    out = {"metric": "frames/sec and per-frame latency (forward + softmax + decode + adaptive pdf filter + decode)", "unit": "frames/s",
+           "n_gpus": 1, "dtype": "bf16", "data": "synthetic", "higher_is_better": True,
+           "config": {"workload": "BASELINE configs[4]: temporal D-SPEED-shaped stream, Mobile-URSONet+ heads, random frames"}}
+    for S in (1, 64):
+        eng = Engine(IMG[0], IMG[1], N_ORI, 1000, True, "bf16", S, dev)
+        eng.load_state_dict(sd)
+        eng.set_ori_histogram(ori_hist)
+        eng.set_pos_histogram(pos_hist)
+        eng.temporal_reset(S)
+        frames = synthetic.synthetic_images(S, IMG, 99).to(dev)
+        for _ in range(5):
+            eng.temporal_step(frames)
+        torch.cuda.synchronize()
+        n_frames = 200 if S == 1 else 50
+        lat = []
+        for _ in range(n_frames):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            eng.temporal_step(frames)
+            e1.record()
+            e1.synchronize()
+            lat.append(e0.elapsed_time(e1))
+        lat = np.array(lat)
+        key = "batch1" if S == 1 else "streams64"
+        out[key] = {"p50_ms": float(np.percentile(lat, 50)), "p99_ms": float(np.percentile(lat, 99)),
+                    "frames_per_s": float(S / (np.median(lat) * 1e-3)), "launches_per_frame_step": None}
+        l0 = eng.launch_count()
+        eng.temporal_step(frames)
+        out[key]["launches_per_frame_step"] = eng.launch_count() - l0
+        if S == 1:  # the 63-launch frame step as ONE CUDA graph: removes the launch gaps that dominate batch-1 latency
+            g = torch.cuda.CUDAGraph()
+            side = torch.cuda.Stream(dev)
+            with torch.cuda.stream(side):
+                eng.temporal_step(frames)
+                torch.cuda.synchronize()
+                with torch.cuda.graph(g, stream=side):
+                    res = eng.temporal_step(frames)
+            torch.cuda.synchronize()
+            glat = []
+            for _ in range(n_frames):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                g.replay()
+                e1.record()
+                e1.synchronize()
+                glat.append(e0.elapsed_time(e1))
+            glat = np.array(glat)
+            out[key]["cuda_graph"] = {"p50_ms": float(np.percentile(glat, 50)), "p99_ms": float(np.percentile(glat, 99)),
+                                      "frames_per_s": float(1.0 / (np.median(glat) * 1e-3))}
+        eng.close()
+    out["value"] = out["streams64"]["frames_per_s"]
+    emit(out)
 
 
 def main():
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "decode":
+        run_decode_sweep(args)
+    elif args.workload == "temporal":
+        run_temporal(args)
     else:
         run_b200(args)
 

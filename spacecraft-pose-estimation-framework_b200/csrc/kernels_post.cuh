@@ -15,7 +15,16 @@ __device__ __forceinline__ void for_each_in_row(const float* __restrict__ row, i
   if (vec_ok) {
     const float4* r4 = reinterpret_cast<const float4*>(row);
     const int n4 = n >> 2;
-    for (int i = lane; i < n4; i += 32) {
+    int i = lane;
+    // four independent 16-byte loads in flight per lane before any of them is consumed (memory-level parallelism)
+    for (; i + 96 < n4; i += 128) {
+      const float4 v0 = r4[i], v1 = r4[i + 32], v2 = r4[i + 64], v3 = r4[i + 96];
+      f(i * 4, v0.x, v0.y, v0.z, v0.w, 4);
+      f((i + 32) * 4, v1.x, v1.y, v1.z, v1.w, 4);
+      f((i + 64) * 4, v2.x, v2.y, v2.z, v2.w, 4);
+      f((i + 96) * 4, v3.x, v3.y, v3.z, v3.w, 4);
+    }
+    for (; i < n4; i += 32) {
       const float4 v = r4[i];
       f(i * 4, v.x, v.y, v.z, v.w, 4);
     }
@@ -74,92 +83,20 @@ __host__ __device__ inline void jacobi4(double (&a)[4][4], double (&v)[4][4]) {
 }
 
 // --------------------------------------------------------------------------------------------------
-// Orientation: softmax (spe_utils.py:75-76) + decode (classification_utils.py:131-147), one warp per image.
-//   pass 1: row max + first-max argmax (np.argmax tie rule)
-//   pass 2: w = exp(z - max) (or w = p when the input is already a pdf); S = sum w; A = sum w q q^T
-//           (10 unique entries; 4-bin f32 partial sums flushed into f64 accumulators, f64 warp reduction)
-//   then cyclic Jacobi in f64 on the 4x4, dominant eigenvector, renormalise, cast to f32.
-//   pass 3 (optional): ori_soft = w / S.
-// The eigenvector sign is unspecified in the reference (LAPACK geev); we return scalar part >= 0.
-// qtab: [n] float4 (scalar-first quaternion bins).  ld = row pitch of `in` in floats.
+// Orientation: softmax (spe_utils.py:75-76) + decode (classification_utils.py:131-147).
+// One warp streams G images one after the other; every image is read ONCE (online softmax):
+//   each lane keeps its own running maximum m and 11 accumulators S = sum w, A = sum w q q^T (10 unique entries) with
+//   w = exp(z - m); when a lane meets a larger value it rescales its accumulators by exp(m_old - m_new).  4-bin f32
+//   partial sums (up to 16 bins) are flushed into f64 accumulators.  Lanes are combined with M = max m, scale exp(m - M), f64 shuffles.
+//   The first-max argmax (np.argmax tie rule) rides along.
+// The 4x4 eigen-problems of the G images are then solved in parallel, one image per lane (cyclic Jacobi in f64, dominant
+// eigenvector, renormalise, cast) -- with G = 1 every lane solves the same matrix (small batches: latency matters).
+// Optional second pass writes ori_soft = exp(z - M) / S.  The eigenvector sign is unspecified in the reference (LAPACK
+// geev); we return scalar part >= 0.  qtab: [n] float4 (scalar-first bins).  ld = row pitch of `in` in floats.
 // --------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) decode_ori_kernel(const float* __restrict__ in, int ld, int B, int n, int is_logits,
-                                                         const float4* __restrict__ qtab, float* __restrict__ soft_out,
-                                                         float* __restrict__ quat_out, float* __restrict__ hinv_out,
-                                                         int* __restrict__ argmax_out, uint32_t* __restrict__ flags) {
-  const int lane = threadIdx.x & 31;
-  const int img = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (img >= B) return;
-  const float* row = in + (size_t)img * ld;
-  const bool vec_ok = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(in) & 15) == 0);
-
-  float mx = -INFINITY;
-  int amax = 0x7fffffff;
-  if (is_logits || argmax_out != nullptr) {
-    for_each_in_row(row, n, vec_ok, lane, [&](int i, float a, float b, float c, float d, int cnt) {
-      if (a > mx) { mx = a; amax = i; }
-      if (cnt == 4) {
-        if (b > mx) { mx = b; amax = i + 1; }
-        if (c > mx) { mx = c; amax = i + 2; }
-        if (d > mx) { mx = d; amax = i + 3; }
-      }
-    });
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float om = __shfl_xor_sync(0xffffffffu, mx, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, amax, o);
-      if (om > mx || (om == mx && oi < amax)) { mx = om; amax = oi; }
-    }
-    if (argmax_out != nullptr && lane == 0) argmax_out[img] = amax;
-  }
-
-  // accumulators: S, then a00 a01 a02 a03 a11 a12 a13 a22 a23 a33
-  double acc[11];
-#pragma unroll
-  for (int k = 0; k < 11; ++k) acc[k] = 0.0;
-  for_each_in_row(row, n, vec_ok, lane, [&](int i, float a, float b, float c, float d, int cnt) {
-    const float z[4] = {a, b, c, d};
-    float part[11];
-#pragma unroll
-    for (int k = 0; k < 11; ++k) part[k] = 0.f;
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      if (e < cnt) {
-        const float w = is_logits ? expf(z[e] - mx) : z[e];
-        const float4 q = __ldg(qtab + i + e);
-        const float w0 = w * q.x, w1 = w * q.y, w2 = w * q.z, w3 = w * q.w;
-        part[0] += w;
-        part[1] = fmaf(w0, q.x, part[1]); part[2] = fmaf(w0, q.y, part[2]);
-        part[3] = fmaf(w0, q.z, part[3]); part[4] = fmaf(w0, q.w, part[4]);
-        part[5] = fmaf(w1, q.y, part[5]); part[6] = fmaf(w1, q.z, part[6]);
-        part[7] = fmaf(w1, q.w, part[7]); part[8] = fmaf(w2, q.z, part[8]);
-        part[9] = fmaf(w2, q.w, part[9]); part[10] = fmaf(w3, q.w, part[10]);
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < 11; ++k) acc[k] += (double)part[k];
-  });
-#pragma unroll
-  for (int k = 0; k < 11; ++k) acc[k] = warp_sum(acc[k]);
-
+__device__ __forceinline__ void decode_solve_and_store(const double (&acc)[11], bool is_logits, int img, float* __restrict__ quat_out,
+                                                       float* __restrict__ hinv_out, uint32_t* __restrict__ flags) {
   const double S = acc[0];
-  if (soft_out != nullptr && is_logits) {
-    const float sf = (float)S;
-    float* orow = soft_out + (size_t)img * n;
-    const bool ovec = vec_ok && ((n & 3) == 0) && ((reinterpret_cast<uintptr_t>(soft_out) & 15) == 0);
-    if (ovec) {
-      const float4* r4 = reinterpret_cast<const float4*>(row);
-      float4* o4 = reinterpret_cast<float4*>(orow);
-      for (int i = lane; i < (n >> 2); i += 32) {
-        const float4 v = r4[i];
-        o4[i] = make_float4(expf(v.x - mx) / sf, expf(v.y - mx) / sf, expf(v.z - mx) / sf, expf(v.w - mx) / sf);
-      }
-    } else {
-      for (int i = lane; i < n; i += 32) orow[i] = expf(row[i] - mx) / sf;
-    }
-  }
-
-  // every lane solves the same 4x4 redundantly (no divergence, no broadcast needed)
   double a[4][4], v[4][4];
   a[0][0] = acc[1]; a[0][1] = a[1][0] = acc[2]; a[0][2] = a[2][0] = acc[3]; a[0][3] = a[3][0] = acc[4];
   a[1][1] = acc[5]; a[1][2] = a[2][1] = acc[6]; a[1][3] = a[3][1] = acc[7];
@@ -176,11 +113,9 @@ __global__ void __launch_bounds__(128) decode_ori_kernel(const float* __restrict
   for (int k = 1; k < 11; ++k) bad = bad || isnan(acc[k]);
   bad = bad || (is_logits && isnan(S));
   if (bad) {
-    if (lane == 0) {
-      if (flags != nullptr) atomicOr(flags + img, 1u);
-      const float qn = __int_as_float(0x7fc00000);
-      reinterpret_cast<float4*>(quat_out)[img] = make_float4(qn, qn, qn, qn);
-    }
+    if (flags != nullptr) atomicOr(flags + img, 1u);
+    const float qn = __int_as_float(0x7fc00000);
+    reinterpret_cast<float4*>(quat_out)[img] = make_float4(qn, qn, qn, qn);
     return;
   }
   jacobi4(a, v);
@@ -193,13 +128,11 @@ __global__ void __launch_bounds__(128) decode_ori_kernel(const float* __restrict
   double q[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) q[k] = (best == 0) ? v[k][0] : (best == 1) ? v[k][1] : (best == 2) ? v[k][2] : v[k][3];
-  double nrm = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
-  double sgn = (q[0] < 0.0) ? -1.0 : 1.0;
+  const double nrm = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  const double sgn = (q[0] < 0.0) ? -1.0 : 1.0;
 #pragma unroll
   for (int k = 0; k < 4; ++k) q[k] = sgn * q[k] / nrm;
-  if (lane == 0) {
-    reinterpret_cast<float4*>(quat_out)[img] = make_float4((float)q[0], (float)q[1], (float)q[2], (float)q[3]);
-  }
+  reinterpret_cast<float4*>(quat_out)[img] = make_float4((float)q[0], (float)q[1], (float)q[2], (float)q[3]);
   if (hinv_out != nullptr) {
     // h_inv = A^-1 = V diag(1/lambda) V^T  (classification_utils.py:142); static indexing keeps a, v in registers
 #pragma unroll
@@ -208,8 +141,121 @@ __global__ void __launch_bounds__(128) decode_ori_kernel(const float* __restrict
       double h = 0.0;
 #pragma unroll
       for (int k = 0; k < 4; ++k) h += v[r][k] * v[c][k] / a[k][k];
-      if (lane == e) hinv_out[(size_t)img * 16 + e] = (float)h;
+      hinv_out[(size_t)img * 16 + e] = (float)h;
     }
+  }
+}
+
+template <int G>
+__global__ void __launch_bounds__(128) decode_ori_kernel(const float* __restrict__ in, int ld, int B, int n, int is_logits,
+                                                         const float4* __restrict__ qtab, float* __restrict__ soft_out,
+                                                         float* __restrict__ quat_out, float* __restrict__ hinv_out,
+                                                         int* __restrict__ argmax_out, uint32_t* __restrict__ flags) {
+  const int lane = threadIdx.x & 31;
+  const int img0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * G;
+  if (img0 >= B) return;
+  const bool vec_ok = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(in) & 15) == 0);
+  double keep[11];
+#pragma unroll
+  for (int k = 0; k < 11; ++k) keep[k] = 0.0;
+
+  for (int g = 0; g < G; ++g) {
+    const int img = img0 + g;
+    if (img >= B) break;  // warp-uniform
+    const float* row = in + (size_t)img * ld;
+    float m = -INFINITY;      // running maximum of this lane
+    int amax = 0x7fffffff;
+    double acc[11];           // S, a00 a01 a02 a03 a11 a12 a13 a22 a23 a33
+    float part[11];           // f32 partial sums of up to 16 bins, flushed into acc
+    int pending = 0;
+#pragma unroll
+    for (int k = 0; k < 11; ++k) { acc[k] = 0.0; part[k] = 0.f; }
+    for_each_in_row(row, n, vec_ok, lane, [&](int i, float z0, float z1, float z2, float z3, int cnt) {
+      const float z[4] = {z0, z1, z2, z3};
+      float lm = z0;
+      int li = i;
+      if (cnt == 4) {
+        if (z1 > lm) { lm = z1; li = i + 1; }
+        if (z2 > lm) { lm = z2; li = i + 2; }
+        if (z3 > lm) { lm = z3; li = i + 3; }
+      }
+      if (lm > m) {  // new running maximum on this lane (first occurrence wins ties: indices increase)
+        if (is_logits) {
+          const float scf = __expf(m - lm);  // m = -inf the first time -> 0
+          const double sc = (double)scf;
+#pragma unroll
+          for (int k = 0; k < 11; ++k) { acc[k] *= sc; part[k] *= scf; }
+        }
+        m = lm;
+        amax = li;
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (e < cnt) {
+          // ex2.approx path: relative error ~1e-6 on the weights moves the eigenvector by < 1e-3 deg (gate 0.05 deg);
+          // the ori_soft output below uses the accurate expf
+          const float w = is_logits ? __expf(z[e] - m) : z[e];
+          const float4 q = __ldg(qtab + i + e);
+          const float w0 = w * q.x, w1 = w * q.y, w2 = w * q.z, w3 = w * q.w;
+          part[0] += w;
+          part[1] = fmaf(w0, q.x, part[1]); part[2] = fmaf(w0, q.y, part[2]);
+          part[3] = fmaf(w0, q.z, part[3]); part[4] = fmaf(w0, q.w, part[4]);
+          part[5] = fmaf(w1, q.y, part[5]); part[6] = fmaf(w1, q.z, part[6]);
+          part[7] = fmaf(w1, q.w, part[7]); part[8] = fmaf(w2, q.z, part[8]);
+          part[9] = fmaf(w2, q.w, part[9]); part[10] = fmaf(w3, q.w, part[10]);
+        }
+      }
+      if (++pending == 4) {
+        pending = 0;
+#pragma unroll
+        for (int k = 0; k < 11; ++k) { acc[k] += (double)part[k]; part[k] = 0.f; }
+      }
+    });
+#pragma unroll
+    for (int k = 0; k < 11; ++k) acc[k] += (double)part[k];
+    // combine the lanes: global maximum / argmax, rescale, sum
+    float M = m;
+    int AM = amax;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float om = __shfl_xor_sync(0xffffffffu, M, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, AM, o);
+      if (om > M || (om == M && oi < AM)) { M = om; AM = oi; }
+    }
+    if (argmax_out != nullptr && lane == 0) argmax_out[img] = AM;
+    if (is_logits) {
+      const double sc = (double)__expf(m - M);  // lanes that saw nothing (m = -inf) contribute 0; NaN rows stay NaN
+#pragma unroll
+      for (int k = 0; k < 11; ++k) acc[k] *= sc;
+    }
+#pragma unroll
+    for (int k = 0; k < 11; ++k) acc[k] = warp_sum(acc[k]);
+
+    if (soft_out != nullptr && is_logits) {
+      const float sf = (float)acc[0];
+      float* orow = soft_out + (size_t)img * n;
+      const bool ovec = vec_ok && ((n & 3) == 0) && ((reinterpret_cast<uintptr_t>(soft_out) & 15) == 0);
+      if (ovec) {
+        const float4* r4 = reinterpret_cast<const float4*>(row);
+        float4* o4 = reinterpret_cast<float4*>(orow);
+        for (int i = lane; i < (n >> 2); i += 32) {
+          const float4 x = r4[i];
+          o4[i] = make_float4(expf(x.x - M) / sf, expf(x.y - M) / sf, expf(x.z - M) / sf, expf(x.w - M) / sf);
+        }
+      } else {
+        for (int i = lane; i < n; i += 32) orow[i] = expf(row[i] - M) / sf;
+      }
+    }
+    if (G == 1) {
+      if (lane == 0) decode_solve_and_store(acc, is_logits != 0, img, quat_out, hinv_out, flags);
+    } else if (lane == g) {
+#pragma unroll
+      for (int k = 0; k < 11; ++k) keep[k] = acc[k];
+    }
+  }
+  if (G > 1) {
+    const int img = img0 + lane;
+    if (lane < G && img < B) decode_solve_and_store(keep, is_logits != 0, img, quat_out, hinv_out, flags);
   }
 }
 

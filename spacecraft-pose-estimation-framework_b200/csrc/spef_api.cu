@@ -786,7 +786,11 @@ static int decode_ori_ld(spef_ctx* ctx, const float* in, int ld, int B, int n, i
   if (!ctx->ori_tab) return fail(ctx, SPEF_ERR_STATE, "decode_ori: orientation histogram not set (spef_set_ori_histogram)");
   if (n != ctx->ori_n) return fail(ctx, SPEF_ERR_INVALID, "decode_ori: n = %d but the histogram has %d bins", n, ctx->ori_n);
   if (!in || !quat || B < 1) return fail(ctx, SPEF_ERR_INVALID, "decode_ori: bad argument");
-  decode_ori_kernel<<<cdiv(B, 4), 128, 0, st>>>(in, ld, B, n, is_logits, ctx->ori_tab, soft, quat, hinv, amax, flags);
+  // images per warp: 32 (eigen-solves fully lane-parallel) once there are enough images to fill the GPU that way
+  const long long fill = (long long)ctx->num_sms * 16;  // warps needed for ~16 warps per SM
+  if ((long long)B >= 32 * fill) decode_ori_kernel<32><<<cdiv(cdiv(B, 32), 4), 128, 0, st>>>(in, ld, B, n, is_logits, ctx->ori_tab, soft, quat, hinv, amax, flags);
+  else if ((long long)B >= 8 * fill) decode_ori_kernel<8><<<cdiv(cdiv(B, 8), 4), 128, 0, st>>>(in, ld, B, n, is_logits, ctx->ori_tab, soft, quat, hinv, amax, flags);
+  else decode_ori_kernel<1><<<cdiv(B, 4), 128, 0, st>>>(in, ld, B, n, is_logits, ctx->ori_tab, soft, quat, hinv, amax, flags);
   CK_LAUNCH("decode_ori_kernel");
   return SPEF_OK;
 }
