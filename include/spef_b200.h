@@ -89,6 +89,13 @@ int spef_finalize_weights(spef_ctx* ctx);
 int spef_set_ori_histogram(spef_ctx* ctx, const double* quat_bins_host /*[n,4]*/, int32_t n);
 int spef_set_pos_histogram(spef_ctx* ctx, const double* pos_bins_host /*[n,3]*/, int32_t n);
 
+/* ---- image element type (input side of the path, src/data/utils.py:212-249): SPEF_IMG_F32 (default) is the reference's
+ * tensor contract, float32 in [0,1]; SPEF_IMG_U8 takes the 8-bit pixels that ToTensor divides by 255 -- the stem computes
+ * float(u8) / 255.0f itself, bit-identical to feeding the float tensor, with 4x less host-to-device and HBM traffic.
+ * Applies to every images_* argument of this context (BF16 engine, tcgen05 path only). */
+enum { SPEF_IMG_F32 = 0, SPEF_IMG_U8 = 1 };
+int spef_set_image_dtype(spef_ctx* ctx, int32_t image_dtype);
+
 /* ---- network: replaces ModelWrapper.forward (src/modeling/common/pytorch_layers.py:29-32) ------ */
 int spef_forward(spef_ctx* ctx, const float* images_dev, int32_t batch,
                  float* ori_out_dev /*[B,n_ori] logits*/, float* pos_out_dev /*[B,n_pos]*/, void* stream);
@@ -140,6 +147,13 @@ int spef_eval_reset(spef_ctx* ctx, void* stream);
 int spef_eval_batch_host(spef_ctx* ctx, const float* images_host, const float* quat_true_host,
                          const float* pos_true_host, int32_t batch, float* per_image_out_host /*[B,2] or NULL*/,
                          void* stream);
+/* pipelined variant of spef_eval_batch_host for loaders that keep several batches in flight: the H2D copy of this
+ * batch runs on an internal copy stream into one of two staging buffers while the previous batch is still computing on
+ * `stream`; the call returns without synchronising.  per_image_out_host (pinned, or NULL) is filled asynchronously and is
+ * valid after spef_eval_wait.  images / targets must stay valid until spef_eval_wait (or two further submits). */
+int spef_eval_submit_host(spef_ctx* ctx, const float* images_host, const float* quat_true_host,
+                          const float* pos_true_host, int32_t batch, float* per_image_out_host, void* stream);
+int spef_eval_wait(spef_ctx* ctx, void* stream);
 int spef_eval_batch(spef_ctx* ctx, const float* images_dev, const float* quat_true_dev,
                     const float* pos_true_dev, int32_t batch, float* per_image_out_dev, void* stream);
 int spef_eval_read(spef_ctx* ctx, double* sums_host /*[8]*/, void* stream);

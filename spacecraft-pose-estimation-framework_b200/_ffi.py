@@ -47,6 +47,7 @@ SIGNATURES = {
     "spef_finalize_weights": (C.c_int, [_vp]),
     "spef_set_ori_histogram": (C.c_int, [_vp, _vp, _i32]),
     "spef_set_pos_histogram": (C.c_int, [_vp, _vp, _i32]),
+    "spef_set_image_dtype": (C.c_int, [_vp, _i32]),
     "spef_forward": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp]),
     "spef_num_layers": (C.c_int, [_vp]),
     "spef_layer_info": (C.c_int, [_vp, _i32] + [C.POINTER(_i32)] * 10),
@@ -59,6 +60,8 @@ SIGNATURES = {
     "spef_eval_reset": (C.c_int, [_vp, _vp]),
     "spef_eval_batch_host": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _vp, _vp]),
     "spef_eval_batch": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _vp, _vp]),
+    "spef_eval_submit_host": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _vp, _vp]),
+    "spef_eval_wait": (C.c_int, [_vp, _vp]),
     "spef_eval_read": (C.c_int, [_vp, _vp, _vp]),
     "spef_eval_sums_dev": (_vp, [_vp]),
     "spef_decode_ori_host": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),

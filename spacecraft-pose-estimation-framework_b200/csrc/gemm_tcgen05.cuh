@@ -39,6 +39,7 @@ struct GemmParams {
   // im2col producer (stem as an implicit GEMM): image [B,3,H,W] f32 NCHW, output pixels [B,Ho,Wo]
   const float* img;
   int img_h, img_w, out_h, out_w;
+  int img_u8;          // 1: img points at uint8 pixels, value = float(u8) / 255.0f (torchvision ToTensor)
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------

@@ -208,46 +208,84 @@ pw_gemm_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     // the 128B-swizzled K-major layout the UMMA descriptor expects (16-byte chunk c of row r at r*128 + ((c ^ (r & 7)) << 4)).
     const int t = (int)threadIdx.x - 128;
     const int H = p.img_h, W = p.img_w, Ho = p.out_h, Wo = p.out_w;
-    auto gather = [&](int tile, float (&tap)[27]) {
+    // uint8 images: a 256-entry table maps a pixel to bf16(float(u8) / 255.0f), exactly what rounding the reference's
+    // float tensor gives; the table lives at the end of the bias area (bias_floats() reserves 256 spare floats)
+    uint16_t* lut = reinterpret_cast<uint16_t*>(bias_s + bias_floats(p.N) - 128);
+    if (p.img_u8) {
+      for (int i = t; i < 256; i += 128) {
+        const bf16 h = __float2bfloat16_rn(__fdiv_rn((float)i, 255.0f));
+        lut[i] = *reinterpret_cast<const uint16_t*>(&h);
+      }
+      asm volatile("bar.sync 2, 128;" ::: "memory");  // producer warps only
+    }
+    // gather: 27 taps of this thread's output pixel as bf16 bit patterns (zero outside the image / beyond M)
+    auto gather = [&](int tile, uint16_t (&tap)[27]) {
       const int m = tile * BLOCK_M + t;
       const bool m_ok = m < p.M;
       const int mm = m_ok ? m : 0;
       const int ox = mm % Wo;
       const int oy = (mm / Wo) % Ho;
       const int b = mm / (Wo * Ho);
-      const float* ib = p.img + (size_t)b * 3 * H * W;
+      const size_t base = (size_t)b * 3 * H * W;
+      if (p.img_u8) {
+        const uint8_t* ib = reinterpret_cast<const uint8_t*>(p.img) + base;
+        uint8_t raw[27];
+        bool okm[27];
 #pragma unroll
-      for (int ky = 0; ky < 3; ++ky) {
-        const int iy = oy * 2 - 1 + ky;
-        const bool yok = m_ok && (iy >= 0) && (iy < H);
-        const int iyc = min(max(iy, 0), H - 1);
+        for (int ky = 0; ky < 3; ++ky) {
+          const int iy = oy * 2 - 1 + ky;
+          const bool yok = m_ok && (iy >= 0) && (iy < H);
+          const int iyc = min(max(iy, 0), H - 1);
 #pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-          const int ix = ox * 2 - 1 + kx;
-          const bool ok = yok && (ix >= 0) && (ix < W);
-          const int ixc = min(max(ix, 0), W - 1);
+          for (int kx = 0; kx < 3; ++kx) {
+            const int ix = ox * 2 - 1 + kx;
+            const bool ok = yok && (ix >= 0) && (ix < W);
+            const int ixc = min(max(ix, 0), W - 1);
 #pragma unroll
-          for (int ci = 0; ci < 3; ++ci) {
-            const float v = __ldg(ib + ((size_t)ci * H + iyc) * W + ixc);
-            tap[(ci * 3 + ky) * 3 + kx] = ok ? v : 0.f;
+            for (int ci = 0; ci < 3; ++ci) {
+              raw[(ci * 3 + ky) * 3 + kx] = __ldg(ib + ((size_t)ci * H + iyc) * W + ixc);
+              okm[(ci * 3 + ky) * 3 + kx] = ok;
+            }
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 27; ++k) tap[k] = okm[k] ? lut[raw[k]] : (uint16_t)0;
+      } else {
+        const float* ib = p.img + base;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+          const int iy = oy * 2 - 1 + ky;
+          const bool yok = m_ok && (iy >= 0) && (iy < H);
+          const int iyc = min(max(iy, 0), H - 1);
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            const int ix = ox * 2 - 1 + kx;
+            const bool ok = yok && (ix >= 0) && (ix < W);
+            const int ixc = min(max(ix, 0), W - 1);
+#pragma unroll
+            for (int ci = 0; ci < 3; ++ci) {
+              const float v = __ldg(ib + ((size_t)ci * H + iyc) * W + ixc);
+              const bf16 h = __float2bfloat16_rn(ok ? v : 0.f);
+              tap[(ci * 3 + ky) * 3 + kx] = *reinterpret_cast<const uint16_t*>(&h);
+            }
           }
         }
       }
     };
     int stage = 0;
     uint32_t phase = 0;
-    float cur[27], nxt[27];
+    uint16_t cur[27], nxt[27];
     if ((int)blockIdx.x < num_tiles) gather(blockIdx.x, cur);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      // software pipeline: the taps of the next tile are in flight while this one is converted and staged
+      // software pipeline: the taps of the next tile are in flight while this one is staged
       const int next = tile + (int)gridDim.x;
       if (next < num_tiles) gather(next, nxt);
       uint32_t pk[16];
 #pragma unroll
       for (int k = 0; k < 16; ++k) {
-        const float lo = (2 * k < 27) ? cur[2 * k] : 0.f;
-        const float hi = (2 * k + 1 < 27) ? cur[2 * k + 1] : 0.f;
-        pk[k] = Vec8<bf16>::pack2(lo, hi);
+        const uint32_t lo = (2 * k < 27) ? cur[2 * k] : 0u;
+        const uint32_t hi = (2 * k + 1 < 27) ? cur[2 * k + 1] : 0u;
+        pk[k] = lo | (hi << 16);
       }
       mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
       const uint32_t sa = smem_u32(stage_base + (size_t)stage * sbytes) + (uint32_t)t * 128u;

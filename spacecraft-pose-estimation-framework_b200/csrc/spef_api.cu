@@ -70,6 +70,7 @@ struct spef_ctx {
   int gemm_ng = 2;  // epilogue groups of the tcgen05 GEMM (SPEF_GEMM_NG = 1 | 2)
   long long* trace_dev = nullptr;  // SPEF_GEMM_TRACE=<layer index>: dump CTA-0 timestamps of that layer to stderr
   int trace_layer = -1;
+  int image_u8 = 0;    // SPEF_IMG_U8: images are uint8, the stem divides by 255
   int gemm_impl = 2;   // 2: drain/store warp-specialised epilogue (default); 1: v1 epilogue (SPEF_GEMM_IMPL=1)
   int gemm_nsw = 4;    // store warps of the v2 epilogue (SPEF_GEMM_NSW = 4 | 8; 8 only with one drain group)
   int gemm_ndg = 2;    // drain groups of the v2 epilogue (SPEF_GEMM_NDG = 1 | 2)
@@ -91,6 +92,16 @@ struct spef_ctx {
   double* eval_sums = nullptr;  // [8]
   // workspaces for the *_host entry points and fused predict
   float* ws_images = nullptr;
+  // pipelined host evaluation: two staging slots (images + targets + per-image results), a copy stream and events
+  float* pipe_images[2] = {nullptr, nullptr};
+  float* pipe_qt[2] = {nullptr, nullptr};
+  float* pipe_tt[2] = {nullptr, nullptr};
+  float* pipe_per[2] = {nullptr, nullptr};
+  cudaStream_t pipe_copy_stream = nullptr;
+  cudaEvent_t pipe_copied[2] = {nullptr, nullptr};   // H2D of slot s complete
+  cudaEvent_t pipe_consumed[2] = {nullptr, nullptr}; // compute that read slot s complete
+  int pipe_slot = 0;
+  long long pipe_submitted = 0;
   float* ws_quat = nullptr;     // [max_batch,4]
   float* ws_pos = nullptr;      // [max_batch,3]
   float* ws_qt = nullptr;       // [max_batch,4]
@@ -318,6 +329,12 @@ extern "C" void spef_destroy(spef_ctx* ctx) {
   for (void* p : ptrs) cudaFree(p);
   for (int i = 0; i < 8; ++i) cudaFree(ctx->t_ws[i]);
   for (cudaEvent_t ev : ctx->events) cudaEventDestroy(ev);
+  for (int s = 0; s < 2; ++s) {
+    cudaFree(ctx->pipe_images[s]); cudaFree(ctx->pipe_qt[s]); cudaFree(ctx->pipe_tt[s]); cudaFree(ctx->pipe_per[s]);
+    if (ctx->pipe_copied[s]) cudaEventDestroy(ctx->pipe_copied[s]);
+    if (ctx->pipe_consumed[s]) cudaEventDestroy(ctx->pipe_consumed[s]);
+  }
+  if (ctx->pipe_copy_stream) cudaStreamDestroy(ctx->pipe_copy_stream);
   delete ctx;
 }
 
@@ -610,6 +627,7 @@ static int launch_stem_tcgen05(spef_ctx* ctx, Layer& l, const void* images, void
   memset(&p, 0, sizeof(p));
   p.bias = l.bias; p.residual = nullptr; p.M = B * l.hout * l.wout; p.N = 32; p.K = 32; p.block_n = 32; p.num_stages = l.stages; p.relu = 1;
   p.store_mode = 0; p.out = out; p.ldd = 32; p.trace = nullptr;
+  p.img_u8 = ctx->image_u8;
   p.img = (const float*)images; p.img_h = l.hin; p.img_w = l.win; p.out_h = l.hout; p.out_w = l.wout;
   const int tiles = cdiv(p.M, tc::BLOCK_M);
   const int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
@@ -635,7 +653,7 @@ static int launch_tcgen05_layer(spef_ctx* ctx, Layer& l, const void* in, const v
   tc::GemmParams p;
   p.bias = l.bias; p.residual = (const bf16*)res; p.M = M; p.N = N; p.K = K; p.block_n = l.block_n; p.num_stages = l.stages; p.relu = l.relu;
   p.store_mode = ctx->gemm_store; p.out = out; p.ldd = N;
-  p.img = nullptr; p.img_h = p.img_w = p.out_h = p.out_w = 0;
+  p.img = nullptr; p.img_h = p.img_w = p.out_h = p.out_w = 0; p.img_u8 = 0;
   const bool trace = ctx->trace_dev && (&l == &ctx->layers[ctx->trace_layer < (int)ctx->layers.size() && ctx->trace_layer >= 0 ? ctx->trace_layer : 0]) && ctx->trace_layer >= 0;
   p.trace = (trace && ctx->gemm_impl == 1) ? ctx->trace_dev : nullptr;
   if (trace) cudaMemsetAsync(ctx->trace_dev, 0, 256 * 8 * sizeof(long long), st);
@@ -681,6 +699,8 @@ static int launch_tcgen05_layer(spef_ctx* ctx, Layer& l, const void* in, const v
 
 static int run_layer(spef_ctx* ctx, Layer& l, const void* in, const void* res, void* out, int B, cudaStream_t st, bool cached_maps) {
   const bool use_bf16 = ctx->cfg.precision == SPEF_BF16;
+  if (l.kind == K_STEM && ctx->image_u8 && !(use_bf16 && ctx->cfg.pw_impl == 0 && ctx->gemm_impl == 2 && !getenv("SPEF_STEM_SIMT")))
+    return fail(ctx, SPEF_ERR_UNSUPPORTED, "uint8 images are implemented on the BF16 tcgen05 stem only");
   if (use_bf16 && (l.kind == K_PW || l.kind == K_HEAD) && ctx->cfg.pw_impl == 0) return launch_tcgen05_layer(ctx, l, in, res, out, B, st, cached_maps);
   if (use_bf16 && l.kind == K_DW && ctx->cfg.pw_impl == 0) return launch_dw_tma_layer(ctx, l, in, out, B, st, cached_maps);
   if (use_bf16 && l.kind == K_STEM && ctx->cfg.pw_impl == 0 && ctx->gemm_impl == 2 && !getenv("SPEF_STEM_SIMT")) return launch_stem_tcgen05(ctx, l, in, out, B, st);
@@ -748,6 +768,14 @@ extern "C" int spef_forward_timed(spef_ctx* ctx, const float* images_dev, int32_
   rc = forward_internal(ctx, images_dev, B, (cudaStream_t)stream, layer_ms);
   if (rc) return rc;
   return copy_head_out(ctx, B, ori_out, pos_out, (cudaStream_t)stream);
+}
+
+extern "C" int spef_set_image_dtype(spef_ctx* ctx, int32_t dt) {
+  if (!ctx) return SPEF_ERR_INVALID;
+  if (dt != SPEF_IMG_F32 && dt != SPEF_IMG_U8) return fail(ctx, SPEF_ERR_INVALID, "spef_set_image_dtype: unknown dtype %d", dt);
+  if (dt == SPEF_IMG_U8 && ctx->cfg.precision != SPEF_BF16) return fail(ctx, SPEF_ERR_UNSUPPORTED, "uint8 images need the BF16 engine");
+  ctx->image_u8 = (dt == SPEF_IMG_U8);
+  return SPEF_OK;
 }
 
 extern "C" int spef_num_layers(const spef_ctx* ctx) { return ctx ? (int)ctx->layers.size() : 0; }
@@ -884,7 +912,7 @@ extern "C" int spef_predict_host(spef_ctx* ctx, const float* images_host, int32_
   CK(cudaSetDevice(ctx->cfg.device));
   cudaStream_t st = (cudaStream_t)stream;
   if ((rc = ensure_ws_images(ctx))) return rc;
-  const size_t img_bytes = (size_t)B * 3 * ctx->cfg.img_h * ctx->cfg.img_w * sizeof(float);
+  const size_t img_bytes = (size_t)B * 3 * ctx->cfg.img_h * ctx->cfg.img_w * (ctx->image_u8 ? 1 : sizeof(float));
   CK(cudaMemcpyAsync(ctx->ws_images, images_host, img_bytes, cudaMemcpyHostToDevice, st));
   float* soft_d = nullptr;
   float* psoft_d = nullptr;
@@ -936,7 +964,7 @@ extern "C" int spef_eval_batch_host(spef_ctx* ctx, const float* images_host, con
   CK(cudaSetDevice(ctx->cfg.device));
   cudaStream_t st = (cudaStream_t)stream;
   if ((rc = ensure_ws_images(ctx))) return rc;
-  CK(cudaMemcpyAsync(ctx->ws_images, images_host, (size_t)B * 3 * ctx->cfg.img_h * ctx->cfg.img_w * sizeof(float), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->ws_images, images_host, (size_t)B * 3 * ctx->cfg.img_h * ctx->cfg.img_w * (ctx->image_u8 ? 1 : sizeof(float)), cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(ctx->ws_qt, qt_h, (size_t)B * 16, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(ctx->ws_tt, tt_h, (size_t)B * 12, cudaMemcpyHostToDevice, st));
   rc = spef_eval_batch(ctx, ctx->ws_images, ctx->ws_qt, ctx->ws_tt, B, per_image_h ? ctx->ws_per_image : nullptr, stream);
@@ -945,6 +973,54 @@ extern "C" int spef_eval_batch_host(spef_ctx* ctx, const float* images_host, con
     CK(cudaMemcpyAsync(per_image_h, ctx->ws_per_image, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
   }
+  return SPEF_OK;
+}
+
+static int ensure_pipe(spef_ctx* ctx) {
+  if (ctx->pipe_copy_stream) return SPEF_OK;
+  const size_t B = (size_t)ctx->cfg.max_batch;
+  CK(cudaStreamCreateWithFlags(&ctx->pipe_copy_stream, cudaStreamNonBlocking));
+  for (int s = 0; s < 2; ++s) {
+    CK(cudaMalloc((void**)&ctx->pipe_images[s], B * 3 * ctx->cfg.img_h * ctx->cfg.img_w * sizeof(float)));
+    CK(cudaMalloc((void**)&ctx->pipe_qt[s], B * 16));
+    CK(cudaMalloc((void**)&ctx->pipe_tt[s], B * 12));
+    CK(cudaMalloc((void**)&ctx->pipe_per[s], B * 8));
+    CK(cudaEventCreateWithFlags(&ctx->pipe_copied[s], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ctx->pipe_consumed[s], cudaEventDisableTiming));
+  }
+  return SPEF_OK;
+}
+
+extern "C" int spef_eval_submit_host(spef_ctx* ctx, const float* images_host, const float* qt_h, const float* tt_h, int32_t B,
+                                     float* per_image_h, void* stream) {
+  int rc = check_ready(ctx, B, "spef_eval_submit_host");
+  if (rc) return rc;
+  if (!images_host || !qt_h || !tt_h) return fail(ctx, SPEF_ERR_INVALID, "spef_eval_submit_host: NULL argument");
+  CK(cudaSetDevice(ctx->cfg.device));
+  if ((rc = ensure_pipe(ctx))) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int s = ctx->pipe_slot;
+  // the copy into slot s may start once the compute that last read slot s (two submits ago) has finished
+  if (ctx->pipe_submitted >= 2) CK(cudaStreamWaitEvent(ctx->pipe_copy_stream, ctx->pipe_consumed[s], 0));
+  CK(cudaMemcpyAsync(ctx->pipe_images[s], images_host, (size_t)B * 3 * ctx->cfg.img_h * ctx->cfg.img_w * (ctx->image_u8 ? 1 : sizeof(float)), cudaMemcpyHostToDevice, ctx->pipe_copy_stream));
+  CK(cudaMemcpyAsync(ctx->pipe_qt[s], qt_h, (size_t)B * 16, cudaMemcpyHostToDevice, ctx->pipe_copy_stream));
+  CK(cudaMemcpyAsync(ctx->pipe_tt[s], tt_h, (size_t)B * 12, cudaMemcpyHostToDevice, ctx->pipe_copy_stream));
+  CK(cudaEventRecord(ctx->pipe_copied[s], ctx->pipe_copy_stream));
+  CK(cudaStreamWaitEvent(st, ctx->pipe_copied[s], 0));
+  rc = spef_eval_batch(ctx, ctx->pipe_images[s], ctx->pipe_qt[s], ctx->pipe_tt[s], B, per_image_h ? ctx->pipe_per[s] : nullptr, stream);
+  if (rc) return rc;
+  if (per_image_h) CK(cudaMemcpyAsync(per_image_h, ctx->pipe_per[s], (size_t)B * 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaEventRecord(ctx->pipe_consumed[s], st));
+  ctx->pipe_slot ^= 1;
+  ctx->pipe_submitted++;
+  return SPEF_OK;
+}
+
+extern "C" int spef_eval_wait(spef_ctx* ctx, void* stream) {
+  if (!ctx) return SPEF_ERR_INVALID;
+  CK(cudaSetDevice(ctx->cfg.device));
+  if (ctx->pipe_copy_stream) CK(cudaStreamSynchronize(ctx->pipe_copy_stream));
+  CK(cudaStreamSynchronize((cudaStream_t)stream));
   return SPEF_OK;
 }
 

@@ -47,6 +47,7 @@ class Engine:
         self.n_ori, self.n_pos, self.pos_classification = n_ori, n_pos, bool(pos_classification)
         self.max_batch, self.img_h, self.img_w = max_batch, img_h, img_w
         self.weights_ready = False
+        self.image_dtype = torch.float32
         self.ori_hist_n = self.pos_hist_n = 0
 
     # ---- lifecycle -------------------------------------------------------------------------------
@@ -89,6 +90,12 @@ class Engine:
         self._ck(self.lib.spef_set_pos_histogram(self._h, h.ctypes.data, h.shape[0]))
         self.pos_hist_n = h.shape[0]
 
+    def set_image_dtype(self, dtype: torch.dtype):
+        """torch.float32 (reference contract, default) or torch.uint8 (pixels before ToTensor's /255; the stem divides)."""
+        assert dtype in (torch.float32, torch.uint8)
+        self._ck(self.lib.spef_set_image_dtype(self._h, 1 if dtype == torch.uint8 else 0))
+        self.image_dtype = dtype
+
     # ---- helpers ---------------------------------------------------------------------------------
     def _dev_f32(self, x, shape=None) -> torch.Tensor:
         t = torch.as_tensor(x)
@@ -96,6 +103,12 @@ class Engine:
         if shape is not None:
             assert tuple(t.shape) == tuple(shape), f"expected shape {shape}, got {tuple(t.shape)}"
         return t
+
+    def _dev_img(self, images: torch.Tensor) -> torch.Tensor:
+        if self.image_dtype == torch.uint8:
+            assert images.dtype == torch.uint8, "engine is set to uint8 images"
+            return images.to(self.device, non_blocking=True).contiguous()
+        return self._dev_f32(images)
 
     def _empty(self, *shape, dtype=torch.float32) -> torch.Tensor:
         return torch.empty(*shape, dtype=dtype, device=self.device)
@@ -111,14 +124,14 @@ class Engine:
     def forward(self, images: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         """ModelWrapper.forward: images [B,3,H,W] f32 on this device -> (ori logits [B,n_ori], pos [B,n_pos])."""
         B = self._check_images(images)
-        x = self._dev_f32(images)
+        x = self._dev_img(images)
         ori, pos = self._empty(B, self.n_ori), self._empty(B, self.n_pos)
         self._ck(self.lib.spef_forward(self._h, ptr(x), B, ptr(ori), ptr(pos), _stream(self.device)))
         return ori, pos
 
     def forward_timed(self, images: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, np.ndarray]:
         B = self._check_images(images)
-        x = self._dev_f32(images)
+        x = self._dev_img(images)
         ori, pos = self._empty(B, self.n_ori), self._empty(B, self.n_pos)
         ms = np.zeros(self.num_layers(), np.float32)
         self._ck(self.lib.spef_forward_timed(self._h, ptr(x), B, ptr(ori), ptr(pos), ms.ctypes.data, _stream(self.device)))
@@ -191,7 +204,7 @@ class Engine:
     def predict(self, images: torch.Tensor, want_soft=True, want_argmax=False) -> Dict[str, torch.Tensor]:
         """forward + softmax + decode on device tensors (spef_predict)."""
         B = self._check_images(images)
-        x = self._dev_f32(images)
+        x = self._dev_img(images)
         out = {"ori": self._empty(B, 4), "pos": self._empty(B, 3), "flags": torch.zeros(B, dtype=torch.int32, device=self.device)}
         if want_soft:
             out["ori_soft"] = self._empty(B, self.n_ori)
@@ -235,10 +248,27 @@ class Engine:
             self._ck(self.lib.spef_eval_batch_host(self._h, x.data_ptr(), qt.ctypes.data, tt.ctypes.data, B, ptr(per),
                                                    _stream(self.device)))
             return per
-        x, qt, tt = self._dev_f32(images), self._dev_f32(quat_true, (B, 4)), self._dev_f32(pos_true, (B, 3))
+        x, qt, tt = self._dev_img(images), self._dev_f32(quat_true, (B, 4)), self._dev_f32(pos_true, (B, 3))
         per = self._empty(B, 2) if want_per_image else None
         self._ck(self.lib.spef_eval_batch(self._h, ptr(x), ptr(qt), ptr(tt), B, ptr(per), _stream(self.device)))
         return per
+
+    def eval_submit_host(self, images: torch.Tensor, quat_true: torch.Tensor, pos_true: torch.Tensor,
+                         per_image_out: Optional[torch.Tensor] = None):
+        """Pipelined batch step (spef_eval_submit_host): H2D of this batch overlaps the compute of the previous one.
+        All tensors are CPU float32, contiguous (pinned for true overlap) and must stay alive until eval_wait()."""
+        B = self._check_images(images)
+        assert images.device.type == "cpu" and images.dtype == self.image_dtype and images.is_contiguous()
+        for t in (quat_true, pos_true):
+            assert t.device.type == "cpu" and t.dtype == torch.float32 and t.is_contiguous()
+        assert quat_true.shape == (B, 4) and pos_true.shape == (B, 3)
+        if per_image_out is not None:
+            assert per_image_out.device.type == "cpu" and per_image_out.dtype == torch.float32 and per_image_out.shape == (B, 2)
+        self._ck(self.lib.spef_eval_submit_host(self._h, images.data_ptr(), quat_true.data_ptr(), pos_true.data_ptr(), B,
+                                                ptr(per_image_out), _stream(self.device)))
+
+    def eval_wait(self):
+        self._ck(self.lib.spef_eval_wait(self._h, _stream(self.device)))
 
     def eval_read(self) -> np.ndarray:
         s = np.zeros(8, np.float64)
@@ -310,7 +340,7 @@ class Engine:
 
     def temporal_step(self, images: torch.Tensor, apply_filter: bool = True) -> Dict[str, torch.Tensor]:
         S = self._check_images(images)
-        x = self._dev_f32(images)
+        x = self._dev_img(images)
         t, st = self._temporal_out(S)
         self._ck(self.lib.spef_temporal_step(self._h, ptr(x), S, int(apply_filter), C.byref(st), _stream(self.device)))
         if not apply_filter:

@@ -82,11 +82,25 @@ def evaluation(
         if isinstance(spe_model, SPEB200):
             eng = spe_model.engine
             eng.eval_reset()
-            per = []
+            per, keep = [], []
             for images, targets in dataloader[phase]:
-                per.append(eng.eval_batch(images['torch'], targets['ori'], targets['pos'], want_per_image=True))
+                x = images['torch']
+                if x.device.type == "cpu":
+                    # pipelined: the H2D copy of this batch overlaps the kernels of the previous one; host buffers are kept
+                    # alive until the phase is drained
+                    x = x.detach().to(torch.float32).contiguous()
+                    qt = torch.as_tensor(targets['ori']).detach().to("cpu", torch.float32).contiguous()
+                    tt = torch.as_tensor(targets['pos']).detach().to("cpu", torch.float32).contiguous()
+                    out = torch.empty((x.shape[0], 2), dtype=torch.float32, pin_memory=True)
+                    eng.eval_submit_host(x, qt, tt, out)
+                    keep.append((x, qt, tt))
+                    per.append(out)
+                else:
+                    per.append(eng.eval_batch(x, targets['ori'], targets['pos'], want_per_image=True))
+            eng.eval_wait()
             sums = eng.eval_read()
             per = [p.cpu().numpy() if isinstance(p, torch.Tensor) else p for p in per]
+            del keep
             per_image = np.concatenate(per, axis=0) if per else np.zeros((0, 2), np.float32)
             _finish(rec_score, rec_error, phase, sums, per_image, eng.device)
         else:

@@ -240,3 +240,21 @@ def test_full_batch_256_properties(sd):
     assert rel(o.cpu().numpy(), want_ori.numpy()) < 3e-2
     want_q, _ = O.ori_decode_batch(O.softmax(o.cpu().numpy()), O.ori_histogram(12)[0])
     assert O.quat_angle_deg(qa[:4], want_q).max() <= 0.05   # decode on identical logits: the 0.05 deg gate
+
+
+def test_uint8_images_equal_float_images(sd):
+    """Input side of the path: uint8 pixels (what ToTensor divides by 255) give bit-identical results to the float
+    tensor of the reference contract, because the stem maps a pixel to bf16(float(u8) / 255.0f) itself."""
+    eng = _engine(sd, "bf16")
+    g = torch.Generator().manual_seed(3)
+    u8 = torch.randint(0, 256, (3, 3, 240, 384), generator=g, dtype=torch.uint8)
+    f32 = u8.float().div(255)          # torchvision ToTensor semantics
+    o_f, p_f = eng.forward(f32)
+    eng.set_image_dtype(torch.uint8)
+    o_u, p_u = eng.forward(u8)
+    eng.set_image_dtype(torch.float32)
+    np.testing.assert_array_equal(o_u.cpu().numpy(), o_f.cpu().numpy())
+    np.testing.assert_array_equal(p_u.cpu().numpy(), p_f.cpu().numpy())
+    fp32 = _engine(sd, "fp32")
+    with pytest.raises(Exception, match="BF16"):
+        fp32.set_image_dtype(torch.uint8)
