@@ -203,8 +203,31 @@ def layer_table(eng, batch, ms):
         else:
             by, fl = ein * esz + eout * 4 + li["cin"] * li["cout"] * esz, 2 * li["cin"] * eout
         rows.append({"layer": i, "kernel": kinds[k], "cin": li["cin"], "cout": li["cout"], "hw": f"{li['hout']}x{li['wout']}",
-                     "stride": li["stride"], "bytes": by, "flops": fl, "ms": float(ms[i])})
-    return rows
+                     "stride": li["stride"], "bytes": by, "flops": fl, "ms": float(ms[i]), "ein": ein, "eout": eout,
+                     "residual": li["residual"]})
+    # fused InvertedResidual blocks: one launch covers expand + depthwise + project; its compulsory traffic is the block
+    # boundary (read x once, write y once) and its time is reported in the slot of the block's first layer
+    merged, skip = [], set()
+    fused_first = {}
+    for b in range(eng.num_blocks()):
+        bi = eng.block_info(b)
+        if bi["fused"]:
+            fused_first[bi["first_layer"]] = bi
+    for r in rows:
+        if r["layer"] in skip:
+            continue
+        bi = fused_first.get(r["layer"])
+        if bi is None:
+            merged.append(r)
+            continue
+        grp = rows[r["layer"]:r["layer"] + bi["n_layers"]]
+        skip.update(g["layer"] for g in grp)
+        merged.append({"layer": r["layer"], "kernel": "fused_block_kernel", "cin": grp[0]["cin"], "cout": grp[-1]["cout"],
+                       "hw": grp[-1]["hw"], "stride": max(g["stride"] for g in grp),
+                       "bytes": (grp[0]["ein"] + grp[-1]["eout"]) * esz, "flops": sum(g["flops"] for g in grp),
+                       "ms": sum(g["ms"] for g in grp), "hidden": grp[0]["cout"], "tile": f"{bi['tile_h']}x{bi['tile_w']}",
+                       "unfused_bytes": sum(g["bytes"] for g in grp)})
+    return merged
 
 
 def run_b200(args):

@@ -111,6 +111,19 @@ int spef_layer_info(const spef_ctx* ctx, int32_t layer, int32_t* kind /*0 stem,1
 int spef_layer_forward(spef_ctx* ctx, int32_t layer, const void* in_dev, const void* residual_dev,
                        void* out_dev, int32_t batch, void* stream);
 
+/* InvertedResidual blocks (src/modeling/common/pytorch_layers.py:65-98; 17 of them, mobilenet_v2.py:240-262).
+ * On the BF16 tcgen05 path a block runs as ONE kernel (expand 1x1 -> depthwise 3x3 -> project 1x1 [+ x]) whose
+ * hidden tensor stays in shared memory / TMEM.  spef_block_info reports which layers [first_layer, first_layer +
+ * n_layers) a block covers and whether it is fused in the current configuration (plus its tile plan);
+ * spef_block_forward is the teacher-forced single block (in [B,H,W,Cin] -> out [B,Ho,Wo,Cout], NHWC bf16) and fails with
+ * SPEF_ERR_UNSUPPORTED for a block that is not fused.  spef_set_fusion(0) makes spef_forward run the per-layer kernels
+ * (the parity cross-check of the fused path); default on, or SPEF_FUSE=0 in the environment. */
+int spef_num_blocks(const spef_ctx* ctx);
+int spef_block_info(const spef_ctx* ctx, int32_t block, int32_t* first_layer, int32_t* n_layers, int32_t* fused,
+                    int32_t* tile_h, int32_t* tile_w, int32_t* groups, int32_t* w_stages, int32_t* resident);
+int spef_set_fusion(spef_ctx* ctx, int32_t on);
+int spef_block_forward(spef_ctx* ctx, int32_t block, const void* in_dev, void* out_dev, int32_t batch, void* stream);
+
 /* ---- post-processing -------------------------------------------------------------------------
  * spef_decode_ori replaces SPEUtils.last_activ (softmax, src/spe/spe_utils.py:75-76) when
  * is_logits != 0, and OrientationSoftClassification.decode_batch

@@ -52,6 +52,10 @@ SIGNATURES = {
     "spef_num_layers": (C.c_int, [_vp]),
     "spef_layer_info": (C.c_int, [_vp, _i32] + [C.POINTER(_i32)] * 10),
     "spef_layer_forward": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _i32, _vp]),
+    "spef_num_blocks": (C.c_int, [_vp]),
+    "spef_block_info": (C.c_int, [_vp, _i32] + [C.POINTER(_i32)] * 8),
+    "spef_set_fusion": (C.c_int, [_vp, _i32]),
+    "spef_block_forward": (C.c_int, [_vp, _i32, _vp, _vp, _i32, _vp]),
     "spef_decode_ori": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "spef_decode_pos": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "spef_score": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),

@@ -167,6 +167,30 @@ class Engine:
         self._ck(self.lib.spef_layer_forward(self._h, i, ptr(x), ptr(r), ptr(out), B, _stream(self.device)))
         return out
 
+    # ---- fused InvertedResidual blocks ----------------------------------------------------------------
+    def num_blocks(self) -> int:
+        return self.lib.spef_num_blocks(self._h)
+
+    def block_info(self, i: int) -> dict:
+        v = [C.c_int32() for _ in range(8)]
+        self._ck(self.lib.spef_block_info(self._h, i, *[C.byref(x) for x in v]))
+        names = ("first_layer", "n_layers", "fused", "tile_h", "tile_w", "groups", "w_stages", "resident")
+        return {n: x.value for n, x in zip(names, v)}
+
+    def set_fusion(self, on: bool):
+        """True (default): InvertedResidual blocks run as one fused kernel each; False: per-layer kernels."""
+        self._ck(self.lib.spef_set_fusion(self._h, 1 if on else 0))
+
+    def block_forward(self, i: int, x: torch.Tensor) -> torch.Tensor:
+        """Teacher-forced fused block: x NHWC [B,H,W,Cin] bf16 -> [B,Ho,Wo,Cout] bf16."""
+        bi = self.block_info(i)
+        last = self.layer_info(bi["first_layer"] + bi["n_layers"] - 1)
+        x = x.to(self.device).contiguous()
+        assert x.dtype == torch.bfloat16
+        out = self._empty(x.shape[0], last["hout"], last["wout"], last["cout"], dtype=torch.bfloat16)
+        self._ck(self.lib.spef_block_forward(self._h, i, ptr(x), ptr(out), x.shape[0], _stream(self.device)))
+        return out
+
     # ---- post-processing (device tensors) --------------------------------------------------------
     def decode_ori(self, x: torch.Tensor, is_logits: bool, want_soft=False, want_hinv=False, want_argmax=False):
         x = self._dev_f32(x)

@@ -104,6 +104,57 @@ def test_every_layer_teacher_forced(sd, images, precision, pw_impl):
     print(f"[{precision} pw_impl={pw_impl}] worst per-layer relative error {worst:.3e}")
 
 
+def test_fused_blocks_teacher_forced(sd, images):
+    """Every fused InvertedResidual kernel (expand -> depthwise -> project [+ x] in one launch) on the oracle's BF16 input of
+    that block (B = 3).
+      * against the chain of per-layer kernels (each within 1 BF16 ulp of the oracle, test above): bit-identical -- same
+        rounding points, same FP32 accumulation order;
+      * against the oracle: the hidden activations are not teacher-forced inside a block, so a 1-ulp flip of a hidden BF16
+        value (FP32 accumulation order) moves a few block outputs by a few output ulps: < 1 % of the elements may differ
+        and none by more than 16 BF16 ulp (floored at 2^-8 of the tensor scale)."""
+    eng = _engine(sd, "bf16", 0)
+    x = images[:3]
+    ios = _oracle_layer_io(sd, x, True)
+    n_fused = 0
+    for bi in range(eng.num_blocks()):
+        info = eng.block_info(bi)
+        if not info["fused"]:
+            with pytest.raises(Exception, match="no fused kernel"):
+                eng.block_forward(bi, nhwc(ios[info["first_layer"]][0], torch.bfloat16))
+            continue
+        n_fused += 1
+        first, last = info["first_layer"], info["first_layer"] + info["n_layers"] - 1
+        inp = nhwc(ios[first][0], torch.bfloat16)
+        want = ios[last][2].permute(0, 2, 3, 1).contiguous()
+        got = eng.block_forward(bi, inp).float().cpu()
+        assert got.shape == want.shape, (bi, info)
+        cur = inp
+        for li in range(first, last + 1):
+            cur = eng.layer_forward(li, cur, inp if eng.layer_info(li)["residual"] else None)
+        np.testing.assert_array_equal(got.numpy(), cur.float().cpu().numpy(), err_msg=f"block {bi} {info} vs per-layer kernels")
+        scale = float(want.abs().max())
+        err = (got - want).abs()
+        ulp = torch.maximum(want.abs(), torch.tensor(scale * 2 ** -8)) * 2 ** -7
+        worst, frac_off = float((err / ulp).max()), float((err > 0).float().mean())
+        assert worst <= 16.0, f"block {bi} {info} vs oracle: {worst:.2f} BF16 ulp"
+        assert frac_off < 0.01, f"block {bi} {info} vs oracle: {frac_off:.4f} of the elements differ"
+    assert n_fused >= 8, f"only {n_fused} blocks are fused"
+
+
+def test_fused_forward_equals_per_layer_forward(sd):
+    """End to end: logits of the fused path vs the per-layer path (same rounding points) on a ragged batch."""
+    eng = _engine(sd, "bf16", 0)
+    x = synthetic.synthetic_images(5, seed=11)
+    o_f, p_f = [t.cpu().numpy() for t in eng.forward(x)]
+    eng.set_fusion(False)
+    assert not any(eng.block_info(i)["fused"] for i in range(eng.num_blocks()))
+    o_l, p_l = [t.cpu().numpy() for t in eng.forward(x)]
+    eng.set_fusion(True)
+    print(f"fused vs per-layer: logits {rel(o_f, o_l):.2e}, pos {rel(p_f, p_l):.2e}")
+    assert rel(o_f, o_l) < 3e-2 and rel(p_f, p_l) < 3e-2
+    assert (o_f.argmax(1) == o_l.argmax(1)).mean() >= 0.8
+
+
 @pytest.mark.parametrize("tag,n_pos", [("murso", 3), ("mursop", 1000)])
 def test_fp32_logits_vs_reference_golden(golden, images, tag, n_pos):
     g = golden("network")
