@@ -114,7 +114,8 @@ int spef_layer_forward(spef_ctx* ctx, int32_t layer, const void* in_dev, const v
 /* InvertedResidual blocks (src/modeling/common/pytorch_layers.py:65-98; 17 of them, mobilenet_v2.py:240-262).
  * On the BF16 tcgen05 path a block runs as ONE kernel (expand 1x1 -> depthwise 3x3 -> project 1x1 [+ x]) whose
  * hidden tensor stays in shared memory / TMEM.  spef_block_info reports which layers [first_layer, first_layer +
- * n_layers) a block covers and whether it is fused in the current configuration (plus its tile plan);
+ * n_layers) a block covers and whether it is fused in the current configuration (*fused = 0 per-layer kernels, 1 staged
+ * fused kernel, 2 channel-lane fused kernel; plus its tile plan);
  * spef_block_forward is the teacher-forced single block (in [B,H,W,Cin] -> out [B,Ho,Wo,Cout], NHWC bf16) and fails with
  * SPEF_ERR_UNSUPPORTED for a block that is not fused.  spef_set_fusion(0) makes spef_forward run the per-layer kernels
  * (the parity cross-check of the fused path); default on, or SPEF_FUSE=0 in the environment. */

@@ -1,0 +1,520 @@
+// Fused InvertedResidual block, "channel-lane" variant (second generation of fused_block.cuh; same reference semantics,
+// src/modeling/common/pytorch_layers.py:65-98, same rounding points as the per-layer kernels).
+//
+// What the clock64 traces of the first fused kernel showed: with the hidden tile staged in shared memory (TMEM -> regs ->
+// smem -> regs -> smem) the worker warps retire one instruction per ~4 cycles -- every phase is a chain of LDS / tcgen05.ld
+// latencies, and two block-wide phases per chunk need two barriers.  This variant removes the staging:
+//
+//   expand is computed TRANSPOSED:  D_e^T[hidden channel (128 TMEM lanes), box pixel (<= 128 columns)] = We_chunk * X_tile^T
+//     (A = We chunk [128 x Cin] K-major, B = the TMA-loaded x tile [pixels x Cin] K-major -- the same smem tiles as before
+//     with the operand roles swapped).
+//   A worker thread owns ONE hidden channel (its TMEM lane) for the whole chunk: 9 depthwise weights + 2 biases live in
+//     registers, it walks down the tile row by row: tcgen05.ld.x16 of one pixel row -> +bias, ReLU, round to BF16 (packed
+//     f32x2 / bf16x2 ops) -> 3-row register window -> 3x3 stride-S depthwise in FP32 -> +bias, ReLU, BF16 -> shared memory.
+//     No shared-memory loads and no intra-chunk barrier in the loop; image-border zero padding is a per-row / per-column
+//     select.
+//   The depthwise output is written as the MN-major (pixel-contiguous) A operand of the project GEMM
+//     D_p[pixel (128 lanes), Cout] += A2^T[channel, pixel]^T * Wp_chunk^T, so a thread stores runs of adjacent pixels of its
+//     channel (8-byte stores) instead of 2-byte scatters.
+//   Chunks hold up to 128 channels spread evenly over the four 32-lane TMEM quarters (a warp can only read its own
+//     quarter), so all four SM sub-partitions carry the same load even when Ch is not a multiple of 128; the host builds
+//     the permuted / zero-padded We', Wp' and aux arrays (a padding lane computes exact zeros end to end).
+//   Two worker groups (4 warps each) alternate (tile, chunk) items over three TMEM expand stages, so the expand MMA of an
+//     item is issued one and a half items ahead of its consumer.
+#pragma once
+#include <cuda.h>
+#include "common.cuh"
+#include "gemm_tcgen05.cuh"
+#include "gemm_tcgen05_v2.cuh"
+#include "dwconv_tma.cuh"
+#include "fused_block.cuh"
+
+namespace spef {
+namespace fbt {
+
+constexpr int CL = 128;                      // channel slots (TMEM lanes) per chunk
+constexpr int MAX_NGT = 3;                   // worker groups (template parameter NG = 2 | 3)
+constexpr int GWT = 4;                       // warps per group: one per TMEM lane quarter
+constexpr int AUX_ROWS = 11;                 // per chunk: expand bias | dw bias | dw weights[9], each [128] f32
+constexpr int AUX_BYTES = AUX_ROWS * CL * 4; // 5632
+constexpr int AUX_STRIDE = 6144;
+constexpr int A2_BYTES = 32768;              // A2^T [128 ch][128 px] bf16, MN-major SWIZZLE_128B
+constexpr int A2_SBO = 1024;                 // 8 channels x 128 B
+constexpr int A2_LBO = 16384;                // next 64-pixel block
+constexpr int CTRL_WARPS = 8;                // 4 epilogue warps + TMEM alloc, TMA producer, project issuer, expand issuer
+constexpr int MAX_W_STAGES = 8;
+constexpr int MAX_ACC = 4;
+
+struct FbtParams {
+  const bf16* x;       // block input  [B,H,W,Cin]  (residual source)
+  bf16* y;             // block output [B,Ho,Wo,Cout]
+  const float* aux;    // [n_chunks][AUX_ROWS][128]
+  const float* bp;     // project bias [cpad]
+  int B, H, W, Cin, Cout, Ho, Wo;
+  int TH, TW, THI, TWI, tiles_y, tiles_x;
+  int n_px;            // expand MMA N: THI*TWI rounded up to 16 (<= 128)
+  int kc_in, n_chunks, cpad;
+  int x_stages, w_stages, resident, proj_stages;
+  int n_acc, acc_stride, proj_col0, proj_stride;
+  int residual;
+  long long* trace;
+};
+
+__host__ __device__ inline int w_stage_bytes(int kc_in, int cpad) { return kc_in * (CL * 128) + 2 * cpad * 128 + AUX_STRIDE; }
+__host__ __device__ inline int x_stage_bytes(int kc_in, int n_px) { return kc_in * n_px * 128; }
+inline size_t smem_bytes(const FbtParams& p, int ng) {
+  return 1024 + (size_t)p.x_stages * x_stage_bytes(p.kc_in, p.n_px) + (size_t)p.w_stages * w_stage_bytes(p.kc_in, p.cpad) +
+         (size_t)ng * A2_BYTES + 2048 /*bias*/ + 512 /*barriers*/;
+}
+// Register budget per role when three worker groups share the SM.  setmaxnreg only moves registers inside the CTA's own
+// allocation (20 warps x 96 at launch), so 12 * WORKER + 4 * EPI + 4 * CTRL <= 20 * 96 = 1920 per lane: 1440 + 288 + 160 = 1888.
+constexpr int REGS_WORKER = 120, REGS_EPI = 72, REGS_CTRL = 40;
+template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ float lds_f32(uint32_t saddr) {
+  float r;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(saddr));
+  return r;
+}
+__device__ __forceinline__ void sts_u2(uint32_t saddr, uint32_t a, uint32_t b) {
+  asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(saddr), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ void sts_u1(uint32_t saddr, uint32_t a) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(saddr), "r"(a) : "memory");
+}
+// UMMA shared-memory descriptor, MN-major operand, SWIZZLE_128B: 64 MN-elements (128 B) contiguous, 8 K-rows per 1024-byte
+// atom; LBO = byte distance between 64-element MN blocks, SBO = byte distance between 8-row K groups
+// (cute/atom/mma_traits_sm100.hpp: ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units).
+__device__ __forceinline__ uint64_t make_smem_desc_mn_sw128(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// kind::f16 instruction descriptor, A MN-major (bit 15), B K-major
+__host__ __device__ inline uint32_t make_idesc_bf16_amn(int m, int n) { return tc::make_idesc_bf16(m, n) | (1u << 15); }
+
+// round(relu(a + bias)) to BF16 for a pair of FP32 accumulators; returns the packed bf16x2 (low half = first element)
+__device__ __forceinline__ uint32_t bias_relu_bf16x2(uint32_t a0, uint32_t a1, uint64_t bias2) {
+  return tc::relu_bf16x2(tc::cvt_bf16x2(tc::add_f32x2(tc::pack_f32x2(a0, a1), bias2)));
+}
+
+// S: depthwise stride; TH: output rows of a tile (compile time: the row loop is fully unrolled, so the register window
+// rotates by renaming and every shared-memory store address is a constant)
+template <int S, int TH, int NG>
+__global__ void __launch_bounds__(32 * (CTRL_WARPS + NG * GWT), 1)
+fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWe,
+                     const __grid_constant__ CUtensorMap tmWp, const FbtParams p) {
+  constexpr int GW = GWT;
+  constexpr int GT = 32 * GW;
+  constexpr int TW = (S == 1) ? 12 : 6;           // output columns of a tile
+  constexpr int TWI = (TW - 1) * S + 3;           // 14 | 13 input columns: one tcgen05.ld.x16 per pixel row
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int xsb = x_stage_bytes(p.kc_in, p.n_px);
+  const int wsb = w_stage_bytes(p.kc_in, p.cpad);
+  uint8_t* x_s = smem;
+  uint8_t* w_s = x_s + (size_t)p.x_stages * xsb;
+  uint8_t* a2_s = w_s + (size_t)p.w_stages * wsb;             // [NG][A2_BYTES]
+  float* bp_s = reinterpret_cast<float*>(a2_s + (size_t)NG * A2_BYTES);   // [<= 512]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bp_s + 512);
+  uint64_t* x_full = bars;                        // [4]
+  uint64_t* x_empty = x_full + 4;                 // [4]
+  uint64_t* w_full = x_empty + 4;                 // [MAX_W_STAGES]
+  uint64_t* w_empty = w_full + MAX_W_STAGES;      // [MAX_W_STAGES]
+  uint64_t* acc_full = w_empty + MAX_W_STAGES;    // [MAX_ACC]  expand MMA -> workers
+  uint64_t* acc_empty = acc_full + MAX_ACC;       // [MAX_ACC]  workers -> expand MMA
+  uint64_t* a2_full = acc_empty + MAX_ACC;        // [NG]  workers -> project MMA
+  uint64_t* a2_empty = a2_full + MAX_NGT;         // [NG]  project MMA -> workers
+  uint64_t* proj_full = a2_empty + MAX_NGT;       // [2]
+  uint64_t* proj_empty = proj_full + 2;           // [2]
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(proj_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  constexpr int FIRST_EPI_WARP = NG * GW;
+  constexpr int WARP_ALLOC = NG * GW + 4, WARP_TMA = NG * GW + 5, WARP_MMA_P = NG * GW + 6, WARP_MMA = NG * GW + 7;
+  constexpr int THI = (TH - 1) * S + 3;
+  const int P_in = THI * TWI;
+  const int tiles_per_img = p.tiles_y * p.tiles_x;
+  const long long num_tiles = (long long)p.B * tiles_per_img;
+  const int my_tiles = (int)((num_tiles - (long long)blockIdx.x + (long long)gridDim.x - 1) / (long long)gridDim.x);
+  const int total = my_tiles * p.n_chunks;
+  const bool tr = (p.trace != nullptr) && blockIdx.x == 0;
+#define FBT_TRACE(n_, slot_) do { if (tr && (n_) < 64) p.trace[(n_) * 16 + (slot_)] = clock64(); } while (0)
+
+  // the WorkIt iterator of fused_block.cuh only needs these fields
+  fb::FbParams itp;
+  itp.n_chunks = p.n_chunks; itp.x_stages = p.x_stages; itp.w_stages = p.w_stages; itp.resident = p.resident;
+  itp.proj_stages = p.proj_stages; itp.n_acc = p.n_acc;
+
+  for (int i = threadIdx.x; i < 512; i += (int)blockDim.x) bp_s[i] = (i < p.cpad) ? p.bp[i] : 0.f;
+  if (warp == WARP_TMA && lane == 0) {
+    tc::tma_prefetch_desc(&tmX);
+    tc::tma_prefetch_desc(&tmWe);
+    tc::tma_prefetch_desc(&tmWp);
+  }
+  if (warp == WARP_MMA && lane == 0) {
+    for (int i = 0; i < 4; ++i) {
+      tc::mbar_init(tc::smem_u32(&x_full[i]), 1);
+      tc::mbar_init(tc::smem_u32(&x_empty[i]), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      tc::mbar_init(tc::smem_u32(&proj_full[i]), 1);
+      tc::mbar_init(tc::smem_u32(&proj_empty[i]), 4);
+    }
+    for (int i = 0; i < MAX_W_STAGES; ++i) {
+      tc::mbar_init(tc::smem_u32(&w_full[i]), 1);
+      tc::mbar_init(tc::smem_u32(&w_empty[i]), 1);
+    }
+    for (int i = 0; i < MAX_ACC; ++i) {
+      tc::mbar_init(tc::smem_u32(&acc_full[i]), 1);
+      tc::mbar_init(tc::smem_u32(&acc_empty[i]), GW);
+    }
+    for (int i = 0; i < NG; ++i) {
+      tc::mbar_init(tc::smem_u32(&a2_full[i]), 1);
+      tc::mbar_init(tc::smem_u32(&a2_empty[i]), 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == WARP_ALLOC) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(tmem_ptr_s)), "r"(tc::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  tc::tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_s;
+
+  const float rcp_tpi = 1.0f / (float)tiles_per_img, rcp_tx = 1.0f / (float)p.tiles_x;
+  auto tile_coords = [&](int i, int& b, int& oy0, int& ox0) {
+    const int t = (int)blockIdx.x + i * (int)gridDim.x;
+    b = fb::fast_div(t, tiles_per_img, rcp_tpi);
+    const int r = t - b * tiles_per_img;
+    const int ty = fb::fast_div(r, p.tiles_x, rcp_tx);
+    oy0 = ty * TH;
+    ox0 = (r - ty * p.tiles_x) * TW;
+  };
+
+  // NG == 3 (20 warps): the compiler's cap is 96 registers per thread; every role re-sizes its register file first
+  // (setmaxnreg at the top of each role's branch, so that the role's code is dominated by it)
+  if (warp == WARP_TMA) {
+    // ===================== TMA producer =====================
+    if (NG == 3) reg_dec<REGS_CTRL>();
+    if (lane == 0) {
+      const uint32_t x_tx = (uint32_t)(p.kc_in * P_in * 128);
+      const uint32_t w_tx = (uint32_t)(p.kc_in * CL * 128 + 2 * p.cpad * 128 + AUX_BYTES);
+      for (fb::WorkIt w = fb::work_begin(); w.n < total; fb::work_next<NG>(w, itp)) {
+        if (w.c == 0) {
+          int b, oy0, ox0;
+          tile_coords(w.i, b, oy0, ox0);
+          tc::mbar_wait_relaxed(tc::smem_u32(&x_empty[w.xs]), (uint32_t)(w.xph ^ 1), 256);
+          const uint32_t fbar = tc::smem_u32(&x_full[w.xs]);
+          tc::mbar_arrive_expect_tx(fbar, x_tx);
+          for (int kc = 0; kc < p.kc_in; ++kc)
+            dw::tma_load_4d(tc::smem_u32(x_s + (size_t)w.xs * xsb + (size_t)kc * p.n_px * 128), &tmX, kc * 64, ox0 * S - 1, oy0 * S - 1, b, fbar);
+        }
+        if (!p.resident || w.i == 0) {
+          if (!p.resident) tc::mbar_wait_relaxed(tc::smem_u32(&w_empty[w.ws]), (uint32_t)(w.wph ^ 1), 256);
+          const uint32_t fbar = tc::smem_u32(&w_full[w.ws]);
+          uint8_t* dst = w_s + (size_t)w.ws * wsb;
+          tc::mbar_arrive_expect_tx(fbar, w_tx);
+          for (int kc = 0; kc < p.kc_in; ++kc) tc::tma_load_2d(tc::smem_u32(dst + (size_t)kc * CL * 128), &tmWe, kc * 64, w.c * CL, fbar);
+          uint8_t* wp = dst + (size_t)p.kc_in * CL * 128;
+          tc::tma_load_2d(tc::smem_u32(wp), &tmWp, w.c * CL, 0, fbar);
+          tc::tma_load_2d(tc::smem_u32(wp + (size_t)p.cpad * 128), &tmWp, w.c * CL + 64, 0, fbar);
+          fb::bulk_load_1d(tc::smem_u32(wp + (size_t)2 * p.cpad * 128), p.aux + (size_t)w.c * AUX_ROWS * CL, AUX_BYTES, fbar);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == WARP_MMA) {
+    // ===================== expand MMA issuer: D_e^T[128 ch, n_px] = We_chunk[128, Cin] * X[n_px, Cin]^T =====================
+    if (NG == 3) reg_dec<REGS_CTRL>();
+    const uint32_t idesc_e = tc::make_idesc_bf16(128, p.n_px);
+    const uint32_t kst_last = (uint32_t)(((p.Cin - (p.kc_in - 1) * 64) + 15) / 16);
+    const uint64_t a_base = tc::make_smem_desc_sw128(tc::smem_u32(w_s));
+    const uint64_t b_base = tc::make_smem_desc_sw128(tc::smem_u32(x_s));
+    const uint32_t x_step = (uint32_t)xsb >> 4, w_step = (uint32_t)wsb >> 4;
+    const uint32_t xk_step = (uint32_t)(p.n_px * 128) >> 4;
+    for (fb::WorkIt w = fb::work_begin(); w.n < total; fb::work_next<NG>(w, itp)) {
+      const int n = w.n;
+      if (lane == 0) FBT_TRACE(n, 0);
+      if (w.c == 0) tc::mbar_wait_relaxed(tc::smem_u32(&x_full[w.xs]), (uint32_t)w.xph, 64);
+      tc::mbar_wait_relaxed(tc::smem_u32(&w_full[w.ws]), (uint32_t)w.wph, 64);
+      tc::mbar_wait_relaxed(tc::smem_u32(&acc_empty[w.as]), (uint32_t)(w.aph ^ 1), 64);
+      tc::tcgen05_fence_after();
+      if (lane == 0) FBT_TRACE(n, 1);
+      const uint64_t a0 = a_base + (uint64_t)((uint32_t)w.ws * w_step);
+      const uint64_t b0 = b_base + (uint64_t)((uint32_t)w.xs * x_step);
+      const uint32_t d0 = tmem_base + (uint32_t)(w.as * p.acc_stride);
+      for (int kc = 0; kc < p.kc_in; ++kc) {
+        const uint32_t ksteps = (kc == p.kc_in - 1) ? kst_last : 4u;
+        for (uint32_t ks = 0; ks < ksteps; ++ks)
+          fb::mma_elect(d0, a0 + (uint64_t)((uint32_t)kc * (uint32_t)(CL * 128 >> 4) + ks * 2u),
+                        b0 + (uint64_t)((uint32_t)kc * xk_step + ks * 2u), idesc_e, (kc > 0 || ks > 0) ? 1u : 0u);
+      }
+      fb::commit_elect(tc::smem_u32(&acc_full[w.as]));
+      if (w.c == p.n_chunks - 1) fb::commit_elect(tc::smem_u32(&x_empty[w.xs]));
+      if (lane == 0) FBT_TRACE(n, 2);
+    }
+  } else if (warp == WARP_MMA_P) {
+    // ===================== project MMA issuer: D_p[128 px, cpad] += A2^T[128 ch, 128 px]^T * Wp_chunk[cpad, 128 ch]^T =====================
+    if (NG == 3) reg_dec<REGS_CTRL>();
+    const uint32_t idesc_p = make_idesc_bf16_amn(128, p.cpad);
+    const uint64_t a_base = make_smem_desc_mn_sw128(tc::smem_u32(a2_s), A2_LBO, A2_SBO);
+    const uint64_t b_base = tc::make_smem_desc_sw128(tc::smem_u32(w_s + (size_t)p.kc_in * CL * 128));
+    const uint32_t w_step = (uint32_t)wsb >> 4;
+    const uint32_t wp_half = (uint32_t)(p.cpad * 128) >> 4;
+    for (fb::WorkIt w = fb::work_begin(); w.n < total; fb::work_next<NG>(w, itp)) {
+      const int n = w.n;
+      if (w.c == 0) tc::mbar_wait_relaxed(tc::smem_u32(&proj_empty[w.ps]), (uint32_t)(w.pph ^ 1), 64);
+      tc::mbar_wait_relaxed(tc::smem_u32(&a2_full[w.g]), (uint32_t)w.kph, 64);
+      tc::tcgen05_fence_after();
+      if (lane == 0) FBT_TRACE(n, 4);
+      const uint64_t a0 = a_base + (uint64_t)((uint32_t)w.g * (uint32_t)(A2_BYTES >> 4));
+      const uint64_t b0 = b_base + (uint64_t)((uint32_t)w.ws * w_step);
+      const uint32_t d = tmem_base + (uint32_t)(p.proj_col0 + w.ps * p.proj_stride);
+#pragma unroll
+      for (uint32_t ks = 0; ks < 8; ++ks)   // K = 128 channel slots: 16 per step = two 8-channel groups (2 * SBO)
+        fb::mma_elect(d, a0 + (uint64_t)(ks * (uint32_t)(2 * A2_SBO >> 4)), b0 + (uint64_t)((ks >> 2) * wp_half + (ks & 3u) * 2u), idesc_p,
+                      (w.c > 0 || ks > 0) ? 1u : 0u);
+      fb::commit_elect(tc::smem_u32(&a2_empty[w.g]));
+      if (!p.resident) fb::commit_elect(tc::smem_u32(&w_empty[w.ws]));
+      if (w.c == p.n_chunks - 1) fb::commit_elect(tc::smem_u32(&proj_full[w.ps]));
+      if (lane == 0) FBT_TRACE(n, 5);
+    }
+  } else if (warp >= FIRST_EPI_WARP && warp < FIRST_EPI_WARP + 4) {
+    // ===================== epilogue: project accumulator -> +bias (+x) -> bf16 -> global =====================
+    if (NG == 3) reg_dec<REGS_EPI>();
+    const int q = warp & 3;
+    const int o = q * 32 + lane;                  // accumulator row = output pixel of the tile
+    const int oy_l = o / TW, ox_l = o - oy_l * TW;
+    int ps = 0;
+    uint32_t pph = 0;
+    for (int i = 0; i < my_tiles; ++i) {
+      int b, oy0, ox0;
+      tile_coords(i, b, oy0, ox0);
+      const int gy = oy0 + oy_l, gx = ox0 + ox_l;
+      const bool valid = (o < TH * TW) && gy < p.Ho && gx < p.Wo;
+      const size_t pix = ((size_t)b * p.Ho + gy) * p.Wo + gx;
+      bf16* yp = p.y + pix * p.Cout;
+      const bf16* rp = p.x + pix * p.Cout;        // residual blocks: S == 1, Cin == Cout, same pixel
+      tc::mbar_wait_relaxed(tc::smem_u32(&proj_full[ps]), pph, 512);
+      tc::tcgen05_fence_after();
+      if (warp == FIRST_EPI_WARP && lane == 0) FBT_TRACE(i * p.n_chunks, 13);
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(p.proj_col0 + ps * p.proj_stride);
+      for (int c0 = 0; c0 < p.Cout; c0 += 32) {
+        uint32_t v[32];
+        tc::tmem_ld_32x32b_x32(t_row + (uint32_t)c0, v);
+        tc::tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (c0 + j * 8 < p.Cout) {
+              float f[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j * 8 + e]) + bp_s[c0 + j * 8 + e];
+              if (p.residual) {
+                float r[8];
+                Vec8<bf16>::load(rp + c0 + j * 8, r);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[e] += r[e];
+              }
+              Vec8<bf16>::store(yp + c0 + j * 8, f);
+            }
+          }
+        }
+      }
+      tc::tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(tc::smem_u32(&proj_empty[ps]));
+      if (warp == FIRST_EPI_WARP && lane == 0) FBT_TRACE(i * p.n_chunks, 14);
+      if (++ps == p.proj_stages) { ps = 0; pph ^= 1u; }
+    }
+  } else if (warp < NG * GW) {
+    // ===================== workers: one hidden channel per thread, TMEM -> depthwise -> A2^T =====================
+    if (NG == 3) reg_inc<REGS_WORKER>();
+    const int g = warp / GW;
+    const int q = warp & 3;                         // TMEM lane quarter
+    const int slot = q * 32 + lane;                 // channel slot of this thread = TMEM lane = K index of the project GEMM
+    const int tg = (int)threadIdx.x - 32 * g * GW;
+    const uint32_t sw4 = (uint32_t)(slot & 7) << 4; // 128-byte swizzle: 16-byte chunk index ^= (channel row & 7)
+    const uint32_t a2_u = tc::smem_u32(a2_s + (size_t)g * A2_BYTES) + (uint32_t)((slot >> 3) * A2_SBO + (slot & 7) * 128);
+    fb::WorkIt w = fb::work_begin();
+    for (int s = 0; s < g && w.n < total; ++s) fb::work_next<NG>(w, itp);
+    int cur_i = -1, cur_c = -1, b = 0, oy0 = 0, ox0 = 0;
+    float be = 0.f, bd = 0.f, wd[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    // A row of the hidden tile in registers.  S == 1: h[j] = column j.  S == 2: columns de-interleaved (e[i] = column 2i,
+    // o[i] = column 2i+1) so that horizontally adjacent OUTPUTS read adjacent registers (packed FFMA2 operands).
+    struct Row { float a[8]; float c[8]; };         // S == 1: a[i] = col 2i, c[i] = col 2i+1 as well (pairs (a[i], c[i]) are the bf16x2 words)
+    while (w.n < total) {
+      const int n = w.n;
+      if (w.i != cur_i) { cur_i = w.i; tile_coords(cur_i, b, oy0, ox0); }
+      if (tg == 0) FBT_TRACE(n, 6);
+      tc::mbar_wait(tc::smem_u32(&w_full[w.ws]), (uint32_t)w.wph);
+      if (w.c != cur_c || !p.resident) {            // per-channel constants of this chunk
+        cur_c = w.c;
+        const uint32_t aux_u = tc::smem_u32(w_s + (size_t)w.ws * wsb + (size_t)p.kc_in * CL * 128 + (size_t)2 * p.cpad * 128) + (uint32_t)slot * 4u;
+        be = lds_f32(aux_u);
+        bd = lds_f32(aux_u + CL * 4);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) wd[k] = lds_f32(aux_u + (uint32_t)((2 + k) * CL * 4));
+      }
+      const uint64_t be2 = f32x2(be, be);
+      const bool left_ok = (ox0 * S - 1) >= 0;
+      const bool right_ok = (ox0 * S - 1 + TWI - 1) < p.W;
+      const int gy0 = oy0 * S - 1;
+      const uint32_t kph = (uint32_t)w.kph;
+      const int as = w.as, gsel = w.g;
+      tc::mbar_wait(tc::smem_u32(&acc_full[as]), (uint32_t)w.aph);
+      tc::tcgen05_fence_after();
+      if (tg == 0) FBT_TRACE(n, 7);
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.acc_stride);
+      // bookkeeping of the next item now, so that it overlaps the arithmetic below
+      for (int s = 0; s < NG && w.n < total; ++s) fb::work_next<NG>(w, itp);
+
+      // hidden pixel row r of the box -> relu(acc + be) rounded to BF16 (as f32), zero outside the image
+      auto load_row = [&](int r, Row& h) {
+        const int gy = gy0 + r;
+        if (gy >= 0 && gy < p.H) {                 // uniform
+          uint32_t v[16];
+          tmem_ld_32x32b_x16(t_row + (uint32_t)(r * TWI), v);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (2 * i < TWI) {
+              const uint32_t pk = bias_relu_bf16x2(v[2 * i], v[2 * i + 1], be2);
+              h.a[i] = __uint_as_float(pk << 16);
+              h.c[i] = __uint_as_float(pk & 0xffff0000u);
+            }
+          }
+          if (!left_ok) h.a[0] = 0.f;
+          if (!right_ok) { if ((TWI - 1) & 1) h.c[(TWI - 1) / 2] = 0.f; else h.a[(TWI - 1) / 2] = 0.f; }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { h.a[i] = 0.f; h.c[i] = 0.f; }
+        }
+      };
+      // column j of a row
+      auto col = [](const Row& h, int j) -> float { return (j & 1) ? h.c[j >> 1] : h.a[j >> 1]; };
+      // one tap row (ky) into the accumulator pairs; per output the order is kx = 0, 1, 2 as in the per-layer kernel
+      auto tap_row = [&](const Row& h, int ky, uint64_t (&acc)[TW / 2]) {
+        const uint64_t w0 = f32x2(wd[ky * 3 + 0], wd[ky * 3 + 0]);
+        const uint64_t w2 = f32x2(wd[ky * 3 + 2], wd[ky * 3 + 2]);
+        const uint64_t w1 = f32x2(wd[ky * 3 + 1], wd[ky * 3 + 1]);
+        const float w1s = wd[ky * 3 + 1], w2s = wd[ky * 3 + 2];
+#pragma unroll
+        for (int i = 0; i < TW / 2; ++i) {          // outputs x = 2i, 2i+1
+          if (S == 1) {
+            // inputs x+kx: kx=0 -> (2i, 2i+1) = (a[i], c[i]) adjacent; kx=1 -> (2i+1, 2i+2) = (c[i], a[i+1]) scalar; kx=2 -> (a[i+1], c[i+1])
+            acc[i] = fma_f32x2(f32x2(h.a[i], h.c[i]), w0, acc[i]);
+            float lo, hi;
+            f32x2_unpack(acc[i], lo, hi);
+            lo = fmaf(h.c[i], w1s, lo);
+            hi = fmaf(h.a[i + 1], w1s, hi);
+            acc[i] = fma_f32x2(f32x2(h.a[i + 1], h.c[i + 1]), w2, f32x2(lo, hi));
+          } else {
+            // inputs 2x+kx: kx=0 -> cols (4i, 4i+2) = (a[2i], a[2i+1]); kx=1 -> (c[2i], c[2i+1]); kx=2 -> (a[2i+1], a[2i+2]) scalar
+            acc[i] = fma_f32x2(f32x2(h.a[2 * i], h.a[2 * i + 1]), w0, acc[i]);
+            acc[i] = fma_f32x2(f32x2(h.c[2 * i], h.c[2 * i + 1]), w1, acc[i]);
+            float lo, hi;
+            f32x2_unpack(acc[i], lo, hi);
+            lo = fmaf(h.a[2 * i + 1], w2s, lo);
+            hi = fmaf(h.a[2 * i + 2], w2s, hi);
+            acc[i] = f32x2(lo, hi);
+          }
+        }
+      };
+      // output row y (compile-time) of the tile from three hidden rows, stored as adjacent pixels of channel `slot`
+      auto emit_row = [&](int y, const Row& r0, const Row& r1, const Row& r2) {
+        uint64_t acc[TW / 2];
+#pragma unroll
+        for (int i = 0; i < TW / 2; ++i) acc[i] = f32x2(bd, bd);
+        tap_row(r0, 0, acc);
+        tap_row(r1, 1, acc);
+        tap_row(r2, 2, acc);
+        uint32_t pk[TW / 2];
+#pragma unroll
+        for (int i = 0; i < TW / 2; ++i) pk[i] = tc::relu_bf16x2(tc::cvt_bf16x2(acc[i]));
+        constexpr int QUAD = (S == 1) ? 2 : 1;      // bf16x2 words per store: 4 pixels = 8 bytes never straddle a 16-byte chunk (y*TW % 4 == 0)
+#pragma unroll
+        for (int i = 0; i < TW / 2; i += QUAD) {
+          const uint32_t op = (uint32_t)(y * TW + 2 * i);
+          const uint32_t u = (op >> 6) * (uint32_t)A2_LBO + (((op & 63u) >> 3) << 4) + (op & 7u) * 2u;   // folds to a constant when y is
+          const uint32_t addr = a2_u + (u ^ sw4);
+          if (S == 1) sts_u2(addr, pk[i], pk[i + 1]); else sts_u1(addr, pk[i]);
+        }
+      };
+      (void)col;
+
+      Row ra, rb, rc;
+      if (S == 1) {
+        // rows rotate through (ra, rb, rc): output y uses input rows y, y+1, y+2
+        load_row(0, ra);
+        load_row(1, rb);
+        load_row(2, rc);
+        tc::mbar_wait(tc::smem_u32(&a2_empty[gsel]), kph ^ 1u);   // project MMA of this group's previous item has read A2
+#pragma unroll
+        for (int y = 0; y < TH; y += 3) {
+          if (y > 0) load_row(y + 2, rc);
+          emit_row(y, ra, rb, rc);
+          if (y + 1 < TH) { load_row(y + 3, ra); emit_row(y + 1, rb, rc, ra); }
+          if (y + 2 < TH) { load_row(y + 4, rb); emit_row(y + 2, rc, ra, rb); }
+        }
+      } else {
+        // output y uses input rows 2y, 2y+1, 2y+2; the bottom row of one output is the top row of the next
+        load_row(0, ra);
+        load_row(1, rb);
+        load_row(2, rc);
+        tc::mbar_wait(tc::smem_u32(&a2_empty[gsel]), kph ^ 1u);
+#pragma unroll
+        for (int y = 0; y < TH; y += 2) {
+          if (y > 0) { load_row(2 * y + 1, rb); load_row(2 * y + 2, rc); }
+          emit_row(y, ra, rb, rc);
+          if (y + 1 < TH) {
+            load_row(2 * y + 3, rb);
+            load_row(2 * y + 4, ra);
+            emit_row(y + 1, rc, rb, ra);
+          }
+        }
+      }
+      if (tg == 0) FBT_TRACE(n, 8);
+      // all tcgen05.ld of this warp on the stage are complete (wait::ld after each) -> hand the TMEM stage back
+      tc::tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(tc::smem_u32(&acc_empty[as]));
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // A2 (generic-proxy writes) -> visible to the tensor core
+      fb::group_sync(g, GT);
+      if (tg == 0) tc::mbar_arrive(tc::smem_u32(&a2_full[gsel]));
+      if (tg == 0) FBT_TRACE(n, 12);
+    }
+  }
+  else if (warp == WARP_ALLOC) {
+    if (NG == 3) reg_dec<REGS_CTRL>();
+  }
+#undef FBT_TRACE
+  // ---- teardown ----
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  if (warp == WARP_ALLOC) {
+    tc::tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tc::TMEM_COLS) : "memory");
+  }
+}
+
+}  // namespace fbt
+}  // namespace spef

@@ -76,6 +76,22 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
   }
 }
+// Wait for a role that is not on the critical path (epilogue, TMA producer, MMA issuers with look-ahead): back off with
+// nanosleep between polls.  try_wait only suspends for ~60 cycles, so a tight poll loop executes ~9 instructions every
+// ~70 cycles per waiting warp -- ncu showed these loops taking a third of all issue slots of the fused kernels, competing
+// with the arithmetic warps of the same SM sub-partition.
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity, uint32_t sleep_ns) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  int it = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(sleep_ns);
+    if ((++it & 1023) == 0 && clock64() - t0 > 4000000000LL) {
+      printf("spef: mbarrier timeout block %d thread %d\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
 __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"

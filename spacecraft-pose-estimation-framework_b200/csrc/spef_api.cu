@@ -19,6 +19,7 @@
 #include "gemm_tcgen05_v2.cuh"
 #include "dwconv_tma.cuh"
 #include "fused_block.cuh"
+#include "fused_block_t.cuh"
 #include "kernels_conv.cuh"
 #include "kernels_post.cuh"
 
@@ -56,6 +57,7 @@ struct Layer {
   CUtensorMap tmX;
   // host copies of the folded bias (pw, dw) and the packed [9][C] depthwise weights: inputs of the fused-block plan
   std::vector<float> h_bias, h_wdw;
+  std::vector<bf16> h_wb;   // pointwise weights [N][K] as uploaded (BF16 engine)
 };
 
 // One InvertedResidual block as a single fused kernel (fused_block.cuh): layers [first, first + n_layers)
@@ -71,6 +73,18 @@ struct Block {
   bool tmW_ready = false;
   const void* tmX_ptr = nullptr;
   int tmX_batch = -1;
+  // channel-lane variant (fused_block_t.cuh): permuted / zero-padded weights, one 128-slot chunk per TMEM pass
+  bool t_ok = false;
+  int t_ng = 2;                  // worker groups of the channel-lane kernel
+  fbt::FbtParams tprm;
+  size_t t_smem = 0;
+  bf16* t_we = nullptr;          // [n_chunks*128][Cin]
+  bf16* t_wp = nullptr;          // [Cout][n_chunks*128]
+  float* t_aux = nullptr;        // [n_chunks][11][128]
+  CUtensorMap t_tmX, t_tmWe, t_tmWp;
+  bool t_tmW_ready = false;
+  const void* t_tmX_ptr = nullptr;
+  int t_tmX_batch = -1;
 };
 
 const double kBnEps = 1e-5;  // torch.nn.BatchNorm2d default (pytorch_layers.py:55-56)
@@ -86,6 +100,8 @@ struct spef_ctx {
   int fuse = 1;        // fused InvertedResidual kernels on the BF16 tcgen05 path (SPEF_FUSE=0 disables)
   int fb_gw = 4;       // warps per worker group of the fused kernel (SPEF_FB_GW = 4 | 8; 4 measured faster: more registers per thread)
   int fb_max_cin = 64; // fuse blocks with Cin <= this (SPEF_FB_MAX_CIN); wider blocks measured faster as three kernels
+  int fbt_max_ng = 3;  // worker groups of the channel-lane kernel: 3 where TMEM / shared memory allow, else 2 (SPEF_FBT_NG)
+  int fb_variant = 1;  // 1: channel-lane fused kernel where it applies, else the staged one; 0: staged kernel only (SPEF_FB_VARIANT)
   int fb_trace_block = -1;  // SPEF_FB_TRACE=<block index>: dump CTA-0 clock64 timestamps of that fused block to stderr
   bool finalized = false;
   int num_sms = 148;
@@ -298,6 +314,8 @@ extern "C" int spef_create(spef_ctx** out, const spef_config* cfg) {
   if (const char* e8 = getenv("SPEF_FUSE")) ctx->fuse = atoi(e8) ? 1 : 0;
   if (const char* e9 = getenv("SPEF_FB_GW")) ctx->fb_gw = (atoi(e9) == 8) ? 8 : 4;
   if (const char* e11 = getenv("SPEF_FB_MAX_CIN")) ctx->fb_max_cin = atoi(e11);
+  if (const char* e12 = getenv("SPEF_FB_VARIANT")) ctx->fb_variant = atoi(e12) ? 1 : 0;
+  if (const char* e13 = getenv("SPEF_FBT_NG")) ctx->fbt_max_ng = (atoi(e13) == 2) ? 2 : 3;
   if (const char* e10 = getenv("SPEF_FB_TRACE")) { ctx->fb_trace_block = atoi(e10); if (!ctx->trace_dev) cudaMalloc((void**)&ctx->trace_dev, 256 * 16 * sizeof(long long)); }
   build_layers(ctx);
 
@@ -357,7 +375,7 @@ extern "C" void spef_destroy(spef_ctx* ctx) {
     cudaFree(l.w_bf16);
     cudaFree(l.bias);
   }
-  for (Block& b : ctx->blocks) cudaFree(b.aux);
+  for (Block& b : ctx->blocks) { cudaFree(b.aux); cudaFree(b.t_we); cudaFree(b.t_wp); cudaFree(b.t_aux); }
   for (int i = 0; i < 4; ++i) cudaFree(ctx->act[i]);
   void* ptrs[] = {ctx->pooled, ctx->head_out, ctx->ori_tab, ctx->pos_tab, ctx->eval_sums, ctx->ws_images, ctx->ws_quat,
                   ctx->ws_pos, ctx->ws_qt, ctx->ws_tt, ctx->ws_soft, ctx->ws_soft2, ctx->ws_hinv, ctx->ws_per_image,
@@ -478,6 +496,89 @@ static int plan_blocks(spef_ctx* ctx) {
   return SPEF_OK;
 }
 
+// Channel-lane fused plan (fused_block_t.cuh): tile rows, TMEM / shared-memory stages and the permuted weight arrays.
+static int plan_blocks_t(spef_ctx* ctx) {
+  std::vector<Layer>& L = ctx->layers;
+  const size_t limit = ctx->smem_optin;
+  for (Block& b : ctx->blocks) {
+    b.t_ok = false;
+    b.t_tmW_ready = false;
+    b.t_tmX_ptr = nullptr;
+    if (b.i_exp < 0) continue;
+    const Layer& e = L[b.i_exp];
+    const Layer& d = L[b.i_dw];
+    const Layer& pj = L[b.i_proj];
+    const int S = d.stride, TW = (S == 1) ? 12 : 6, TWI = (TW - 1) * S + 3;
+    const int Ch = e.cout;
+    if (d.wout % TW != 0 || Ch % 4 != 0) continue;   // exact tiling in x: only the two halo columns can leave the image
+    fbt::FbtParams& q = b.tprm;
+    memset(&q, 0, sizeof(q));
+    q.H = e.hin; q.W = e.win; q.Cin = e.cin; q.Cout = pj.cout; q.Ho = d.hout; q.Wo = d.wout;
+    q.TW = TW; q.TWI = TWI;
+    long long best = -1;
+    for (int TH = 3; TH <= 6; ++TH) {              // instantiated kernels: S = 1: TH 4..6, S = 2: TH 3..4
+      const int thi = (TH - 1) * S + 3;
+      if ((S == 1 && TH < 4) || (S == 2 && TH > 4)) continue;
+      if (thi * TWI > 128 || TH * TW > 128) continue;
+      const long long cost = (long long)cdiv(q.Ho, TH) * thi;   // hidden rows computed per image column of tiles
+      if (best < 0 || cost < best) { best = cost; q.TH = TH; }
+    }
+    if (best < 0) continue;
+    q.THI = (q.TH - 1) * S + 3;
+    q.tiles_y = cdiv(q.Ho, q.TH); q.tiles_x = q.Wo / TW;
+    q.n_px = ((q.THI * TWI + 15) / 16) * 16;
+    q.kc_in = cdiv(q.Cin, 64); q.n_chunks = cdiv(Ch, fbt::CL); q.cpad = ((q.Cout + 15) / 16) * 16;
+    if (q.cpad > 128 || q.n_chunks > fbt::MAX_W_STAGES) continue;
+    q.residual = pj.residual;
+    // worker groups, TMEM expand stages (n_px columns each, one more than groups when they fit) and the project
+    // accumulator(s) behind them; shared memory: resident weights before a ring, as many x stages as fit
+    bool found = false;
+    for (int ng = ctx->fbt_max_ng; ng >= 2 && !found; --ng) {
+      const int pcols = ((q.cpad + 31) / 32) * 32;
+      int n_acc = 0, pstages = 0;
+      for (int na = ng + 1; na >= ng && !n_acc; --na)
+        for (int ps = 2; ps >= 1 && !n_acc; --ps)
+          if (na * q.n_px + ps * pcols <= 512) { n_acc = na; pstages = ps; }
+      if (!n_acc) continue;
+      q.n_acc = n_acc; q.acc_stride = q.n_px; q.proj_col0 = n_acc * q.n_px; q.proj_stages = pstages; q.proj_stride = (pstages == 2) ? pcols : 0;
+      struct Opt { int w, res, x; };
+      std::vector<Opt> opts;
+      for (int xs = 4; xs >= 1; --xs) opts.push_back({q.n_chunks, 1, xs});
+      if (q.n_chunks > 3) for (int xs = 2; xs >= 1; --xs) { opts.push_back({4, 0, xs}); opts.push_back({3, 0, xs}); }
+      for (const Opt& o : opts) {
+        q.w_stages = o.w; q.resident = o.res; q.x_stages = o.x;
+        if (fbt::smem_bytes(q, ng) <= limit) { found = true; b.t_ng = ng; b.t_smem = fbt::smem_bytes(q, ng); break; }
+      }
+    }
+    if (!found) continue;
+    // channel -> (chunk, quarter, lane): every chunk spreads its channels evenly over the four TMEM lane quarters
+    const int per_q = Ch / 4, base = per_q / q.n_chunks, rem = per_q % q.n_chunks;
+    std::vector<bf16> we((size_t)q.n_chunks * fbt::CL * q.Cin, __float2bfloat16_rn(0.f));
+    std::vector<bf16> wp((size_t)q.Cout * q.n_chunks * fbt::CL, __float2bfloat16_rn(0.f));
+    std::vector<float> aux((size_t)q.n_chunks * fbt::AUX_ROWS * fbt::CL, 0.f);
+    int ch = 0;
+    for (int c = 0; c < q.n_chunks; ++c) {
+      const int nvq = base + (c < rem ? 1 : 0);
+      if (nvq > 32) return fail(ctx, SPEF_ERR_INVALID, "plan_blocks_t: internal error (nvq = %d)", nvq);
+      for (int qq = 0; qq < 4; ++qq)
+        for (int l = 0; l < nvq; ++l, ++ch) {
+          const int slot = qq * 32 + l;
+          const size_t row = (size_t)c * fbt::CL + slot;
+          for (int k = 0; k < q.Cin; ++k) we[row * q.Cin + k] = e.h_wb[(size_t)ch * q.Cin + k];
+          for (int co = 0; co < q.Cout; ++co) wp[(size_t)co * q.n_chunks * fbt::CL + row] = pj.h_wb[(size_t)co * Ch + ch];
+          float* a = aux.data() + (size_t)c * fbt::AUX_ROWS * fbt::CL;
+          a[slot] = e.h_bias[ch];
+          a[fbt::CL + slot] = d.h_bias[ch];
+          for (int k = 0; k < 9; ++k) a[(2 + k) * fbt::CL + slot] = d.h_wdw[(size_t)k * Ch + ch];
+        }
+    }
+    if (ch != Ch) return fail(ctx, SPEF_ERR_INVALID, "plan_blocks_t: internal error (%d of %d channels placed)", ch, Ch);
+    if (!upload(&b.t_we, we) || !upload(&b.t_wp, wp) || !upload(&b.t_aux, aux)) return fail(ctx, SPEF_ERR_CUDA, "spef_finalize_weights: upload failed");
+    b.t_ok = true;
+  }
+  return SPEF_OK;
+}
+
 extern "C" int spef_finalize_weights(spef_ctx* ctx) {
   if (!ctx) return SPEF_ERR_INVALID;
   CK(cudaSetDevice(ctx->cfg.device));
@@ -546,6 +647,7 @@ extern "C" int spef_finalize_weights(spef_ctx* ctx) {
         }
         if (!upload(&l.w_bf16, wb)) return fail(ctx, SPEF_ERR_CUDA, "spef_finalize_weights: upload failed");
         l.tmW_ready = false;
+        if (l.kind == K_PW) l.h_wb = wb;
       }
       packed.resize((size_t)K * Np);
       for (int n = 0; n < Np; ++n)
@@ -594,6 +696,13 @@ extern "C" int spef_finalize_weights(spef_ctx* ctx) {
     const int so = (int)ctx->smem_optin;
     int rcb = plan_blocks(ctx);
     if (rcb) return rcb;
+    rcb = plan_blocks_t(ctx);
+    if (rcb) return rcb;
+#define SPEF_FBT_ATTR(S_, TH_) \
+    CK(cudaFuncSetAttribute(fbt::fused_block_t_kernel<S_, TH_, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, so)); \
+    CK(cudaFuncSetAttribute(fbt::fused_block_t_kernel<S_, TH_, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, so));
+    SPEF_FBT_ATTR(1, 6) SPEF_FBT_ATTR(1, 5) SPEF_FBT_ATTR(1, 4) SPEF_FBT_ATTR(2, 4) SPEF_FBT_ATTR(2, 3)
+#undef SPEF_FBT_ATTR
     CK(cudaFuncSetAttribute(fb::fused_block_kernel<1, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, so));
     CK(cudaFuncSetAttribute(fb::fused_block_kernel<2, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, so));
     CK(cudaFuncSetAttribute(fb::fused_block_kernel<1, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, so));
@@ -808,11 +917,71 @@ static int launch_tcgen05_layer(spef_ctx* ctx, Layer& l, const void* in, const v
 }
 
 // true when block bi runs as one fused kernel in the current configuration
-static bool block_is_fused(const spef_ctx* ctx, int bi) {
-  return ctx->fuse && ctx->cfg.precision == SPEF_BF16 && ctx->cfg.pw_impl == 0 && bi >= 0 && bi < (int)ctx->blocks.size() && ctx->blocks[bi].fusable;
+// 0: per-layer kernels, 1: staged fused kernel (fused_block.cuh), 2: channel-lane fused kernel (fused_block_t.cuh)
+static int block_variant(const spef_ctx* ctx, int bi) {
+  if (!(ctx->fuse && ctx->cfg.precision == SPEF_BF16 && ctx->cfg.pw_impl == 0 && bi >= 0 && bi < (int)ctx->blocks.size())) return 0;
+  const Block& b = ctx->blocks[bi];
+  if (ctx->fb_variant == 1 && b.t_ok) return 2;
+  return b.fusable ? 1 : 0;
+}
+static bool block_is_fused(const spef_ctx* ctx, int bi) { return block_variant(ctx, bi) != 0; }
+
+static int launch_fused_block_t(spef_ctx* ctx, Block& b, const void* in, void* out, int B, cudaStream_t st) {
+  std::vector<Layer>& L = ctx->layers;
+  fbt::FbtParams& q = b.tprm;
+  if (!b.t_tmW_ready) {
+    if (!tc::make_tmap_2d(ctx->encode, &b.t_tmWe, b.t_we, false, (long long)q.n_chunks * fbt::CL, q.Cin, q.Cin, fbt::CL) ||
+        !tc::make_tmap_2d(ctx->encode, &b.t_tmWp, b.t_wp, false, q.Cout, (long long)q.n_chunks * fbt::CL, (long long)q.n_chunks * fbt::CL, q.cpad))
+      return fail(ctx, SPEF_ERR_CUDA, "cuTensorMapEncodeTiled(W') failed for fused block at layer %d", b.first);
+    b.t_tmW_ready = true;
+  }
+  if (b.t_tmX_ptr != in || b.t_tmX_batch != B) {
+    if (!fb::make_tmap_x(ctx->encode, &b.t_tmX, in, B, q.H, q.W, q.Cin, q.TWI, q.THI))
+      return fail(ctx, SPEF_ERR_CUDA, "cuTensorMapEncodeTiled(X) failed for fused block at layer %d", b.first);
+    b.t_tmX_ptr = in; b.t_tmX_batch = B;
+  }
+  q.x = (const bf16*)in; q.y = (bf16*)out; q.B = B; q.aux = b.t_aux; q.bp = L[b.i_proj].bias;
+  const bool trace = ctx->trace_dev && ctx->fb_trace_block >= 0 && &b == &ctx->blocks[ctx->fb_trace_block < (int)ctx->blocks.size() ? ctx->fb_trace_block : 0];
+  q.trace = trace ? ctx->trace_dev : nullptr;
+  if (trace) cudaMemsetAsync(ctx->trace_dev, 0, 256 * 16 * sizeof(long long), st);
+  const long long tiles = (long long)B * q.tiles_y * q.tiles_x;
+  if (tiles >= (1 << 22)) return fail(ctx, SPEF_ERR_UNSUPPORTED, "fused block: %lld tiles exceed the 2^22 limit of the tile index arithmetic", tiles);
+  const int grid = (int)(tiles < ctx->num_sms ? tiles : ctx->num_sms);
+  const int nthr = 32 * (fbt::CTRL_WARPS + b.t_ng * fbt::GWT);
+#define SPEF_FBT_LAUNCH(S_, TH_) do { if (b.t_ng == 3) fbt::fused_block_t_kernel<S_, TH_, 3><<<grid, nthr, b.t_smem, st>>>(b.t_tmX, b.t_tmWe, b.t_tmWp, q); \
+                                      else fbt::fused_block_t_kernel<S_, TH_, 2><<<grid, nthr, b.t_smem, st>>>(b.t_tmX, b.t_tmWe, b.t_tmWp, q); } while (0)
+  const int S = L[b.i_dw].stride;
+  if (S == 1 && q.TH == 6) SPEF_FBT_LAUNCH(1, 6);
+  else if (S == 1 && q.TH == 5) SPEF_FBT_LAUNCH(1, 5);
+  else if (S == 1 && q.TH == 4) SPEF_FBT_LAUNCH(1, 4);
+  else if (S == 2 && q.TH == 4) SPEF_FBT_LAUNCH(2, 4);
+  else if (S == 2 && q.TH == 3) SPEF_FBT_LAUNCH(2, 3);
+  else return fail(ctx, SPEF_ERR_UNSUPPORTED, "fused block: no kernel instance for stride %d tile height %d", S, q.TH);
+#undef SPEF_FBT_LAUNCH
+  CK_LAUNCH("fused_block_t_kernel");
+  if (trace) {
+    static int dumped = 0;
+    if (dumped++ == 3) {
+      std::vector<long long> h(64 * 16);
+      cudaStreamSynchronize(st);
+      cudaMemcpy(h.data(), ctx->trace_dev, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+      long long t0 = 0;
+      for (int j = 0; j < 16; ++j) if (h[j] && (!t0 || h[j] < t0)) t0 = h[j];
+      fprintf(stderr, "FBT TRACE block at layer %d: tile %dx%d (in %dx%d, n_px %d) chunks %d w_stages %d resident %d x_stages %d grid %d B %d\n"
+              " n: E enter/waited/exit - P waited/exit | worker: top acc_full rows_done - - - synced | epilogue: proj_full done\n",
+              b.first, q.TH, q.TW, q.THI, q.TWI, q.n_px, q.n_chunks, q.w_stages, q.resident, q.x_stages, grid, B);
+      for (int t = 0; t < 48; ++t) {
+        fprintf(stderr, "%3d:", t);
+        for (int j = 0; j < 16; ++j) fprintf(stderr, " %7lld", h[t * 16 + j] ? h[t * 16 + j] - t0 : -1);
+        fprintf(stderr, "\n");
+      }
+    }
+  }
+  return SPEF_OK;
 }
 
 static int launch_fused_block(spef_ctx* ctx, Block& b, const void* in, void* out, int B, cudaStream_t st) {
+  if (block_variant(ctx, (int)(&b - ctx->blocks.data())) == 2) return launch_fused_block_t(ctx, b, in, out, B, st);
   std::vector<Layer>& L = ctx->layers;
   fb::FbParams& q = b.prm;
   if (!b.tmW_ready) {
@@ -995,15 +1164,15 @@ extern "C" int spef_block_info(const spef_ctx* ctx, int32_t i, int32_t* first_la
                                int32_t* tile_h, int32_t* tile_w, int32_t* groups, int32_t* w_stages, int32_t* resident) {
   if (!ctx || i < 0 || i >= (int)ctx->blocks.size()) return SPEF_ERR_INVALID;
   const Block& b = ctx->blocks[i];
-  const bool f = block_is_fused(ctx, i);
+  const int v = block_variant(ctx, i);
   if (first_layer) *first_layer = b.first;
   if (n_layers) *n_layers = b.n_layers;
-  if (fused) *fused = f ? 1 : 0;
-  if (tile_h) *tile_h = f ? b.prm.TH : 0;
-  if (tile_w) *tile_w = f ? b.prm.TW : 0;
-  if (groups) *groups = f ? b.ng : 0;
-  if (w_stages) *w_stages = f ? b.prm.w_stages : 0;
-  if (resident) *resident = f ? b.prm.resident : 0;
+  if (fused) *fused = v;
+  if (tile_h) *tile_h = v == 2 ? b.tprm.TH : (v == 1 ? b.prm.TH : 0);
+  if (tile_w) *tile_w = v == 2 ? b.tprm.TW : (v == 1 ? b.prm.TW : 0);
+  if (groups) *groups = v == 2 ? b.t_ng : (v == 1 ? b.ng : 0);
+  if (w_stages) *w_stages = v == 2 ? b.tprm.w_stages : (v == 1 ? b.prm.w_stages : 0);
+  if (resident) *resident = v == 2 ? b.tprm.resident : (v == 1 ? b.prm.resident : 0);
   return SPEF_OK;
 }
 

@@ -30,7 +30,7 @@ for bi in range(eng.num_blocks()):
         cur = eng.layer_forward(li, cur, inp if eng.layer_info(li)["residual"] else None)
     chain = cur.float().cpu()
     scale = float(want.abs().max())
-    msg = f"block {bi:2d} L{first}-{last} tile {info['tile_h']}x{info['tile_w']} ng{info['groups']} w{info['w_stages']} res{info['resident']} shape {tuple(got.shape)}:"
+    msg = f"block {bi:2d} v{info['fused']} L{first}-{last} tile {info['tile_h']}x{info['tile_w']} ng{info['groups']} w{info['w_stages']} res{info['resident']} shape {tuple(got.shape)}:"
     for name, ref in (("oracle", want), ("chain", chain)):
         err = (got - ref).abs()
         ulp = torch.maximum(ref.abs(), torch.tensor(scale * 2 ** -8)) * 2 ** -7
