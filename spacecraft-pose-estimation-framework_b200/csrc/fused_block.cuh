@@ -228,7 +228,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     // ===================== TMA producer =====================
     if (lane == 0) {
       const uint32_t x_tx = (uint32_t)(p.kc_in * P_in * 128);
-      const uint32_t w_tx = (uint32_t)(p.kc_in * HC * 128 + p.cpad * 128 + AUX_BYTES);
+      const uint32_t w_tx = (uint32_t)((p.has_expand ? p.kc_in * HC * 128 : 0) + p.cpad * 128 + AUX_BYTES);
       for (WorkIt w = work_begin(); w.n < total; work_next<NG>(w, p)) {
         const int i = w.i, c = w.c, xs = w.xs;
         if (c == 0) {
@@ -246,7 +246,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
           const uint32_t fb = tc::smem_u32(&w_full[ws]);
           uint8_t* dst = w_s + (size_t)ws * wsb;
           tc::mbar_arrive_expect_tx(fb, w_tx);
-          for (int kc = 0; kc < p.kc_in; ++kc) tc::tma_load_2d(tc::smem_u32(dst + (size_t)kc * HC * 128), &tmWe, kc * 64, c * HC, fb);
+          for (int kc = 0; kc < p.kc_in && p.has_expand; ++kc) tc::tma_load_2d(tc::smem_u32(dst + (size_t)kc * HC * 128), &tmWe, kc * 64, c * HC, fb);
           tc::tma_load_2d(tc::smem_u32(dst + (size_t)p.kc_in * HC * 128), &tmWp, c * HC, 0, fb);
           bulk_load_1d(tc::smem_u32(dst + (size_t)p.kc_in * HC * 128 + (size_t)p.cpad * 128), p.aux + (size_t)c * AUX_FLOATS, AUX_BYTES, fb);
         }
@@ -260,7 +260,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     const uint64_t a_base = tc::make_smem_desc_sw128(tc::smem_u32(x_s));
     const uint64_t b_base = tc::make_smem_desc_sw128(tc::smem_u32(w_s));
     const uint32_t x_step = (uint32_t)xsb >> 4, w_step = (uint32_t)wsb >> 4;
-    for (WorkIt w = work_begin(); w.n < total; work_next<NG>(w, p)) {
+    for (WorkIt w = work_begin(); w.n < total && p.has_expand; work_next<NG>(w, p)) {
       const int n = w.n;
       if (lane == 0) FB_TRACE(n, 0);
       if (w.c == 0) tc::mbar_wait(tc::smem_u32(&x_full[w.xs]), (uint32_t)w.xph);
@@ -365,7 +365,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     const int tg = (int)threadIdx.x - 32 * g * GW;   // thread index inside the group
     uint8_t* hs = hs_s + (size_t)g * 2 * MT_BYTES;
     uint8_t* a2 = a2_s + (size_t)g * MT_BYTES;
-    const uint32_t hs_u = tc::smem_u32(hs), a2_u = tc::smem_u32(a2);
+    const uint32_t hs_u0 = tc::smem_u32(hs), a2_u = tc::smem_u32(a2);
     const int nstrips_x = p.TW / TX;
     const int nstrips = nstrips_x * p.TH;
     const float rcp_nsx = 1.0f / (float)nstrips_x;
@@ -381,11 +381,17 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       const uint32_t aux_u = tc::smem_u32(w_s + (size_t)ws * wsb + (size_t)p.kc_in * HC * 128 + (size_t)p.cpad * 128);
       if (tg == 0) FB_TRACE(n, 6);
       tc::mbar_wait(tc::smem_u32(&w_full[ws]), (uint32_t)w.wph);
+      // t = 1 block (no expand conv): the TMA-loaded x tile *is* the hidden tile (same 128-byte pixel rows, same XOR
+      // swizzle, image border already zero from the TMA out-of-bounds fill); one chunk per tile, x stage == item
+      const uint32_t hs_u = p.has_expand ? hs_u0 : tc::smem_u32(x_s + (size_t)w.xs * xsb);
+      if (!p.has_expand) tc::mbar_wait(tc::smem_u32(&x_full[w.xs]), (uint32_t)w.xph);
       // ---- drain ----
-      tc::mbar_wait(tc::smem_u32(&acc_full[w.as]), (uint32_t)w.aph);
-      tc::tcgen05_fence_after();
+      if (p.has_expand) {
+        tc::mbar_wait(tc::smem_u32(&acc_full[w.as]), (uint32_t)w.aph);
+        tc::tcgen05_fence_after();
+      }
       if (tg == 0) FB_TRACE(n, 7);
-      for (int mt = wg >> 2; mt < n_mt && !(p.debug_skip & 1); mt += GW / 4) {
+      for (int mt = wg >> 2; mt < n_mt && !(p.debug_skip & 1) && p.has_expand; mt += GW / 4) {
         const int pp = mt * 128 + q * 32 + lane;       // box pixel = accumulator row
         const int py = fast_div(pp, p.TWI, rcp_twi), px = pp - py * p.TWI;
         const int gy = oy0 * S - 1 + py, gx = ox0 * S - 1 + px;
@@ -420,8 +426,10 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       if (tg == 0) FB_TRACE(n, 8);
       tc::tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(tc::smem_u32(&acc_empty[w.as]));   // this warp's tcgen05.ld on the stage are complete
-      group_sync(g, GT);                                             // Hs complete
+      if (p.has_expand) {
+        if (lane == 0) tc::mbar_arrive(tc::smem_u32(&acc_empty[w.as]));   // this warp's tcgen05.ld on the stage are complete
+        group_sync(g, GT);                                             // Hs complete
+      }
       if (tg == 0) FB_TRACE(n, 9);
       // ---- depthwise 3x3 ----
       tc::mbar_wait(tc::smem_u32(&a2_empty[g]), kph ^ 1u);   // project MMA of the previous chunk of this group has read A2
@@ -487,6 +495,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // A2 (generic-proxy writes) -> visible to the tensor core
       group_sync(g, GT);                                             // A2 complete; everyone is done reading Hs
       if (tg == 0) tc::mbar_arrive(tc::smem_u32(&a2_full[g]));
+      if (tg == 0 && !p.has_expand) tc::mbar_arrive(tc::smem_u32(&x_empty[w.xs]));   // everyone is done reading the x stage
       if (tg == 0) FB_TRACE(n, 12);
       for (int s = 0; s < NG && w.n < total; ++s) work_next<NG>(w, p);
     }

@@ -202,21 +202,24 @@ pw_gemm_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
       }
     }
     __syncwarp();
-  } else if (PROD == 1 && warp >= 4 && warp < FIRST_DRAIN_WARP) {
+  } else if (PROD >= 1 && warp >= 4 && warp < FIRST_DRAIN_WARP) {
     // ===================== im2col producer warps (stem): thread t builds row t of the A tile =====================
     // A row = the 27 taps (ci, ky, kx) of one output pixel as bf16, k = (ci*3 + ky)*3 + kx, zero padded to 32; written in
     // the 128B-swizzled K-major layout the UMMA descriptor expects (16-byte chunk c of row r at r*128 + ((c ^ (r & 7)) << 4)).
-    const int t = (int)threadIdx.x - 128;
+    // PROD producer groups of 128 threads take the CTA's tiles round-robin (tile k of the CTA -> group k % PROD), so
+    // PROD x 27 x 128 image loads are in flight per SM
+    const int t = ((int)threadIdx.x - 128) & 127;
+    const int pg = ((int)threadIdx.x - 128) >> 7;
     const int H = p.img_h, W = p.img_w, Ho = p.out_h, Wo = p.out_w;
     // uint8 images: a 256-entry table maps a pixel to bf16(float(u8) / 255.0f), exactly what rounding the reference's
     // float tensor gives; the table lives at the end of the bias area (bias_floats() reserves 256 spare floats)
     uint16_t* lut = reinterpret_cast<uint16_t*>(bias_s + bias_floats(p.N) - 128);
     if (p.img_u8) {
-      for (int i = t; i < 256; i += 128) {
+      for (int i = (int)threadIdx.x - 128; i < 256; i += 128 * PROD) {
         const bf16 h = __float2bfloat16_rn(__fdiv_rn((float)i, 255.0f));
         lut[i] = *reinterpret_cast<const uint16_t*>(&h);
       }
-      asm volatile("bar.sync 2, 128;" ::: "memory");  // producer warps only
+      asm volatile("bar.sync 2, %0;" ::"n"(128 * PROD) : "memory");  // producer warps only
     }
     // gather: 27 taps of this thread's output pixel as bf16 bit patterns (zero outside the image / beyond M)
     auto gather = [&](int tile, uint16_t (&tap)[27]) {
@@ -272,13 +275,14 @@ pw_gemm_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
         }
       }
     };
-    int stage = 0;
-    uint32_t phase = 0;
+    int stage = pg % nstages;
+    uint32_t phase = (uint32_t)((pg / nstages) & 1);
     uint16_t cur[27], nxt[27];
-    if ((int)blockIdx.x < num_tiles) gather(blockIdx.x, cur);
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const int tile0 = (int)blockIdx.x + pg * (int)gridDim.x, tstep = PROD * (int)gridDim.x;
+    if (tile0 < num_tiles) gather(tile0, cur);
+    for (int tile = tile0; tile < num_tiles; tile += tstep) {
       // software pipeline: the taps of the next tile are in flight while this one is staged
-      const int next = tile + (int)gridDim.x;
+      const int next = tile + tstep;
       if (next < num_tiles) gather(next, nxt);
       uint32_t pk[16];
 #pragma unroll
@@ -294,7 +298,8 @@ pw_gemm_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
         sts_u4(sa + (((uint32_t)c ^ ((uint32_t)t & 7u)) << 4), make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]));
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
       mbar_arrive(smem_u32(&full_bar[stage]));
-      if (++stage == nstages) { stage = 0; phase ^= 1; }
+      stage += PROD;
+      if (stage >= nstages) { stage -= nstages; phase ^= 1; }
 #pragma unroll
       for (int k = 0; k < 27; ++k) cur[k] = nxt[k];
     }

@@ -100,6 +100,7 @@ struct spef_ctx {
   int fuse = 1;        // fused InvertedResidual kernels on the BF16 tcgen05 path (SPEF_FUSE=0 disables)
   int fb_gw = 4;       // warps per worker group of the fused kernel (SPEF_FB_GW = 4 | 8; 4 measured faster: more registers per thread)
   int fb_max_cin = 64; // fuse blocks with Cin <= this (SPEF_FB_MAX_CIN); wider blocks measured faster as three kernels
+  int stem_prod = 2;   // im2col producer groups (128 threads each) of the tcgen05 stem (SPEF_STEM_PROD = 1 | 2)
   int fbt_max_ng = 3;  // worker groups of the channel-lane kernel: 3 where TMEM / shared memory allow, else 2 (SPEF_FBT_NG)
   int fb_variant = 1;  // 1: channel-lane fused kernel where it applies, else the staged one; 0: staged kernel only (SPEF_FB_VARIANT)
   int fb_trace_block = -1;  // SPEF_FB_TRACE=<block index>: dump CTA-0 clock64 timestamps of that fused block to stderr
@@ -315,6 +316,7 @@ extern "C" int spef_create(spef_ctx** out, const spef_config* cfg) {
   if (const char* e9 = getenv("SPEF_FB_GW")) ctx->fb_gw = (atoi(e9) == 8) ? 8 : 4;
   if (const char* e11 = getenv("SPEF_FB_MAX_CIN")) ctx->fb_max_cin = atoi(e11);
   if (const char* e12 = getenv("SPEF_FB_VARIANT")) ctx->fb_variant = atoi(e12) ? 1 : 0;
+  if (const char* e14 = getenv("SPEF_STEM_PROD")) { int v = atoi(e14); ctx->stem_prod = (v == 1 || v == 4) ? v : 2; }
   if (const char* e13 = getenv("SPEF_FBT_NG")) ctx->fbt_max_ng = (atoi(e13) == 2) ? 2 : 3;
   if (const char* e10 = getenv("SPEF_FB_TRACE")) { ctx->fb_trace_block = atoi(e10); if (!ctx->trace_dev) cudaMalloc((void**)&ctx->trace_dev, 256 * 16 * sizeof(long long)); }
   build_layers(ctx);
@@ -446,13 +448,14 @@ static int plan_blocks(spef_ctx* ctx) {
     b.fusable = false;
     b.tmW_ready = false;
     b.tmX_ptr = nullptr;
-    if (b.i_exp < 0) continue;  // t = 1 block (no expand conv): runs as depthwise + project kernels
-    const Layer& e = L[b.i_exp];
+    const bool has_exp = b.i_exp >= 0;   // t = 1 block (no expand conv): the x tile is the hidden tile
     const Layer& d = L[b.i_dw];
+    const Layer& e = has_exp ? L[b.i_exp] : d;
     const Layer& pj = L[b.i_proj];
     fb::FbParams& q = b.prm;
     memset(&q, 0, sizeof(q));
-    q.H = e.hin; q.W = e.win; q.Cin = e.cin; q.Ch = e.cout; q.Cout = pj.cout; q.Ho = d.hout; q.Wo = d.wout;
+    q.H = e.hin; q.W = e.win; q.Cin = e.cin; q.Ch = has_exp ? e.cout : d.cin; q.Cout = pj.cout; q.Ho = d.hout; q.Wo = d.wout;
+    if (!has_exp && q.Ch > fb::HC) continue;
     const int S = d.stride;
     fb::pick_tile(q.Ho, q.Wo, S, &q.TH, &q.TW);
     q.THI = (q.TH - 1) * S + 3; q.TWI = (q.TW - 1) * S + 3;
@@ -465,14 +468,14 @@ static int plan_blocks(spef_ctx* ctx) {
     q.n_acc = (q.cpad <= 64) ? 3 : 2;
     q.proj_col0 = q.n_acc * 128;
     q.proj_stride = (q.proj_stages == 2) ? ((q.cpad <= 64) ? 64 : 128) : 0;
-    q.residual = pj.residual; q.has_expand = 1;
+    q.residual = pj.residual; q.has_expand = has_exp ? 1 : 0;
     // shared-memory plan, best first: two worker groups before one, resident weights before a ring, two x stages before one.
     // A weight ring needs >= NG + 1 stages: the MMA thread issues expand(n + NG) before project(n) frees the stage of chunk n.
     bool found = false;
     for (int ng = 2; ng >= 1 && !found; --ng) {
       struct Opt { int w, res, x; };
       std::vector<Opt> opts;
-      if (q.n_chunks <= fb::MAX_W_STAGES) { opts.push_back({q.n_chunks, 1, 2}); opts.push_back({q.n_chunks, 1, 1}); }
+      if (q.n_chunks <= fb::MAX_W_STAGES) { opts.push_back({q.n_chunks, 1, 2}); if (has_exp) opts.push_back({q.n_chunks, 1, 1}); }
       if (q.n_chunks > ng + 1) {
         opts.push_back({ng + 2, 0, 2}); opts.push_back({ng + 1, 0, 2}); opts.push_back({ng + 2, 0, 1}); opts.push_back({ng + 1, 0, 1});
       }
@@ -486,7 +489,7 @@ static int plan_blocks(spef_ctx* ctx) {
     for (int ch = 0; ch < q.Ch; ++ch) {
       float* a = aux.data() + (size_t)(ch / fb::HC) * fb::AUX_FLOATS;
       const int j = ch % fb::HC;
-      a[j] = e.h_bias[ch];
+      a[j] = has_exp ? e.h_bias[ch] : 0.f;
       a[fb::HC + j] = d.h_bias[ch];
       for (int k = 0; k < 9; ++k) a[(2 + k) * fb::HC + j] = d.h_wdw[(size_t)k * q.Ch + ch];
     }
@@ -540,6 +543,7 @@ static int plan_blocks_t(spef_ctx* ctx) {
         for (int ps = 2; ps >= 1 && !n_acc; --ps)
           if (na * q.n_px + ps * pcols <= 512) { n_acc = na; pstages = ps; }
       if (!n_acc) continue;
+      if (ng == 3 && n_acc < 4) continue;   // three groups on three stages leave no look-ahead for the expand MMA: measured slower than two groups
       q.n_acc = n_acc; q.acc_stride = q.n_px; q.proj_col0 = n_acc * q.n_px; q.proj_stages = pstages; q.proj_stride = (pstages == 2) ? pcols : 0;
       struct Opt { int w, res, x; };
       std::vector<Opt> opts;
@@ -718,6 +722,8 @@ extern "C" int spef_finalize_weights(spef_ctx* ctx) {
     CK(cudaFuncSetAttribute(tc::pw_gemm_tcgen05_v2_kernel<false, 2, 4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, so));
     CK(cudaFuncSetAttribute(tc::pw_gemm_tcgen05_v2_kernel<true, 2, 4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, so));
     CK(cudaFuncSetAttribute(tc::pw_gemm_tcgen05_v2_kernel<false, 1, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, so));
+    CK(cudaFuncSetAttribute(tc::pw_gemm_tcgen05_v2_kernel<false, 1, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, so));
+    CK(cudaFuncSetAttribute(tc::pw_gemm_tcgen05_v2_kernel<false, 1, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, so));
     CK(cudaFuncSetAttribute(tc::pw_gemm_tcgen05_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, so));
     CK(cudaFuncSetAttribute(tc::pw_gemm_tcgen05_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, so));
     CK(cudaFuncSetAttribute(tc::pw_gemm_tcgen05_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, so));
@@ -849,7 +855,9 @@ static int launch_stem_tcgen05(spef_ctx* ctx, Layer& l, const void* images, void
   p.img = (const float*)images; p.img_h = l.hin; p.img_w = l.win; p.out_h = l.hout; p.out_w = l.wout;
   const int tiles = cdiv(p.M, tc::BLOCK_M);
   const int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
-  tc::pw_gemm_tcgen05_v2_kernel<false, 1, 4, 1><<<grid, 128 + 128 + 128 + 128, l.smem, st>>>(l.tmW, l.tmW, p);
+  if (ctx->stem_prod == 4) tc::pw_gemm_tcgen05_v2_kernel<false, 1, 4, 4><<<grid, 128 + 512 + 128 + 128, l.smem, st>>>(l.tmW, l.tmW, p);
+  else if (ctx->stem_prod == 2) tc::pw_gemm_tcgen05_v2_kernel<false, 1, 4, 2><<<grid, 128 + 256 + 128 + 128, l.smem, st>>>(l.tmW, l.tmW, p);
+  else tc::pw_gemm_tcgen05_v2_kernel<false, 1, 4, 1><<<grid, 128 + 128 + 128 + 128, l.smem, st>>>(l.tmW, l.tmW, p);
   CK_LAUNCH("pw_gemm_tcgen05_v2_kernel<im2col stem>");
   return SPEF_OK;
 }
@@ -985,9 +993,9 @@ static int launch_fused_block(spef_ctx* ctx, Block& b, const void* in, void* out
   std::vector<Layer>& L = ctx->layers;
   fb::FbParams& q = b.prm;
   if (!b.tmW_ready) {
-    const Layer& e = L[b.i_exp];
     const Layer& pj = L[b.i_proj];
-    if (!tc::make_tmap_2d(ctx->encode, &b.tmWe, e.w_bf16, false, q.Ch, q.Cin, q.Cin, fb::HC) ||
+    const Layer& e = b.i_exp >= 0 ? L[b.i_exp] : pj;   // t = 1 block: tmWe is never used by the kernel
+    if (!tc::make_tmap_2d(ctx->encode, &b.tmWe, e.w_bf16, false, b.i_exp >= 0 ? q.Ch : q.Cout, b.i_exp >= 0 ? q.Cin : q.Ch, b.i_exp >= 0 ? q.Cin : q.Ch, fb::HC) ||
         !tc::make_tmap_2d(ctx->encode, &b.tmWp, pj.w_bf16, false, q.Cout, q.Ch, q.Ch, q.cpad))
       return fail(ctx, SPEF_ERR_CUDA, "cuTensorMapEncodeTiled(W) failed for fused block at layer %d", b.first);
     b.tmW_ready = true;
