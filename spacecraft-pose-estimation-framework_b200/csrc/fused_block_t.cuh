@@ -107,9 +107,17 @@ __device__ __forceinline__ uint64_t make_smem_desc_mn_sw128(uint32_t saddr, uint
 // kind::f16 instruction descriptor, A MN-major (bit 15), B K-major
 __host__ __device__ inline uint32_t make_idesc_bf16_amn(int m, int n) { return tc::make_idesc_bf16(m, n) | (1u << 15); }
 
+// two f32 (packed in a b64) -> bf16x2 with ReLU folded into the conversion (cvt.rn.relu: max(x, 0) then round; identical to
+// rounding first because rounding is monotonic and round(0) = 0); low half = first element
+__device__ __forceinline__ uint32_t cvt_relu_bf16x2(uint64_t v) {
+  uint32_t lo, hi, r;
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(__uint_as_float(hi)), "f"(__uint_as_float(lo)));
+  return r;
+}
 // round(relu(a + bias)) to BF16 for a pair of FP32 accumulators; returns the packed bf16x2 (low half = first element)
 __device__ __forceinline__ uint32_t bias_relu_bf16x2(uint32_t a0, uint32_t a1, uint64_t bias2) {
-  return tc::relu_bf16x2(tc::cvt_bf16x2(tc::add_f32x2(tc::pack_f32x2(a0, a1), bias2)));
+  return cvt_relu_bf16x2(tc::add_f32x2(tc::pack_f32x2(a0, a1), bias2));
 }
 
 // S: depthwise stride; TH: output rows of a tile (compile time: the row loop is fully unrolled, so the register window
@@ -449,7 +457,7 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         tap_row(r2, 2, acc);
         uint32_t pk[TW / 2];
 #pragma unroll
-        for (int i = 0; i < TW / 2; ++i) pk[i] = tc::relu_bf16x2(tc::cvt_bf16x2(acc[i]));
+        for (int i = 0; i < TW / 2; ++i) pk[i] = cvt_relu_bf16x2(acc[i]);
         constexpr int QUAD = (S == 1) ? 2 : 1;      // bf16x2 words per store: 4 pixels = 8 bytes never straddle a 16-byte chunk (y*TW % 4 == 0)
 #pragma unroll
         for (int i = 0; i < TW / 2; i += QUAD) {
