@@ -57,13 +57,24 @@ struct FbtParams {
   int x_stages, w_stages, resident, proj_stages;
   int n_acc, acc_stride, proj_col0, proj_stride;
   int residual;
+  // Strip stacking (stack = 4) for a block with <= 32 hidden channels and no expand conv (t = 1): the four TMEM lane quarters
+  // hold the SAME channels of four horizontally adjacent strips of a 4x wider tile.  The "expand" GEMM is the identity routed
+  // per strip: the K chunks of the operand pair are the strips (A chunk q = identity in the rows of quarter q, B chunk q =
+  // x tile of strip q), so the issuer code is unchanged; the project GEMM runs once per strip (K = 32 = two K steps) into
+  // its own accumulator.
+  int stack;           // 1 | 4
+  int cx;              // channels of the x tensor (TMA map); == Cin unless stacked
+  int proj_sub;        // TMEM columns between the per-strip project accumulators (stack = 4)
+  int we_bytes;        // bytes of the expand-weight region of a weight stage: kc_in * 16 KB, or the 224-row window matrix (stack = 4):
+                       // rows 96..127 of We' hold the identity, and strip q's A operand is the 128-row window starting at row
+                       // 96 - 32 q (its quarter q sees the identity, the other quarters zeros) -- 28 KB instead of 4 x 16 KB
   long long* trace;
 };
 
-__host__ __device__ inline int w_stage_bytes(int kc_in, int cpad) { return kc_in * (CL * 128) + 2 * cpad * 128 + AUX_STRIDE; }
+__host__ __device__ inline int w_stage_bytes(int we_bytes, int cpad) { return we_bytes + 2 * cpad * 128 + AUX_STRIDE; }
 __host__ __device__ inline int x_stage_bytes(int kc_in, int n_px) { return kc_in * n_px * 128; }
 inline size_t smem_bytes(const FbtParams& p, int ng) {
-  return 1024 + (size_t)p.x_stages * x_stage_bytes(p.kc_in, p.n_px) + (size_t)p.w_stages * w_stage_bytes(p.kc_in, p.cpad) +
+  return 1024 + (size_t)p.x_stages * x_stage_bytes(p.kc_in, p.n_px) + (size_t)p.w_stages * w_stage_bytes(p.we_bytes, p.cpad) +
          (size_t)ng * A2_BYTES + 2048 /*bias*/ + 512 /*barriers*/;
 }
 // Register budget per role when three worker groups share the SM.  setmaxnreg only moves registers inside the CTA's own
@@ -133,7 +144,7 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int xsb = x_stage_bytes(p.kc_in, p.n_px);
-  const int wsb = w_stage_bytes(p.kc_in, p.cpad);
+  const int wsb = w_stage_bytes(p.we_bytes, p.cpad);
   uint8_t* x_s = smem;
   uint8_t* w_s = x_s + (size_t)p.x_stages * xsb;
   uint8_t* a2_s = w_s + (size_t)p.w_stages * wsb;             // [NG][A2_BYTES]
@@ -214,7 +225,7 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     const int r = t - b * tiles_per_img;
     const int ty = fb::fast_div(r, p.tiles_x, rcp_tx);
     oy0 = ty * TH;
-    ox0 = (r - ty * p.tiles_x) * TW;
+    ox0 = (r - ty * p.tiles_x) * TW * p.stack;
   };
 
   // NG == 3 (20 warps): the compiler's cap is 96 registers per thread; every role re-sizes its register file first
@@ -224,7 +235,7 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     if (NG == 3) reg_dec<REGS_CTRL>();
     if (lane == 0) {
       const uint32_t x_tx = (uint32_t)(p.kc_in * P_in * 128);
-      const uint32_t w_tx = (uint32_t)(p.kc_in * CL * 128 + 2 * p.cpad * 128 + AUX_BYTES);
+      const uint32_t w_tx = (uint32_t)(p.we_bytes + 2 * p.cpad * 128 + AUX_BYTES);
       for (fb::WorkIt w = fb::work_begin(); w.n < total; fb::work_next<NG>(w, itp)) {
         if (w.c == 0) {
           int b, oy0, ox0;
@@ -233,15 +244,17 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
           const uint32_t fbar = tc::smem_u32(&x_full[w.xs]);
           tc::mbar_arrive_expect_tx(fbar, x_tx);
           for (int kc = 0; kc < p.kc_in; ++kc)
-            dw::tma_load_4d(tc::smem_u32(x_s + (size_t)w.xs * xsb + (size_t)kc * p.n_px * 128), &tmX, kc * 64, ox0 * S - 1, oy0 * S - 1, b, fbar);
+            dw::tma_load_4d(tc::smem_u32(x_s + (size_t)w.xs * xsb + (size_t)kc * p.n_px * 128), &tmX, p.stack > 1 ? 0 : kc * 64,
+                            (ox0 + (p.stack > 1 ? kc * TW : 0)) * S - 1, oy0 * S - 1, b, fbar);
         }
         if (!p.resident || w.i == 0) {
           if (!p.resident) tc::mbar_wait_relaxed(tc::smem_u32(&w_empty[w.ws]), (uint32_t)(w.wph ^ 1), 256);
           const uint32_t fbar = tc::smem_u32(&w_full[w.ws]);
           uint8_t* dst = w_s + (size_t)w.ws * wsb;
           tc::mbar_arrive_expect_tx(fbar, w_tx);
-          for (int kc = 0; kc < p.kc_in; ++kc) tc::tma_load_2d(tc::smem_u32(dst + (size_t)kc * CL * 128), &tmWe, kc * 64, w.c * CL, fbar);
-          uint8_t* wp = dst + (size_t)p.kc_in * CL * 128;
+          if (p.stack > 1) tc::tma_load_2d(tc::smem_u32(dst), &tmWe, 0, 0, fbar);   // one box: the 224-row window matrix
+          else for (int kc = 0; kc < p.kc_in; ++kc) tc::tma_load_2d(tc::smem_u32(dst + (size_t)kc * CL * 128), &tmWe, kc * 64, w.c * CL, fbar);
+          uint8_t* wp = dst + (size_t)p.we_bytes;
           tc::tma_load_2d(tc::smem_u32(wp), &tmWp, w.c * CL, 0, fbar);
           tc::tma_load_2d(tc::smem_u32(wp + (size_t)p.cpad * 128), &tmWp, w.c * CL + 64, 0, fbar);
           fb::bulk_load_1d(tc::smem_u32(wp + (size_t)2 * p.cpad * 128), p.aux + (size_t)w.c * AUX_ROWS * CL, AUX_BYTES, fbar);
@@ -270,9 +283,10 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       const uint64_t b0 = b_base + (uint64_t)((uint32_t)w.xs * x_step);
       const uint32_t d0 = tmem_base + (uint32_t)(w.as * p.acc_stride);
       for (int kc = 0; kc < p.kc_in; ++kc) {
-        const uint32_t ksteps = (kc == p.kc_in - 1) ? kst_last : 4u;
+        const uint32_t ksteps = (p.stack > 1) ? 2u : ((kc == p.kc_in - 1) ? kst_last : 4u);   // stacked: K = 32 channels per strip
+        const uint32_t a_off = (p.stack > 1) ? (uint32_t)((96 - 32 * kc) * 128) >> 4 : (uint32_t)kc * (uint32_t)(CL * 128 >> 4);
         for (uint32_t ks = 0; ks < ksteps; ++ks)
-          fb::mma_elect(d0, a0 + (uint64_t)((uint32_t)kc * (uint32_t)(CL * 128 >> 4) + ks * 2u),
+          fb::mma_elect(d0, a0 + (uint64_t)(a_off + ks * 2u),
                         b0 + (uint64_t)((uint32_t)kc * xk_step + ks * 2u), idesc_e, (kc > 0 || ks > 0) ? 1u : 0u);
       }
       fb::commit_elect(tc::smem_u32(&acc_full[w.as]));
@@ -284,7 +298,7 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     if (NG == 3) reg_dec<REGS_CTRL>();
     const uint32_t idesc_p = make_idesc_bf16_amn(128, p.cpad);
     const uint64_t a_base = make_smem_desc_mn_sw128(tc::smem_u32(a2_s), A2_LBO, A2_SBO);
-    const uint64_t b_base = tc::make_smem_desc_sw128(tc::smem_u32(w_s + (size_t)p.kc_in * CL * 128));
+    const uint64_t b_base = tc::make_smem_desc_sw128(tc::smem_u32(w_s + (size_t)p.we_bytes));
     const uint32_t w_step = (uint32_t)wsb >> 4;
     const uint32_t wp_half = (uint32_t)(p.cpad * 128) >> 4;
     for (fb::WorkIt w = fb::work_begin(); w.n < total; fb::work_next<NG>(w, itp)) {
@@ -296,10 +310,17 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       const uint64_t a0 = a_base + (uint64_t)((uint32_t)w.g * (uint32_t)(A2_BYTES >> 4));
       const uint64_t b0 = b_base + (uint64_t)((uint32_t)w.ws * w_step);
       const uint32_t d = tmem_base + (uint32_t)(p.proj_col0 + w.ps * p.proj_stride);
+      if (p.stack == 1) {
 #pragma unroll
-      for (uint32_t ks = 0; ks < 8; ++ks)   // K = 128 channel slots: 16 per step = two 8-channel groups (2 * SBO)
-        fb::mma_elect(d, a0 + (uint64_t)(ks * (uint32_t)(2 * A2_SBO >> 4)), b0 + (uint64_t)((ks >> 2) * wp_half + (ks & 3u) * 2u), idesc_p,
-                      (w.c > 0 || ks > 0) ? 1u : 0u);
+        for (uint32_t ks = 0; ks < 8; ++ks)   // K = 128 channel slots: 16 per step = two 8-channel groups (2 * SBO)
+          fb::mma_elect(d, a0 + (uint64_t)(ks * (uint32_t)(2 * A2_SBO >> 4)), b0 + (uint64_t)((ks >> 2) * wp_half + (ks & 3u) * 2u), idesc_p,
+                        (w.c > 0 || ks > 0) ? 1u : 0u);
+      } else {
+#pragma unroll
+        for (uint32_t ks = 0; ks < 8; ++ks)   // strip ks / 2 = channel slots 32 * (ks / 2) ..: its own accumulator, K = 32
+          fb::mma_elect(d + (ks >> 1) * (uint32_t)p.proj_sub, a0 + (uint64_t)(ks * (uint32_t)(2 * A2_SBO >> 4)),
+                        b0 + (uint64_t)((ks >> 2) * wp_half + (ks & 3u) * 2u), idesc_p, ks & 1u);
+      }
       fb::commit_elect(tc::smem_u32(&a2_empty[w.g]));
       if (!p.resident) fb::commit_elect(tc::smem_u32(&w_empty[w.ws]));
       if (w.c == p.n_chunks - 1) fb::commit_elect(tc::smem_u32(&proj_full[w.ps]));
@@ -316,18 +337,24 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     for (int i = 0; i < my_tiles; ++i) {
       int b, oy0, ox0;
       tile_coords(i, b, oy0, ox0);
-      const int gy = oy0 + oy_l, gx = ox0 + ox_l;
+      tc::mbar_wait_relaxed(tc::smem_u32(&proj_full[ps]), pph, 512);
+      tc::tcgen05_fence_after();
+      if (warp == FIRST_EPI_WARP && lane == 0) FBT_TRACE(i * p.n_chunks, 13);
+      for (int st = 0; st < p.stack; ++st) {
+      const int gy = oy0 + oy_l, gx = ox0 + st * TW + ox_l;
       const bool valid = (o < TH * TW) && gy < p.Ho && gx < p.Wo;
       const size_t pix = ((size_t)b * p.Ho + gy) * p.Wo + gx;
       bf16* yp = p.y + pix * p.Cout;
       const bf16* rp = p.x + pix * p.Cout;        // residual blocks: S == 1, Cin == Cout, same pixel
-      tc::mbar_wait_relaxed(tc::smem_u32(&proj_full[ps]), pph, 512);
-      tc::tcgen05_fence_after();
-      if (warp == FIRST_EPI_WARP && lane == 0) FBT_TRACE(i * p.n_chunks, 13);
-      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(p.proj_col0 + ps * p.proj_stride);
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(p.proj_col0 + ps * p.proj_stride + st * p.proj_sub);
       for (int c0 = 0; c0 < p.Cout; c0 += 32) {
         uint32_t v[32];
-        tc::tmem_ld_32x32b_x32(t_row + (uint32_t)c0, v);
+        if (p.Cout - c0 <= 16) {   // never read past the accumulator's 16-column slot (the last one may end at TMEM column 512)
+          uint32_t(&v16)[16] = *reinterpret_cast<uint32_t(*)[16]>(&v[0]);
+          tmem_ld_32x32b_x16(t_row + (uint32_t)c0, v16);
+        } else {
+          tc::tmem_ld_32x32b_x32(t_row + (uint32_t)c0, v);
+        }
         tc::tmem_ld_wait();
         if (valid) {
 #pragma unroll
@@ -346,6 +373,7 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
             }
           }
         }
+      }
       }
       tc::tcgen05_fence_before();
       __syncwarp();
@@ -376,15 +404,16 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       tc::mbar_wait(tc::smem_u32(&w_full[w.ws]), (uint32_t)w.wph);
       if (w.c != cur_c || !p.resident) {            // per-channel constants of this chunk
         cur_c = w.c;
-        const uint32_t aux_u = tc::smem_u32(w_s + (size_t)w.ws * wsb + (size_t)p.kc_in * CL * 128 + (size_t)2 * p.cpad * 128) + (uint32_t)slot * 4u;
+        const uint32_t aux_u = tc::smem_u32(w_s + (size_t)w.ws * wsb + (size_t)p.we_bytes + (size_t)2 * p.cpad * 128) + (uint32_t)slot * 4u;
         be = lds_f32(aux_u);
         bd = lds_f32(aux_u + CL * 4);
 #pragma unroll
         for (int k = 0; k < 9; ++k) wd[k] = lds_f32(aux_u + (uint32_t)((2 + k) * CL * 4));
       }
       const uint64_t be2 = f32x2(be, be);
-      const bool left_ok = (ox0 * S - 1) >= 0;
-      const bool right_ok = (ox0 * S - 1 + TWI - 1) < p.W;
+      const int ox0q = ox0 + (p.stack > 1 ? q * TW : 0);     // stacked: quarter q owns strip q of the tile
+      const bool left_ok = (ox0q * S - 1) >= 0;
+      const bool right_ok = (ox0q * S - 1 + TWI - 1) < p.W;
       const int gy0 = oy0 * S - 1;
       const uint32_t kph = (uint32_t)w.kph;
       const int as = w.as, gsel = w.g;

@@ -507,16 +507,20 @@ static int plan_blocks_t(spef_ctx* ctx) {
     b.t_ok = false;
     b.t_tmW_ready = false;
     b.t_tmX_ptr = nullptr;
-    if (b.i_exp < 0) continue;
-    const Layer& e = L[b.i_exp];
+    const bool has_exp = b.i_exp >= 0;
     const Layer& d = L[b.i_dw];
+    const Layer& e = has_exp ? L[b.i_exp] : d;
     const Layer& pj = L[b.i_proj];
     const int S = d.stride, TW = (S == 1) ? 12 : 6, TWI = (TW - 1) * S + 3;
-    const int Ch = e.cout;
-    if (d.wout % TW != 0 || Ch % 4 != 0) continue;   // exact tiling in x: only the two halo columns can leave the image
+    const int Ch = has_exp ? e.cout : d.cin;
+    // t = 1 block: identity "expand", four strips stacked in the four TMEM lane quarters (needs Ch == 32, stride 1, no skip)
+    const int stack = has_exp ? 1 : 4;
+    if (!has_exp && !(Ch == 32 && S == 1 && !pj.residual && !getenv("SPEF_FBT_NO_STACK"))) continue;
+    if (d.wout % (TW * stack) != 0 || Ch % 4 != 0 || (stack == 4 && pj.cout > 16)) continue;   // exact tiling in x: only the two halo columns can leave the image
     fbt::FbtParams& q = b.tprm;
     memset(&q, 0, sizeof(q));
-    q.H = e.hin; q.W = e.win; q.Cin = e.cin; q.Cout = pj.cout; q.Ho = d.hout; q.Wo = d.wout;
+    q.H = e.hin; q.W = e.win; q.Cin = has_exp ? e.cin : 4 * 64; q.Cout = pj.cout; q.Ho = d.hout; q.Wo = d.wout;
+    q.cx = e.cin; q.stack = stack;
     q.TW = TW; q.TWI = TWI;
     long long best = -1;
     for (int TH = 3; TH <= 6; ++TH) {              // instantiated kernels: S = 1: TH 4..6, S = 2: TH 3..4
@@ -528,16 +532,19 @@ static int plan_blocks_t(spef_ctx* ctx) {
     }
     if (best < 0) continue;
     q.THI = (q.TH - 1) * S + 3;
-    q.tiles_y = cdiv(q.Ho, q.TH); q.tiles_x = q.Wo / TW;
+    q.tiles_y = cdiv(q.Ho, q.TH); q.tiles_x = q.Wo / (TW * stack);
     q.n_px = ((q.THI * TWI + 15) / 16) * 16;
     q.kc_in = cdiv(q.Cin, 64); q.n_chunks = cdiv(Ch, fbt::CL); q.cpad = ((q.Cout + 15) / 16) * 16;
+    q.we_bytes = (stack == 4) ? 224 * 128 : q.kc_in * fbt::CL * 128;
     if (q.cpad > 128 || q.n_chunks > fbt::MAX_W_STAGES) continue;
     q.residual = pj.residual;
     // worker groups, TMEM expand stages (n_px columns each, one more than groups when they fit) and the project
     // accumulator(s) behind them; shared memory: resident weights before a ring, as many x stages as fit
     bool found = false;
-    for (int ng = ctx->fbt_max_ng; ng >= 2 && !found; --ng) {
-      const int pcols = ((q.cpad + 31) / 32) * 32;
+    for (int ng = (stack == 4) ? 2 : ctx->fbt_max_ng; ng >= 2 && !found; --ng) {
+      // stacked: the per-strip accumulators sit cpad columns apart (the epilogue's x32 load over-reads into the next one)
+      const int pcols = (stack == 4) ? ((q.cpad * 4 + 31) / 32) * 32 : ((q.cpad + 31) / 32) * 32;
+      q.proj_sub = q.cpad;
       int n_acc = 0, pstages = 0;
       for (int na = ng + 1; na >= ng && !n_acc; --na)
         for (int ps = 2; ps >= 1 && !n_acc; --ps)
@@ -547,7 +554,8 @@ static int plan_blocks_t(spef_ctx* ctx) {
       q.n_acc = n_acc; q.acc_stride = q.n_px; q.proj_col0 = n_acc * q.n_px; q.proj_stages = pstages; q.proj_stride = (pstages == 2) ? pcols : 0;
       struct Opt { int w, res, x; };
       std::vector<Opt> opts;
-      for (int xs = 4; xs >= 1; --xs) opts.push_back({q.n_chunks, 1, xs});
+      // a stacked tile is four TMA boxes of 64-byte pixel rows (~2700 cycles): it must be prefetched behind the previous item
+      for (int xs = 4; xs >= (stack == 4 ? 2 : 1); --xs) opts.push_back({q.n_chunks, 1, xs});
       if (q.n_chunks > 3) for (int xs = 2; xs >= 1; --xs) { opts.push_back({4, 0, xs}); opts.push_back({3, 0, xs}); }
       for (const Opt& o : opts) {
         q.w_stages = o.w; q.resident = o.res; q.x_stages = o.x;
@@ -557,11 +565,22 @@ static int plan_blocks_t(spef_ctx* ctx) {
     if (!found) continue;
     // channel -> (chunk, quarter, lane): every chunk spreads its channels evenly over the four TMEM lane quarters
     const int per_q = Ch / 4, base = per_q / q.n_chunks, rem = per_q % q.n_chunks;
-    std::vector<bf16> we((size_t)q.n_chunks * fbt::CL * q.Cin, __float2bfloat16_rn(0.f));
+    std::vector<bf16> we(stack == 4 ? (size_t)224 * 64 : (size_t)q.n_chunks * fbt::CL * q.Cin, __float2bfloat16_rn(0.f));
     std::vector<bf16> wp((size_t)q.Cout * q.n_chunks * fbt::CL, __float2bfloat16_rn(0.f));
     std::vector<float> aux((size_t)q.n_chunks * fbt::AUX_ROWS * fbt::CL, 0.f);
     int ch = 0;
-    for (int c = 0; c < q.n_chunks; ++c) {
+    if (stack == 4) {   // slot (quarter qq, lane c) = channel c of strip qq: identity routed through K chunk qq
+      for (int qq = 0; qq < 4; ++qq)
+        for (int c = 0; c < Ch; ++c) {
+          const int slot = qq * 32 + c;
+          if (qq == 0) we[(size_t)(96 + c) * 64 + c] = __float2bfloat16_rn(1.f);   // window matrix: identity in rows 96..127
+          for (int co = 0; co < q.Cout; ++co) wp[(size_t)co * fbt::CL + slot] = pj.h_wb[(size_t)co * Ch + c];
+          aux[fbt::CL + slot] = d.h_bias[c];
+          for (int k = 0; k < 9; ++k) aux[(size_t)(2 + k) * fbt::CL + slot] = d.h_wdw[(size_t)k * Ch + c];
+        }
+      ch = Ch;
+    }
+    for (int c = 0; c < q.n_chunks && stack == 1; ++c) {
       const int nvq = base + (c < rem ? 1 : 0);
       if (nvq > 32) return fail(ctx, SPEF_ERR_INVALID, "plan_blocks_t: internal error (nvq = %d)", nvq);
       for (int qq = 0; qq < 4; ++qq)
@@ -938,13 +957,14 @@ static int launch_fused_block_t(spef_ctx* ctx, Block& b, const void* in, void* o
   std::vector<Layer>& L = ctx->layers;
   fbt::FbtParams& q = b.tprm;
   if (!b.t_tmW_ready) {
-    if (!tc::make_tmap_2d(ctx->encode, &b.t_tmWe, b.t_we, false, (long long)q.n_chunks * fbt::CL, q.Cin, q.Cin, fbt::CL) ||
+    if (!(q.stack == 4 ? tc::make_tmap_2d(ctx->encode, &b.t_tmWe, b.t_we, false, 224, 64, 64, 224)
+                       : tc::make_tmap_2d(ctx->encode, &b.t_tmWe, b.t_we, false, (long long)q.n_chunks * fbt::CL, q.Cin, q.Cin, fbt::CL)) ||
         !tc::make_tmap_2d(ctx->encode, &b.t_tmWp, b.t_wp, false, q.Cout, (long long)q.n_chunks * fbt::CL, (long long)q.n_chunks * fbt::CL, q.cpad))
       return fail(ctx, SPEF_ERR_CUDA, "cuTensorMapEncodeTiled(W') failed for fused block at layer %d", b.first);
     b.t_tmW_ready = true;
   }
   if (b.t_tmX_ptr != in || b.t_tmX_batch != B) {
-    if (!fb::make_tmap_x(ctx->encode, &b.t_tmX, in, B, q.H, q.W, q.Cin, q.TWI, q.THI))
+    if (!fb::make_tmap_x(ctx->encode, &b.t_tmX, in, B, q.H, q.W, q.cx, q.TWI, q.THI))
       return fail(ctx, SPEF_ERR_CUDA, "cuTensorMapEncodeTiled(X) failed for fused block at layer %d", b.first);
     b.t_tmX_ptr = in; b.t_tmX_batch = B;
   }
