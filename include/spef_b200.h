@@ -125,6 +125,23 @@ int spef_block_info(const spef_ctx* ctx, int32_t block, int32_t* first_layer, in
 int spef_set_fusion(spef_ctx* ctx, int32_t on);
 int spef_block_forward(spef_ctx* ctx, int32_t block, const void* in_dev, void* out_dev, int32_t batch, void* stream);
 
+/* ---- encode (label side) and error statistics (8f #3) ----------------------------
+ * spef_encode_ori replaces OrientationSoftClassification.encode for a batch of labels
+ * (src/spe/classification_utils.py:85-111): k_b = exp(-((2 acos(min(1, |q . h_b|)) / pi)^2 / (2 variance))), bins with
+ * masked_dev[b] != 0 (the reference's redundant_flags when delete_unused_bins is False; may be NULL) set to 0,
+ * pdf = k / sum k, float64 arithmetic, float32 result [B,n].  spef_encode_pos replaces PositionSoftClassification.encode
+ * (:218-240).  variance = (smooth_factor / n_bins_per_dim)^2 / 12.  flags_dev (nullable, zero it first): SPEF_FLAG_ENC_NAN
+ * where the reference raises ValueError('NaN found in encoded ...').
+ * spef_error_stats replaces np.mean / np.std / np.median / mad() over the per-image error lists of evaluation()
+ * (src/tools/evaluation.py:16-32, 95-99): x_dev[i * stride], i < n (e.g. a column of per_image) ->
+ * out_host[4] = {mean, population std, median, median absolute deviation}; synchronises the stream. */
+enum { SPEF_FLAG_ENC_NAN = 16u };
+int spef_encode_ori(spef_ctx* ctx, const double* quat_dev /*[B,4] float64 labels*/, int32_t batch, int32_t n, double variance,
+                    const uint8_t* masked_dev /*[n] or NULL*/, float* pdf_out_dev /*[B,n]*/, uint32_t* flags_dev, void* stream);
+int spef_encode_pos(spef_ctx* ctx, const double* pos_dev /*[B,3] float64 labels*/, int32_t batch, int32_t n, double variance,
+                    float* pdf_out_dev /*[B,n]*/, uint32_t* flags_dev, void* stream);
+int spef_error_stats(spef_ctx* ctx, const float* x_dev, int32_t stride, int32_t n, double* out_host /*[4]*/, void* stream);
+
 /* ---- post-processing -------------------------------------------------------------------------
  * spef_decode_ori replaces SPEUtils.last_activ (softmax, src/spe/spe_utils.py:75-76) when
  * is_logits != 0, and OrientationSoftClassification.decode_batch

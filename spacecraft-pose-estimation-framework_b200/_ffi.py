@@ -13,7 +13,7 @@ _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG_DIR, "libspef_b200.so")
 
 SPEF_FP32, SPEF_BF16 = 0, 1
-FLAG_ORI_NAN, FLAG_POS_ZERO_SUM, FLAG_POS_NAN, FLAG_DOT_GT_1_01 = 1, 2, 4, 8
+FLAG_ORI_NAN, FLAG_POS_ZERO_SUM, FLAG_POS_NAN, FLAG_DOT_GT_1_01, FLAG_ENC_NAN = 1, 2, 4, 8, 16
 KIND_STEM, KIND_PW, KIND_DW, KIND_POOL, KIND_HEAD = 0, 1, 2, 3, 4
 
 
@@ -59,6 +59,9 @@ SIGNATURES = {
     "spef_decode_ori": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "spef_decode_pos": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "spef_score": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
+    "spef_encode_ori": (C.c_int, [_vp, _vp, _i32, _i32, C.c_double, _vp, _vp, _vp, _vp]),
+    "spef_encode_pos": (C.c_int, [_vp, _vp, _i32, _i32, C.c_double, _vp, _vp, _vp]),
+    "spef_error_stats": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp]),
     "spef_predict": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "spef_predict_host": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "spef_eval_reset": (C.c_int, [_vp, _vp]),

@@ -470,4 +470,171 @@ __global__ void quat_continuity_kernel(float* __restrict__ quat, float* __restri
   if (fabsf(dot) > 0.5f) reinterpret_cast<float4*>(prev)[s] = q;
 }
 
+
+// --------------------------------------------------------------------------------------------------
+// Soft-classification ENCODE (label side):
+//   orientation (classification_utils.py:85-111): k_b = exp(-((2 acos(min(1, |q . h_b|)) / pi)^2) / (2 var)), masked bins = 0,
+//   p = k / sum k;  position (:218-240): k_b = exp(-|t - x_b|^2 / (2 var)).  The reference computes both in float64 (the labels
+//   come from the dataset JSON as float64) and casts the pdf to float32; so do these kernels.  One CTA per label.
+//   tab64: [n][4] doubles (quaternion bins, or x, y, z, 0).  flags: SPEF_FLAG_ENC_NAN when the pdf has a NaN (sum == 0).
+// --------------------------------------------------------------------------------------------------
+template <bool ORI>
+__global__ void __launch_bounds__(256) encode_kernel(const double* __restrict__ label, int B, int n, double inv_2var,
+                                                     const double* __restrict__ tab64, const uint8_t* __restrict__ masked,
+                                                     float* __restrict__ out, uint32_t* __restrict__ flags) {
+  const int b = blockIdx.x;
+  if (b >= B) return;
+  constexpr int LD = ORI ? 4 : 3;
+  double l[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+  for (int k = 0; k < LD; ++k) l[k] = label[(size_t)b * LD + k];
+  float* o = out + (size_t)b * n;
+  double part = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double h0 = tab64[(size_t)i * 4 + 0], h1 = tab64[(size_t)i * 4 + 1], h2 = tab64[(size_t)i * 4 + 2], h3 = tab64[(size_t)i * 4 + 3];
+    double k;
+    if (ORI) {
+      // np.sum(ori * histogram, axis=1): products then pairwise-free left-to-right sum of 4 terms, no FMA contraction
+      const double d = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(l[0], h0), __dmul_rn(l[1], h1)), __dmul_rn(l[2], h2)), __dmul_rn(l[3], h3));
+      const double c = (fabs(d) < 1.0 || d != d) ? fabs(d) : 1.0;   // np.minimum propagates NaN (fmin would not)
+      const double a = 2.0 * acos(c) / 3.141592653589793;
+      k = exp(-(a * a) * inv_2var);
+      if (masked != nullptr && masked[i]) k = 0.0;
+    } else {
+      const double dx = l[0] - h0, dy = l[1] - h1, dz = l[2] - h2;
+      k = exp(-__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)) * inv_2var);
+    }
+    o[i] = (float)k;   // staged un-normalised; rescaled below (the float64 value is recomputed there to divide in float64)
+    part += k;
+  }
+  __shared__ double red[8];
+  __shared__ double total;
+  part = warp_sum(part);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+    total = t;
+    if (!(t > 0.0) && flags != nullptr) flags[b] |= 16u;   // SPEF_FLAG_ENC_NAN: 0 / 0 (or a NaN label)
+  }
+  __syncthreads();
+  const double t = total;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double h0 = tab64[(size_t)i * 4 + 0], h1 = tab64[(size_t)i * 4 + 1], h2 = tab64[(size_t)i * 4 + 2], h3 = tab64[(size_t)i * 4 + 3];
+    double k;
+    if (ORI) {
+      const double d = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(l[0], h0), __dmul_rn(l[1], h1)), __dmul_rn(l[2], h2)), __dmul_rn(l[3], h3));
+      const double a = 2.0 * acos((fabs(d) < 1.0 || d != d) ? fabs(d) : 1.0) / 3.141592653589793;
+      k = exp(-(a * a) * inv_2var);
+      if (masked != nullptr && masked[i]) k = 0.0;
+    } else {
+      const double dx = l[0] - h0, dy = l[1] - h1, dz = l[2] - h2;
+      k = exp(-__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)) * inv_2var);
+    }
+    o[i] = (float)(k / t);
+  }
+}
+
+// --------------------------------------------------------------------------------------------------
+// Error statistics of evaluation() on the device (src/tools/evaluation.py:16-32, 95-99):
+//   out[0] = mean, out[1] = np.std (population, float64), out[2] = np.median, out[3] = mad = median(|x - median|).
+// One CTA.  Medians by an exact 4-pass radix select on the order-preserving integer image of the float32 values (np.median
+// of an even count averages the two middle elements; NumPy does that in the array's dtype -- float32 here, like the
+// reference's lists of float32 scalars converted by np.median).  scratch: n floats for |x - median|.
+// --------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t f32_order_key(float x) {
+  const uint32_t u = __float_as_uint(x);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float f32_from_key(uint32_t k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+// k-th smallest (0-based) of x[0..n): block-wide, every thread returns the value
+__device__ float block_select(const float* __restrict__ x, int n, int k, uint32_t* hist /*[256] shared*/, uint32_t* sh /*[2] shared*/) {
+  uint32_t prefix = 0, mask = 0;
+  int kk = k;
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const uint32_t key = f32_order_key(x[i]);
+      if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t acc = 0;
+      int d = 0;
+      for (; d < 256; ++d) {
+        if (acc + hist[d] > (uint32_t)kk) break;
+        acc += hist[d];
+      }
+      sh[0] = (uint32_t)d;
+      sh[1] = acc;
+    }
+    __syncthreads();
+    prefix |= sh[0] << shift;
+    mask |= 255u << shift;
+    kk -= (int)sh[1];
+    __syncthreads();
+  }
+  return f32_from_key(prefix);
+}
+__device__ float block_median(const float* __restrict__ x, int n, uint32_t* hist, uint32_t* sh) {
+  const float hi = block_select(x, n, n / 2, hist, sh);
+  if (n & 1) return hi;
+  const float lo = block_select(x, n, n / 2 - 1, hist, sh);
+  return __fmul_rn(__fadd_rn(lo, hi), 0.5f);   // np.median: mean of the two middle values, float32
+}
+__global__ void __launch_bounds__(1024) error_stats_kernel(const float* __restrict__ x, int stride, int n, float* __restrict__ scratch,
+                                                           float* __restrict__ packed, double* __restrict__ out) {
+  __shared__ uint32_t hist[256];
+  __shared__ uint32_t sh[2];
+  __shared__ double red[32];
+  __shared__ double mean_s;
+  // pack the strided column, mean and population variance in float64 (np.std of float32 data accumulates in float64? no:
+  // np.std on a list of float32 scalars builds a float32 array and reduces with float32 pairwise sums; the host wrapper
+  // documents the 1e-6 relative tolerance this implies)
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float v = x[(size_t)i * stride];
+    packed[i] = v;
+    s += (double)v;
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+    mean_s = t / (double)n;
+  }
+  __syncthreads();
+  const double mean = mean_s;
+  double v2 = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double d = (double)packed[i] - mean;
+    v2 += d * d;
+  }
+  v2 = warp_sum(v2);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v2;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+    out[0] = mean;
+    out[1] = sqrt(t / (double)n);
+  }
+  __syncthreads();
+  const float med = block_median(packed, n, hist, sh);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) scratch[i] = fabsf(__fsub_rn(packed[i], med));
+  __syncthreads();
+  const float madv = block_median(scratch, n, hist, sh);
+  if (threadIdx.x == 0) {
+    out[2] = (double)med;
+    out[3] = (double)madv;
+  }
+}
+
 }  // namespace spef

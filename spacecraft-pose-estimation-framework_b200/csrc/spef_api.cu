@@ -125,6 +125,8 @@ struct spef_ctx {
   int head_pad = 0;
   int plan_batch = -1;
   // tables
+  double* ori_tab64 = nullptr;   // [n][4] float64 bins for the encode kernels (the reference encodes in float64)
+  double* pos_tab64 = nullptr;
   float4* ori_tab = nullptr;
   int ori_n = 0;
   float4* pos_tab = nullptr;
@@ -379,7 +381,7 @@ extern "C" void spef_destroy(spef_ctx* ctx) {
   }
   for (Block& b : ctx->blocks) { cudaFree(b.aux); cudaFree(b.t_we); cudaFree(b.t_wp); cudaFree(b.t_aux); }
   for (int i = 0; i < 4; ++i) cudaFree(ctx->act[i]);
-  void* ptrs[] = {ctx->pooled, ctx->head_out, ctx->ori_tab, ctx->pos_tab, ctx->eval_sums, ctx->ws_images, ctx->ws_quat,
+  void* ptrs[] = {ctx->pooled, ctx->head_out, ctx->ori_tab64, ctx->pos_tab64, ctx->ori_tab, ctx->pos_tab, ctx->eval_sums, ctx->ws_images, ctx->ws_quat,
                   ctx->ws_pos, ctx->ws_qt, ctx->ws_tt, ctx->ws_soft, ctx->ws_soft2, ctx->ws_hinv, ctx->ws_per_image,
                   ctx->ws_argmax, ctx->ws_flags, ctx->ws_sums, ctx->t_ori_state, ctx->t_pos_state, ctx->t_has,
                   ctx->t_prev_still, ctx->t_prev_video};
@@ -774,6 +776,7 @@ extern "C" int spef_set_ori_histogram(spef_ctx* ctx, const double* q, int32_t n)
   std::vector<float4> t(n);
   for (int i = 0; i < n; ++i) t[i] = make_float4((float)q[i * 4], (float)q[i * 4 + 1], (float)q[i * 4 + 2], (float)q[i * 4 + 3]);
   if (!upload(&ctx->ori_tab, t)) return fail(ctx, SPEF_ERR_CUDA, "spef_set_ori_histogram: upload failed");
+  if (!upload(&ctx->ori_tab64, std::vector<double>(q, q + (size_t)n * 4))) return fail(ctx, SPEF_ERR_CUDA, "spef_set_ori_histogram: upload failed");
   ctx->ori_n = n;
   return SPEF_OK;
 }
@@ -785,6 +788,11 @@ extern "C" int spef_set_pos_histogram(spef_ctx* ctx, const double* x, int32_t n)
   std::vector<float4> t(n);
   for (int i = 0; i < n; ++i) t[i] = make_float4((float)x[i * 3], (float)x[i * 3 + 1], (float)x[i * 3 + 2], 0.f);
   if (!upload(&ctx->pos_tab, t)) return fail(ctx, SPEF_ERR_CUDA, "spef_set_pos_histogram: upload failed");
+  {
+    std::vector<double> t64((size_t)n * 4, 0.0);
+    for (int i = 0; i < n; ++i) { t64[(size_t)i * 4] = x[i * 3]; t64[(size_t)i * 4 + 1] = x[i * 3 + 1]; t64[(size_t)i * 4 + 2] = x[i * 3 + 2]; }
+    if (!upload(&ctx->pos_tab64, t64)) return fail(ctx, SPEF_ERR_CUDA, "spef_set_pos_histogram: upload failed");
+  }
   ctx->pos_n = n;
   return SPEF_OK;
 }
@@ -1257,6 +1265,50 @@ extern "C" int spef_decode_pos(spef_ctx* ctx, const float* in, int32_t B, int32_
   if (!ctx) return SPEF_ERR_INVALID;
   CK(cudaSetDevice(ctx->cfg.device));
   return decode_pos_ld(ctx, in, n, B, n, is_logits, soft, pos, flags, (cudaStream_t)stream);
+}
+
+// ---- encode (label side) and error statistics ---------------------------------------------------------------
+extern "C" int spef_encode_ori(spef_ctx* ctx, const double* quat_dev, int32_t B, int32_t n, double variance, const uint8_t* masked_dev,
+                               float* out_dev, uint32_t* flags_dev, void* stream) {
+  if (!ctx) return SPEF_ERR_INVALID;
+  if (!quat_dev || !out_dev || B < 1 || !(variance > 0.0)) return fail(ctx, SPEF_ERR_INVALID, "spef_encode_ori: bad argument");
+  if (!ctx->ori_tab64) return fail(ctx, SPEF_ERR_STATE, "spef_encode_ori: orientation histogram not set (spef_set_ori_histogram)");
+  if (n != ctx->ori_n) return fail(ctx, SPEF_ERR_INVALID, "spef_encode_ori: n = %d but the histogram has %d bins", n, ctx->ori_n);
+  CK(cudaSetDevice(ctx->cfg.device));
+  encode_kernel<true><<<B, 256, 0, (cudaStream_t)stream>>>(quat_dev, B, n, 1.0 / (2.0 * variance), ctx->ori_tab64, masked_dev, out_dev, flags_dev);
+  CK_LAUNCH("encode_kernel<ori>");
+  return SPEF_OK;
+}
+
+extern "C" int spef_encode_pos(spef_ctx* ctx, const double* pos_dev, int32_t B, int32_t n, double variance, float* out_dev, uint32_t* flags_dev,
+                               void* stream) {
+  if (!ctx) return SPEF_ERR_INVALID;
+  if (!pos_dev || !out_dev || B < 1 || !(variance > 0.0)) return fail(ctx, SPEF_ERR_INVALID, "spef_encode_pos: bad argument");
+  if (!ctx->pos_tab64) return fail(ctx, SPEF_ERR_STATE, "spef_encode_pos: position histogram not set (spef_set_pos_histogram)");
+  if (n != ctx->pos_n) return fail(ctx, SPEF_ERR_INVALID, "spef_encode_pos: n = %d but the histogram has %d bins", n, ctx->pos_n);
+  CK(cudaSetDevice(ctx->cfg.device));
+  encode_kernel<false><<<B, 256, 0, (cudaStream_t)stream>>>(pos_dev, B, n, 1.0 / (2.0 * variance), ctx->pos_tab64, nullptr, out_dev, flags_dev);
+  CK_LAUNCH("encode_kernel<pos>");
+  return SPEF_OK;
+}
+
+extern "C" int spef_error_stats(spef_ctx* ctx, const float* x_dev, int32_t stride, int32_t n, double* out_host, void* stream) {
+  if (!ctx) return SPEF_ERR_INVALID;
+  if (!x_dev || !out_host || stride < 1 || n < 1) return fail(ctx, SPEF_ERR_INVALID, "spef_error_stats: bad argument");
+  CK(cudaSetDevice(ctx->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  float* ws = nullptr;
+  double* out_d = nullptr;
+  CK(cudaMallocAsync((void**)&ws, (size_t)n * 8, st));
+  CK(cudaMallocAsync((void**)&out_d, 4 * sizeof(double), st));
+  error_stats_kernel<<<1, 1024, 0, st>>>(x_dev, stride, n, ws, ws + n, out_d);
+  cudaError_t le = cudaGetLastError();
+  if (le == cudaSuccess) { ctx->launches++; cudaMemcpyAsync(out_host, out_d, 4 * sizeof(double), cudaMemcpyDeviceToHost, st); }
+  cudaFreeAsync(ws, st);
+  cudaFreeAsync(out_d, st);
+  if (le != cudaSuccess) return fail(ctx, SPEF_ERR_CUDA, "launch of error_stats_kernel failed: %s", cudaGetErrorString(le));
+  CK(cudaStreamSynchronize(st));
+  return SPEF_OK;
 }
 
 extern "C" int spef_score(spef_ctx* ctx, const float* qp, const float* tp, const float* qt, const float* tt, int32_t B, double* sums,

@@ -214,6 +214,33 @@ class Engine:
                                           _stream(self.device)))
         return {"soft": soft if is_logits else x, "pos": pos, "flags": flags}
 
+    def encode_ori(self, quat: torch.Tensor, variance: float, masked: Optional[torch.Tensor] = None):
+        """Batch of true orientations [B,4] -> soft-classification pdfs [B,n_bins] (spef_encode_ori); masked: uint8 [n] or None."""
+        q = torch.as_tensor(quat).to(self.device, torch.float64).contiguous()   # labels are float64 in the reference's datasets
+        B = q.shape[0]
+        out = self._empty(B, self.ori_hist_n)
+        flags = torch.zeros(B, dtype=torch.int32, device=self.device)
+        m = None if masked is None else masked.to(self.device, torch.uint8).contiguous()
+        self._ck(self.lib.spef_encode_ori(self._h, ptr(q), B, self.ori_hist_n, float(variance), ptr(m), ptr(out), ptr(flags), _stream(self.device)))
+        return out, flags
+
+    def encode_pos(self, pos: torch.Tensor, variance: float):
+        t = torch.as_tensor(pos).to(self.device, torch.float64).contiguous()
+        B = t.shape[0]
+        out = self._empty(B, self.pos_hist_n)
+        flags = torch.zeros(B, dtype=torch.int32, device=self.device)
+        self._ck(self.lib.spef_encode_pos(self._h, ptr(t), B, self.pos_hist_n, float(variance), ptr(out), ptr(flags), _stream(self.device)))
+        return out, flags
+
+    def error_stats(self, x: torch.Tensor, column: int = 0) -> Dict[str, float]:
+        """mean / population std / median / median absolute deviation of x[:, column] (or of a 1-D x) on the device."""
+        x = self._dev_f32(x)
+        stride = 1 if x.dim() == 1 else x.shape[1]
+        view = x if x.dim() == 1 else x[:, column]
+        out = np.zeros(4, np.float64)
+        self._ck(self.lib.spef_error_stats(self._h, view.data_ptr(), stride, x.shape[0], out.ctypes.data, _stream(self.device)))
+        return {"mean": float(out[0]), "std": float(out[1]), "median": float(out[2]), "mad": float(out[3])}
+
     def score(self, quat_pred, pos_pred, quat_true, pos_true, sums: Optional[torch.Tensor] = None, want_per_image=False):
         qp, tp = self._dev_f32(quat_pred), self._dev_f32(pos_pred)
         qt, tt = self._dev_f32(quat_true), self._dev_f32(pos_true)

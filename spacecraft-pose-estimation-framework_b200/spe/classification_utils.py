@@ -91,6 +91,17 @@ class OrientationSoftClassification(_DeviceDecoder):
             eng.set_ori_histogram(self.histogram)
         return eng
 
+    def encode_batch(self, ori_batch: np.ndarray) -> np.ndarray:
+        """[B,4] true orientations -> [B,n_bins] float32 pdfs on the GPU (spef_encode_ori): `encode` (:85-111) for a batch,
+        e.g. label generation for a whole dataset.  Raises like `encode` when a pdf has a NaN."""
+        import torch
+        variance = (self.smooth_factor / self.n_bins_per_dim) ** 2 / 12
+        masked = None if self.delete_unused_bins else torch.from_numpy(self.redundant_flags.astype(np.uint8))
+        out, flags = self._engine_ready().encode_ori(torch.as_tensor(np.asarray(ori_batch, np.float64)), variance, masked)
+        if bool((flags & _ffi.FLAG_ENC_NAN).any()):
+            raise ValueError('NaN found in encoded orientation')
+        return out.cpu().numpy()
+
     def decode_batch(self, ori_batch: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
         """:149-166 -- [B,n_bins] pdfs -> ([B,4] float32 quaternions, [B,4,4] float32 inv(A))."""
         out = self._engine_ready().decode_ori_host(np.asarray(ori_batch), is_logits=False, want_hinv=True)
@@ -136,6 +147,15 @@ class PositionSoftClassification(_DeviceDecoder):
         if eng.pos_hist_n != self.n_bins:
             eng.set_pos_histogram(self.histogram)
         return eng
+
+    def encode_batch(self, pos_batch: np.ndarray) -> np.ndarray:
+        """[B,3] true positions -> [B,n_bins] float32 pdfs on the GPU (spef_encode_pos): `encode` (:218-240) for a batch."""
+        import torch
+        variance = (self.smooth_factor / self.n_bins_per_dim) ** 2 / 12
+        out, flags = self._engine_ready().encode_pos(torch.as_tensor(np.asarray(pos_batch, np.float64)), variance)
+        if bool((flags & _ffi.FLAG_ENC_NAN).any()):
+            raise ValueError('NaN found in encoded position')
+        return out.cpu().numpy()
 
     def decode_batch(self, pos_batch: np.ndarray) -> np.ndarray:
         """:269-285."""

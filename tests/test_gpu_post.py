@@ -219,3 +219,70 @@ def test_decode_large_batch_properties(post):
     idx = [0, 1, 1000, 4095, 4096, 6000, 8190, 8191]
     want, _ = O.ori_decode_batch(O.softmax(logits[idx].numpy()), hist)
     assert O.quat_angle_deg(qa[idx], want).max() <= QUAT_TOL_DEG
+
+
+def test_encode_batch_vs_reference_golden(golden):
+    """spef_encode_ori / spef_encode_pos (label side, SURVEY 8f #4) against the pdfs the unmodified reference encoded for 32 real
+    SPEED labels (tests/golden/encode_decode.npz: all bins / unused bins deleted / position); float64 in the kernel like NumPy."""
+    from spef_b200.spe.classification_utils import OrientationSoftClassification, PositionSoftClassification
+    g = golden("encode_decode")
+    q, t = g["labels_q"][:32], g["labels_t"][:32]
+    osc = OrientationSoftClassification(12, 3, False)
+    got = osc.encode_batch(q)
+    assert got.shape == g["enc_ori"].shape and got.dtype == np.float32
+    np.testing.assert_allclose(got, g["enc_ori"], rtol=2e-6, atol=1e-30)
+    np.testing.assert_allclose(got.sum(1), 1.0, atol=1e-6)
+    assert (got[:, osc.redundant_flags] == 0).all()
+    np.testing.assert_allclose(OrientationSoftClassification(12, 3, True).encode_batch(q), g["enc_ori_del"], rtol=2e-6, atol=1e-30)
+    psc = PositionSoftClassification(10, 100, np.array([-16, -12, -2]), np.array([16, 12, 40]))
+    np.testing.assert_allclose(psc.encode_batch(t), g["enc_pos"], rtol=2e-6, atol=1e-30)
+    # other histogram sizes against the oracle
+    hist, red = O.ori_histogram(16, False)
+    want = np.stack([O.ori_encode(qq, hist, red, 16, 3, False) for qq in q[:8]])
+    np.testing.assert_allclose(OrientationSoftClassification(16, 3, False).encode_batch(q[:8]), want, rtol=2e-6, atol=1e-30)
+    # encode -> decode round trip equals the reference's decoded labels
+    q_dec, _ = osc.decode_batch(got)
+    assert O.quat_angle_deg(q_dec, g["dec_ori"]).max() <= 0.05
+    with pytest.raises(ValueError):
+        osc.encode_batch(np.full((1, 4), np.nan))
+
+
+@pytest.mark.parametrize("n", [1, 2, 7, 1800, 4097])
+def test_error_stats_vs_numpy(n):
+    """spef_error_stats (SURVEY 8f #3) = np.mean / np.std / np.median / mad() of evaluation.py:16-32 on a float32 column."""
+    from spef_b200.engine import Engine
+    eng = Engine(32, 32, 8, 3, False, "fp32", 1)
+    rng = np.random.default_rng(n)
+    x = np.abs(rng.standard_normal((n, 2))).astype(np.float32) * np.array([30.0, 0.5], np.float32)
+    x[::5] = x[0]                                    # duplicates
+    if n > 10:
+        x[3, 0] = 1e4                                # an outlier
+    for col in (0, 1):
+        s = eng.error_stats(torch.from_numpy(x).cuda(), col)
+        c = x[:, col]
+        assert s["median"] == float(np.median(c))                       # exact: radix select + float32 mean of the middle pair
+        assert s["mad"] == float(O.mad(list(c)))
+        np.testing.assert_allclose(s["mean"], c.astype(np.float64).mean(), rtol=1e-12)
+        np.testing.assert_allclose(s["std"], c.astype(np.float64).std(), rtol=1e-10)
+        np.testing.assert_allclose(s["std"], np.std(c), rtol=2e-5)     # NumPy's float32 reduction
+
+
+def test_evaluation_device_stats_matches_host():
+    from spef_b200.modeling import import_model
+    from spef_b200.spe import SPEB200, SPEUtils
+    from spef_b200.tools import evaluation, synthetic
+    su = SPEUtils(None, 'classification', 12, 3, False, 'regression', 10, 100, None)
+    loader = synthetic.SyntheticLoader(10, 4)
+    model, _ = import_model({"valid": loader}, 'mobilenet_v2_pytorch', 'ursonet_pytorch', ori_mode='classification',
+                            n_ori_bins=su.orientation.n_bins, pos_mode='regression', precision="bf16")
+    model.load_state_dict(synthetic.synthetic_state_dict(1728, 3))
+    spe = SPEB200(model, torch.device("cuda:0"), su)
+    s_host, e_host = evaluation(spe, {"valid": loader}, su, ("valid",))
+    s_dev, e_dev = evaluation(spe, {"valid": loader}, su, ("valid",), device_stats=True)
+    assert s_host == s_dev
+    for k in ("ori", "pos"):
+        assert e_host["valid"][k] == e_dev["valid"][k]
+    for k in ("ori_std", "pos_std"):
+        np.testing.assert_allclose(e_dev["valid"][k], e_host["valid"][k], rtol=2e-5)
+    for k in ("ori_mad", "pos_mad"):
+        np.testing.assert_allclose(e_dev["valid"][k], e_host["valid"][k], rtol=1e-6)
