@@ -40,7 +40,15 @@ struct GemmParams {
   const float* img;
   int img_h, img_w, out_h, out_w;
   int img_u8;          // 1: img points at uint8 pixels, value = float(u8) / 255.0f (torchvision ToTensor)
+  // patch mode (stem): an M tile is a 2-row x 64-column patch of output pixels; its 5 x (2*64+1) x 3 input patch is staged in
+  // shared memory by TMA (tmA = 4-D map of the NCHW image, zero fill outside) and the im2col gather reads shared memory
+  // The patch is fetched as column chunks of 128 bytes (every TMA box in this library has an inner extent <= 128 B; a 528-byte
+  // inner box was accepted by cuTensorMapEncodeTiled but faulted with "illegal instruction" at the first load):
+  // chunk c = pixels [c * patch_w, (c + 1) * patch_w) stored as [3 planes][5 rows][patch_w]
+  int patch_mode, patch_tiles_x, patch_w, patch_chunks, patch_x0;   // tiles per output row (Wo / 64); patch_w = 32 (f32) | 128 (u8) pixels; 5 | 2 chunks
 };
+constexpr int PATCH_STAGES = 4;
+constexpr int PATCH_STAGE_BYTES = 10240;   // >= 5 chunks * 3 * 5 * 32 * 4 B
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

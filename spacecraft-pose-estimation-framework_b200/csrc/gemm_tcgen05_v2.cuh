@@ -37,6 +37,13 @@ __host__ __device__ inline bool w_is_resident(int N, int K, int block_n) { retur
 __host__ __device__ inline int stage_bytes_v2(int N, int K, int block_n) {
   return w_is_resident(N, K, block_n) ? A_STAGE_BYTES : stage_bytes(block_n);
 }
+// image patch: 3-D map {W, H, 3 * B planes} of the NCHW image
+__device__ __forceinline__ void tma_load_3d_img(uint32_t smem_dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 inline size_t smem_bytes_v2(int block_n, int num_stages, int N, int K) {
   return 1024 + (w_is_resident(N, K, block_n) ? (size_t)w_region_bytes(N, K, block_n) : 0) +
          (size_t)num_stages * stage_bytes_v2(N, K, block_n) + (size_t)V2_RING * STAGING_BYTES + (size_t)bias_floats(N) * 4 + 512;
@@ -97,6 +104,10 @@ pw_gemm_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
   uint64_t* sempty_bar = sfull_bar + V2_RING;                  // [V2_RING]     store -> drain
   uint64_t* w_bar = sempty_bar + V2_RING;                      // [1]           resident weights landed
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(w_bar + 1);
+  // stem patch ring (PROD, patch mode): barriers and buffers behind everything else (the host adds the bytes)
+  uint64_t* patch_full = reinterpret_cast<uint64_t*>(tmem_ptr_s + 2);      // [PATCH_STAGES]  TMA -> im2col producers
+  uint64_t* patch_empty = patch_full + PATCH_STAGES;                        // [PATCH_STAGES]  producers -> TMA
+  uint8_t* patch_s = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(patch_empty + PATCH_STAGES) + 1023) & ~(uintptr_t)1023);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -127,6 +138,12 @@ pw_gemm_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
       mbar_init(smem_u32(&sempty_bar[i]), NSW);           // one arrive per store warp
     }
     mbar_init(smem_u32(w_bar), 1);
+    if (PROD && p.patch_mode) {
+      for (int i = 0; i < PATCH_STAGES; ++i) {
+        mbar_init(smem_u32(&patch_full[i]), 1);
+        mbar_init(smem_u32(&patch_empty[i]), 128);
+      }
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -165,6 +182,25 @@ pw_gemm_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
           if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
         if (n_tiles == 1) { tm += gridDim.x; } else { const int t2 = tile + (int)gridDim.x; tm = t2 / n_tiles; tn = t2 % n_tiles; }
+      }
+      if (PROD && p.patch_mode) {   // stem: stage the input patch of every tile of this CTA (ring of PATCH_STAGES)
+        const int tiles_img = (p.out_h / 2) * p.patch_tiles_x;
+        const uint32_t cbytes = (uint32_t)(p.patch_w * 5 * 3 * (p.img_u8 ? 1 : 4));   // one column chunk
+        const uint32_t pbytes = cbytes * (uint32_t)p.patch_chunks;
+        int ps = 0;
+        uint32_t pph = 0;
+        // The innermost TMA coordinate must stay 16-byte aligned (x = -1 faulted with "illegal instruction" while -1 in an outer
+        // dimension is fine): the patch starts patch_x0 = 4 (f32) or 16 (u8) pixels left of the tile, pixel column -1 = patch column patch_x0 - 1.
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+          const int b = tile / tiles_img, r = tile - b * tiles_img;
+          const int ty = r / p.patch_tiles_x, tx = r - ty * p.patch_tiles_x;
+          mbar_wait(smem_u32(&patch_empty[ps]), pph ^ 1);
+          const uint32_t fb = smem_u32(&patch_full[ps]);
+          mbar_arrive_expect_tx(fb, pbytes);
+          for (int ch = 0; ch < p.patch_chunks; ++ch)
+            tma_load_3d_img(smem_u32(patch_s + (size_t)ps * PATCH_STAGE_BYTES + (size_t)ch * cbytes), &tmA, tx * 128 - p.patch_x0 + ch * p.patch_w, ty * 4 - 1, 3 * b, fb);
+          if (++ps == PATCH_STAGES) { ps = 0; pph ^= 1; }
+        }
       }
     }
     __syncwarp();
@@ -279,11 +315,56 @@ pw_gemm_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     uint32_t phase = (uint32_t)((pg / nstages) & 1);
     uint16_t cur[27], nxt[27];
     const int tile0 = (int)blockIdx.x + pg * (int)gridDim.x, tstep = PROD * (int)gridDim.x;
-    if (tile0 < num_tiles) gather(tile0, cur);
+    // patch mode: thread t = output pixel (row t >> 6, column t & 63) of the 2 x 64 patch; tap (ci, ky, kx) sits at
+    // patch[ci][2 * row + ky][2 * col + kx] of the TMA-staged input patch (zero outside the image)
+    int pst = pg % PATCH_STAGES;
+    uint32_t pphase = (uint32_t)((pg / PATCH_STAGES) & 1);
+    auto gather_patch = [&](uint16_t (&tap)[27]) {
+      mbar_wait(smem_u32(&patch_full[pst]), pphase);
+      const int pr = t >> 6, pc = t & 63;
+      // taps kx = 0, 1, 2 = patch columns colA, colA + 1, colA + 2 with colA = 2c + patch_x0 - 1 (odd): colA + 1, colA + 2 share a
+      // chunk (chunk widths are even) and form an aligned pair; colA may sit in the previous chunk
+      const int colA = 2 * pc + p.patch_x0 - 1, chA = colA / p.patch_w, inA = colA - chA * p.patch_w;
+      const int chB = (colA + 1) / p.patch_w, inB = colA + 1 - chB * p.patch_w;
+      const int cpix = p.patch_w * 15;   // pixels per chunk
+      if (p.img_u8) {
+        const uint8_t* pb = patch_s + (size_t)pst * PATCH_STAGE_BYTES + (size_t)(2 * pr) * p.patch_w;
+        const int oA = chA * cpix + inA, oB = chB * cpix + inB;
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky) {
+            const uint8_t* rowp = pb + (size_t)(ci * 5 + ky) * p.patch_w;
+            tap[(ci * 3 + ky) * 3 + 0] = lut[rowp[oA]];
+            tap[(ci * 3 + ky) * 3 + 1] = lut[rowp[oB]];
+            tap[(ci * 3 + ky) * 3 + 2] = lut[rowp[oB + 1]];
+          }
+      } else {
+        const float* pb = reinterpret_cast<const float*>(patch_s + (size_t)pst * PATCH_STAGE_BYTES) + (size_t)(2 * pr) * p.patch_w;
+        const int oA = chA * cpix + inA, oB = chB * cpix + inB;
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky) {
+            const float* rowp = pb + (size_t)(ci * 5 + ky) * p.patch_w;
+            const float v0 = rowp[oA];
+            const float2 v12 = *reinterpret_cast<const float2*>(rowp + oB);   // patch columns colA + 1, colA + 2 (8-byte aligned)
+            const bf16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v12.x), h2 = __float2bfloat16_rn(v12.y);
+            tap[(ci * 3 + ky) * 3 + 0] = *reinterpret_cast<const uint16_t*>(&h0);
+            tap[(ci * 3 + ky) * 3 + 1] = *reinterpret_cast<const uint16_t*>(&h1);
+            tap[(ci * 3 + ky) * 3 + 2] = *reinterpret_cast<const uint16_t*>(&h2);
+          }
+      }
+      mbar_arrive(smem_u32(&patch_empty[pst]));   // this thread's taps are in registers
+      pst += PROD;
+      if (pst >= PATCH_STAGES) { pst -= PATCH_STAGES; pphase ^= 1; }
+    };
+    if (!p.patch_mode && tile0 < num_tiles) gather(tile0, cur);
     for (int tile = tile0; tile < num_tiles; tile += tstep) {
       // software pipeline: the taps of the next tile are in flight while this one is staged
       const int next = tile + tstep;
-      if (next < num_tiles) gather(next, nxt);
+      if (p.patch_mode) gather_patch(cur);
+      else if (next < num_tiles) gather(next, nxt);
       uint32_t pk[16];
 #pragma unroll
       for (int k = 0; k < 16; ++k) {
@@ -440,7 +521,21 @@ pw_gemm_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
         const uint32_t sbuf = smem_u32(staging + (size_t)slot * STAGING_BYTES) + (uint32_t)(pc * 16);
         uint8_t* gp = outb + ((size_t)(m_idx + r0) * p.ldd + gcol) * ESZ;
         const size_t gstep = (size_t)(NST / 8) * p.ldd * ESZ;
-        if (col_ok) {
+        if (PROD && p.patch_mode) {
+          // patch tile: row r of the tile = output pixel (2 * ty + (r >> 6), 64 * tx + (r & 63)) of image b
+          const int tiles_img = (p.out_h / 2) * p.patch_tiles_x;
+          const int b = tm / tiles_img, rr = tm - b * tiles_img;
+          const int ty = rr / p.patch_tiles_x, tx = rr - ty * p.patch_tiles_x;
+          const size_t pix0 = ((size_t)b * p.out_h + 2 * ty) * p.out_w + 64 * tx;
+          if (col_ok) {
+#pragma unroll
+            for (int k = 0; k < 1024 / NST; ++k) {
+              const int r = r0 + k * (NST / 8);
+              const uint4 val = lds_u4(sbuf + (uint32_t)(r * STAGING_PITCH));
+              *reinterpret_cast<uint4*>(outb + ((pix0 + (size_t)(r >> 6) * p.out_w + (r & 63)) * p.ldd + gcol) * ESZ) = val;
+            }
+          }
+        } else if (col_ok) {
 #pragma unroll
           for (int k = 0; k < 1024 / NST; ++k) {
             const int r = r0 + k * (NST / 8);

@@ -100,6 +100,7 @@ struct spef_ctx {
   int fuse = 1;        // fused InvertedResidual kernels on the BF16 tcgen05 path (SPEF_FUSE=0 disables)
   int fb_gw = 4;       // warps per worker group of the fused kernel (SPEF_FB_GW = 4 | 8; 4 measured faster: more registers per thread)
   int fb_max_cin = 64; // fuse blocks with Cin <= this (SPEF_FB_MAX_CIN); wider blocks measured faster as three kernels
+  int stem_patch = 1;  // stem input patches staged by TMA (SPEF_STEM_PATCH=0: gather the 27 taps from global memory)
   int stem_prod = 2;   // im2col producer groups (128 threads each) of the tcgen05 stem (SPEF_STEM_PROD = 1 | 2)
   int fbt_max_ng = 3;  // worker groups of the channel-lane kernel: 3 where TMEM / shared memory allow, else 2 (SPEF_FBT_NG)
   int fb_variant = 1;  // 1: channel-lane fused kernel where it applies, else the staged one; 0: staged kernel only (SPEF_FB_VARIANT)
@@ -318,6 +319,7 @@ extern "C" int spef_create(spef_ctx** out, const spef_config* cfg) {
   if (const char* e9 = getenv("SPEF_FB_GW")) ctx->fb_gw = (atoi(e9) == 8) ? 8 : 4;
   if (const char* e11 = getenv("SPEF_FB_MAX_CIN")) ctx->fb_max_cin = atoi(e11);
   if (const char* e12 = getenv("SPEF_FB_VARIANT")) ctx->fb_variant = atoi(e12) ? 1 : 0;
+  if (const char* e15 = getenv("SPEF_STEM_PATCH")) ctx->stem_patch = atoi(e15) ? 1 : 0;
   if (const char* e14 = getenv("SPEF_STEM_PROD")) { int v = atoi(e14); ctx->stem_prod = (v == 1 || v == 4) ? v : 2; }
   if (const char* e13 = getenv("SPEF_FBT_NG")) ctx->fbt_max_ng = (atoi(e13) == 2) ? 2 : 3;
   if (const char* e10 = getenv("SPEF_FB_TRACE")) { ctx->fb_trace_block = atoi(e10); if (!ctx->trace_dev) cudaMalloc((void**)&ctx->trace_dev, 256 * 16 * sizeof(long long)); }
@@ -703,8 +705,8 @@ extern "C" int spef_finalize_weights(spef_ctx* ctx) {
     }
     if (l.kind == K_STEM) {  // stem as an implicit GEMM: M = B*Ho*Wo, N = 32, K = 27 -> 32
       l.block_n = 32;
-      l.stages = tc::pick_stages_v2(32, 32, 32, ctx->smem_optin);
-      l.smem = tc::smem_bytes_v2(32, l.stages, 32, 32);
+      l.stages = tc::pick_stages_v2(32, 32, 32, ctx->smem_optin - (tc::PATCH_STAGES * tc::PATCH_STAGE_BYTES + 1280));
+      l.smem = tc::smem_bytes_v2(32, l.stages, 32, 32) + tc::PATCH_STAGES * tc::PATCH_STAGE_BYTES + 1280;   // + stem patch ring (1024-byte aligned)
     }
     if (l.kind == K_PW || l.kind == K_HEAD) {
       l.block_n = tc::pick_block_n(l.n_pad);
@@ -880,11 +882,30 @@ static int launch_stem_tcgen05(spef_ctx* ctx, Layer& l, const void* images, void
   p.store_mode = 0; p.out = out; p.ldd = 32; p.trace = nullptr;
   p.img_u8 = ctx->image_u8;
   p.img = (const float*)images; p.img_h = l.hin; p.img_w = l.win; p.out_h = l.hout; p.out_w = l.wout;
+  // patch mode: 2 x 64 output-pixel tiles whose input patch is staged by TMA (needs exact tiling and 16-byte image rows)
+  CUtensorMap tmImg = l.tmW;
+  p.patch_mode = (ctx->stem_patch && l.hout % 2 == 0 && l.wout % 64 == 0 && l.hin == 2 * l.hout && l.win == 2 * l.wout &&
+                  (l.win * (ctx->image_u8 ? 1 : 4)) % 16 == 0 && ((uintptr_t)images % 16) == 0) ? 1 : 0;
+  if (p.patch_mode) {
+    p.patch_tiles_x = l.wout / 64;
+    p.patch_w = ctx->image_u8 ? 128 : 32;        // 128-byte column chunks
+    p.patch_chunks = ctx->image_u8 ? 2 : 5;      // >= patch_x0 + 2 * 64 pixels
+    p.patch_x0 = ctx->image_u8 ? 16 : 4;         // 16 bytes: the innermost TMA coordinate must be 16-byte aligned
+    const size_t esz = ctx->image_u8 ? 1 : 4;
+    const cuuint64_t gdim[3] = {(cuuint64_t)l.win, (cuuint64_t)l.hin, (cuuint64_t)3 * B};   // planes of all images: NCHW is [B*3][H][W]
+    const cuuint64_t gstride[2] = {(cuuint64_t)l.win * esz, (cuuint64_t)l.win * l.hin * esz};
+    const cuuint32_t box[3] = {(cuuint32_t)p.patch_w, 5, 3};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = ctx->encode(&tmImg, ctx->image_u8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(images),
+                             gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, SPEF_ERR_CUDA, "cuTensorMapEncodeTiled(image) failed for the stem");
+  }
   const int tiles = cdiv(p.M, tc::BLOCK_M);
   const int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
-  if (ctx->stem_prod == 4) tc::pw_gemm_tcgen05_v2_kernel<false, 1, 4, 4><<<grid, 128 + 512 + 128 + 128, l.smem, st>>>(l.tmW, l.tmW, p);
-  else if (ctx->stem_prod == 2) tc::pw_gemm_tcgen05_v2_kernel<false, 1, 4, 2><<<grid, 128 + 256 + 128 + 128, l.smem, st>>>(l.tmW, l.tmW, p);
-  else tc::pw_gemm_tcgen05_v2_kernel<false, 1, 4, 1><<<grid, 128 + 128 + 128 + 128, l.smem, st>>>(l.tmW, l.tmW, p);
+  if (ctx->stem_prod == 4) tc::pw_gemm_tcgen05_v2_kernel<false, 1, 4, 4><<<grid, 128 + 512 + 128 + 128, l.smem, st>>>(tmImg, l.tmW, p);
+  else if (ctx->stem_prod == 2) tc::pw_gemm_tcgen05_v2_kernel<false, 1, 4, 2><<<grid, 128 + 256 + 128 + 128, l.smem, st>>>(tmImg, l.tmW, p);
+  else tc::pw_gemm_tcgen05_v2_kernel<false, 1, 4, 1><<<grid, 128 + 128 + 128 + 128, l.smem, st>>>(tmImg, l.tmW, p);
   CK_LAUNCH("pw_gemm_tcgen05_v2_kernel<im2col stem>");
   return SPEF_OK;
 }
@@ -905,6 +926,7 @@ static int launch_tcgen05_layer(spef_ctx* ctx, Layer& l, const void* in, const v
     if (cached_maps) l.plan_batch = B;
   }
   tc::GemmParams p;
+  memset(&p, 0, sizeof(p));
   p.bias = l.bias; p.residual = (const bf16*)res; p.M = M; p.N = N; p.K = K; p.block_n = l.block_n; p.num_stages = l.stages; p.relu = l.relu;
   p.store_mode = ctx->gemm_store; p.out = out; p.ldd = N;
   p.img = nullptr; p.img_h = p.img_w = p.out_h = p.out_w = 0; p.img_u8 = 0;
