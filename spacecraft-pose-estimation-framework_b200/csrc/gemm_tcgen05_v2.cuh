@@ -44,6 +44,25 @@ __device__ __forceinline__ void tma_load_3d_img(uint32_t smem_dst, const CUtenso
       ::"r"(smem_dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// tcgen05.mma / tcgen05.commit issued by the elected lane of a converged warp (always the same lane: commit tracks the MMAs of
+// the executing thread)
+__device__ __forceinline__ void mma_elect_v2(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void commit_elect_v2(uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+      ::"r"(bar)
+      : "memory");
+}
 inline size_t smem_bytes_v2(int block_n, int num_stages, int N, int K) {
   return 1024 + (w_is_resident(N, K, block_n) ? (size_t)w_region_bytes(N, K, block_n) : 0) +
          (size_t)num_stages * stage_bytes_v2(N, K, block_n) + (size_t)V2_RING * STAGING_BYTES + (size_t)bias_floats(N) * 4 + 512;
@@ -206,33 +225,41 @@ pw_gemm_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     __syncwarp();
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // The whole warp runs the loop converged and one elected lane issues (elect.sync inside the asm): under `if (lane == 0)` the
+    // compiler wraps every tcgen05.mma in an ELECT / R2UR / BRA.U.ANY sequence, and a single thread retires ~1 instruction per
+    // 10 cycles, so the issuer -- not the tensor pipe -- paced the K-heavy layers (345 cycles per MMA at 960 -> 320).
+    // Descriptors are advanced by adding to precomputed bases.
+    {
       const uint32_t idesc = make_idesc_bf16(BLOCK_M, block_n);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
       int tn = (int)blockIdx.x % n_tiles;
+      const uint64_t a_base = make_smem_desc_sw128(smem_u32(stage_base));
+      const uint64_t bs_base = make_smem_desc_sw128(smem_u32(stage_base + A_STAGE_BYTES));   // streamed weights: behind the A tile of the stage
+      const uint64_t bw_base = make_smem_desc_sw128(smem_u32(w_region));                      // resident weights
+      const uint32_t s_step = (uint32_t)sbytes >> 4, w_step = (uint32_t)(block_n * 128) >> 4;
+      const uint32_t kst_last = (uint32_t)((p.K - (k_chunks - 1) * BLOCK_K + 15) / 16);
       if (w_resident) mbar_wait(smem_u32(w_bar), 0);
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         mbar_wait(smem_u32(&tmem_empty_bar[acc]), acc_phase ^ 1);
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * acc_stride);
+        uint64_t bw = bw_base + (uint64_t)((uint32_t)(tn * k_chunks) * w_step);
         for (int kc = 0; kc < k_chunks; ++kc) {
           mbar_wait(smem_u32(&full_bar[stage]), phase);
           tcgen05_fence_after();
-          uint8_t* sa = stage_base + (size_t)stage * sbytes;
-          const uint64_t a_desc = make_smem_desc_sw128(smem_u32(sa));
-          const uint64_t b_desc = make_smem_desc_sw128(w_resident ? smem_u32(w_region + (size_t)(tn * k_chunks + kc) * (block_n * 128))
-                                                                  : smem_u32(sa + A_STAGE_BYTES));
-          const int k_rem = p.K - kc * BLOCK_K;
-          const int ksteps = k_rem >= BLOCK_K ? 4 : (k_rem + 15) / 16;
-          for (int k = 0; k < ksteps; ++k)
-            tcgen05_mma_bf16(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kc > 0 || k > 0) ? 1u : 0u);
-          tcgen05_commit(smem_u32(&empty_bar[stage]));
+          const uint64_t a_desc = a_base + (uint64_t)((uint32_t)stage * s_step);
+          const uint64_t b_desc = w_resident ? bw : bs_base + (uint64_t)((uint32_t)stage * s_step);
+          const uint32_t ksteps = (kc == k_chunks - 1) ? kst_last : 4u;
+          for (uint32_t k = 0; k < ksteps; ++k)
+            mma_elect_v2(d_tmem, a_desc + (uint64_t)(k * 2u), b_desc + (uint64_t)(k * 2u), idesc, (kc > 0 || k > 0) ? 1u : 0u);
+          commit_elect_v2(smem_u32(&empty_bar[stage]));
           if (++stage == nstages) { stage = 0; phase ^= 1; }
+          bw += w_step;
         }
-        tcgen05_commit(smem_u32(&tmem_full_bar[acc]));
+        commit_elect_v2(smem_u32(&tmem_full_bar[acc]));
         if (++acc == acc_stages) { acc = 0; acc_phase ^= 1; }
         if (n_tiles > 1) tn = (tile + (int)gridDim.x) % n_tiles;
       }
