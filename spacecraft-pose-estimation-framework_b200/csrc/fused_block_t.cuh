@@ -62,7 +62,12 @@ struct FbtParams {
   // per strip: the K chunks of the operand pair are the strips (A chunk q = identity in the rows of quarter q, B chunk q =
   // x tile of strip q), so the issuer code is unchanged; the project GEMM runs once per strip (K = 32 = two K steps) into
   // its own accumulator.
-  int stack;           // 1 | 4
+  // Generalised (stack = 2, blocks with an expand conv and Cin <= 64): the lanes are split into `stack` blocks of 128 / stack channel
+  // slots; block s works on strip s with the SAME chunk of <= 128 / stack hidden channels, so a 144- or 192-channel block needs
+  // 3 chunk passes per two tiles instead of 4 (lane utilisation 75 % instead of 56 %).  The A operand of strip s is the 128-row
+  // window starting at row (stack - 1 - s) * (128 / stack) of [zeros | We chunk | zeros].
+  int stack;           // 1 | 2 | 4
+  int kst_stack;       // K steps of one strip's expand MMA (stack > 1): ceil(Cin / 16), or 2 for the identity
   int cx;              // channels of the x tensor (TMA map); == Cin unless stacked
   int proj_sub;        // TMEM columns between the per-strip project accumulators (stack = 4)
   int we_bytes;        // bytes of the expand-weight region of a weight stage: kc_in * 16 KB, or the 224-row window matrix (stack = 4):
@@ -252,7 +257,7 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
           const uint32_t fbar = tc::smem_u32(&w_full[w.ws]);
           uint8_t* dst = w_s + (size_t)w.ws * wsb;
           tc::mbar_arrive_expect_tx(fbar, w_tx);
-          if (p.stack > 1) tc::tma_load_2d(tc::smem_u32(dst), &tmWe, 0, 0, fbar);   // one box: the 224-row window matrix
+          if (p.stack > 1) tc::tma_load_2d(tc::smem_u32(dst), &tmWe, 0, w.c * (p.we_bytes >> 7), fbar);   // one box: the window matrix of chunk c
           else for (int kc = 0; kc < p.kc_in; ++kc) tc::tma_load_2d(tc::smem_u32(dst + (size_t)kc * CL * 128), &tmWe, kc * 64, w.c * CL, fbar);
           uint8_t* wp = dst + (size_t)p.we_bytes;
           tc::tma_load_2d(tc::smem_u32(wp), &tmWp, w.c * CL, 0, fbar);
@@ -271,6 +276,7 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     const uint64_t b_base = tc::make_smem_desc_sw128(tc::smem_u32(x_s));
     const uint32_t x_step = (uint32_t)xsb >> 4, w_step = (uint32_t)wsb >> 4;
     const uint32_t xk_step = (uint32_t)(p.n_px * 128) >> 4;
+    const uint32_t ls_rows16 = (uint32_t)((CL / p.stack) * 128) >> 4;   // one strip's block of channel slots, in 16-byte descriptor units
     for (fb::WorkIt w = fb::work_begin(); w.n < total; fb::work_next<NG>(w, itp)) {
       const int n = w.n;
       if (lane == 0) FBT_TRACE(n, 0);
@@ -283,8 +289,9 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       const uint64_t b0 = b_base + (uint64_t)((uint32_t)w.xs * x_step);
       const uint32_t d0 = tmem_base + (uint32_t)(w.as * p.acc_stride);
       for (int kc = 0; kc < p.kc_in; ++kc) {
-        const uint32_t ksteps = (p.stack > 1) ? 2u : ((kc == p.kc_in - 1) ? kst_last : 4u);   // stacked: K = 32 channels per strip
-        const uint32_t a_off = (p.stack > 1) ? (uint32_t)((96 - 32 * kc) * 128) >> 4 : (uint32_t)kc * (uint32_t)(CL * 128 >> 4);
+        const uint32_t ksteps = (p.stack > 1) ? (uint32_t)p.kst_stack : ((kc == p.kc_in - 1) ? kst_last : 4u);
+        // stacked: "K chunk" kc is strip kc; its A operand is the window at row (stack - 1 - kc) * (128 / stack)
+        const uint32_t a_off = (p.stack > 1) ? (uint32_t)(p.stack - 1 - kc) * ls_rows16 : (uint32_t)kc * (uint32_t)(CL * 128 >> 4);
         for (uint32_t ks = 0; ks < ksteps; ++ks)
           fb::mma_elect(d0, a0 + (uint64_t)(a_off + ks * 2u),
                         b0 + (uint64_t)((uint32_t)kc * xk_step + ks * 2u), idesc_e, (kc > 0 || ks > 0) ? 1u : 0u);
@@ -316,10 +323,12 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
           fb::mma_elect(d, a0 + (uint64_t)(ks * (uint32_t)(2 * A2_SBO >> 4)), b0 + (uint64_t)((ks >> 2) * wp_half + (ks & 3u) * 2u), idesc_p,
                         (w.c > 0 || ks > 0) ? 1u : 0u);
       } else {
+        // K steps per strip = 8 / stack (a power of two): strip s = channel slots [s * 128 / stack, ...) -> its own accumulator
+        const uint32_t kshift = (p.stack == 2) ? 2u : 1u, kmask = (1u << kshift) - 1u;
 #pragma unroll
-        for (uint32_t ks = 0; ks < 8; ++ks)   // strip ks / 2 = channel slots 32 * (ks / 2) ..: its own accumulator, K = 32
-          fb::mma_elect(d + (ks >> 1) * (uint32_t)p.proj_sub, a0 + (uint64_t)(ks * (uint32_t)(2 * A2_SBO >> 4)),
-                        b0 + (uint64_t)((ks >> 2) * wp_half + (ks & 3u) * 2u), idesc_p, ks & 1u);
+        for (uint32_t ks = 0; ks < 8; ++ks)
+          fb::mma_elect(d + (ks >> kshift) * (uint32_t)p.proj_sub, a0 + (uint64_t)(ks * (uint32_t)(2 * A2_SBO >> 4)),
+                        b0 + (uint64_t)((ks >> 2) * wp_half + (ks & 3u) * 2u), idesc_p, (w.c > 0 || (ks & kmask) > 0) ? 1u : 0u);
       }
       fb::commit_elect(tc::smem_u32(&a2_empty[w.g]));
       if (!p.resident) fb::commit_elect(tc::smem_u32(&w_empty[w.ws]));
@@ -411,7 +420,7 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         for (int k = 0; k < 9; ++k) wd[k] = lds_f32(aux_u + (uint32_t)((2 + k) * CL * 4));
       }
       const uint64_t be2 = f32x2(be, be);
-      const int ox0q = ox0 + (p.stack > 1 ? q * TW : 0);     // stacked: quarter q owns strip q of the tile
+      const int ox0q = ox0 + ((q * p.stack) >> 2) * TW;      // stacked: quarter q works on strip q * stack / 4 of the tile
       const bool left_ok = (ox0q * S - 1) >= 0;
       const bool right_ok = (ox0q * S - 1 + TWI - 1) < p.W;
       const int gy0 = oy0 * S - 1;

@@ -517,14 +517,22 @@ static int plan_blocks_t(spef_ctx* ctx) {
     const Layer& pj = L[b.i_proj];
     const int S = d.stride, TW = (S == 1) ? 12 : 6, TWI = (TW - 1) * S + 3;
     const int Ch = has_exp ? e.cout : d.cin;
-    // t = 1 block: identity "expand", four strips stacked in the four TMEM lane quarters (needs Ch == 32, stride 1, no skip)
-    const int stack = has_exp ? 1 : 4;
-    if (!has_exp && !(Ch == 32 && S == 1 && !pj.residual && !getenv("SPEF_FBT_NO_STACK"))) continue;
-    if (d.wout % (TW * stack) != 0 || Ch % 4 != 0 || (stack == 4 && pj.cout > 16)) continue;   // exact tiling in x: only the two halo columns can leave the image
+    // Strip stacking (fused_block_t.cuh): t = 1 block -> identity "expand", four strips in the four TMEM lane quarters (needs Ch == 32,
+    // stride 1, no skip, Cout <= 16); blocks whose hidden width wastes lanes at 128 channels per pass (144, 192) -> two strips of 64 slots
+    int stack = 1;
+    if (!has_exp) {
+      if (!(Ch == 32 && S == 1 && !pj.residual && pj.cout <= 16 && !getenv("SPEF_FBT_NO_STACK"))) continue;
+      stack = 4;
+    } else if (S == 1 && e.cin <= 64 && !getenv("SPEF_FBT_NO_STACK") && cdiv(Ch, 64) < 2 * cdiv(Ch, fbt::CL) && d.wout % (TW * 2) == 0) {
+      // (stride-2 blocks measured no faster stacked: their items are dominated by the conversion of the 4x larger hidden tile)
+      stack = 2;
+    }
+    const int LS = fbt::CL / stack;                  // channel slots per strip
+    if (d.wout % (TW * stack) != 0 || Ch % 4 != 0) continue;   // exact tiling in x: only the two halo columns can leave the image
     fbt::FbtParams& q = b.tprm;
     memset(&q, 0, sizeof(q));
-    q.H = e.hin; q.W = e.win; q.Cin = has_exp ? e.cin : 4 * 64; q.Cout = pj.cout; q.Ho = d.hout; q.Wo = d.wout;
-    q.cx = e.cin; q.stack = stack;
+    q.H = e.hin; q.W = e.win; q.Cin = (stack > 1) ? stack * 64 : e.cin; q.Cout = pj.cout; q.Ho = d.hout; q.Wo = d.wout;
+    q.cx = e.cin; q.stack = stack; q.kst_stack = has_exp ? cdiv(e.cin, 16) : 2;
     q.TW = TW; q.TWI = TWI;
     long long best = -1;
     for (int TH = 3; TH <= 6; ++TH) {              // instantiated kernels: S = 1: TH 4..6, S = 2: TH 3..4
@@ -538,17 +546,18 @@ static int plan_blocks_t(spef_ctx* ctx) {
     q.THI = (q.TH - 1) * S + 3;
     q.tiles_y = cdiv(q.Ho, q.TH); q.tiles_x = q.Wo / (TW * stack);
     q.n_px = ((q.THI * TWI + 15) / 16) * 16;
-    q.kc_in = cdiv(q.Cin, 64); q.n_chunks = cdiv(Ch, fbt::CL); q.cpad = ((q.Cout + 15) / 16) * 16;
-    q.we_bytes = (stack == 4) ? 224 * 128 : q.kc_in * fbt::CL * 128;
+    q.kc_in = cdiv(q.Cin, 64); q.n_chunks = cdiv(Ch, LS); q.cpad = ((q.Cout + 15) / 16) * 16;
+    const int we_rows = LS * (2 * stack - 1);       // window matrix [zeros | chunk | zeros]: 224 (stack 4), 192 (stack 2)
+    q.we_bytes = (stack > 1) ? we_rows * 128 : q.kc_in * fbt::CL * 128;
     if (q.cpad > 128 || q.n_chunks > fbt::MAX_W_STAGES) continue;
     q.residual = pj.residual;
     // worker groups, TMEM expand stages (n_px columns each, one more than groups when they fit) and the project
     // accumulator(s) behind them; shared memory: resident weights before a ring, as many x stages as fit
     bool found = false;
-    for (int ng = (stack == 4) ? 2 : ctx->fbt_max_ng; ng >= 2 && !found; --ng) {
+    for (int ng = (stack > 1) ? 2 : ctx->fbt_max_ng; ng >= 2 && !found; --ng) {
       // stacked: the per-strip accumulators sit cpad columns apart (the epilogue's x32 load over-reads into the next one)
-      const int pcols = (stack == 4) ? ((q.cpad * 4 + 31) / 32) * 32 : ((q.cpad + 31) / 32) * 32;
-      q.proj_sub = q.cpad;
+      const int pcols = (stack > 1) ? ((q.cpad * stack + 31) / 32) * 32 : ((q.cpad + 31) / 32) * 32;
+      q.proj_sub = (stack == 2) ? ((q.cpad + 31) / 32) * 32 : q.cpad;   // (the epilogue reads 32 columns at a time when Cout > 16)
       int n_acc = 0, pstages = 0;
       for (int na = ng + 1; na >= ng && !n_acc; --na)
         for (int ps = 2; ps >= 1 && !n_acc; --ps)
@@ -567,36 +576,38 @@ static int plan_blocks_t(spef_ctx* ctx) {
       }
     }
     if (!found) continue;
-    // channel -> (chunk, quarter, lane): every chunk spreads its channels evenly over the four TMEM lane quarters
-    const int per_q = Ch / 4, base = per_q / q.n_chunks, rem = per_q % q.n_chunks;
-    std::vector<bf16> we(stack == 4 ? (size_t)224 * 64 : (size_t)q.n_chunks * fbt::CL * q.Cin, __float2bfloat16_rn(0.f));
+    // channel -> (chunk, quarter, lane): every chunk spreads its channels evenly over the TMEM lane quarters of a strip; the
+    // strips of a stacked tile hold the same channels (slot = strip * LS + quarter-in-strip * 32 + lane)
+    const int QS = 4 / stack;                        // lane quarters per strip
+    const int per_q = Ch / QS, base = per_q / q.n_chunks, rem = per_q % q.n_chunks;
+    const size_t we_cols = (stack > 1) ? 64 : (size_t)q.Cin;
+    std::vector<bf16> we((stack > 1 ? (size_t)q.n_chunks * we_rows : (size_t)q.n_chunks * fbt::CL) * we_cols, __float2bfloat16_rn(0.f));
     std::vector<bf16> wp((size_t)q.Cout * q.n_chunks * fbt::CL, __float2bfloat16_rn(0.f));
     std::vector<float> aux((size_t)q.n_chunks * fbt::AUX_ROWS * fbt::CL, 0.f);
+    if (Ch % QS != 0) continue;
     int ch = 0;
-    if (stack == 4) {   // slot (quarter qq, lane c) = channel c of strip qq: identity routed through K chunk qq
-      for (int qq = 0; qq < 4; ++qq)
-        for (int c = 0; c < Ch; ++c) {
-          const int slot = qq * 32 + c;
-          if (qq == 0) we[(size_t)(96 + c) * 64 + c] = __float2bfloat16_rn(1.f);   // window matrix: identity in rows 96..127
-          for (int co = 0; co < q.Cout; ++co) wp[(size_t)co * fbt::CL + slot] = pj.h_wb[(size_t)co * Ch + c];
-          aux[fbt::CL + slot] = d.h_bias[c];
-          for (int k = 0; k < 9; ++k) aux[(size_t)(2 + k) * fbt::CL + slot] = d.h_wdw[(size_t)k * Ch + c];
-        }
-      ch = Ch;
-    }
-    for (int c = 0; c < q.n_chunks && stack == 1; ++c) {
+    for (int c = 0; c < q.n_chunks; ++c) {
       const int nvq = base + (c < rem ? 1 : 0);
       if (nvq > 32) return fail(ctx, SPEF_ERR_INVALID, "plan_blocks_t: internal error (nvq = %d)", nvq);
-      for (int qq = 0; qq < 4; ++qq)
+      float* a = aux.data() + (size_t)c * fbt::AUX_ROWS * fbt::CL;
+      for (int qq = 0; qq < QS; ++qq)
         for (int l = 0; l < nvq; ++l, ++ch) {
-          const int slot = qq * 32 + l;
-          const size_t row = (size_t)c * fbt::CL + slot;
-          for (int k = 0; k < q.Cin; ++k) we[row * q.Cin + k] = e.h_wb[(size_t)ch * q.Cin + k];
-          for (int co = 0; co < q.Cout; ++co) wp[(size_t)co * q.n_chunks * fbt::CL + row] = pj.h_wb[(size_t)co * Ch + ch];
-          float* a = aux.data() + (size_t)c * fbt::AUX_ROWS * fbt::CL;
-          a[slot] = e.h_bias[ch];
-          a[fbt::CL + slot] = d.h_bias[ch];
-          for (int k = 0; k < 9; ++k) a[(2 + k) * fbt::CL + slot] = d.h_wdw[(size_t)k * Ch + ch];
+          const int in_strip = qq * 32 + l;          // slot inside the strip's block of LS lanes
+          // expand weights: one copy (the window matrix places it for every strip), identity for the t = 1 block
+          if (stack > 1) {
+            bf16* row = we.data() + ((size_t)c * we_rows + (size_t)(stack - 1) * LS + in_strip) * 64;
+            if (has_exp) for (int k = 0; k < e.cin; ++k) row[k] = e.h_wb[(size_t)ch * e.cin + k];
+            else row[ch] = __float2bfloat16_rn(1.f);
+          } else {
+            for (int k = 0; k < q.Cin; ++k) we[((size_t)c * fbt::CL + in_strip) * q.Cin + k] = e.h_wb[(size_t)ch * q.Cin + k];
+          }
+          for (int st = 0; st < stack; ++st) {       // per-slot project weights and depthwise constants, replicated per strip
+            const int slot = st * LS + in_strip;
+            for (int co = 0; co < q.Cout; ++co) wp[(size_t)co * q.n_chunks * fbt::CL + (size_t)c * fbt::CL + slot] = pj.h_wb[(size_t)co * Ch + ch];
+            a[slot] = has_exp ? e.h_bias[ch] : 0.f;
+            a[fbt::CL + slot] = d.h_bias[ch];
+            for (int k = 0; k < 9; ++k) a[(2 + k) * fbt::CL + slot] = d.h_wdw[(size_t)k * Ch + ch];
+          }
         }
     }
     if (ch != Ch) return fail(ctx, SPEF_ERR_INVALID, "plan_blocks_t: internal error (%d of %d channels placed)", ch, Ch);
@@ -987,7 +998,7 @@ static int launch_fused_block_t(spef_ctx* ctx, Block& b, const void* in, void* o
   std::vector<Layer>& L = ctx->layers;
   fbt::FbtParams& q = b.tprm;
   if (!b.t_tmW_ready) {
-    if (!(q.stack == 4 ? tc::make_tmap_2d(ctx->encode, &b.t_tmWe, b.t_we, false, 224, 64, 64, 224)
+    if (!(q.stack > 1 ? tc::make_tmap_2d(ctx->encode, &b.t_tmWe, b.t_we, false, (long long)q.n_chunks * (q.we_bytes >> 7), 64, 64, q.we_bytes >> 7)
                        : tc::make_tmap_2d(ctx->encode, &b.t_tmWe, b.t_we, false, (long long)q.n_chunks * fbt::CL, q.Cin, q.Cin, fbt::CL)) ||
         !tc::make_tmap_2d(ctx->encode, &b.t_tmWp, b.t_wp, false, q.Cout, (long long)q.n_chunks * fbt::CL, (long long)q.n_chunks * fbt::CL, q.cpad))
       return fail(ctx, SPEF_ERR_CUDA, "cuTensorMapEncodeTiled(W') failed for fused block at layer %d", b.first);
