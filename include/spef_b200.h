@@ -96,6 +96,18 @@ int spef_set_pos_histogram(spef_ctx* ctx, const double* pos_bins_host /*[n,3]*/,
 enum { SPEF_IMG_F32 = 0, SPEF_IMG_U8 = 1 };
 int spef_set_image_dtype(spef_ctx* ctx, int32_t image_dtype);
 
+/* ---- camera frames (the step before the tensor contract) -----------------------------
+ * replaces, per frame, SPEDataset.__getitem__'s  self.transform(Image.open(path).convert("RGB"))  (src/data/utils.py:215-226)
+ * with transform = Compose([Resize(img_size), ToTensor()]) (src/data/datasets/speed.py:59-62): Pillow's antialiased BILINEAR
+ * resample (separable triangle filter, 22-bit fixed point on 8-bit pixels, horizontal pass first, each pass rounded and
+ * clipped) followed by float32(u8) / 255.  frames_dev: decoded 8-bit frames [B, src_h, src_w, channels], channels = 1
+ * (SPEED's greyscale JPEGs; replicated to three planes like convert("RGB")) or 3 (RGB, HWC as np.array(image)).
+ * images_out_dev: [B, 3, img_h, img_w] of out_dtype: SPEF_IMG_U8 (feed it to a context set to SPEF_IMG_U8) or SPEF_IMG_F32
+ * (the reference tensor).  Bit-exact against torchvision + Pillow for any source size (up- or down-scaling).  JPEG
+ * decoding stays with the caller. */
+int spef_resize_frames(spef_ctx* ctx, const uint8_t* frames_dev, int32_t batch, int32_t src_h, int32_t src_w, int32_t channels,
+                       void* images_out_dev, int32_t out_dtype, void* stream);
+
 /* ---- network: replaces ModelWrapper.forward (src/modeling/common/pytorch_layers.py:29-32) ------ */
 int spef_forward(spef_ctx* ctx, const float* images_dev, int32_t batch,
                  float* ori_out_dev /*[B,n_ori] logits*/, float* pos_out_dev /*[B,n_pos]*/, void* stream);
@@ -243,6 +255,8 @@ int spef_forward_timed(spef_ctx* ctx, const float* images_dev, int32_t batch, fl
 /* debug: the device-side 4x4 Jacobi eigen-solver compiled for the host (no GPU needed), so that the CPU
  * test-suite can pin it against LAPACK.  a_in row-major symmetric; evecs row-major with eigenvectors as columns. */
 int spef_debug_jacobi4_host(const double* a_in, double* evals, double* evecs);
+/* the eigen-solve of the large-batch decode kernel on the host: sums = {S, a00 a01 a02 a03 a11 a12 a13 a22 a23 a33} */
+int spef_debug_decode_solve_host(const double* sums, int32_t is_logits, float* quat, float* hinv);
 
 #ifdef __cplusplus
 }

@@ -430,3 +430,75 @@ def quat_angle_deg(a: np.ndarray, b: np.ndarray) -> np.ndarray:
     a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
     dm, dp = np.linalg.norm(a - b, axis=-1), np.linalg.norm(a + b, axis=-1)
     return np.degrees(2 * np.arctan2(np.minimum(dm, dp), np.maximum(dm, dp))) * 2
+
+
+# --------------------------------------------------------------------------------------
+# Input side of the path: SPEDataset.__getitem__ (src/data/utils.py:212-226) opens the frame with
+# PIL, .convert("RGB"), then applies transforms.Compose([Resize(img_size), ToTensor()]) (src/data/datasets/speed.py:59-62).
+# The arithmetic lives in third-party Pillow (unpinned by the reference; 12.2.0 here): Image.resize(BILINEAR) is a
+# separable, antialiased triangle filter evaluated in 22-bit fixed point on 8-bit pixels, horizontal pass first, each
+# pass rounded and clipped to 8 bits; torchvision's ToTensor is float32(u8) / 255.  Restated from Pillow's published
+# algorithm (libImaging "Resample": coefficient pre-computation in float64, 8-bit-per-channel passes) and pinned against
+# the real torchvision + Pillow pipeline by tests/golden/resize.npz (tests/golden/make_goldens.py: golden_resize).
+# --------------------------------------------------------------------------------------
+RESIZE_PRECISION_BITS = 32 - 8 - 2
+
+
+def resize_coeffs(in_size: int, out_size: int) -> Tuple[np.ndarray, np.ndarray]:
+    """Triangle-filter taps for one axis: (bounds [out,2] = first input index / tap count, kk [out,ksize] int32)."""
+    scale = float(in_size) / out_size
+    fscale = max(scale, 1.0)
+    support = 1.0 * fscale
+    ksize = int(math.ceil(support)) * 2 + 1
+    bounds = np.zeros((out_size, 2), np.int32)
+    kk = np.zeros((out_size, ksize), np.int32)
+    inv = 1.0 / fscale
+    for o in range(out_size):
+        center = (o + 0.5) * scale
+        lo = max(int(center - support + 0.5), 0)
+        hi = min(int(center + support + 0.5), in_size)
+        n = hi - lo
+        w = np.zeros(n, np.float64)
+        total = 0.0
+        for j in range(n):
+            t = abs((j + lo - center + 0.5) * inv)
+            w[j] = 1.0 - t if t < 1.0 else 0.0
+            total += w[j]
+        if total != 0.0:
+            w = w / total
+        bounds[o] = (lo, n)
+        for j in range(n):
+            v = w[j] * (1 << RESIZE_PRECISION_BITS)
+            kk[o, j] = int(-0.5 + v) if w[j] < 0 else int(0.5 + v)
+    return bounds, kk
+
+
+def _resize_pass(img: np.ndarray, bounds: np.ndarray, kk: np.ndarray) -> np.ndarray:
+    """One 8-bit pass along axis -1 of img [..., in] -> [..., out]."""
+    out = np.empty(img.shape[:-1] + (bounds.shape[0],), np.uint8)
+    src = img.astype(np.int64)
+    for o in range(bounds.shape[0]):
+        lo, n = int(bounds[o, 0]), int(bounds[o, 1])
+        acc = (src[..., lo:lo + n] * kk[o, :n].astype(np.int64)).sum(-1) + (1 << (RESIZE_PRECISION_BITS - 1))
+        out[..., o] = np.clip(acc >> RESIZE_PRECISION_BITS, 0, 255).astype(np.uint8)
+    return out
+
+
+def resize_frames(frames: np.ndarray, out_h: int, out_w: int) -> np.ndarray:
+    """frames uint8 [B,H,W] (grey, replicated like .convert('RGB')) or [B,H,W,3] -> uint8 [B,3,out_h,out_w] (the bytes
+    ToTensor divides by 255)."""
+    f = np.asarray(frames)
+    assert f.dtype == np.uint8
+    if f.ndim == 3:
+        f = np.repeat(f[..., None], 3, axis=-1)
+    f = np.ascontiguousarray(f.transpose(0, 3, 1, 2))          # [B,3,H,W]
+    hb, hk = resize_coeffs(f.shape[3], out_w)
+    vb, vk = resize_coeffs(f.shape[2], out_h)
+    h = _resize_pass(f, hb, hk)                                 # [B,3,H,out_w]
+    v = _resize_pass(np.ascontiguousarray(h.transpose(0, 1, 3, 2)), vb, vk)   # [B,3,out_w,out_h]
+    return np.ascontiguousarray(v.transpose(0, 1, 3, 2))
+
+
+def to_tensor(u8: np.ndarray) -> np.ndarray:
+    """torchvision ToTensor on 8-bit data: float32(u8) / 255 (float32 division)."""
+    return u8.astype(np.float32) / np.float32(255.0)

@@ -48,6 +48,7 @@ SIGNATURES = {
     "spef_set_ori_histogram": (C.c_int, [_vp, _vp, _i32]),
     "spef_set_pos_histogram": (C.c_int, [_vp, _vp, _i32]),
     "spef_set_image_dtype": (C.c_int, [_vp, _i32]),
+    "spef_resize_frames": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
     "spef_forward": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp]),
     "spef_num_layers": (C.c_int, [_vp]),
     "spef_layer_info": (C.c_int, [_vp, _i32] + [C.POINTER(_i32)] * 10),
@@ -82,6 +83,7 @@ SIGNATURES = {
     "spef_forward_cost": (C.c_int, [_vp, _i32, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "spef_forward_timed": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp]),
     "spef_debug_jacobi4_host": (C.c_int, [_vp, _vp, _vp]),
+    "spef_debug_decode_solve_host": (C.c_int, [_vp, _i32, _vp, _vp]),
 }
 
 _lib: Optional[C.CDLL] = None

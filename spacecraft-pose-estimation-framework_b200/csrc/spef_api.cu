@@ -22,6 +22,8 @@
 #include "fused_block_t.cuh"
 #include "kernels_conv.cuh"
 #include "kernels_post.cuh"
+#include "kernels_ingest.cuh"
+#include "decode_stream.cuh"
 
 using namespace spef;
 
@@ -129,6 +131,9 @@ struct spef_ctx {
   double* ori_tab64 = nullptr;   // [n][4] float64 bins for the encode kernels (the reference encodes in float64)
   double* pos_tab64 = nullptr;
   float4* ori_tab = nullptr;
+  float* ori_tab_soa = nullptr;  // [4][ori_tab_ld]: one plane per quaternion component, zero padded (decode_ori_stream_kernel)
+  int ori_tab_ld = 0;
+  int decode_stream = 1;         // large batches take the streaming decode kernel (SPEF_DECODE_STREAM: 0 never, 2 always)
   int ori_n = 0;
   float4* pos_tab = nullptr;
   int pos_n = 0;
@@ -167,6 +172,9 @@ struct spef_ctx {
   float* t_prev_still = nullptr; // [S,4]
   float* t_prev_video = nullptr;
   float* t_ws[8] = {nullptr};    // scratch outputs when the caller passes NULL
+  // ingest plan (spef_resize_frames): taps of both axes for the last (src_h, src_w) seen, one device allocation
+  int rz_sh = 0, rz_sw = 0, rz_hks = 0, rz_vks = 0, rz_band = 0, rz_max_rows = 0, rz_pitch = 0;
+  int* rz_tab = nullptr;
   // bookkeeping
   int64_t launches = 0;
   std::vector<cudaEvent_t> events;
@@ -310,6 +318,7 @@ extern "C" int spef_create(spef_ctx** out, const spef_config* cfg) {
   ctx->smem_optin = prop.sharedMemPerBlockOptin;
   ctx->esz = (cfg->precision == SPEF_BF16) ? 2 : 4;
   if (const char* e4 = getenv("SPEF_GEMM_TRACE")) { ctx->trace_layer = atoi(e4); cudaMalloc((void**)&ctx->trace_dev, 256 * 16 * sizeof(long long)); }
+  if (const char* e12 = getenv("SPEF_DECODE_STREAM")) ctx->decode_stream = atoi(e12);  // 0 never, 1 large batches, 2 always (tests)
   if (const char* e5 = getenv("SPEF_GEMM_IMPL")) ctx->gemm_impl = (atoi(e5) == 1) ? 1 : 2;
   if (const char* e7 = getenv("SPEF_GEMM_NDG")) ctx->gemm_ndg = (atoi(e7) == 1) ? 1 : 2;
   if (const char* e6 = getenv("SPEF_GEMM_NSW")) ctx->gemm_nsw = (atoi(e6) == 8 && ctx->gemm_ndg == 1) ? 8 : 4;
@@ -386,7 +395,7 @@ extern "C" void spef_destroy(spef_ctx* ctx) {
   void* ptrs[] = {ctx->pooled, ctx->head_out, ctx->ori_tab64, ctx->pos_tab64, ctx->ori_tab, ctx->pos_tab, ctx->eval_sums, ctx->ws_images, ctx->ws_quat,
                   ctx->ws_pos, ctx->ws_qt, ctx->ws_tt, ctx->ws_soft, ctx->ws_soft2, ctx->ws_hinv, ctx->ws_per_image,
                   ctx->ws_argmax, ctx->ws_flags, ctx->ws_sums, ctx->t_ori_state, ctx->t_pos_state, ctx->t_has,
-                  ctx->t_prev_still, ctx->t_prev_video};
+                  ctx->t_prev_still, ctx->t_prev_video, ctx->rz_tab, ctx->ori_tab_soa};
   for (void* p : ptrs) cudaFree(p);
   for (int i = 0; i < 8; ++i) cudaFree(ctx->t_ws[i]);
   for (cudaEvent_t ev : ctx->events) cudaEventDestroy(ev);
@@ -790,6 +799,11 @@ extern "C" int spef_set_ori_histogram(spef_ctx* ctx, const double* q, int32_t n)
   for (int i = 0; i < n; ++i) t[i] = make_float4((float)q[i * 4], (float)q[i * 4 + 1], (float)q[i * 4 + 2], (float)q[i * 4 + 3]);
   if (!upload(&ctx->ori_tab, t)) return fail(ctx, SPEF_ERR_CUDA, "spef_set_ori_histogram: upload failed");
   if (!upload(&ctx->ori_tab64, std::vector<double>(q, q + (size_t)n * 4))) return fail(ctx, SPEF_ERR_CUDA, "spef_set_ori_histogram: upload failed");
+  ctx->ori_tab_ld = (n + dstream::SUB - 1) / dstream::SUB * dstream::SUB;
+  std::vector<float> soa((size_t)4 * ctx->ori_tab_ld, 0.f);
+  for (int i = 0; i < n; ++i)
+    for (int c = 0; c < 4; ++c) soa[(size_t)c * ctx->ori_tab_ld + i] = (float)q[i * 4 + c];
+  if (!upload(&ctx->ori_tab_soa, soa)) return fail(ctx, SPEF_ERR_CUDA, "spef_set_ori_histogram: upload failed");
   ctx->ori_n = n;
   return SPEF_OK;
 }
@@ -1261,6 +1275,80 @@ extern "C" int spef_block_forward(spef_ctx* ctx, int32_t i, const void* in, void
 }
 
 // ------------------------------------------------------------------------------------------------------
+// ingest: camera frames -> the tensor the stem reads
+// ------------------------------------------------------------------------------------------------------
+static int resize_plan(spef_ctx* ctx, int sh, int sw, int C) {
+  const int oh = ctx->cfg.img_h, ow = ctx->cfg.img_w;
+  if (ctx->rz_tab && ctx->rz_sh == sh && ctx->rz_sw == sw) return SPEF_OK;
+  const ingest::AxisTaps h = ingest::make_axis_taps(sw, ow), v = ingest::make_axis_taps(sh, oh);
+  // layout of the table block (int32): hfirst[ow] hcount[ow] hcoef[hks][ow] vfirst[oh] vcount[oh] vcoef[oh][vks]
+  std::vector<int> tab;
+  tab.insert(tab.end(), h.first.begin(), h.first.end());
+  tab.insert(tab.end(), h.count.begin(), h.count.end());
+  for (int j = 0; j < h.ksize; ++j)
+    for (int o = 0; o < ow; ++o) tab.push_back(h.coef[(size_t)o * h.ksize + j]);
+  tab.insert(tab.end(), v.first.begin(), v.first.end());
+  tab.insert(tab.end(), v.count.begin(), v.count.end());
+  tab.insert(tab.end(), v.coef.begin(), v.coef.end());
+  cudaFree(ctx->rz_tab);
+  ctx->rz_tab = nullptr;
+  CK(cudaMalloc(&ctx->rz_tab, tab.size() * sizeof(int)));
+  CK(cudaMemcpy(ctx->rz_tab, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice));
+  ctx->rz_sh = sh; ctx->rz_sw = sw; ctx->rz_hks = h.ksize; ctx->rz_vks = v.ksize;
+  ctx->rz_pitch = (ow + 15) & ~15;
+  // rows per CTA: as many as keep the filtered rows of a 3-channel band within 96 KB of shared memory (two CTAs per SM)
+  for (int band = 8; band >= 1; band >>= 1) {
+    int rows = 0;
+    for (int y0 = 0; y0 < oh; y0 += band) {
+      const int y1 = std::min(y0 + band, oh) - 1;
+      rows = std::max(rows, v.first[y1] + v.count[y1] - v.first[y0]);
+    }
+    ctx->rz_band = band;
+    ctx->rz_max_rows = rows;
+    if ((size_t)3 * rows * ctx->rz_pitch <= (size_t)96 * 1024) break;
+  }
+  if ((size_t)C * ctx->rz_max_rows * ctx->rz_pitch > ctx->smem_optin)
+    return fail(ctx, SPEF_ERR_UNSUPPORTED, "spef_resize_frames: a %d-row filter window of %d-pixel rows does not fit in shared memory", ctx->rz_max_rows, ow);
+  return SPEF_OK;
+}
+
+template <int KREG, int C>
+static cudaError_t launch_resize(const ingest::ResizeParams& p, int B, size_t smem, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(ingest::resize_aa_kernel<KREG, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const int threads = std::min(384, (p.ow + 31) & ~31);
+  ingest::resize_aa_kernel<KREG, C><<<dim3((p.oh + p.band - 1) / p.band, B), threads, smem, st>>>(p);
+  return cudaGetLastError();
+}
+
+extern "C" int spef_resize_frames(spef_ctx* ctx, const uint8_t* frames_dev, int32_t B, int32_t src_h, int32_t src_w, int32_t channels,
+                                  void* images_out_dev, int32_t out_dtype, void* stream) {
+  if (!ctx) return SPEF_ERR_INVALID;
+  if (!frames_dev || !images_out_dev || B < 1 || B > 65535 || src_h < 1 || src_w < 1)
+    return fail(ctx, SPEF_ERR_INVALID, "spef_resize_frames: bad argument");
+  if (channels != 1 && channels != 3) return fail(ctx, SPEF_ERR_INVALID, "spef_resize_frames: frames must have 1 (grey) or 3 (RGB) channels, got %d", channels);
+  if (out_dtype != SPEF_IMG_F32 && out_dtype != SPEF_IMG_U8) return fail(ctx, SPEF_ERR_INVALID, "spef_resize_frames: unknown output dtype %d", out_dtype);
+  CK(cudaSetDevice(ctx->cfg.device));
+  int rc = resize_plan(ctx, src_h, src_w, channels);
+  if (rc) return rc;
+  const int oh = ctx->cfg.img_h, ow = ctx->cfg.img_w;
+  ingest::ResizeParams p;
+  p.src = frames_dev; p.dst = images_out_dev;
+  p.hfirst = ctx->rz_tab; p.hcount = p.hfirst + ow; p.hcoef = p.hcount + ow;
+  p.vfirst = p.hcoef + (size_t)ctx->rz_hks * ow; p.vcount = p.vfirst + oh; p.vcoef = p.vcount + oh;
+  p.sh = src_h; p.sw = src_w; p.C = channels; p.oh = oh; p.ow = ow; p.hks = ctx->rz_hks; p.vks = ctx->rz_vks;
+  p.band = ctx->rz_band; p.max_rows = ctx->rz_max_rows; p.pitch = ctx->rz_pitch; p.out_f32 = (out_dtype == SPEF_IMG_F32);
+  const size_t smem = (size_t)channels * p.max_rows * p.pitch;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e;
+  if (p.hks <= 12) e = (channels == 1) ? launch_resize<12, 1>(p, B, smem, st) : launch_resize<12, 3>(p, B, smem, st);
+  else e = (channels == 1) ? launch_resize<0, 1>(p, B, smem, st) : launch_resize<0, 3>(p, B, smem, st);
+  if (e != cudaSuccess) return fail(ctx, SPEF_ERR_CUDA, "launch of resize_aa_kernel failed: %s", cudaGetErrorString(e));
+  ctx->launches++;
+  return SPEF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
 // post-processing
 // ------------------------------------------------------------------------------------------------------
 static int decode_ori_ld(spef_ctx* ctx, const float* in, int ld, int B, int n, int is_logits, float* soft, float* quat, float* hinv,
@@ -1270,6 +1358,19 @@ static int decode_ori_ld(spef_ctx* ctx, const float* in, int ld, int B, int n, i
   if (!in || !quat || B < 1) return fail(ctx, SPEF_ERR_INVALID, "decode_ori: bad argument");
   // images per warp: 32 (eigen-solves fully lane-parallel) once there are enough images to fill the GPU that way
   const long long fill = (long long)ctx->num_sms * 16;  // warps needed for ~16 warps per SM
+  // large batches: the streaming kernel (persistent CTAs of 8 warps, SoA table in shared memory, packed FP32 pairs)
+  const bool vec_ok = (n % 4 == 0) && (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(in) & 15) == 0) &&
+                      (!soft || (reinterpret_cast<uintptr_t>(soft) & 15) == 0);
+  if (vec_ok && ((ctx->decode_stream == 1 && (long long)B >= 8 * fill) || ctx->decode_stream == 2)) {
+    constexpr int NW = 8;
+    const size_t smem = (size_t)4 * dstream::TC * sizeof(float) + (size_t)NW * 32 * 11 * sizeof(double);
+    const int grid = std::min(cdiv(B, NW), 2 * ctx->num_sms);
+    auto kern = amax ? dstream::decode_ori_stream_kernel<NW, true> : dstream::decode_ori_stream_kernel<NW, false>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, NW * 32, smem, st>>>(in, ld, B, n, is_logits, ctx->ori_tab_soa, ctx->ori_tab_ld, soft, quat, hinv, amax, flags);
+    CK_LAUNCH("decode_ori_stream_kernel");
+    return SPEF_OK;
+  }
   if ((long long)B >= 32 * fill) decode_ori_kernel<32><<<cdiv(cdiv(B, 32), 4), 128, 0, st>>>(in, ld, B, n, is_logits, ctx->ori_tab, soft, quat, hinv, amax, flags);
   else if ((long long)B >= 8 * fill) decode_ori_kernel<8><<<cdiv(cdiv(B, 8), 4), 128, 0, st>>>(in, ld, B, n, is_logits, ctx->ori_tab, soft, quat, hinv, amax, flags);
   else decode_ori_kernel<1><<<cdiv(B, 4), 128, 0, st>>>(in, ld, B, n, is_logits, ctx->ori_tab, soft, quat, hinv, amax, flags);
@@ -1735,6 +1836,17 @@ extern "C" int spef_forward_cost(const spef_ctx* ctx, int32_t B, double* bytes_o
   }
   if (bytes_out) *bytes_out = bytes * B;
   if (flops_out) *flops_out = flops * B;
+  return SPEF_OK;
+}
+
+// debug: the eigen-solve of the streaming decode kernel (f32 Jacobi + f64 polish, cofactor inverse) compiled for the host
+extern "C" int spef_debug_decode_solve_host(const double* sums /*[11]*/, int32_t is_logits, float* quat /*[4]*/, float* hinv /*[16] or NULL*/) {
+  if (!sums || !quat) return SPEF_ERR_INVALID;
+  double tot[11];
+  for (int k = 0; k < 11; ++k) tot[k] = sums[k];
+  float q[4];
+  if (!dstream::solve_core(tot, is_logits != 0, q, hinv)) return SPEF_ERR_INVALID;
+  for (int k = 0; k < 4; ++k) quat[k] = q[k];
   return SPEF_OK;
 }
 

@@ -120,6 +120,24 @@ class Engine:
             raise ValueError(f"batch {images.shape[0]} exceeds the engine's max_batch {self.max_batch}")
         return images.shape[0]
 
+    # ---- camera frames -> image tensor (input side of the path) ----------------------------------
+    def resize_frames(self, frames: torch.Tensor, out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+        """SPEDataset's transform on a batch of decoded frames: Image.convert("RGB") -> Resize((img_h, img_w)) -> ToTensor
+        (src/data/utils.py:215-226, src/data/datasets/speed.py:59-62), bit-exact against torchvision + Pillow.
+        frames: uint8 [B,H,W] (grey) or [B,H,W,3] (RGB, HWC); returns [B,3,img_h,img_w] on this device, uint8 (the pixels
+        ToTensor divides by 255; feed to an engine set to uint8 images) or float32 (the reference tensor).  Default:
+        the engine's image dtype."""
+        if frames.dtype != torch.uint8 or frames.dim() not in (3, 4) or (frames.dim() == 4 and frames.shape[3] != 3):
+            raise ValueError(f"frames must be uint8 [B,H,W] or [B,H,W,3], got {frames.dtype} {tuple(frames.shape)}")
+        out_dtype = out_dtype or self.image_dtype
+        assert out_dtype in (torch.float32, torch.uint8)
+        f = frames.to(self.device, non_blocking=True).contiguous()
+        B, H, W = f.shape[0], f.shape[1], f.shape[2]
+        out = self._empty(B, 3, self.img_h, self.img_w, dtype=out_dtype)
+        self._ck(self.lib.spef_resize_frames(self._h, ptr(f), B, H, W, 1 if f.dim() == 3 else 3, ptr(out),
+                                             1 if out_dtype == torch.uint8 else 0, _stream(self.device)))
+        return out
+
     # ---- network ---------------------------------------------------------------------------------
     def forward(self, images: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         """ModelWrapper.forward: images [B,3,H,W] f32 on this device -> (ori logits [B,n_ori], pos [B,n_pos])."""

@@ -114,3 +114,30 @@ class SyntheticLoader:
 
     def __len__(self):
         return len(self.batches)
+
+
+def synthetic_frames(batch: int, height: int = 1200, width: int = 1920, channels: int = 1, seed: int = 4242,
+                     kind: str = "speed") -> np.ndarray:
+    """uint8 camera frames [B,H,W] (channels = 1, SPEED's greyscale JPEGs) or [B,H,W,3], the input of
+    SPEDataset.__getitem__ before Resize -> ToTensor (src/data/utils.py:212-226; Camera 1920 x 1200,
+    src/data/datasets/speed.py:23-24).  kind 'speed': dark sky, sensor noise and one bright textured blob per frame;
+    'noise': uniform white noise (worst case for the resampling filter)."""
+    rng = np.random.default_rng(seed)
+    shape = (batch, height, width) if channels == 1 else (batch, height, width, channels)
+    if kind == "noise":
+        return rng.integers(0, 256, size=shape, dtype=np.uint8)
+    yy, xx = np.mgrid[0:height, 0:width].astype(np.float32)
+    out = np.empty(shape, np.uint8)
+    for b in range(batch):
+        cy, cx = rng.uniform(0.2, 0.8) * height, rng.uniform(0.2, 0.8) * width
+        s = rng.uniform(0.03, 0.15) * min(height, width)
+        blob = 230.0 * np.exp(-(((yy - cy) / s) ** 2 + ((xx - cx) / (1.4 * s)) ** 2))
+        tex = 0.75 + 0.25 * np.sin(xx * 0.9 + b) * np.cos(yy * 0.7)
+        for c in range(channels):
+            f = blob * tex * (1.0 - 0.1 * c) + rng.normal(6.0, 3.0, size=(height, width))
+            plane = np.clip(np.rint(f), 0, 255).astype(np.uint8)
+            if channels == 1:
+                out[b] = plane
+            else:
+                out[b, :, :, c] = plane
+    return out

@@ -274,6 +274,44 @@ def golden_temporal(ref):
     print("temporal distances:", np.array(rec["ori_distance"]).round(4))
 
 
+def golden_resize(ref):
+    """Input side: the reference's own transform, transforms.Compose([Resize(img_size), ToTensor()])
+    (src/data/datasets/speed.py:59-62) applied to Image.fromarray(frame).convert("RGB") as SPEDataset.__getitem__ does
+    (src/data/utils.py:215-226).  Frames are regenerated from seeds by the tests; the stored values are the 8-bit pixels
+    behind ToTensor's output (checked here to be exactly out * 255) plus two float32 samples of the tensor itself."""
+    from PIL import Image
+    from torchvision import transforms
+    cases = [  # name, frames kwargs, img_size
+        ("speed_1200x1920", dict(batch=2, height=1200, width=1920, channels=1, seed=11, kind="speed"), (240, 384)),
+        ("noise_1200x1920", dict(batch=1, height=1200, width=1920, channels=1, seed=12, kind="noise"), (240, 384)),
+        ("noise_1200x1920_sq", dict(batch=1, height=1200, width=1920, channels=1, seed=13, kind="noise"), (240, 240)),
+        ("rgb_480x640", dict(batch=1, height=480, width=640, channels=3, seed=14, kind="noise"), (240, 384)),
+        ("up_123x257", dict(batch=1, height=123, width=257, channels=1, seed=15, kind="noise"), (240, 384)),
+        ("odd_601x997_rgb", dict(batch=1, height=601, width=997, channels=3, seed=16, kind="speed"), (240, 384)),
+        ("same_240x384", dict(batch=1, height=240, width=384, channels=1, seed=17, kind="noise"), (240, 384)),
+    ]
+    out = {"cases": json.dumps([[n, k, list(s)] for n, k, s in cases])}
+    for name, kw, size in cases:
+        frames = synthetic.synthetic_frames(**kw)
+        tf = transforms.Compose([transforms.Resize(size), transforms.ToTensor()])
+        res = []
+        for fr in frames:
+            t = tf(Image.fromarray(fr).convert("RGB"))
+            u8 = torch.round(t * 255).to(torch.uint8)
+            assert torch.equal(u8.float() / 255, t)
+            res.append(u8.numpy())
+        res = np.stack(res)
+        if kw["channels"] == 1:
+            assert (res[:, 0] == res[:, 1]).all() and (res[:, 0] == res[:, 2]).all()
+            res = res[:, :1]
+        out[name] = res
+        print(name, res.shape, res.mean())
+    t = transforms.Compose([transforms.Resize((240, 384)), transforms.ToTensor()])(
+        Image.fromarray(synthetic.synthetic_frames(**cases[0][1])[0]).convert("RGB"))
+    out["speed_1200x1920_f32_row100"] = t[:, 100, :].numpy()
+    np.savez_compressed(os.path.join(OUT, "resize.npz"), **out)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--calibrate", action="store_true")
@@ -285,7 +323,7 @@ def main():
         calibrate(ref)
         return
     steps = {"histograms": golden_histograms, "encode_decode": golden_encode_decode, "decode_logits": golden_decode_logits,
-             "score": golden_score, "network": golden_network, "evaluation": golden_evaluation, "temporal": golden_temporal}
+             "score": golden_score, "network": golden_network, "evaluation": golden_evaluation, "temporal": golden_temporal, "resize": golden_resize}
     for name, fn in steps.items():
         if args.only and name != args.only:
             continue

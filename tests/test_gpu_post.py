@@ -286,3 +286,98 @@ def test_evaluation_device_stats_matches_host():
         np.testing.assert_allclose(e_dev["valid"][k], e_host["valid"][k], rtol=2e-5)
     for k in ("ori_mad", "pos_mad"):
         np.testing.assert_allclose(e_dev["valid"][k], e_host["valid"][k], rtol=1e-6)
+
+
+# ---- the large-batch (streaming) decode kernel: csrc/decode_stream.cuh ---------------------------------
+@pytest.fixture(scope="module")
+def stream_post():
+    """An engine whose spef_decode_ori always takes decode_ori_stream_kernel (SPEF_DECODE_STREAM=2), next to the default
+    one (`post`), which takes it from 18 944 images up."""
+    import os
+    from spef_b200.engine import Engine
+    os.environ["SPEF_DECODE_STREAM"] = "2"
+    try:
+        e = Engine(32, 32, 8, 3, False, "fp32", 1)
+    finally:
+        del os.environ["SPEF_DECODE_STREAM"]
+    return e
+
+
+@pytest.mark.parametrize("n_dim", [8, 12, 16, 24])
+def test_stream_decode_vs_oracle(stream_post, n_dim):
+    """Same gates as the per-image kernel: <= 0.05 deg on identical logits / pdfs, argmax bit-exact, inv(A) 1e-3.
+    n_dim 16 and 24 take the chunked-table path (n > 2048 bins), 12 and 24 have a ragged last 1024-bin step."""
+    hist, _ = O.ori_histogram(n_dim)
+    stream_post.set_ori_histogram(hist)
+    n = hist.shape[0]
+    rs = np.random.RandomState(77 + n_dim)
+    B = 70   # 9 groups of 8 warps: two passes over the grid loop for a 4-CTA grid is not reachable here; ragged last group is
+    for sigma in (1.0, 3.0, 10.0):
+        logits = (rs.randn(B, n) * sigma).astype(np.float32)
+        out = stream_post.decode_ori(torch.from_numpy(logits), is_logits=True, want_soft=True, want_hinv=True, want_argmax=True)
+        soft = O.softmax(logits)
+        want_q, want_h = O.ori_decode_batch(soft, hist)
+        assert not out["flags"].cpu().numpy().any()
+        assert O.quat_angle_deg(out["quat"].cpu().numpy(), want_q).max() <= QUAT_TOL_DEG
+        np.testing.assert_array_equal(out["argmax"].cpu().numpy(), logits.argmax(1))
+        np.testing.assert_allclose(out["soft"].cpu().numpy(), soft, rtol=5e-6, atol=1e-30)
+        hv = out["hinv"].cpu().numpy()
+        assert np.abs(hv - want_h).max() <= 1e-3 * np.abs(want_h).max()
+        # pdf input (the temporal path decodes filtered pdfs)
+        out2 = stream_post.decode_ori(torch.from_numpy(soft), is_logits=False, want_argmax=True)
+        assert O.quat_angle_deg(out2["quat"].cpu().numpy(), want_q).max() <= QUAT_TOL_DEG
+        np.testing.assert_array_equal(out2["argmax"].cpu().numpy(), soft.argmax(1))
+
+
+def test_stream_decode_edge_cases(stream_post, golden):
+    hist, _ = O.ori_histogram(12)
+    stream_post.set_ori_histogram(hist)
+    n = hist.shape[0]
+    # ties: first maximum wins (np.argmax); a maximum in the last bin; constant rows
+    z = np.zeros((9, n), np.float32)
+    z[0, [5, 900, 1700]] = 4.0
+    z[1, n - 1] = 2.0
+    z[2, 1024] = 1.0            # first bin of the second 1024-bin step
+    z[3, [1023, 1024]] = 3.0
+    z[4] = -50.0
+    z[5, 17] = 80.0             # one-hot after softmax
+    z[6] = np.linspace(-20, 20, n)
+    z[7, 1] = np.nan            # -> flagged like the reference's ValueError
+    out = stream_post.decode_ori(torch.from_numpy(z), is_logits=True, want_argmax=True)
+    am = out["argmax"].cpu().numpy()
+    np.testing.assert_array_equal(am[:7], z[:7].argmax(1))
+    fl = out["flags"].cpu().numpy()
+    assert fl[7] == 1 and not fl[:7].any() and not fl[8]
+    q = out["quat"].cpu().numpy()
+    assert np.isnan(q[7]).all()
+    want_q, _ = O.ori_decode_batch(O.softmax(z[[0, 1, 2, 3, 5, 6]]), hist)
+    assert O.quat_angle_deg(q[[0, 1, 2, 3, 5, 6]], want_q).max() <= QUAT_TOL_DEG
+    # encoded SPEED labels from the reference
+    g = golden("encode_decode")
+    out = stream_post.decode_ori(torch.from_numpy(g["enc_ori"]), is_logits=False, want_hinv=True)
+    assert O.quat_angle_deg(out["quat"].cpu().numpy(), g["dec_ori"]).max() <= QUAT_TOL_DEG
+
+
+def test_stream_decode_full_size_matches_per_image_kernel(post, stream_post):
+    """BASELINE configs[3] size (1728 bins, 77 672 images: every CTA loops, 32-image solve batches plus a remainder):
+    the default engine dispatches to the streaming kernel by itself; results against the per-image kernel on the same
+    device buffer, plus slot independence and determinism."""
+    hist, _ = O.ori_histogram(12)
+    post.set_ori_histogram(hist)
+    stream_post.set_ori_histogram(hist)
+    g = torch.Generator().manual_seed(5)
+    B = 77672
+    logits = (torch.randn((B, 1728), generator=g) * 3).cuda()
+    a = post.decode_ori(logits, is_logits=True, want_argmax=True)            # >= 18 944 images: streaming kernel
+    b = post.decode_ori(logits, is_logits=True, want_argmax=True)
+    assert torch.equal(a["quat"], b["quat"])
+    assert torch.equal(a["argmax"].long(), logits.argmax(1))
+    assert not a["flags"].any()
+    qa = a["quat"].cpu().numpy()
+    ref = np.concatenate([post.decode_ori(logits[i:i + 4096], is_logits=True)["quat"].cpu().numpy() for i in range(0, B, 4096)])  # per-image kernel
+    assert O.quat_angle_deg(qa, ref).max() <= 1e-2
+    sub = stream_post.decode_ori(logits[1000:1100], is_logits=True)["quat"].cpu().numpy()
+    assert O.quat_angle_deg(sub, qa[1000:1100]).max() <= 1e-4
+    idx = np.arange(0, B, 607)[:128]
+    want_q, _ = O.ori_decode_batch(O.softmax(logits[idx].cpu().numpy()), hist)
+    assert O.quat_angle_deg(qa[idx], want_q).max() <= QUAT_TOL_DEG

@@ -92,6 +92,39 @@ def test_device_jacobi_solver_matches_lapack():
         np.testing.assert_allclose(evec @ np.diag(ev) @ evec.T, a, atol=1e-14)
 
 
+def test_stream_decode_solver_matches_lapack(golden):
+    """The eigen-solve of the large-batch decode kernel (f32 Jacobi + one f64 polish step, cofactor inverse), compiled for
+    the host, against np.linalg.eig / np.linalg.inv as classification_utils.py:137-142 uses them; gate 0.05 deg."""
+    lib = _ffi.lib()
+    rs = np.random.RandomState(1)
+    hist, _ = O.ori_histogram(12)
+    g = golden("encode_decode")
+    cases = []
+    for sigma in (1e-9, 0.1, 1.0, 3.0, 10.0, 30.0):
+        z = (rs.randn(6, 1728) * sigma).astype(np.float32)
+        w = np.exp(z.astype(np.float64) - z.max(1, keepdims=True))    # unnormalised weights, S != 1
+        cases += [(wi, True) for wi in w]
+    cases += [(p.astype(np.float64), False) for p in g["enc_ori"][:16]]  # encoded SPEED labels: sharp pdfs
+    worst = 0.0
+    for w, is_logits in cases:
+        a = np.einsum("b,bi,bj->ij", w, hist, hist)
+        sums = np.array([w.sum(), a[0, 0], a[0, 1], a[0, 2], a[0, 3], a[1, 1], a[1, 2], a[1, 3], a[2, 2], a[2, 3], a[3, 3]])
+        q, hinv = np.zeros(4, np.float32), np.zeros(16, np.float32)
+        assert lib.spef_debug_decode_solve_host(sums.ctypes.data, int(is_logits), q.ctypes.data, hinv.ctypes.data) == 0
+        an = a / w.sum() if is_logits else a
+        ev, evec = np.linalg.eigh(an)
+        gap = (ev[-1] - ev[-2]) / ev[-1]
+        ang = float(O.quat_angle_deg(q, evec[:, -1]))
+        if gap > 1e-6:   # the dominant direction is defined
+            worst = max(worst, ang)
+            assert ang < 1e-3, (ang, gap)
+        assert abs(np.linalg.norm(q) - 1) < 1e-6 and q[0] >= 0
+        want = np.linalg.inv(an)
+        assert np.abs(hinv.reshape(4, 4) - want).max() <= 1e-5 * np.abs(want).max()
+    bad = np.full(11, np.nan)
+    assert lib.spef_debug_decode_solve_host(bad.ctypes.data, 1, q.ctypes.data, None) != 0
+
+
 def test_arch_and_state_dict_spec(golden):
     spec = arch.state_dict_spec(1728, 3)
     assert len(spec) == 316 and len(arch.conv_layers()) == 52
