@@ -53,7 +53,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--layers", action="store_true", help="also print the per-layer table to stderr")
-    ap.add_argument("--workload", default="forward", choices=["forward", "decode", "temporal"],
+    ap.add_argument("--workload", default="forward", choices=["forward", "decode", "temporal", "ingest"],
                     help="forward: BASELINE configs[1]/[2] (default, the driver's line); decode: configs[3] bins-per-axis sweep of the "
                          "decode kernel alone; temporal: configs[4] D-SPEED-shaped stream, batch-1 latency and 64-stream throughput")
     return ap.parse_args()
@@ -450,7 +450,13 @@ def run_decode_sweep(args):
         hist = OrientationSoftClassification(n_dim, 3, False).histogram
         n = hist.shape[0]
         eng.set_ori_histogram(hist)
-        B = int(max(4096, min(262144, (1 << 29) // (4 * n))))     # >= 512 MB of logits: larger than L2
+        # ~512 MB of logits (larger than L2), in whole multiples of the persistent grid's warps (148 CTAs x 16 warps, one image
+        # per warp and pass) and, from 32 passes up, of the 32-image eigen-solve batches
+        wave = 16 * torch.cuda.get_device_properties(dev).multi_processor_count
+        passes = max(1, round((1 << 29) / (4 * n) / wave))
+        if passes >= 32:
+            passes -= passes % 32
+        B = int(passes * wave)
         logits = torch.randn((B, n), device=dev) * 3
         # pre-allocated outputs and the bare C-ABI call in the timed loop: the Python wrapper's allocations would make the
         # GPU wait for the host at these kernel durations
@@ -546,6 +552,99 @@ def run_temporal(args):
     emit(out)
 
 
+def run_ingest(args):
+    """Input side of the path: decoded 1200 x 1920 greyscale camera frames -> Resize((240, 384)) -> ToTensor
+    (spef_resize_frames, bit-exact against torchvision + Pillow) -> forward + decode + score.  Reports the resize kernel alone
+    (device-resident frames, against the HBM roof), the frames -> score step on the device, the same step end to end from
+    pinned host frames, and the reference's CPU transform (PIL resize + ToTensor restated in the oracle) on one host core."""
+    from spef_b200.engine import Engine
+    from spef_b200.tools import synthetic
+    from spef_b200.spe.classification_utils import OrientationSoftClassification
+    dev = torch.device("cuda", 0)
+    B, SH, SW = args.batch, 1200, 1920
+    eng = Engine(IMG[0], IMG[1], N_ORI, 3, False, "bf16", B, dev)
+    eng.load_state_dict(synthetic.synthetic_state_dict(N_ORI, 3))
+    eng.set_ori_histogram(OrientationSoftClassification(12, 3, False).histogram)
+    eng.set_image_dtype(torch.uint8)
+    base = torch.from_numpy(synthetic.synthetic_frames(8, SH, SW, 1, seed=21, kind="speed"))
+    host = base.repeat((B + 7) // 8, 1, 1)[:B].contiguous().pin_memory()          # 590 MB at B = 256
+    frames = host.to(dev)
+    tg = synthetic.synthetic_targets(B, 2024)
+    qt, tt = torch.from_numpy(tg["ori"]).to(dev), torch.from_numpy(tg["pos"]).to(dev)
+    pk = peaks()
+
+    def timed(fn, steps):
+        for _ in range(max(3, args.warmup)):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+
+    out_u8 = torch.empty((B, 3, IMG[0], IMG[1]), dtype=torch.uint8, device=dev)
+    from spef_b200._ffi import ptr
+    st = torch.cuda.current_stream(dev).cuda_stream or None
+
+    def resize_only():
+        assert eng.lib.spef_resize_frames(eng._h, ptr(frames), B, SH, SW, 1, ptr(out_u8), 1, st) == 0
+
+    ms_rz = timed(resize_only, args.steps)
+    alg = B * (SH * SW + 3 * IMG[0] * IMG[1])
+    eng.eval_reset()
+
+    def frames_to_score():
+        resize_only()
+        eng.eval_batch(out_u8, qt, tt)
+
+    ms_dev = timed(frames_to_score, args.steps)
+
+    def e2e_step():
+        frames.copy_(host, non_blocking=True)
+        frames_to_score()
+
+    for _ in range(2):
+        e2e_step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    sums = eng.eval_read()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    # CPU: the reference's transform (PIL antialiased bilinear + ToTensor) on one core, a bounded sample
+    cpu = None
+    if not args.no_cpu_baseline:
+        try:
+            from PIL import Image
+            from torchvision import transforms
+            tf = transforms.Compose([transforms.Resize(IMG), transforms.ToTensor()])
+            fr = [Image.fromarray(f).convert("RGB") for f in base.numpy()]
+            t0 = time.perf_counter()
+            n = 0
+            while time.perf_counter() - t0 < min(args.cpu_seconds, 5.0):
+                tf(fr[n % len(fr)])
+                n += 1
+            cpu = {"value": n / (time.perf_counter() - t0), "unit": "frames/s", "cores": 1, "kind": "reference",
+                   "sample": f"{n} frames through torchvision Resize((240, 384)) + ToTensor on PIL RGB images (the reference's SPEDataset transform; JPEG decode excluded)"}
+        except Exception as ex:  # torchvision / Pillow missing on the box
+            cpu = {"unavailable": repr(ex)}
+    emit({"metric": "images/sec (camera frames -> resize -> forward + decode + score)", "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+          "warmup": max(3, args.warmup), "dtype": "u8 resize (22-bit fixed point) + bf16 network", "data": "synthetic", "higher_is_better": True,
+          "value": B / (ms_dev * 1e-3), "ms_per_step": ms_dev,
+          "config": {"workload": f"1200x1920 greyscale uint8 frames, batch {B}: spef_resize_frames -> uint8 [B,3,240,384] -> spef_eval_batch",
+                     "l2": "inputs larger than L2 (590 MB of frames per step)"},
+          "e2e": {"value": B * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(host.numel()), "d2h_bytes_per_step": 64,
+                  "api": "pinned host frames -> H2D -> spef_resize_frames -> spef_eval_batch, sums read back at the end"},
+          "roofline": {"kernel": "resize_aa_kernel", "bound": "hbm", "achieved": alg / (ms_rz * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                       "frac": alg / (ms_rz * 1e-3) / 1e9 / pk["hbm_gbs"], "traffic": None, "algorithmic_bytes_per_launch": alg,
+                       "avg_launch_ms": ms_rz, "peak_source": pk["source"], "frames_per_s": B / (ms_rz * 1e-3)},
+          "cpu_baseline": cpu, "esa": {"images": float(sums[3]), "esa_score": float((sums[0] + sums[1]) / max(sums[3], 1.0))}})
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
@@ -554,6 +653,8 @@ def main():
         run_decode_sweep(args)
     elif args.workload == "temporal":
         run_temporal(args)
+    elif args.workload == "ingest":
+        run_ingest(args)
     else:
         run_b200(args)
 

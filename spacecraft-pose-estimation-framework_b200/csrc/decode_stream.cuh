@@ -18,6 +18,7 @@
 #pragma once
 #include "common.cuh"
 #include "kernels_post.cuh"
+#include "gemm_tcgen05.cuh"  // mbarrier PTX wrappers
 
 namespace spef {
 namespace dstream {
@@ -267,18 +268,38 @@ __device__ __forceinline__ void solve_and_store(const double (&tot)[11], bool is
   reinterpret_cast<float4*>(quat_out)[img] = make_float4(q[0], q[1], q[2], q[3]);
 }
 
+// The logits of a warp's images arrive through a per-warp ring of RING 4 KB slots filled by 1-D bulk async copies
+// (cp.async.bulk + mbarrier complete_tx, issued by lane 0, RING - 1 steps ahead): the bytes in flight per SM do not depend
+// on how many registers a thread can spare, and the loads of the next image overlap the reduction and the eigen-solve.
+struct Cursor {   // position in a warp's sequence of 1024-bin steps: (group iteration, table chunk, step)
+  int g, c0, s0;
+};
+
+__device__ __forceinline__ void bulk_load_1d(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+inline size_t smem_bytes(int nw, int ring) {
+  return (size_t)4 * TC * sizeof(float) + (size_t)nw * ring * SUB * sizeof(float) + (size_t)nw * 32 * 11 * sizeof(double) + (size_t)nw * ring * 8;
+}
+
 // in: [B][ld] f32 rows, 16-byte aligned, n and ld multiples of 4.  tab: [4][tab_ld] f32 SoA (plane c = component c of the
 // scalar-first bins), tab_ld a multiple of SUB, zero padded.  Grid: persistent CTAs of NW warps; warp w of CTA c takes images
-// (c + i * gridDim.x) * NW + w, i = 0, 1, ...; dynamic shared memory: 4 * TC floats + NW * 32 * 11 doubles.
-template <int NW, bool AMAX>
-__global__ void __launch_bounds__(NW * 32, 2) decode_ori_stream_kernel(const float* __restrict__ in, int ld, int B, int n, int is_logits,
+// (c + i * gridDim.x) * NW + w, i = 0, 1, ...  PRECISE (used when inv(A) is requested: it amplifies errors of A by the
+// condition number, 1e8 for sharp pdfs): f32 partial sums are flushed into the f64 sums every 4 bins instead of every 32.
+template <int NW, int RING, int PF, bool AMAX, bool PRECISE, bool LOGITS>
+__global__ void __launch_bounds__(NW * 32, 1) decode_ori_stream_kernel(const float* __restrict__ in, int ld, int B, int n,
                                                                        const float* __restrict__ tab, int tab_ld,
                                                                        float* __restrict__ soft_out, float* __restrict__ quat_out,
                                                                        float* __restrict__ hinv_out, int* __restrict__ argmax_out,
                                                                        uint32_t* __restrict__ flags) {
-  extern __shared__ __align__(16) unsigned char dsm[];
-  float* stab = reinterpret_cast<float*>(dsm);                           // [4][TC]
-  double* stash = reinterpret_cast<double*>(dsm + 4 * TC * sizeof(float));  // [NW][32][11]
+  extern __shared__ __align__(128) unsigned char dsm[];
+  float* stab = reinterpret_cast<float*>(dsm);                                            // [4][TC]
+  float* ring = stab + 4 * TC;                                                            // [NW][RING][SUB]
+  double* stash = reinterpret_cast<double*>(ring + (size_t)NW * RING * SUB);              // [NW][32][11]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stash + (size_t)NW * 32 * 11);             // [NW][RING]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int groups = cdiv(B, NW);
   const bool whole = tab_ld <= TC;
@@ -288,6 +309,53 @@ __global__ void __launch_bounds__(NW * 32, 2) decode_ori_stream_kernel(const flo
       reinterpret_cast<float4*>(stab + c * TC)[o] = __ldg(reinterpret_cast<const float4*>(tab + (size_t)c * tab_ld + c0) + o);
     }
   };
+  const float* my_ring = ring + (size_t)warp * RING * SUB;
+  const uint32_t ring_u = tc::smem_u32(my_ring), bar_u = tc::smem_u32(bars + warp * RING);
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < RING; ++s) tc::mbar_init(bar_u + 8u * s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  // producer cursor: lane 0 copies the step at `pc` into a ring slot; the L2 cursor `lc` runs PF steps further ahead and only
+  // prefetches into L2 (cp.async.bulk.prefetch.L2), so that the ring -- whose depth is bounded by shared memory -- is filled
+  // from L2 instead of waiting for HBM
+  Cursor pc{(int)blockIdx.x, 0, 0}, lc{(int)blockIdx.x, 0, 0};
+  auto step_bytes = [&](const Cursor& c) { return (uint32_t)(min(SUB, min(TC, n - c.c0) - c.s0) * 4); };
+  auto step_ptr = [&](const Cursor& c) { return in + ((size_t)c.g * NW + warp) * ld + c.c0 + c.s0; };
+  auto ended = [&](const Cursor& c) { return c.g >= groups || (long long)c.g * NW + warp >= B; };
+  auto advance = [&](Cursor& c) {
+    c.s0 += SUB;
+    if (c.s0 >= min(TC, n - c.c0)) {
+      c.s0 = 0;
+      c.c0 += TC;
+      if (c.c0 >= n) { c.c0 = 0; c.g += gridDim.x; }
+    }
+  };
+  auto prefetch_l2 = [&]() {
+    if (PF == 0 || ended(lc)) return;
+    if (lane == 0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(step_ptr(lc)), "r"(step_bytes(lc)) : "memory");
+    advance(lc);
+  };
+  auto produce = [&](int slot) {
+    prefetch_l2();
+    if (ended(pc)) return;   // this warp's sequence has ended
+    if (lane == 0) {
+      const uint32_t bytes = step_bytes(pc);
+      tc::mbar_arrive_expect_tx(bar_u + 8u * slot, bytes);
+      bulk_load_1d(ring_u + (uint32_t)slot * (SUB * 4), step_ptr(pc), bytes, bar_u + 8u * slot);
+    }
+    advance(pc);
+  };
+#pragma unroll 1
+  for (int s = 0; s < PF; ++s) {   // lc starts PF steps ahead of pc (the first ring fills come straight from HBM)
+    if (!ended(lc)) advance(lc);
+  }
+#pragma unroll
+  for (int s = 0; s < RING - 1; ++s) produce(s);
+  int slot = 0, fill_slot = RING - 1;
+  uint32_t phases = 0;   // bit s = parity to wait for on slot s
+
   if (whole) {
     stage_table(0, tab_ld);
     __syncthreads();
@@ -301,18 +369,17 @@ __global__ void __launch_bounds__(NW * 32, 2) decode_ori_stream_kernel(const flo
         double tot[11];
 #pragma unroll
         for (int k = 0; k < 11; ++k) tot[k] = my_stash[lane * 11 + k];
-        solve_and_store(tot, is_logits != 0, img, quat_out, hinv_out, flags);
+        solve_and_store(tot, LOGITS, img, quat_out, hinv_out, flags);
       }
     }
     __syncwarp();
   };
 
-  const float pad = is_logits ? -INFINITY : 0.f;
+  const float pad = LOGITS ? -INFINITY : 0.f;
   int it = 0;
   for (int g = blockIdx.x; g < groups; g += gridDim.x, ++it) {
     const int img = g * NW + warp;
     const bool active = img < B;  // warp-uniform
-    const float4* row4 = reinterpret_cast<const float4*>(in + (size_t)(active ? img : 0) * ld);
     float M = -INFINITY;
     int AM = 0;
     double acc[16];
@@ -327,13 +394,21 @@ __global__ void __launch_bounds__(NW * 32, 2) decode_ori_stream_kernel(const flo
       }
       if (!active) continue;
       for (int s0 = 0; s0 < cn; s0 += SUB) {
+        // this step's logits: ring slot -> registers, then the slot is refilled with the step RING - 1 ahead
+        produce(fill_slot);
+        fill_slot = (fill_slot + 1 == RING) ? 0 : fill_slot + 1;
+        tc::mbar_wait(bar_u + 8u * slot, (phases >> slot) & 1u);
+        phases ^= 1u << slot;
         float4 z[8];
+        const float4* zs = reinterpret_cast<const float4*>(my_ring + (size_t)slot * SUB);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int b = s0 + (j * 32 + lane) * 4;
-          z[j] = (b < cn) ? __ldg(row4 + ((c0 + b) >> 2)) : make_float4(pad, pad, pad, pad);
+          z[j] = (b < cn) ? zs[j * 32 + lane] : make_float4(pad, pad, pad, pad);
         }
-        if (is_logits || AMAX) {
+        __syncwarp();
+        slot = (slot + 1 == RING) ? 0 : slot + 1;
+        if (LOGITS || AMAX) {
           float lm = fmaxf(fmaxf(z[0].x, z[0].y), fmaxf(z[0].z, z[0].w));
 #pragma unroll
           for (int j = 1; j < 8; ++j) lm = fmaxf(fmaxf(lm, fmaxf(z[j].x, z[j].y)), fmaxf(z[j].z, z[j].w));
@@ -353,7 +428,7 @@ __global__ void __launch_bounds__(NW * 32, 2) decode_ori_stream_kernel(const flo
               }
               AM = __reduce_min_sync(0xffffffffu, cand);
             }
-            if (is_logits) {
+            if (LOGITS) {
               const double sc = (double)ex2_approx((M - cm) * LOG2E);  // M = -inf the first time -> 0
 #pragma unroll
               for (int k = 0; k < 11; ++k) acc[k] *= sc;
@@ -365,13 +440,16 @@ __global__ void __launch_bounds__(NW * 32, 2) decode_ori_stream_kernel(const flo
         uint64_t P[11];
 #pragma unroll
         for (int k = 0; k < 11; ++k) P[k] = 0ull;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float w0 = z[j].x, w1 = z[j].y, w2 = z[j].z, w3 = z[j].w;
-          if (is_logits) {
+        const uint64_t mb2 = f32x2(mb, mb), l2e2 = f32x2(LOG2E, LOG2E);
+        auto slice = [&](int j) {   // 128 bins: 4 per lane, two per packed instruction
+          uint64_t W01 = f32x2(z[j].x, z[j].y), W23 = f32x2(z[j].z, z[j].w);
+          if (LOGITS) {
             // ex2.approx: ~1e-6 relative on the weights moves the eigenvector by < 1e-3 deg (gate 0.05 deg); ori_soft below uses expf
-            w0 = ex2_approx(fmaf(w0, LOG2E, mb)); w1 = ex2_approx(fmaf(w1, LOG2E, mb));
-            w2 = ex2_approx(fmaf(w2, LOG2E, mb)); w3 = ex2_approx(fmaf(w3, LOG2E, mb));
+            float t0, t1, t2, t3;
+            f32x2_unpack(fma_f32x2(W01, l2e2, mb2), t0, t1);
+            f32x2_unpack(fma_f32x2(W23, l2e2, mb2), t2, t3);
+            W01 = f32x2(ex2_approx(t0), ex2_approx(t1));
+            W23 = f32x2(ex2_approx(t2), ex2_approx(t3));
           }
           const int o = s0 + (j * 32 + lane) * 4;
           const ulonglong2 q0 = *reinterpret_cast<const ulonglong2*>(stab + 0 * TC + o);
@@ -379,8 +457,8 @@ __global__ void __launch_bounds__(NW * 32, 2) decode_ori_stream_kernel(const flo
           const ulonglong2 q2 = *reinterpret_cast<const ulonglong2*>(stab + 2 * TC + o);
           const ulonglong2 q3 = *reinterpret_cast<const ulonglong2*>(stab + 3 * TC + o);
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {  // two bins per packed instruction
-            const uint64_t W = h ? f32x2(w2, w3) : f32x2(w0, w1);
+          for (int h = 0; h < 2; ++h) {
+            const uint64_t W = h ? W23 : W01;
             const uint64_t Q0 = h ? q0.y : q0.x, Q1 = h ? q1.y : q1.x, Q2 = h ? q2.y : q2.x, Q3 = h ? q3.y : q3.x;
             const uint64_t T0 = mul_f32x2(W, Q0), T1 = mul_f32x2(W, Q1), T2 = mul_f32x2(W, Q2), T3 = mul_f32x2(W, Q3);
             P[0] = add_f32x2(P[0], W);
@@ -388,19 +466,41 @@ __global__ void __launch_bounds__(NW * 32, 2) decode_ori_stream_kernel(const flo
             P[5] = fma_f32x2(T1, Q1, P[5]); P[6] = fma_f32x2(T1, Q2, P[6]); P[7] = fma_f32x2(T1, Q3, P[7]);
             P[8] = fma_f32x2(T2, Q2, P[8]); P[9] = fma_f32x2(T2, Q3, P[9]); P[10] = fma_f32x2(T3, Q3, P[10]);
           }
-        }
+          if (PRECISE) {
 #pragma unroll
-        for (int k = 0; k < 11; ++k) {  // 32-bin f32 partial sums into the f64 running sums
-          float lo, hi;
-          f32x2_unpack(P[k], lo, hi);
-          acc[k] += (double)(lo + hi);
+            for (int k = 0; k < 11; ++k) {
+              float lo, hi;
+              f32x2_unpack(P[k], lo, hi);
+              acc[k] += (double)lo + (double)hi;
+              P[k] = 0ull;
+            }
+          }
+        };
+        if (cn - s0 >= SUB) {   // a full step: straight-line code, the loads and ex2 of one slice overlap the FMAs of the previous one
+#pragma unroll
+          for (int j = 0; j < 8; ++j) slice(j);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (s0 + j * 128 >= cn) break;   // warp-uniform: no lane has bins in this or any later 128-bin slice
+            slice(j);
+          }
+        }
+        if (!PRECISE) {
+#pragma unroll
+          for (int k = 0; k < 11; ++k) {  // 32-bin f32 partial sums into the f64 running sums
+            float lo, hi;
+            f32x2_unpack(P[k], lo, hi);
+            acc[k] += (double)(lo + hi);
+          }
         }
       }
     }
     if (active) {
       const double r = warp_transpose_sum16(acc, lane);
-      if (soft_out != nullptr && is_logits) {
+      if (soft_out != nullptr && LOGITS) {
         const float sf = (float)__shfl_sync(0xffffffffu, r, 0);
+        const float4* row4 = reinterpret_cast<const float4*>(in + (size_t)img * ld);
         float4* o4 = reinterpret_cast<float4*>(soft_out + (size_t)img * n);   // n % 4 == 0, base 16-byte aligned (checked by the host)
         for (int i = lane; i < (n >> 2); i += 32) {
           const float4 x = __ldg(row4 + i);

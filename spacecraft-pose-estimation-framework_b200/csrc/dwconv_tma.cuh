@@ -16,11 +16,10 @@
 namespace spef {
 namespace dw {
 
-constexpr int TX = 4;  // outputs per thread along x
 
 struct DwParams {
   int B, H, W, C, Ho, Wo;
-  int TH, TW;        // output tile (TW multiple of TX)
+  int TH, TW;        // output tile (TW multiple of the kernel's TX)
   int THI, TWI;      // input box rows / cols = (T-1)*S + 3
   int tiles_y, tiles_x, nchunks;
   int relu;
@@ -36,7 +35,8 @@ __device__ __forceinline__ void tma_load_4d(uint32_t smem_dst, const CUtensorMap
 __host__ __device__ inline int stage_stride(int thi, int twi, int cv) { return ((thi * twi * cv * 16 + 127) / 128) * 128; }
 inline size_t smem_bytes(const DwParams& p, int cv) { return 2 * (size_t)stage_stride(p.THI, p.TWI, cv) + 128 + 64; }
 
-template <int S, int CV>
+// TX: outputs per thread along x (4; 3 for the 12-column maps, where 3 strips x 8 rows would leave a quarter of the threads idle)
+template <int S, int CV, int TX = 4>
 __global__ void __launch_bounds__(32 * CV, (CV == 4) ? 4 : 2)
 dwconv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__ w, const float* __restrict__ bias,
                      bf16* __restrict__ out, const DwParams p) {

@@ -15,6 +15,7 @@ namespace spef {
 namespace ingest {
 
 constexpr int kFixBits = 32 - 8 - 2;  // fixed-point fraction bits of the 8-bit resampler
+constexpr int KWIN = 12;              // taps of the fixed horizontal window (covers reductions up to 5.5x)
 
 // Host: taps of one axis.  first[o] / count[o] = window of input samples of output o, coef[o * ksize + j] = fixed-point
 // weight of sample first[o] + j.  All arithmetic in float64, in the operation order of the resampler being reproduced.
@@ -64,7 +65,7 @@ struct ResizeParams {
   void* dst;           // [B, 3, oh, ow] uint8 or float32
   const int* hfirst;   // [ow]
   const int* hcount;   // [ow]
-  const int32_t* hcoef;  // [hks][ow]  (tap-major: lanes read consecutive words)
+  const int32_t* hcoef;  // [hks][ow]  (tap-major: lanes read consecutive words); fixed-window plan: [KWIN][ow], see resize_plan
   const int* vfirst;   // [oh]
   const int* vcount;   // [oh]
   const int32_t* vcoef;  // [oh][vks]
@@ -94,24 +95,26 @@ __global__ void __launch_bounds__(384) resize_aa_kernel(const ResizeParams p) {
   for (int xx = threadIdx.x; xx < p.ow; xx += blockDim.x) {
     const int x0 = p.hfirst[xx], cnt = p.hcount[xx];
     if (KREG > 0) {
+      // fixed window of KREG taps at compile-time offsets (the host shifts the window of the right-most outputs left so that
+      // it never leaves the row, and pads the coefficients with zeros): no predicates, no per-tap address arithmetic
       int32_t k[KREG > 0 ? KREG : 1];
 #pragma unroll
-      for (int j = 0; j < KREG; ++j) k[j] = (j < cnt) ? p.hcoef[(size_t)j * p.ow + xx] : 0;
+      for (int j = 0; j < KREG; ++j) k[j] = p.hcoef[(size_t)j * p.ow + xx];
+      const uint8_t* px = img + ((size_t)r0 * p.sw + x0) * C;
+      const size_t row_bytes = (size_t)p.sw * C;
+      uint8_t* dst = filtered + xx;
 #pragma unroll 2
-      for (int r = r0; r < r1; ++r) {
-        const uint8_t* px = img + ((size_t)r * p.sw + x0) * C;
+      for (int r = r0; r < r1; ++r, px += row_bytes, dst += p.pitch) {
         int32_t acc[C];
 #pragma unroll
         for (int c = 0; c < C; ++c) acc[c] = 1 << (kFixBits - 1);
 #pragma unroll
         for (int j = 0; j < KREG; ++j) {
-          if (j < cnt) {
 #pragma unroll
-            for (int c = 0; c < C; ++c) acc[c] += (int32_t)px[j * C + c] * k[j];
-          }
+          for (int c = 0; c < C; ++c) acc[c] += (int32_t)px[j * C + c] * k[j];
         }
 #pragma unroll
-        for (int c = 0; c < C; ++c) filtered[((size_t)c * p.max_rows + (r - r0)) * p.pitch + xx] = clip8(acc[c]);
+        for (int c = 0; c < C; ++c) dst[(size_t)c * p.max_rows * p.pitch] = clip8(acc[c]);
       }
     } else {
       for (int r = r0; r < r1; ++r) {

@@ -55,6 +55,7 @@ struct Layer {
   int plan_batch = -1;      // batch size the cached activation tensor maps (tmA/tmD/tmX) were encoded for
   // TMA depthwise plan
   int dw_cv = 0;
+  int dw_tx = 4;            // outputs per thread along x of the TMA depthwise kernel
   dw::DwParams dwp;
   CUtensorMap tmX;
   // host copies of the folded bias (pw, dw) and the packed [9][C] depthwise weights: inputs of the fused-block plan
@@ -133,7 +134,9 @@ struct spef_ctx {
   float4* ori_tab = nullptr;
   float* ori_tab_soa = nullptr;  // [4][ori_tab_ld]: one plane per quaternion component, zero padded (decode_ori_stream_kernel)
   int ori_tab_ld = 0;
-  int decode_stream = 1;         // large batches take the streaming decode kernel (SPEF_DECODE_STREAM: 0 never, 2 always)
+  int dw_small_plan = 1;         // task-filling tile plans for the 15x24 / 8x12 depthwise layers (SPEF_DW_SMALL=0: first plan)
+  int decode_cfg = -1;           // -1: by batch size (launch_decode_stream)
+  int decode_stream = 1;         // spef_decode_ori takes the streaming kernel for 16-byte aligned rows (SPEF_DECODE_STREAM=0: decode_ori_kernel)
   int ori_n = 0;
   float4* pos_tab = nullptr;
   int pos_n = 0;
@@ -173,6 +176,7 @@ struct spef_ctx {
   float* t_prev_video = nullptr;
   float* t_ws[8] = {nullptr};    // scratch outputs when the caller passes NULL
   // ingest plan (spef_resize_frames): taps of both axes for the last (src_h, src_w) seen, one device allocation
+  int rz_fixed = 0;
   int rz_sh = 0, rz_sw = 0, rz_hks = 0, rz_vks = 0, rz_band = 0, rz_max_rows = 0, rz_pitch = 0;
   int* rz_tab = nullptr;
   // bookkeeping
@@ -181,6 +185,7 @@ struct spef_ctx {
 };
 
 static std::string g_create_err;
+static cudaError_t decode_stream_init();
 
 static int fail(spef_ctx* c, int code, const char* fmt, ...) {
   char buf[1024];
@@ -318,7 +323,9 @@ extern "C" int spef_create(spef_ctx** out, const spef_config* cfg) {
   ctx->smem_optin = prop.sharedMemPerBlockOptin;
   ctx->esz = (cfg->precision == SPEF_BF16) ? 2 : 4;
   if (const char* e4 = getenv("SPEF_GEMM_TRACE")) { ctx->trace_layer = atoi(e4); cudaMalloc((void**)&ctx->trace_dev, 256 * 16 * sizeof(long long)); }
-  if (const char* e12 = getenv("SPEF_DECODE_STREAM")) ctx->decode_stream = atoi(e12);  // 0 never, 1 large batches, 2 always (tests)
+  if (const char* e15 = getenv("SPEF_DW_SMALL")) ctx->dw_small_plan = atoi(e15);
+  if (const char* e13 = getenv("SPEF_DECODE_CFG")) ctx->decode_cfg = atoi(e13);
+  if (const char* e12 = getenv("SPEF_DECODE_STREAM")) ctx->decode_stream = atoi(e12);
   if (const char* e5 = getenv("SPEF_GEMM_IMPL")) ctx->gemm_impl = (atoi(e5) == 1) ? 1 : 2;
   if (const char* e7 = getenv("SPEF_GEMM_NDG")) ctx->gemm_ndg = (atoi(e7) == 1) ? 1 : 2;
   if (const char* e6 = getenv("SPEF_GEMM_NSW")) ctx->gemm_nsw = (atoi(e6) == 8 && ctx->gemm_ndg == 1) ? 8 : 4;
@@ -378,6 +385,10 @@ extern "C" int spef_create(spef_ctx** out, const spef_config* cfg) {
     return fail(nullptr, SPEF_ERR_CUDA, "%s", m.c_str());
   }
   cudaMemset(ctx->eval_sums, 0, 8 * sizeof(double));
+  if (decode_stream_init() != cudaSuccess) {
+    spef_destroy(ctx);
+    return fail(nullptr, SPEF_ERR_CUDA, "spef_create: cannot reserve shared memory for the decode kernel");
+  }
   *out = ctx;
   return SPEF_OK;
 }
@@ -713,6 +724,11 @@ extern "C" int spef_finalize_weights(spef_ctx* ctx) {
       d.TH = (l.stride == 1) ? 8 : 4;
       d.TW = (l.stride == 1) ? (wo4 < 32 ? wo4 : 32) : (wo4 < 16 ? wo4 : 16);
       if (l.stride == 1 && l.dw_cv == 6 && d.TW > 24) d.TW = 24;
+      // small maps of the 64-channel-chunk kernel (256 threads = 32 (strip, row) tasks per pass): fill the pass
+      if (l.dw_cv == 8 && ctx->dw_small_plan) {
+        if (l.wout == 12) { l.dw_tx = 3; d.TW = 12; }                             // 4 strips of 3 columns: 32 tasks at stride 1 (was 24), 16 at stride 2 (was 12)
+        else if (l.stride == 1 && l.wout == 24 && l.hout == 15) { d.TH = 5; }     // 6 strips x 5 rows = 30 tasks, three tiles of 5 rows (was 48 tasks = two passes, 8 + 7 rows)
+      }
       d.THI = (d.TH - 1) * l.stride + 3;
       d.TWI = (d.TW - 1) * l.stride + 3;
       // bank-conflict-free row pitch for the rows-fastest lane order (dwconv_tma.cuh): 64-byte pixels need an odd box
@@ -778,6 +794,8 @@ extern "C" int spef_finalize_weights(spef_ctx* ctx) {
     CK(cudaFuncSetAttribute(dw::dwconv3x3_tma_kernel<1, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem));
     CK(cudaFuncSetAttribute(dw::dwconv3x3_tma_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem));
     CK(cudaFuncSetAttribute(dw::dwconv3x3_tma_kernel<2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem));
+    CK(cudaFuncSetAttribute(dw::dwconv3x3_tma_kernel<1, 8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem));
+    CK(cudaFuncSetAttribute(dw::dwconv3x3_tma_kernel<2, 8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem));
     CK(cudaFuncSetAttribute(dw::dwconv3x3_tma_kernel<2, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem));
     CK(cudaFuncSetAttribute(dw::dwconv3x3_tma_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem));
   }
@@ -860,9 +878,9 @@ static int launch_cuda_core_layer(spef_ctx* ctx, const Layer& l, const void* in,
   return SPEF_OK;
 }
 
-template <int S, int CV>
+template <int S, int CV, int TX = 4>
 static void launch_dw_inst(const CUtensorMap& tm, const Layer& l, bf16* out, int grid, size_t smem, cudaStream_t st) {
-  dw::dwconv3x3_tma_kernel<S, CV><<<grid, 32 * CV, smem, st>>>(tm, l.w_f32, l.bias, out, l.dwp);
+  dw::dwconv3x3_tma_kernel<S, CV, TX><<<grid, 32 * CV, smem, st>>>(tm, l.w_f32, l.bias, out, l.dwp);
 }
 
 static int launch_dw_tma_layer(spef_ctx* ctx, Layer& l, const void* in, void* out, int B, cudaStream_t st, bool cached_maps) {
@@ -884,11 +902,13 @@ static int launch_dw_tma_layer(spef_ctx* ctx, Layer& l, const void* in, void* ou
   const size_t smem = dw::smem_bytes(l.dwp, l.dw_cv);
   bf16* o = (bf16*)out;
   if (l.stride == 1) {
-    if (l.dw_cv == 8) launch_dw_inst<1, 8>(*tm, l, o, grid, smem, st);
+    if (l.dw_cv == 8 && l.dw_tx == 3) launch_dw_inst<1, 8, 3>(*tm, l, o, grid, smem, st);
+    else if (l.dw_cv == 8) launch_dw_inst<1, 8>(*tm, l, o, grid, smem, st);
     else if (l.dw_cv == 6) launch_dw_inst<1, 6>(*tm, l, o, grid, smem, st);
     else launch_dw_inst<1, 4>(*tm, l, o, grid, smem, st);
   } else {
-    if (l.dw_cv == 8) launch_dw_inst<2, 8>(*tm, l, o, grid, smem, st);
+    if (l.dw_cv == 8 && l.dw_tx == 3) launch_dw_inst<2, 8, 3>(*tm, l, o, grid, smem, st);
+    else if (l.dw_cv == 8) launch_dw_inst<2, 8>(*tm, l, o, grid, smem, st);
     else if (l.dw_cv == 6) launch_dw_inst<2, 6>(*tm, l, o, grid, smem, st);
     else launch_dw_inst<2, 4>(*tm, l, o, grid, smem, st);
   }
@@ -1283,10 +1303,20 @@ static int resize_plan(spef_ctx* ctx, int sh, int sw, int C) {
   const ingest::AxisTaps h = ingest::make_axis_taps(sw, ow), v = ingest::make_axis_taps(sh, oh);
   // layout of the table block (int32): hfirst[ow] hcount[ow] hcoef[hks][ow] vfirst[oh] vcount[oh] vcoef[oh][vks]
   std::vector<int> tab;
-  tab.insert(tab.end(), h.first.begin(), h.first.end());
+  // horizontal taps: when the filter has at most KWIN taps (and the row at least that many pixels) every output gets a
+  // window of exactly KWIN taps that stays inside the row -- shifted left at the right edge, zero coefficients elsewhere --
+  // so that the kernel reads at compile-time offsets without predicates
+  ctx->rz_fixed = (h.ksize <= ingest::KWIN && sw >= ingest::KWIN) ? 1 : 0;
+  const int hk = ctx->rz_fixed ? ingest::KWIN : h.ksize;
+  std::vector<int> hfirst(h.first), hcoef((size_t)hk * ow, 0);
+  for (int o = 0; o < ow; ++o) {
+    int shift = 0;
+    if (ctx->rz_fixed && h.first[o] + ingest::KWIN > sw) { shift = h.first[o] + ingest::KWIN - sw; hfirst[o] = sw - ingest::KWIN; }
+    for (int j = 0; j < h.count[o]; ++j) hcoef[(size_t)(j + shift) * ow + o] = h.coef[(size_t)o * h.ksize + j];
+  }
+  tab.insert(tab.end(), hfirst.begin(), hfirst.end());
   tab.insert(tab.end(), h.count.begin(), h.count.end());
-  for (int j = 0; j < h.ksize; ++j)
-    for (int o = 0; o < ow; ++o) tab.push_back(h.coef[(size_t)o * h.ksize + j]);
+  tab.insert(tab.end(), hcoef.begin(), hcoef.end());
   tab.insert(tab.end(), v.first.begin(), v.first.end());
   tab.insert(tab.end(), v.count.begin(), v.count.end());
   tab.insert(tab.end(), v.coef.begin(), v.coef.end());
@@ -1294,7 +1324,7 @@ static int resize_plan(spef_ctx* ctx, int sh, int sw, int C) {
   ctx->rz_tab = nullptr;
   CK(cudaMalloc(&ctx->rz_tab, tab.size() * sizeof(int)));
   CK(cudaMemcpy(ctx->rz_tab, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice));
-  ctx->rz_sh = sh; ctx->rz_sw = sw; ctx->rz_hks = h.ksize; ctx->rz_vks = v.ksize;
+  ctx->rz_sh = sh; ctx->rz_sw = sw; ctx->rz_hks = hk; ctx->rz_vks = v.ksize;
   ctx->rz_pitch = (ow + 15) & ~15;
   // rows per CTA: as many as keep the filtered rows of a 3-channel band within 96 KB of shared memory (two CTAs per SM)
   for (int band = 8; band >= 1; band >>= 1) {
@@ -1341,7 +1371,7 @@ extern "C" int spef_resize_frames(spef_ctx* ctx, const uint8_t* frames_dev, int3
   const size_t smem = (size_t)channels * p.max_rows * p.pitch;
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e;
-  if (p.hks <= 12) e = (channels == 1) ? launch_resize<12, 1>(p, B, smem, st) : launch_resize<12, 3>(p, B, smem, st);
+  if (ctx->rz_fixed) e = (channels == 1) ? launch_resize<ingest::KWIN, 1>(p, B, smem, st) : launch_resize<ingest::KWIN, 3>(p, B, smem, st);
   else e = (channels == 1) ? launch_resize<0, 1>(p, B, smem, st) : launch_resize<0, 3>(p, B, smem, st);
   if (e != cudaSuccess) return fail(ctx, SPEF_ERR_CUDA, "launch of resize_aa_kernel failed: %s", cudaGetErrorString(e));
   ctx->launches++;
@@ -1351,6 +1381,50 @@ extern "C" int spef_resize_frames(spef_ctx* ctx, const uint8_t* frames_dev, int3
 // ------------------------------------------------------------------------------------------------------
 // post-processing
 // ------------------------------------------------------------------------------------------------------
+template <int NW, int RING, int PF, bool LOGITS>
+static auto decode_stream_pick(bool amax, bool precise) {
+  return precise ? (amax ? dstream::decode_ori_stream_kernel<NW, RING, PF, true, true, LOGITS> : dstream::decode_ori_stream_kernel<NW, RING, PF, false, true, LOGITS>)
+                 : (amax ? dstream::decode_ori_stream_kernel<NW, RING, PF, true, false, LOGITS> : dstream::decode_ori_stream_kernel<NW, RING, PF, false, false, LOGITS>);
+}
+template <int NW, int RING, int PF>
+static cudaError_t decode_stream_attr() {
+  const int smem = (int)dstream::smem_bytes(NW, RING);
+  cudaError_t e = cudaSuccess;
+  for (int v = 0; v < 8 && e == cudaSuccess; ++v)
+    e = (v & 4) ? cudaFuncSetAttribute(decode_stream_pick<NW, RING, PF, true>(v & 1, v & 2), cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
+                : cudaFuncSetAttribute(decode_stream_pick<NW, RING, PF, false>(v & 1, v & 2), cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  return e;
+}
+// once per context (not at launch time: launches may be under CUDA-graph capture)
+static cudaError_t decode_stream_init() {
+  cudaError_t e = decode_stream_attr<8, 4, 0>();
+  if (e == cudaSuccess) e = decode_stream_attr<16, 2, 0>();
+  return e;
+}
+
+template <int NW, int RING, int PF>
+static int launch_decode_stream_cfg(spef_ctx* ctx, const float* in, int ld, int B, int n, int is_logits, float* soft, float* quat, float* hinv,
+                                    int32_t* amax, uint32_t* flags, cudaStream_t st) {
+  const size_t smem = dstream::smem_bytes(NW, RING);
+  const int grid = std::min(cdiv(B, NW), ctx->num_sms);
+  auto kern = is_logits ? decode_stream_pick<NW, RING, PF, true>(amax != nullptr, hinv != nullptr)
+                        : decode_stream_pick<NW, RING, PF, false>(amax != nullptr, hinv != nullptr);
+  kern<<<grid, NW * 32, smem, st>>>(in, ld, B, n, ctx->ori_tab_soa, ctx->ori_tab_ld, soft, quat, hinv, amax, flags);
+  CK_LAUNCH("decode_ori_stream_kernel");
+  return SPEF_OK;
+}
+
+// The streaming decode kernel (one persistent CTA per SM, SoA table in shared memory, logits through per-warp rings of bulk
+// async copies, packed FP32 pairs).  Warps x ring slots per CTA: batches that fill the GPU take 16 x 2 (more warps beat a deeper
+// ring, and an L2 prefetch 6 steps ahead only cost issue slots: profiles/r01_decode_ab.txt), smaller ones 8 x 4 (more CTAs).
+// SPEF_DECODE_CFG overrides: 0 = 8 x 4, 2 = 16 x 2.
+static int launch_decode_stream(spef_ctx* ctx, const float* in, int ld, int B, int n, int is_logits, float* soft, float* quat, float* hinv,
+                                int32_t* amax, uint32_t* flags, cudaStream_t st) {
+  const int cfg = ctx->decode_cfg >= 0 ? ctx->decode_cfg : ((long long)B >= 16LL * ctx->num_sms ? 2 : 0);
+  if (cfg == 0) return launch_decode_stream_cfg<8, 4, 0>(ctx, in, ld, B, n, is_logits, soft, quat, hinv, amax, flags, st);
+  return launch_decode_stream_cfg<16, 2, 0>(ctx, in, ld, B, n, is_logits, soft, quat, hinv, amax, flags, st);
+}
+
 static int decode_ori_ld(spef_ctx* ctx, const float* in, int ld, int B, int n, int is_logits, float* soft, float* quat, float* hinv,
                          int32_t* amax, uint32_t* flags, cudaStream_t st) {
   if (!ctx->ori_tab) return fail(ctx, SPEF_ERR_STATE, "decode_ori: orientation histogram not set (spef_set_ori_histogram)");
@@ -1361,15 +1435,8 @@ static int decode_ori_ld(spef_ctx* ctx, const float* in, int ld, int B, int n, i
   // large batches: the streaming kernel (persistent CTAs of 8 warps, SoA table in shared memory, packed FP32 pairs)
   const bool vec_ok = (n % 4 == 0) && (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(in) & 15) == 0) &&
                       (!soft || (reinterpret_cast<uintptr_t>(soft) & 15) == 0);
-  if (vec_ok && ((ctx->decode_stream == 1 && (long long)B >= 8 * fill) || ctx->decode_stream == 2)) {
-    constexpr int NW = 8;
-    const size_t smem = (size_t)4 * dstream::TC * sizeof(float) + (size_t)NW * 32 * 11 * sizeof(double);
-    const int grid = std::min(cdiv(B, NW), 2 * ctx->num_sms);
-    auto kern = amax ? dstream::decode_ori_stream_kernel<NW, true> : dstream::decode_ori_stream_kernel<NW, false>;
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, NW * 32, smem, st>>>(in, ld, B, n, is_logits, ctx->ori_tab_soa, ctx->ori_tab_ld, soft, quat, hinv, amax, flags);
-    CK_LAUNCH("decode_ori_stream_kernel");
-    return SPEF_OK;
+  if (vec_ok && ctx->decode_stream != 0) {
+    return launch_decode_stream(ctx, in, ld, B, n, is_logits, soft, quat, hinv, amax, flags, st);
   }
   if ((long long)B >= 32 * fill) decode_ori_kernel<32><<<cdiv(cdiv(B, 32), 4), 128, 0, st>>>(in, ld, B, n, is_logits, ctx->ori_tab, soft, quat, hinv, amax, flags);
   else if ((long long)B >= 8 * fill) decode_ori_kernel<8><<<cdiv(cdiv(B, 8), 4), 128, 0, st>>>(in, ld, B, n, is_logits, ctx->ori_tab, soft, quat, hinv, amax, flags);

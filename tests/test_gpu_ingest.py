@@ -86,3 +86,19 @@ def test_resize_rejects_bad_arguments(eng):
         eng.resize_frames(torch.zeros(1, 10, 10, dtype=torch.float32))
     with pytest.raises(ValueError):
         eng.resize_frames(torch.zeros(1, 10, 10, 2, dtype=torch.uint8))
+
+
+def test_frame_transform_mirror(eng, golden):
+    """spef_b200.data.FrameTransform = the reference's Compose([Resize(img_size), ToTensor()]) for a batch of frames."""
+    from spef_b200.data import FrameTransform
+    g = golden("resize")
+    frames = synthetic.synthetic_frames(batch=2, height=1200, width=1920, channels=1, seed=11, kind="speed")
+    tf = FrameTransform(eng, (240, 384))
+    x = tf(frames).cpu().numpy()
+    assert x.dtype == np.float32 and x.shape == (2, 3, 240, 384)
+    np.testing.assert_array_equal(x[0, :, 100, :], g["speed_1200x1920_f32_row100"])
+    np.testing.assert_array_equal(tf(frames[0]).cpu().numpy()[0], x[0])           # a single [H,W] frame
+    u8 = FrameTransform(eng, (240, 384), torch.uint8)(torch.from_numpy(frames).cuda())
+    np.testing.assert_array_equal(u8.cpu().numpy()[:, :1], g["speed_1200x1920"])
+    with pytest.raises(ValueError):
+        FrameTransform(eng, (240, 240))
