@@ -112,17 +112,18 @@ __device__ __forceinline__ int fast_div(int t, int d, float rcp) {
 struct WorkIt {
   int n, i, c;        // item, tile iteration, chunk
   int g, kph;         // worker group and parity of the group's item counter
+  int kph2;           // parity of (item counter >> 1): barrier parity when the group owns two A2 buffers (buffer = kph)
   int xs, xph;        // x stage / parity
   int ws, wph;        // weight stage / parity
   int ps, pph;        // project accumulator stage / parity
   int as, aph;        // TMEM expand stage / parity
 };
-__device__ __forceinline__ WorkIt work_begin() { return WorkIt{0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; }
+__device__ __forceinline__ WorkIt work_begin() { return WorkIt{0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; }
 template <int NG>
 __device__ __forceinline__ void work_next(WorkIt& w, const FbParams& p) {
   const int n_chunks = p.n_chunks, x_stages = p.x_stages, w_stages = p.w_stages, resident = p.resident, proj_stages = p.proj_stages;
   ++w.n;
-  if (++w.g == NG) { w.g = 0; w.kph ^= 1; }
+  if (++w.g == NG) { w.g = 0; w.kph ^= 1; if (w.kph == 0) w.kph2 ^= 1; }
   if (++w.as == p.n_acc) { w.as = 0; w.aph ^= 1; }
   if (++w.c == n_chunks) {
     w.c = 0; ++w.i;

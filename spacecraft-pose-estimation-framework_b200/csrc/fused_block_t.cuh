@@ -57,6 +57,8 @@ struct FbtParams {
   int x_stages, w_stages, resident, proj_stages;
   int n_acc, acc_stride, proj_col0, proj_stride;
   int residual;
+  int a2_bufs;         // A2 buffers per worker group: 2 when shared memory allows (the workers of item k + 1 then never wait for the
+                       // project MMA of item k to have read A2: ncu showed 24 polls per item on that barrier), else 1
   // Strip stacking (stack = 4) for a block with <= 32 hidden channels and no expand conv (t = 1): the four TMEM lane quarters
   // hold the SAME channels of four horizontally adjacent strips of a 4x wider tile.  The "expand" GEMM is the identity routed
   // per strip: the K chunks of the operand pair are the strips (A chunk q = identity in the rows of quarter q, B chunk q =
@@ -80,7 +82,7 @@ __host__ __device__ inline int w_stage_bytes(int we_bytes, int cpad) { return we
 __host__ __device__ inline int x_stage_bytes(int kc_in, int n_px) { return kc_in * n_px * 128; }
 inline size_t smem_bytes(const FbtParams& p, int ng) {
   return 1024 + (size_t)p.x_stages * x_stage_bytes(p.kc_in, p.n_px) + (size_t)p.w_stages * w_stage_bytes(p.we_bytes, p.cpad) +
-         (size_t)ng * A2_BYTES + 2048 /*bias*/ + 512 /*barriers*/;
+         (size_t)ng * p.a2_bufs * A2_BYTES + 2048 /*bias*/ + 512 /*barriers*/;
 }
 // Register budget per role when three worker groups share the SM.  setmaxnreg only moves registers inside the CTA's own
 // allocation (20 warps x 96 at launch), so 12 * WORKER + 4 * EPI + 4 * CTRL <= 20 * 96 = 1920 per lane: 1440 + 288 + 160 = 1888.
@@ -152,8 +154,8 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   const int wsb = w_stage_bytes(p.we_bytes, p.cpad);
   uint8_t* x_s = smem;
   uint8_t* w_s = x_s + (size_t)p.x_stages * xsb;
-  uint8_t* a2_s = w_s + (size_t)p.w_stages * wsb;             // [NG][A2_BYTES]
-  float* bp_s = reinterpret_cast<float*>(a2_s + (size_t)NG * A2_BYTES);   // [<= 512]
+  uint8_t* a2_s = w_s + (size_t)p.w_stages * wsb;             // [NG][a2_bufs][A2_BYTES]
+  float* bp_s = reinterpret_cast<float*>(a2_s + (size_t)NG * p.a2_bufs * A2_BYTES);   // [<= 512]
   uint64_t* bars = reinterpret_cast<uint64_t*>(bp_s + 512);
   uint64_t* x_full = bars;                        // [4]
   uint64_t* x_empty = x_full + 4;                 // [4]
@@ -161,9 +163,9 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   uint64_t* w_empty = w_full + MAX_W_STAGES;      // [MAX_W_STAGES]
   uint64_t* acc_full = w_empty + MAX_W_STAGES;    // [MAX_ACC]  expand MMA -> workers
   uint64_t* acc_empty = acc_full + MAX_ACC;       // [MAX_ACC]  workers -> expand MMA
-  uint64_t* a2_full = acc_empty + MAX_ACC;        // [NG]  workers -> project MMA
-  uint64_t* a2_empty = a2_full + MAX_NGT;         // [NG]  project MMA -> workers
-  uint64_t* proj_full = a2_empty + MAX_NGT;       // [2]
+  uint64_t* a2_full = acc_empty + MAX_ACC;        // [NG][2]  workers -> project MMA
+  uint64_t* a2_empty = a2_full + 2 * MAX_NGT;     // [NG][2]  project MMA -> workers
+  uint64_t* proj_full = a2_empty + 2 * MAX_NGT;   // [2]
   uint64_t* proj_empty = proj_full + 2;           // [2]
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(proj_empty + 2);
 
@@ -208,7 +210,7 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       tc::mbar_init(tc::smem_u32(&acc_full[i]), 1);
       tc::mbar_init(tc::smem_u32(&acc_empty[i]), GW);
     }
-    for (int i = 0; i < NG; ++i) {
+    for (int i = 0; i < 2 * NG; ++i) {
       tc::mbar_init(tc::smem_u32(&a2_full[i]), 1);
       tc::mbar_init(tc::smem_u32(&a2_empty[i]), 1);
     }
@@ -311,10 +313,12 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     for (fb::WorkIt w = fb::work_begin(); w.n < total; fb::work_next<NG>(w, itp)) {
       const int n = w.n;
       if (w.c == 0) tc::mbar_wait_relaxed(tc::smem_u32(&proj_empty[w.ps]), (uint32_t)(w.pph ^ 1), 64);
-      tc::mbar_wait_relaxed(tc::smem_u32(&a2_full[w.g]), (uint32_t)w.kph, 64);
+      const int a2i = (p.a2_bufs == 2) ? 2 * w.g + w.kph : w.g;            // A2 buffer / barrier of this item
+      const uint32_t a2ph = (uint32_t)((p.a2_bufs == 2) ? w.kph2 : w.kph);
+      tc::mbar_wait_relaxed(tc::smem_u32(&a2_full[a2i]), a2ph, 64);
       tc::tcgen05_fence_after();
       if (lane == 0) FBT_TRACE(n, 4);
-      const uint64_t a0 = a_base + (uint64_t)((uint32_t)w.g * (uint32_t)(A2_BYTES >> 4));
+      const uint64_t a0 = a_base + (uint64_t)((uint32_t)a2i * (uint32_t)(A2_BYTES >> 4));
       const uint64_t b0 = b_base + (uint64_t)((uint32_t)w.ws * w_step);
       const uint32_t d = tmem_base + (uint32_t)(p.proj_col0 + w.ps * p.proj_stride);
       if (p.stack == 1) {
@@ -330,7 +334,7 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
           fb::mma_elect(d + (ks >> kshift) * (uint32_t)p.proj_sub, a0 + (uint64_t)(ks * (uint32_t)(2 * A2_SBO >> 4)),
                         b0 + (uint64_t)((ks >> 2) * wp_half + (ks & 3u) * 2u), idesc_p, (w.c > 0 || (ks & kmask) > 0) ? 1u : 0u);
       }
-      fb::commit_elect(tc::smem_u32(&a2_empty[w.g]));
+      fb::commit_elect(tc::smem_u32(&a2_empty[a2i]));
       if (!p.resident) fb::commit_elect(tc::smem_u32(&w_empty[w.ws]));
       if (w.c == p.n_chunks - 1) fb::commit_elect(tc::smem_u32(&proj_full[w.ps]));
       if (lane == 0) FBT_TRACE(n, 5);
@@ -398,7 +402,7 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     const int slot = q * 32 + lane;                 // channel slot of this thread = TMEM lane = K index of the project GEMM
     const int tg = (int)threadIdx.x - 32 * g * GW;
     const uint32_t sw4 = (uint32_t)(slot & 7) << 4; // 128-byte swizzle: 16-byte chunk index ^= (channel row & 7)
-    const uint32_t a2_u = tc::smem_u32(a2_s + (size_t)g * A2_BYTES) + (uint32_t)((slot >> 3) * A2_SBO + (slot & 7) * 128);
+    const uint32_t a2_u0 = tc::smem_u32(a2_s) + (uint32_t)((slot >> 3) * A2_SBO + (slot & 7) * 128);
     fb::WorkIt w = fb::work_begin();
     for (int s = 0; s < g && w.n < total; ++s) fb::work_next<NG>(w, itp);
     int cur_i = -1, cur_c = -1, b = 0, oy0 = 0, ox0 = 0;
@@ -424,8 +428,10 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       const bool left_ok = (ox0q * S - 1) >= 0;
       const bool right_ok = (ox0q * S - 1 + TWI - 1) < p.W;
       const int gy0 = oy0 * S - 1;
-      const uint32_t kph = (uint32_t)w.kph;
-      const int as = w.as, gsel = w.g;
+      const int as = w.as;
+      const int gsel = (p.a2_bufs == 2) ? 2 * w.g + w.kph : w.g;            // A2 buffer / barrier of this item
+      const uint32_t kph = (uint32_t)((p.a2_bufs == 2) ? w.kph2 : w.kph);
+      const uint32_t a2_u = a2_u0 + (uint32_t)gsel * (uint32_t)A2_BYTES;
       tc::mbar_wait(tc::smem_u32(&acc_full[as]), (uint32_t)w.aph);
       tc::tcgen05_fence_after();
       if (tg == 0) FBT_TRACE(n, 7);
@@ -433,7 +439,9 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       // bookkeeping of the next item now, so that it overlaps the arithmetic below
       for (int s = 0; s < NG && w.n < total; ++s) fb::work_next<NG>(w, itp);
 
-      // hidden pixel row r of the box -> relu(acc + be) rounded to BF16 (as f32), zero outside the image
+      // hidden pixel row r of the box -> relu(acc + be) rounded to BF16 (as f32), zero outside the image.
+      // (Issuing the tcgen05.ld of row r + 1 before converting row r -- a software pipeline over the nine TMEM loads of an
+      // item -- was measured: the 16 extra live registers spill in every instantiation and the step got 6 % slower.)
       auto load_row = [&](int r, Row& h) {
         const int gy = gy0 + r;
         if (gy >= 0 && gy < p.H) {                 // uniform

@@ -105,6 +105,7 @@ struct spef_ctx {
   int fb_max_cin = 64; // fuse blocks with Cin <= this (SPEF_FB_MAX_CIN); wider blocks measured faster as three kernels
   int stem_patch = 1;  // stem input patches staged by TMA (SPEF_STEM_PATCH=0: gather the 27 taps from global memory)
   int stem_prod = 2;   // im2col producer groups (128 threads each) of the tcgen05 stem (SPEF_STEM_PROD = 1 | 2)
+  int fbt_a2_bufs = 2; // A2 buffers per worker group of the channel-lane kernel where shared memory allows (SPEF_FBT_A2 = 1 | 2)
   int fbt_max_ng = 3;  // worker groups of the channel-lane kernel: 3 where TMEM / shared memory allow, else 2 (SPEF_FBT_NG)
   int fb_variant = 1;  // 1: channel-lane fused kernel where it applies, else the staged one; 0: staged kernel only (SPEF_FB_VARIANT)
   int fb_trace_block = -1;  // SPEF_FB_TRACE=<block index>: dump CTA-0 clock64 timestamps of that fused block to stderr
@@ -337,6 +338,7 @@ extern "C" int spef_create(spef_ctx** out, const spef_config* cfg) {
   if (const char* e12 = getenv("SPEF_FB_VARIANT")) ctx->fb_variant = atoi(e12) ? 1 : 0;
   if (const char* e15 = getenv("SPEF_STEM_PATCH")) ctx->stem_patch = atoi(e15) ? 1 : 0;
   if (const char* e14 = getenv("SPEF_STEM_PROD")) { int v = atoi(e14); ctx->stem_prod = (v == 1 || v == 4) ? v : 2; }
+  if (const char* e16 = getenv("SPEF_FBT_A2")) ctx->fbt_a2_bufs = (atoi(e16) == 1) ? 1 : 2;
   if (const char* e13 = getenv("SPEF_FBT_NG")) ctx->fbt_max_ng = (atoi(e13) == 2) ? 2 : 3;
   if (const char* e10 = getenv("SPEF_FB_TRACE")) { ctx->fb_trace_block = atoi(e10); if (!ctx->trace_dev) cudaMalloc((void**)&ctx->trace_dev, 256 * 16 * sizeof(long long)); }
   build_layers(ctx);
@@ -590,9 +592,15 @@ static int plan_blocks_t(spef_ctx* ctx) {
       // a stacked tile is four TMA boxes of 64-byte pixel rows (~2700 cycles): it must be prefetched behind the previous item
       for (int xs = 4; xs >= (stack == 4 ? 2 : 1); --xs) opts.push_back({q.n_chunks, 1, xs});
       if (q.n_chunks > 3) for (int xs = 2; xs >= 1; --xs) { opts.push_back({4, 0, xs}); opts.push_back({3, 0, xs}); }
-      for (const Opt& o : opts) {
-        q.w_stages = o.w; q.resident = o.res; q.x_stages = o.x;
-        if (fbt::smem_bytes(q, ng) <= limit) { found = true; b.t_ng = ng; b.t_smem = fbt::smem_bytes(q, ng); break; }
+      // two A2 buffers per group where they fit next to at least two x stages (the workers then never wait for the project MMA
+      // of their previous item), else one
+      for (int a2b = ctx->fbt_a2_bufs; a2b >= 1 && !found; --a2b) {
+        q.a2_bufs = a2b;
+        for (const Opt& o : opts) {
+          if (a2b == 2 && o.x < 2) continue;
+          q.w_stages = o.w; q.resident = o.res; q.x_stages = o.x;
+          if (fbt::smem_bytes(q, ng) <= limit) { found = true; b.t_ng = ng; b.t_smem = fbt::smem_bytes(q, ng); break; }
+        }
       }
     }
     if (!found) continue;
