@@ -32,6 +32,20 @@ __device__ __forceinline__ void tma_load_4d(uint32_t smem_dst, const CUtensorMap
       : "memory");
 }
 
+// two f32 (packed in a b64) -> bf16x2, low half = first element; the .relu form folds max(x, 0) into the conversion
+__device__ __forceinline__ uint32_t cvt_relu_bf16x2(uint64_t v) {
+  uint32_t lo, hi, r;
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(__uint_as_float(hi)), "f"(__uint_as_float(lo)));
+  return r;
+}
+__device__ __forceinline__ uint32_t cvt_bf16x2(uint64_t v) {
+  uint32_t lo, hi, r;
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(__uint_as_float(hi)), "f"(__uint_as_float(lo)));
+  return r;
+}
+
 __host__ __device__ inline int stage_stride(int thi, int twi, int cv) { return ((thi * twi * cv * 16 + 127) / 128) * 128; }
 inline size_t smem_bytes(const DwParams& p, int cv) { return 2 * (size_t)stage_stride(p.THI, p.TWI, cv) + 128 + 64; }
 
@@ -102,27 +116,50 @@ dwconv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmX, const float* __res
 #pragma unroll
     for (int e = 0; e < 4; ++e) bv[e] = f32x2(b8[2 * e], b8[2 * e + 1]);
   }
+  // This thread's (strip, row) tasks are the same in every tile: decode them once (ncu: the per-task divisions, 64-bit
+  // address arithmetic and generic-space loads of the first version made FFMA2 only 19 % of the instruction stream).
+  // S == 1 with 64/96-byte pixels: consecutive lane groups take vertically adjacent rows and the host picks the box width
+  // so that the row pitch is 64 resp. 96 (mod 128) bytes => the 8 lanes of a quarter-warp hit 8 distinct 16-byte bank
+  // groups.  Otherwise strips along x are adjacent.
+  constexpr bool rows_fastest = (S == 1 && CV != 8);
+  constexpr int MAX_TASKS = 2;             // tasks per thread and tile (checked by the host: TW / TX * TH <= MAX_TASKS * 32)
+  int t_xs[MAX_TASKS], t_ry[MAX_TASKS];
+  uint32_t t_off[MAX_TASKS];               // byte offset of the task's first input pixel inside a stage
+#pragma unroll
+  for (int k = 0; k < MAX_TASKS; ++k) {
+    const int task = task0 + k * task_step;
+    const int xs = rows_fastest ? task / p.TH : task % nxs;
+    const int ry = rows_fastest ? task % p.TH : task / nxs;
+    t_xs[k] = (task < tasks) ? xs : -1;
+    t_ry[k] = ry;
+    t_off[k] = (uint32_t)(((ry * S) * p.TWI + xs * TX * S) * (CV * 16) + cv * 16);
+  }
+  const uint32_t row_pitch = (uint32_t)(p.TWI * CV * 16);
+  const uint32_t smem_u = tc::smem_u32(smem);
+  // tile coordinates advance by sp_step tiles per iteration: carry (b, ty, tx) instead of dividing
+  int tx, ty, b;
+  {
+    long long r = sp0;
+    tx = (int)(r % p.tiles_x); r /= p.tiles_x;
+    ty = (int)(r % p.tiles_y);
+    b = (int)(r / p.tiles_y);
+  }
+  const int step_tx = (int)(sp_step % p.tiles_x);
+  const int step_ty = (int)((sp_step / p.tiles_x) % p.tiles_y);
+  const int step_b = (int)(sp_step / ((long long)p.tiles_x * p.tiles_y));
   uint32_t phases = 0;  // bit s = parity of stage s
   int stage = 0;
   for (; sp < spatial_tiles; sp += sp_step) {
-    long long r = sp;
-    const int tx = (int)(r % p.tiles_x); r /= p.tiles_x;
-    const int ty = (int)(r % p.tiles_y);
-    const int b = (int)(r / p.tiles_y);
     tc::mbar_wait(tc::smem_u32(&full_bar[stage]), (phases >> stage) & 1u);
     phases ^= 1u << stage;
-    const uint8_t* tile_s = smem + (size_t)stage * sstride + cv * 16;
+    const uint32_t tile_u = smem_u + (uint32_t)stage * (uint32_t)sstride;
 
     if (c_ok) {
-      for (int task = task0; task < tasks; task += task_step) {
-        // S == 1 with 64/96-byte pixels: consecutive lanes groups take vertically adjacent rows and the host picks the
-        // box width so that the row pitch is 64 resp. 96 (mod 128) bytes => the 8 lanes of a quarter-warp hit 8 distinct
-        // 16-byte bank groups.  Otherwise strips along x are adjacent.
-        const bool rows_fastest = (S == 1 && CV != 8);
-        const int xs = rows_fastest ? task / p.TH : task % nxs;
-        const int ry = rows_fastest ? task % p.TH : task / nxs;
-        const int oy = ty * p.TH + ry;
-        const int ox0 = tx * p.TW + xs * TX;
+#pragma unroll
+      for (int k = 0; k < MAX_TASKS; ++k) {
+        if (t_xs[k] < 0) break;
+        const int oy = ty * p.TH + t_ry[k];
+        const int ox0 = tx * p.TW + t_xs[k] * TX;
         if (oy >= p.Ho || ox0 >= p.Wo) continue;
         uint64_t acc[TX][4];
 #pragma unroll
@@ -131,10 +168,10 @@ dwconv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmX, const float* __res
           for (int e = 0; e < 4; ++e) acc[t][e] = bv[e];
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
-          const uint8_t* row = tile_s + ((size_t)(ry * S + ky) * p.TWI + xs * TX * S) * (CV * 16);
+          const uint32_t row_u = tile_u + t_off[k] + (uint32_t)ky * row_pitch;
 #pragma unroll
           for (int j = 0; j < NCOLS; ++j) {
-            const uint4 u = *reinterpret_cast<const uint4*>(row + (size_t)j * (CV * 16));
+            const uint4 u = tc::lds_u4(row_u + (uint32_t)(j * CV * 16));
             // bf16 pair -> packed f32 pair: low half << 16, high half masked
             const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
             uint64_t v[4];
@@ -154,14 +191,15 @@ dwconv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmX, const float* __res
 #pragma unroll
         for (int t = 0; t < TX; ++t) {
           if (ox0 + t < p.Wo) {
-            float o[8];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) f32x2_unpack(acc[t][e], o[2 * e], o[2 * e + 1]);
-            if (p.relu) {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) o[e] = fmaxf(o[e], 0.f);
+            uint4 o;
+            if (p.relu) {   // ReLU folded into the conversion (max(x, 0) then round == round then max)
+              o.x = cvt_relu_bf16x2(acc[t][0]); o.y = cvt_relu_bf16x2(acc[t][1]);
+              o.z = cvt_relu_bf16x2(acc[t][2]); o.w = cvt_relu_bf16x2(acc[t][3]);
+            } else {
+              o.x = cvt_bf16x2(acc[t][0]); o.y = cvt_bf16x2(acc[t][1]);
+              o.z = cvt_bf16x2(acc[t][2]); o.w = cvt_bf16x2(acc[t][3]);
             }
-            Vec8<bf16>::store(op + (size_t)t * p.C, o);
+            *reinterpret_cast<uint4*>(op + (size_t)t * p.C) = o;
           }
         }
       }
@@ -172,6 +210,11 @@ dwconv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmX, const float* __res
       if (next < spatial_tiles) issue(next, stage);
     }
     stage ^= 1;
+    tx += step_tx;
+    if (tx >= p.tiles_x) { tx -= p.tiles_x; ++ty; }
+    ty += step_ty;
+    if (ty >= p.tiles_y) { ty -= p.tiles_y; ++b; }
+    b += step_b;
   }
 }
 

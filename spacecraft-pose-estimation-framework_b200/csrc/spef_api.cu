@@ -900,6 +900,7 @@ static int launch_dw_tma_layer(spef_ctx* ctx, Layer& l, const void* in, void* ou
     if (cached_maps) l.plan_batch = B;
   }
   l.dwp.B = B;
+  if ((l.dwp.TW / l.dw_tx) * l.dwp.TH > 2 * 32) return fail(ctx, SPEF_ERR_INVALID, "depthwise tile plan of %s has more than two tasks per thread", l.prefix.c_str());
   const long long sp_tiles = (long long)B * l.dwp.tiles_y * l.dwp.tiles_x;
   const int per_sm = (l.dw_cv == 4) ? 4 : 2;
   // grid = nchunks * (CTAs per chunk): every chunk gets the same number of CTAs, at most the resident capacity
