@@ -158,5 +158,92 @@ __global__ void __launch_bounds__(384) resize_aa_kernel(const ResizeParams p) {
   }
 }
 
+// Greyscale fast path (SPEED's frames): the frame rows a band needs are staged in shared memory RB rows at a time with
+// 16-byte cp.async copies (double buffered), and a thread takes its 12-tap window as four aligned 32-bit words; the 22-bit
+// coefficients are split into three byte planes laid out on the same word grid, so that a row costs 4 LDS.32 + 12 DP4A
+// (u8 x u8 dot products, exact) instead of 12 byte loads + 12 IMAD -- the first version was bound by byte-load issue (LSU).
+// Requirements (host): one channel, fixed-window plan, src_w a multiple of 16, 16-byte aligned frames.
+struct GrayPlan {
+  const int* hword;        // [ow] index of the first aligned word of the window
+  const uint32_t* hplane;  // [3][4][ow] byte planes of the coefficients on the word grid (plane q = bits 8q .. 8q+7)
+};
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int RB>
+__global__ void __launch_bounds__(384) resize_aa_gray_kernel(const ResizeParams p, const GrayPlan g) {
+  extern __shared__ __align__(16) uint8_t gsm[];
+  const int stage_bytes = RB * p.sw + 16;                 // + one word the last window may over-read (zero coefficients)
+  uint8_t* stage = gsm;                                   // [2][stage_bytes]
+  uint8_t* filtered = gsm + 2 * stage_bytes;              // [max_rows][pitch]
+  const int b = blockIdx.y;
+  const int y0 = blockIdx.x * p.band, y1 = min(y0 + p.band, p.oh);
+  const int r0 = p.vfirst[y0];
+  const int r1 = p.vfirst[y1 - 1] + p.vcount[y1 - 1];
+  const uint8_t* img = p.src + (size_t)b * p.sh * p.sw;
+  const int nchunks = (r1 - r0 + RB - 1) / RB;
+  const uint32_t stage_u = (uint32_t)__cvta_generic_to_shared(stage);
+  const int vec_per_row = p.sw >> 4;
+  auto issue = [&](int c) {
+    const int rows = min(RB, r1 - r0 - c * RB);
+    const uint8_t* src = img + (size_t)(r0 + c * RB) * p.sw;   // RB consecutive rows are contiguous in the frame
+    const uint32_t dst = stage_u + (uint32_t)((c & 1) * stage_bytes);
+    for (int i = threadIdx.x; i < rows * vec_per_row; i += blockDim.x) cp_async16(dst + (uint32_t)i * 16u, src + (size_t)i * 16);
+    cp_async_commit();
+  };
+  issue(0);
+  for (int c = 0; c < nchunks; ++c) {
+    if (c + 1 < nchunks) { issue(c + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+    __syncthreads();
+    const int rows = min(RB, r1 - r0 - c * RB);
+    const uint32_t* sw32 = reinterpret_cast<const uint32_t*>(stage + (c & 1) * stage_bytes);
+    const int row_words = p.sw >> 2;
+    for (int xx = threadIdx.x; xx < p.ow; xx += blockDim.x) {
+      const int wi = g.hword[xx];
+      uint32_t k0[4], k1[4], k2[4];
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        k0[w] = g.hplane[(size_t)(0 * 4 + w) * p.ow + xx];
+        k1[w] = g.hplane[(size_t)(1 * 4 + w) * p.ow + xx];
+        k2[w] = g.hplane[(size_t)(2 * 4 + w) * p.ow + xx];
+      }
+      const uint32_t* px = sw32 + wi;
+      uint8_t* dst = filtered + (size_t)(c * RB) * p.pitch + xx;
+#pragma unroll 4
+      for (int rr = 0; rr < rows; ++rr, px += row_words, dst += p.pitch) {
+        const uint32_t w0 = px[0], w1 = px[1], w2 = px[2], w3 = px[3];
+        uint32_t s0 = __dp4a(w0, k0[0], 0u), s1 = __dp4a(w0, k1[0], 0u), s2 = __dp4a(w0, k2[0], 0u);
+        s0 = __dp4a(w1, k0[1], s0); s1 = __dp4a(w1, k1[1], s1); s2 = __dp4a(w1, k2[1], s2);
+        s0 = __dp4a(w2, k0[2], s0); s1 = __dp4a(w2, k1[2], s1); s2 = __dp4a(w2, k2[2], s2);
+        s0 = __dp4a(w3, k0[3], s0); s1 = __dp4a(w3, k1[3], s1); s2 = __dp4a(w3, k2[3], s2);
+        const int32_t acc = (int32_t)(s0 + (s1 << 8) + (s2 << 16)) + (1 << (kFixBits - 1));
+        *dst = clip8(acc);
+      }
+    }
+    __syncthreads();   // the buffer is refilled two chunks later
+  }
+
+  // pass 2 (same as resize_aa_kernel): filter along y from shared memory, replicate the grey plane three times
+  const size_t plane = (size_t)p.oh * p.ow;
+  for (int idx = threadIdx.x; idx < (y1 - y0) * p.ow; idx += blockDim.x) {
+    const int y = y0 + idx / p.ow, xx = idx % p.ow;
+    const int rb = p.vfirst[y] - r0, cnt = p.vcount[y];
+    const int32_t* kv = p.vcoef + (size_t)y * p.vks;
+    int32_t acc = 1 << (kFixBits - 1);
+    for (int j = 0; j < cnt; ++j) acc += (int32_t)filtered[(size_t)(rb + j) * p.pitch + xx] * kv[j];
+    const uint8_t v = clip8(acc);
+    const size_t o = (size_t)b * 3 * plane + (size_t)y * p.ow + xx;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      if (p.out_f32) reinterpret_cast<float*>(p.dst)[o + ch * plane] = __fdiv_rn((float)v, 255.0f);  // ToTensor
+      else reinterpret_cast<uint8_t*>(p.dst)[o + ch * plane] = v;
+    }
+  }
+}
+
 }  // namespace ingest
 }  // namespace spef

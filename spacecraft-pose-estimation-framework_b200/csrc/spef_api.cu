@@ -135,6 +135,7 @@ struct spef_ctx {
   float4* ori_tab = nullptr;
   float* ori_tab_soa = nullptr;  // [4][ori_tab_ld]: one plane per quaternion component, zero padded (decode_ori_stream_kernel)
   int ori_tab_ld = 0;
+  int rz_gray_kernel = 1;        // greyscale fast path of spef_resize_frames (SPEF_RESIZE_GRAY=0: generic kernel)
   int dw_small_plan = 1;         // task-filling tile plans for the 15x24 / 8x12 depthwise layers (SPEF_DW_SMALL=0: first plan)
   int decode_cfg = -1;           // -1: by batch size (launch_decode_stream)
   int decode_stream = 1;         // spef_decode_ori takes the streaming kernel for 16-byte aligned rows (SPEF_DECODE_STREAM=0: decode_ori_kernel)
@@ -177,7 +178,7 @@ struct spef_ctx {
   float* t_prev_video = nullptr;
   float* t_ws[8] = {nullptr};    // scratch outputs when the caller passes NULL
   // ingest plan (spef_resize_frames): taps of both axes for the last (src_h, src_w) seen, one device allocation
-  int rz_fixed = 0;
+  int rz_fixed = 0, rz_gray = 0, rz_gray_off = 0;
   int rz_sh = 0, rz_sw = 0, rz_hks = 0, rz_vks = 0, rz_band = 0, rz_max_rows = 0, rz_pitch = 0;
   int* rz_tab = nullptr;
   // bookkeeping
@@ -324,6 +325,7 @@ extern "C" int spef_create(spef_ctx** out, const spef_config* cfg) {
   ctx->smem_optin = prop.sharedMemPerBlockOptin;
   ctx->esz = (cfg->precision == SPEF_BF16) ? 2 : 4;
   if (const char* e4 = getenv("SPEF_GEMM_TRACE")) { ctx->trace_layer = atoi(e4); cudaMalloc((void**)&ctx->trace_dev, 256 * 16 * sizeof(long long)); }
+  if (const char* e17 = getenv("SPEF_RESIZE_GRAY")) ctx->rz_gray_kernel = atoi(e17);
   if (const char* e15 = getenv("SPEF_DW_SMALL")) ctx->dw_small_plan = atoi(e15);
   if (const char* e13 = getenv("SPEF_DECODE_CFG")) ctx->decode_cfg = atoi(e13);
   if (const char* e12 = getenv("SPEF_DECODE_STREAM")) ctx->decode_stream = atoi(e12);
@@ -1326,9 +1328,27 @@ static int resize_plan(spef_ctx* ctx, int sh, int sw, int C) {
   tab.insert(tab.end(), hfirst.begin(), hfirst.end());
   tab.insert(tab.end(), h.count.begin(), h.count.end());
   tab.insert(tab.end(), hcoef.begin(), hcoef.end());
+  // greyscale fast path (resize_aa_gray_kernel): first aligned word of every window and the coefficients as three byte planes
+  // on that word grid
+  ctx->rz_gray = (ctx->rz_fixed && sw % 16 == 0) ? 1 : 0;
+  std::vector<int> gword(ow, 0), gplane((size_t)12 * ow, 0);
+  if (ctx->rz_gray) {
+    for (int o = 0; o < ow; ++o) {
+      const int x0 = hfirst[o], sh4 = x0 & 3;
+      gword[o] = x0 >> 2;
+      for (int j = 0; j < ingest::KWIN; ++j) {
+        const unsigned k = (unsigned)hcoef[(size_t)j * ow + o];
+        const int pos = j + sh4, w = pos >> 2, bb = pos & 3;
+        for (int q = 0; q < 3; ++q) gplane[(size_t)(q * 4 + w) * ow + o] |= (int)(((k >> (8 * q)) & 0xffu) << (8 * bb));
+      }
+    }
+  }
   tab.insert(tab.end(), v.first.begin(), v.first.end());
   tab.insert(tab.end(), v.count.begin(), v.count.end());
   tab.insert(tab.end(), v.coef.begin(), v.coef.end());
+  ctx->rz_gray_off = (int)tab.size();
+  tab.insert(tab.end(), gword.begin(), gword.end());
+  tab.insert(tab.end(), gplane.begin(), gplane.end());
   cudaFree(ctx->rz_tab);
   ctx->rz_tab = nullptr;
   CK(cudaMalloc(&ctx->rz_tab, tab.size() * sizeof(int)));
@@ -1380,7 +1400,20 @@ extern "C" int spef_resize_frames(spef_ctx* ctx, const uint8_t* frames_dev, int3
   const size_t smem = (size_t)channels * p.max_rows * p.pitch;
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e;
-  if (ctx->rz_fixed) e = (channels == 1) ? launch_resize<ingest::KWIN, 1>(p, B, smem, st) : launch_resize<ingest::KWIN, 3>(p, B, smem, st);
+  constexpr int RB = 8;
+  const size_t gsmem = 2 * ((size_t)RB * src_w + 16) + (size_t)p.max_rows * p.pitch;
+  if (channels == 1 && ctx->rz_gray && ctx->rz_gray_kernel && (reinterpret_cast<uintptr_t>(frames_dev) & 15) == 0 && ((size_t)src_h * src_w) % 16 == 0 &&
+      gsmem <= ctx->smem_optin) {
+    ingest::GrayPlan g;
+    g.hword = ctx->rz_tab + ctx->rz_gray_off;
+    g.hplane = reinterpret_cast<const uint32_t*>(g.hword + ow);
+    e = cudaFuncSetAttribute(ingest::resize_aa_gray_kernel<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem);
+    if (e == cudaSuccess) {
+      const int threads = std::min(384, (ow + 31) & ~31);
+      ingest::resize_aa_gray_kernel<RB><<<dim3((oh + p.band - 1) / p.band, B), threads, gsmem, st>>>(p, g);
+      e = cudaGetLastError();
+    }
+  } else if (ctx->rz_fixed) e = (channels == 1) ? launch_resize<ingest::KWIN, 1>(p, B, smem, st) : launch_resize<ingest::KWIN, 3>(p, B, smem, st);
   else e = (channels == 1) ? launch_resize<0, 1>(p, B, smem, st) : launch_resize<0, 3>(p, B, smem, st);
   if (e != cudaSuccess) return fail(ctx, SPEF_ERR_CUDA, "launch of resize_aa_kernel failed: %s", cudaGetErrorString(e));
   ctx->launches++;
