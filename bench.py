@@ -394,7 +394,7 @@ def run_b200(args):
                 "how": f"algorithmic bytes (DESIGN.md section 5: a fused block reads x once and writes y once) / CUDA-event time of that launch on the "
                        f"launch stream, mean of {reps} passes after the timed region, same inputs",
                 "note": ("fused InvertedResidual kernel: the 6x hidden tensor never reaches HBM, so the launch is far below the HBM roof by design; "
-                         "its limiter is FP32 instruction issue on the CUDA cores (ncu: issue slots 65 %, fma pipe 42 %, DRAM 4 %), see "
+                         "its limiter is the per-warp latency of the worker warps (ncu source page: FP32 arithmetic is 16 % of the issued instructions, mbarrier polls over half; DRAM 7 %), see "
                          "profiles/ and DESIGN.md section 4.2; unfused_bytes is what the three per-layer kernels would move") if fused else None,
                 "unfused_bytes_per_launch": top.get("unfused_bytes")}
     tot_bytes, tot_flops = eng.forward_cost(B)

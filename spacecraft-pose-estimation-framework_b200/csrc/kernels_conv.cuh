@@ -262,7 +262,19 @@ __global__ void __launch_bounds__(256) global_mean_kernel(const T* __restrict__ 
   const int cg = tid % CG, b = tid / CG;
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   const T* p = in + (size_t)b * HW * C + cg * 8;
-  for (int i = 0; i < HW; ++i) {
+  // eight independent 16-byte loads in flight per thread, added in pixel order (same sums as a plain loop: the first
+  // version had one dependent load per iteration and ran at 2.4 TB/s)
+  int i = 0;
+  for (; i + 8 <= HW; i += 8) {
+    float v[8][8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) Vec8<T>::load(p + (size_t)(i + u) * C, v[u]);
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] += v[u][e];
+  }
+  for (; i < HW; ++i) {
     float v[8];
     Vec8<T>::load(p + (size_t)i * C, v);
 #pragma unroll

@@ -105,6 +105,7 @@ struct spef_ctx {
   int fb_max_cin = 64; // fuse blocks with Cin <= this (SPEF_FB_MAX_CIN); wider blocks measured faster as three kernels
   int stem_patch = 1;  // stem input patches staged by TMA (SPEF_STEM_PATCH=0: gather the 27 taps from global memory)
   int stem_prod = 2;   // im2col producer groups (128 threads each) of the tcgen05 stem (SPEF_STEM_PROD = 1 | 2)
+  int fbt_th_s2 = 0;   // force the tile height of the stride-2 channel-lane blocks (SPEF_FBT_TH_S2 = 3 | 4; 0: fewest hidden rows)
   int fbt_a2_bufs = 2; // A2 buffers per worker group of the channel-lane kernel where shared memory allows (SPEF_FBT_A2 = 1 | 2)
   int fbt_max_ng = 3;  // worker groups of the channel-lane kernel: 3 where TMEM / shared memory allow, else 2 (SPEF_FBT_NG)
   int fb_variant = 1;  // 1: channel-lane fused kernel where it applies, else the staged one; 0: staged kernel only (SPEF_FB_VARIANT)
@@ -340,6 +341,7 @@ extern "C" int spef_create(spef_ctx** out, const spef_config* cfg) {
   if (const char* e12 = getenv("SPEF_FB_VARIANT")) ctx->fb_variant = atoi(e12) ? 1 : 0;
   if (const char* e15 = getenv("SPEF_STEM_PATCH")) ctx->stem_patch = atoi(e15) ? 1 : 0;
   if (const char* e14 = getenv("SPEF_STEM_PROD")) { int v = atoi(e14); ctx->stem_prod = (v == 1 || v == 4) ? v : 2; }
+  if (const char* e18 = getenv("SPEF_FBT_TH_S2")) ctx->fbt_th_s2 = atoi(e18);
   if (const char* e16 = getenv("SPEF_FBT_A2")) ctx->fbt_a2_bufs = (atoi(e16) == 1) ? 1 : 2;
   if (const char* e13 = getenv("SPEF_FBT_NG")) ctx->fbt_max_ng = (atoi(e13) == 2) ? 2 : 3;
   if (const char* e10 = getenv("SPEF_FB_TRACE")) { ctx->fb_trace_block = atoi(e10); if (!ctx->trace_dev) cudaMalloc((void**)&ctx->trace_dev, 256 * 16 * sizeof(long long)); }
@@ -564,6 +566,7 @@ static int plan_blocks_t(spef_ctx* ctx) {
       if ((S == 1 && TH < 4) || (S == 2 && TH > 4)) continue;
       if (thi * TWI > 128 || TH * TW > 128) continue;
       const long long cost = (long long)cdiv(q.Ho, TH) * thi;   // hidden rows computed per image column of tiles
+      if (S == 2 && ctx->fbt_th_s2 > 0 && TH != ctx->fbt_th_s2) continue;
       if (best < 0 || cost < best) { best = cost; q.TH = TH; }
     }
     if (best < 0) continue;
@@ -756,6 +759,9 @@ extern "C" int spef_finalize_weights(spef_ctx* ctx) {
     }
     if (l.kind == K_PW || l.kind == K_HEAD) {
       l.block_n = tc::pick_block_n(l.n_pad);
+      // head GEMM: M = batch is at most a few 128-row tiles, so 256-column tiles would keep 14 CTAs busy at B = 256 (22.5 us to
+      // stream 4.4 MB of weights); 64-column tiles spread the same weights over 4x as many CTAs
+      if (l.kind == K_HEAD && ctx->gemm_impl == 2 && ctx->cfg.max_batch <= 2048 && !getenv("SPEF_HEAD_WIDE")) l.block_n = 64;
       if (ctx->gemm_impl == 2) {
         l.stages = tc::pick_stages_v2(l.block_n, l.n_pad, l.cin, ctx->smem_optin);
         l.smem = tc::smem_bytes_v2(l.block_n, l.stages, l.n_pad, l.cin);
