@@ -255,6 +255,10 @@ int spef_forward_timed(spef_ctx* ctx, const float* images_dev, int32_t batch, fl
 /* debug: the device-side 4x4 Jacobi eigen-solver compiled for the host (no GPU needed), so that the CPU
  * test-suite can pin it against LAPACK.  a_in row-major symmetric; evecs row-major with eigenvectors as columns. */
 int spef_debug_jacobi4_host(const double* a_in, double* evals, double* evecs);
+/* the tap tables spef_resize_frames builds on the host for one axis (first input sample, tap count, 22-bit fixed-point coefficients
+ * [out_size][*ksize_out]); coef_capacity = number of int32 the caller allocated for coef_out */
+int spef_debug_resize_taps_host(int32_t in_size, int32_t out_size, int32_t* first_out, int32_t* count_out, int32_t* coef_out,
+                                int32_t coef_capacity, int32_t* ksize_out);
 /* the eigen-solve of the large-batch decode kernel on the host: sums = {S, a00 a01 a02 a03 a11 a12 a13 a22 a23 a33} */
 int spef_debug_decode_solve_host(const double* sums, int32_t is_logits, float* quat, float* hinv);
 

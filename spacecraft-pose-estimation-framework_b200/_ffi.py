@@ -84,6 +84,7 @@ SIGNATURES = {
     "spef_forward_timed": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp]),
     "spef_debug_jacobi4_host": (C.c_int, [_vp, _vp, _vp]),
     "spef_debug_decode_solve_host": (C.c_int, [_vp, _i32, _vp, _vp]),
+    "spef_debug_resize_taps_host": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _i32, _vp]),
 }
 
 _lib: Optional[C.CDLL] = None

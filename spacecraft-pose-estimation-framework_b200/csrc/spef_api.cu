@@ -1954,6 +1954,19 @@ extern "C" int spef_forward_cost(const spef_ctx* ctx, int32_t B, double* bytes_o
   return SPEF_OK;
 }
 
+// debug: the host-side tap tables of spef_resize_frames (float64 coefficient computation, 22-bit rounding), so that the CPU
+// test-suite can pin them against the oracle / Pillow without a GPU.  coef_out holds out_size * ksize values (ksize returned).
+extern "C" int spef_debug_resize_taps_host(int32_t in_size, int32_t out_size, int32_t* first_out, int32_t* count_out, int32_t* coef_out,
+                                           int32_t coef_capacity, int32_t* ksize_out) {
+  if (in_size < 1 || out_size < 1 || !first_out || !count_out || !coef_out || !ksize_out) return SPEF_ERR_INVALID;
+  const ingest::AxisTaps t = ingest::make_axis_taps(in_size, out_size);
+  *ksize_out = t.ksize;
+  if ((long long)out_size * t.ksize > coef_capacity) return SPEF_ERR_INVALID;
+  for (int o = 0; o < out_size; ++o) { first_out[o] = t.first[o]; count_out[o] = t.count[o]; }
+  for (size_t i = 0; i < t.coef.size(); ++i) coef_out[i] = t.coef[i];
+  return SPEF_OK;
+}
+
 // debug: the eigen-solve of the streaming decode kernel (f32 Jacobi + f64 polish, cofactor inverse) compiled for the host
 extern "C" int spef_debug_decode_solve_host(const double* sums /*[11]*/, int32_t is_logits, float* quat /*[4]*/, float* hinv /*[16] or NULL*/) {
   if (!sums || !quat) return SPEF_ERR_INVALID;

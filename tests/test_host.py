@@ -125,6 +125,24 @@ def test_stream_decode_solver_matches_lapack(golden):
     assert lib.spef_debug_decode_solve_host(bad.ctypes.data, 1, q.ctypes.data, None) != 0
 
 
+def test_resize_tap_tables_match_oracle():
+    """The tap tables the library builds for spef_resize_frames (host code, float64) against the oracle's restatement of
+    Pillow's coefficient computation -- which tests/test_oracle_golden.py pins to the real torchvision + Pillow transform."""
+    import ctypes as C
+    lib = _ffi.lib()
+    for in_size, out_size in [(1920, 384), (1200, 240), (1200, 1200), (123, 240), (257, 384), (5000, 384), (3000, 240), (1, 7), (997, 384)]:
+        b, k = O.resize_coeffs(in_size, out_size)
+        first, count = np.zeros(out_size, np.int32), np.zeros(out_size, np.int32)
+        coef = np.zeros(out_size * k.shape[1], np.int32)
+        ks = C.c_int32(0)
+        assert lib.spef_debug_resize_taps_host(in_size, out_size, first.ctypes.data, count.ctypes.data, coef.ctypes.data, coef.size,
+                                               C.addressof(ks)) == 0
+        assert ks.value == k.shape[1]
+        np.testing.assert_array_equal(first, b[:, 0])
+        np.testing.assert_array_equal(count, b[:, 1])
+        np.testing.assert_array_equal(coef.reshape(out_size, -1), k)
+
+
 def test_arch_and_state_dict_spec(golden):
     spec = arch.state_dict_spec(1728, 3)
     assert len(spec) == 316 and len(arch.conv_layers()) == 52
