@@ -386,7 +386,68 @@ pw_gemm_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
       pst += PROD;
       if (pst >= PATCH_STAGES) { pst -= PATCH_STAGES; pphase ^= 1; }
     };
-    if (!p.patch_mode && tile0 < num_tiles) gather(tile0, cur);
+    if (p.patch_mode) {
+      // Lean loop for the TMA-staged patch (ncu's source page: 350 instructions per thread and tile in the generic loop below --
+      // two divisions by the chunk width, 27 single bf16 conversions, 13 byte-permute packs, 27 register copies).  Everything
+      // that depends only on the thread is computed once; adjacent taps are converted and packed by one cvt.rn.bf16x2.f32.
+      const int pr = t >> 6, pcx = t & 63;
+      const int colA = 2 * pcx + p.patch_x0 - 1, chA = colA / p.patch_w, inA = colA - chA * p.patch_w;
+      const int chB = (colA + 1) / p.patch_w, inB = colA + 1 - chB * p.patch_w;
+      const int cpix = p.patch_w * 15;   // pixels per chunk
+      const int oA = chA * cpix + inA + (2 * pr) * p.patch_w, oB = chB * cpix + inB + (2 * pr) * p.patch_w;
+      const uint32_t patch_u = smem_u32(patch_s);
+      const uint32_t sa_row = (uint32_t)t * 128u, swz = (uint32_t)t & 7u;
+      for (int tile = tile0; tile < num_tiles; tile += tstep) {
+        mbar_wait(smem_u32(&patch_full[pst]), pphase);
+        uint32_t pk[16];
+        if (p.img_u8) {
+          const uint8_t* pb = patch_s + (size_t)pst * PATCH_STAGE_BYTES;
+          uint16_t tap[28];
+#pragma unroll
+          for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+              const uint8_t* rowp = pb + (ci * 5 + ky) * p.patch_w;
+              tap[(ci * 3 + ky) * 3 + 0] = lut[rowp[oA]];
+              tap[(ci * 3 + ky) * 3 + 1] = lut[rowp[oB]];
+              tap[(ci * 3 + ky) * 3 + 2] = lut[rowp[oB + 1]];
+            }
+          tap[27] = 0;
+#pragma unroll
+          for (int k = 0; k < 14; ++k) pk[k] = (uint32_t)tap[2 * k] | ((uint32_t)tap[2 * k + 1] << 16);
+        } else {
+          const uint32_t pb = patch_u + (uint32_t)pst * (uint32_t)PATCH_STAGE_BYTES;
+          float f[28];
+#pragma unroll
+          for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+              const uint32_t rowu = pb + (uint32_t)((ci * 5 + ky) * p.patch_w) * 4u;
+              float v0, v1, v2;
+              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v0) : "r"(rowu + (uint32_t)oA * 4u));
+              asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v1), "=f"(v2) : "r"(rowu + (uint32_t)oB * 4u));   // 8-byte aligned
+              f[(ci * 3 + ky) * 3 + 0] = v0; f[(ci * 3 + ky) * 3 + 1] = v1; f[(ci * 3 + ky) * 3 + 2] = v2;
+            }
+          f[27] = 0.f;
+#pragma unroll
+          for (int k = 0; k < 14; ++k) asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pk[k]) : "f"(f[2 * k + 1]), "f"(f[2 * k]));
+        }
+        pk[14] = 0u; pk[15] = 0u;
+        mbar_arrive(smem_u32(&patch_empty[pst]));   // this thread's taps are in registers
+        pst += PROD;
+        if (pst >= PATCH_STAGES) { pst -= PATCH_STAGES; pphase ^= 1; }
+        mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+        const uint32_t sa = smem_u32(stage_base + (size_t)stage * sbytes) + sa_row;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          sts_u4(sa + (((uint32_t)c ^ swz) << 4), make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]));
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
+        mbar_arrive(smem_u32(&full_bar[stage]));
+        stage += PROD;
+        if (stage >= nstages) { stage -= nstages; phase ^= 1; }
+      }
+    } else {
+    if (tile0 < num_tiles) gather(tile0, cur);
     for (int tile = tile0; tile < num_tiles; tile += tstep) {
       // software pipeline: the taps of the next tile are in flight while this one is staged
       const int next = tile + tstep;
@@ -411,6 +472,7 @@ pw_gemm_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
 #pragma unroll
       for (int k = 0; k < 27; ++k) cur[k] = nxt[k];
     }
+    }
   } else if (warp >= FIRST_DRAIN_WARP && warp < FIRST_STORE_WARP) {
     // ===================== drain warps: TMEM -> registers -> bf16 -> staging ring =====================
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
@@ -420,6 +482,46 @@ pw_gemm_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     uint32_t acc_phase = 0;
     uint32_t box = 0;                       // global box counter: identical sequence in every drain / store warp
     int tm = (int)blockIdx.x / n_tiles, tn = (int)blockIdx.x % n_tiles;
+    if (PROD && NDG == 1 && !OUT_F32 && p.patch_mode && p.N == 32 && n_tiles == 1 && p.residual == nullptr && p.relu) {
+      // Stem: one 32-column box per tile.  Bias pairs live in registers, ReLU is folded into the conversion, no box bookkeeping.
+      uint64_t bias2[16];
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const float4 b4 = lds_f4(smem_u32(bias_s) + (uint32_t)g * 16u);
+        bias2[2 * g] = pack_f32x2(__float_as_uint(b4.x), __float_as_uint(b4.y));
+        bias2[2 * g + 1] = pack_f32x2(__float_as_uint(b4.z), __float_as_uint(b4.w));
+      }
+      const uint32_t srow = (uint32_t)row * (uint32_t)STAGING_PITCH;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++box) {
+        const int slot = (int)(box % V2_RING);
+        const uint32_t ring_phase = (box / V2_RING) & 1u;
+        mbar_wait(smem_u32(&tmem_full_bar[acc]), acc_phase);
+        tcgen05_fence_after();
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * acc_stride), v);
+        mbar_wait(smem_u32(&sempty_bar[slot]), ring_phase ^ 1);  // staging slot drained by the store warps
+        tmem_ld_wait();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
+        const uint32_t sb = smem_u32(staging + (size_t)slot * STAGING_BYTES) + srow;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint32_t o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const uint64_t sum = add_f32x2(pack_f32x2(v[g * 8 + 2 * e], v[g * 8 + 2 * e + 1]), bias2[g * 4 + e]);
+            uint32_t lo, hi;
+            asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(sum));
+            asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(o[e]) : "f"(__uint_as_float(hi)), "f"(__uint_as_float(lo)));
+          }
+          sts_u4(sb + (uint32_t)g * 16u, make_uint4(o[0], o[1], o[2], o[3]));
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&sfull_bar[slot]));
+        if (++acc == acc_stages) { acc = 0; acc_phase ^= 1; }
+      }
+    } else
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_idx = tm * BLOCK_M, n_idx = tn * block_n;
       const int m = m_idx + row;
@@ -535,6 +637,43 @@ pw_gemm_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     uint8_t* outb = reinterpret_cast<uint8_t*>(p.out);
     uint32_t box = 0;
     int tm = (int)blockIdx.x / n_tiles, tn = (int)blockIdx.x % n_tiles;
+    if (PROD && p.patch_mode && !OUT_F32 && p.N == 32 && n_tiles == 1) {
+      // Stem (32 channels = 64-byte rows): ncu's source page showed this role as the slowest of the kernel -- 338 instructions per
+      // tile, 130 of them IMAD (64-bit address arithmetic per store, two divisions per tile) with half of the lanes idle (the
+      // generic loop below assumes 128-byte rows).  Here: four 16-byte pieces per row so that every lane stores, per-thread byte
+      // offsets computed once, the (image, tile row, tile column) of the tile carried instead of divided.
+      const int pc4 = ts & 3, r04 = ts >> 2;
+      constexpr int RSTEP = NST / 4, NPASS = BLOCK_M / RSTEP;
+      uint32_t goff[NPASS], soff[NPASS];
+#pragma unroll
+      for (int k = 0; k < NPASS; ++k) {
+        const int r = r04 + k * RSTEP;          // row r of the tile = output pixel (2 ty + (r >> 6), 64 tx + (r & 63))
+        goff[k] = (uint32_t)((((r >> 6) * p.out_w + (r & 63)) * p.ldd + pc4 * 8) * 2);
+        soff[k] = (uint32_t)(r * STAGING_PITCH + pc4 * 16);
+      }
+      const int TXn = p.patch_tiles_x, TYn = p.out_h / 2, G = (int)gridDim.x;
+      int tx = tm % TXn, ty = (tm / TXn) % TYn, b = tm / (TXn * TYn);
+      const int d_tx = G % TXn, d_ty = (G / TXn) % TYn, d_b = G / (TXn * TYn);
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++box) {
+        const int slot = (int)(box % V2_RING);
+        const uint32_t ring_phase = (box / V2_RING) & 1u;
+        uint8_t* base = outb + ((size_t)(b * p.out_h + 2 * ty) * p.out_w + 64 * tx) * (size_t)(p.ldd * 2);
+        mbar_wait(smem_u32(&sfull_bar[slot]), ring_phase);
+        const uint32_t sbuf = smem_u32(staging + (size_t)slot * STAGING_BYTES);
+        uint4 val[NPASS];
+#pragma unroll
+        for (int k = 0; k < NPASS; ++k) val[k] = lds_u4(sbuf + soff[k]);
+#pragma unroll
+        for (int k = 0; k < NPASS; ++k) *reinterpret_cast<uint4*>(base + goff[k]) = val[k];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&sempty_bar[slot]));
+        tx += d_tx;
+        if (tx >= TXn) { tx -= TXn; ++ty; }
+        ty += d_ty;
+        if (ty >= TYn) { ty -= TYn; ++b; }
+        b += d_b;
+      }
+    } else
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_idx = tm * BLOCK_M, n_idx = tn * block_n;
       const int ncols = min(block_n, p.N - n_idx);
