@@ -577,6 +577,38 @@ pw_gemm_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
             o.w = __float_as_uint(__uint_as_float(v[g * 4 + 3]) + b4.w);
             sts_u4(sb + (uint32_t)g * 16u, o);
           }
+        } else if (p.residual == nullptr && c0 + COLS_PER_BOX <= ncols) {
+          // full box without skip connection: no per-piece bounds checks, ReLU folded into the conversion (cvt.rn.relu)
+          if (p.relu) {
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              const float4 b0 = lds_f4(bias_sa + (uint32_t)g * 32u);
+              const float4 b1 = lds_f4(bias_sa + (uint32_t)g * 32u + 16u);
+              const uint64_t bb[4] = {pack_f32x2(__float_as_uint(b0.x), __float_as_uint(b0.y)), pack_f32x2(__float_as_uint(b0.z), __float_as_uint(b0.w)),
+                                      pack_f32x2(__float_as_uint(b1.x), __float_as_uint(b1.y)), pack_f32x2(__float_as_uint(b1.z), __float_as_uint(b1.w))};
+              uint32_t o[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const uint64_t sum = add_f32x2(pack_f32x2(v[g * 8 + 2 * e], v[g * 8 + 2 * e + 1]), bb[e]);
+                uint32_t lo, hi;
+                asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(sum));
+                asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(o[e]) : "f"(__uint_as_float(hi)), "f"(__uint_as_float(lo)));
+              }
+              sts_u4(sb + (uint32_t)g * 16u, make_uint4(o[0], o[1], o[2], o[3]));
+            }
+          } else {
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              const float4 b0 = lds_f4(bias_sa + (uint32_t)g * 32u);
+              const float4 b1 = lds_f4(bias_sa + (uint32_t)g * 32u + 16u);
+              uint32_t o[4];
+              o[0] = cvt_bf16x2(add_f32x2(pack_f32x2(v[g * 8 + 0], v[g * 8 + 1]), pack_f32x2(__float_as_uint(b0.x), __float_as_uint(b0.y))));
+              o[1] = cvt_bf16x2(add_f32x2(pack_f32x2(v[g * 8 + 2], v[g * 8 + 3]), pack_f32x2(__float_as_uint(b0.z), __float_as_uint(b0.w))));
+              o[2] = cvt_bf16x2(add_f32x2(pack_f32x2(v[g * 8 + 4], v[g * 8 + 5]), pack_f32x2(__float_as_uint(b1.x), __float_as_uint(b1.y))));
+              o[3] = cvt_bf16x2(add_f32x2(pack_f32x2(v[g * 8 + 6], v[g * 8 + 7]), pack_f32x2(__float_as_uint(b1.z), __float_as_uint(b1.w))));
+              sts_u4(sb + (uint32_t)g * 16u, make_uint4(o[0], o[1], o[2], o[3]));
+            }
+          }
         } else if (p.residual == nullptr) {
           // packed path: f32x2 bias add, cvt to bf16x2, ReLU on the packed pair (round(max(x,0)) == max(round(x),0))
 #pragma unroll
@@ -701,6 +733,15 @@ pw_gemm_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
               *reinterpret_cast<uint4*>(outb + ((pix0 + (size_t)(r >> 6) * p.out_w + (r & 63)) * p.ldd + gcol) * ESZ) = val;
             }
           }
+        } else if (col_ok && rows_here == BLOCK_M) {
+          // full tile (all but the last M tile): loads first, then stores, 32-bit offsets from one 64-bit base (ncu's source page:
+          // the predicated loop below spent 197 instructions per box and thread, most of them address arithmetic)
+          const uint32_t gstep32 = (uint32_t)gstep;
+          uint4 val[1024 / NST];
+#pragma unroll
+          for (int k = 0; k < 1024 / NST; ++k) val[k] = lds_u4(sbuf + (uint32_t)((r0 + k * (NST / 8)) * STAGING_PITCH));
+#pragma unroll
+          for (int k = 0; k < 1024 / NST; ++k) *reinterpret_cast<uint4*>(gp + (uint32_t)k * gstep32) = val[k];
         } else if (col_ok) {
 #pragma unroll
           for (int k = 0; k < 1024 / NST; ++k) {
