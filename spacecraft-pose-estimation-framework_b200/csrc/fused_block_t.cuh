@@ -353,6 +353,10 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       tc::mbar_wait_relaxed(tc::smem_u32(&proj_full[ps]), pph, 512);
       tc::tcgen05_fence_after();
       if (warp == FIRST_EPI_WARP && lane == 0) FBT_TRACE(i * p.n_chunks, 13);
+      // ncu (wait sites of block 2): the project issuer polled proj_empty 21x per tile and the workers a2_empty 31x per item --
+      // both were waiting for THIS role, which released the accumulator only after its global stores.  With one strip and
+      // Cout <= 32 the accumulator row is a single tcgen05.ld: hand the TMEM stage back as soon as it is in registers.
+      const bool early = (p.stack == 1 && p.Cout <= 32);
       for (int st = 0; st < p.stack; ++st) {
       const int gy = oy0 + oy_l, gx = ox0 + st * TW + ox_l;
       const bool valid = (o < TH * TW) && gy < p.Ho && gx < p.Wo;
@@ -369,13 +373,21 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
           tc::tmem_ld_32x32b_x32(t_row + (uint32_t)c0, v);
         }
         tc::tmem_ld_wait();
+        if (early) {
+          tc::tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(tc::smem_u32(&proj_empty[ps]));
+        }
         if (valid) {
+          const uint32_t bias_u = tc::smem_u32(bp_s + c0);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             if (c0 + j * 8 < p.Cout) {
-              float f[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j * 8 + e]) + bp_s[c0 + j * 8 + e];
+              const float4 b0 = tc::lds_f4(bias_u + (uint32_t)j * 32u), b1 = tc::lds_f4(bias_u + (uint32_t)j * 32u + 16u);
+              float f[8] = {__uint_as_float(v[j * 8 + 0]) + b0.x, __uint_as_float(v[j * 8 + 1]) + b0.y,
+                            __uint_as_float(v[j * 8 + 2]) + b0.z, __uint_as_float(v[j * 8 + 3]) + b0.w,
+                            __uint_as_float(v[j * 8 + 4]) + b1.x, __uint_as_float(v[j * 8 + 5]) + b1.y,
+                            __uint_as_float(v[j * 8 + 6]) + b1.z, __uint_as_float(v[j * 8 + 7]) + b1.w};
               if (p.residual) {
                 float r[8];
                 Vec8<bf16>::load(rp + c0 + j * 8, r);
@@ -388,9 +400,11 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         }
       }
       }
-      tc::tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(tc::smem_u32(&proj_empty[ps]));
+      if (!early) {
+        tc::tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(tc::smem_u32(&proj_empty[ps]));
+      }
       if (warp == FIRST_EPI_WARP && lane == 0) FBT_TRACE(i * p.n_chunks, 14);
       if (++ps == p.proj_stages) { ps = 0; pph ^= 1u; }
     }
