@@ -609,16 +609,36 @@ def run_ingest(args):
 
     ms_dev = timed(frames_to_score, args.steps)
 
-    def e2e_step():
-        frames.copy_(host, non_blocking=True)
-        frames_to_score()
+    # end to end from pinned host frames: the H2D copy of step i + 1 (590 MB, PCIe) runs on a copy stream while step i computes
+    # (two device frame buffers, events in both directions)
+    dbuf = [frames, torch.empty_like(frames)]
+    copy_stream = torch.cuda.Stream(dev)
+    copied = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+    main = torch.cuda.current_stream(dev)
 
-    for _ in range(2):
-        e2e_step()
+    def submit_copy(i):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[i % 2])
+            dbuf[i % 2].copy_(host, non_blocking=True)
+            copied[i % 2].record(copy_stream)
+
+    def e2e_run(n):
+        for ev in consumed:
+            ev.record(main)
+        submit_copy(0)
+        for i in range(n):
+            if i + 1 < n:
+                submit_copy(i + 1)
+            main.wait_event(copied[i % 2])
+            assert eng.lib.spef_resize_frames(eng._h, ptr(dbuf[i % 2]), B, SH, SW, 1, ptr(out_u8), 1, st) == 0
+            consumed[i % 2].record(main)
+            eng.eval_batch(out_u8, qt, tt)
+
+    e2e_run(2)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()
+    e2e_run(args.steps)
     sums = eng.eval_read()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
@@ -645,7 +665,7 @@ def run_ingest(args):
           "config": {"workload": f"1200x1920 greyscale uint8 frames, batch {B}: spef_resize_frames -> uint8 [B,3,240,384] -> spef_eval_batch",
                      "l2": "inputs larger than L2 (590 MB of frames per step)"},
           "e2e": {"value": B * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(host.numel()), "d2h_bytes_per_step": 64,
-                  "api": "pinned host frames -> H2D -> spef_resize_frames -> spef_eval_batch, sums read back at the end"},
+                  "api": "pinned host frames -> H2D on a copy stream (double buffered, overlapping the previous step) -> spef_resize_frames -> spef_eval_batch, sums read back at the end"},
           "roofline": {"kernel": "resize_aa_kernel", "bound": "hbm", "achieved": alg / (ms_rz * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
                        "frac": alg / (ms_rz * 1e-3) / 1e9 / pk["hbm_gbs"], "traffic": None, "algorithmic_bytes_per_launch": alg,
                        "avg_launch_ms": ms_rz, "peak_source": pk["source"], "frames_per_s": B / (ms_rz * 1e-3)},
