@@ -82,7 +82,7 @@ __host__ __device__ inline int w_stage_bytes(int we_bytes, int cpad) { return we
 __host__ __device__ inline int x_stage_bytes(int kc_in, int n_px) { return kc_in * n_px * 128; }
 inline size_t smem_bytes(const FbtParams& p, int ng) {
   return 1024 + (size_t)p.x_stages * x_stage_bytes(p.kc_in, p.n_px) + (size_t)p.w_stages * w_stage_bytes(p.we_bytes, p.cpad) +
-         (size_t)ng * p.a2_bufs * A2_BYTES + 2048 /*bias*/ + 512 /*barriers*/;
+         (size_t)ng * p.a2_bufs * A2_BYTES + 1024 /*bias: cpad <= 128 floats, padded*/ + 512 /*barriers*/;
 }
 // Register budget per role when three worker groups share the SM.  setmaxnreg only moves registers inside the CTA's own
 // allocation (20 warps x 96 at launch), so 12 * WORKER + 4 * EPI + 4 * CTRL <= 20 * 96 = 1920 per lane: 1440 + 288 + 160 = 1888.
@@ -155,8 +155,8 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   uint8_t* x_s = smem;
   uint8_t* w_s = x_s + (size_t)p.x_stages * xsb;
   uint8_t* a2_s = w_s + (size_t)p.w_stages * wsb;             // [NG][a2_bufs][A2_BYTES]
-  float* bp_s = reinterpret_cast<float*>(a2_s + (size_t)NG * p.a2_bufs * A2_BYTES);   // [<= 512]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(bp_s + 512);
+  float* bp_s = reinterpret_cast<float*>(a2_s + (size_t)NG * p.a2_bufs * A2_BYTES);   // [256] (cpad <= 128)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bp_s + 256);
   uint64_t* x_full = bars;                        // [4]
   uint64_t* x_empty = x_full + 4;                 // [4]
   uint64_t* w_full = x_empty + 4;                 // [MAX_W_STAGES]
@@ -187,7 +187,7 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   itp.n_chunks = p.n_chunks; itp.x_stages = p.x_stages; itp.w_stages = p.w_stages; itp.resident = p.resident;
   itp.proj_stages = p.proj_stages; itp.n_acc = p.n_acc;
 
-  for (int i = threadIdx.x; i < 512; i += (int)blockDim.x) bp_s[i] = (i < p.cpad) ? p.bp[i] : 0.f;
+  for (int i = threadIdx.x; i < 256; i += (int)blockDim.x) bp_s[i] = (i < p.cpad) ? p.bp[i] : 0.f;
   if (warp == WARP_TMA && lane == 0) {
     tc::tma_prefetch_desc(&tmX);
     tc::tma_prefetch_desc(&tmWe);

@@ -591,6 +591,7 @@ static int plan_blocks_t(spef_ctx* ctx) {
           if (na * q.n_px + ps * pcols <= 512) { n_acc = na; pstages = ps; }
       if (!n_acc) continue;
       if (ng == 3 && n_acc < 4) continue;   // three groups on three stages leave no look-ahead for the expand MMA: measured slower than two groups
+      if (ng == 3 && pstages < 2) continue; // three groups behind ONE project accumulator stage: blocks 8-10 measured 57 -> 62 us
       q.n_acc = n_acc; q.acc_stride = q.n_px; q.proj_col0 = n_acc * q.n_px; q.proj_stages = pstages; q.proj_stride = (pstages == 2) ? pcols : 0;
       struct Opt { int w, res, x; };
       std::vector<Opt> opts;
