@@ -879,7 +879,6 @@ static int launch_cuda_core_layer(spef_ctx* ctx, const Layer& l, const void* in,
     }
     CK_LAUNCH("dwconv3x3_kernel");
   } else if (l.kind == K_POOL) {
-    const int total = B * (l.cin / 8);
     global_mean_kernel<T><<<B * cdiv(l.cin / 8, 32), 256, 0, st>>>((const T*)in, (T*)out, B, l.hin * l.win, l.cin);
     CK_LAUNCH("global_mean_kernel");
   } else {  // K_PW / K_HEAD on CUDA cores
