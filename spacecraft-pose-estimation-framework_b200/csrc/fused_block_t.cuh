@@ -535,7 +535,7 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         load_row(0, ra);
         load_row(1, rb);
         load_row(2, rc);
-        tc::mbar_wait(tc::smem_u32(&a2_empty[gsel]), kph ^ 1u);   // project MMA of this group's previous item has read A2
+        tc::mbar_wait_relaxed(tc::smem_u32(&a2_empty[gsel]), kph ^ 1u, 32);   // project MMA of this group's previous item has read A2
 #pragma unroll
         for (int y = 0; y < TH; y += 3) {
           if (y > 0) load_row(y + 2, rc);
@@ -548,7 +548,7 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         load_row(0, ra);
         load_row(1, rb);
         load_row(2, rc);
-        tc::mbar_wait(tc::smem_u32(&a2_empty[gsel]), kph ^ 1u);
+        tc::mbar_wait_relaxed(tc::smem_u32(&a2_empty[gsel]), kph ^ 1u, 32);
 #pragma unroll
         for (int y = 0; y < TH; y += 2) {
           if (y > 0) { load_row(2 * y + 1, rb); load_row(2 * y + 2, rc); }
