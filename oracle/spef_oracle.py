@@ -121,29 +121,30 @@ def folded_layers(sd) -> List[dict]:
     """Flat list of the 52 conv layers + meta, BN folded (float32)."""
     L = []
 
-    def add(prefix, kind, stride, act, residual=False):
+    def add(prefix, kind, stride, act, residual=False, block=None, role=None):
         w = sd[prefix + ".0.weight"]
         wf, bf = fold_bn(w, *_bn(sd, prefix + ".1"))
-        L.append(dict(prefix=prefix, kind=kind, stride=stride, act=act, residual=residual, w=wf, b=bf))
+        L.append(dict(prefix=prefix, kind=kind, stride=stride, act=act, residual=residual, w=wf, b=bf, block=block, role=role or kind))
 
     add("features.features.0", "stem", 2, True)
     for blk in block_table():
         p = f"features.features.{blk['idx']}.conv"
         j = 0
         if blk["expand"]:
-            add(f"{p}.{j}", "pw", 1, True)
+            add(f"{p}.{j}", "pw", 1, True, block=blk["idx"], role="expand")
             j += 1
-        add(f"{p}.{j}", "dw", blk["stride"], True)
+        add(f"{p}.{j}", "dw", blk["stride"], True, block=blk["idx"], role="dw")
         j += 1
-        add(f"{p}.{j}", "pw", 1, False, residual=blk["residual"])
+        add(f"{p}.{j}", "pw", 1, False, residual=blk["residual"], block=blk["idx"], role="project")
     add("features.features.18", "pw", 1, True)
     return L
 
 
-def apply_layer(layer: dict, x: torch.Tensor, res: Optional[torch.Tensor], bf16: bool) -> torch.Tensor:
+def apply_layer(layer: dict, x: torch.Tensor, res: Optional[torch.Tensor], bf16: bool, round_out: bool = True) -> torch.Tensor:
     """One folded conv layer on NCHW float32 tensors, optionally with BF16 rounding points:
     pointwise and stem weights (and the stem's image taps) rounded to bf16 (tensor-core operands), depthwise weights kept
-    f32, fp32 accumulate, +bias, ReLU, (+residual), output rounded to bf16."""
+    f32, fp32 accumulate, +bias, ReLU, (+residual), output rounded to bf16 (round_out=False: the expand output of a block whose
+    fused kernel keeps the hidden tensor in FP32 on the SM -- it never reaches HBM, so there is nothing to round for)."""
     w, b = layer["w"], layer["b"]
     if layer["kind"] in ("pw", "stem") and bf16:
         w = bf16_round(w)  # tensor-core operands (the stem runs as an implicit GEMM: image taps and weights in BF16)
@@ -156,11 +157,14 @@ def apply_layer(layer: dict, x: torch.Tensor, res: Optional[torch.Tensor], bf16:
         y = F.relu(y)
     if res is not None:
         y = res + y
-    return bf16_round(y) if bf16 else y
+    return bf16_round(y) if (bf16 and round_out) else y
 
 
-def forward_folded(sd, images: torch.Tensor, bf16: bool = False, return_layers: bool = False):
-    """BN-folded forward; bf16=True reproduces the CUDA BF16 path's rounding points."""
+def forward_folded(sd, images: torch.Tensor, bf16: bool = False, return_layers: bool = False, fp32_hidden_blocks=()):
+    """BN-folded forward; bf16=True reproduces the CUDA BF16 path's rounding points.  fp32_hidden_blocks: feature indices
+    (1..17) of the InvertedResidual blocks that run as a channel-lane fused kernel, whose hidden tensor (expand output) stays
+    FP32 between the expand GEMM and the depthwise taps (Engine.fp32_hidden_blocks())."""
+    fp32_hidden_blocks = set(fp32_hidden_blocks)
     outs = []
     with torch.no_grad():
         x = images
@@ -170,7 +174,7 @@ def forward_folded(sd, images: torch.Tensor, bf16: bool = False, return_layers: 
             if first_of_block:
                 block_in = x
             res = block_in if layer["residual"] else None
-            x = apply_layer(layer, x, res, bf16)
+            x = apply_layer(layer, x, res, bf16, round_out=not (layer["role"] == "expand" and layer["block"] in fp32_hidden_blocks))
             outs.append(x)
         f = x.mean([2, 3])
         wo, wp = sd["head.ori.1.weight"], sd["head.pos.0.weight"]

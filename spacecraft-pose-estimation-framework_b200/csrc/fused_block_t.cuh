@@ -84,9 +84,12 @@ inline size_t smem_bytes(const FbtParams& p, int ng) {
   return 1024 + (size_t)p.x_stages * x_stage_bytes(p.kc_in, p.n_px) + (size_t)p.w_stages * w_stage_bytes(p.we_bytes, p.cpad) +
          (size_t)ng * p.a2_bufs * A2_BYTES + 1024 /*bias: cpad <= 128 floats, padded*/ + 512 /*barriers*/;
 }
-// Register budget per role when three worker groups share the SM.  setmaxnreg only moves registers inside the CTA's own
-// allocation (20 warps x 96 at launch), so 12 * WORKER + 4 * EPI + 4 * CTRL <= 20 * 96 = 1920 per lane: 1440 + 288 + 160 = 1888.
-constexpr int REGS_WORKER = 120, REGS_EPI = 72, REGS_CTRL = 40;
+// Register budget per role (setmaxnreg only moves registers inside the CTA's own launch allocation; every count is a multiple
+// of 8 and each role is a whole warpgroup of four warps):
+//   three worker groups, 20 warps x 96 at launch : 12 * 120 + 4 * 72 + 4 * 40 = 1888 <= 1920
+//   two worker groups,   16 warps x 128 at launch:  8 * 184 + 4 * 88 + 4 * 56 = 2048
+// A first version that counted on the SM's unallocated registers deadlocked in setmaxnreg.inc.
+template <int NG> struct RegPlan { static constexpr int WORKER = (NG == 3) ? 120 : 184, EPI = (NG == 3) ? 72 : 88, CTRL = (NG == 3) ? 40 : 56; };
 template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 
@@ -98,6 +101,38 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&v)
         "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr)
       : "memory");
+}
+// tcgen05.wait::ld with the landing registers as in/out operands: the compiler cannot move a use of v[] above the wait
+__device__ __forceinline__ void tmem_ld_wait16(uint32_t (&v)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                 "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+               :: "memory");
+}
+// mbarrier wait that lets the hardware suspend the warp (try_wait with a suspend-time hint) instead of polling: the nanosleep
+// poll loops of the first version were ~25 % of all issued instructions of the kernel (ncu source page) on the same schedulers
+// as the arithmetic warps.  Still bounded: a protocol bug must trap, not hang the GPU box.
+__device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_hw(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait_hint(bar, parity, 1000000u)) return;
+  const long long t0 = clock64();
+  int it = 0;
+  while (!mbar_try_wait_hint(bar, parity, 1000000u)) {
+    if ((++it & 255) == 0 && clock64() - t0 > 4000000000LL) {
+      printf("spef: mbarrier timeout block %d thread %d\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
 }
 __device__ __forceinline__ float lds_f32(uint32_t saddr) {
   float r;
@@ -140,7 +175,7 @@ __device__ __forceinline__ uint32_t bias_relu_bf16x2(uint32_t a0, uint32_t a1, u
 
 // S: depthwise stride; TH: output rows of a tile (compile time: the row loop is fully unrolled, so the register window
 // rotates by renaming and every shared-memory store address is a constant)
-template <int S, int TH, int NG>
+template <int S, int TH, int NG, bool EXP>
 __global__ void __launch_bounds__(32 * (CTRL_WARPS + NG * GWT), 1)
 fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWe,
                      const __grid_constant__ CUtensorMap tmWp, const FbtParams p) {
@@ -235,11 +270,12 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     ox0 = (r - ty * p.tiles_x) * TW * p.stack;
   };
 
-  // NG == 3 (20 warps): the compiler's cap is 96 registers per thread; every role re-sizes its register file first
-  // (setmaxnreg at the top of each role's branch, so that the role's code is dominated by it)
+  // every role re-sizes its register file at the top of its own branch (ptxas budgets registers per setmaxnreg in program order:
+  // one common if / else chain of the three setmaxnreg in front of the roles made it allocate the worker loop with the control
+  // warps' 56 registers -- 1300 bytes of spills)
   if (warp == WARP_TMA) {
     // ===================== TMA producer =====================
-    if (NG == 3) reg_dec<REGS_CTRL>();
+    reg_dec<RegPlan<NG>::CTRL>();
     if (lane == 0) {
       const uint32_t x_tx = (uint32_t)(p.kc_in * P_in * 128);
       const uint32_t w_tx = (uint32_t)(p.we_bytes + 2 * p.cpad * 128 + AUX_BYTES);
@@ -247,7 +283,7 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         if (w.c == 0) {
           int b, oy0, ox0;
           tile_coords(w.i, b, oy0, ox0);
-          tc::mbar_wait_relaxed(tc::smem_u32(&x_empty[w.xs]), (uint32_t)(w.xph ^ 1), 256);
+          mbar_wait_hw(tc::smem_u32(&x_empty[w.xs]), (uint32_t)(w.xph ^ 1));
           const uint32_t fbar = tc::smem_u32(&x_full[w.xs]);
           tc::mbar_arrive_expect_tx(fbar, x_tx);
           for (int kc = 0; kc < p.kc_in; ++kc)
@@ -255,7 +291,7 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
                             (ox0 + (p.stack > 1 ? kc * TW : 0)) * S - 1, oy0 * S - 1, b, fbar);
         }
         if (!p.resident || w.i == 0) {
-          if (!p.resident) tc::mbar_wait_relaxed(tc::smem_u32(&w_empty[w.ws]), (uint32_t)(w.wph ^ 1), 256);
+          if (!p.resident) mbar_wait_hw(tc::smem_u32(&w_empty[w.ws]), (uint32_t)(w.wph ^ 1));
           const uint32_t fbar = tc::smem_u32(&w_full[w.ws]);
           uint8_t* dst = w_s + (size_t)w.ws * wsb;
           tc::mbar_arrive_expect_tx(fbar, w_tx);
@@ -271,7 +307,7 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     __syncwarp();
   } else if (warp == WARP_MMA) {
     // ===================== expand MMA issuer: D_e^T[128 ch, n_px] = We_chunk[128, Cin] * X[n_px, Cin]^T =====================
-    if (NG == 3) reg_dec<REGS_CTRL>();
+    reg_dec<RegPlan<NG>::CTRL>();
     const uint32_t idesc_e = tc::make_idesc_bf16(128, p.n_px);
     const uint32_t kst_last = (uint32_t)(((p.Cin - (p.kc_in - 1) * 64) + 15) / 16);
     const uint64_t a_base = tc::make_smem_desc_sw128(tc::smem_u32(w_s));
@@ -282,9 +318,9 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     for (fb::WorkIt w = fb::work_begin(); w.n < total; fb::work_next<NG>(w, itp)) {
       const int n = w.n;
       if (lane == 0) FBT_TRACE(n, 0);
-      if (w.c == 0) tc::mbar_wait_relaxed(tc::smem_u32(&x_full[w.xs]), (uint32_t)w.xph, 64);
-      tc::mbar_wait_relaxed(tc::smem_u32(&w_full[w.ws]), (uint32_t)w.wph, 64);
-      tc::mbar_wait_relaxed(tc::smem_u32(&acc_empty[w.as]), (uint32_t)(w.aph ^ 1), 64);
+      if (w.c == 0) mbar_wait_hw(tc::smem_u32(&x_full[w.xs]), (uint32_t)w.xph);
+      mbar_wait_hw(tc::smem_u32(&w_full[w.ws]), (uint32_t)w.wph);
+      mbar_wait_hw(tc::smem_u32(&acc_empty[w.as]), (uint32_t)(w.aph ^ 1));
       tc::tcgen05_fence_after();
       if (lane == 0) FBT_TRACE(n, 1);
       const uint64_t a0 = a_base + (uint64_t)((uint32_t)w.ws * w_step);
@@ -304,7 +340,7 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     }
   } else if (warp == WARP_MMA_P) {
     // ===================== project MMA issuer: D_p[128 px, cpad] += A2^T[128 ch, 128 px]^T * Wp_chunk[cpad, 128 ch]^T =====================
-    if (NG == 3) reg_dec<REGS_CTRL>();
+    reg_dec<RegPlan<NG>::CTRL>();
     const uint32_t idesc_p = make_idesc_bf16_amn(128, p.cpad);
     const uint64_t a_base = make_smem_desc_mn_sw128(tc::smem_u32(a2_s), A2_LBO, A2_SBO);
     const uint64_t b_base = tc::make_smem_desc_sw128(tc::smem_u32(w_s + (size_t)p.we_bytes));
@@ -312,10 +348,10 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     const uint32_t wp_half = (uint32_t)(p.cpad * 128) >> 4;
     for (fb::WorkIt w = fb::work_begin(); w.n < total; fb::work_next<NG>(w, itp)) {
       const int n = w.n;
-      if (w.c == 0) tc::mbar_wait_relaxed(tc::smem_u32(&proj_empty[w.ps]), (uint32_t)(w.pph ^ 1), 64);
+      if (w.c == 0) mbar_wait_hw(tc::smem_u32(&proj_empty[w.ps]), (uint32_t)(w.pph ^ 1));
       const int a2i = (p.a2_bufs == 2) ? 2 * w.g + w.kph : w.g;            // A2 buffer / barrier of this item
       const uint32_t a2ph = (uint32_t)((p.a2_bufs == 2) ? w.kph2 : w.kph);
-      tc::mbar_wait_relaxed(tc::smem_u32(&a2_full[a2i]), a2ph, 64);
+      mbar_wait_hw(tc::smem_u32(&a2_full[a2i]), a2ph);
       tc::tcgen05_fence_after();
       if (lane == 0) FBT_TRACE(n, 4);
       const uint64_t a0 = a_base + (uint64_t)((uint32_t)a2i * (uint32_t)(A2_BYTES >> 4));
@@ -341,7 +377,7 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     }
   } else if (warp >= FIRST_EPI_WARP && warp < FIRST_EPI_WARP + 4) {
     // ===================== epilogue: project accumulator -> +bias (+x) -> bf16 -> global =====================
-    if (NG == 3) reg_dec<REGS_EPI>();
+    reg_dec<RegPlan<NG>::EPI>();
     const int q = warp & 3;
     const int o = q * 32 + lane;                  // accumulator row = output pixel of the tile
     const int oy_l = o / TW, ox_l = o - oy_l * TW;
@@ -350,7 +386,7 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     for (int i = 0; i < my_tiles; ++i) {
       int b, oy0, ox0;
       tile_coords(i, b, oy0, ox0);
-      tc::mbar_wait_relaxed(tc::smem_u32(&proj_full[ps]), pph, 512);
+      mbar_wait_hw(tc::smem_u32(&proj_full[ps]), pph);
       tc::tcgen05_fence_after();
       if (warp == FIRST_EPI_WARP && lane == 0) FBT_TRACE(i * p.n_chunks, 13);
       // ncu (wait sites of block 2): the project issuer polled proj_empty 21x per tile and the workers a2_empty 31x per item --
@@ -410,7 +446,11 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     }
   } else if (warp < NG * GW) {
     // ===================== workers: one hidden channel per thread, TMEM -> depthwise -> A2^T =====================
-    if (NG == 3) reg_inc<REGS_WORKER>();
+    // The hidden tensor stays FP32 between the expand GEMM and the depthwise taps (it never leaves the SM, so rounding it to BF16
+    // would only cost instructions): h = relu(acc + be) is carried as h' = max(acc, -be) = h - be -- ONE FMNMX per hidden element --
+    // and the constant is folded into the depthwise bias on the host (bd' = bd + be * sum(w)).  A pixel outside the image must
+    // be h = 0 (zero padding of the hidden tensor), i.e. h' = -be.  The t = 1 block has no expand conv: h = x, nothing to do.
+    reg_inc<RegPlan<NG>::WORKER>();
     const int g = warp / GW;
     const int q = warp & 3;                         // TMEM lane quarter
     const int slot = q * 32 + lane;                 // channel slot of this thread = TMEM lane = K index of the project GEMM
@@ -420,24 +460,27 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     fb::WorkIt w = fb::work_begin();
     for (int s = 0; s < g && w.n < total; ++s) fb::work_next<NG>(w, itp);
     int cur_i = -1, cur_c = -1, b = 0, oy0 = 0, ox0 = 0;
-    float be = 0.f, bd = 0.f, wd[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    // A row of the hidden tile in registers.  S == 1: h[j] = column j.  S == 2: columns de-interleaved (e[i] = column 2i,
-    // o[i] = column 2i+1) so that horizontally adjacent OUTPUTS read adjacent registers (packed FFMA2 operands).
-    struct Row { float a[8]; float c[8]; };         // S == 1: a[i] = col 2i, c[i] = col 2i+1 as well (pairs (a[i], c[i]) are the bf16x2 words)
+    float nbe = 0.f, bd = 0.f, wd[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    // A row of the hidden tile in registers, columns de-interleaved: a[i] = column 2i, c[i] = column 2i+1.  S == 1: (a[i], c[i]) are
+    // horizontally adjacent pixels; S == 2: horizontally adjacent OUTPUTS read (a[2i], a[2i+1]) and (c[2i], c[2i+1]) -- adjacent
+    // registers either way (packed FFMA2 operands).
+    struct Row { float a[8]; float c[8]; };
     while (w.n < total) {
       const int n = w.n;
       if (w.i != cur_i) { cur_i = w.i; tile_coords(cur_i, b, oy0, ox0); }
       if (tg == 0) FBT_TRACE(n, 6);
-      tc::mbar_wait(tc::smem_u32(&w_full[w.ws]), (uint32_t)w.wph);
+      mbar_wait_hw(tc::smem_u32(&w_full[w.ws]), (uint32_t)w.wph);
       if (w.c != cur_c || !p.resident) {            // per-channel constants of this chunk
         cur_c = w.c;
         const uint32_t aux_u = tc::smem_u32(w_s + (size_t)w.ws * wsb + (size_t)p.we_bytes + (size_t)2 * p.cpad * 128) + (uint32_t)slot * 4u;
-        be = lds_f32(aux_u);
+        nbe = lds_f32(aux_u);
         bd = lds_f32(aux_u + CL * 4);
 #pragma unroll
         for (int k = 0; k < 9; ++k) wd[k] = lds_f32(aux_u + (uint32_t)((2 + k) * CL * 4));
       }
-      const uint64_t be2 = f32x2(be, be);
+      const float mv = EXP ? nbe : 0.f;             // value of a hidden pixel outside the image
+      // be * (sum of the top / bottom tap row's weights) with the sign that takes it out of bd (zero for the t = 1 block: be = 0)
+      const float dtop = EXP ? nbe * ((wd[0] + wd[1]) + wd[2]) : 0.f, dbot = EXP ? nbe * ((wd[6] + wd[7]) + wd[8]) : 0.f;
       const int ox0q = ox0 + ((q * p.stack) >> 2) * TW;      // stacked: quarter q works on strip q * stack / 4 of the tile
       const bool left_ok = (ox0q * S - 1) >= 0;
       const bool right_ok = (ox0q * S - 1 + TWI - 1) < p.W;
@@ -446,53 +489,33 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       const int gsel = (p.a2_bufs == 2) ? 2 * w.g + w.kph : w.g;            // A2 buffer / barrier of this item
       const uint32_t kph = (uint32_t)((p.a2_bufs == 2) ? w.kph2 : w.kph);
       const uint32_t a2_u = a2_u0 + (uint32_t)gsel * (uint32_t)A2_BYTES;
-      tc::mbar_wait(tc::smem_u32(&acc_full[as]), (uint32_t)w.aph);
+      mbar_wait_hw(tc::smem_u32(&acc_full[as]), (uint32_t)w.aph);
       tc::tcgen05_fence_after();
       if (tg == 0) FBT_TRACE(n, 7);
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.acc_stride);
       // bookkeeping of the next item now, so that it overlaps the arithmetic below
       for (int s = 0; s < NG && w.n < total; ++s) fb::work_next<NG>(w, itp);
 
-      // hidden pixel row r of the box -> relu(acc + be) rounded to BF16 (as f32), zero outside the image.
-      // (Issuing the tcgen05.ld of row r + 1 before converting row r -- a software pipeline over the nine TMEM loads of an
-      // item -- was measured: the 16 extra live registers spill in every instantiation and the step got 6 % slower.)
-      auto load_row = [&](int r, Row& h) {
-        const int gy = gy0 + r;
-        if (gy >= 0 && gy < p.H) {                 // uniform
-          uint32_t v[16];
-          tmem_ld_32x32b_x16(t_row + (uint32_t)(r * TWI), v);
-          tc::tmem_ld_wait();
+      // raw accumulator row -> h' (see above); the two halo columns -> mv when they lie outside the image.  Rows outside the image are
+      // NOT patched here (a uniform branch per row made ptxas fill the whole row with mv first: 13 moves per row): their TMEM
+      // content is finite (the TMA zero fill gives acc = 0), and emit_row drops their tap row instead.
+      auto convert = [&](const uint32_t (&v)[16], Row& h) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            if (2 * i < TWI) {
-              const uint32_t pk = bias_relu_bf16x2(v[2 * i], v[2 * i + 1], be2);
-              h.a[i] = __uint_as_float(pk << 16);
-              h.c[i] = __uint_as_float(pk & 0xffff0000u);
-            }
-          }
-          if (!left_ok) h.a[0] = 0.f;
-          if (!right_ok) { if ((TWI - 1) & 1) h.c[(TWI - 1) / 2] = 0.f; else h.a[(TWI - 1) / 2] = 0.f; }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) { h.a[i] = 0.f; h.c[i] = 0.f; }
+        for (int j = 0; j < TWI; ++j) {
+          const float x = __uint_as_float(v[j]);
+          const float y = EXP ? fmaxf(x, nbe) : x;
+          if (j & 1) h.c[j >> 1] = y; else h.a[j >> 1] = y;
         }
-        if (r == THI - 1) {
-          // last row of the item: every tcgen05.ld of this warp on the stage has completed (wait::ld after each) -> hand the TMEM
-          // stage back NOW, one or two emit_rows before the end of the item, so that the expand MMA of the item after next starts
-          // earlier (traces: the workers waited 270-780 cycles per item for acc_full)
-          tc::tcgen05_fence_before();
-          __syncwarp();
-          if (lane == 0) tc::mbar_arrive(tc::smem_u32(&acc_empty[as]));
+        if (EXP) {                                 // (t = 1: TMA zero fill outside the image is already h = 0)
+          if (!left_ok) h.a[0] = mv;
+          if (!right_ok) { if ((TWI - 1) & 1) h.c[(TWI - 1) / 2] = mv; else h.a[(TWI - 1) / 2] = mv; }
         }
       };
-      // column j of a row
-      auto col = [](const Row& h, int j) -> float { return (j & 1) ? h.c[j >> 1] : h.a[j >> 1]; };
       // one tap row (ky) into the accumulator pairs; per output the order is kx = 0, 1, 2 as in the per-layer kernel
-      auto tap_row = [&](const Row& h, int ky, uint64_t (&acc)[TW / 2]) {
-        const uint64_t w0 = f32x2(wd[ky * 3 + 0], wd[ky * 3 + 0]);
-        const uint64_t w2 = f32x2(wd[ky * 3 + 2], wd[ky * 3 + 2]);
-        const uint64_t w1 = f32x2(wd[ky * 3 + 1], wd[ky * 3 + 1]);
-        const float w1s = wd[ky * 3 + 1], w2s = wd[ky * 3 + 2];
+      auto tap_row = [&](const Row& h, const float w0s, const float w1s, const float w2s, uint64_t (&acc)[TW / 2]) {
+        const uint64_t w0 = f32x2(w0s, w0s);
+        const uint64_t w2 = f32x2(w2s, w2s);
+        const uint64_t w1 = f32x2(w1s, w1s);
 #pragma unroll
         for (int i = 0; i < TW / 2; ++i) {          // outputs x = 2i, 2i+1
           if (S == 1) {
@@ -515,61 +538,77 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
           }
         }
       };
-      // output row y (compile-time) of the tile from three hidden rows, stored as adjacent pixels of channel `slot`
+      // The tile's outputs of this channel as BF16 pairs (word k = pixels 2k, 2k+1 of the tile in row-major order), stored in
+      // whole 16-byte chunks (8 adjacent pixels): the lanes of a warp are 32 channel rows 128 bytes apart whose chunks the swizzle
+      // spreads over all banks, so a v4 store is four full 128-byte wavefronts (the 4- and 8-byte stores of the first version
+      // replayed 4x: ncu counted 59 % of the kernel's shared wavefronts as bank conflicts).
+      constexpr int NWORDS = TH * TW / 2;
+      uint32_t pk[NWORDS] = {};
+      auto flush = [&](int k0) {                     // words k0 .. k0+3 = pixels 2 k0 .. 2 k0 + 7
+        const uint32_t op = (uint32_t)(2 * k0);
+        const uint32_t u = (op >> 6) * (uint32_t)A2_LBO + (((op & 63u) >> 3) << 4);
+        tc::sts_u4(a2_u + (u ^ sw4), make_uint4(pk[k0], pk[k0 + 1], pk[k0 + 2], pk[k0 + 3]));
+      };
+      // output row y (compile-time) of the tile from three hidden rows
       auto emit_row = [&](int y, const Row& r0, const Row& r1, const Row& r2) {
+        // zero padding in y: when the top (only y = 0 of the image's first tile row) or the bottom tap row lies outside the image its
+        // hidden pixels are h = 0, i.e. the tap row contributes nothing: its three weights are dropped and be * (their sum), which the
+        // host folded into bd, is taken out again (dtop / dbot).  Rows further outside only feed outputs the epilogue discards.
+        float by = bd, t0 = wd[0], t1 = wd[1], t2 = wd[2], u0 = wd[6], u1 = wd[7], u2 = wd[8];
+        {
+          if (y == 0 && gy0 < 0) { t0 = 0.f; t1 = 0.f; t2 = 0.f; by += dtop; }
+          if (gy0 + S * y + 2 >= p.H) { u0 = 0.f; u1 = 0.f; u2 = 0.f; by += dbot; }
+        }
         uint64_t acc[TW / 2];
 #pragma unroll
-        for (int i = 0; i < TW / 2; ++i) acc[i] = f32x2(bd, bd);
-        tap_row(r0, 0, acc);
-        tap_row(r1, 1, acc);
-        tap_row(r2, 2, acc);
-        uint32_t pk[TW / 2];
+        for (int i = 0; i < TW / 2; ++i) acc[i] = f32x2(by, by);
+        tap_row(r0, t0, t1, t2, acc);
+        tap_row(r1, wd[3], wd[4], wd[5], acc);
+        tap_row(r2, u0, u1, u2, acc);
 #pragma unroll
-        for (int i = 0; i < TW / 2; ++i) pk[i] = cvt_relu_bf16x2(acc[i]);
-        constexpr int QUAD = (S == 1) ? 2 : 1;      // bf16x2 words per store: 4 pixels = 8 bytes never straddle a 16-byte chunk (y*TW % 4 == 0)
+        for (int i = 0; i < TW / 2; ++i) pk[y * (TW / 2) + i] = cvt_relu_bf16x2(acc[i]);
 #pragma unroll
-        for (int i = 0; i < TW / 2; i += QUAD) {
-          const uint32_t op = (uint32_t)(y * TW + 2 * i);
-          const uint32_t u = (op >> 6) * (uint32_t)A2_LBO + (((op & 63u) >> 3) << 4) + (op & 7u) * 2u;   // folds to a constant when y is
-          const uint32_t addr = a2_u + (u ^ sw4);
-          if (S == 1) sts_u2(addr, pk[i], pk[i + 1]); else sts_u1(addr, pk[i]);
+        for (int k0 = 0; k0 + 4 <= NWORDS; k0 += 4)   // chunks completed by this row
+          if (k0 + 4 > y * (TW / 2) && k0 + 4 <= (y + 1) * (TW / 2)) flush(k0);
+        if (y == TH - 1 && (NWORDS & 3)) {            // tail of the tile (TH * TW not a multiple of 8): 4-byte stores
+#pragma unroll
+          for (int k = NWORDS & ~3; k < NWORDS; ++k) {
+            const uint32_t op = (uint32_t)(2 * k);
+            const uint32_t u = (op >> 6) * (uint32_t)A2_LBO + (((op & 63u) >> 3) << 4) + (op & 7u) * 2u;
+            sts_u1(a2_u + (u ^ sw4), pk[k]);
+          }
         }
       };
-      (void)col;
 
-      Row ra, rb, rc;
-      if (S == 1) {
-        // rows rotate through (ra, rb, rc): output y uses input rows y, y+1, y+2
-        load_row(0, ra);
-        load_row(1, rb);
-        load_row(2, rc);
-        tc::mbar_wait_relaxed(tc::smem_u32(&a2_empty[gsel]), kph ^ 1u, 32);   // project MMA of this group's previous item has read A2
+      // Row pipeline: the TMEM load of row r + 1 is in flight while row r is converted and its output row computed (two 16-register
+      // landing buffers; tcgen05.wait::ld waits for every outstanding load, so the next load is issued right after the wait).
+      Row win[3];
+      uint32_t va[16], vb[16];
+      tmem_ld_32x32b_x16(t_row, va);
 #pragma unroll
-        for (int y = 0; y < TH; y += 3) {
-          if (y > 0) load_row(y + 2, rc);
-          emit_row(y, ra, rb, rc);
-          if (y + 1 < TH) { load_row(y + 3, ra); emit_row(y + 1, rb, rc, ra); }
-          if (y + 2 < TH) { load_row(y + 4, rb); emit_row(y + 2, rc, ra, rb); }
+      for (int r = 0; r < THI; ++r) {
+        if (r & 1) tmem_ld_wait16(vb); else tmem_ld_wait16(va);
+        if (r + 1 < THI) {
+          if (r & 1) tmem_ld_32x32b_x16(t_row + (uint32_t)((r + 1) * TWI), va);
+          else tmem_ld_32x32b_x16(t_row + (uint32_t)((r + 1) * TWI), vb);
+        } else {
+          // every tcgen05.ld of this warp on the stage has completed -> hand the TMEM stage back now
+          tc::tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(tc::smem_u32(&acc_empty[as]));
         }
-      } else {
-        // output y uses input rows 2y, 2y+1, 2y+2; the bottom row of one output is the top row of the next
-        load_row(0, ra);
-        load_row(1, rb);
-        load_row(2, rc);
-        tc::mbar_wait_relaxed(tc::smem_u32(&a2_empty[gsel]), kph ^ 1u, 32);
-#pragma unroll
-        for (int y = 0; y < TH; y += 2) {
-          if (y > 0) { load_row(2 * y + 1, rb); load_row(2 * y + 2, rc); }
-          emit_row(y, ra, rb, rc);
-          if (y + 1 < TH) {
-            load_row(2 * y + 3, rb);
-            load_row(2 * y + 4, ra);
-            emit_row(y + 1, rc, rb, ra);
-          }
+        // window slot of row r.  S == 1: output y reads rows y, y+1, y+2 -> slot r % 3.  S == 2: output y reads rows 2y, 2y+1, 2y+2;
+        // odd rows -> slot 1, even rows alternate between slots 0 and 2
+        const int sl = (S == 1) ? (r % 3) : ((r & 1) ? 1 : ((r >> 1) & 1) * 2);
+        if (r & 1) convert(vb, win[sl]); else convert(va, win[sl]);
+        if (r == 2) mbar_wait_hw(tc::smem_u32(&a2_empty[gsel]), kph ^ 1u);   // project MMA of this group's previous use of the A2 buffer
+        if (S == 1) {
+          if (r >= 2) { const int y = r - 2; emit_row(y, win[y % 3], win[(y + 1) % 3], win[(y + 2) % 3]); }
+        } else {
+          if (r >= 2 && !(r & 1)) { const int y = (r - 2) >> 1; emit_row(y, win[(y & 1) * 2], win[1], win[((y + 1) & 1) * 2]); }
         }
       }
       if (tg == 0) FBT_TRACE(n, 8);
-      // (the TMEM stage was handed back inside load_row, after the item's last row)
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // A2 (generic-proxy writes) -> visible to the tensor core
       fb::group_sync(g, GT);
       if (tg == 0) tc::mbar_arrive(tc::smem_u32(&a2_full[gsel]));
@@ -577,7 +616,7 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     }
   }
   else if (warp == WARP_ALLOC) {
-    if (NG == 3) reg_dec<REGS_CTRL>();
+    reg_dec<RegPlan<NG>::CTRL>();
   }
 #undef FBT_TRACE
   // ---- teardown ----

@@ -105,7 +105,6 @@ struct spef_ctx {
   int fb_max_cin = 64; // fuse blocks with Cin <= this (SPEF_FB_MAX_CIN); wider blocks measured faster as three kernels
   int stem_patch = 1;  // stem input patches staged by TMA (SPEF_STEM_PATCH=0: gather the 27 taps from global memory)
   int stem_prod = 2;   // im2col producer groups (128 threads each) of the tcgen05 stem (SPEF_STEM_PROD = 1 | 2)
-  int fbt_th_s2 = 0;   // force the tile height of the stride-2 channel-lane blocks (SPEF_FBT_TH_S2 = 3 | 4; 0: fewest hidden rows)
   int fbt_a2_bufs = 2; // A2 buffers per worker group of the channel-lane kernel where shared memory allows (SPEF_FBT_A2 = 1 | 2)
   int fbt_max_ng = 3;  // worker groups of the channel-lane kernel: 3 where TMEM / shared memory allow, else 2 (SPEF_FBT_NG)
   int fb_variant = 1;  // 1: channel-lane fused kernel where it applies, else the staged one; 0: staged kernel only (SPEF_FB_VARIANT)
@@ -341,7 +340,6 @@ extern "C" int spef_create(spef_ctx** out, const spef_config* cfg) {
   if (const char* e12 = getenv("SPEF_FB_VARIANT")) ctx->fb_variant = atoi(e12) ? 1 : 0;
   if (const char* e15 = getenv("SPEF_STEM_PATCH")) ctx->stem_patch = atoi(e15) ? 1 : 0;
   if (const char* e14 = getenv("SPEF_STEM_PROD")) { int v = atoi(e14); ctx->stem_prod = (v == 1 || v == 4) ? v : 2; }
-  if (const char* e18 = getenv("SPEF_FBT_TH_S2")) ctx->fbt_th_s2 = atoi(e18);
   if (const char* e16 = getenv("SPEF_FBT_A2")) ctx->fbt_a2_bufs = (atoi(e16) == 1) ? 1 : 2;
   if (const char* e13 = getenv("SPEF_FBT_NG")) ctx->fbt_max_ng = (atoi(e13) == 2) ? 2 : 3;
   if (const char* e10 = getenv("SPEF_FB_TRACE")) { ctx->fb_trace_block = atoi(e10); if (!ctx->trace_dev) cudaMalloc((void**)&ctx->trace_dev, 256 * 16 * sizeof(long long)); }
@@ -561,12 +559,11 @@ static int plan_blocks_t(spef_ctx* ctx) {
     q.cx = e.cin; q.stack = stack; q.kst_stack = has_exp ? cdiv(e.cin, 16) : 2;
     q.TW = TW; q.TWI = TWI;
     long long best = -1;
-    for (int TH = 3; TH <= 6; ++TH) {              // instantiated kernels: S = 1: TH 4..6, S = 2: TH 3..4
+    for (int TH = 4; TH <= 6; ++TH) {              // instantiated kernels: S = 1: TH 5..6, S = 2: TH 4
       const int thi = (TH - 1) * S + 3;
-      if ((S == 1 && TH < 4) || (S == 2 && TH > 4)) continue;
+      if ((S == 1 && TH < 5) || (S == 2 && TH > 4)) continue;
       if (thi * TWI > 128 || TH * TW > 128) continue;
       const long long cost = (long long)cdiv(q.Ho, TH) * thi;   // hidden rows computed per image column of tiles
-      if (S == 2 && ctx->fbt_th_s2 > 0 && TH != ctx->fbt_th_s2) continue;
       if (best < 0 || cost < best) { best = cost; q.TH = TH; }
     }
     if (best < 0) continue;
@@ -638,8 +635,11 @@ static int plan_blocks_t(spef_ctx* ctx) {
           for (int st = 0; st < stack; ++st) {       // per-slot project weights and depthwise constants, replicated per strip
             const int slot = st * LS + in_strip;
             for (int co = 0; co < q.Cout; ++co) wp[(size_t)co * q.n_chunks * fbt::CL + (size_t)c * fbt::CL + slot] = pj.h_wb[(size_t)co * Ch + ch];
-            a[slot] = has_exp ? e.h_bias[ch] : 0.f;
-            a[fbt::CL + slot] = d.h_bias[ch];
+            // the workers carry h' = h - be = max(acc, -be) (fused_block_t.cuh): row 0 = -be, row 1 = bd + be * sum(w)
+            double wsum = 0.0;
+            for (int k = 0; k < 9; ++k) wsum += (double)d.h_wdw[(size_t)k * Ch + ch];
+            a[slot] = has_exp ? -e.h_bias[ch] : 0.f;
+            a[fbt::CL + slot] = has_exp ? (float)((double)d.h_bias[ch] + (double)e.h_bias[ch] * wsum) : d.h_bias[ch];
             for (int k = 0; k < 9; ++k) a[(2 + k) * fbt::CL + slot] = d.h_wdw[(size_t)k * Ch + ch];
           }
         }
@@ -779,10 +779,11 @@ extern "C" int spef_finalize_weights(spef_ctx* ctx) {
     rcb = plan_blocks_t(ctx);
     if (rcb) return rcb;
 #define SPEF_FBT_ATTR(S_, TH_) \
-    CK(cudaFuncSetAttribute(fbt::fused_block_t_kernel<S_, TH_, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, so)); \
-    CK(cudaFuncSetAttribute(fbt::fused_block_t_kernel<S_, TH_, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, so));
-    SPEF_FBT_ATTR(1, 6) SPEF_FBT_ATTR(1, 5) SPEF_FBT_ATTR(1, 4) SPEF_FBT_ATTR(2, 4) SPEF_FBT_ATTR(2, 3)
+    CK(cudaFuncSetAttribute(fbt::fused_block_t_kernel<S_, TH_, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, so)); \
+    CK(cudaFuncSetAttribute(fbt::fused_block_t_kernel<S_, TH_, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, so));
+    SPEF_FBT_ATTR(1, 6) SPEF_FBT_ATTR(1, 5) SPEF_FBT_ATTR(2, 4)
 #undef SPEF_FBT_ATTR
+    CK(cudaFuncSetAttribute(fbt::fused_block_t_kernel<1, 6, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, so));
     CK(cudaFuncSetAttribute(fb::fused_block_kernel<1, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, so));
     CK(cudaFuncSetAttribute(fb::fused_block_kernel<2, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, so));
     CK(cudaFuncSetAttribute(fb::fused_block_kernel<1, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, so));
@@ -1068,14 +1069,16 @@ static int launch_fused_block_t(spef_ctx* ctx, Block& b, const void* in, void* o
   if (tiles >= (1 << 22)) return fail(ctx, SPEF_ERR_UNSUPPORTED, "fused block: %lld tiles exceed the 2^22 limit of the tile index arithmetic", tiles);
   const int grid = (int)(tiles < ctx->num_sms ? tiles : ctx->num_sms);
   const int nthr = 32 * (fbt::CTRL_WARPS + b.t_ng * fbt::GWT);
-#define SPEF_FBT_LAUNCH(S_, TH_) do { if (b.t_ng == 3) fbt::fused_block_t_kernel<S_, TH_, 3><<<grid, nthr, b.t_smem, st>>>(b.t_tmX, b.t_tmWe, b.t_tmWp, q); \
-                                      else fbt::fused_block_t_kernel<S_, TH_, 2><<<grid, nthr, b.t_smem, st>>>(b.t_tmX, b.t_tmWe, b.t_tmWp, q); } while (0)
+#define SPEF_FBT_LAUNCH(S_, TH_) do { if (b.t_ng == 3) fbt::fused_block_t_kernel<S_, TH_, 3, true><<<grid, nthr, b.t_smem, st>>>(b.t_tmX, b.t_tmWe, b.t_tmWp, q); \
+                                      else fbt::fused_block_t_kernel<S_, TH_, 2, true><<<grid, nthr, b.t_smem, st>>>(b.t_tmX, b.t_tmWe, b.t_tmWp, q); } while (0)
   const int S = L[b.i_dw].stride;
-  if (S == 1 && q.TH == 6) SPEF_FBT_LAUNCH(1, 6);
+  if (b.i_exp < 0) {   // t = 1 block: no expand conv (strip-stacked four ways, two worker groups)
+    if (!(S == 1 && q.TH == 6 && b.t_ng == 2)) return fail(ctx, SPEF_ERR_UNSUPPORTED, "fused block: no kernel instance for the t = 1 block with tile height %d", q.TH);
+    fbt::fused_block_t_kernel<1, 6, 2, false><<<grid, nthr, b.t_smem, st>>>(b.t_tmX, b.t_tmWe, b.t_tmWp, q);
+  }
+  else if (S == 1 && q.TH == 6) SPEF_FBT_LAUNCH(1, 6);
   else if (S == 1 && q.TH == 5) SPEF_FBT_LAUNCH(1, 5);
-  else if (S == 1 && q.TH == 4) SPEF_FBT_LAUNCH(1, 4);
   else if (S == 2 && q.TH == 4) SPEF_FBT_LAUNCH(2, 4);
-  else if (S == 2 && q.TH == 3) SPEF_FBT_LAUNCH(2, 3);
   else return fail(ctx, SPEF_ERR_UNSUPPORTED, "fused block: no kernel instance for stride %d tile height %d", S, q.TH);
 #undef SPEF_FBT_LAUNCH
   CK_LAUNCH("fused_block_t_kernel");

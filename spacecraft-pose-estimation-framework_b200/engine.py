@@ -195,6 +195,11 @@ class Engine:
         names = ("first_layer", "n_layers", "fused", "tile_h", "tile_w", "groups", "w_stages", "resident")
         return {n: x.value for n, x in zip(names, v)}
 
+    def fp32_hidden_blocks(self):
+        """Feature indices (1..17, the reference's `features.features.{i}`) of the blocks that run as a channel-lane fused kernel
+        in the current configuration: their hidden tensor stays FP32 on the SM (a rounding point the oracle needs to know)."""
+        return {i + 1 for i in range(self.num_blocks()) if self.block_info(i)["fused"] == 2}
+
     def set_fusion(self, on: bool):
         """True (default): InvertedResidual blocks run as one fused kernel each; False: per-layer kernels."""
         self._ck(self.lib.spef_set_fusion(self._h, 1 if on else 0))

@@ -58,20 +58,30 @@ def _oracle_layer_io(sd, x, bf16):
     return ios
 
 
-@pytest.mark.parametrize("precision,pw_impl", [("fp32", 0), ("bf16", 1), ("bf16", 0)])
-def test_every_layer_teacher_forced(sd, images, precision, pw_impl):
-    """Each of the 54 launches of the forward on the oracle's input for that layer (B = 2)."""
+def _spread(t, batch, pick):
+    """[len(pick), ...] -> [batch, ...]: the picked slots hold the oracle's images, every other slot a copy of the first."""
+    if batch == len(pick):
+        return t
+    full = t[:1].repeat(batch, *([1] * (t.dim() - 1)))
+    full[pick] = t
+    return full
+
+
+def _check_every_layer(sd, images, precision, pw_impl, batch, pick):
+    """Each of the 54 launches of the forward on the oracle's input for that layer.  batch / pick: the launch runs `batch` images,
+    the oracle checks the slots in `pick` (images are independent, so three slots of a 256-image launch -- first, middle, last --
+    cover what changes with the batch: persistent CTAs looping over many tiles, ring slots wrapping, tile tails)."""
     bf16 = precision == "bf16"
-    eng = _engine(sd, precision, pw_impl)
+    eng = _engine(sd, precision, pw_impl, max_batch=max(8, batch))
     dt = torch.bfloat16 if bf16 else torch.float32
-    x = images[:2]
+    x = images[:len(pick)]
     ios = _oracle_layer_io(sd, x, bf16)
     assert eng.num_layers() == len(ios) + 2
     worst = 0.0
     for i, (inp, res, want) in enumerate(ios):
         info = eng.layer_info(i)
-        got = eng.layer_forward(i, inp if i == 0 else nhwc(inp, dt), None if res is None else nhwc(res, dt))
-        got = got.float().cpu()
+        got = eng.layer_forward(i, _spread(inp if i == 0 else nhwc(inp, dt), batch, pick), None if res is None else _spread(nhwc(res, dt), batch, pick))
+        got = got[pick].float().cpu()
         want_nhwc = want.permute(0, 2, 3, 1).contiguous()
         assert got.shape == want_nhwc.shape, (i, info)
         scale = float(want_nhwc.abs().max())
@@ -87,35 +97,61 @@ def test_every_layer_teacher_forced(sd, images, precision, pw_impl):
         worst = max(worst, float(err.max()) / scale)
     # global mean (layer 52) and head GEMM (layer 53)
     last = ios[-1][2]
-    feat = last.permute(0, 2, 3, 1).reshape(2, -1, 1280).contiguous()
-    pooled = eng.layer_forward(52, feat.to(dt)).float().cpu()
+    feat = last.permute(0, 2, 3, 1).reshape(len(pick), -1, 1280).contiguous()
+    pooled = eng.layer_forward(52, _spread(feat.to(dt), batch, pick))[pick].float().cpu()
     want_pool = last.mean([2, 3])
     want_pool = O.bf16_round(want_pool) if bf16 else want_pool
     assert float((pooled - want_pool).abs().max()) <= (2 ** -7 if bf16 else 1e-5) * float(want_pool.abs().max())
     wo, wp = sd["head.ori.1.weight"], sd["head.pos.0.weight"]
     if bf16:
         wo, wp = O.bf16_round(wo), O.bf16_round(wp)
-    head = eng.layer_forward(53, want_pool.to(dt)).cpu()
+    head = eng.layer_forward(53, _spread(want_pool.to(dt), batch, pick))[pick].cpu()
     want_head = torch.cat([torch.nn.functional.linear(want_pool, wo, sd["head.ori.1.bias"]),
                            torch.nn.functional.linear(want_pool, wp, sd["head.pos.0.bias"])], dim=1)
     assert head.shape[1] == eng.layer_info(53)["cout"] >= want_head.shape[1]
     assert rel(head[:, :want_head.shape[1]].numpy(), want_head.numpy()) < 2e-5
     assert float(head[:, want_head.shape[1]:].abs().max() if head.shape[1] > want_head.shape[1] else 0.0) == 0.0
-    print(f"[{precision} pw_impl={pw_impl}] worst per-layer relative error {worst:.3e}")
+    print(f"[{precision} pw_impl={pw_impl} B={batch}] worst per-layer relative error {worst:.3e}")
 
 
-def _check_fused_blocks(sd, images):
+@pytest.mark.parametrize("precision,pw_impl", [("fp32", 0), ("bf16", 1), ("bf16", 0)])
+def test_every_layer_teacher_forced(sd, images, precision, pw_impl):
+    _check_every_layer(sd, images, precision, pw_impl, 2, [0, 1])
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_every_layer_teacher_forced_full_batch(sd, images, precision):
+    """The same gates inside a launch of the benchmark shape (B = 256): slots 0, 127 and 255 against the oracle."""
+    _check_every_layer(sd, images, precision, 0, 256, [0, 127, 255])
+
+
+def _oracle_block(layers, first, last, x, hidden_fp32):
+    """Oracle output of one InvertedResidual block (layers first..last) on NCHW input x with the rounding points of its kernel:
+    the channel-lane fused kernel keeps the hidden tensor (expand output) in FP32, everything else rounds every layer output."""
+    cur = x
+    for li in range(first, last + 1):
+        layer = layers[li]
+        cur = O.apply_layer(layer, cur, x if layer["residual"] else None, True,
+                            round_out=not (hidden_fp32 and layer["role"] == "expand"))
+    return cur
+
+
+def _check_fused_blocks(sd, images, batch=3, pick=None):
     """Every fused InvertedResidual kernel (expand -> depthwise -> project [+ x] in one launch) on the oracle's BF16 input of
-    that block (B = 3), both fused variants (staged / channel-lane).
-      * against the chain of per-layer kernels (each within 1 BF16 ulp of the oracle, test above): same rounding points; the
-        staged kernel also has the same FP32 accumulation order and is bit-identical, the channel-lane kernel permutes the K
-        order of the project GEMM, so a few outputs flip one BF16 rounding (<= 1 ulp, < 0.1 % of the elements);
-      * against the oracle: the hidden activations are not teacher-forced inside a block, so a 1-ulp flip of a hidden BF16
-        value (FP32 accumulation order) moves a few block outputs by a few output ulps: < 1 % of the elements may differ
-        and none by more than 16 BF16 ulp (floored at 2^-8 of the tensor scale)."""
-    eng = _engine(sd, "bf16", 0)
-    x = images[:3]
+    that block, both fused variants (staged / channel-lane).
+      * against the oracle WITH THE KERNEL'S ROUNDING POINTS (the staged kernel rounds the hidden tensor to BF16 like the
+        per-layer kernels, the channel-lane kernel keeps it in FP32): the depthwise outputs are not teacher-forced inside a block,
+        so a 1-ulp flip of a BF16 depthwise value (FP32 accumulation order) moves a few block outputs by a few output ulps:
+        < 1 % of the elements may differ and none by more than 16 BF16 ulp (floored at 2^-8 of the tensor scale);
+      * against the chain of per-layer kernels (each within 1 BF16 ulp of the oracle, test above): the staged kernel has the
+        same rounding points and FP32 accumulation order and is bit-identical; the channel-lane kernel differs by the hidden
+        tensor's BF16 rounding (2^-9 relative per hidden element), which is reported and bounded at 16 output ulp.
+    batch / pick: the images of the batch the oracle checks (the B = 256 test teacher-forces images 0, 127, 255 of a full batch)."""
+    eng = _engine(sd, "bf16", 0, max_batch=max(8, batch))
+    pick = list(range(batch)) if pick is None else pick
+    x = images[:len(pick)]
     ios = _oracle_layer_io(sd, x, True)
+    layers = O.folded_layers(sd)
     n_fused = {1: 0, 2: 0}
     for bi in range(eng.num_blocks()):
         info = eng.block_info(bi)
@@ -125,32 +161,43 @@ def _check_fused_blocks(sd, images):
             continue
         n_fused[info["fused"]] += 1
         first, last = info["first_layer"], info["first_layer"] + info["n_layers"] - 1
-        inp = nhwc(ios[first][0], torch.bfloat16)
-        want = ios[last][2].permute(0, 2, 3, 1).contiguous()
-        got = eng.block_forward(bi, inp).float().cpu()
+        inp = _spread(nhwc(ios[first][0], torch.bfloat16), batch, pick)
+        want = _oracle_block(layers, first, last, ios[first][0], hidden_fp32=(info["fused"] == 2)).permute(0, 2, 3, 1).contiguous()
+        got_full = eng.block_forward(bi, inp)
+        got = got_full[pick].float().cpu()
         assert got.shape == want.shape, (bi, info)
         cur = inp
         for li in range(first, last + 1):
             cur = eng.layer_forward(li, cur, inp if eng.layer_info(li)["residual"] else None)
-        chain = cur.float().cpu()
+        chain = cur[pick].float().cpu()
         scale = float(want.abs().max())
         if info["fused"] == 1:
             np.testing.assert_array_equal(got.numpy(), chain.numpy(), err_msg=f"block {bi} {info} vs per-layer kernels")
         else:
             err = (got - chain).abs()
             ulp = torch.maximum(chain.abs(), torch.tensor(scale * 2 ** -8)) * 2 ** -7
-            assert float((err / ulp).max()) <= 1.01, f"block {bi} {info} vs per-layer kernels: > 1 BF16 ulp"
-            assert float((err > 0).float().mean()) < 1e-3, f"block {bi} {info} vs per-layer kernels: too many elements differ"
+            print(f"block {bi}: channel-lane vs per-layer kernels (hidden tensor FP32 vs BF16): max {float((err / ulp).max()):.2f} ulp, "
+                  f"{float((err > 0).float().mean()):.3f} of the elements differ")
+            assert float((err / ulp).max()) <= 16.0, f"block {bi} {info} vs per-layer kernels: > 16 BF16 ulp"
         err = (got - want).abs()
         ulp = torch.maximum(want.abs(), torch.tensor(scale * 2 ** -8)) * 2 ** -7
         worst, frac_off = float((err / ulp).max()), float((err > 0).float().mean())
         assert worst <= 16.0, f"block {bi} {info} vs oracle: {worst:.2f} BF16 ulp"
         assert frac_off < 0.01, f"block {bi} {info} vs oracle: {frac_off:.4f} of the elements differ"
+        if batch != len(pick):   # every other slot holds a copy of image 0: bit-identical to slot pick[0]
+            ref0 = got_full[pick[0]]
+            assert all(torch.equal(got_full[j], ref0) for j in range(batch) if j not in pick), f"block {bi}: batch slots differ"
     return n_fused
 
 
 def test_fused_blocks_teacher_forced(sd, images):
     n = _check_fused_blocks(sd, images)
+    assert n[1] + n[2] >= 8, f"only {n} blocks are fused"
+
+
+def test_fused_blocks_teacher_forced_full_batch(sd, images):
+    """Every fused block inside a B = 256 launch: slots 0, 127, 255 against the oracle, all other slots bit-identical copies."""
+    n = _check_fused_blocks(sd, images, batch=256, pick=[0, 127, 255])
     assert n[1] + n[2] >= 8, f"only {n} blocks are fused"
 
 
@@ -193,9 +240,9 @@ def test_fp32_logits_vs_reference_golden(golden, images, tag, n_pos):
 
 def test_bf16_end_to_end(golden, sd, images):
     g = golden("network")
-    want_ori, want_pos = O.forward_folded(sd, images, bf16=True)
     tc = _engine(sd, "bf16", 0)
     simt = _engine(sd, "bf16", 1)
+    want_ori, want_pos = O.forward_folded(sd, images, bf16=True, fp32_hidden_blocks=tc.fp32_hidden_blocks())
     o_tc, p_tc = [t.cpu().numpy() for t in tc.forward(images)]
     o_si, p_si = [t.cpu().numpy() for t in simt.forward(images)]
     print(f"BF16 tcgen05 vs fake-BF16 oracle: logits {rel(o_tc, want_ori.numpy()):.2e} pos {rel(p_tc, want_pos.numpy()):.2e}; "
@@ -311,7 +358,7 @@ def test_full_batch_256_properties(sd):
     np.testing.assert_array_equal(a["argmax"].cpu().numpy()[:128], a["argmax"].cpu().numpy()[128:])
     assert np.abs(np.linalg.norm(qa, axis=1) - 1).max() < 1e-6 and not a["flags"].any()
     # 4 of the 256 against the fake-BF16 oracle (same rounding points)
-    want_ori, want_pos = O.forward_folded(sd, base[:4], bf16=True)
+    want_ori, want_pos = O.forward_folded(sd, base[:4], bf16=True, fp32_hidden_blocks=eng.fp32_hidden_blocks())
     o, p = eng.forward(x[:4])
     assert rel(o.cpu().numpy(), want_ori.numpy()) < 3e-2
     want_q, _ = O.ori_decode_batch(O.softmax(o.cpu().numpy()), O.ori_histogram(12)[0])
