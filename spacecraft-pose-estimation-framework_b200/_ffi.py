@@ -10,7 +10,7 @@ import os
 from typing import Optional
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, "libspef_b200.so")
+LIB_PATH = os.environ.get("SPEF_DEV_LIB") or os.path.join(_PKG_DIR, "libspef_b200.so")   # SPEF_DEV_LIB: developer A/B builds (tools_dev/build_variant.sh)
 
 SPEF_FP32, SPEF_BF16 = 0, 1
 FLAG_ORI_NAN, FLAG_POS_ZERO_SUM, FLAG_POS_NAN, FLAG_DOT_GT_1_01, FLAG_ENC_NAN = 1, 2, 4, 8, 16

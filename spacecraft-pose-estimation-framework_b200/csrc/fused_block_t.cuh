@@ -44,6 +44,8 @@ constexpr int A2_LBO = 16384;                // next 64-pixel block
 constexpr int CTRL_WARPS = 8;                // 4 epilogue warps + TMEM alloc, TMA producer, project issuer, expand issuer
 constexpr int MAX_W_STAGES = 8;
 constexpr int MAX_ACC = 4;
+constexpr int MAX_PROJ = 4;                  // project accumulator stages in TMEM: the project issuer -> epilogue -> project issuer round trip is
+                                             // ~2000 cycles of hand-off latency, so two stages capped small tiles at one per ~1000 cycles
 
 struct FbtParams {
   const bf16* x;       // block input  [B,H,W,Cin]  (residual source)
@@ -123,16 +125,27 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity
       : "memory");
   return ok != 0;
 }
+#ifndef SPEF_FBT_WAIT_MODE
+#define SPEF_FBT_WAIT_MODE 0   // build-time experiment knob: 0 lean try_wait spin, 1 try_wait with a 1 ms suspend hint, 2 nanosleep poll
+#endif
 __device__ __forceinline__ void mbar_wait_hw(uint32_t bar, uint32_t parity) {
+#if SPEF_FBT_WAIT_MODE == 1
   if (mbar_try_wait_hint(bar, parity, 1000000u)) return;
   const long long t0 = clock64();
   int it = 0;
   while (!mbar_try_wait_hint(bar, parity, 1000000u)) {
-    if ((++it & 255) == 0 && clock64() - t0 > 4000000000LL) {
-      printf("spef: mbarrier timeout block %d thread %d\n", blockIdx.x, threadIdx.x);
-      __trap();
-    }
+    if ((++it & 255) == 0 && clock64() - t0 > 4000000000LL) { printf("spef: mbarrier timeout block %d thread %d\n", blockIdx.x, threadIdx.x); __trap(); }
   }
+#elif SPEF_FBT_WAIT_MODE == 2
+  tc::mbar_wait_relaxed(bar, parity, 64);
+#else
+  // lean spin: try_wait suspends the warp in hardware for a system-dependent time and wakes on completion; bounded so that a
+  // protocol bug traps instead of hanging the GPU box
+  uint32_t it = 0;
+  while (!tc::mbar_try_wait(bar, parity)) {
+    if (++it > (1u << 26)) __trap();   // (no printf here: twelve inlined wait sites with a printf slow path each cost 5 KB of code in the hot loops)
+  }
+#endif
 }
 __device__ __forceinline__ float lds_f32(uint32_t saddr) {
   float r;
@@ -200,9 +213,9 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   uint64_t* acc_empty = acc_full + MAX_ACC;       // [MAX_ACC]  workers -> expand MMA
   uint64_t* a2_full = acc_empty + MAX_ACC;        // [NG][2]  workers -> project MMA
   uint64_t* a2_empty = a2_full + 2 * MAX_NGT;     // [NG][2]  project MMA -> workers
-  uint64_t* proj_full = a2_empty + 2 * MAX_NGT;   // [2]
-  uint64_t* proj_empty = proj_full + 2;           // [2]
-  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(proj_empty + 2);
+  uint64_t* proj_full = a2_empty + 2 * MAX_NGT;   // [MAX_PROJ]
+  uint64_t* proj_empty = proj_full + MAX_PROJ;    // [MAX_PROJ]
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(proj_empty + MAX_PROJ);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -233,7 +246,7 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       tc::mbar_init(tc::smem_u32(&x_full[i]), 1);
       tc::mbar_init(tc::smem_u32(&x_empty[i]), 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < MAX_PROJ; ++i) {
       tc::mbar_init(tc::smem_u32(&proj_full[i]), 1);
       tc::mbar_init(tc::smem_u32(&proj_empty[i]), 4);
     }

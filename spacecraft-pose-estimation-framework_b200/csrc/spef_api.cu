@@ -106,6 +106,7 @@ struct spef_ctx {
   int stem_patch = 1;  // stem input patches staged by TMA (SPEF_STEM_PATCH=0: gather the 27 taps from global memory)
   int stem_prod = 2;   // im2col producer groups (128 threads each) of the tcgen05 stem (SPEF_STEM_PROD = 1 | 2)
   int fbt_a2_bufs = 2; // A2 buffers per worker group of the channel-lane kernel where shared memory allows (SPEF_FBT_A2 = 1 | 2)
+  int fbt_max_pstages = 4; // project accumulator stages of the channel-lane kernel, as many as TMEM has columns for (SPEF_FBT_PSTAGES)
   int fbt_max_ng = 3;  // worker groups of the channel-lane kernel: 3 where TMEM / shared memory allow, else 2 (SPEF_FBT_NG)
   int fb_variant = 1;  // 1: channel-lane fused kernel where it applies, else the staged one; 0: staged kernel only (SPEF_FB_VARIANT)
   int fb_trace_block = -1;  // SPEF_FB_TRACE=<block index>: dump CTA-0 clock64 timestamps of that fused block to stderr
@@ -342,6 +343,7 @@ extern "C" int spef_create(spef_ctx** out, const spef_config* cfg) {
   if (const char* e14 = getenv("SPEF_STEM_PROD")) { int v = atoi(e14); ctx->stem_prod = (v == 1 || v == 4) ? v : 2; }
   if (const char* e16 = getenv("SPEF_FBT_A2")) ctx->fbt_a2_bufs = (atoi(e16) == 1) ? 1 : 2;
   if (const char* e13 = getenv("SPEF_FBT_NG")) ctx->fbt_max_ng = (atoi(e13) == 2) ? 2 : 3;
+  if (const char* e19 = getenv("SPEF_FBT_PSTAGES")) { int v = atoi(e19); ctx->fbt_max_pstages = (v >= 1 && v <= fbt::MAX_PROJ) ? v : fbt::MAX_PROJ; }
   if (const char* e10 = getenv("SPEF_FB_TRACE")) { ctx->fb_trace_block = atoi(e10); if (!ctx->trace_dev) cudaMalloc((void**)&ctx->trace_dev, 256 * 16 * sizeof(long long)); }
   build_layers(ctx);
 
@@ -584,12 +586,12 @@ static int plan_blocks_t(spef_ctx* ctx) {
       q.proj_sub = (stack == 2) ? ((q.cpad + 31) / 32) * 32 : q.cpad;   // (the epilogue reads 32 columns at a time when Cout > 16)
       int n_acc = 0, pstages = 0;
       for (int na = ng + 1; na >= ng && !n_acc; --na)
-        for (int ps = 2; ps >= 1 && !n_acc; --ps)
+        for (int ps = ctx->fbt_max_pstages; ps >= 1 && !n_acc; --ps)
           if (na * q.n_px + ps * pcols <= 512) { n_acc = na; pstages = ps; }
       if (!n_acc) continue;
       if (ng == 3 && n_acc < 4) continue;   // three groups on three stages leave no look-ahead for the expand MMA: measured slower than two groups
       if (ng == 3 && pstages < 2) continue; // three groups behind ONE project accumulator stage: blocks 8-10 measured 57 -> 62 us
-      q.n_acc = n_acc; q.acc_stride = q.n_px; q.proj_col0 = n_acc * q.n_px; q.proj_stages = pstages; q.proj_stride = (pstages == 2) ? pcols : 0;
+      q.n_acc = n_acc; q.acc_stride = q.n_px; q.proj_col0 = n_acc * q.n_px; q.proj_stages = pstages; q.proj_stride = (pstages >= 2) ? pcols : 0;
       struct Opt { int w, res, x; };
       std::vector<Opt> opts;
       // a stacked tile is four TMA boxes of 64-byte pixel rows (~2700 cycles): it must be prefetched behind the previous item
