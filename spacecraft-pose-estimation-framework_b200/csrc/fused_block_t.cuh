@@ -41,9 +41,11 @@ constexpr int AUX_STRIDE = 6144;
 constexpr int A2_BYTES = 32768;              // A2^T [128 ch][128 px] bf16, MN-major SWIZZLE_128B
 constexpr int A2_SBO = 1024;                 // 8 channels x 128 B
 constexpr int A2_LBO = 16384;                // next 64-pixel block
-constexpr int CTRL_WARPS = 8;                // 4 epilogue warps + TMEM alloc, TMA producer, project issuer, expand issuer
+constexpr int EPI_WARPS = 8;                 // two teams of four epilogue warps (one warp per TMEM lane quarter and team)
+constexpr int CTRL_WARPS = EPI_WARPS + 4;    // epilogue warps + TMEM alloc, TMA producer, project issuer, expand issuer
 constexpr int MAX_W_STAGES = 8;
 constexpr int MAX_ACC = 4;
+constexpr int N_PFULL = 8;                   // project-accumulator "full" barriers, one per tile modulo 8 (see the kernel)
 constexpr int MAX_PROJ = 4;                  // project accumulator stages in TMEM: the project issuer -> epilogue -> project issuer round trip is
                                              // ~2000 cycles of hand-off latency, so two stages capped small tiles at one per ~1000 cycles
 
@@ -87,11 +89,9 @@ inline size_t smem_bytes(const FbtParams& p, int ng) {
          (size_t)ng * p.a2_bufs * A2_BYTES + 1024 /*bias: cpad <= 128 floats, padded*/ + 512 /*barriers*/;
 }
 // Register budget per role (setmaxnreg only moves registers inside the CTA's own launch allocation; every count is a multiple
-// of 8 and each role is a whole warpgroup of four warps):
-//   three worker groups, 20 warps x 96 at launch : 12 * 120 + 4 * 72 + 4 * 40 = 1888 <= 1920
-//   two worker groups,   16 warps x 128 at launch:  8 * 184 + 4 * 88 + 4 * 56 = 2048
-// A first version that counted on the SM's unallocated registers deadlocked in setmaxnreg.inc.
-template <int NG> struct RegPlan { static constexpr int WORKER = (NG == 3) ? 120 : 184, EPI = (NG == 3) ? 72 : 88, CTRL = (NG == 3) ? 40 : 56; };
+// of 8 and each role is a whole warpgroup of four warps).  Two worker groups + two epilogue teams + control = 20 warps x 96 at launch:
+//   8 * 160 + 8 * 56 + 4 * 40 = 1888 <= 1920.   (A first version that counted on the SM's unallocated registers deadlocked in setmaxnreg.inc.)
+template <int NG> struct RegPlan { static constexpr int WORKER = 160, EPI = 56, CTRL = 40; };
 template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 
@@ -143,7 +143,7 @@ __device__ __forceinline__ void mbar_wait_hw(uint32_t bar, uint32_t parity) {
   // protocol bug traps instead of hanging the GPU box
   uint32_t it = 0;
   while (!tc::mbar_try_wait(bar, parity)) {
-    if (++it > (1u << 26)) __trap();   // (no printf here: twelve inlined wait sites with a printf slow path each cost 5 KB of code in the hot loops)
+    if (++it > (1u << 22)) __trap();   // (no printf here: twelve inlined wait sites with a printf slow path each cost 5 KB of code in the hot loops)
   }
 #endif
 }
@@ -213,22 +213,35 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   uint64_t* acc_empty = acc_full + MAX_ACC;       // [MAX_ACC]  workers -> expand MMA
   uint64_t* a2_full = acc_empty + MAX_ACC;        // [NG][2]  workers -> project MMA
   uint64_t* a2_empty = a2_full + 2 * MAX_NGT;     // [NG][2]  project MMA -> workers
-  uint64_t* proj_full = a2_empty + 2 * MAX_NGT;   // [MAX_PROJ]
-  uint64_t* proj_empty = proj_full + MAX_PROJ;    // [MAX_PROJ]
+  // proj_full is indexed by the TILE (i & 7), not by the TMEM stage: a consumer (epilogue warp / team) only sees every 2nd or
+  // 8th tile, and a parity wait on a barrier whose other phases belong to other consumers returns on a stale phase (ABA) -- with
+  // eight barriers every barrier has one consumer set, which observes each of its phases; 8 >= MAX_PROJ keeps the issuer from
+  // completing a barrier twice before it is consumed
+  uint64_t* proj_full = a2_empty + 2 * MAX_NGT;   // [N_PFULL]
+  uint64_t* proj_empty = proj_full + N_PFULL;     // [MAX_PROJ]
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(proj_empty + MAX_PROJ);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   constexpr int FIRST_EPI_WARP = NG * GW;
-  constexpr int WARP_ALLOC = NG * GW + 4, WARP_TMA = NG * GW + 5, WARP_MMA_P = NG * GW + 6, WARP_MMA = NG * GW + 7;
+  constexpr int WARP_ALLOC = NG * GW + EPI_WARPS, WARP_TMA = WARP_ALLOC + 1, WARP_MMA_P = WARP_ALLOC + 2, WARP_MMA = WARP_ALLOC + 3;
   constexpr int THI = (TH - 1) * S + 3;
+  constexpr int N_EPI = (TH * TW + 31) / 32;      // TMEM lane quarters that hold output pixels of a tile
+  // Tiles of at most 32 pixels (stride 2: 4 x 6) ROTATE through the four lane quarters: tile i of the CTA puts its pixels at
+  // accumulator rows 32 (i & 3) .. (the workers shift the A2 columns they write), so that eight epilogue warps work on eight
+  // different tiles at once.  Larger tiles keep row = pixel and split their strips (or alternate tiles) between the two teams.
+  constexpr bool ROT = (TH * TW <= 32);
   const int P_in = THI * TWI;
   const int tiles_per_img = p.tiles_y * p.tiles_x;
   const long long num_tiles = (long long)p.B * tiles_per_img;
   const int my_tiles = (int)((num_tiles - (long long)blockIdx.x + (long long)gridDim.x - 1) / (long long)gridDim.x);
   const int total = my_tiles * p.n_chunks;
+#ifdef SPEF_FBT_TRACE_BUILD   // clock64 trace of CTA 0 (tools_dev/build_variant.sh trace -DSPEF_FBT_TRACE_BUILD): compiled out of the product
   const bool tr = (p.trace != nullptr) && blockIdx.x == 0;
 #define FBT_TRACE(n_, slot_) do { if (tr && (n_) < 64) p.trace[(n_) * 16 + (slot_)] = clock64(); } while (0)
+#else
+#define FBT_TRACE(n_, slot_) do { } while (0)
+#endif
 
   // the WorkIt iterator of fused_block.cuh only needs these fields
   fb::FbParams itp;
@@ -246,10 +259,8 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       tc::mbar_init(tc::smem_u32(&x_full[i]), 1);
       tc::mbar_init(tc::smem_u32(&x_empty[i]), 1);
     }
-    for (int i = 0; i < MAX_PROJ; ++i) {
-      tc::mbar_init(tc::smem_u32(&proj_full[i]), 1);
-      tc::mbar_init(tc::smem_u32(&proj_empty[i]), 4);
-    }
+    for (int i = 0; i < N_PFULL; ++i) tc::mbar_init(tc::smem_u32(&proj_full[i]), 1);
+    for (int i = 0; i < MAX_PROJ; ++i) tc::mbar_init(tc::smem_u32(&proj_empty[i]), ROT ? 1 : (p.stack > 1 ? 2 * N_EPI : N_EPI));
     for (int i = 0; i < MAX_W_STAGES; ++i) {
       tc::mbar_init(tc::smem_u32(&w_full[i]), 1);
       tc::mbar_init(tc::smem_u32(&w_empty[i]), 1);
@@ -259,7 +270,7 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       tc::mbar_init(tc::smem_u32(&acc_empty[i]), GW);
     }
     for (int i = 0; i < 2 * NG; ++i) {
-      tc::mbar_init(tc::smem_u32(&a2_full[i]), 1);
+      tc::mbar_init(tc::smem_u32(&a2_full[i]), GW);   // one arrival per worker warp of the group
       tc::mbar_init(tc::smem_u32(&a2_empty[i]), 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -385,69 +396,88 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       }
       fb::commit_elect(tc::smem_u32(&a2_empty[a2i]));
       if (!p.resident) fb::commit_elect(tc::smem_u32(&w_empty[w.ws]));
-      if (w.c == p.n_chunks - 1) fb::commit_elect(tc::smem_u32(&proj_full[w.ps]));
+      if (w.c == p.n_chunks - 1) fb::commit_elect(tc::smem_u32(&proj_full[w.i & (N_PFULL - 1)]));
       if (lane == 0) FBT_TRACE(n, 5);
     }
-  } else if (warp >= FIRST_EPI_WARP && warp < FIRST_EPI_WARP + 4) {
+  } else if (warp >= FIRST_EPI_WARP && warp < FIRST_EPI_WARP + EPI_WARPS) {
     // ===================== epilogue: project accumulator -> +bias (+x) -> bf16 -> global =====================
+    // ncu (source page) and the clock64 traces showed this role, not the workers, pacing the kernel after the worker diet: one
+    // warp per lane quarter ran ~150 dependent instructions per tile (strip) at ~8-10 cycles each, and for the 24-pixel stride-2
+    // tiles only ONE of the four warps had pixels at all.  Now: eight warps in two teams; 24-pixel tiles rotate through the lane
+    // quarters (ROT) so that every warp owns every eighth tile; larger tiles split their strips (stacked) or alternate (one
+    // strip) between the teams; warps whose quarter holds no pixels leave at once; tile coordinates are carried, not divided.
     reg_dec<RegPlan<NG>::EPI>();
     const int q = warp & 3;
-    const int o = q * 32 + lane;                  // accumulator row = output pixel of the tile
+    const int team = (warp - FIRST_EPI_WARP) >> 2;
+    if (ROT || q < N_EPI) {
+    const int o = ROT ? lane : q * 32 + lane;     // output pixel of the tile held by this lane's accumulator row
     const int oy_l = o / TW, ox_l = o - oy_l * TW;
-    int ps = 0;
-    uint32_t pph = 0;
-    for (int i = 0; i < my_tiles; ++i) {
-      int b, oy0, ox0;
-      tile_coords(i, b, oy0, ox0);
-      mbar_wait_hw(tc::smem_u32(&proj_full[ps]), pph);
+    const bool lane_ok = o < TH * TW;
+    const int ng8 = p.Cout >> 3;                  // 8-channel groups (every Cout of the network is a multiple of 8)
+    // tiles of this warp: i = i0, i0 + step, ... (tile i of the CTA is global tile blockIdx.x + i * gridDim.x)
+    const int i0 = ROT ? (q + 4 * team) : (p.stack > 1 ? 0 : team);
+    const int step = ROT ? 8 : (p.stack > 1 ? 1 : 2);
+    int tb, ty, tx;
+    {
+      const long long t0 = (long long)blockIdx.x + (long long)i0 * gridDim.x;
+      tb = (int)(t0 / tiles_per_img);
+      const int r = (int)(t0 - (long long)tb * tiles_per_img);
+      ty = r / p.tiles_x; tx = r - ty * p.tiles_x;
+    }
+    const int gstep = step * (int)gridDim.x;
+    const int db = gstep / tiles_per_img, dr = gstep - db * tiles_per_img, dty = dr / p.tiles_x, dtx = dr - dty * p.tiles_x;
+    const int row_px = p.Wo, img_px = p.Ho * p.Wo;
+    // project accumulator stage of tile i: i % proj_stages -- carried
+    int ps = i0 % p.proj_stages;
+    const int ps_step = step % p.proj_stages;
+    for (int i = i0; i < my_tiles; i += step) {
+      const int oy0 = ty * TH, ox0 = tx * TW * p.stack;
+      const int gy = oy0 + oy_l;
+      const bool row_ok = lane_ok && gy < p.Ho;
+      const int pix0 = tb * img_px + gy * row_px + ox0 + ox_l;     // strip 0; strip st is st * TW pixels to the right
+      mbar_wait_hw(tc::smem_u32(&proj_full[i & (N_PFULL - 1)]), (uint32_t)((i >> 3) & 1));
       tc::tcgen05_fence_after();
       if (warp == FIRST_EPI_WARP && lane == 0) FBT_TRACE(i * p.n_chunks, 13);
-      // ncu (wait sites of block 2): the project issuer polled proj_empty 21x per tile and the workers a2_empty 31x per item --
-      // both were waiting for THIS role, which released the accumulator only after its global stores.  With one strip and
-      // Cout <= 32 the accumulator row is a single tcgen05.ld: hand the TMEM stage back as soon as it is in registers.
+      // one strip and Cout <= 32: the accumulator row is a single tcgen05.ld -- hand the TMEM stage back as soon as it is in registers
       const bool early = (p.stack == 1 && p.Cout <= 32);
-      for (int st = 0; st < p.stack; ++st) {
-      const int gy = oy0 + oy_l, gx = ox0 + st * TW + ox_l;
-      const bool valid = (o < TH * TW) && gy < p.Ho && gx < p.Wo;
-      const size_t pix = ((size_t)b * p.Ho + gy) * p.Wo + gx;
-      bf16* yp = p.y + pix * p.Cout;
-      const bf16* rp = p.x + pix * p.Cout;        // residual blocks: S == 1, Cin == Cout, same pixel
-      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(p.proj_col0 + ps * p.proj_stride + st * p.proj_sub);
-      for (int c0 = 0; c0 < p.Cout; c0 += 32) {
-        uint32_t v[32];
-        if (p.Cout - c0 <= 16) {   // never read past the accumulator's 16-column slot (the last one may end at TMEM column 512)
-          uint32_t(&v16)[16] = *reinterpret_cast<uint32_t(*)[16]>(&v[0]);
-          tmem_ld_32x32b_x16(t_row + (uint32_t)c0, v16);
-        } else {
-          tc::tmem_ld_32x32b_x32(t_row + (uint32_t)c0, v);
-        }
-        tc::tmem_ld_wait();
-        if (early) {
-          tc::tcgen05_fence_before();
-          __syncwarp();
-          if (lane == 0) tc::mbar_arrive(tc::smem_u32(&proj_empty[ps]));
-        }
-        if (valid) {
-          const uint32_t bias_u = tc::smem_u32(bp_s + c0);
+      const uint32_t t_tile = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(p.proj_col0 + ps * p.proj_stride);
+      for (int st = (p.stack > 1 ? team : 0); st < p.stack; st += (p.stack > 1 ? 2 : 1)) {
+        const bool valid = row_ok && (ox0 + st * TW + ox_l) < p.Wo;
+        const long long off = (long long)(pix0 + st * TW) * p.Cout;
+        bf16* yp = p.y + off;
+        const bf16* rp = p.x + off;               // residual blocks: S == 1, Cin == Cout, same pixel
+        const uint32_t t_row = t_tile + (uint32_t)(st * p.proj_sub);
+        for (int c0 = 0; c0 < p.Cout; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld_32x32b_x16(t_row + (uint32_t)c0, v);
+          tc::tmem_ld_wait();
+          if (early && c0 + 16 >= p.Cout) {
+            tc::tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(tc::smem_u32(&proj_empty[ps]));
+          }
+          if (valid) {
+            const uint32_t bias_u = tc::smem_u32(bp_s + c0);
+            const int nj = min(2, ng8 - (c0 >> 3));
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (c0 + j * 8 < p.Cout) {
-              const float4 b0 = tc::lds_f4(bias_u + (uint32_t)j * 32u), b1 = tc::lds_f4(bias_u + (uint32_t)j * 32u + 16u);
-              float f[8] = {__uint_as_float(v[j * 8 + 0]) + b0.x, __uint_as_float(v[j * 8 + 1]) + b0.y,
-                            __uint_as_float(v[j * 8 + 2]) + b0.z, __uint_as_float(v[j * 8 + 3]) + b0.w,
-                            __uint_as_float(v[j * 8 + 4]) + b1.x, __uint_as_float(v[j * 8 + 5]) + b1.y,
-                            __uint_as_float(v[j * 8 + 6]) + b1.z, __uint_as_float(v[j * 8 + 7]) + b1.w};
-              if (p.residual) {
-                float r[8];
-                Vec8<bf16>::load(rp + c0 + j * 8, r);
+            for (int j = 0; j < 2; ++j) {
+              if (j < nj) {
+                const float4 b0 = tc::lds_f4(bias_u + (uint32_t)j * 32u), b1 = tc::lds_f4(bias_u + (uint32_t)j * 32u + 16u);
+                float f[8] = {__uint_as_float(v[j * 8 + 0]) + b0.x, __uint_as_float(v[j * 8 + 1]) + b0.y,
+                              __uint_as_float(v[j * 8 + 2]) + b0.z, __uint_as_float(v[j * 8 + 3]) + b0.w,
+                              __uint_as_float(v[j * 8 + 4]) + b1.x, __uint_as_float(v[j * 8 + 5]) + b1.y,
+                              __uint_as_float(v[j * 8 + 6]) + b1.z, __uint_as_float(v[j * 8 + 7]) + b1.w};
+                if (p.residual) {
+                  float r[8];
+                  Vec8<bf16>::load(rp + c0 + j * 8, r);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) f[e] += r[e];
+                  for (int e = 0; e < 8; ++e) f[e] += r[e];
+                }
+                Vec8<bf16>::store(yp + c0 + j * 8, f);
               }
-              Vec8<bf16>::store(yp + c0 + j * 8, f);
             }
           }
         }
-      }
       }
       if (!early) {
         tc::tcgen05_fence_before();
@@ -455,7 +485,13 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         if (lane == 0) tc::mbar_arrive(tc::smem_u32(&proj_empty[ps]));
       }
       if (warp == FIRST_EPI_WARP && lane == 0) FBT_TRACE(i * p.n_chunks, 14);
-      if (++ps == p.proj_stages) { ps = 0; pph ^= 1u; }
+      // next tile of this warp
+      ps += ps_step;
+      if (ps >= p.proj_stages) ps -= p.proj_stages;
+      tx += dtx; ty += dty; tb += db;
+      if (tx >= p.tiles_x) { tx -= p.tiles_x; ++ty; }
+      if (ty >= p.tiles_y) { ty -= p.tiles_y; ++tb; }
+    }
     }
   } else if (warp < NG * GW) {
     // ===================== workers: one hidden channel per thread, TMEM -> depthwise -> A2^T =====================
@@ -472,7 +508,15 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     const uint32_t a2_u0 = tc::smem_u32(a2_s) + (uint32_t)((slot >> 3) * A2_SBO + (slot & 7) * 128);
     fb::WorkIt w = fb::work_begin();
     for (int s = 0; s < g && w.n < total; ++s) fb::work_next<NG>(w, itp);
-    int cur_i = -1, cur_c = -1, b = 0, oy0 = 0, ox0 = 0;
+    int cur_i = 0, cur_c = -1;
+    // tile row / column of tile cur_i of this CTA (global tile blockIdx.x + cur_i * gridDim.x), carried: the division-based
+    // tile_coords sat at the head of every item's dependent chain (~150 cycles)
+    int ty, tx;
+    {
+      const int r = (int)blockIdx.x % tiles_per_img;
+      ty = r / p.tiles_x; tx = r - ty * p.tiles_x;
+    }
+    const int dr1 = (int)gridDim.x % tiles_per_img, dty1 = dr1 / p.tiles_x, dtx1 = dr1 - dty1 * p.tiles_x;
     float nbe = 0.f, bd = 0.f, wd[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     // A row of the hidden tile in registers, columns de-interleaved: a[i] = column 2i, c[i] = column 2i+1.  S == 1: (a[i], c[i]) are
     // horizontally adjacent pixels; S == 2: horizontally adjacent OUTPUTS read (a[2i], a[2i+1]) and (c[2i], c[2i+1]) -- adjacent
@@ -480,10 +524,15 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     struct Row { float a[8]; float c[8]; };
     while (w.n < total) {
       const int n = w.n;
-      if (w.i != cur_i) { cur_i = w.i; tile_coords(cur_i, b, oy0, ox0); }
+      for (; cur_i < w.i; ++cur_i) {               // (at most NG steps)
+        tx += dtx1; ty += dty1;
+        if (tx >= p.tiles_x) { tx -= p.tiles_x; ++ty; }
+        if (ty >= p.tiles_y) ty -= p.tiles_y;
+      }
+      const int oy0 = ty * TH, ox0 = tx * TW * p.stack;
       if (tg == 0) FBT_TRACE(n, 6);
-      mbar_wait_hw(tc::smem_u32(&w_full[w.ws]), (uint32_t)w.wph);
-      if (w.c != cur_c || !p.resident) {            // per-channel constants of this chunk
+      if (w.c != cur_c || !p.resident) {            // per-channel constants of this chunk (one chunk, resident: read once per CTA)
+        mbar_wait_hw(tc::smem_u32(&w_full[w.ws]), (uint32_t)w.wph);
         cur_c = w.c;
         const uint32_t aux_u = tc::smem_u32(w_s + (size_t)w.ws * wsb + (size_t)p.we_bytes + (size_t)2 * p.cpad * 128) + (uint32_t)slot * 4u;
         nbe = lds_f32(aux_u);
@@ -501,7 +550,11 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       const int as = w.as;
       const int gsel = (p.a2_bufs == 2) ? 2 * w.g + w.kph : w.g;            // A2 buffer / barrier of this item
       const uint32_t kph = (uint32_t)((p.a2_bufs == 2) ? w.kph2 : w.kph);
-      const uint32_t a2_u = a2_u0 + (uint32_t)gsel * (uint32_t)A2_BYTES;
+      // ROT: tile i of the CTA writes its pixels at A2 columns (= accumulator rows) 32 (i & 3) ..: columns 64.. are the second
+      // 64-pixel block (LBO), columns 32..63 are 64 bytes into the 128-byte row, i.e. bit 6 of the swizzled chunk offset
+      const uint32_t rq = ROT ? (uint32_t)(cur_i & 3) : 0u;
+      const uint32_t a2_u = a2_u0 + (uint32_t)gsel * (uint32_t)A2_BYTES + (rq >> 1) * (uint32_t)A2_LBO;
+      const uint32_t swz = sw4 ^ ((rq & 1u) << 6);
       mbar_wait_hw(tc::smem_u32(&acc_full[as]), (uint32_t)w.aph);
       tc::tcgen05_fence_after();
       if (tg == 0) FBT_TRACE(n, 7);
@@ -560,7 +613,7 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       auto flush = [&](int k0) {                     // words k0 .. k0+3 = pixels 2 k0 .. 2 k0 + 7
         const uint32_t op = (uint32_t)(2 * k0);
         const uint32_t u = (op >> 6) * (uint32_t)A2_LBO + (((op & 63u) >> 3) << 4);
-        tc::sts_u4(a2_u + (u ^ sw4), make_uint4(pk[k0], pk[k0 + 1], pk[k0 + 2], pk[k0 + 3]));
+        tc::sts_u4(a2_u + (u ^ swz), make_uint4(pk[k0], pk[k0 + 1], pk[k0 + 2], pk[k0 + 3]));
       };
       // output row y (compile-time) of the tile from three hidden rows
       auto emit_row = [&](int y, const Row& r0, const Row& r1, const Row& r2) {
@@ -588,7 +641,7 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
           for (int k = NWORDS & ~3; k < NWORDS; ++k) {
             const uint32_t op = (uint32_t)(2 * k);
             const uint32_t u = (op >> 6) * (uint32_t)A2_LBO + (((op & 63u) >> 3) << 4) + (op & 7u) * 2u;
-            sts_u1(a2_u + (u ^ sw4), pk[k]);
+            sts_u1(a2_u + (u ^ swz), pk[k]);
           }
         }
       };
@@ -622,9 +675,11 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         }
       }
       if (tg == 0) FBT_TRACE(n, 8);
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // A2 (generic-proxy writes) -> visible to the tensor core
-      fb::group_sync(g, GT);
-      if (tg == 0) tc::mbar_arrive(tc::smem_u32(&a2_full[gsel]));
+      // A2 (generic-proxy writes) -> visible to the tensor core; every warp arrives for itself (the group barrier + single arrival
+      // of the first version kept each warp ~500 cycles per item waiting for the slowest of the four: clock64 trace)
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(tc::smem_u32(&a2_full[gsel]));
       if (tg == 0) FBT_TRACE(n, 12);
     }
   }

@@ -107,7 +107,6 @@ struct spef_ctx {
   int stem_prod = 2;   // im2col producer groups (128 threads each) of the tcgen05 stem (SPEF_STEM_PROD = 1 | 2)
   int fbt_a2_bufs = 2; // A2 buffers per worker group of the channel-lane kernel where shared memory allows (SPEF_FBT_A2 = 1 | 2)
   int fbt_max_pstages = 4; // project accumulator stages of the channel-lane kernel, as many as TMEM has columns for (SPEF_FBT_PSTAGES)
-  int fbt_max_ng = 3;  // worker groups of the channel-lane kernel: 3 where TMEM / shared memory allow, else 2 (SPEF_FBT_NG)
   int fb_variant = 1;  // 1: channel-lane fused kernel where it applies, else the staged one; 0: staged kernel only (SPEF_FB_VARIANT)
   int fb_trace_block = -1;  // SPEF_FB_TRACE=<block index>: dump CTA-0 clock64 timestamps of that fused block to stderr
   bool finalized = false;
@@ -342,7 +341,6 @@ extern "C" int spef_create(spef_ctx** out, const spef_config* cfg) {
   if (const char* e15 = getenv("SPEF_STEM_PATCH")) ctx->stem_patch = atoi(e15) ? 1 : 0;
   if (const char* e14 = getenv("SPEF_STEM_PROD")) { int v = atoi(e14); ctx->stem_prod = (v == 1 || v == 4) ? v : 2; }
   if (const char* e16 = getenv("SPEF_FBT_A2")) ctx->fbt_a2_bufs = (atoi(e16) == 1) ? 1 : 2;
-  if (const char* e13 = getenv("SPEF_FBT_NG")) ctx->fbt_max_ng = (atoi(e13) == 2) ? 2 : 3;
   if (const char* e19 = getenv("SPEF_FBT_PSTAGES")) { int v = atoi(e19); ctx->fbt_max_pstages = (v >= 1 && v <= fbt::MAX_PROJ) ? v : fbt::MAX_PROJ; }
   if (const char* e10 = getenv("SPEF_FB_TRACE")) { ctx->fb_trace_block = atoi(e10); if (!ctx->trace_dev) cudaMalloc((void**)&ctx->trace_dev, 256 * 16 * sizeof(long long)); }
   build_layers(ctx);
@@ -580,7 +578,7 @@ static int plan_blocks_t(spef_ctx* ctx) {
     // worker groups, TMEM expand stages (n_px columns each, one more than groups when they fit) and the project
     // accumulator(s) behind them; shared memory: resident weights before a ring, as many x stages as fit
     bool found = false;
-    for (int ng = (stack > 1) ? 2 : ctx->fbt_max_ng; ng >= 2 && !found; --ng) {
+    for (int ng = 2; ng >= 2 && !found; --ng) {   // (three worker groups never fit next to four TMEM expand stages with the shipped tile shapes)
       // stacked: the per-strip accumulators sit cpad columns apart (the epilogue's x32 load over-reads into the next one)
       const int pcols = (stack > 1) ? ((q.cpad * stack + 31) / 32) * 32 : ((q.cpad + 31) / 32) * 32;
       q.proj_sub = (stack == 2) ? ((q.cpad + 31) / 32) * 32 : q.cpad;   // (the epilogue reads 32 columns at a time when Cout > 16)
@@ -589,8 +587,6 @@ static int plan_blocks_t(spef_ctx* ctx) {
         for (int ps = ctx->fbt_max_pstages; ps >= 1 && !n_acc; --ps)
           if (na * q.n_px + ps * pcols <= 512) { n_acc = na; pstages = ps; }
       if (!n_acc) continue;
-      if (ng == 3 && n_acc < 4) continue;   // three groups on three stages leave no look-ahead for the expand MMA: measured slower than two groups
-      if (ng == 3 && pstages < 2) continue; // three groups behind ONE project accumulator stage: blocks 8-10 measured 57 -> 62 us
       q.n_acc = n_acc; q.acc_stride = q.n_px; q.proj_col0 = n_acc * q.n_px; q.proj_stages = pstages; q.proj_stride = (pstages >= 2) ? pcols : 0;
       struct Opt { int w, res, x; };
       std::vector<Opt> opts;
@@ -781,8 +777,7 @@ extern "C" int spef_finalize_weights(spef_ctx* ctx) {
     rcb = plan_blocks_t(ctx);
     if (rcb) return rcb;
 #define SPEF_FBT_ATTR(S_, TH_) \
-    CK(cudaFuncSetAttribute(fbt::fused_block_t_kernel<S_, TH_, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, so)); \
-    CK(cudaFuncSetAttribute(fbt::fused_block_t_kernel<S_, TH_, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, so));
+    CK(cudaFuncSetAttribute(fbt::fused_block_t_kernel<S_, TH_, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, so));
     SPEF_FBT_ATTR(1, 6) SPEF_FBT_ATTR(1, 5) SPEF_FBT_ATTR(2, 4)
 #undef SPEF_FBT_ATTR
     CK(cudaFuncSetAttribute(fbt::fused_block_t_kernel<1, 6, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, so));
@@ -1069,10 +1064,10 @@ static int launch_fused_block_t(spef_ctx* ctx, Block& b, const void* in, void* o
   if (trace) cudaMemsetAsync(ctx->trace_dev, 0, 256 * 16 * sizeof(long long), st);
   const long long tiles = (long long)B * q.tiles_y * q.tiles_x;
   if (tiles >= (1 << 22)) return fail(ctx, SPEF_ERR_UNSUPPORTED, "fused block: %lld tiles exceed the 2^22 limit of the tile index arithmetic", tiles);
+  if ((long long)B * q.Ho * q.Wo >= (1LL << 31)) return fail(ctx, SPEF_ERR_UNSUPPORTED, "fused block: %lld output pixels exceed the 32-bit pixel offsets of the epilogue", (long long)B * q.Ho * q.Wo);
   const int grid = (int)(tiles < ctx->num_sms ? tiles : ctx->num_sms);
   const int nthr = 32 * (fbt::CTRL_WARPS + b.t_ng * fbt::GWT);
-#define SPEF_FBT_LAUNCH(S_, TH_) do { if (b.t_ng == 3) fbt::fused_block_t_kernel<S_, TH_, 3, true><<<grid, nthr, b.t_smem, st>>>(b.t_tmX, b.t_tmWe, b.t_tmWp, q); \
-                                      else fbt::fused_block_t_kernel<S_, TH_, 2, true><<<grid, nthr, b.t_smem, st>>>(b.t_tmX, b.t_tmWe, b.t_tmWp, q); } while (0)
+#define SPEF_FBT_LAUNCH(S_, TH_) fbt::fused_block_t_kernel<S_, TH_, 2, true><<<grid, nthr, b.t_smem, st>>>(b.t_tmX, b.t_tmWe, b.t_tmWp, q)
   const int S = L[b.i_dw].stride;
   if (b.i_exp < 0) {   // t = 1 block: no expand conv (strip-stacked four ways, two worker groups)
     if (!(S == 1 && q.TH == 6 && b.t_ng == 2)) return fail(ctx, SPEF_ERR_UNSUPPORTED, "fused block: no kernel instance for the t = 1 block with tile height %d", q.TH);
