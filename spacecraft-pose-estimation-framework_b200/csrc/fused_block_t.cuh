@@ -79,13 +79,18 @@ struct FbtParams {
   int we_bytes;        // bytes of the expand-weight region of a weight stage: kc_in * 16 KB, or the 224-row window matrix (stack = 4):
                        // rows 96..127 of We' hold the identity, and strip q's A operand is the 128-row window starting at row
                        // 96 - 32 q (its quarter q sees the identity, the other quarters zeros) -- 28 KB instead of 4 x 16 KB
+  int wz_bytes;        // stack = 2: the window matrices of all chunks share their zero blocks -- ONE resident region
+                       // [Z | C0 | Z | C1 | ... | Z] of 64-row blocks (chunk c, strip 0: rows [C_c | Z], strip 1: rows [Z | C_c]) in front
+                       // of the weight stages, which then hold only Wp and the aux rows (we_bytes = 0): 16 KB less for three chunks,
+                       // which is what lets a second x stage fit (one x stage left the expand issuer waiting ~3000 cycles per tile
+                       // for the TMA load of the next tile: clock64 trace of block 3)
   long long* trace;
 };
 
 __host__ __device__ inline int w_stage_bytes(int we_bytes, int cpad) { return we_bytes + 2 * cpad * 128 + AUX_STRIDE; }
 __host__ __device__ inline int x_stage_bytes(int kc_in, int n_px) { return kc_in * n_px * 128; }
 inline size_t smem_bytes(const FbtParams& p, int ng) {
-  return 1024 + (size_t)p.x_stages * x_stage_bytes(p.kc_in, p.n_px) + (size_t)p.w_stages * w_stage_bytes(p.we_bytes, p.cpad) +
+  return 1024 + (size_t)p.x_stages * x_stage_bytes(p.kc_in, p.n_px) + (size_t)p.wz_bytes + (size_t)p.w_stages * w_stage_bytes(p.we_bytes, p.cpad) +
          (size_t)ng * p.a2_bufs * A2_BYTES + 1024 /*bias: cpad <= 128 floats, padded*/ + 512 /*barriers*/;
 }
 // Register budget per role (setmaxnreg only moves registers inside the CTA's own launch allocation; every count is a multiple
@@ -201,7 +206,8 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   const int xsb = x_stage_bytes(p.kc_in, p.n_px);
   const int wsb = w_stage_bytes(p.we_bytes, p.cpad);
   uint8_t* x_s = smem;
-  uint8_t* w_s = x_s + (size_t)p.x_stages * xsb;
+  uint8_t* wz_s = x_s + (size_t)p.x_stages * xsb;             // shared-zero expand weights (stack = 2), else empty
+  uint8_t* w_s = wz_s + (size_t)p.wz_bytes;
   uint8_t* a2_s = w_s + (size_t)p.w_stages * wsb;             // [NG][a2_bufs][A2_BYTES]
   float* bp_s = reinterpret_cast<float*>(a2_s + (size_t)NG * p.a2_bufs * A2_BYTES);   // [256] (cpad <= 128)
   uint64_t* bars = reinterpret_cast<uint64_t*>(bp_s + 256);
@@ -297,35 +303,58 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   // every role re-sizes its register file at the top of its own branch (ptxas budgets registers per setmaxnreg in program order:
   // one common if / else chain of the three setmaxnreg in front of the roles made it allocate the worker loop with the control
   // warps' 56 registers -- 1300 bytes of spills)
+  // The three single-warp roles below walk (tile, chunk) with plain nested loops and carried ring counters: the clock64 traces
+  // showed the expand issuer pacing the kernel at ~1300 cycles per item once the workers and the epilogue were out of the way --
+  // ~220 dependent instructions per item, most of them the generic work-item iterator and division-based tile coordinates.
   if (warp == WARP_TMA) {
     // ===================== TMA producer =====================
     reg_dec<RegPlan<NG>::CTRL>();
     if (lane == 0) {
       const uint32_t x_tx = (uint32_t)(p.kc_in * P_in * 128);
       const uint32_t w_tx = (uint32_t)(p.we_bytes + 2 * p.cpad * 128 + AUX_BYTES);
-      for (fb::WorkIt w = fb::work_begin(); w.n < total; fb::work_next<NG>(w, itp)) {
-        if (w.c == 0) {
-          int b, oy0, ox0;
-          tile_coords(w.i, b, oy0, ox0);
-          mbar_wait_hw(tc::smem_u32(&x_empty[w.xs]), (uint32_t)(w.xph ^ 1));
-          const uint32_t fbar = tc::smem_u32(&x_full[w.xs]);
+      int tb, ty, tx;
+      {
+        const int t0 = (int)blockIdx.x;
+        tb = t0 / tiles_per_img;
+        const int r = t0 - tb * tiles_per_img;
+        ty = r / p.tiles_x; tx = r - ty * p.tiles_x;
+      }
+      const int gdim = (int)gridDim.x;
+      const int db = gdim / tiles_per_img, dr = gdim - db * tiles_per_img, dty = dr / p.tiles_x, dtx = dr - dty * p.tiles_x;
+      int xs = 0, ws = 0;
+      uint32_t xph = 0, wph = 0;
+      for (int i = 0; i < my_tiles; ++i) {
+        const int oy0 = ty * TH, ox0 = tx * TW * p.stack;
+        mbar_wait_hw(tc::smem_u32(&x_empty[xs]), xph ^ 1u);
+        {
+          const uint32_t fbar = tc::smem_u32(&x_full[xs]);
           tc::mbar_arrive_expect_tx(fbar, x_tx);
           for (int kc = 0; kc < p.kc_in; ++kc)
-            dw::tma_load_4d(tc::smem_u32(x_s + (size_t)w.xs * xsb + (size_t)kc * p.n_px * 128), &tmX, p.stack > 1 ? 0 : kc * 64,
-                            (ox0 + (p.stack > 1 ? kc * TW : 0)) * S - 1, oy0 * S - 1, b, fbar);
+            dw::tma_load_4d(tc::smem_u32(x_s + (size_t)xs * xsb + (size_t)kc * p.n_px * 128), &tmX, p.stack > 1 ? 0 : kc * 64,
+                            (ox0 + (p.stack > 1 ? kc * TW : 0)) * S - 1, oy0 * S - 1, tb, fbar);
         }
-        if (!p.resident || w.i == 0) {
-          if (!p.resident) mbar_wait_hw(tc::smem_u32(&w_empty[w.ws]), (uint32_t)(w.wph ^ 1));
-          const uint32_t fbar = tc::smem_u32(&w_full[w.ws]);
-          uint8_t* dst = w_s + (size_t)w.ws * wsb;
-          tc::mbar_arrive_expect_tx(fbar, w_tx);
-          if (p.stack > 1) tc::tma_load_2d(tc::smem_u32(dst), &tmWe, 0, w.c * (p.we_bytes >> 7), fbar);   // one box: the window matrix of chunk c
-          else for (int kc = 0; kc < p.kc_in; ++kc) tc::tma_load_2d(tc::smem_u32(dst + (size_t)kc * CL * 128), &tmWe, kc * 64, w.c * CL, fbar);
-          uint8_t* wp = dst + (size_t)p.we_bytes;
-          tc::tma_load_2d(tc::smem_u32(wp), &tmWp, w.c * CL, 0, fbar);
-          tc::tma_load_2d(tc::smem_u32(wp + (size_t)p.cpad * 128), &tmWp, w.c * CL + 64, 0, fbar);
-          fb::bulk_load_1d(tc::smem_u32(wp + (size_t)2 * p.cpad * 128), p.aux + (size_t)w.c * AUX_ROWS * CL, AUX_BYTES, fbar);
+        if (!p.resident || i == 0) {
+          for (int c = 0; c < p.n_chunks; ++c) {
+            if (p.resident) ws = c; else mbar_wait_hw(tc::smem_u32(&w_empty[ws]), wph ^ 1u);
+            const uint32_t fbar = tc::smem_u32(&w_full[ws]);
+            uint8_t* dst = w_s + (size_t)ws * wsb;
+            tc::mbar_arrive_expect_tx(fbar, w_tx + ((p.wz_bytes && c == 0) ? (uint32_t)p.wz_bytes : 0u));
+            if (p.wz_bytes) {                       // the shared-zero region rides on chunk 0's barrier: 64-row blocks
+              if (c == 0) for (int blk = 0; blk * 8192 < p.wz_bytes; ++blk) tc::tma_load_2d(tc::smem_u32(wz_s + (size_t)blk * 8192), &tmWe, 0, blk * 64, fbar);
+            }
+            else if (p.stack > 1) tc::tma_load_2d(tc::smem_u32(dst), &tmWe, 0, c * (p.we_bytes >> 7), fbar);   // one box: the window matrix of chunk c
+            else for (int kc = 0; kc < p.kc_in; ++kc) tc::tma_load_2d(tc::smem_u32(dst + (size_t)kc * CL * 128), &tmWe, kc * 64, c * CL, fbar);
+            uint8_t* wp = dst + (size_t)p.we_bytes;
+            tc::tma_load_2d(tc::smem_u32(wp), &tmWp, c * CL, 0, fbar);
+            tc::tma_load_2d(tc::smem_u32(wp + (size_t)p.cpad * 128), &tmWp, c * CL + 64, 0, fbar);
+            fb::bulk_load_1d(tc::smem_u32(wp + (size_t)2 * p.cpad * 128), p.aux + (size_t)c * AUX_ROWS * CL, AUX_BYTES, fbar);
+            if (!p.resident && ++ws == p.w_stages) { ws = 0; wph ^= 1u; }
+          }
         }
+        if (++xs == p.x_stages) { xs = 0; xph ^= 1u; }
+        tx += dtx; ty += dty; tb += db;
+        if (tx >= p.tiles_x) { tx -= p.tiles_x; ++ty; }
+        if (ty >= p.tiles_y) { ty -= p.tiles_y; ++tb; }
       }
     }
     __syncwarp();
@@ -335,32 +364,41 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     const uint32_t idesc_e = tc::make_idesc_bf16(128, p.n_px);
     const uint32_t kst_last = (uint32_t)(((p.Cin - (p.kc_in - 1) * 64) + 15) / 16);
     const uint64_t a_base = tc::make_smem_desc_sw128(tc::smem_u32(w_s));
+    const uint64_t az_base = tc::make_smem_desc_sw128(tc::smem_u32(wz_s));
     const uint64_t b_base = tc::make_smem_desc_sw128(tc::smem_u32(x_s));
     const uint32_t x_step = (uint32_t)xsb >> 4, w_step = (uint32_t)wsb >> 4;
     const uint32_t xk_step = (uint32_t)(p.n_px * 128) >> 4;
     const uint32_t ls_rows16 = (uint32_t)((CL / p.stack) * 128) >> 4;   // one strip's block of channel slots, in 16-byte descriptor units
-    for (fb::WorkIt w = fb::work_begin(); w.n < total; fb::work_next<NG>(w, itp)) {
-      const int n = w.n;
+    int xs = 0, ws = 0, as = 0, n = 0;
+    uint32_t xph = 0, wph = 0, aph = 0;
+    for (int i = 0; i < my_tiles; ++i) {
       if (lane == 0) FBT_TRACE(n, 0);
-      if (w.c == 0) mbar_wait_hw(tc::smem_u32(&x_full[w.xs]), (uint32_t)w.xph);
-      mbar_wait_hw(tc::smem_u32(&w_full[w.ws]), (uint32_t)w.wph);
-      mbar_wait_hw(tc::smem_u32(&acc_empty[w.as]), (uint32_t)(w.aph ^ 1));
-      tc::tcgen05_fence_after();
-      if (lane == 0) FBT_TRACE(n, 1);
-      const uint64_t a0 = a_base + (uint64_t)((uint32_t)w.ws * w_step);
-      const uint64_t b0 = b_base + (uint64_t)((uint32_t)w.xs * x_step);
-      const uint32_t d0 = tmem_base + (uint32_t)(w.as * p.acc_stride);
-      for (int kc = 0; kc < p.kc_in; ++kc) {
-        const uint32_t ksteps = (p.stack > 1) ? (uint32_t)p.kst_stack : ((kc == p.kc_in - 1) ? kst_last : 4u);
-        // stacked: "K chunk" kc is strip kc; its A operand is the window at row (stack - 1 - kc) * (128 / stack)
-        const uint32_t a_off = (p.stack > 1) ? (uint32_t)(p.stack - 1 - kc) * ls_rows16 : (uint32_t)kc * (uint32_t)(CL * 128 >> 4);
-        for (uint32_t ks = 0; ks < ksteps; ++ks)
-          fb::mma_elect(d0, a0 + (uint64_t)(a_off + ks * 2u),
-                        b0 + (uint64_t)((uint32_t)kc * xk_step + ks * 2u), idesc_e, (kc > 0 || ks > 0) ? 1u : 0u);
+      mbar_wait_hw(tc::smem_u32(&x_full[xs]), xph);
+      if (lane == 0) FBT_TRACE(n, 3);
+      const uint64_t b0 = b_base + (uint64_t)((uint32_t)xs * x_step);
+      for (int c = 0; c < p.n_chunks; ++c, ++n) {
+        if (p.resident) { ws = c; if (i == 0) mbar_wait_hw(tc::smem_u32(&w_full[ws]), 0u); }   // resident weights: loaded once per CTA
+        else mbar_wait_hw(tc::smem_u32(&w_full[ws]), wph);
+        mbar_wait_hw(tc::smem_u32(&acc_empty[as]), aph ^ 1u);
+        tc::tcgen05_fence_after();
+        if (lane == 0) FBT_TRACE(n, 1);
+        const uint64_t a0 = p.wz_bytes ? az_base + (uint64_t)((uint32_t)c * (uint32_t)(2 * 8192 >> 4)) : a_base + (uint64_t)((uint32_t)ws * w_step);
+        const uint32_t d0 = tmem_base + (uint32_t)(as * p.acc_stride);
+        for (int kc = 0; kc < p.kc_in; ++kc) {
+          const uint32_t ksteps = (p.stack > 1) ? (uint32_t)p.kst_stack : ((kc == p.kc_in - 1) ? kst_last : 4u);
+          // stacked: "K chunk" kc is strip kc; its A operand is the window at row (stack - 1 - kc) * (128 / stack)
+          const uint32_t a_off = (p.stack > 1) ? (uint32_t)(p.stack - 1 - kc) * ls_rows16 : (uint32_t)kc * (uint32_t)(CL * 128 >> 4);
+          for (uint32_t ks = 0; ks < ksteps; ++ks)
+            fb::mma_elect(d0, a0 + (uint64_t)(a_off + ks * 2u),
+                          b0 + (uint64_t)((uint32_t)kc * xk_step + ks * 2u), idesc_e, (kc > 0 || ks > 0) ? 1u : 0u);
+        }
+        fb::commit_elect(tc::smem_u32(&acc_full[as]));
+        if (lane == 0) FBT_TRACE(n, 2);
+        if (++as == p.n_acc) { as = 0; aph ^= 1u; }
+        if (!p.resident && ++ws == p.w_stages) { ws = 0; wph ^= 1u; }
       }
-      fb::commit_elect(tc::smem_u32(&acc_full[w.as]));
-      if (w.c == p.n_chunks - 1) fb::commit_elect(tc::smem_u32(&x_empty[w.xs]));
-      if (lane == 0) FBT_TRACE(n, 2);
+      fb::commit_elect(tc::smem_u32(&x_empty[xs]));
+      if (++xs == p.x_stages) { xs = 0; xph ^= 1u; }
     }
   } else if (warp == WARP_MMA_P) {
     // ===================== project MMA issuer: D_p[128 px, cpad] += A2^T[128 ch, 128 px]^T * Wp_chunk[cpad, 128 ch]^T =====================
@@ -370,34 +408,40 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     const uint64_t b_base = tc::make_smem_desc_sw128(tc::smem_u32(w_s + (size_t)p.we_bytes));
     const uint32_t w_step = (uint32_t)wsb >> 4;
     const uint32_t wp_half = (uint32_t)(p.cpad * 128) >> 4;
-    for (fb::WorkIt w = fb::work_begin(); w.n < total; fb::work_next<NG>(w, itp)) {
-      const int n = w.n;
-      if (w.c == 0) mbar_wait_hw(tc::smem_u32(&proj_empty[w.ps]), (uint32_t)(w.pph ^ 1));
-      const int a2i = (p.a2_bufs == 2) ? 2 * w.g + w.kph : w.g;            // A2 buffer / barrier of this item
-      const uint32_t a2ph = (uint32_t)((p.a2_bufs == 2) ? w.kph2 : w.kph);
-      mbar_wait_hw(tc::smem_u32(&a2_full[a2i]), a2ph);
-      tc::tcgen05_fence_after();
-      if (lane == 0) FBT_TRACE(n, 4);
-      const uint64_t a0 = a_base + (uint64_t)((uint32_t)a2i * (uint32_t)(A2_BYTES >> 4));
-      const uint64_t b0 = b_base + (uint64_t)((uint32_t)w.ws * w_step);
-      const uint32_t d = tmem_base + (uint32_t)(p.proj_col0 + w.ps * p.proj_stride);
-      if (p.stack == 1) {
+    int ps = 0, ws = 0, g = 0, k = 0, n = 0;        // g: worker group of the item, k: items that group has finished before it
+    uint32_t pph = 0;
+    for (int i = 0; i < my_tiles; ++i) {
+      mbar_wait_hw(tc::smem_u32(&proj_empty[ps]), pph ^ 1u);
+      const uint32_t d = tmem_base + (uint32_t)(p.proj_col0 + ps * p.proj_stride);
+      for (int c = 0; c < p.n_chunks; ++c, ++n) {
+        const int a2i = (p.a2_bufs == 2) ? 2 * g + (k & 1) : g;            // A2 buffer / barrier of this item
+        const uint32_t a2ph = (uint32_t)((p.a2_bufs == 2) ? (k >> 1) & 1 : k & 1);
+        mbar_wait_hw(tc::smem_u32(&a2_full[a2i]), a2ph);
+        tc::tcgen05_fence_after();
+        if (lane == 0) FBT_TRACE(n, 4);
+        if (p.resident) ws = c;
+        const uint64_t a0 = a_base + (uint64_t)((uint32_t)a2i * (uint32_t)(A2_BYTES >> 4));
+        const uint64_t b0 = b_base + (uint64_t)((uint32_t)ws * w_step);
+        if (p.stack == 1) {
 #pragma unroll
-        for (uint32_t ks = 0; ks < 8; ++ks)   // K = 128 channel slots: 16 per step = two 8-channel groups (2 * SBO)
-          fb::mma_elect(d, a0 + (uint64_t)(ks * (uint32_t)(2 * A2_SBO >> 4)), b0 + (uint64_t)((ks >> 2) * wp_half + (ks & 3u) * 2u), idesc_p,
-                        (w.c > 0 || ks > 0) ? 1u : 0u);
-      } else {
-        // K steps per strip = 8 / stack (a power of two): strip s = channel slots [s * 128 / stack, ...) -> its own accumulator
-        const uint32_t kshift = (p.stack == 2) ? 2u : 1u, kmask = (1u << kshift) - 1u;
+          for (uint32_t ks = 0; ks < 8; ++ks)   // K = 128 channel slots: 16 per step = two 8-channel groups (2 * SBO)
+            fb::mma_elect(d, a0 + (uint64_t)(ks * (uint32_t)(2 * A2_SBO >> 4)), b0 + (uint64_t)((ks >> 2) * wp_half + (ks & 3u) * 2u), idesc_p,
+                          (c > 0 || ks > 0) ? 1u : 0u);
+        } else {
+          // K steps per strip = 8 / stack (a power of two): strip s = channel slots [s * 128 / stack, ...) -> its own accumulator
+          const uint32_t kshift = (p.stack == 2) ? 2u : 1u, kmask = (1u << kshift) - 1u;
 #pragma unroll
-        for (uint32_t ks = 0; ks < 8; ++ks)
-          fb::mma_elect(d + (ks >> kshift) * (uint32_t)p.proj_sub, a0 + (uint64_t)(ks * (uint32_t)(2 * A2_SBO >> 4)),
-                        b0 + (uint64_t)((ks >> 2) * wp_half + (ks & 3u) * 2u), idesc_p, (w.c > 0 || (ks & kmask) > 0) ? 1u : 0u);
+          for (uint32_t ks = 0; ks < 8; ++ks)
+            fb::mma_elect(d + (ks >> kshift) * (uint32_t)p.proj_sub, a0 + (uint64_t)(ks * (uint32_t)(2 * A2_SBO >> 4)),
+                          b0 + (uint64_t)((ks >> 2) * wp_half + (ks & 3u) * 2u), idesc_p, (c > 0 || (ks & kmask) > 0) ? 1u : 0u);
+        }
+        fb::commit_elect(tc::smem_u32(&a2_empty[a2i]));
+        if (!p.resident) { fb::commit_elect(tc::smem_u32(&w_empty[ws])); if (++ws == p.w_stages) ws = 0; }
+        if (lane == 0) FBT_TRACE(n, 5);
+        if (++g == NG) { g = 0; ++k; }
       }
-      fb::commit_elect(tc::smem_u32(&a2_empty[a2i]));
-      if (!p.resident) fb::commit_elect(tc::smem_u32(&w_empty[w.ws]));
-      if (w.c == p.n_chunks - 1) fb::commit_elect(tc::smem_u32(&proj_full[w.i & (N_PFULL - 1)]));
-      if (lane == 0) FBT_TRACE(n, 5);
+      fb::commit_elect(tc::smem_u32(&proj_full[i & (N_PFULL - 1)]));
+      if (++ps == p.proj_stages) { ps = 0; pph ^= 1u; }
     }
   } else if (warp >= FIRST_EPI_WARP && warp < FIRST_EPI_WARP + EPI_WARPS) {
     // ===================== epilogue: project accumulator -> +bias (+x) -> bf16 -> global =====================
@@ -448,6 +492,14 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         const bf16* rp = p.x + off;               // residual blocks: S == 1, Cin == Cout, same pixel
         const uint32_t t_row = t_tile + (uint32_t)(st * p.proj_sub);
         for (int c0 = 0; c0 < p.Cout; c0 += 16) {
+          // skip-connection input of this pixel's 16 channels, requested BEFORE the accumulator load: behind the stores of the
+          // previous group the compiler may not hoist these loads (x and y could alias), and one exposed L2 / HBM round trip per
+          // 8 channels made a 72-pixel strip of a residual block take ~3400 cycles (clock64 trace of block 3)
+          uint4 rres[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+          if (p.residual && valid) {
+            rres[0] = __ldg(reinterpret_cast<const uint4*>(rp + c0));
+            if (c0 + 8 < p.Cout) rres[1] = __ldg(reinterpret_cast<const uint4*>(rp + c0 + 8));
+          }
           uint32_t v[16];
           tmem_ld_32x32b_x16(t_row + (uint32_t)c0, v);
           tc::tmem_ld_wait();
@@ -469,7 +521,7 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
                               __uint_as_float(v[j * 8 + 6]) + b1.z, __uint_as_float(v[j * 8 + 7]) + b1.w};
                 if (p.residual) {
                   float r[8];
-                  Vec8<bf16>::load(rp + c0 + j * 8, r);
+                  Vec8<bf16>::unpack(rres[j], r);
 #pragma unroll
                   for (int e = 0; e < 8; ++e) f[e] += r[e];
                 }

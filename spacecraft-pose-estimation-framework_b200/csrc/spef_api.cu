@@ -573,6 +573,9 @@ static int plan_blocks_t(spef_ctx* ctx) {
     q.kc_in = cdiv(q.Cin, 64); q.n_chunks = cdiv(Ch, LS); q.cpad = ((q.Cout + 15) / 16) * 16;
     const int we_rows = LS * (2 * stack - 1);       // window matrix [zeros | chunk | zeros]: 224 (stack 4), 192 (stack 2)
     q.we_bytes = (stack > 1) ? we_rows * 128 : q.kc_in * fbt::CL * 128;
+    // stack = 2: the chunks share their zero blocks in one resident region [Z | C0 | Z | C1 | ... | Z] (fused_block_t.cuh, wz_bytes)
+    const bool we_shared = (stack == 2 && q.n_chunks >= 2 && q.n_chunks <= fbt::MAX_W_STAGES);
+    if (we_shared) { q.wz_bytes = (2 * q.n_chunks + 1) * 64 * 128; q.we_bytes = 0; }
     if (q.cpad > 128 || q.n_chunks > fbt::MAX_W_STAGES) continue;
     q.residual = pj.residual;
     // worker groups, TMEM expand stages (n_px columns each, one more than groups when they fit) and the project
@@ -592,7 +595,7 @@ static int plan_blocks_t(spef_ctx* ctx) {
       std::vector<Opt> opts;
       // a stacked tile is four TMA boxes of 64-byte pixel rows (~2700 cycles): it must be prefetched behind the previous item
       for (int xs = 4; xs >= (stack == 4 ? 2 : 1); --xs) opts.push_back({q.n_chunks, 1, xs});
-      if (q.n_chunks > 3) for (int xs = 2; xs >= 1; --xs) { opts.push_back({4, 0, xs}); opts.push_back({3, 0, xs}); }
+      if (q.n_chunks > 3 && !we_shared) for (int xs = 2; xs >= 1; --xs) { opts.push_back({4, 0, xs}); opts.push_back({3, 0, xs}); }
       // two A2 buffers per group where they fit next to at least two x stages (the workers then never wait for the project MMA
       // of their previous item), else one
       for (int a2b = ctx->fbt_a2_bufs; a2b >= 1 && !found; --a2b) {
@@ -610,7 +613,7 @@ static int plan_blocks_t(spef_ctx* ctx) {
     const int QS = 4 / stack;                        // lane quarters per strip
     const int per_q = Ch / QS, base = per_q / q.n_chunks, rem = per_q % q.n_chunks;
     const size_t we_cols = (stack > 1) ? 64 : (size_t)q.Cin;
-    std::vector<bf16> we((stack > 1 ? (size_t)q.n_chunks * we_rows : (size_t)q.n_chunks * fbt::CL) * we_cols, __float2bfloat16_rn(0.f));
+    std::vector<bf16> we((we_shared ? (size_t)(2 * q.n_chunks + 1) * 64 : (stack > 1 ? (size_t)q.n_chunks * we_rows : (size_t)q.n_chunks * fbt::CL)) * we_cols, __float2bfloat16_rn(0.f));
     std::vector<bf16> wp((size_t)q.Cout * q.n_chunks * fbt::CL, __float2bfloat16_rn(0.f));
     std::vector<float> aux((size_t)q.n_chunks * fbt::AUX_ROWS * fbt::CL, 0.f);
     if (Ch % QS != 0) continue;
@@ -624,7 +627,7 @@ static int plan_blocks_t(spef_ctx* ctx) {
           const int in_strip = qq * 32 + l;          // slot inside the strip's block of LS lanes
           // expand weights: one copy (the window matrix places it for every strip), identity for the t = 1 block
           if (stack > 1) {
-            bf16* row = we.data() + ((size_t)c * we_rows + (size_t)(stack - 1) * LS + in_strip) * 64;
+            bf16* row = we.data() + (we_shared ? ((size_t)(2 * c + 1) * 64 + in_strip) : ((size_t)c * we_rows + (size_t)(stack - 1) * LS + in_strip)) * 64;
             if (has_exp) for (int k = 0; k < e.cin; ++k) row[k] = e.h_wb[(size_t)ch * e.cin + k];
             else row[ch] = __float2bfloat16_rn(1.f);
           } else {
@@ -1047,7 +1050,8 @@ static int launch_fused_block_t(spef_ctx* ctx, Block& b, const void* in, void* o
   std::vector<Layer>& L = ctx->layers;
   fbt::FbtParams& q = b.tprm;
   if (!b.t_tmW_ready) {
-    if (!(q.stack > 1 ? tc::make_tmap_2d(ctx->encode, &b.t_tmWe, b.t_we, false, (long long)q.n_chunks * (q.we_bytes >> 7), 64, 64, q.we_bytes >> 7)
+    if (!(q.wz_bytes ? tc::make_tmap_2d(ctx->encode, &b.t_tmWe, b.t_we, false, (long long)(q.wz_bytes >> 7), 64, 64, 64)
+          : q.stack > 1 ? tc::make_tmap_2d(ctx->encode, &b.t_tmWe, b.t_we, false, (long long)q.n_chunks * (q.we_bytes >> 7), 64, 64, q.we_bytes >> 7)
                        : tc::make_tmap_2d(ctx->encode, &b.t_tmWe, b.t_we, false, (long long)q.n_chunks * fbt::CL, q.Cin, q.Cin, fbt::CL)) ||
         !tc::make_tmap_2d(ctx->encode, &b.t_tmWp, b.t_wp, false, q.Cout, (long long)q.n_chunks * fbt::CL, (long long)q.n_chunks * fbt::CL, q.cpad))
       return fail(ctx, SPEF_ERR_CUDA, "cuTensorMapEncodeTiled(W') failed for fused block at layer %d", b.first);
