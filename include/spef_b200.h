@@ -169,7 +169,10 @@ int spef_decode_pos(spef_ctx* ctx, const float* in_dev, int32_t batch, int32_t n
 /* replaces SPEUtils.get_score (src/spe/spe_utils.py:104-159) and the per-image error lists of
  * evaluation() (src/tools/evaluation.py:82-85).  sums_dev[8] (double) is ACCUMULATED into:
  *   [0] sum e_q (rad)  [1] sum e_t/|t|  [2] sum e_t (m)  [3] image count  [4] #images with |q.q^|>1.01
- *   [5] #images with NaN error  [6],[7] reserved.  per_image_dev [B,2] = (e_q in degrees, e_t) may be NULL. */
+ *   [5] #images with NaN error  [6] #images whose orientation decode raised its NaN guard  [7] #images whose position decode
+ *   raised a guard (zero pdf sum / NaN) -- [6],[7] are only counted by the fused spef_eval_batch* route, which knows the decode
+ *   flags of the batch; the reference raises ValueError from decode() for these (classification_utils.py:134, 253, 262), and so
+ *   does evaluation() after spef_eval_read.  per_image_dev [B,2] = (e_q in degrees, e_t) may be NULL. */
 int spef_score(spef_ctx* ctx, const float* quat_pred_dev, const float* pos_pred_dev,
                const float* quat_true_dev, const float* pos_true_dev, int32_t batch,
                double* sums_dev, float* per_image_dev, void* stream);

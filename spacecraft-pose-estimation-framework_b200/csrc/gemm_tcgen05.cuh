@@ -1,3 +1,5 @@
+// Shared pieces of the tcgen05 kernels (PTX wrappers, UMMA descriptors, GemmParams, tensor-map encoder); the kernel itself is
+// pw_gemm_tcgen05_v2_kernel in gemm_tcgen05_v2.cuh (the first-generation kernel that used to live here was removed in round 2).
 // Pointwise 1x1 conv / Linear on the 5th-gen tensor cores:  D[M,N] = act(A[M,K] * W[N,K]^T + bias) (+ R)
 //   A = NHWC activations (bf16, K-major = channel contiguous), W = PyTorch [Cout,Cin] weights (bf16, K-major,
 //   no repack), D = bf16 NHWC activations (or f32 logits for the head).
@@ -175,10 +177,6 @@ __host__ __device__ inline uint32_t make_idesc_bf16(int m, int n) {
 // ---- shared-memory plan (host and device agree through these helpers) -------------------------------
 __host__ __device__ inline int stage_bytes(int block_n) { return A_STAGE_BYTES + block_n * 128; }
 __host__ __device__ inline int bias_floats(int N) { return ((N + 63) / 64) * 64 + 256; }
-inline size_t smem_bytes(int block_n, int num_stages, int N, int ng) {
-  return 1024 /*align slack*/ + (size_t)num_stages * stage_bytes(block_n) + (size_t)ng * 2 * STAGING_BYTES +
-         (size_t)bias_floats(N) * 4 + 256 /*barriers + tmem ptr*/;
-}
 inline int pick_block_n(int N) {
   if (N <= 256) return ((N + 15) / 16) * 16;
   int best = 256, best_pad = 1 << 30;
@@ -189,267 +187,8 @@ inline int pick_block_n(int N) {
   }
   return best;
 }
-inline int pick_stages(int block_n, int N, size_t smem_limit, int ng) {
-  int s = MAX_STAGES;
-  while (s > 2 && smem_bytes(block_n, s, N, ng) > smem_limit) --s;
-  return s;
-}
 
-template <bool OUT_F32, int NG>
-__global__ void __launch_bounds__(128 + 128 * NG, 1)
-pw_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-                       const __grid_constant__ CUtensorMap tmD, const GemmParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  // 128B-swizzled TMA/UMMA tiles need 1024-byte alignment
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const int block_n = p.block_n;
-  const int nstages = p.num_stages;
-  const int sbytes = stage_bytes(block_n);
-  uint8_t* stage_base = smem;
-  uint8_t* staging = stage_base + (size_t)nstages * sbytes;  // NG x 2 x 16 KB, 1024-aligned (sbytes % 1024 == 0)
-  float* bias_s = reinterpret_cast<float*>(staging + (size_t)NG * 2 * STAGING_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + bias_floats(p.N));
-  uint64_t* full_bar = bars;                       // [MAX_STAGES]
-  uint64_t* empty_bar = bars + MAX_STAGES;         // [MAX_STAGES]
-  uint64_t* tmem_full_bar = bars + 2 * MAX_STAGES;   // [2]
-  uint64_t* tmem_empty_bar = bars + 2 * MAX_STAGES + 2;  // [2]
-  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4);
 
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
-  const int n_tiles = (p.N + block_n - 1) / block_n;
-  const int num_tiles = m_tiles * n_tiles;
-  const int k_chunks = (p.K + BLOCK_K - 1) / BLOCK_K;
-
-  // ---- one-time setup ----
-  for (int i = threadIdx.x; i < bias_floats(p.N); i += (int)blockDim.x) bias_s[i] = (i < p.N) ? p.bias[i] : 0.f;
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmW);
-    tma_prefetch_desc(&tmD);
-  }
-  if (warp == 1 && lane == 0) {
-    for (int i = 0; i < nstages; ++i) {
-      mbar_init(smem_u32(&full_bar[i]), 1);
-      mbar_init(smem_u32(&empty_bar[i]), 1);
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(smem_u32(&tmem_full_bar[i]), 1);
-      mbar_init(smem_u32(&tmem_empty_bar[i]), 4 * NG);  // one arrive per epilogue warp
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_s)), "r"(TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tcgen05_fence_before();
-  __syncthreads();
-  tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_s;
-
-  if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      const uint32_t tx_bytes = (uint32_t)sbytes;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_idx = (tile / n_tiles) * BLOCK_M;
-        const int n_idx = (tile % n_tiles) * block_n;
-        for (int kc = 0; kc < k_chunks; ++kc) {
-          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
-          const uint32_t fb = smem_u32(&full_bar[stage]);
-          mbar_arrive_expect_tx(fb, tx_bytes);
-          uint8_t* sa = stage_base + (size_t)stage * sbytes;
-          tma_load_2d(smem_u32(sa), &tmA, kc * BLOCK_K, m_idx, fb);
-          tma_load_2d(smem_u32(sa + A_STAGE_BYTES), &tmW, kc * BLOCK_K, n_idx, fb);
-          if (++stage == nstages) { stage = 0; phase ^= 1; }
-        }
-      }
-    }
-    __syncwarp();
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(BLOCK_M, block_n);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(smem_u32(&tmem_empty_bar[acc]), acc_phase ^ 1);
-        tcgen05_fence_after();
-        const int lt = (tile - (int)blockIdx.x) / (int)gridDim.x;
-        if (p.trace && blockIdx.x == 0 && lt < 256) p.trace[lt * 8 + 0] = clock64();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);  // accumulator stages at columns 0 / 256
-        for (int kc = 0; kc < k_chunks; ++kc) {
-          mbar_wait(smem_u32(&full_bar[stage]), phase);
-          tcgen05_fence_after();
-          uint8_t* sa = stage_base + (size_t)stage * sbytes;
-          const uint64_t a_desc = make_smem_desc_sw128(smem_u32(sa));
-          const uint64_t b_desc = make_smem_desc_sw128(smem_u32(sa + A_STAGE_BYTES));
-          const int k_rem = p.K - kc * BLOCK_K;
-          const int ksteps = k_rem >= BLOCK_K ? 4 : (k_rem + 15) / 16;
-          for (int k = 0; k < ksteps; ++k) {
-            // advancing 16 bf16 (32 B) inside the 128-byte swizzle row = +2 in the (addr >> 4) field
-            tcgen05_mma_bf16(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc,
-                             (kc > 0 || k > 0) ? 1u : 0u);
-          }
-          tcgen05_commit(smem_u32(&empty_bar[stage]));  // frees the smem stage when these MMAs retire
-          if (++stage == nstages) { stage = 0; phase ^= 1; }
-        }
-        tcgen05_commit(smem_u32(&tmem_full_bar[acc]));  // accumulator complete -> epilogue
-        if (p.trace && blockIdx.x == 0 && lt < 256) p.trace[lt * 8 + 1] = clock64();
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-      }
-    }
-    __syncwarp();
-  } else if (warp >= 4) {
-    // ===================== epilogue: NG groups of 4 warps =====================
-    // Each group owns two staging boxes and a named barrier; 128-byte column boxes of the accumulator stream are
-    // dealt round-robin to the groups, so TMEM loads, the bias/ReLU/residual math, the smem staging and the TMA
-    // stores of different groups overlap (one epilogue warp per SM sub-partition cannot hide its own latencies).
-    constexpr int COLS_PER_BOX = OUT_F32 ? 32 : 64;   // one 128-byte staging row
-    const int q = warp & 3;                           // TMEM lane quarter this warp may access
-    const int grp = (warp - 4) >> 2;                  // epilogue group
-    const int row = q * 32 + lane;                    // row of the 128-row tile == TMEM lane
-    const bool leader = (q == 0 && lane == 0);
-    const uint32_t bar_id = 1 + grp;
-    uint8_t* my_staging = staging + (size_t)grp * 2 * STAGING_BYTES;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    int buf = 0;
-    uint32_t box_counter = 0;                         // identical sequence in every group
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_idx = (tile / n_tiles) * BLOCK_M;
-      const int n_idx = (tile % n_tiles) * block_n;
-      mbar_wait(smem_u32(&tmem_full_bar[acc]), acc_phase);
-      tcgen05_fence_after();
-      const int lt = (tile - (int)blockIdx.x) / (int)gridDim.x;
-      const bool tr = (p.trace != nullptr) && blockIdx.x == 0 && lt < 256 && leader && grp == 0;
-      if (tr) p.trace[lt * 8 + 2] = clock64();
-      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256);
-      const int m = m_idx + row;
-      for (int c0 = 0; c0 < block_n && n_idx + c0 < p.N; c0 += COLS_PER_BOX, ++box_counter) {
-        if ((int)(box_counter % NG) != grp) continue;
-        uint32_t v[COLS_PER_BOX];
-        {
-          uint32_t(&v0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[0]);
-          tmem_ld_32x32b_x32(t_row + (uint32_t)c0, v0);
-          if constexpr (!OUT_F32) {
-            uint32_t(&v1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[32]);
-            tmem_ld_32x32b_x32(t_row + (uint32_t)(c0 + 32), v1);
-          }
-        }
-        const bool tma_store = (p.store_mode != 0);
-        // TMA mode: staging buffer `buf` is free once the TMA store this group issued two boxes ago has read it.
-        // Copy-out mode: it is free because every thread passed the barrier of the previous box after finishing the
-        // copy-out of the box before that (program order), so no extra wait is needed.
-        if (tma_store && leader) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-        tmem_ld_wait();
-        if (tr) p.trace[lt * 8 + 3] = clock64();
-        if (tma_store) asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-        const uint32_t sbuf = smem_u32(my_staging + (size_t)buf * STAGING_BYTES);
-        const uint32_t sb = sbuf + (uint32_t)row * (tma_store ? 128u : (uint32_t)STAGING_PITCH);
-        const uint32_t swz = tma_store ? (uint32_t)(row & 7) : 0u;
-        const uint32_t bias_sa = smem_u32(bias_s + n_idx + c0);
-#pragma unroll
-        for (int h = 0; h < COLS_PER_BOX / 32; ++h) {
-          const int cc = c0 + h * 32;  // column offset inside the tile
-          float f[32];
-#pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 b4 = lds_f4(bias_sa + (uint32_t)(h * 32 + j4 * 4) * 4u);
-            f[j4 * 4 + 0] = __uint_as_float(v[h * 32 + j4 * 4 + 0]) + b4.x;
-            f[j4 * 4 + 1] = __uint_as_float(v[h * 32 + j4 * 4 + 1]) + b4.y;
-            f[j4 * 4 + 2] = __uint_as_float(v[h * 32 + j4 * 4 + 2]) + b4.z;
-            f[j4 * 4 + 3] = __uint_as_float(v[h * 32 + j4 * 4 + 3]) + b4.w;
-          }
-          if (p.relu) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
-          }
-          if constexpr (!OUT_F32) {
-            if (p.residual != nullptr && m < p.M) {
-              const bf16* rp = p.residual + (size_t)m * p.N + n_idx + cc;
-#pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                if (n_idx + cc + g * 8 < p.N) {
-                  float r[8];
-                  Vec8<bf16>::load(rp + g * 8, r);
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) f[g * 8 + e] += r[e];
-                }
-              }
-            }
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {  // four 16-byte chunks = 32 bf16 columns
-              float t8[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) t8[e] = f[g * 8 + e];
-              const uint32_t chunk = (uint32_t)(h * 4 + g);  // 0..7 inside the 128-byte row
-              sts_u4(sb + ((chunk ^ swz) << 4), Vec8<bf16>::pack(t8));
-            }
-          } else {
-#pragma unroll
-            for (int g = 0; g < 8; ++g) {  // eight 16-byte chunks = 32 f32 columns
-              uint4 o;
-              o.x = __float_as_uint(f[g * 4]); o.y = __float_as_uint(f[g * 4 + 1]);
-              o.z = __float_as_uint(f[g * 4 + 2]); o.w = __float_as_uint(f[g * 4 + 3]);
-              sts_u4(sb + (((uint32_t)g ^ swz) << 4), o);
-            }
-          }
-        }
-        if (tr) p.trace[lt * 8 + 4] = clock64();  // math + STS done
-        if (tma_store) {
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to TMA
-          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-          if (leader) {
-            tma_store_2d(&tmD, sbuf, n_idx + c0, m_idx);
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          }
-        } else {
-          // coalesced copy-out: 8 consecutive threads write one 128-byte row segment of D
-          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-          if (tr) p.trace[lt * 8 + 5] = clock64();  // barrier passed
-          constexpr int ELEMS_PER_PIECE = OUT_F32 ? 4 : 8;
-          constexpr int ESZ = OUT_F32 ? 4 : 2;
-          const int tg = (int)threadIdx.x - 128 - grp * 128;  // 0..127 inside the group
-          uint8_t* outb = reinterpret_cast<uint8_t*>(p.out);
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const int i = tg + k * 128;
-            const int r = i >> 3, pc = i & 7;
-            const int gm = m_idx + r, gcol = n_idx + c0 + pc * ELEMS_PER_PIECE;
-            if (gm < p.M && gcol < p.N) {
-              const uint4 val = lds_u4(sbuf + (uint32_t)(r * STAGING_PITCH + pc * 16));
-              *reinterpret_cast<uint4*>(outb + ((size_t)gm * p.ldd + gcol) * ESZ) = val;
-            }
-          }
-        }
-        if (tr) p.trace[lt * 8 + 6] = clock64();  // copy-out / store issue done
-        buf ^= 1;
-      }
-      // all tcgen05.ld of this warp on this accumulator have completed (wait::ld above): hand TMEM back
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
-      if (tr) p.trace[lt * 8 + 7] = clock64();
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-    }
-    if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-  }
-
-  // ---- teardown ----
-  tcgen05_fence_before();
-  __syncthreads();
-  if (warp == 2) {
-    tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
-  }
-}
 
 // ---- host side: tensor maps -------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

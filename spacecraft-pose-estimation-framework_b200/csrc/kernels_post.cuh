@@ -318,13 +318,16 @@ __global__ void __launch_bounds__(128) decode_pos_kernel(const float* __restrict
 // --------------------------------------------------------------------------------------------------
 // Score (spe_utils.py:119-157): per image, float32 with NumPy's operation order and no FMA contraction:
 //   e_t = sqrt(dx^2 + dy^2 + dz^2); e_tn = e_t / |t|; c = |sum q^ q|; c = min(c, 1); e_q = 2 acos(c).
-// Block-reduced in f64 and atomically accumulated into sums[0..5] (see spef_b200.h).  per_image [B,2]
-// = (e_q in degrees, e_t) as evaluation.py:82-85.
+// Block-reduced in f64 and atomically accumulated into sums[0..7] (see spef_b200.h).  per_image [B,2]
+// = (e_q in degrees, e_t) as evaluation.py:82-85.  flags (optional): the decode kernels' per-image guard flags of the same
+// batch; images whose orientation / position decode raised a guard (the reference's ValueErrors, classification_utils.py:134,
+// 253, 262) are COUNTED in sums[6] / sums[7], so that the fused evaluation route can raise like the reference does.
 // --------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) score_kernel(const float* __restrict__ qp, const float* __restrict__ tp,
                                                     const float* __restrict__ qt, const float* __restrict__ tt, int B,
-                                                    double* __restrict__ sums, float* __restrict__ per_image) {
-  double s[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+                                                    double* __restrict__ sums, float* __restrict__ per_image,
+                                                    const uint32_t* __restrict__ flags) {
+  double s[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B; i += gridDim.x * blockDim.x) {
     const float dx = __fsub_rn(tt[i * 3 + 0], tp[i * 3 + 0]);
     const float dy = __fsub_rn(tt[i * 3 + 1], tp[i * 3 + 1]);
@@ -347,21 +350,26 @@ __global__ void __launch_bounds__(256) score_kernel(const float* __restrict__ qp
     s[3] += 1.0;
     if (over) s[4] += 1.0;
     if (isnan(e_q) || isnan(e_tn)) s[5] += 1.0;
+    if (flags != nullptr) {
+      const uint32_t f = flags[i];
+      if (f & 1u) s[6] += 1.0;          // SPEF_FLAG_ORI_NAN
+      if (f & 6u) s[7] += 1.0;          // SPEF_FLAG_POS_ZERO_SUM | SPEF_FLAG_POS_NAN
+    }
     if (per_image != nullptr) {
       per_image[i * 2 + 0] = __fdiv_rn(__fmul_rn(e_q, 180.f), 3.14159265358979323846f);
       per_image[i * 2 + 1] = e_t;
     }
   }
-  __shared__ double red[8][6];
+  __shared__ double red[8][8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-  for (int k = 0; k < 6; ++k) s[k] = warp_sum(s[k]);
+  for (int k = 0; k < 8; ++k) s[k] = warp_sum(s[k]);
   if (lane == 0) {
 #pragma unroll
-    for (int k = 0; k < 6; ++k) red[warp][k] = s[k];
+    for (int k = 0; k < 8; ++k) red[warp][k] = s[k];
   }
   __syncthreads();
-  if (threadIdx.x < 6) {
+  if (threadIdx.x < 8) {
     double t = 0.0;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w][threadIdx.x];
     if (t != 0.0) atomicAdd(sums + threadIdx.x, t);

@@ -50,7 +50,7 @@ struct Layer {
   // tcgen05 plan
   int block_n = 0, stages = 0;
   size_t smem = 0;
-  CUtensorMap tmA, tmW, tmD;
+  CUtensorMap tmA, tmW;
   bool tmW_ready = false;
   int plan_batch = -1;      // batch size the cached activation tensor maps (tmA/tmD/tmX) were encoded for
   // TMA depthwise plan
@@ -113,14 +113,15 @@ struct spef_ctx {
   int num_sms = 148;
   size_t smem_optin = 0;
   tc::EncodeTiledFn encode = nullptr;
-  int gemm_ng = 2;  // epilogue groups of the tcgen05 GEMM (SPEF_GEMM_NG = 1 | 2)
   long long* trace_dev = nullptr;  // SPEF_GEMM_TRACE=<layer index>: dump CTA-0 timestamps of that layer to stderr
   int trace_layer = -1;
   int image_u8 = 0;    // SPEF_IMG_U8: images are uint8, the stem divides by 255
-  int gemm_impl = 2;   // 2: drain/store warp-specialised epilogue (default); 1: v1 epilogue (SPEF_GEMM_IMPL=1)
+  int stem_simt = 0;   // SPEF_STEM_SIMT=1: CUDA-core stem instead of the tcgen05 implicit GEMM (cross-check; float images only)
+  int fb_debug_skip = 0;   // SPEF_FB_DEBUG_SKIP: timing experiments of the staged fused kernel (wrong results)
+  int fbt_no_stack = 0;    // SPEF_FBT_NO_STACK=1: no strip stacking in the channel-lane plan
+  int head_wide = 0;       // SPEF_HEAD_WIDE=1: 256-column tiles for the head GEMM
   int gemm_nsw = 4;    // store warps of the v2 epilogue (SPEF_GEMM_NSW = 4 | 8; 8 only with one drain group)
   int gemm_ndg = 2;    // drain groups of the v2 epilogue (SPEF_GEMM_NDG = 1 | 2)
-  int gemm_store = 0;  // 0 coalesced copy-out (default), 1 TMA store (SPEF_GEMM_STORE=tma)
   size_t esz = 2;
   // activations
   void* act[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -329,11 +330,12 @@ extern "C" int spef_create(spef_ctx** out, const spef_config* cfg) {
   if (const char* e15 = getenv("SPEF_DW_SMALL")) ctx->dw_small_plan = atoi(e15);
   if (const char* e13 = getenv("SPEF_DECODE_CFG")) ctx->decode_cfg = atoi(e13);
   if (const char* e12 = getenv("SPEF_DECODE_STREAM")) ctx->decode_stream = atoi(e12);
-  if (const char* e5 = getenv("SPEF_GEMM_IMPL")) ctx->gemm_impl = (atoi(e5) == 1) ? 1 : 2;
+  if (const char* e5 = getenv("SPEF_STEM_SIMT")) ctx->stem_simt = atoi(e5) ? 1 : 0;
+  if (const char* e5 = getenv("SPEF_FB_DEBUG_SKIP")) ctx->fb_debug_skip = atoi(e5);
+  if (getenv("SPEF_FBT_NO_STACK")) ctx->fbt_no_stack = 1;
+  if (getenv("SPEF_HEAD_WIDE")) ctx->head_wide = 1;
   if (const char* e7 = getenv("SPEF_GEMM_NDG")) ctx->gemm_ndg = (atoi(e7) == 1) ? 1 : 2;
   if (const char* e6 = getenv("SPEF_GEMM_NSW")) ctx->gemm_nsw = (atoi(e6) == 8 && ctx->gemm_ndg == 1) ? 8 : 4;
-  if (const char* e3 = getenv("SPEF_GEMM_STORE")) ctx->gemm_store = (strcmp(e3, "tma") == 0) ? 1 : 0;
-  if (const char* e2 = getenv("SPEF_GEMM_NG")) { int v = atoi(e2); if (v == 1 || v == 2) ctx->gemm_ng = v; }
   if (const char* e8 = getenv("SPEF_FUSE")) ctx->fuse = atoi(e8) ? 1 : 0;
   if (const char* e9 = getenv("SPEF_FB_GW")) ctx->fb_gw = (atoi(e9) == 8) ? 8 : 4;
   if (const char* e11 = getenv("SPEF_FB_MAX_CIN")) ctx->fb_max_cin = atoi(e11);
@@ -545,9 +547,9 @@ static int plan_blocks_t(spef_ctx* ctx) {
     // stride 1, no skip, Cout <= 16); blocks whose hidden width wastes lanes at 128 channels per pass (144, 192) -> two strips of 64 slots
     int stack = 1;
     if (!has_exp) {
-      if (!(Ch == 32 && S == 1 && !pj.residual && pj.cout <= 16 && !getenv("SPEF_FBT_NO_STACK"))) continue;
+      if (!(Ch == 32 && S == 1 && !pj.residual && pj.cout <= 16 && !ctx->fbt_no_stack)) continue;
       stack = 4;
-    } else if (S == 1 && e.cin <= 64 && !getenv("SPEF_FBT_NO_STACK") && cdiv(Ch, 64) < 2 * cdiv(Ch, fbt::CL) && d.wout % (TW * 2) == 0) {
+    } else if (S == 1 && e.cin <= 64 && !ctx->fbt_no_stack && cdiv(Ch, 64) < 2 * cdiv(Ch, fbt::CL) && d.wout % (TW * 2) == 0) {
       // (stride-2 blocks measured no faster stacked: their items are dominated by the conversion of the 4x larger hidden tile)
       stack = 2;
     }
@@ -763,14 +765,9 @@ extern "C" int spef_finalize_weights(spef_ctx* ctx) {
       l.block_n = tc::pick_block_n(l.n_pad);
       // head GEMM: M = batch is at most a few 128-row tiles, so 256-column tiles would keep 14 CTAs busy at B = 256 (22.5 us to
       // stream 4.4 MB of weights); 64-column tiles spread the same weights over 4x as many CTAs
-      if (l.kind == K_HEAD && ctx->gemm_impl == 2 && ctx->cfg.max_batch <= 2048 && !getenv("SPEF_HEAD_WIDE")) l.block_n = 64;
-      if (ctx->gemm_impl == 2) {
-        l.stages = tc::pick_stages_v2(l.block_n, l.n_pad, l.cin, ctx->smem_optin);
-        l.smem = tc::smem_bytes_v2(l.block_n, l.stages, l.n_pad, l.cin);
-      } else {
-        l.stages = tc::pick_stages(l.block_n, l.n_pad, ctx->smem_optin, ctx->gemm_ng);
-        l.smem = tc::smem_bytes(l.block_n, l.stages, l.n_pad, ctx->gemm_ng);
-      }
+      if (l.kind == K_HEAD && ctx->cfg.max_batch <= 2048 && !ctx->head_wide) l.block_n = 64;
+      l.stages = tc::pick_stages_v2(l.block_n, l.n_pad, l.cin, ctx->smem_optin);
+      l.smem = tc::smem_bytes_v2(l.block_n, l.stages, l.n_pad, l.cin);
     }
   }
   if (use_bf16) {
@@ -801,12 +798,6 @@ extern "C" int spef_finalize_weights(spef_ctx* ctx) {
     CK(cudaFuncSetAttribute(tc::pw_gemm_tcgen05_v2_kernel<false, 1, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, so));
     CK(cudaFuncSetAttribute(tc::pw_gemm_tcgen05_v2_kernel<false, 1, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, so));
     CK(cudaFuncSetAttribute(tc::pw_gemm_tcgen05_v2_kernel<false, 1, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, so));
-    CK(cudaFuncSetAttribute(tc::pw_gemm_tcgen05_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, so));
-    CK(cudaFuncSetAttribute(tc::pw_gemm_tcgen05_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, so));
-    CK(cudaFuncSetAttribute(tc::pw_gemm_tcgen05_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, so));
-    CK(cudaFuncSetAttribute(tc::pw_gemm_tcgen05_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, so));
-    CK(cudaFuncSetAttribute(tc::pw_gemm_tcgen05_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, so));
-    CK(cudaFuncSetAttribute(tc::pw_gemm_tcgen05_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, so));
     const int dw_smem = 112 * 1024;
     CK(cudaFuncSetAttribute(dw::dwconv3x3_tma_kernel<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem));
     CK(cudaFuncSetAttribute(dw::dwconv3x3_tma_kernel<1, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem));
@@ -980,26 +971,23 @@ static int launch_tcgen05_layer(spef_ctx* ctx, Layer& l, const void* in, const v
     if (!tc::make_tmap_2d(ctx->encode, &l.tmW, l.w_bf16, false, N, K, K, l.block_n)) return fail(ctx, SPEF_ERR_CUDA, "cuTensorMapEncodeTiled(W) failed for %s", l.prefix.c_str());
     l.tmW_ready = true;
   }
-  CUtensorMap tA_local, tD_local;
+  CUtensorMap tA_local;
   CUtensorMap* tA = cached_maps ? &l.tmA : &tA_local;
-  CUtensorMap* tD = cached_maps ? &l.tmD : &tD_local;
   if (!cached_maps || l.plan_batch != B) {
     if (!tc::make_tmap_2d(ctx->encode, tA, in, false, M, K, K, tc::BLOCK_M)) return fail(ctx, SPEF_ERR_CUDA, "cuTensorMapEncodeTiled(A) failed for %s (M=%d K=%d)", l.prefix.c_str(), M, K);
-    if (!tc::make_tmap_2d(ctx->encode, tD, out, f32out, M, N, N, tc::BLOCK_M)) return fail(ctx, SPEF_ERR_CUDA, "cuTensorMapEncodeTiled(D) failed for %s (M=%d N=%d)", l.prefix.c_str(), M, N);
     if (cached_maps) l.plan_batch = B;
   }
   tc::GemmParams p;
   memset(&p, 0, sizeof(p));
   p.bias = l.bias; p.residual = (const bf16*)res; p.M = M; p.N = N; p.K = K; p.block_n = l.block_n; p.num_stages = l.stages; p.relu = l.relu;
-  p.store_mode = ctx->gemm_store; p.out = out; p.ldd = N;
+  p.store_mode = 0; p.out = out; p.ldd = N;
   p.img = nullptr; p.img_h = p.img_w = p.out_h = p.out_w = 0; p.img_u8 = 0;
   const bool trace = ctx->trace_dev && (&l == &ctx->layers[ctx->trace_layer < (int)ctx->layers.size() && ctx->trace_layer >= 0 ? ctx->trace_layer : 0]) && ctx->trace_layer >= 0;
-  p.trace = (trace && ctx->gemm_impl == 1) ? ctx->trace_dev : nullptr;
+  p.trace = nullptr;
   if (trace) cudaMemsetAsync(ctx->trace_dev, 0, 256 * 16 * sizeof(long long), st);
   const int tiles = cdiv(M, tc::BLOCK_M) * cdiv(N, l.block_n);
   const int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
-  const int ng = ctx->gemm_ng, nthr = 128 + 128 * ng;
-  if (ctx->gemm_impl == 2) {
+  {
     const int nsw = ctx->gemm_nsw, ndg = ctx->gemm_ndg, nt2 = 128 + 128 * ndg + 32 * nsw;
 #define SPEF_V2_LAUNCH(F32, NDG_, NSW_) tc::pw_gemm_tcgen05_v2_kernel<F32, NDG_, NSW_, 0><<<grid, nt2, l.smem, st>>>(*tA, l.tmW, p)
     if (f32out) {
@@ -1008,16 +996,8 @@ static int launch_tcgen05_layer(spef_ctx* ctx, Layer& l, const void* in, const v
       if (ndg == 2) SPEF_V2_LAUNCH(false, 2, 4); else if (nsw == 8) SPEF_V2_LAUNCH(false, 1, 8); else SPEF_V2_LAUNCH(false, 1, 4);
     }
 #undef SPEF_V2_LAUNCH
-  } else if (f32out) {
-    if (ng == 1) tc::pw_gemm_tcgen05_kernel<true, 1><<<grid, nthr, l.smem, st>>>(*tA, l.tmW, *tD, p);
-    else if (ng == 2) tc::pw_gemm_tcgen05_kernel<true, 2><<<grid, nthr, l.smem, st>>>(*tA, l.tmW, *tD, p);
-    else tc::pw_gemm_tcgen05_kernel<true, 4><<<grid, nthr, l.smem, st>>>(*tA, l.tmW, *tD, p);
-  } else {
-    if (ng == 1) tc::pw_gemm_tcgen05_kernel<false, 1><<<grid, nthr, l.smem, st>>>(*tA, l.tmW, *tD, p);
-    else if (ng == 2) tc::pw_gemm_tcgen05_kernel<false, 2><<<grid, nthr, l.smem, st>>>(*tA, l.tmW, *tD, p);
-    else tc::pw_gemm_tcgen05_kernel<false, 4><<<grid, nthr, l.smem, st>>>(*tA, l.tmW, *tD, p);
   }
-  CK_LAUNCH("pw_gemm_tcgen05_kernel");
+  CK_LAUNCH("pw_gemm_tcgen05_v2_kernel");
   if (trace) {
     static int dumped = 0;
     if (dumped++ == 3) {  // 4th call: warmed up
@@ -1124,7 +1104,7 @@ static int launch_fused_block(spef_ctx* ctx, Block& b, const void* in, void* out
   q.x = (const bf16*)in; q.y = (bf16*)out; q.B = B; q.aux = b.aux; q.bp = L[b.i_proj].bias;
   const bool trace = ctx->trace_dev && ctx->fb_trace_block >= 0 && &b == &ctx->blocks[ctx->fb_trace_block < (int)ctx->blocks.size() ? ctx->fb_trace_block : 0];
   q.trace = trace ? ctx->trace_dev : nullptr;
-  { const char* ds = getenv("SPEF_FB_DEBUG_SKIP"); q.debug_skip = ds ? atoi(ds) : 0; }
+  q.debug_skip = ctx->fb_debug_skip;
   if (trace) cudaMemsetAsync(ctx->trace_dev, 0, 256 * 16 * sizeof(long long), st);
   const long long tiles = (long long)B * q.tiles_y * q.tiles_x;
   const int grid = (int)(tiles < ctx->num_sms ? tiles : ctx->num_sms);
@@ -1163,11 +1143,11 @@ static int launch_fused_block(spef_ctx* ctx, Block& b, const void* in, void* out
 
 static int run_layer(spef_ctx* ctx, Layer& l, const void* in, const void* res, void* out, int B, cudaStream_t st, bool cached_maps) {
   const bool use_bf16 = ctx->cfg.precision == SPEF_BF16;
-  if (l.kind == K_STEM && ctx->image_u8 && !(use_bf16 && ctx->cfg.pw_impl == 0 && ctx->gemm_impl == 2 && !getenv("SPEF_STEM_SIMT")))
+  if (l.kind == K_STEM && ctx->image_u8 && !(use_bf16 && ctx->cfg.pw_impl == 0 && !ctx->stem_simt))
     return fail(ctx, SPEF_ERR_UNSUPPORTED, "uint8 images are implemented on the BF16 tcgen05 stem only");
   if (use_bf16 && (l.kind == K_PW || l.kind == K_HEAD) && ctx->cfg.pw_impl == 0) return launch_tcgen05_layer(ctx, l, in, res, out, B, st, cached_maps);
   if (use_bf16 && l.kind == K_DW && ctx->cfg.pw_impl == 0) return launch_dw_tma_layer(ctx, l, in, out, B, st, cached_maps);
-  if (use_bf16 && l.kind == K_STEM && ctx->cfg.pw_impl == 0 && ctx->gemm_impl == 2 && !getenv("SPEF_STEM_SIMT")) return launch_stem_tcgen05(ctx, l, in, out, B, st);
+  if (use_bf16 && l.kind == K_STEM && ctx->cfg.pw_impl == 0 && !ctx->stem_simt) return launch_stem_tcgen05(ctx, l, in, out, B, st);
   if (use_bf16) return launch_cuda_core_layer<bf16>(ctx, l, in, res, out, B, st);
   return launch_cuda_core_layer<float>(ctx, l, in, res, out, B, st);
 }
@@ -1564,16 +1544,21 @@ extern "C" int spef_error_stats(spef_ctx* ctx, const float* x_dev, int32_t strid
   return SPEF_OK;
 }
 
-extern "C" int spef_score(spef_ctx* ctx, const float* qp, const float* tp, const float* qt, const float* tt, int32_t B, double* sums,
-                          float* per_image, void* stream) {
-  if (!ctx) return SPEF_ERR_INVALID;
+static int score_internal(spef_ctx* ctx, const float* qp, const float* tp, const float* qt, const float* tt, int32_t B, double* sums,
+                          float* per_image, const uint32_t* flags, void* stream) {
   if (!qp || !tp || !qt || !tt || !sums || B < 1) return fail(ctx, SPEF_ERR_INVALID, "spef_score: bad argument");
   CK(cudaSetDevice(ctx->cfg.device));
   int grid = cdiv(B, 256);
   if (grid > 4 * ctx->num_sms) grid = 4 * ctx->num_sms;
-  score_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(qp, tp, qt, tt, B, sums, per_image);
+  score_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(qp, tp, qt, tt, B, sums, per_image, flags);
   CK_LAUNCH("score_kernel");
   return SPEF_OK;
+}
+
+extern "C" int spef_score(spef_ctx* ctx, const float* qp, const float* tp, const float* qt, const float* tt, int32_t B, double* sums,
+                          float* per_image, void* stream) {
+  if (!ctx) return SPEF_ERR_INVALID;
+  return score_internal(ctx, qp, tp, qt, tt, B, sums, per_image, nullptr, stream);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -1671,7 +1656,8 @@ extern "C" int spef_eval_batch(spef_ctx* ctx, const float* images_dev, const flo
   cudaStream_t st = (cudaStream_t)stream;
   rc = predict_internal(ctx, images_dev, B, nullptr, ctx->ws_quat, nullptr, ctx->ws_pos, nullptr, ctx->ws_flags, st);
   if (rc) return rc;
-  return spef_score(ctx, ctx->ws_quat, ctx->ws_pos, qt, tt, B, ctx->eval_sums, per_image, stream);
+  // the decode guard flags of this batch are counted into sums[6] / sums[7] (the reference raises ValueError from decode())
+  return score_internal(ctx, ctx->ws_quat, ctx->ws_pos, qt, tt, B, ctx->eval_sums, per_image, ctx->ws_flags, stream);
 }
 
 extern "C" int spef_eval_batch_host(spef_ctx* ctx, const float* images_host, const float* qt_h, const float* tt_h, int32_t B,

@@ -17,7 +17,8 @@ _PRECISIONS = {"fp32": _ffi.SPEF_FP32, "float32": _ffi.SPEF_FP32, "bf16": _ffi.S
 def _require_cuda(device) -> torch.device:
     if not torch.cuda.is_available():
         raise RuntimeError("spef_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
-    dev = torch.device(device if device is not None else "cuda:0")
+    # no device given: the CURRENT device (one process per GPU sets it once; "cuda:0" would put every rank's helper contexts on GPU 0)
+    dev = torch.device(device if device is not None else ("cuda", torch.cuda.current_device()))
     if dev.type != "cuda":
         raise RuntimeError(f"spef_b200 runs on CUDA devices only, got {dev}")
     return torch.device("cuda", dev.index if dev.index is not None else torch.cuda.current_device())
@@ -274,6 +275,21 @@ class Engine:
         self._ck(self.lib.spef_score(self._h, ptr(qp), ptr(tp), ptr(qt), ptr(tt), B, ptr(sums), ptr(per), _stream(self.device)))
         return sums, per
 
+    def _host_img(self, images: torch.Tensor) -> torch.Tensor:
+        """Host image batch in the dtype the context was told to expect (spef_set_image_dtype): the *_host entry points copy
+        B*3*H*W elements of THAT type, so a float batch handed to a uint8 context (or the reverse) must be converted here --
+        uint8 pixels are ToTensor's input (value / 255), float images are ToTensor's output."""
+        x = images.detach()
+        if self.image_dtype == torch.uint8:
+            if x.dtype != torch.uint8:
+                if not torch.is_floating_point(x):
+                    raise TypeError(f"uint8 engine: images must be uint8 pixels or float images in [0, 1], got {x.dtype}")
+                x = (x.to("cpu", torch.float32) * 255.0).round().clamp_(0, 255).to(torch.uint8)
+            return x.to("cpu").contiguous()
+        if x.dtype == torch.uint8:
+            x = x.to("cpu", torch.float32) / 255.0   # torchvision ToTensor
+        return x.to("cpu", torch.float32).contiguous()
+
     # ---- fused predict ---------------------------------------------------------------------------
     def predict(self, images: torch.Tensor, want_soft=True, want_argmax=False) -> Dict[str, torch.Tensor]:
         """forward + softmax + decode on device tensors (spef_predict)."""
@@ -293,9 +309,7 @@ class Engine:
     def predict_host(self, images: torch.Tensor, want_soft=True, want_argmax=False) -> Dict[str, np.ndarray]:
         """Host buffers in, host buffers out (spef_predict_host): the call SPETorch.predict maps to."""
         B = self._check_images(images)
-        x = images.detach()
-        if x.dtype != torch.float32 or not x.is_contiguous() or x.device.type != "cpu":
-            x = x.to("cpu", torch.float32).contiguous()
+        x = self._host_img(images)
         out = {"ori": np.empty((B, 4), np.float32), "pos": np.empty((B, 3), np.float32), "flags": np.zeros(B, np.uint32)}
         if want_soft:
             out["ori_soft"] = np.empty((B, self.n_ori), np.float32)
@@ -315,7 +329,7 @@ class Engine:
     def eval_batch(self, images: torch.Tensor, quat_true, pos_true, want_per_image=False):
         B = self._check_images(images)
         if images.device.type == "cpu":
-            x = images.detach().to(torch.float32).contiguous()
+            x = self._host_img(images)
             qt = np.ascontiguousarray(torch.as_tensor(quat_true).cpu().numpy(), np.float32)
             tt = np.ascontiguousarray(torch.as_tensor(pos_true).cpu().numpy(), np.float32)
             per = np.empty((B, 2), np.float32) if want_per_image else None

@@ -141,19 +141,26 @@ def save_model(model: nn.Module, bit_width: Optional[dict], path: str) -> None:
     torch.save(model.state_dict(), os.path.join(path, "parameters.pt"))
 
 
-def copy_state_dict(src: Dict[str, torch.Tensor], dst: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
-    """Positional copy between two state_dicts whose keys differ but whose tensors line up
-    (src/modeling/model.py:92-119): the i-th floating tensor of `src` goes to the i-th key of `dst`."""
-    src_items = [(k, v) for k, v in src.items()]
-    dst_keys = list(dst.keys())
-    if len(src_items) != len(dst_keys):
-        raise ValueError(f"state dicts differ in length: {len(src_items)} vs {len(dst_keys)}")
-    out = {}
-    for (sk, sv), dk in zip(src_items, dst_keys):
-        if tuple(sv.shape) != tuple(dst[dk].shape):
-            raise ValueError(f"shape mismatch copying {sk} -> {dk}: {tuple(sv.shape)} vs {tuple(dst[dk].shape)}")
-        out[dk] = sv
-    return out
+def copy_state_dict(state_dict_1: Dict[str, torch.Tensor], state_dict_2: Dict[str, torch.Tensor], act_quant: bool = False) -> Dict[str, torch.Tensor]:
+    """Manual copy of state_dict_1 into state_dict_2 for state dicts whose keys differ (src/modeling/model.py:92-119): per key
+    FAMILY ("weight", "bias", "running_mean", "running_var", "num_batches_tracked", and "act_quant" when asked), the i-th tensor
+    of that family in state_dict_1 goes to the i-th key of that family in state_dict_2; other keys (e.g. the act_quant entries
+    of a Brevitas checkpoint when act_quant=False) are ignored, as in the reference.  One addition: a shape check, because a
+    silent mis-ordered copy would only surface as wrong poses."""
+    keys1, keys2 = list(state_dict_1.keys()), list(state_dict_2.keys())
+    families = ["weight", "bias", "running_mean", "running_var", "num_batches_tracked"]
+    if act_quant:
+        families.append("act_quant")
+    for fam in families:
+        k1 = [k for k in keys1 if fam in k]
+        k2 = [k for k in keys2 if fam in k]
+        if len(k1) > len(k2):
+            raise ValueError(f"copy_state_dict: {len(k1)} '{fam}' tensors in the source but only {len(k2)} in the destination")
+        for i, src_key in enumerate(k1):
+            if tuple(state_dict_1[src_key].shape) != tuple(state_dict_2[k2[i]].shape):
+                raise ValueError(f"shape mismatch copying {src_key} -> {k2[i]}: {tuple(state_dict_1[src_key].shape)} vs {tuple(state_dict_2[k2[i]].shape)}")
+            state_dict_2[k2[i]] = state_dict_1[src_key]
+    return state_dict_2
 
 
 def import_model(
@@ -172,13 +179,15 @@ def import_model(
     pos_mode: str = 'regression',
     n_pos_bins: int = None,
     *,
-    precision: str = "bf16",
+    precision: str = "fp32",
     max_batch: int = None,
     pw_impl: int = 0,
 ) -> tuple:
     """Same contract as the reference's import_model (src/modeling/model.py:122-279); returns (model, bit_width)
     with bit_width = None for PyTorch backbones (:180-182).  Keyword-only extras select the B200 engine's
-    precision ('bf16' | 'fp32') and workspace size.
+    precision and workspace size.  precision defaults to 'fp32' -- the reference model family is FP32 and a drop-in caller gets
+    its arithmetic (logits within 1e-4 relative) unless it asks for the BF16 tensor-core path with precision='bf16'
+    (the throughput path of bench.py).
 
     Differences, all outside the inference arithmetic: only the FP32 PyTorch model family is built
     ('mobilenet_v2_pytorch' + 'ursonet_pytorch'; Brevitas/FINN variants are out of scope), the dry-run forward

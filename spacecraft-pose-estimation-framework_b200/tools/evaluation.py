@@ -52,8 +52,19 @@ def gather_per_image(err: np.ndarray, device=None) -> np.ndarray:
     return np.concatenate(parts, axis=0)
 
 
+def _raise_decode_guards(sums: np.ndarray) -> None:
+    """The reference's decode() raises on these conditions (classification_utils.py:134-135, 253-254, 262-263); the fused route
+    counts the per-image guard flags of every batch into sums[6] / sums[7] (spef_b200.h) -- after the cross-rank reduction, so
+    that every rank raises together."""
+    if sums[6] > 0:
+        raise ValueError("Error during orientation decoding")
+    if sums[7] > 0:
+        raise ValueError("Error during position decoding, NaN found in decoded position (or the encoded position vector sum is zero).")
+
+
 def _finish(rec_score, rec_error, phase, sums, per_image, device=None, stats_engine=None):
     sums = reduce_eval_sums(sums, device)
+    _raise_decode_guards(sums)
     per_image = gather_per_image(per_image, device)
     m = SPEUtils.metrics_from_sums(sums)
     rec_score[phase]['ori'].append(float(m['ori_score']))
@@ -95,12 +106,19 @@ def evaluation(
             eng = spe_model.engine
             eng.eval_reset()
             per, keep = [], []
+            dtype0 = eng.image_dtype
             for images, targets in dataloader[phase]:
                 x = images['torch']
+                # a loader that yields uint8 pixels (ToTensor not applied yet) takes the uint8 ingest route: a quarter of the
+                # H2D bytes, bit-identical results (the stem divides by 255 itself)
+                want = torch.uint8 if (x.dtype == torch.uint8 and eng.precision == "bf16") else torch.float32
+                if want != eng.image_dtype:
+                    eng.eval_wait()
+                    eng.set_image_dtype(want)
                 if x.device.type == "cpu":
                     # pipelined: the H2D copy of this batch overlaps the kernels of the previous one; host buffers are kept
                     # alive until the phase is drained
-                    x = x.detach().to(torch.float32).contiguous()
+                    x = eng._host_img(x)
                     qt = torch.as_tensor(targets['ori']).detach().to("cpu", torch.float32).contiguous()
                     tt = torch.as_tensor(targets['pos']).detach().to("cpu", torch.float32).contiguous()
                     out = torch.empty((x.shape[0], 2), dtype=torch.float32, pin_memory=True)
@@ -111,6 +129,8 @@ def evaluation(
                     per.append(eng.eval_batch(x, targets['ori'], targets['pos'], want_per_image=True))
             eng.eval_wait()
             sums = eng.eval_read()
+            if eng.image_dtype != dtype0:
+                eng.set_image_dtype(dtype0)
             per = [p.cpu().numpy() if isinstance(p, torch.Tensor) else p for p in per]
             del keep
             per_image = np.concatenate(per, axis=0) if per else np.zeros((0, 2), np.float32)

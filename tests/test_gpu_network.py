@@ -386,3 +386,61 @@ def test_uint8_images_equal_float_images(sd):
     fp32 = _engine(sd, "fp32")
     with pytest.raises(Exception, match="BF16"):
         fp32.set_image_dtype(torch.uint8)
+
+
+def test_uint8_host_paths_and_decode_guards(sd):
+    """(1) after set_image_dtype(uint8) the host-buffer entry points must be fed uint8 pixels -- predict_host / eval_batch on
+    CPU tensors convert (or pass through) accordingly and agree bit for bit with the float route; (2) the fused evaluation route
+    raises the reference's ValueError when a decode guard fires (classification_utils.py:134), here for an image full of NaN."""
+    from spef_b200.modeling import import_model
+    from spef_b200.spe import SPEB200, SPEUtils
+    from spef_b200.tools import evaluation
+    eng = _engine(sd, "bf16")
+    eng.set_ori_histogram(O.ori_histogram(12)[0])
+    g = torch.Generator().manual_seed(5)
+    u8 = torch.randint(0, 256, (3, 3, 240, 384), generator=g, dtype=torch.uint8)
+    f32 = u8.float().div(255)
+    tg = synthetic.synthetic_targets(3)
+    want = eng.predict_host(f32, want_soft=False)
+    eng.eval_reset()
+    per_f = eng.eval_batch(f32, tg["ori"], tg["pos"], want_per_image=True)
+    sums_f = eng.eval_read()
+    eng.set_image_dtype(torch.uint8)
+    for x in (u8, f32):   # uint8 pixels pass through, a float batch is converted back to pixels
+        got = eng.predict_host(x, want_soft=False)
+        np.testing.assert_array_equal(got["ori"], want["ori"])
+        np.testing.assert_array_equal(got["pos"], want["pos"])
+    eng.eval_reset()
+    per_u = eng.eval_batch(u8, tg["ori"], tg["pos"], want_per_image=True)
+    np.testing.assert_array_equal(per_u, per_f)
+    np.testing.assert_array_equal(eng.eval_read(), sums_f)
+    eng.set_image_dtype(torch.float32)
+
+    su = SPEUtils(None, 'classification', 12, 3, False, 'regression', 10, 100, None)
+    loader = synthetic.SyntheticLoader(8, 4)
+    model, _ = import_model({"valid": loader}, 'mobilenet_v2_pytorch', 'ursonet_pytorch', ori_mode='classification',
+                            n_ori_bins=1728, pos_mode='regression', precision="bf16")
+    model.load_state_dict(sd)
+    spe = SPEB200(model, torch.device("cuda:0"), su)
+    rs, _ = evaluation(spe, {"valid": loader}, su, ("valid",))
+    # the same loader as uint8 pixels: the uint8 ingest route is taken automatically and restores the engine's dtype
+    class U8Loader:
+        def __iter__(self):
+            for images, targets in loader:
+                yield {"torch": (images["torch"] * 255).round().to(torch.uint8)}, targets
+    rs8, _ = evaluation(spe, {"valid": U8Loader()}, su, ("valid",))
+    assert spe.engine.image_dtype == torch.float32
+    class QuantLoader:   # float images of exactly those pixels: must give the same numbers as the uint8 route
+        def __iter__(self):
+            for images, targets in loader:
+                yield {"torch": (images["torch"] * 255).round().div(255)}, targets
+    rsq, _ = evaluation(spe, {"valid": QuantLoader()}, su, ("valid",))
+    assert rs8["valid"]["esa"] == rsq["valid"]["esa"] and abs(rs8["valid"]["esa"][0] - rs["valid"]["esa"][0]) < 0.5
+    class NanLoader:
+        def __iter__(self):
+            for images, targets in loader:
+                x = images["torch"].clone()
+                x[1] = float("nan")
+                yield {"torch": x}, targets
+    with pytest.raises(ValueError, match="orientation decoding"):
+        evaluation(spe, {"valid": NanLoader()}, su, ("valid",))

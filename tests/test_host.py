@@ -204,6 +204,19 @@ def test_import_model_api_on_cpu():
     model.load_state_dict(synthetic.synthetic_state_dict(1728, 3))
     assert torch.equal(model.state_dict()["head.pos.0.bias"], torch.tensor([0.0, 0.0, 10.0]))
     assert set(copy_state_dict(sd, model.state_dict()).keys()) == set(sd.keys())
+    assert model.precision == "fp32"  # the reference model family is FP32: BF16 is opt-in (precision='bf16')
+    # manual_copy semantics of the reference (model.py:92-119): per key family, by position; foreign keys (a quantised
+    # checkpoint's act_quant entries) are ignored unless act_quant=True; a mis-shaped copy is refused
+    src = {("module." + k): v + 1 for k, v in synthetic.synthetic_state_dict(1728, 3).items()}
+    src["module.features.0.act_quant.scale"] = torch.ones(1)
+    out = copy_state_dict(src, dict(model.state_dict()))
+    assert list(out.keys()) == list(sd.keys())
+    assert torch.equal(out["head.ori.1.weight"], src["module.head.ori.1.weight"])
+    assert torch.equal(out["features.features.0.1.running_var"], src["module.features.features.0.1.running_var"])
+    bad = dict(src)
+    bad["module.head.ori.1.weight"] = torch.zeros(5, 5)
+    with pytest.raises(ValueError, match="shape mismatch"):
+        copy_state_dict(bad, dict(model.state_dict()))
     with pytest.raises(NotImplementedError):
         import_model(data, 'mobilenet_v2_brevitas', 'ursonet_brevitas', n_ori_bins=1728)
     with pytest.raises(AssertionError):
