@@ -31,7 +31,11 @@ os.dup2(2, 1)
 
 
 def emit(obj):
-    _REAL_STDOUT.write(json.dumps(obj) + "\n")
+    def np_default(o):
+        if isinstance(o, np.generic):
+            return o.item()
+        raise TypeError(f"not JSON serializable: {type(o).__name__}")
+    _REAL_STDOUT.write(json.dumps(obj, default=np_default) + "\n")
     _REAL_STDOUT.flush()
 
 
@@ -51,6 +55,7 @@ def parse_args():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--pw-impl", type=int, default=0, help="0 tcgen05 (default), 1 SIMT cross-check")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the compact decode-sweep / temporal / fp32 / eager-baseline sub-objects")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--layers", action="store_true", help="also print the per-layer table to stderr")
     ap.add_argument("--workload", default="forward", choices=["forward", "decode", "temporal", "ingest"],
@@ -168,16 +173,139 @@ def run_reference(args):
     el = time.perf_counter() - t0
     v = sample * args.steps / el
     desc = f"{sample}-image sample of the {args.batch}-image batch per step, FP32, {cores} host threads"
+    workload = (f"Mobile-URSONet batched inference (forward + softmax + decode + ESA score) on a {sample}-image sample per step of the "
+                f"batch-{args.batch}-per-GPU workload (the full batch takes ~10 s per step on host cores), 240x384, 1728 orientation bins")
     emit({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000 * el / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "Mobile-URSONet batched inference (forward + softmax + decode + ESA score), batch 256 per GPU, 240x384, 1728 orientation bins",
+        "config": {"workload": workload, "sample_images_per_step": sample,
                    "note": "reference = the reference's own PyTorch/NumPy CPU path as restated by oracle/ (the reference is pure Python and has no pip-installable package); rank 0 only"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     })
+
+
+# ------------------------------------------------------------------------------------------------------
+# host placement and the H2D roof (the end-to-end number is PCIe-bound: 283 MB of float images per step)
+# ------------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(local_gpu):
+    """Pin this rank's threads (and therefore its first-touch pinned buffers) to the NUMA node of its GPU's PCIe root.
+    Best effort: returns a description of what was done."""
+    try:
+        pr = torch.cuda.get_device_properties(local_gpu)
+        bus = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        base = f"/sys/bus/pci/devices/{bus}"
+        node = int(open(base + "/numa_node").read().strip())
+        cpus = open(base + "/local_cpulist").read().strip()
+        ids = set()
+        for part in cpus.split(","):
+            if "-" in part:
+                a, b = part.split("-"); ids.update(range(int(a), int(b) + 1))
+            elif part:
+                ids.add(int(part))
+        ids &= os.sched_getaffinity(0)
+        if node >= 0 and ids:
+            os.sched_setaffinity(0, ids)
+            return {"gpu_pci": bus, "numa_node": node, "cpus_bound": len(ids)}
+        return {"gpu_pci": bus, "numa_node": node, "cpus_bound": 0, "note": "no NUMA information for this device: affinity unchanged"}
+    except Exception as ex:  # containers often hide /sys/bus/pci
+        return {"note": f"NUMA binding unavailable ({type(ex).__name__})"}
+
+
+def h2d_roof(host_pinned, dev, dist, reps=4):
+    """GB/s of a plain cudaMemcpyAsync of the step's image buffer on one stream per GPU: rank 0 alone, then all ranks at once."""
+    dst = torch.empty_like(host_pinned, device=dev)
+    nbytes = host_pinned.numel() * host_pinned.element_size()
+
+    def once():
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        e0.record()
+        for _ in range(reps):
+            dst.copy_(host_pinned, non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return nbytes * reps / (e0.elapsed_time(e1) * 1e-3) / 1e9
+
+    once()
+    rank = dist.get_rank() if dist is not None else 0
+    alone = None
+    if dist is not None:
+        dist.barrier()
+    if rank == 0:
+        alone = once()
+    if dist is not None:
+        dist.barrier()
+        conc = once()
+        t = torch.tensor([conc], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        conc = float(t.item())
+        a = torch.tensor([alone if alone is not None else 0.0], dtype=torch.float64, device=dev)
+        dist.all_reduce(a, op=dist.ReduceOp.MAX)
+        alone = float(a.item())
+    else:
+        conc = alone
+    del dst
+    return alone, conc
+
+
+def torch_eager_forward(sd, x):
+    """The reference network as PLAIN PyTorch library calls (cuDNN / cuBLAS through torch.nn.functional): what SPETorch runs on a
+    GPU today (spe_torch.py:57-61) and the only "Blackwell path" the reference has.  Library baseline, not this
+    repo's kernels and not the oracle: BatchNorm unfolded, ReLU separate, exactly the module graph of mobilenet_v2.py."""
+    import torch.nn.functional as F
+    settings = [(1, 16, 1, 1), (6, 24, 2, 2), (6, 32, 3, 2), (6, 64, 4, 2), (6, 96, 3, 1), (6, 160, 3, 2), (6, 320, 1, 1)]
+
+    def cba(y, prefix, stride, groups, act):
+        w = sd[prefix + ".0.weight"]
+        y = F.conv2d(y, w, None, stride, (w.shape[-1] - 1) // 2, 1, groups)
+        y = F.batch_norm(y, sd[prefix + ".1.running_mean"], sd[prefix + ".1.running_var"], sd[prefix + ".1.weight"], sd[prefix + ".1.bias"], False, 0.0, 1e-5)
+        return F.relu(y) if act else y
+
+    x = cba(x, "features.features.0", 2, 1, True)
+    cin, idx = 32, 1
+    for t, c, n, s_ in settings:
+        for i in range(n):
+            stride, hidden, p, j, y = (s_ if i == 0 else 1), cin * t, f"features.features.{idx}.conv", 0, x
+            if t != 1:
+                y = cba(y, f"{p}.{j}", 1, 1, True); j += 1
+            y = cba(y, f"{p}.{j}", stride, hidden, True); j += 1
+            y = cba(y, f"{p}.{j}", 1, 1, False)
+            x = x + y if (stride == 1 and cin == c) else y
+            cin, idx = c, idx + 1
+    x = cba(x, "features.features.18", 1, 1, True)
+    f = x.mean([2, 3])
+    return F.linear(f, sd["head.ori.1.weight"], sd["head.ori.1.bias"]), F.linear(f, sd["head.pos.0.weight"], sd["head.pos.0.bias"])
+
+
+def gpu_eager_baseline(sd, images, steps=5):
+    """images/s of the forward alone through PyTorch eager on the same GPU, bf16 + channels_last (and fp32 for context)."""
+    out = {}
+    for name, dt in (("bf16_channels_last", torch.bfloat16), ("fp32_channels_last", torch.float32)):
+        try:
+            w = {k: (v.to(images.device, dt) if v.is_floating_point() else v.to(images.device)) for k, v in sd.items()}
+            x = images.to(dt).contiguous(memory_format=torch.channels_last)
+            with torch.no_grad():
+                for _ in range(2):
+                    torch_eager_forward(w, x)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(steps):
+                    torch_eager_forward(w, x)
+                e1.record()
+                torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out[name] = {"images_per_s": images.shape[0] / (ms * 1e-3), "ms_per_step": ms}
+            del w, x
+        except Exception as ex:
+            out[name] = {"unavailable": repr(ex)[:200]}
+    torch.cuda.empty_cache()
+    out["what"] = ("forward only (no decode / score) of the same network through torch.nn.functional (cuDNN / cuBLAS library kernels, BatchNorm "
+                   "and ReLU unfused as in the reference module), same batch, CUDA-event timed; torch " + torch.__version__)
+    return out
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -231,6 +359,41 @@ def layer_table(eng, batch, ms):
     return merged
 
 
+def fp32_numbers(B, sd, base, steps=5):
+    """The FP32 engine (north star: logits within 1e-4 relative of the reference) at the same batch: images/s of the same step."""
+    from spef_b200.engine import Engine
+    from spef_b200.tools import synthetic
+    from spef_b200.spe.classification_utils import OrientationSoftClassification
+    dev = torch.device("cuda", torch.cuda.current_device())
+    eng = Engine(IMG[0], IMG[1], N_ORI, 3, False, "fp32", B, dev)
+    eng.load_state_dict(sd)
+    eng.set_ori_histogram(OrientationSoftClassification(12, 3, False).histogram)
+    x = base.repeat((B + base.shape[0] - 1) // base.shape[0], 1, 1, 1)[:B].contiguous().to(dev)
+    tg = synthetic.synthetic_targets(B, 2024)
+    qt, tt = torch.from_numpy(tg["ori"]).to(dev), torch.from_numpy(tg["pos"]).to(dev)
+    eng.eval_reset()
+    for _ in range(2):
+        eng.eval_batch(x, qt, tt)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        eng.eval_batch(x, qt, tt)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    by, fl = eng.forward_cost(B)
+    pk = peaks()
+    eng.close()
+    del x
+    torch.cuda.empty_cache()
+    return {"config": f"Mobile-URSONet FP32 engine (CUDA-core FFMA GEMMs: tcgen05 has no FP32-input MMA and single-pass TF32 misses the 1e-4 gate), batch {B}, same step",
+            "value": B / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "dtype": "f32", "achieved_TFLOPs": fl / (ms * 1e-3) / 1e12,
+            "roofline": {"bound": "hbm", "achieved": by / (ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": by / (ms * 1e-3) / 1e9 / pk["hbm_gbs"], "traffic": None,
+                         "note": "per-layer algorithmic bytes with FP32 activations (101 MB per image); the pointwise layers of this path are FP32-FMA-issue-bound, not HBM-bound"},
+            "cpu_baseline": "the line's cpu_baseline (the reference's FP32 path on the host cores) is the CPU arm of this configuration"}
+
+
 def run_b200(args):
     from spef_b200.engine import Engine
     from spef_b200.tools import synthetic
@@ -244,6 +407,7 @@ def run_b200(args):
             raise SystemExit("launch multi-GPU runs with torch.distributed.run (one process per GPU)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(local)   # before any pinned allocation: first touch places the host buffers on the GPU's node
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -251,7 +415,8 @@ def run_b200(args):
 
     B = args.batch
     eng = Engine(IMG[0], IMG[1], N_ORI, 3, False, args.precision, B, dev, args.pw_impl)
-    eng.load_state_dict(synthetic.synthetic_state_dict(N_ORI, 3))
+    sd_main = synthetic.synthetic_state_dict(N_ORI, 3)
+    eng.load_state_dict(sd_main)
     from spef_b200.spe.classification_utils import OrientationSoftClassification
     eng.set_ori_histogram(OrientationSoftClassification(12, 3, False).histogram)
 
@@ -353,18 +518,24 @@ def run_b200(args):
             u8_s = float(t.item())
         e2e_u8 = {"value": world * B * args.steps / u8_s, "unit": UNIT, "h2d_bytes_per_step": int(u8a.numel() + B * 28),
                   "d2h_bytes_per_step": int(B * 8), "note": "uint8 host images (spef_set_image_dtype(SPEF_IMG_U8)); results bit-identical to float images"}
-    e2e = {"value": world * B * args.steps / e2e_s, "unit": UNIT,
-           "h2d_bytes_per_step": int(host_images.numel() * 4 + B * 28), "d2h_bytes_per_step": int(B * 8),
+    # the H2D roof this end-to-end number runs against: a plain cudaMemcpyAsync of the same pinned 283 MB buffer, rank 0 alone and
+    # all ranks at once (on a shared host the concurrent figure is what caps N-GPU end-to-end scaling, not the kernels)
+    roof_alone, roof_conc = h2d_roof(host_images, dev, dist)
+    h2d_bytes = int(host_images.numel() * 4 + B * 28)
+    e2e_val = world * B * args.steps / e2e_s
+    e2e = {"value": e2e_val, "unit": UNIT,
+           "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": int(B * 8),
+           "h2d_roof_GBps": roof_conc, "h2d_roof_alone_GBps": roof_alone,
+           "achieved_h2d_GBps_per_gpu": e2e_val / world / B * h2d_bytes / 1e9,
+           "frac_of_h2d_roof": (e2e_val / world / B * h2d_bytes / 1e9) / roof_conc if roof_conc else None,
+           "bound": "host-to-device copy (PCIe): float images are 1.11 MB each; the device-timed `value` is what the kernels sustain",
+           "numa": numa,
            "api": "spef_eval_submit_host / spef_eval_wait (pinned host images + targets in, per-image errors out every step; H2D of step i+1 overlaps the kernels of step i)"}
 
     # ---- per-kernel roofline: per-layer CUDA events on the same stream, same inputs, K steps -------------------
     nl = eng.num_layers()
-    ms_layers = np.zeros(nl)
-    reps = max(3, min(args.steps, 10))
-    for _ in range(reps):
-        _, _, ms = eng.forward_timed(images)
-        ms_layers += ms
-    ms_layers /= reps
+    reps = max(5, min(args.steps, 11))
+    ms_layers = np.median(np.stack([eng.forward_timed(images)[2] for _ in range(reps)]), axis=0).astype(np.float64)   # median: one event glitch cannot end up in the table
     pk = peaks()
     rows = layer_table(eng, B, ms_layers)
     fam = {}
@@ -399,14 +570,71 @@ def run_b200(args):
                 "share_of_step": top["ms"] / ms_layers.sum(),
                 "achieved_TFLOPs": top["flops"] / (top["ms"] * 1e-3) / 1e12,
                 "how": f"algorithmic bytes (DESIGN.md section 5: a fused block reads x once and writes y once) / CUDA-event time of that launch on the "
-                       f"launch stream, mean of {reps} passes after the timed region, same inputs",
+                       f"launch stream, median of {reps} passes after the timed region, same inputs; share_of_step and kernels[].share are relative to "
+                       f"the sum of the per-launch event times (a few % above ms_per_step: an event pair per launch adds gaps)",
                 "note": ("fused InvertedResidual kernel: the 6x hidden tensor never reaches HBM, so the launch is far below the HBM roof by design; "
-                         "its limiter is the per-warp latency of the worker warps (ncu source page: FP32 arithmetic is 16 % of the issued instructions, mbarrier polls over half; DRAM 7 %), see "
-                         "profiles/ and DESIGN.md section 4.2; unfused_bytes is what the three per-layer kernels would move") if fused else None,
+                         "its limiter is instruction issue / per-warp latency of the depthwise worker warps and the hand-offs between the single-warp roles "
+                         "(profiles/r02_*, DESIGN.md section 4.2); unfused_bytes is what the three per-layer kernels would move") if fused else None,
                 "unfused_bytes_per_launch": top.get("unfused_bytes")}
     tot_bytes, tot_flops = eng.forward_cost(B)
     shipped_bytes = float(sum(r["bytes"] for r in rows))
     step_ms = ms_total / args.steps
+
+    # ---- multi-GPU parity on hardware: ONE fixed seed-defined dataset, sharded over the ranks + one NCCL SUM
+    # all-reduce of the float64 accumulators, against rank 0 evaluating all of it alone.  Gate: rel <= 1e-12 on the sums.
+    parity = None
+    if dist is not None:
+        n_batches, pb = 8, B
+        def dataset_batch(k):
+            return (synthetic.synthetic_images(min(pb, 32), IMG, 4242 + k).repeat((pb + 31) // 32, 1, 1, 1)[:pb].contiguous().to(dev),
+                    synthetic.synthetic_targets(pb, 777 + k))
+        eng.eval_reset()
+        for k in range(rank, n_batches, world):
+            xk, tk = dataset_batch(k)
+            eng.eval_batch(xk, torch.from_numpy(tk["ori"]).to(dev), torch.from_numpy(tk["pos"]).to(dev))
+        sharded = torch.from_numpy(eng.eval_read()).to(dev)
+        dist.all_reduce(sharded, op=dist.ReduceOp.SUM)
+        sharded = sharded.cpu().numpy()
+        if rank == 0:
+            eng.eval_reset()
+            for k in range(n_batches):
+                xk, tk = dataset_batch(k)
+                eng.eval_batch(xk, torch.from_numpy(tk["ori"]).to(dev), torch.from_numpy(tk["pos"]).to(dev))
+            alone = eng.eval_read()
+            rel = float(np.max(np.abs(sharded[:4] - alone[:4]) / np.maximum(np.abs(alone[:4]), 1e-300)))
+            parity = {"images": int(alone[3]), "rel_diff": rel, "gate": 1e-12, "ok": bool(rel <= 1e-12 and sharded[3] == alone[3]),
+                      "esa_sharded": float((sharded[0] + sharded[1]) / sharded[3]), "esa_one_rank": float((alone[0] + alone[1]) / alone[3]),
+                      "what": f"{n_batches} seed-defined batches of {pb}: ranks evaluate batches r, r+N, ... and all-reduce (NCCL SUM) the 8 float64 sums; "
+                              "rank 0 then evaluates all batches alone; max relative difference of the four sums"}
+        dist.barrier()
+
+    # ---- compact secondary workloads on the driver's line (N = 1 only; each bounded to a few seconds) ------------------------
+    extras = {}
+    if world == 1 and not args.no_extras:
+        del images
+        torch.cuda.empty_cache()
+        cpu = not args.no_cpu_baseline
+        try:
+            extras["decode_sweep"] = {"config": "BASELINE configs[3]: decode kernel isolated, bins per axis 8..32, ~256 MB of logits per size (larger than L2)",
+                                      "rows": decode_sweep(10, 1 << 28, cpu_images=32 if cpu else 0)}
+        except Exception as ex:
+            extras["decode_sweep"] = {"error": repr(ex)[:300]}
+        try:
+            t = temporal_numbers(100, 20, cpu_frames=10 if cpu else 0)
+            t["config"] = "BASELINE configs[4]: temporal stream, Mobile-URSONet+ heads, batch-1 latency and 64 streams, through Engine.temporal_step"
+            extras["temporal"] = t
+        except Exception as ex:
+            extras["temporal"] = {"error": repr(ex)[:300]}
+        try:
+            extras["fp32"] = fp32_numbers(B, sd_main, base)
+        except Exception as ex:
+            extras["fp32"] = {"error": repr(ex)[:300]}
+        try:
+            xb = base.repeat((B + base.shape[0] - 1) // base.shape[0], 1, 1, 1)[:B].contiguous().to(dev)
+            extras["gpu_eager_baseline"] = gpu_eager_baseline(sd_main, xb)
+            del xb
+        except Exception as ex:
+            extras["gpu_eager_baseline"] = {"error": repr(ex)[:300]}
 
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -430,6 +658,9 @@ def run_b200(args):
         "kernels": kernels,
         "esa": {"images": float(s[3]), "esa_score": float((s[0] + s[1]) / s[3]), "flagged": float(s[4] + s[5])},
     }
+    if parity is not None:
+        out["multi_gpu_parity"] = parity
+    out.update(extras)
     if rank == 0 and not args.no_cpu_baseline and world >= 1:
         v, cores, desc = time_cpu(args.cpu_seconds)
         out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
@@ -445,11 +676,14 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
-def run_decode_sweep(args):
-    """BASELINE configs[3]: soft-classification decode kernel isolated, orientation bins per axis 8..32."""
+def decode_sweep(steps, total_bytes=1 << 29, cpu_images=0):
+    """BASELINE configs[3]: soft-classification decode kernel isolated, orientation bins per axis 8..32.  Returns one row per
+    size: images/s and achieved GB/s of the algorithmic bytes (4 n_bins + 16 per image) against the measured HBM roof;
+    cpu_images > 0 adds the oracle's decode_batch (the reference's per-image NumPy + LAPACK loop) on that many images."""
     from spef_b200.engine import Engine
     from spef_b200.spe.classification_utils import OrientationSoftClassification
-    dev = torch.device("cuda", 0)
+    from spef_b200._ffi import ptr
+    dev = torch.device("cuda", torch.cuda.current_device())
     eng = Engine(32, 32, 8, 3, False, "fp32", 1, dev)
     pk = peaks()
     rows = []
@@ -457,17 +691,16 @@ def run_decode_sweep(args):
         hist = OrientationSoftClassification(n_dim, 3, False).histogram
         n = hist.shape[0]
         eng.set_ori_histogram(hist)
-        # ~512 MB of logits (larger than L2), in whole multiples of the persistent grid's warps (148 CTAs x 16 warps, one image
-        # per warp and pass) and, from 32 passes up, of the 32-image eigen-solve batches
+        # logits larger than L2, in whole multiples of the persistent grid's warps (148 CTAs x 16 warps, one image per warp and
+        # pass) and, from 32 passes up, of the 32-image eigen-solve batches
         wave = 16 * torch.cuda.get_device_properties(dev).multi_processor_count
-        passes = max(1, round((1 << 29) / (4 * n) / wave))
+        passes = max(1, round(total_bytes / (4 * n) / wave))
         if passes >= 32:
             passes -= passes % 32
         B = int(passes * wave)
         logits = torch.randn((B, n), device=dev) * 3
         # pre-allocated outputs and the bare C-ABI call in the timed loop: the Python wrapper's allocations would make the
         # GPU wait for the host at these kernel durations
-        from spef_b200._ffi import ptr
         quat = torch.empty((B, 4), device=dev)
         flags = torch.zeros(B, dtype=torch.int32, device=dev)
         st = torch.cuda.current_stream(dev).cuda_stream or None
@@ -480,34 +713,49 @@ def run_decode_sweep(args):
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(args.steps):
+        for _ in range(steps):
             call()
         e1.record()
         torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / args.steps
+        ms = e0.elapsed_time(e1) / steps
         gbs = B * (4 * n + 16) / (ms * 1e-3) / 1e9
-        rows.append({"bins_per_axis": n_dim, "n_bins": n, "batch": B, "ms": ms, "images_per_s": B / (ms * 1e-3),
-                     "achieved_GBps": gbs, "hbm_frac": gbs / pk["hbm_gbs"]})
+        row = {"bins_per_axis": n_dim, "n_bins": n, "batch": B, "ms": ms, "images_per_s": B / (ms * 1e-3),
+               "roofline": {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"], "traffic": None}}
+        if cpu_images > 0:  # the reference's decode on the host cores (oracle restatement; cpu_baseline leg)
+            from oracle import spef_oracle as O
+            z = logits[:cpu_images].cpu().numpy()
+            t0 = time.perf_counter()
+            O.ori_decode_batch(O.softmax(z), np.asarray(hist, np.float64))
+            el = time.perf_counter() - t0
+            row["cpu_baseline"] = {"value": cpu_images / el, "unit": UNIT, "cores": 1, "kind": "port",
+                                   "sample": f"{cpu_images} images, softmax + decode_batch (NumPy + LAPACK eig per image)"}
+        rows.append(row)
         del logits
+    eng.close()
+    return rows
+
+
+def run_decode_sweep(args):
+    rows = decode_sweep(args.steps, 1 << 29, cpu_images=0 if args.no_cpu_baseline else 64)
     emit({"metric": "decode images/sec (softmax + weighted quaternion average, kernel isolated)", "unit": UNIT, "n_gpus": 1,
           "steps": args.steps, "warmup": 3, "dtype": "f32", "data": "synthetic", "higher_is_better": True,
           "value": rows[1]["images_per_s"], "config": {"workload": "BASELINE configs[3]: decode sweep, bins per axis 8..32, logits ~ 3*N(0,1), inputs larger than L2"},
-          "algorithmic_bytes": "4*n_bins + 16 per image", "peak_GBps": pk["hbm_gbs"], "sweep": rows})
+          "algorithmic_bytes": "4*n_bins + 16 per image", "peak_GBps": peaks()["hbm_gbs"], "sweep": rows})
 
 
-def run_temporal(args):
-    """BASELINE configs[4]: Mobile-URSONet+ (1728 + 1000 bins) frame stream through spef_temporal_step:
-    batch-1 latency (plain launches and one CUDA graph per frame) and 64 parallel streams throughput."""
+def temporal_numbers(n_frames_b1=200, n_steps_s64=50, cpu_frames=0):
+    """BASELINE configs[4]: Mobile-URSONet+ (1728 + 1000 bins) frame stream through spef_temporal_step (forward + softmax + decode +
+    adaptive pdf filter + decode): batch-1 latency per frame and 64 parallel streams throughput, both through the call a user makes
+    (Engine.temporal_step: the library replays the few-stream step as ONE CUDA graph after the second frame)."""
     from spef_b200.engine import Engine
     from spef_b200.tools import synthetic
     from spef_b200.spe.classification_utils import OrientationSoftClassification, PositionSoftClassification
-    dev = torch.device("cuda", 0)
+    dev = torch.device("cuda", torch.cuda.current_device())
     sd = synthetic.synthetic_state_dict(N_ORI, 1000)
     ori_hist = OrientationSoftClassification(12, 3, False).histogram
     pos_hist = PositionSoftClassification(10, 100, np.array([-16, -12, -2]), np.array([16, 12, 40])).histogram
-    out = {"metric": "frames/sec and per-frame latency (forward + softmax + decode + adaptive pdf filter + decode)", "unit": "frames/s",
-           "n_gpus": 1, "dtype": "bf16", "data": "synthetic", "higher_is_better": True,
-           "config": {"workload": "BASELINE configs[4]: temporal D-SPEED-shaped stream, Mobile-URSONet+ heads, random frames"}}
+    pk = peaks()
+    out = {}
     for S in (1, 64):
         eng = Engine(IMG[0], IMG[1], N_ORI, 1000, True, "bf16", S, dev)
         eng.load_state_dict(sd)
@@ -518,9 +766,8 @@ def run_temporal(args):
         for _ in range(5):
             eng.temporal_step(frames)
         torch.cuda.synchronize()
-        n_frames = 200 if S == 1 else 50
         lat = []
-        for _ in range(n_frames):
+        for _ in range(n_frames_b1 if S == 1 else n_steps_s64):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             eng.temporal_step(frames)
@@ -529,32 +776,39 @@ def run_temporal(args):
             lat.append(e0.elapsed_time(e1))
         lat = np.array(lat)
         key = "batch1" if S == 1 else "streams64"
-        out[key] = {"p50_ms": float(np.percentile(lat, 50)), "p99_ms": float(np.percentile(lat, 99)),
-                    "frames_per_s": float(S / (np.median(lat) * 1e-3)), "launches_per_frame_step": None}
         l0 = eng.launch_count()
         eng.temporal_step(frames)
-        out[key]["launches_per_frame_step"] = eng.launch_count() - l0
-        if S == 1:  # the 63-launch frame step as ONE CUDA graph: removes the launch gaps that dominate batch-1 latency
-            g = torch.cuda.CUDAGraph()
-            side = torch.cuda.Stream(dev)
-            with torch.cuda.stream(side):
-                eng.temporal_step(frames)
-                torch.cuda.synchronize()
-                with torch.cuda.graph(g, stream=side):
-                    res = eng.temporal_step(frames)
-            torch.cuda.synchronize()
-            glat = []
-            for _ in range(n_frames):
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                g.replay()
-                e1.record()
-                e1.synchronize()
-                glat.append(e0.elapsed_time(e1))
-            glat = np.array(glat)
-            out[key]["cuda_graph"] = {"p50_ms": float(np.percentile(glat, 50)), "p99_ms": float(np.percentile(glat, 99)),
-                                      "frames_per_s": float(1.0 / (np.median(glat) * 1e-3))}
+        by, fl = eng.forward_cost(S)
+        by += 8.9e6                                     # + the BF16 weights, read once per step (not amortised at batch 1)
+        gbs = by / (np.median(lat) * 1e-3) / 1e9
+        out[key] = {"p50_ms": float(np.percentile(lat, 50)), "p99_ms": float(np.percentile(lat, 99)),
+                    "frames_per_s": float(S / (np.median(lat) * 1e-3)), "kernels_per_frame_step": eng.launch_count() - l0,
+                    "cuda_graph_inside_the_library": bool(S <= 8),
+                    "roofline": {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"], "traffic": None,
+                                 "note": "per-layer algorithmic bytes of one forward at this batch + the weights; batch 1 is latency-bound (one frame cannot fill 148 SMs)"}}
         eng.close()
+    if cpu_frames > 0:  # the reference's frame loop on the host cores (oracle restatement; cpu_baseline leg)
+        from oracle import spef_oracle as O
+        cores = len(os.sched_getaffinity(0))
+        torch.set_num_threads(cores)
+        ref = O.TemporalInference(O.ori_histogram(12)[0], O.pos_histogram(10))
+        x = synthetic.synthetic_images(1, IMG, 99)
+        O.forward_fp32(sd, x)
+        t0 = time.perf_counter()
+        for _ in range(cpu_frames):
+            o, p_ = O.forward_fp32(sd, x)
+            ref.step(o[0].numpy(), p_[0].numpy())
+        el = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": cpu_frames / el, "unit": "frames/s", "cores": cores, "kind": "port",
+                               "sample": f"{cpu_frames} frames, batch 1: FP32 forward + softmax + decode + TemporalPDF filters + decode ({el / cpu_frames * 1e3:.1f} ms per frame)"}
+    return out
+
+
+def run_temporal(args):
+    out = {"metric": "frames/sec and per-frame latency (forward + softmax + decode + adaptive pdf filter + decode)", "unit": "frames/s",
+           "n_gpus": 1, "dtype": "bf16", "data": "synthetic", "higher_is_better": True,
+           "config": {"workload": "BASELINE configs[4]: temporal D-SPEED-shaped stream, Mobile-URSONet+ heads, random frames"}}
+    out.update(temporal_numbers(cpu_frames=0 if args.no_cpu_baseline else 20))
     out["value"] = out["streams64"]["frames_per_s"]
     emit(out)
 

@@ -74,6 +74,15 @@ __device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c
   return r;
 }
 
+// ReLU that PROPAGATES NaN like torch.relu (fmaxf(NaN, 0) = 0 would turn a NaN image into a finite pose and hide the reference's
+// "Error during orientation decoding" ValueError, classification_utils.py:134); same FMNMX instruction with the .NaN modifier
+__device__ __forceinline__ float max_nan(float a, float b) {
+  float r;
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ float relu_nan(float x) { return max_nan(x, 0.f); }
+
 // ---- warp reductions -----------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -621,7 +621,7 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
 #pragma unroll
         for (int j = 0; j < TWI; ++j) {
           const float x = __uint_as_float(v[j]);
-          const float y = EXP ? fmaxf(x, nbe) : x;
+          const float y = EXP ? max_nan(x, nbe) : x;   // (NaN-propagating like torch.relu)
           if (j & 1) h.c[j >> 1] = y; else h.a[j >> 1] = y;
         }
         if (EXP) {                                 // (t = 1: TMA zero fill outside the image is already h = 0)

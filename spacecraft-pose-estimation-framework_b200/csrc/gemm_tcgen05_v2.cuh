@@ -92,7 +92,7 @@ __device__ __forceinline__ uint32_t cvt_bf16x2(uint64_t v) {
 }
 __device__ __forceinline__ uint32_t relu_bf16x2(uint32_t v) {
   uint32_t r;
-  asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(0u));
+  asm("max.NaN.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(0u));
   return r;
 }
 
@@ -641,7 +641,7 @@ pw_gemm_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
                           __uint_as_float(v[g * 8 + 6]) + b1.z, __uint_as_float(v[g * 8 + 7]) + b1.w};
             if (p.relu) {
 #pragma unroll
-              for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
+              for (int e = 0; e < 8; ++e) f[e] = relu_nan(f[e]);
             }
             if (m < p.M && n_idx + c0 + g * 8 < p.N) {
               float r[8];

@@ -90,8 +90,8 @@ __global__ void __launch_bounds__(256) stem_conv3x3s2_kernel(const float* __rest
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         f32x2_unpack(acc[t][j], o[2 * j], o[2 * j + 1]);
-        o[2 * j] = fmaxf(o[2 * j], 0.f);
-        o[2 * j + 1] = fmaxf(o[2 * j + 1], 0.f);
+        o[2 * j] = relu_nan(o[2 * j]);
+        o[2 * j + 1] = relu_nan(o[2 * j + 1]);
       }
       Vec8<T>::store(out + (((size_t)b * Ho + oy) * Wo + ox + t) * 32 + cg * 8, o);
     }
@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(256) dwconv3x3_kernel(const T* __restrict__ in
     if (ox < Wo) {
       if (relu) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc[t][e] = fmaxf(acc[t][e], 0.f);
+        for (int e = 0; e < 8; ++e) acc[t][e] = relu_nan(acc[t][e]);
       }
       Vec8<T>::store(ob + (size_t)ox * C, acc[t]);
     }
@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(256) pw_gemm_simt_kernel(const TIn* __restrict
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       o[j] = acc[i][j] + bv[j];
-      if (relu) o[j] = fmaxf(o[j], 0.f);
+      if (relu) o[j] = relu_nan(o[j]);
     }
     if (R != nullptr) {
 #pragma unroll

@@ -178,6 +178,14 @@ struct spef_ctx {
   float* t_prev_still = nullptr; // [S,4]
   float* t_prev_video = nullptr;
   float* t_ws[8] = {nullptr};    // scratch outputs when the caller passes NULL
+  // spef_temporal_step as a CUDA graph (batch-1 / few-stream latency: ~40 launches per frame are launch-bound): one instantiated
+  // graph per call signature (image pointer, n_streams, apply_filter, output pointers), captured the second time a signature is seen
+  struct TGraph { const void* img; int S, filt; spef_temporal_out out; cudaGraphExec_t exec; int64_t launches; };
+  std::vector<TGraph> tgraphs;
+  TGraph tg_last{};                // signature of the previous direct (non-graph) call
+  cudaStream_t cap_stream = nullptr;
+  int temporal_graph = 1;          // SPEF_TEMPORAL_GRAPH=0 disables
+  int temporal_graph_max_streams = 8;
   // ingest plan (spef_resize_frames): taps of both axes for the last (src_h, src_w) seen, one device allocation
   int rz_fixed = 0, rz_gray = 0, rz_gray_off = 0;
   int rz_sh = 0, rz_sw = 0, rz_hks = 0, rz_vks = 0, rz_band = 0, rz_max_rows = 0, rz_pitch = 0;
@@ -334,6 +342,7 @@ extern "C" int spef_create(spef_ctx** out, const spef_config* cfg) {
   if (const char* e5 = getenv("SPEF_FB_DEBUG_SKIP")) ctx->fb_debug_skip = atoi(e5);
   if (getenv("SPEF_FBT_NO_STACK")) ctx->fbt_no_stack = 1;
   if (getenv("SPEF_HEAD_WIDE")) ctx->head_wide = 1;
+  if (const char* e5 = getenv("SPEF_TEMPORAL_GRAPH")) ctx->temporal_graph = atoi(e5) ? 1 : 0;
   if (const char* e7 = getenv("SPEF_GEMM_NDG")) ctx->gemm_ndg = (atoi(e7) == 1) ? 1 : 2;
   if (const char* e6 = getenv("SPEF_GEMM_NSW")) ctx->gemm_nsw = (atoi(e6) == 8 && ctx->gemm_ndg == 1) ? 8 : 4;
   if (const char* e8 = getenv("SPEF_FUSE")) ctx->fuse = atoi(e8) ? 1 : 0;
@@ -422,6 +431,8 @@ extern "C" void spef_destroy(spef_ctx* ctx) {
     if (ctx->pipe_consumed[s]) cudaEventDestroy(ctx->pipe_consumed[s]);
   }
   if (ctx->pipe_copy_stream) cudaStreamDestroy(ctx->pipe_copy_stream);
+  for (auto& g : ctx->tgraphs) cudaGraphExecDestroy(g.exec);
+  if (ctx->cap_stream) cudaStreamDestroy(ctx->cap_stream);
   delete ctx;
 }
 
@@ -808,6 +819,9 @@ extern "C" int spef_finalize_weights(spef_ctx* ctx) {
     CK(cudaFuncSetAttribute(dw::dwconv3x3_tma_kernel<2, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem));
     CK(cudaFuncSetAttribute(dw::dwconv3x3_tma_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem));
   }
+  for (auto& g : ctx->tgraphs) cudaGraphExecDestroy(g.exec);   // captured launches hold the old weight pointers
+  ctx->tgraphs.clear();
+  ctx->tg_last = spef_ctx::TGraph{};
   ctx->host_tensors.clear();
   ctx->plan_batch = -1;
   for (Layer& l : ctx->layers) l.plan_batch = -1;
@@ -1835,6 +1849,9 @@ extern "C" int spef_temporal_reset(spef_ctx* ctx, int32_t S, void* stream) {
   CK(cudaSetDevice(ctx->cfg.device));
   cudaStream_t st = (cudaStream_t)stream;
   if (S != ctx->t_streams) {
+    for (auto& g : ctx->tgraphs) cudaGraphExecDestroy(g.exec);   // captured launches hold the old state pointers
+    ctx->tgraphs.clear();
+    ctx->tg_last = spef_ctx::TGraph{};
     void** ptrs[] = {(void**)&ctx->t_ori_state, (void**)&ctx->t_pos_state, (void**)&ctx->t_has, (void**)&ctx->t_prev_still, (void**)&ctx->t_prev_video};
     for (void** p : ptrs) { if (*p) cudaFree(*p); *p = nullptr; }
     for (int i = 0; i < 8; ++i) { if (ctx->t_ws[i]) cudaFree(ctx->t_ws[i]); ctx->t_ws[i] = nullptr; }
@@ -1905,6 +1922,57 @@ extern "C" int spef_temporal_step(spef_ctx* ctx, const float* images_dev, int32_
   if (!images_dev) return fail(ctx, SPEF_ERR_INVALID, "spef_temporal_step: NULL argument");
   CK(cudaSetDevice(ctx->cfg.device));
   cudaStream_t st = (cudaStream_t)stream;
+  if (S != ctx->t_streams) return fail(ctx, SPEF_ERR_STATE, "temporal step: n_streams %d != %d set by spef_temporal_reset", S, ctx->t_streams);
+  // Few streams: the step is ~40 short launches, i.e. launch-bound (0.42 ms per frame at batch 1 against 0.30 ms as one graph).
+  // A call signature seen twice in a row is captured once (on an internal stream: the caller's may be the legacy default
+  // stream, which cannot capture) and replayed from then on; callers that hand over new pointers every frame stay on direct
+  // launches.  Everything the step touches besides its arguments is owned by the ctx (weights, activations, filter state).
+  if (ctx->temporal_graph && S <= ctx->temporal_graph_max_streams) {
+    spef_ctx::TGraph sig{};
+    sig.img = images_dev; sig.S = S; sig.filt = apply_filter ? 1 : 0;
+    if (out) sig.out = *out;
+    auto same = [&](const spef_ctx::TGraph& g) {
+      return g.img == sig.img && g.S == sig.S && g.filt == sig.filt && memcmp(&g.out, &sig.out, sizeof(sig.out)) == 0;
+    };
+    for (auto& g : ctx->tgraphs)
+      if (same(g)) {
+        CK(cudaGraphLaunch(g.exec, st));
+        ctx->launches += g.launches;
+        return SPEF_OK;
+      }
+    if (ctx->tg_last.S == S && same(ctx->tg_last)) {
+      if (!ctx->cap_stream) CK(cudaStreamCreateWithFlags(&ctx->cap_stream, cudaStreamNonBlocking));
+      const int64_t l0 = ctx->launches;
+      CK(cudaStreamBeginCapture(ctx->cap_stream, cudaStreamCaptureModeThreadLocal));
+      rc = forward_internal(ctx, images_dev, S, ctx->cap_stream, nullptr);
+      if (!rc) rc = temporal_from_logits(ctx, ctx->head_out, ctx->head_pad, ctx->head_out + ctx->cfg.n_ori, ctx->head_pad, S, apply_filter, out, ctx->cap_stream);
+      cudaGraph_t graph = nullptr;
+      const cudaError_t ce = cudaStreamEndCapture(ctx->cap_stream, &graph);
+      const int64_t n_launch = ctx->launches - l0;
+      ctx->launches = l0;   // nothing has run yet
+      if (rc || ce != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        ctx->temporal_graph = 0;   // capture is not possible in this process: direct launches from now on
+        if (rc) return rc;
+      } else {
+        cudaGraphExec_t exec = nullptr;
+        const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ie == cudaSuccess) {
+          if (ctx->tgraphs.size() >= 4) { cudaGraphExecDestroy(ctx->tgraphs.front().exec); ctx->tgraphs.erase(ctx->tgraphs.begin()); }
+          sig.exec = exec; sig.launches = n_launch;
+          ctx->tgraphs.push_back(sig);
+          CK(cudaGraphLaunch(exec, st));
+          ctx->launches += n_launch;
+          return SPEF_OK;
+        }
+        cudaGetLastError();
+        ctx->temporal_graph = 0;
+      }
+    }
+    ctx->tg_last = sig;
+  }
   if ((rc = forward_internal(ctx, images_dev, S, st, nullptr))) return rc;
   return temporal_from_logits(ctx, ctx->head_out, ctx->head_pad, ctx->head_out + ctx->cfg.n_ori, ctx->head_pad, S, apply_filter, out, st);
 }

@@ -18,7 +18,7 @@ def _require_cuda(device) -> torch.device:
     if not torch.cuda.is_available():
         raise RuntimeError("spef_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
     # no device given: the CURRENT device (one process per GPU sets it once; "cuda:0" would put every rank's helper contexts on GPU 0)
-    dev = torch.device(device if device is not None else ("cuda", torch.cuda.current_device()))
+    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
     if dev.type != "cuda":
         raise RuntimeError(f"spef_b200 runs on CUDA devices only, got {dev}")
     return torch.device("cuda", dev.index if dev.index is not None else torch.cuda.current_device())
@@ -426,11 +426,45 @@ class Engine:
         self._ck(self.lib.spef_temporal_step_logits(self._h, ptr(o), ptr(p), S, C.byref(st), _stream(self.device)))
         return t
 
+    def _temporal_slots(self, S: int):
+        """Persistent device buffers of the frame step for S streams: the frame staging tensor and ONE flat output buffer the
+        spef_temporal_out pointers are carved from.  Stable pointers are what lets libspef_b200 replay the step as a CUDA graph
+        (spef_temporal_step captures a call signature it sees twice); the caller gets a clone of the flat buffer, so results
+        of earlier frames stay valid."""
+        key = (S, self.image_dtype)
+        slot = self._tslots.get(key) if hasattr(self, "_tslots") else None
+        if slot is None:
+            if not hasattr(self, "_tslots"):
+                self._tslots = {}
+            sizes = [(n, S * w) for n, w in (("still_ori_soft", self.n_ori), ("still_pos_soft", self.n_pos), ("still_quat", 4), ("still_pos", 3),
+                                             ("video_ori_soft", self.n_ori), ("video_pos_soft", self.n_pos), ("video_quat", 4), ("video_pos", 3),
+                                             ("ori_distance", 1), ("pos_distance", 1), ("flags", 1))]
+            offs, total = {}, 0
+            for n, sz in sizes:
+                offs[n] = (total, sz)
+                total += (sz + 3) // 4 * 4           # 16-byte aligned slices
+            flat = torch.zeros(total, dtype=torch.float32, device=self.device)
+            frame = torch.empty((S, 3, self.img_h, self.img_w), dtype=self.image_dtype, device=self.device)
+            st = SpefTemporalOut(*[flat.data_ptr() + 4 * offs[n][0] for n, _ in SpefTemporalOut._fields_])
+            slot = self._tslots[key] = (frame, flat, offs, st)
+        return slot
+
     def temporal_step(self, images: torch.Tensor, apply_filter: bool = True) -> Dict[str, torch.Tensor]:
         S = self._check_images(images)
-        x = self._dev_img(images)
-        t, st = self._temporal_out(S)
-        self._ck(self.lib.spef_temporal_step(self._h, ptr(x), S, int(apply_filter), C.byref(st), _stream(self.device)))
+        frame, flat, offs, st = self._temporal_slots(S)
+        x = images.detach()
+        if x.dtype != self.image_dtype:
+            x = self._dev_img(x)
+        frame.copy_(x, non_blocking=True)
+        self._ck(self.lib.spef_temporal_step(self._h, ptr(frame), S, int(apply_filter), C.byref(st), _stream(self.device)))
+        res = flat.clone()
+        shapes = {"still_ori_soft": (S, self.n_ori), "still_pos_soft": (S, self.n_pos), "still_quat": (S, 4), "still_pos": (S, 3),
+                  "video_ori_soft": (S, self.n_ori), "video_pos_soft": (S, self.n_pos), "video_quat": (S, 4), "video_pos": (S, 3),
+                  "ori_distance": (S,), "pos_distance": (S,), "flags": (S,)}
+        t = {}
+        for n, (o, sz) in offs.items():
+            v = res[o:o + sz].view(shapes[n])
+            t[n] = v.view(torch.int32) if n == "flags" else v
         if not apply_filter:
             t = {k: v for k, v in t.items() if not k.startswith("video_") and not k.endswith("_distance")}
         return t
