@@ -152,6 +152,16 @@ __device__ __forceinline__ void mbar_wait_hw(uint32_t bar, uint32_t parity) {
   }
 #endif
 }
+// Wait of a role with slack (an epilogue warp that owns every eighth tile, the TMA producer several tiles ahead): back off between
+// probes.  ncu: eight epilogue warps in the lean spin above executed 36 % of ALL instructions of the kernel, on the schedulers the
+// depthwise workers need.
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity, uint32_t ns) {
+  uint32_t it = 0;
+  while (!tc::mbar_try_wait(bar, parity)) {
+    __nanosleep(ns);
+    if (++it > (1u << 22)) __trap();
+  }
+}
 __device__ __forceinline__ float lds_f32(uint32_t saddr) {
   float r;
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(saddr));
@@ -193,6 +203,13 @@ __device__ __forceinline__ uint32_t bias_relu_bf16x2(uint32_t a0, uint32_t a1, u
 
 // S: depthwise stride; TH: output rows of a tile (compile time: the row loop is fully unrolled, so the register window
 // rotates by renaming and every shared-memory store address is a constant)
+// Measured and NOT kept (round 2, B = 256, after the worker / epilogue / issuer diets):
+//   * three worker groups on 3 x 6 stride-2 tiles (96 TMEM columns per stage, four stages): block 2 288 -> 327 us -- a third more
+//     items, and the per-item cost of the single-warp issuer roles does not shrink with the tile;
+//   * row split (two worker warps per TMEM lane quarter and group, each computing half of the tile's output rows, 16 worker warps
+//     at 96 registers): block 2 288 -> 366 us, block 4 156 -> 190 us -- the extra halo rows, spills and issue contention cost more
+//     than the halved per-item latency gains.  The worker loop is not simply latency-bound per warp: ncu shows each worker warp
+//     issuing 26 % of the time with no dominant stall reason (wait 17 %, TMEM / barrier scoreboard 13 %, not selected 12 %).
 template <int S, int TH, int NG, bool EXP>
 __global__ void __launch_bounds__(32 * (CTRL_WARPS + NG * GWT), 1)
 fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWe,
@@ -325,7 +342,7 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       uint32_t xph = 0, wph = 0;
       for (int i = 0; i < my_tiles; ++i) {
         const int oy0 = ty * TH, ox0 = tx * TW * p.stack;
-        mbar_wait_hw(tc::smem_u32(&x_empty[xs]), xph ^ 1u);
+        mbar_wait_sleep(tc::smem_u32(&x_empty[xs]), xph ^ 1u, 100);
         {
           const uint32_t fbar = tc::smem_u32(&x_full[xs]);
           tc::mbar_arrive_expect_tx(fbar, x_tx);
@@ -479,7 +496,8 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       const int gy = oy0 + oy_l;
       const bool row_ok = lane_ok && gy < p.Ho;
       const int pix0 = tb * img_px + gy * row_px + ox0 + ox_l;     // strip 0; strip st is st * TW pixels to the right
-      mbar_wait_hw(tc::smem_u32(&proj_full[i & (N_PFULL - 1)]), (uint32_t)((i >> 3) & 1));
+      if (ROT) mbar_wait_sleep(tc::smem_u32(&proj_full[i & (N_PFULL - 1)]), (uint32_t)((i >> 3) & 1), 200);
+      else mbar_wait_hw(tc::smem_u32(&proj_full[i & (N_PFULL - 1)]), (uint32_t)((i >> 3) & 1));
       tc::tcgen05_fence_after();
       if (warp == FIRST_EPI_WARP && lane == 0) FBT_TRACE(i * p.n_chunks, 13);
       // one strip and Cout <= 32: the accumulator row is a single tcgen05.ld -- hand the TMEM stage back as soon as it is in registers
