@@ -130,6 +130,9 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity
       : "memory");
   return ok != 0;
 }
+#ifndef SPEF_FBT_EPI_SLEEP
+#define SPEF_FBT_EPI_SLEEP 200   // ns between probes of an epilogue warp that owns every eighth tile (ROT)
+#endif
 #ifndef SPEF_FBT_WAIT_MODE
 #define SPEF_FBT_WAIT_MODE 0   // build-time experiment knob: 0 lean try_wait spin, 1 try_wait with a 1 ms suspend hint, 2 nanosleep poll
 #endif
@@ -496,7 +499,7 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       const int gy = oy0 + oy_l;
       const bool row_ok = lane_ok && gy < p.Ho;
       const int pix0 = tb * img_px + gy * row_px + ox0 + ox_l;     // strip 0; strip st is st * TW pixels to the right
-      if (ROT) mbar_wait_sleep(tc::smem_u32(&proj_full[i & (N_PFULL - 1)]), (uint32_t)((i >> 3) & 1), 200);
+      if (ROT) mbar_wait_sleep(tc::smem_u32(&proj_full[i & (N_PFULL - 1)]), (uint32_t)((i >> 3) & 1), SPEF_FBT_EPI_SLEEP);
       else mbar_wait_hw(tc::smem_u32(&proj_full[i & (N_PFULL - 1)]), (uint32_t)((i >> 3) & 1));
       tc::tcgen05_fence_after();
       if (warp == FIRST_EPI_WARP && lane == 0) FBT_TRACE(i * p.n_chunks, 13);

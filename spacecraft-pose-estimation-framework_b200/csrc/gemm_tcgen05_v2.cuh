@@ -202,24 +202,41 @@ pw_gemm_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
         }
         if (n_tiles == 1) { tm += gridDim.x; } else { const int t2 = tile + (int)gridDim.x; tm = t2 / n_tiles; tn = t2 % n_tiles; }
       }
-      if (PROD && p.patch_mode) {   // stem: stage the input patch of every tile of this CTA (ring of PATCH_STAGES)
-        const int tiles_img = (p.out_h / 2) * p.patch_tiles_x;
-        const uint32_t cbytes = (uint32_t)(p.patch_w * 5 * 3 * (p.img_u8 ? 1 : 4));   // one column chunk
-        const uint32_t pbytes = cbytes * (uint32_t)p.patch_chunks;
-        int ps = 0;
-        uint32_t pph = 0;
-        // The innermost TMA coordinate must stay 16-byte aligned (x = -1 faulted with "illegal instruction" while -1 in an outer
-        // dimension is fine): the patch starts patch_x0 = 4 (f32) or 16 (u8) pixels left of the tile, pixel column -1 = patch column patch_x0 - 1.
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-          const int b = tile / tiles_img, r = tile - b * tiles_img;
-          const int ty = r / p.patch_tiles_x, tx = r - ty * p.patch_tiles_x;
+    }
+    if (PROD && p.patch_mode) {   // stem: stage the input patch of every tile of this CTA (ring of PATCH_STAGES)
+      // ncu (round 2, wait sites of the stem): this single-thread loop never waited for a free patch slot while the im2col producers
+      // polled patch_full 18x per tile and the MMA issuer full_bar 5x -- the patch issue itself (two divisions, five sequential
+      // TMA launches with their address arithmetic, ~110 dependent instructions) paced the kernel at ~1150 cycles per 128-pixel
+      // tile.  Now the whole warp runs the loop: tile coordinates are carried, lane 0 waits for the slot and arms the barrier, and
+      // lane ch issues column chunk ch.
+      const int tiles_img = (p.out_h / 2) * p.patch_tiles_x;
+      const uint32_t cbytes = (uint32_t)(p.patch_w * 5 * 3 * (p.img_u8 ? 1 : 4));   // one column chunk
+      const uint32_t pbytes = cbytes * (uint32_t)p.patch_chunks;
+      int ps = 0;
+      uint32_t pph = 0;
+      int tb = (int)blockIdx.x / tiles_img, ty, tx;
+      {
+        const int r = (int)blockIdx.x - tb * tiles_img;
+        ty = r / p.patch_tiles_x; tx = r - ty * p.patch_tiles_x;
+      }
+      const int g = (int)gridDim.x, rows_img = p.out_h / 2;
+      const int db = g / tiles_img, dr = g - db * tiles_img, dty = dr / p.patch_tiles_x, dtx = dr - dty * p.patch_tiles_x;
+      // The innermost TMA coordinate must stay 16-byte aligned (x = -1 faulted with "illegal instruction" while -1 in an outer
+      // dimension is fine): the patch starts patch_x0 = 4 (f32) or 16 (u8) pixels left of the tile, pixel column -1 = patch column patch_x0 - 1.
+      const uint32_t my_dst = smem_u32(patch_s) + (uint32_t)lane * cbytes;
+      const int my_x = lane * p.patch_w - p.patch_x0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const uint32_t fb = smem_u32(&patch_full[ps]);
+        if (lane == 0) {
           mbar_wait(smem_u32(&patch_empty[ps]), pph ^ 1);
-          const uint32_t fb = smem_u32(&patch_full[ps]);
           mbar_arrive_expect_tx(fb, pbytes);
-          for (int ch = 0; ch < p.patch_chunks; ++ch)
-            tma_load_3d_img(smem_u32(patch_s + (size_t)ps * PATCH_STAGE_BYTES + (size_t)ch * cbytes), &tmA, tx * 128 - p.patch_x0 + ch * p.patch_w, ty * 4 - 1, 3 * b, fb);
-          if (++ps == PATCH_STAGES) { ps = 0; pph ^= 1; }
         }
+        __syncwarp();
+        if (lane < p.patch_chunks) tma_load_3d_img(my_dst + (uint32_t)ps * (uint32_t)PATCH_STAGE_BYTES, &tmA, tx * 128 + my_x, ty * 4 - 1, 3 * tb, fb);
+        if (++ps == PATCH_STAGES) { ps = 0; pph ^= 1; }
+        tx += dtx; ty += dty; tb += db;
+        if (tx >= p.patch_tiles_x) { tx -= p.patch_tiles_x; ++ty; }
+        if (ty >= rows_img) { ty -= rows_img; ++tb; }
       }
     }
     __syncwarp();
