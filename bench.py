@@ -350,6 +350,17 @@ def layer_table(eng, batch, ms):
             merged.append(r)
             continue
         grp = rows[r["layer"]:r["layer"] + bi["n_layers"]]
+        if bi["fused"] == 3:
+            # expand conv as a GEMM (its own row), then depthwise + project in one kernel: reads the hidden tensor once, writes y
+            # (+ reads the skip input); timed in the slot of the depthwise layer
+            merged.append(r)
+            dwl, pj = grp[1], grp[2]
+            skip.update((dwl["layer"], pj["layer"]))
+            merged.append({"layer": dwl["layer"], "kernel": "dw_project_kernel", "cin": dwl["cin"], "cout": pj["cout"], "hw": pj["hw"],
+                           "stride": dwl["stride"], "bytes": (dwl["ein"] + pj["eout"] * (2 if pj["residual"] else 1)) * esz,
+                           "flops": dwl["flops"] + pj["flops"], "ms": dwl["ms"] + pj["ms"], "tile": f"{bi['tile_h']}x{bi['tile_w']}",
+                           "unfused_bytes": dwl["bytes"] + pj["bytes"]})
+            continue
         skip.update(g["layer"] for g in grp)
         merged.append({"layer": r["layer"], "kernel": "fused_block_kernel", "cin": grp[0]["cin"], "cout": grp[-1]["cout"],
                        "hw": grp[-1]["hw"], "stride": max(g["stride"] for g in grp),

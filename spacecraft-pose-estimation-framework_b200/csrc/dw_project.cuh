@@ -1,0 +1,343 @@
+// Depthwise 3x3 (stride 1, BN folded, ReLU) fused into the project 1x1 conv of an InvertedResidual block:
+//   y = [x +] Wp * relu(dw3x3(h) + bd) + bp        (reference: src/modeling/common/pytorch_layers.py:82-98)
+// for the wide blocks (hidden width 576 / 960) whose weights do not fit next to the tiles of the single-kernel block
+// (fused_block_t.cuh).  Per-layer kernels move the depthwise output through HBM twice (write + read, 2 x 106 MB at
+// 576 ch @ 15x24, batch 256); here it is born in shared memory as the A operand of the project GEMM:
+//
+//   warp 0        TMA: input box {64 channels, W+2, TH+2} of the hidden tensor per (tile, K chunk); the 1-pixel halo and the
+//                 image border are TMA out-of-bounds zero fill (box origin at x = -1, y = y0 - 1)
+//   warp 3        TMA: the [N x 64] chunk of the project weights of the same K chunk (L2-resident, 128B-swizzled)
+//   warps 4-15    depthwise producers: thread = (4 channels, run of 4 output pixels, 2 output rows); 4 x 6 LDS.64 of input +
+//                 10 LDS.128 of folded FP32 weights / bias, packed FFMA2 in the order of dwconv3x3_tma_kernel (bias, then taps
+//                 row-major), cvt.rn.relu.bf16x2, one 8-byte store per pixel into the K-major SWIZZLE_128B A stage
+//   warp 1        tcgen05.mma (M = 128 pixels, N = Cout or two halves of it, K = 16 x 4 per chunk), FP32 accumulators in TMEM
+//   warps 16-19   epilogue: tcgen05.ld -> + bias (+ skip input) -> BF16 -> 16-byte global stores
+//
+// A tile is TH full-width rows of one image (5 x 24 = 120 or 8 x 12 = 96 pixels): rows of a tile are contiguous in NHWC, so
+// pixel p of tile t is pixel t * n_px + p of the tensor.  Same rounding points and FP32 operation order as the per-layer
+// kernels (depthwise output rounded once to BF16, GEMM K chunks of 64 in order): results are bit-identical to them.
+#pragma once
+#include "dwconv_tma.cuh"
+#include "gemm_tcgen05_v2.cuh"
+
+namespace spef {
+namespace dwp {
+
+constexpr int PROD_WARPS = 12;
+constexpr int EPI_WARPS = 4;
+constexpr int NT = 128 + 32 * PROD_WARPS + 32 * EPI_WARPS;
+constexpr int MAX_IN = 4, MAX_AB = 4, MAX_ACC = 2;
+constexpr int A_BYTES = 128 * 128;          // one K chunk of the A operand: 128 pixels x 64 channels
+constexpr int WDW_CHUNK_FLOATS = 10 * 64;   // per K chunk: 9 taps + bias, 64 channels each
+
+struct DwpParams {
+  int B, H, W, C, N;            // hidden map (= output map, stride 1), hidden channels (GEMM K), project outputs
+  int TH, tiles_y, n_px;        // tile = TH full-width rows; n_px = TH * W <= 128
+  int k_chunks;                 // C / 64
+  int in_stages, ab_stages, acc_stages, acc_stride;
+  int n_half, nh;               // N = n_half * nh: one MMA per half (nh <= 256, multiple of 16)
+  int in_bytes, in_stride;      // TMA box bytes (TH+2)(W+2)*128 and the 1024-aligned stage pitch
+  const float* wdw;             // depthwise weights + bias per K chunk [k_chunks][10][64]
+  const float* bias;            // project bias [N]
+  const bf16* residual;         // block input [B,H,W,N] or nullptr
+  bf16* out;                    // [B,H,W,N]
+};
+
+__host__ __device__ inline int ab_stride(const DwpParams& p) { return A_BYTES + p.N * 128; }
+inline size_t smem_bytes(const DwpParams& p) {
+  return 1024 + (size_t)p.ab_stages * ab_stride(p) + (size_t)p.in_stages * p.in_stride + (size_t)p.k_chunks * WDW_CHUNK_FLOATS * 4 +
+         (size_t)p.N * 4 + 512;
+}
+
+__global__ void __launch_bounds__(NT, 1)
+dw_project_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const DwpParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int abs_ = ab_stride(p);
+  uint8_t* ab_s = smem;                                            // [ab_stages][A 16 KB | Wp chunk N x 128 B]
+  uint8_t* in_s = ab_s + (size_t)p.ab_stages * abs_;               // [in_stages][(TH+2)(W+2) pixels x 128 B]
+  float* wdw_s = reinterpret_cast<float*>(in_s + (size_t)p.in_stages * p.in_stride);
+  float* bias_s = wdw_s + (size_t)p.k_chunks * WDW_CHUNK_FLOATS;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + p.N);
+  uint64_t* in_full = bars;                 // [MAX_IN]   TMA -> producers
+  uint64_t* in_empty = in_full + MAX_IN;    // [MAX_IN]   producers -> TMA
+  uint64_t* ab_full = in_empty + MAX_IN;    // [MAX_AB]   producers (A) + TMA (Wp chunk) -> MMA
+  uint64_t* ab_empty = ab_full + MAX_AB;    // [MAX_AB]   MMA -> producers, weight loader
+  uint64_t* acc_full = ab_empty + MAX_AB;   // [MAX_ACC]  MMA -> epilogue
+  uint64_t* acc_empty = acc_full + MAX_ACC; // [MAX_ACC]  epilogue -> MMA
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(acc_empty + MAX_ACC);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = p.B * p.tiles_y;
+
+  for (int i = threadIdx.x; i < p.k_chunks * WDW_CHUNK_FLOATS; i += NT) wdw_s[i] = p.wdw[i];
+  for (int i = threadIdx.x; i < p.N; i += NT) bias_s[i] = p.bias[i];
+  // rows >= n_px of every A stage are never written by the producers: zero them once (their accumulator rows are not stored)
+  {
+    const int tail16 = (128 - p.n_px) * 8;   // 16-byte pieces
+    for (int s = 0; s < p.ab_stages; ++s)
+      for (int i = threadIdx.x; i < tail16; i += NT)
+        *reinterpret_cast<uint4*>(ab_s + (size_t)s * abs_ + (size_t)p.n_px * 128 + (size_t)i * 16) = make_uint4(0u, 0u, 0u, 0u);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 0 && lane == 0) {
+    tc::tma_prefetch_desc(&tmX);
+    tc::tma_prefetch_desc(&tmW);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < MAX_IN; ++i) {
+      tc::mbar_init(tc::smem_u32(&in_full[i]), 1);
+      tc::mbar_init(tc::smem_u32(&in_empty[i]), PROD_WARPS);
+    }
+    for (int i = 0; i < MAX_AB; ++i) {
+      tc::mbar_init(tc::smem_u32(&ab_full[i]), PROD_WARPS + 1);   // one arrive per producer warp + the weight TMA
+      tc::mbar_init(tc::smem_u32(&ab_empty[i]), 1);
+    }
+    for (int i = 0; i < MAX_ACC; ++i) {
+      tc::mbar_init(tc::smem_u32(&acc_full[i]), 1);
+      tc::mbar_init(tc::smem_u32(&acc_empty[i]), EPI_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(tmem_ptr_s)), "r"(tc::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  tc::tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_s;
+
+  if (warp == 0) {
+    // ===================== TMA: hidden-tensor boxes =====================
+    if (lane == 0) {
+      int is = 0;
+      uint32_t ph = 0;
+      int b = (int)blockIdx.x / p.tiles_y, ty = (int)blockIdx.x % p.tiles_y;
+      const int db = (int)gridDim.x / p.tiles_y, dty = (int)gridDim.x % p.tiles_y;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int kc = 0; kc < p.k_chunks; ++kc) {
+          tc::mbar_wait(tc::smem_u32(&in_empty[is]), ph ^ 1);
+          const uint32_t fb = tc::smem_u32(&in_full[is]);
+          tc::mbar_arrive_expect_tx(fb, (uint32_t)p.in_bytes);
+          dw::tma_load_4d(tc::smem_u32(in_s + (size_t)is * p.in_stride), &tmX, kc * 64, -1, ty * p.TH - 1, b, fb);
+          if (++is == p.in_stages) { is = 0; ph ^= 1; }
+        }
+        b += db; ty += dty;
+        if (ty >= p.tiles_y) { ty -= p.tiles_y; ++b; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 3) {
+    // ===================== TMA: project-weight chunks =====================
+    if (lane == 0) {
+      int as = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int kc = 0; kc < p.k_chunks; ++kc) {
+          tc::mbar_wait(tc::smem_u32(&ab_empty[as]), ph ^ 1);
+          const uint32_t fb = tc::smem_u32(&ab_full[as]);
+          tc::mbar_arrive_expect_tx(fb, (uint32_t)(p.N * 128));
+          const uint32_t dst = tc::smem_u32(ab_s + (size_t)as * abs_ + A_BYTES);
+          for (int h = 0; h < p.n_half; ++h) tc::tma_load_2d(dst + (uint32_t)(h * p.nh * 128), &tmW, kc * 64, h * p.nh, fb);
+          if (++as == p.ab_stages) { as = 0; ph ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer (whole warp converged, one elected lane issues) =====================
+    const uint32_t idesc = tc::make_idesc_bf16(128, p.nh);
+    const uint64_t a_base = tc::make_smem_desc_sw128(tc::smem_u32(ab_s));
+    const uint64_t b_base = tc::make_smem_desc_sw128(tc::smem_u32(ab_s + A_BYTES));
+    const uint32_t s_step = (uint32_t)abs_ >> 4, h_step = (uint32_t)(p.nh * 128) >> 4;
+    int as = 0, acc = 0;
+    uint32_t ph = 0, acc_ph = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      tc::mbar_wait(tc::smem_u32(&acc_empty[acc]), acc_ph ^ 1);
+      tc::tcgen05_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_stride);
+      for (int kc = 0; kc < p.k_chunks; ++kc) {
+        tc::mbar_wait(tc::smem_u32(&ab_full[as]), ph);
+        tc::tcgen05_fence_after();
+        const uint64_t a_desc = a_base + (uint64_t)((uint32_t)as * s_step);
+        const uint64_t b_desc = b_base + (uint64_t)((uint32_t)as * s_step);
+        for (int h = 0; h < p.n_half; ++h)
+          for (uint32_t k = 0; k < 4; ++k)
+            tc::mma_elect_v2(d_tmem + (uint32_t)(h * p.nh), a_desc + (uint64_t)(k * 2u), b_desc + (uint64_t)((uint32_t)h * h_step + k * 2u), idesc,
+                             (kc > 0 || k > 0) ? 1u : 0u);
+        tc::commit_elect_v2(tc::smem_u32(&ab_empty[as]));
+        if (++as == p.ab_stages) { as = 0; ph ^= 1; }
+      }
+      tc::commit_elect_v2(tc::smem_u32(&acc_full[acc]));
+      if (++acc == p.acc_stages) { acc = 0; acc_ph ^= 1; }
+    }
+    __syncwarp();
+  } else if (warp >= 4 && warp < 4 + PROD_WARPS) {
+    // ===================== depthwise producers =====================
+    // thread = (4-channel group c4 of the 64-channel chunk, run of 4 output pixels, pair of output rows): a half-warp reads /
+    // writes one complete 128-byte pixel per LDS.64 / STS.64 (conflict-free).  Two output rows per thread: 4 input rows are
+    // loaded and converted for 2 output rows (instead of 3 for 1) and the 9 weight vectors are loaded once for 8 outputs
+    // (ncu on the one-row version: as many bf16 -> f32 conversion instructions as FFMA2, FMA pipe 31 % busy at 45 % issue).
+    const int t = (int)threadIdx.x - 128;
+    const int c4 = t & 15, q = t >> 4;
+    const int nxs = p.W >> 2, nrp = (p.TH + 1) >> 1;
+    const bool has = q < nxs * nrp;
+    const int rp = q / nxs, xs = q - rp * nxs;
+    const int ry = 2 * rp;
+    const bool hasB = has && (ry + 1 < p.TH);
+    const uint32_t row_pitch = (uint32_t)((p.W + 2) * 128);
+    const uint32_t in_off = (uint32_t)((ry * (p.W + 2) + xs * 4) * 128 + c4 * 8);
+    const int row0 = ry * p.W + xs * 4;                 // first of this thread's four A-operand rows of output row ry (row ry + 1: + W)
+    uint32_t a_off[2][4];
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int row = row0 + r * p.W + k;
+        a_off[r][k] = (uint32_t)(row * 128 + (((c4 >> 1) ^ (row & 7)) << 4) + (c4 & 1) * 8);
+      }
+    const uint32_t in_u = tc::smem_u32(in_s), ab_u = tc::smem_u32(ab_s), wdw_u = tc::smem_u32(wdw_s) + (uint32_t)(c4 * 16);
+    int is = 0, as = 0;
+    uint32_t ph_in = 0, ph_ab = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int kc = 0; kc < p.k_chunks; ++kc) {
+        tc::mbar_wait(tc::smem_u32(&in_full[is]), ph_in);
+        uint32_t o[2][4][2];
+        if (has) {
+          const uint32_t wb = wdw_u + (uint32_t)(kc * WDW_CHUNK_FLOATS * 4);
+          uint64_t w[9][2];
+#pragma unroll
+          for (int k = 0; k < 9; ++k) {
+            const float4 w0 = tc::lds_f4(wb + (uint32_t)k * 256u);
+            w[k][0] = f32x2(w0.x, w0.y); w[k][1] = f32x2(w0.z, w0.w);
+          }
+          uint64_t acc[2][4][2];
+          {
+            const float4 b0 = tc::lds_f4(wb + 9u * 256u);
+            const uint64_t bv[2] = {f32x2(b0.x, b0.y), f32x2(b0.z, b0.w)};
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+#pragma unroll
+              for (int k = 0; k < 4; ++k) { acc[r][k][0] = bv[0]; acc[r][k][1] = bv[1]; }
+          }
+          const uint32_t tile_u = in_u + (uint32_t)is * (uint32_t)p.in_stride + in_off;
+          // input row i feeds output row ry with tap row ky = i and output row ry + 1 with ky = i - 1: every output still
+          // accumulates bias, then its taps in row-major order (the order of the per-layer kernel: bit-identical sums)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (i < 3 || hasB) {
+              const uint32_t row_u = tile_u + (uint32_t)i * row_pitch;
+#pragma unroll
+              for (int j = 0; j < 6; ++j) {
+                uint32_t ux, uy;
+                asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(ux), "=r"(uy) : "r"(row_u + (uint32_t)(j * 128)));
+                // bf16 pair -> packed f32 pair: low half << 16, high half masked
+                const uint64_t v[2] = {f32x2(__uint_as_float(ux << 16), __uint_as_float(ux & 0xffff0000u)),
+                                       f32x2(__uint_as_float(uy << 16), __uint_as_float(uy & 0xffff0000u))};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const int kx = j - k;
+                  if (kx >= 0 && kx <= 2) {
+                    if (i < 3) {
+                      acc[0][k][0] = fma_f32x2(v[0], w[i * 3 + kx][0], acc[0][k][0]);
+                      acc[0][k][1] = fma_f32x2(v[1], w[i * 3 + kx][1], acc[0][k][1]);
+                    }
+                    if (i > 0) {
+                      acc[1][k][0] = fma_f32x2(v[0], w[(i - 1) * 3 + kx][0], acc[1][k][0]);
+                      acc[1][k][1] = fma_f32x2(v[1], w[(i - 1) * 3 + kx][1], acc[1][k][1]);
+                    }
+                  }
+                }
+              }
+            }
+          }
+#pragma unroll
+          for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { o[r][k][0] = dw::cvt_relu_bf16x2(acc[r][k][0]); o[r][k][1] = dw::cvt_relu_bf16x2(acc[r][k][1]); }
+        }
+        __syncwarp();                                   // every lane has read its input pixels
+        if (lane == 0) tc::mbar_arrive(tc::smem_u32(&in_empty[is]));
+        if (++is == p.in_stages) { is = 0; ph_in ^= 1; }
+        tc::mbar_wait(tc::smem_u32(&ab_empty[as]), ph_ab ^ 1);
+        if (has) {
+          const uint32_t sa = ab_u + (uint32_t)as * (uint32_t)abs_;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(sa + a_off[0][k]), "r"(o[0][k][0]), "r"(o[0][k][1]) : "memory");
+          if (hasB) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(sa + a_off[1][k]), "r"(o[1][k][0]), "r"(o[1][k][1]) : "memory");
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(tc::smem_u32(&ab_full[as]));
+        if (++as == p.ab_stages) { as = 0; ph_ab ^= 1; }
+      }
+    }
+  } else if (warp >= 4 + PROD_WARPS) {
+    // ===================== epilogue =====================
+    const int qd = warp & 3;                            // TMEM lane quarter this warp may read
+    const int row = qd * 32 + lane;
+    const bool valid = row < p.n_px;
+    const uint32_t bias_u = tc::smem_u32(bias_s);
+    int acc = 0;
+    uint32_t acc_ph = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const size_t pix = (size_t)tile * p.n_px + row;
+      bf16* op = p.out + pix * p.N;
+      const bf16* rp = p.residual ? p.residual + pix * p.N : nullptr;
+      tc::mbar_wait_relaxed(tc::smem_u32(&acc_full[acc]), acc_ph, 64);
+      tc::tcgen05_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(acc * p.acc_stride);
+      for (int c0 = 0; c0 < p.N; c0 += 32) {
+        uint32_t v[32];
+        tc::tmem_ld_32x32b_x32(t_row + (uint32_t)c0, v);
+        tc::tmem_ld_wait();
+        if (c0 + 32 >= p.N) {
+          // last tcgen05.ld of this warp on the accumulator has completed -> hand the TMEM stage back
+          tc::tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(tc::smem_u32(&acc_empty[acc]));
+        }
+        if (valid) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const float4 b0 = tc::lds_f4(bias_u + (uint32_t)(c0 + g * 8) * 4u), b1 = tc::lds_f4(bias_u + (uint32_t)(c0 + g * 8) * 4u + 16u);
+            if (rp) {
+              // linear bottleneck with skip connection: y = x + (acc + bias), one rounding (pytorch_layers.py:93-98)
+              float f[8] = {__uint_as_float(v[g * 8 + 0]) + b0.x, __uint_as_float(v[g * 8 + 1]) + b0.y, __uint_as_float(v[g * 8 + 2]) + b0.z,
+                            __uint_as_float(v[g * 8 + 3]) + b0.w, __uint_as_float(v[g * 8 + 4]) + b1.x, __uint_as_float(v[g * 8 + 5]) + b1.y,
+                            __uint_as_float(v[g * 8 + 6]) + b1.z, __uint_as_float(v[g * 8 + 7]) + b1.w};
+              float r[8];
+              Vec8<bf16>::load(rp + c0 + g * 8, r);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] += r[e];
+              *reinterpret_cast<uint4*>(op + c0 + g * 8) = Vec8<bf16>::pack(f);
+            } else {
+              uint4 ov;
+              ov.x = tc::cvt_bf16x2(tc::add_f32x2(tc::pack_f32x2(v[g * 8 + 0], v[g * 8 + 1]), tc::pack_f32x2(__float_as_uint(b0.x), __float_as_uint(b0.y))));
+              ov.y = tc::cvt_bf16x2(tc::add_f32x2(tc::pack_f32x2(v[g * 8 + 2], v[g * 8 + 3]), tc::pack_f32x2(__float_as_uint(b0.z), __float_as_uint(b0.w))));
+              ov.z = tc::cvt_bf16x2(tc::add_f32x2(tc::pack_f32x2(v[g * 8 + 4], v[g * 8 + 5]), tc::pack_f32x2(__float_as_uint(b1.x), __float_as_uint(b1.y))));
+              ov.w = tc::cvt_bf16x2(tc::add_f32x2(tc::pack_f32x2(v[g * 8 + 6], v[g * 8 + 7]), tc::pack_f32x2(__float_as_uint(b1.z), __float_as_uint(b1.w))));
+              *reinterpret_cast<uint4*>(op + c0 + g * 8) = ov;
+            }
+          }
+        }
+      }
+      if (++acc == p.acc_stages) { acc = 0; acc_ph ^= 1; }
+    }
+  }
+
+  // ---- teardown ----
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc::tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tc::TMEM_COLS) : "memory");
+  }
+}
+
+}  // namespace dwp
+}  // namespace spef

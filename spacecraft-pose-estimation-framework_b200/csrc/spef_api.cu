@@ -20,6 +20,7 @@
 #include "dwconv_tma.cuh"
 #include "fused_block.cuh"
 #include "fused_block_t.cuh"
+#include "dw_project.cuh"
 #include "kernels_conv.cuh"
 #include "kernels_post.cuh"
 #include "kernels_ingest.cuh"
@@ -88,6 +89,15 @@ struct Block {
   bool t_tmW_ready = false;
   const void* t_tmX_ptr = nullptr;
   int t_tmX_batch = -1;
+  // expand GEMM + fused depthwise -> project kernel (dw_project.cuh): the wide blocks that have no single-kernel plan
+  bool dp_ok = false;
+  dwp::DwpParams dprm;
+  size_t dp_smem = 0;
+  float* dp_wdw = nullptr;       // [k_chunks][10][64] depthwise weights + bias per K chunk
+  CUtensorMap dp_tmX, dp_tmW;
+  bool dp_tmW_ready = false;
+  const void* dp_tmX_ptr = nullptr;
+  int dp_tmX_batch = -1;
 };
 
 const double kBnEps = 1e-5;  // torch.nn.BatchNorm2d default (pytorch_layers.py:55-56)
@@ -102,6 +112,8 @@ struct spef_ctx {
   std::vector<Block> blocks;
   int fuse = 1;        // fused InvertedResidual kernels on the BF16 tcgen05 path (SPEF_FUSE=0 disables)
   int fb_gw = 4;       // warps per worker group of the fused kernel (SPEF_FB_GW = 4 | 8; 4 measured faster: more registers per thread)
+  int dwp_enable = 1;  // SPEF_DWP=0: per-layer kernels for the blocks without a single-kernel plan
+  int dwp_force = 0;   // SPEF_DWP_FORCE=1 (tests): expand GEMM + depthwise->project kernel for every block it can run, ahead of the single-kernel plans
   int fb_max_cin = 64; // fuse blocks with Cin <= this (SPEF_FB_MAX_CIN); wider blocks measured faster as three kernels
   int stem_patch = 1;  // stem input patches staged by TMA (SPEF_STEM_PATCH=0: gather the 27 taps from global memory)
   int stem_prod = 2;   // im2col producer groups (128 threads each) of the tcgen05 stem (SPEF_STEM_PROD = 1 | 2)
@@ -346,6 +358,8 @@ extern "C" int spef_create(spef_ctx** out, const spef_config* cfg) {
   if (const char* e7 = getenv("SPEF_GEMM_NDG")) ctx->gemm_ndg = (atoi(e7) == 1) ? 1 : 2;
   if (const char* e6 = getenv("SPEF_GEMM_NSW")) ctx->gemm_nsw = (atoi(e6) == 8 && ctx->gemm_ndg == 1) ? 8 : 4;
   if (const char* e8 = getenv("SPEF_FUSE")) ctx->fuse = atoi(e8) ? 1 : 0;
+  if (const char* e8 = getenv("SPEF_DWP")) ctx->dwp_enable = atoi(e8) ? 1 : 0;
+  if (const char* e8 = getenv("SPEF_DWP_FORCE")) ctx->dwp_force = atoi(e8) ? 1 : 0;
   if (const char* e9 = getenv("SPEF_FB_GW")) ctx->fb_gw = (atoi(e9) == 8) ? 8 : 4;
   if (const char* e11 = getenv("SPEF_FB_MAX_CIN")) ctx->fb_max_cin = atoi(e11);
   if (const char* e12 = getenv("SPEF_FB_VARIANT")) ctx->fb_variant = atoi(e12) ? 1 : 0;
@@ -416,7 +430,7 @@ extern "C" void spef_destroy(spef_ctx* ctx) {
     cudaFree(l.w_bf16);
     cudaFree(l.bias);
   }
-  for (Block& b : ctx->blocks) { cudaFree(b.aux); cudaFree(b.t_we); cudaFree(b.t_wp); cudaFree(b.t_aux); }
+  for (Block& b : ctx->blocks) { cudaFree(b.aux); cudaFree(b.t_we); cudaFree(b.t_wp); cudaFree(b.t_aux); cudaFree(b.dp_wdw); }
   for (int i = 0; i < 4; ++i) cudaFree(ctx->act[i]);
   void* ptrs[] = {ctx->pooled, ctx->head_out, ctx->ori_tab64, ctx->pos_tab64, ctx->ori_tab, ctx->pos_tab, ctx->eval_sums, ctx->ws_images, ctx->ws_quat,
                   ctx->ws_pos, ctx->ws_qt, ctx->ws_tt, ctx->ws_soft, ctx->ws_soft2, ctx->ws_hinv, ctx->ws_per_image,
@@ -665,6 +679,48 @@ static int plan_blocks_t(spef_ctx* ctx) {
   return SPEF_OK;
 }
 
+// Depthwise -> project plan (dw_project.cuh): stride-1 blocks with an expand conv whose hidden width is a multiple of 64.
+static int plan_blocks_dp(spef_ctx* ctx) {
+  std::vector<Layer>& L = ctx->layers;
+  for (Block& b : ctx->blocks) {
+    b.dp_ok = false;
+    b.dp_tmW_ready = false;
+    b.dp_tmX_ptr = nullptr;
+    if (b.i_exp < 0) continue;
+    const Layer& d = L[b.i_dw];
+    const Layer& pj = L[b.i_proj];
+    if (d.stride != 1 || d.cin % 64 != 0 || pj.cout % 32 != 0 || d.wout % 4 != 0 || d.wout > 128) continue;
+    dwp::DwpParams& q = b.dprm;
+    memset(&q, 0, sizeof(q));
+    q.H = d.hin; q.W = d.win; q.C = d.cin; q.N = pj.cout;
+    for (int th = 128 / q.W; th >= 1 && !q.TH; --th)
+      if (q.H % th == 0) q.TH = th;
+    q.tiles_y = q.H / q.TH; q.n_px = q.TH * q.W; q.k_chunks = q.C / 64;
+    if ((q.W / 4) * ((q.TH + 1) / 2) * 16 > 32 * dwp::PROD_WARPS) continue;   // one (4 channels, 4 pixels, 2 rows) task per producer thread
+    q.n_half = (q.N <= 256) ? 1 : 2; q.nh = q.N / q.n_half;
+    if (q.nh > 256 || q.nh % 16 != 0 || q.N > 512) continue;
+    q.acc_stride = q.N; q.acc_stages = (2 * q.N <= 512) ? 2 : 1;
+    q.in_bytes = (q.TH + 2) * (q.W + 2) * 128; q.in_stride = ((q.in_bytes + 1023) / 1024) * 1024;
+    bool found = false;
+    const int opts[6][2] = {{4, 4}, {3, 4}, {3, 3}, {2, 4}, {2, 3}, {2, 2}};   // {A/Wp stages, input stages}
+    for (const auto& o : opts) {
+      q.ab_stages = o[0]; q.in_stages = o[1];
+      if (dwp::smem_bytes(q) <= ctx->smem_optin) { found = true; break; }
+    }
+    if (!found) continue;
+    b.dp_smem = dwp::smem_bytes(q);
+    std::vector<float> w((size_t)q.k_chunks * dwp::WDW_CHUNK_FLOATS);
+    for (int ch = 0; ch < q.C; ++ch) {
+      float* base = w.data() + (size_t)(ch / 64) * dwp::WDW_CHUNK_FLOATS + ch % 64;
+      for (int k = 0; k < 9; ++k) base[k * 64] = d.h_wdw[(size_t)k * q.C + ch];
+      base[9 * 64] = d.h_bias[ch];
+    }
+    if (!upload(&b.dp_wdw, w)) return fail(ctx, SPEF_ERR_CUDA, "spef_finalize_weights: upload failed");
+    b.dp_ok = true;
+  }
+  return SPEF_OK;
+}
+
 extern "C" int spef_finalize_weights(spef_ctx* ctx) {
   if (!ctx) return SPEF_ERR_INVALID;
   CK(cudaSetDevice(ctx->cfg.device));
@@ -787,11 +843,14 @@ extern "C" int spef_finalize_weights(spef_ctx* ctx) {
     if (rcb) return rcb;
     rcb = plan_blocks_t(ctx);
     if (rcb) return rcb;
+    rcb = plan_blocks_dp(ctx);
+    if (rcb) return rcb;
 #define SPEF_FBT_ATTR(S_, TH_) \
     CK(cudaFuncSetAttribute(fbt::fused_block_t_kernel<S_, TH_, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, so));
     SPEF_FBT_ATTR(1, 6) SPEF_FBT_ATTR(1, 5) SPEF_FBT_ATTR(2, 4)
 #undef SPEF_FBT_ATTR
     CK(cudaFuncSetAttribute(fbt::fused_block_t_kernel<1, 6, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, so));
+    CK(cudaFuncSetAttribute(dwp::dw_project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, so));
     CK(cudaFuncSetAttribute(fb::fused_block_kernel<1, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, so));
     CK(cudaFuncSetAttribute(fb::fused_block_kernel<2, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, so));
     CK(cudaFuncSetAttribute(fb::fused_block_kernel<1, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, so));
@@ -1031,12 +1090,15 @@ static int launch_tcgen05_layer(spef_ctx* ctx, Layer& l, const void* in, const v
 }
 
 // true when block bi runs as one fused kernel in the current configuration
-// 0: per-layer kernels, 1: staged fused kernel (fused_block.cuh), 2: channel-lane fused kernel (fused_block_t.cuh)
+// 0: per-layer kernels, 1: staged fused kernel (fused_block.cuh), 2: channel-lane fused kernel (fused_block_t.cuh),
+// 3: expand GEMM + fused depthwise -> project kernel (dw_project.cuh)
 static int block_variant(const spef_ctx* ctx, int bi) {
   if (!(ctx->fuse && ctx->cfg.precision == SPEF_BF16 && ctx->cfg.pw_impl == 0 && bi >= 0 && bi < (int)ctx->blocks.size())) return 0;
   const Block& b = ctx->blocks[bi];
+  if (ctx->dwp_force && b.dp_ok) return 3;
   if (ctx->fb_variant == 1 && b.t_ok) return 2;
-  return b.fusable ? 1 : 0;
+  if (b.fusable) return 1;
+  return (ctx->dwp_enable && b.dp_ok) ? 3 : 0;
 }
 static bool block_is_fused(const spef_ctx* ctx, int bi) { return block_variant(ctx, bi) != 0; }
 
@@ -1098,8 +1160,41 @@ static int launch_fused_block_t(spef_ctx* ctx, Block& b, const void* in, void* o
   return SPEF_OK;
 }
 
+static int run_layer(spef_ctx* ctx, Layer& l, const void* in, const void* res, void* out, int B, cudaStream_t st, bool cached_maps);
+
+// hidden: the expand conv's output [B,H,W,C]; res: the block input (skip connection) or nullptr
+static int launch_dw_project(spef_ctx* ctx, Block& b, const void* hidden, const void* res, void* out, int B, cudaStream_t st) {
+  std::vector<Layer>& L = ctx->layers;
+  dwp::DwpParams& q = b.dprm;
+  const Layer& pj = L[b.i_proj];
+  if (!b.dp_tmW_ready) {
+    if (!tc::make_tmap_2d(ctx->encode, &b.dp_tmW, pj.w_bf16, false, q.N, q.C, q.C, q.nh))
+      return fail(ctx, SPEF_ERR_CUDA, "cuTensorMapEncodeTiled(Wp) failed for the depthwise-project kernel at layer %d", b.i_dw);
+    b.dp_tmW_ready = true;
+  }
+  if (b.dp_tmX_ptr != hidden || b.dp_tmX_batch != B) {
+    if (!dw::make_tmap_nhwc(ctx->encode, &b.dp_tmX, hidden, B, q.H, q.W, q.C, 8, q.W + 2, q.TH + 2))
+      return fail(ctx, SPEF_ERR_CUDA, "cuTensorMapEncodeTiled(X) failed for the depthwise-project kernel at layer %d", b.i_dw);
+    b.dp_tmX_ptr = hidden; b.dp_tmX_batch = B;
+  }
+  q.B = B; q.wdw = b.dp_wdw; q.bias = pj.bias; q.residual = pj.residual ? (const bf16*)res : nullptr; q.out = (bf16*)out;
+  const long long tiles = (long long)B * q.tiles_y;
+  const int grid = (int)(tiles < ctx->num_sms ? tiles : ctx->num_sms);
+  dwp::dw_project_kernel<<<grid, dwp::NT, b.dp_smem, st>>>(b.dp_tmX, b.dp_tmW, q);
+  CK_LAUNCH("dw_project_kernel");
+  return SPEF_OK;
+}
+
 static int launch_fused_block(spef_ctx* ctx, Block& b, const void* in, void* out, int B, cudaStream_t st) {
-  if (block_variant(ctx, (int)(&b - ctx->blocks.data())) == 2) return launch_fused_block_t(ctx, b, in, out, B, st);
+  const int variant = block_variant(ctx, (int)(&b - ctx->blocks.data()));
+  if (variant == 3) {
+    // teacher-forced block (spef_block_forward): expand into the hidden buffer of the forward pass, then the fused kernel
+    Layer& e = ctx->layers[b.i_exp];
+    int rc = run_layer(ctx, e, in, nullptr, buf_ptr(ctx, e.dst), B, st, false);
+    if (rc) return rc;
+    return launch_dw_project(ctx, b, buf_ptr(ctx, e.dst), in, out, B, st);
+  }
+  if (variant == 2) return launch_fused_block_t(ctx, b, in, out, B, st);
   std::vector<Layer>& L = ctx->layers;
   fb::FbParams& q = b.prm;
   if (!b.tmW_ready) {
@@ -1189,6 +1284,19 @@ static int forward_internal(spef_ctx* ctx, const float* images, int B, cudaStrea
   for (int i = 0; i < nl; ++i) {
     Layer& l = ctx->layers[i];
     while (next_block < ctx->blocks.size() && ctx->blocks[next_block].first < i) ++next_block;
+    if (next_block < ctx->blocks.size() && ctx->blocks[next_block].first == i && block_variant(ctx, (int)next_block) == 3) {
+      // expand conv as a GEMM, then depthwise + project in one kernel (its time is reported in the slot of the depthwise layer)
+      Block& b = ctx->blocks[next_block];
+      Layer& pj = ctx->layers[b.i_proj];
+      int rc = run_layer(ctx, l, buf_ptr(ctx, l.src), nullptr, buf_ptr(ctx, l.dst), B, st, true);
+      if (rc) return rc;
+      if (ev) CK(cudaEventRecord(ev[i + 1], st));
+      rc = launch_dw_project(ctx, b, buf_ptr(ctx, l.dst), pj.res_buf >= 0 ? buf_ptr(ctx, pj.res_buf) : nullptr, buf_ptr(ctx, pj.dst), B, st);
+      if (rc) return rc;
+      if (ev) { CK(cudaEventRecord(ev[i + 2], st)); CK(cudaEventRecord(ev[i + 3], st)); }
+      i += 2;
+      continue;
+    }
     if (next_block < ctx->blocks.size() && ctx->blocks[next_block].first == i && block_is_fused(ctx, (int)next_block)) {
       // one kernel for expand + depthwise + project; its time is reported in the slot of the block's first layer
       Block& b = ctx->blocks[next_block];
@@ -1286,8 +1394,8 @@ extern "C" int spef_block_info(const spef_ctx* ctx, int32_t i, int32_t* first_la
   if (first_layer) *first_layer = b.first;
   if (n_layers) *n_layers = b.n_layers;
   if (fused) *fused = v;
-  if (tile_h) *tile_h = v == 2 ? b.tprm.TH : (v == 1 ? b.prm.TH : 0);
-  if (tile_w) *tile_w = v == 2 ? b.tprm.TW : (v == 1 ? b.prm.TW : 0);
+  if (tile_h) *tile_h = v == 3 ? b.dprm.TH : v == 2 ? b.tprm.TH : (v == 1 ? b.prm.TH : 0);
+  if (tile_w) *tile_w = v == 3 ? b.dprm.W : v == 2 ? b.tprm.TW : (v == 1 ? b.prm.TW : 0);
   if (groups) *groups = v == 2 ? b.t_ng : (v == 1 ? b.ng : 0);
   if (w_stages) *w_stages = v == 2 ? b.tprm.w_stages : (v == 1 ? b.prm.w_stages : 0);
   if (resident) *resident = v == 2 ? b.tprm.resident : (v == 1 ? b.prm.resident : 0);

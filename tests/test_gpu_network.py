@@ -137,15 +137,16 @@ def _oracle_block(layers, first, last, x, hidden_fp32):
 
 
 def _check_fused_blocks(sd, images, batch=3, pick=None):
-    """Every fused InvertedResidual kernel (expand -> depthwise -> project [+ x] in one launch) on the oracle's BF16 input of
-    that block, both fused variants (staged / channel-lane).
+    """Every fused InvertedResidual kernel (expand -> depthwise -> project [+ x] in one launch; for the wide blocks the expand
+    GEMM followed by ONE depthwise -> project kernel, variant 3) on the oracle's BF16 input of that block.
       * against the oracle WITH THE KERNEL'S ROUNDING POINTS (the staged kernel rounds the hidden tensor to BF16 like the
         per-layer kernels, the channel-lane kernel keeps it in FP32): the depthwise outputs are not teacher-forced inside a block,
         so a 1-ulp flip of a BF16 depthwise value (FP32 accumulation order) moves a few block outputs by a few output ulps:
         < 1 % of the elements may differ and none by more than 32 BF16 ulp floored at 2^-8 of the tensor scale (= 1e-3 of the scale:
         one flipped depthwise value times its project weight, seen on an output that happens to cancel);
       * against the chain of per-layer kernels (each within 1 BF16 ulp of the oracle, test above): the staged kernel has the
-        same rounding points and FP32 accumulation order and is bit-identical; the channel-lane kernel differs by the hidden
+        same rounding points and FP32 accumulation order and is bit-identical, and so is the depthwise -> project kernel (the depthwise
+        output is rounded once to BF16 either way; it just never leaves the SM); the channel-lane kernel differs by the hidden
         tensor's BF16 rounding (2^-9 relative per hidden element), which is reported and bounded at 16 output ulp.
     batch / pick: the images of the batch the oracle checks (the B = 256 test teacher-forces images 0, 127, 255 of a full batch)."""
     eng = _engine(sd, "bf16", 0, max_batch=max(8, batch))
@@ -153,7 +154,7 @@ def _check_fused_blocks(sd, images, batch=3, pick=None):
     x = images[:len(pick)]
     ios = _oracle_layer_io(sd, x, True)
     layers = O.folded_layers(sd)
-    n_fused = {1: 0, 2: 0}
+    n_fused = {1: 0, 2: 0, 3: 0}
     for bi in range(eng.num_blocks()):
         info = eng.block_info(bi)
         if not info["fused"]:
@@ -172,7 +173,7 @@ def _check_fused_blocks(sd, images, batch=3, pick=None):
             cur = eng.layer_forward(li, cur, inp if eng.layer_info(li)["residual"] else None)
         chain = cur[pick].float().cpu()
         scale = float(want.abs().max())
-        if info["fused"] == 1:
+        if info["fused"] in (1, 3):
             np.testing.assert_array_equal(got.numpy(), chain.numpy(), err_msg=f"block {bi} {info} vs per-layer kernels")
         else:
             err = (got - chain).abs()
@@ -198,12 +199,22 @@ def _check_fused_blocks(sd, images, batch=3, pick=None):
 def test_fused_blocks_teacher_forced(sd, images):
     n = _check_fused_blocks(sd, images)
     assert n[1] + n[2] >= 8, f"only {n} blocks are fused"
+    assert n[1] + n[2] + n[3] >= 16, f"only {n} of the 17 blocks run fused kernels"   # all but the stride-2 block 14 (576 -> 160)
+
+
+def test_dw_project_kernel_on_every_shape_it_takes(sd, images, monkeypatch):
+    """SPEF_DWP_FORCE=1 runs the expand GEMM + depthwise -> project kernel on every stride-1 block it has a plan for (hidden widths
+    192 / 384 / 576 / 960, maps 30x48 ... 8x12, with and without skip connection, one- and two-half accumulators): bit-identical
+    to the per-layer kernels, within the block gates of the oracle."""
+    monkeypatch.setenv("SPEF_DWP_FORCE", "1")
+    n = _check_fused_blocks(sd, images)
+    assert n[3] >= 10, f"only {n} blocks took the depthwise -> project kernel"
 
 
 def test_fused_blocks_teacher_forced_full_batch(sd, images):
     """Every fused block inside a B = 256 launch: slots 0, 127, 255 against the oracle, all other slots bit-identical copies."""
     n = _check_fused_blocks(sd, images, batch=256, pick=[0, 127, 255])
-    assert n[1] + n[2] >= 8, f"only {n} blocks are fused"
+    assert n[1] + n[2] >= 8 and n[3] >= 5, f"only {n} blocks are fused"
 
 
 def test_fused_block_variants(sd, images, monkeypatch):
