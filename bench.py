@@ -626,8 +626,8 @@ def run_b200(args):
         torch.cuda.empty_cache()
         cpu = not args.no_cpu_baseline
         try:
-            extras["decode_sweep"] = {"config": "BASELINE configs[3]: decode kernel isolated, bins per axis 8..32, ~256 MB of logits per size (larger than L2)",
-                                      "rows": decode_sweep(10, 1 << 28, cpu_images=32 if cpu else 0)}
+            extras["decode_sweep"] = {"config": "BASELINE configs[3]: decode kernel isolated, bins per axis 8..32, ~1 GB of logits per size (8x the L2; batch per row)",
+                                      "rows": decode_sweep(10, 1 << 30, cpu_images=32 if cpu else 0)}
         except Exception as ex:
             extras["decode_sweep"] = {"error": repr(ex)[:300]}
         try:

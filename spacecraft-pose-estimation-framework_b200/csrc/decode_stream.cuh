@@ -92,18 +92,25 @@ __host__ __device__ __forceinline__ void jacobi4_f32(float (&a)[4][4], float (&v
 #pragma unroll
       for (int j = i + 1; j < 4; ++j) off = fmaf(a[i][j], a[i][j], off);
     }
-    if (!(off > 1e-15f * diag)) break;
+    // |off| <= 3e-7 |diag|: the f64 polish below corrects the eigenvector to first order, so what is left is second order (1e-13)
+    if (!(off > 1e-13f * diag)) break;
 #pragma unroll
     for (int p = 0; p < 3; ++p) {
 #pragma unroll
       for (int q = p + 1; q < 4; ++q) {
         const float apq = a[p][q];
         // a zero pivot gives theta = inf -> t = 0, c = 1, s = 0: the identity rotation, no branch needed
-        const float theta = (a[q][q] - a[p][p]) / (2.f * apq);
-        const float t = copysignf(1.f, theta) / (fabsf(theta) + sqrtf(fmaf(theta, theta, 1.f)));
 #ifdef __CUDA_ARCH__
+        // approximate division / square root (MUFU, ~2 ulp): a rotation only has to be a rotation to f32 accuracy (c, s come from
+        // the same t) and annihilate a[p][q] approximately -- the sweeps iterate and the f64 polish removes what is left
+        const float theta = __fdividef(a[q][q] - a[p][p], 2.f * apq);
+        float rt;
+        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rt) : "f"(fmaf(theta, theta, 1.f)));
+        const float t = copysignf(__frcp_rn(fabsf(theta) + rt), theta);
         const float c = (apq == 0.f) ? 1.f : rsqrtf(fmaf(t, t, 1.f));
 #else
+        const float theta = (a[q][q] - a[p][p]) / (2.f * apq);
+        const float t = copysignf(1.f, theta) / (fabsf(theta) + sqrtf(fmaf(theta, theta, 1.f)));
         const float c = (apq == 0.f) ? 1.f : 1.f / sqrtf(fmaf(t, t, 1.f));
 #endif
         const float s = (apq == 0.f) ? 0.f : t * c;
@@ -514,6 +521,185 @@ __global__ void __launch_bounds__(NW * 32, 1) decode_ori_stream_kernel(const flo
     if ((it & 31) == 31) solve_batch(it - 31, 32);
   }
   if (it & 31) solve_batch(it & ~31, it & 31);
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// Small histograms (n <= 512 bins, 8 bins per axis in the sweep): half a warp per image.
+// ncu on the kernel above at 512 bins (profiles/r02_ncu_decode512.txt): 740 warp instructions per image of which only 170 are
+// the per-bin work (exp + 15 packed FP per bin pair + table loads); the rest is per-image overhead that does not shrink with
+// n -- ring / cursor bookkeeping, the rescale + flush into the f64 running sums, the 11-value f64 transposing reduction
+// (32 SHFL + 60 FSEL + 27 DADD), padding selects of the half-empty 1024-bin step.  Here
+//   * lanes 0-15 take image 2p, lanes 16-31 image 2p + 1: every per-image instruction above serves two images;
+//   * an image is ONE step (32 bins per lane): no running maximum / rescale, no f64 running sums -- the per-lane sums of 32
+//     products are f32, reduced across the 16 lanes in f32 (15 SHFL; relative error ~1e-7, the eigenvector moves by < 1e-4 deg);
+//   * the whole table [4][512] is staged once per CTA; three ring slots of one image pair (4 KB) per warp.
+// No argmax / softmax / inv(A) outputs: those calls stay on decode_ori_stream_kernel.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int HN = 512;      // bins per image, at most
+constexpr int HNW = 16, HRING = 3;
+inline size_t half_smem_bytes() { return (size_t)4 * HN * 4 + (size_t)HNW * HRING * 2 * HN * 4 + (size_t)HNW * 32 * 12 * 4 + (size_t)HNW * HRING * 8; }
+
+// sum over the 16 lanes of a half-warp of 16 floats per lane with 15 shuffles; lane hl ends with the total of entry hl
+__device__ __forceinline__ float half_transpose_sum16(float (&x)[16], int hl) {
+  bool up = hl & 8;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float send = up ? x[j] : x[j + 8], keep = up ? x[j + 8] : x[j];
+    x[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  up = hl & 4;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float send = up ? x[j] : x[j + 4], keep = up ? x[j + 4] : x[j];
+    x[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  up = hl & 2;
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const float send = up ? x[j] : x[j + 2], keep = up ? x[j + 2] : x[j];
+    x[j] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  up = hl & 1;
+  const float send = up ? x[0] : x[1], keep = up ? x[1] : x[0];
+  return keep + __shfl_xor_sync(0xffffffffu, send, 1);
+}
+
+template <bool LOGITS>
+__global__ void __launch_bounds__(HNW * 32, 1) decode_ori_half_kernel(const float* __restrict__ in, int ld, int B, int n,
+                                                                      const float* __restrict__ tab, int tab_ld,
+                                                                      float* __restrict__ quat_out, uint32_t* __restrict__ flags) {
+  extern __shared__ __align__(128) unsigned char dsm[];
+  float* stab = reinterpret_cast<float*>(dsm);                                   // [4][HN]
+  float* ring = stab + 4 * HN;                                                   // [HNW][HRING][2][HN]
+  float* stash = ring + (size_t)HNW * HRING * 2 * HN;                            // [HNW][32][12]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stash + (size_t)HNW * 32 * 12);   // [HNW][HRING]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, hl = lane & 15, half = lane >> 4;
+  const int pairs = (B + 1) >> 1;
+  const int stride = (int)gridDim.x * HNW;            // pair index step of this warp
+  const float* my_ring = ring + (size_t)warp * HRING * 2 * HN;
+  const uint32_t ring_u = tc::smem_u32(my_ring), bar_u = tc::smem_u32(bars + warp * HRING);
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < HRING; ++s) tc::mbar_init(bar_u + 8u * s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  const uint32_t row_bytes = (uint32_t)n * 4u;
+  int pp = (int)blockIdx.x * HNW + warp;              // producer cursor (pair index)
+  auto produce = [&](int slot) {
+    if (pp < pairs) {
+      if (lane == 0) {
+        const bool two = 2 * pp + 1 < B;
+        const uint32_t bar = bar_u + 8u * slot, dst = ring_u + (uint32_t)slot * (2 * HN * 4);
+        const float* src = in + (size_t)(2 * pp) * ld;
+        tc::mbar_arrive_expect_tx(bar, two ? 2u * row_bytes : row_bytes);
+        bulk_load_1d(dst, src, row_bytes, bar);
+        if (two) bulk_load_1d(dst + HN * 4, src + ld, row_bytes, bar);
+      }
+      pp += stride;
+    }
+  };
+#pragma unroll
+  for (int s = 0; s < HRING - 1; ++s) produce(s);
+  int slot = 0, fill_slot = HRING - 1;
+  uint32_t phases = 0;
+
+  for (int i = threadIdx.x; i < tab_ld; i += HNW * 32) {   // tab_ld <= 2 * HN floats per plane is checked by the host; zero padded
+    const int c = i / (tab_ld >> 2), o = i % (tab_ld >> 2);
+    if (o * 4 < HN) reinterpret_cast<float4*>(stab + c * HN)[o] = __ldg(reinterpret_cast<const float4*>(tab + (size_t)c * tab_ld) + o);
+  }
+  __syncthreads();
+
+  float* my_stash = stash + (size_t)warp * 32 * 12;
+  auto solve_batch = [&](int it_first, int n_pairs) {   // images of pairs it_first .. it_first + n_pairs - 1 of this warp, one per lane
+    __syncwarp();
+    if (lane < 2 * n_pairs) {
+      const int img = 2 * (((int)blockIdx.x + (it_first + (lane >> 1)) * (int)gridDim.x) * HNW + warp) + (lane & 1);
+      if (img < B) {
+        double tot[11];
+#pragma unroll
+        for (int k = 0; k < 11; ++k) tot[k] = (double)my_stash[lane * 12 + k];
+        solve_and_store(tot, LOGITS, img, quat_out, nullptr, flags);
+      }
+    }
+    __syncwarp();
+  };
+
+  const float pad = LOGITS ? -INFINITY : 0.f;
+  const int n4 = n >> 2;
+  int it = 0;
+  for (int p = (int)blockIdx.x * HNW + warp; p < pairs; p += stride, ++it) {
+    produce(fill_slot);
+    fill_slot = (fill_slot + 1 == HRING) ? 0 : fill_slot + 1;
+    tc::mbar_wait(bar_u + 8u * slot, (phases >> slot) & 1u);
+    phases ^= 1u << slot;
+    float4 z[8];
+    const float4* zs = reinterpret_cast<const float4*>(my_ring + (size_t)slot * 2 * HN + half * HN);
+    const bool have = 2 * p + half < B;       // the odd image of the last pair may not exist: its lanes work on padding
+    if (n4 == HN / 4 && have) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) z[j] = zs[j * 16 + hl];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) z[j] = (have && j * 16 + hl < n4) ? zs[j * 16 + hl] : make_float4(pad, pad, pad, pad);
+    }
+    __syncwarp();
+    slot = (slot + 1 == HRING) ? 0 : slot + 1;
+    uint64_t mb2 = 0ull;
+    const uint64_t l2e2 = f32x2(LOG2E, LOG2E);
+    if (LOGITS) {
+      float lm = fmaxf(fmaxf(z[0].x, z[0].y), fmaxf(z[0].z, z[0].w));
+#pragma unroll
+      for (int j = 1; j < 8; ++j) lm = fmaxf(fmaxf(lm, fmaxf(z[j].x, z[j].y)), fmaxf(z[j].z, z[j].w));
+#pragma unroll
+      for (int o = 8; o >= 1; o >>= 1) lm = fmaxf(lm, __shfl_xor_sync(0xffffffffu, lm, o));   // NaN logits: fmaxf drops them, ex2(NaN) keeps them
+      const float mb = -lm * LOG2E;
+      mb2 = f32x2(mb, mb);
+    }
+    uint64_t P[11];
+#pragma unroll
+    for (int k = 0; k < 11; ++k) P[k] = 0ull;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {   // 64 bins of this image: 4 per lane, two per packed instruction
+      uint64_t W01 = f32x2(z[j].x, z[j].y), W23 = f32x2(z[j].z, z[j].w);
+      if (LOGITS) {
+        float t0, t1, t2, t3;
+        f32x2_unpack(fma_f32x2(W01, l2e2, mb2), t0, t1);
+        f32x2_unpack(fma_f32x2(W23, l2e2, mb2), t2, t3);
+        W01 = f32x2(ex2_approx(t0), ex2_approx(t1));
+        W23 = f32x2(ex2_approx(t2), ex2_approx(t3));
+      }
+      const int o = (j * 16 + hl) * 4;
+      const ulonglong2 q0 = *reinterpret_cast<const ulonglong2*>(stab + 0 * HN + o);
+      const ulonglong2 q1 = *reinterpret_cast<const ulonglong2*>(stab + 1 * HN + o);
+      const ulonglong2 q2 = *reinterpret_cast<const ulonglong2*>(stab + 2 * HN + o);
+      const ulonglong2 q3 = *reinterpret_cast<const ulonglong2*>(stab + 3 * HN + o);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const uint64_t W = h ? W23 : W01;
+        const uint64_t Q0 = h ? q0.y : q0.x, Q1 = h ? q1.y : q1.x, Q2 = h ? q2.y : q2.x, Q3 = h ? q3.y : q3.x;
+        const uint64_t T0 = mul_f32x2(W, Q0), T1 = mul_f32x2(W, Q1), T2 = mul_f32x2(W, Q2), T3 = mul_f32x2(W, Q3);
+        P[0] = add_f32x2(P[0], W);
+        P[1] = fma_f32x2(T0, Q0, P[1]); P[2] = fma_f32x2(T0, Q1, P[2]); P[3] = fma_f32x2(T0, Q2, P[3]); P[4] = fma_f32x2(T0, Q3, P[4]);
+        P[5] = fma_f32x2(T1, Q1, P[5]); P[6] = fma_f32x2(T1, Q2, P[6]); P[7] = fma_f32x2(T1, Q3, P[7]);
+        P[8] = fma_f32x2(T2, Q2, P[8]); P[9] = fma_f32x2(T2, Q3, P[9]); P[10] = fma_f32x2(T3, Q3, P[10]);
+      }
+    }
+    float x[16];
+#pragma unroll
+    for (int k = 0; k < 11; ++k) {
+      float lo, hi;
+      f32x2_unpack(P[k], lo, hi);
+      x[k] = lo + hi;
+    }
+#pragma unroll
+    for (int k = 11; k < 16; ++k) x[k] = 0.f;
+    const float r = half_transpose_sum16(x, hl);
+    if (hl < 11) my_stash[(2 * (it & 15) + half) * 12 + hl] = r;
+    if ((it & 15) == 15) solve_batch(it - 15, 16);
+  }
+  if (it & 15) solve_batch(it & ~15, it & 15);
 }
 
 }  // namespace dstream

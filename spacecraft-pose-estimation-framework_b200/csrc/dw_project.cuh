@@ -6,7 +6,10 @@
 //
 //   warp 0        TMA: input box {64 channels, W+2, TH+2} of the hidden tensor per (tile, K chunk); the 1-pixel halo and the
 //                 image border are TMA out-of-bounds zero fill (box origin at x = -1, y = y0 - 1)
-//   warp 3        TMA: the [N x 64] chunk of the project weights of the same K chunk (L2-resident, 128B-swizzled)
+//   warp 3        TMA: the [N x 64] chunk of the project weights of the same K chunk (L2-resident, 128B-swizzled) into a ring of its
+//                 own: with the weights in the A stages (first version) their load could only be issued once the MMA of
+//                 ab_stages chunks earlier had completed, and every role ended up waiting for that round trip (ncu: producers
+//                 16 probes per chunk on the stage-empty barrier, the MMA warp 54 on stage-full, tensor pipe 6 % busy)
 //   warps 4-15    depthwise producers: thread = (4 channels, run of 4 output pixels, 2 output rows); 4 x 6 LDS.64 of input +
 //                 10 LDS.128 of folded FP32 weights / bias, packed FFMA2 in the order of dwconv3x3_tma_kernel (bias, then taps
 //                 row-major), cvt.rn.relu.bf16x2, one 8-byte store per pixel into the K-major SWIZZLE_128B A stage
@@ -26,7 +29,7 @@ namespace dwp {
 constexpr int PROD_WARPS = 12;
 constexpr int EPI_WARPS = 4;
 constexpr int NT = 128 + 32 * PROD_WARPS + 32 * EPI_WARPS;
-constexpr int MAX_IN = 4, MAX_AB = 4, MAX_ACC = 2;
+constexpr int MAX_IN = 4, MAX_AB = 4, MAX_W = 8, MAX_ACC = 2;
 constexpr int A_BYTES = 128 * 128;          // one K chunk of the A operand: 128 pixels x 64 channels
 constexpr int WDW_CHUNK_FLOATS = 10 * 64;   // per K chunk: 9 taps + bias, 64 channels each
 
@@ -34,7 +37,7 @@ struct DwpParams {
   int B, H, W, C, N;            // hidden map (= output map, stride 1), hidden channels (GEMM K), project outputs
   int TH, tiles_y, n_px;        // tile = TH full-width rows; n_px = TH * W <= 128
   int k_chunks;                 // C / 64
-  int in_stages, ab_stages, acc_stages, acc_stride;
+  int in_stages, ab_stages, w_stages, acc_stages, acc_stride;   // ab_stages: A-operand stages; w_stages: project-weight chunk stages
   int n_half, nh;               // N = n_half * nh: one MMA per half (nh <= 256, multiple of 16)
   int in_bytes, in_stride;      // TMA box bytes (TH+2)(W+2)*128 and the 1024-aligned stage pitch
   const float* wdw;             // depthwise weights + bias per K chunk [k_chunks][10][64]
@@ -43,27 +46,30 @@ struct DwpParams {
   bf16* out;                    // [B,H,W,N]
 };
 
-__host__ __device__ inline int ab_stride(const DwpParams& p) { return A_BYTES + p.N * 128; }
+__host__ __device__ inline int w_stride(const DwpParams& p) { return ((p.N * 128 + 1023) / 1024) * 1024; }
 inline size_t smem_bytes(const DwpParams& p) {
-  return 1024 + (size_t)p.ab_stages * ab_stride(p) + (size_t)p.in_stages * p.in_stride + (size_t)p.k_chunks * WDW_CHUNK_FLOATS * 4 +
-         (size_t)p.N * 4 + 512;
+  return 1024 + (size_t)p.ab_stages * A_BYTES + (size_t)p.w_stages * w_stride(p) + (size_t)p.in_stages * p.in_stride +
+         (size_t)p.k_chunks * WDW_CHUNK_FLOATS * 4 + (size_t)p.N * 4 + 512;
 }
 
 __global__ void __launch_bounds__(NT, 1)
 dw_project_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const DwpParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const int abs_ = ab_stride(p);
-  uint8_t* ab_s = smem;                                            // [ab_stages][A 16 KB | Wp chunk N x 128 B]
-  uint8_t* in_s = ab_s + (size_t)p.ab_stages * abs_;               // [in_stages][(TH+2)(W+2) pixels x 128 B]
+  const int abs_ = A_BYTES, ws_ = w_stride(p);
+  uint8_t* ab_s = smem;                                            // [ab_stages][A 16 KB]
+  uint8_t* w_s = ab_s + (size_t)p.ab_stages * abs_;                // [w_stages][Wp chunk N x 128 B]
+  uint8_t* in_s = w_s + (size_t)p.w_stages * ws_;                  // [in_stages][(TH+2)(W+2) pixels x 128 B]
   float* wdw_s = reinterpret_cast<float*>(in_s + (size_t)p.in_stages * p.in_stride);
   float* bias_s = wdw_s + (size_t)p.k_chunks * WDW_CHUNK_FLOATS;
   uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + p.N);
   uint64_t* in_full = bars;                 // [MAX_IN]   TMA -> producers
   uint64_t* in_empty = in_full + MAX_IN;    // [MAX_IN]   producers -> TMA
-  uint64_t* ab_full = in_empty + MAX_IN;    // [MAX_AB]   producers (A) + TMA (Wp chunk) -> MMA
-  uint64_t* ab_empty = ab_full + MAX_AB;    // [MAX_AB]   MMA -> producers, weight loader
-  uint64_t* acc_full = ab_empty + MAX_AB;   // [MAX_ACC]  MMA -> epilogue
+  uint64_t* ab_full = in_empty + MAX_IN;    // [MAX_AB]   producers (A) -> MMA
+  uint64_t* ab_empty = ab_full + MAX_AB;    // [MAX_AB]   MMA -> producers
+  uint64_t* w_full = ab_empty + MAX_AB;     // [MAX_W]    TMA (Wp chunk) -> MMA
+  uint64_t* w_empty = w_full + MAX_W;       // [MAX_W]    MMA -> weight loader
+  uint64_t* acc_full = w_empty + MAX_W;     // [MAX_ACC]  MMA -> epilogue
   uint64_t* acc_empty = acc_full + MAX_ACC; // [MAX_ACC]  epilogue -> MMA
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(acc_empty + MAX_ACC);
 
@@ -90,8 +96,12 @@ dw_project_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       tc::mbar_init(tc::smem_u32(&in_empty[i]), PROD_WARPS);
     }
     for (int i = 0; i < MAX_AB; ++i) {
-      tc::mbar_init(tc::smem_u32(&ab_full[i]), PROD_WARPS + 1);   // one arrive per producer warp + the weight TMA
+      tc::mbar_init(tc::smem_u32(&ab_full[i]), PROD_WARPS);       // one arrive per producer warp
       tc::mbar_init(tc::smem_u32(&ab_empty[i]), 1);
+    }
+    for (int i = 0; i < MAX_W; ++i) {
+      tc::mbar_init(tc::smem_u32(&w_full[i]), 1);
+      tc::mbar_init(tc::smem_u32(&w_empty[i]), 1);
     }
     for (int i = 0; i < MAX_ACC; ++i) {
       tc::mbar_init(tc::smem_u32(&acc_full[i]), 1);
@@ -131,16 +141,16 @@ dw_project_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   } else if (warp == 3) {
     // ===================== TMA: project-weight chunks =====================
     if (lane == 0) {
-      int as = 0;
+      int ws = 0;
       uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         for (int kc = 0; kc < p.k_chunks; ++kc) {
-          tc::mbar_wait(tc::smem_u32(&ab_empty[as]), ph ^ 1);
-          const uint32_t fb = tc::smem_u32(&ab_full[as]);
+          tc::mbar_wait(tc::smem_u32(&w_empty[ws]), ph ^ 1);
+          const uint32_t fb = tc::smem_u32(&w_full[ws]);
           tc::mbar_arrive_expect_tx(fb, (uint32_t)(p.N * 128));
-          const uint32_t dst = tc::smem_u32(ab_s + (size_t)as * abs_ + A_BYTES);
+          const uint32_t dst = tc::smem_u32(w_s + (size_t)ws * ws_);
           for (int h = 0; h < p.n_half; ++h) tc::tma_load_2d(dst + (uint32_t)(h * p.nh * 128), &tmW, kc * 64, h * p.nh, fb);
-          if (++as == p.ab_stages) { as = 0; ph ^= 1; }
+          if (++ws == p.w_stages) { ws = 0; ph ^= 1; }
         }
       }
     }
@@ -149,25 +159,28 @@ dw_project_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     // ===================== MMA issuer (whole warp converged, one elected lane issues) =====================
     const uint32_t idesc = tc::make_idesc_bf16(128, p.nh);
     const uint64_t a_base = tc::make_smem_desc_sw128(tc::smem_u32(ab_s));
-    const uint64_t b_base = tc::make_smem_desc_sw128(tc::smem_u32(ab_s + A_BYTES));
-    const uint32_t s_step = (uint32_t)abs_ >> 4, h_step = (uint32_t)(p.nh * 128) >> 4;
-    int as = 0, acc = 0;
-    uint32_t ph = 0, acc_ph = 0;
+    const uint64_t b_base = tc::make_smem_desc_sw128(tc::smem_u32(w_s));
+    const uint32_t s_step = (uint32_t)abs_ >> 4, w_step = (uint32_t)ws_ >> 4, h_step = (uint32_t)(p.nh * 128) >> 4;
+    int as = 0, ws = 0, acc = 0;
+    uint32_t ph = 0, w_ph = 0, acc_ph = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       tc::mbar_wait(tc::smem_u32(&acc_empty[acc]), acc_ph ^ 1);
       tc::tcgen05_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_stride);
       for (int kc = 0; kc < p.k_chunks; ++kc) {
+        tc::mbar_wait(tc::smem_u32(&w_full[ws]), w_ph);
         tc::mbar_wait(tc::smem_u32(&ab_full[as]), ph);
         tc::tcgen05_fence_after();
         const uint64_t a_desc = a_base + (uint64_t)((uint32_t)as * s_step);
-        const uint64_t b_desc = b_base + (uint64_t)((uint32_t)as * s_step);
+        const uint64_t b_desc = b_base + (uint64_t)((uint32_t)ws * w_step);
         for (int h = 0; h < p.n_half; ++h)
           for (uint32_t k = 0; k < 4; ++k)
             tc::mma_elect_v2(d_tmem + (uint32_t)(h * p.nh), a_desc + (uint64_t)(k * 2u), b_desc + (uint64_t)((uint32_t)h * h_step + k * 2u), idesc,
                              (kc > 0 || k > 0) ? 1u : 0u);
         tc::commit_elect_v2(tc::smem_u32(&ab_empty[as]));
+        tc::commit_elect_v2(tc::smem_u32(&w_empty[ws]));
         if (++as == p.ab_stages) { as = 0; ph ^= 1; }
+        if (++ws == p.w_stages) { ws = 0; w_ph ^= 1; }
       }
       tc::commit_elect_v2(tc::smem_u32(&acc_full[acc]));
       if (++acc == p.acc_stages) { acc = 0; acc_ph ^= 1; }

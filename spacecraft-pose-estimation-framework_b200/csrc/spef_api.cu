@@ -113,6 +113,7 @@ struct spef_ctx {
   int fuse = 1;        // fused InvertedResidual kernels on the BF16 tcgen05 path (SPEF_FUSE=0 disables)
   int fb_gw = 4;       // warps per worker group of the fused kernel (SPEF_FB_GW = 4 | 8; 4 measured faster: more registers per thread)
   int dwp_enable = 1;  // SPEF_DWP=0: per-layer kernels for the blocks without a single-kernel plan
+  int dwp_w_stages = 0; // SPEF_DWP_WST (developer A/B): cap on the project-weight ring depth of the depthwise -> project kernel
   int dwp_force = 0;   // SPEF_DWP_FORCE=1 (tests): expand GEMM + depthwise->project kernel for every block it can run, ahead of the single-kernel plans
   int fb_max_cin = 64; // fuse blocks with Cin <= this (SPEF_FB_MAX_CIN); wider blocks measured faster as three kernels
   int stem_patch = 1;  // stem input patches staged by TMA (SPEF_STEM_PATCH=0: gather the 27 taps from global memory)
@@ -360,6 +361,7 @@ extern "C" int spef_create(spef_ctx** out, const spef_config* cfg) {
   if (const char* e8 = getenv("SPEF_FUSE")) ctx->fuse = atoi(e8) ? 1 : 0;
   if (const char* e8 = getenv("SPEF_DWP")) ctx->dwp_enable = atoi(e8) ? 1 : 0;
   if (const char* e8 = getenv("SPEF_DWP_FORCE")) ctx->dwp_force = atoi(e8) ? 1 : 0;
+  if (const char* e8 = getenv("SPEF_DWP_WST")) ctx->dwp_w_stages = atoi(e8);
   if (const char* e9 = getenv("SPEF_FB_GW")) ctx->fb_gw = (atoi(e9) == 8) ? 8 : 4;
   if (const char* e11 = getenv("SPEF_FB_MAX_CIN")) ctx->fb_max_cin = atoi(e11);
   if (const char* e12 = getenv("SPEF_FB_VARIANT")) ctx->fb_variant = atoi(e12) ? 1 : 0;
@@ -702,9 +704,12 @@ static int plan_blocks_dp(spef_ctx* ctx) {
     q.acc_stride = q.N; q.acc_stages = (2 * q.N <= 512) ? 2 : 1;
     q.in_bytes = (q.TH + 2) * (q.W + 2) * 128; q.in_stride = ((q.in_bytes + 1023) / 1024) * 1024;
     bool found = false;
-    const int opts[6][2] = {{4, 4}, {3, 4}, {3, 3}, {2, 4}, {2, 3}, {2, 2}};   // {A/Wp stages, input stages}
+    // {A stages, project-weight stages, input stages}: the weight ring is the deep one (its loads have the longest round trip: the
+    // MMA that frees a stage, then an L2 read that all CTAs issue for the same lines), three input boxes in flight, two or three A stages
+    const int opts[10][3] = {{3, 6, 4}, {3, 6, 3}, {3, 5, 3}, {3, 4, 3}, {2, 4, 3}, {2, 3, 3}, {2, 3, 2}, {2, 2, 3}, {2, 2, 2}, {1, 2, 2}};
     for (const auto& o : opts) {
-      q.ab_stages = o[0]; q.in_stages = o[1];
+      q.ab_stages = o[0]; q.w_stages = o[1]; q.in_stages = o[2];
+      if (ctx->dwp_w_stages > 0 && q.w_stages > ctx->dwp_w_stages) continue;
       if (dwp::smem_bytes(q) <= ctx->smem_optin) { found = true; break; }
     }
     if (!found) continue;
@@ -1284,7 +1289,14 @@ static int forward_internal(spef_ctx* ctx, const float* images, int B, cudaStrea
   for (int i = 0; i < nl; ++i) {
     Layer& l = ctx->layers[i];
     while (next_block < ctx->blocks.size() && ctx->blocks[next_block].first < i) ++next_block;
-    if (next_block < ctx->blocks.size() && ctx->blocks[next_block].first == i && block_variant(ctx, (int)next_block) == 3) {
+    // the depthwise -> project kernel runs one CTA per (image, row tile): a few-image step (temporal streams) would leave most SMs
+    // idle through its K-chunk loop, so small batches keep the per-layer kernels (batch 1: 0.37 ms per frame with it, 0.30 without)
+    int variant = 0;
+    if (next_block < ctx->blocks.size() && ctx->blocks[next_block].first == i) {
+      variant = block_variant(ctx, (int)next_block);
+      if (variant == 3 && !ctx->dwp_force && (long long)B * ctx->blocks[next_block].dprm.tiles_y < ctx->num_sms / 4) variant = 0;
+    }
+    if (variant == 3) {
       // expand conv as a GEMM, then depthwise + project in one kernel (its time is reported in the slot of the depthwise layer)
       Block& b = ctx->blocks[next_block];
       Layer& pj = ctx->layers[b.i_proj];
@@ -1297,7 +1309,7 @@ static int forward_internal(spef_ctx* ctx, const float* images, int B, cudaStrea
       i += 2;
       continue;
     }
-    if (next_block < ctx->blocks.size() && ctx->blocks[next_block].first == i && block_is_fused(ctx, (int)next_block)) {
+    if (variant != 0) {
       // one kernel for expand + depthwise + project; its time is reported in the slot of the block's first layer
       Block& b = ctx->blocks[next_block];
       int rc = launch_fused_block(ctx, b, buf_ptr(ctx, l.src), buf_ptr(ctx, ctx->layers[b.i_proj].dst), B, st);
@@ -1553,6 +1565,8 @@ static cudaError_t decode_stream_attr() {
 static cudaError_t decode_stream_init() {
   cudaError_t e = decode_stream_attr<8, 4, 0>();
   if (e == cudaSuccess) e = decode_stream_attr<16, 2, 0>();
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(dstream::decode_ori_half_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dstream::half_smem_bytes());
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(dstream::decode_ori_half_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dstream::half_smem_bytes());
   return e;
 }
 
@@ -1575,6 +1589,15 @@ static int launch_decode_stream_cfg(spef_ctx* ctx, const float* in, int ld, int 
 static int launch_decode_stream(spef_ctx* ctx, const float* in, int ld, int B, int n, int is_logits, float* soft, float* quat, float* hinv,
                                 int32_t* amax, uint32_t* flags, cudaStream_t st) {
   const int cfg = ctx->decode_cfg >= 0 ? ctx->decode_cfg : ((long long)B >= 16LL * ctx->num_sms ? 2 : 0);
+  // small histograms at batches that fill the GPU, quaternions only: half a warp per image (decode_ori_half_kernel); SPEF_DECODE_CFG=3 forces it
+  if ((cfg == 2 || ctx->decode_cfg == 3) && ctx->decode_cfg != 2 && n <= dstream::HN && ctx->ori_tab_ld <= 2 * dstream::HN && !soft && !hinv && !amax) {
+    const int pairs = (B + 1) / 2;
+    const int grid = std::min(cdiv(pairs, dstream::HNW), ctx->num_sms);
+    if (is_logits) dstream::decode_ori_half_kernel<true><<<grid, dstream::HNW * 32, dstream::half_smem_bytes(), st>>>(in, ld, B, n, ctx->ori_tab_soa, ctx->ori_tab_ld, quat, flags);
+    else dstream::decode_ori_half_kernel<false><<<grid, dstream::HNW * 32, dstream::half_smem_bytes(), st>>>(in, ld, B, n, ctx->ori_tab_soa, ctx->ori_tab_ld, quat, flags);
+    CK_LAUNCH("decode_ori_half_kernel");
+    return SPEF_OK;
+  }
   if (cfg == 0) return launch_decode_stream_cfg<8, 4, 0>(ctx, in, ld, B, n, is_logits, soft, quat, hinv, amax, flags, st);
   return launch_decode_stream_cfg<16, 2, 0>(ctx, in, ld, B, n, is_logits, soft, quat, hinv, amax, flags, st);
 }

@@ -389,3 +389,42 @@ def test_stream_decode_full_size_matches_per_image_kernel(post, stream_post):
     idx = np.arange(0, B, 607)[:128]
     want_q, _ = O.ori_decode_batch(O.softmax(logits[idx].cpu().numpy()), hist)
     assert O.quat_angle_deg(qa[idx], want_q).max() <= QUAT_TOL_DEG
+
+
+@pytest.mark.parametrize("n_dim,delete", [(8, False), (6, False), (8, True)])
+def test_half_warp_decode_small_histograms(post, stream_post, n_dim, delete):
+    """decode_ori_half_kernel (n <= 512 bins, half a warp per image, f32 reduction): taken by itself for quaternion-only calls
+    at batches that fill the GPU.  512 bins (full 64-bin slices), 216 bins and the pruned 8-bin histogram (ragged slices), an odd
+    batch (the last pair has one image), logits and pdf input, a NaN image; against the oracle on a sample, against the
+    warp-per-image kernel on everything, run-to-run determinism and independence of the batch position."""
+    hist, _ = O.ori_histogram(n_dim, delete)
+    n = hist.shape[0]
+    assert n <= 512
+    if n % 4:
+        pytest.skip("rows of this histogram are not 16-byte multiples: the streaming kernels do not take them")
+    post.set_ori_histogram(hist)
+    stream_post.set_ori_histogram(hist)
+    g = torch.Generator().manual_seed(11 + n_dim)
+    B = 16 * torch.cuda.get_device_properties(0).multi_processor_count * 3 + 37
+    logits = (torch.randn((B, n), generator=g) * 3).cuda()
+    logits[B - 1, 3] = float("nan")
+    l0 = stream_post.launch_count()
+    a = stream_post.decode_ori(logits, is_logits=True)
+    b = stream_post.decode_ori(logits, is_logits=True)
+    assert torch.equal(a["quat"][:-1], b["quat"][:-1])
+    fl = a["flags"].cpu().numpy()
+    assert fl[-1] == 1 and not fl[:-1].any() and torch.isnan(a["quat"][-1]).all()
+    qa = a["quat"].cpu().numpy()[:-1]
+    ref = np.concatenate([post.decode_ori(logits[i:i + 2048], is_logits=True)["quat"].cpu().numpy() for i in range(0, B - 1, 2048)])[:B - 1]
+    assert O.quat_angle_deg(qa, ref).max() <= 1e-2
+    sub = stream_post.decode_ori(logits[1001:1101], is_logits=True)["quat"].cpu().numpy()   # small batch: the one-image-per-warp kernel
+    assert O.quat_angle_deg(sub, qa[1001:1101]).max() <= 1e-2
+    idx = np.arange(0, B - 1, 97)[:96]
+    soft = O.softmax(logits[idx].cpu().numpy())
+    want_q, _ = O.ori_decode_batch(soft, hist)
+    assert O.quat_angle_deg(qa[idx], want_q).max() <= QUAT_TOL_DEG
+    # pdf input through the same kernel
+    pdf = torch.softmax(logits[:-1], 1)
+    qp = stream_post.decode_ori(pdf, is_logits=False)["quat"].cpu().numpy()
+    assert O.quat_angle_deg(qp[idx], want_q).max() <= QUAT_TOL_DEG
+    assert O.quat_angle_deg(qp, qa).max() <= 1e-2
