@@ -10,9 +10,8 @@
 //                 own: with the weights in the A stages (first version) their load could only be issued once the MMA of
 //                 ab_stages chunks earlier had completed, and every role ended up waiting for that round trip (ncu: producers
 //                 16 probes per chunk on the stage-empty barrier, the MMA warp 54 on stage-full, tensor pipe 6 % busy)
-//   warps 4-15    depthwise producers: thread = (4 channels, run of 4 output pixels, 2 output rows); 4 x 6 LDS.64 of input +
-//                 10 LDS.128 of folded FP32 weights / bias, packed FFMA2 in the order of dwconv3x3_tma_kernel (bias, then taps
-//                 row-major), cvt.rn.relu.bf16x2, one 8-byte store per pixel into the K-major SWIZZLE_128B A stage
+//   warps 4-15    depthwise producers (producer_loop below): G groups on alternate K chunks, thread = (4 channels, 2 output
+//                 columns, R output rows)
 //   warp 1        tcgen05.mma (M = 128 pixels, N = Cout or two halves of it, K = 16 x 4 per chunk), FP32 accumulators in TMEM
 //   warps 16-19   epilogue: tcgen05.ld -> + bias (+ skip input) -> BF16 -> 16-byte global stores
 //
@@ -22,6 +21,7 @@
 #pragma once
 #include "dwconv_tma.cuh"
 #include "gemm_tcgen05_v2.cuh"
+#include "fused_block_t.cuh"   // reg_inc / reg_dec (setmaxnreg)
 
 namespace spef {
 namespace dwp {
@@ -39,6 +39,7 @@ struct DwpParams {
   int k_chunks;                 // C / 64
   int in_stages, ab_stages, w_stages, acc_stages, acc_stride;   // ab_stages: A-operand stages; w_stages: project-weight chunk stages
   int n_half, nh;               // N = n_half * nh: one MMA per half (nh <= 256, multiple of 16)
+  int R, G;                     // producer task: R output rows x 2 columns x 4 channels; G producer groups take alternate K chunks
   int in_bytes, in_stride;      // TMA box bytes (TH+2)(W+2)*128 and the 1024-aligned stage pitch
   const float* wdw;             // depthwise weights + bias per K chunk [k_chunks][10][64]
   const float* bias;            // project bias [N]
@@ -50,6 +51,111 @@ __host__ __device__ inline int w_stride(const DwpParams& p) { return ((p.N * 128
 inline size_t smem_bytes(const DwpParams& p) {
   return 1024 + (size_t)p.ab_stages * A_BYTES + (size_t)p.w_stages * w_stride(p) + (size_t)p.in_stages * p.in_stride +
          (size_t)p.k_chunks * WDW_CHUNK_FLOATS * 4 + (size_t)p.N * 4 + 512;
+}
+
+
+struct ProdCtx {
+  uint32_t in_u, ab_u, wdw_u, in_full, in_empty, ab_full, ab_empty;
+  int num_tiles;
+};
+
+// Depthwise producers.  The PROD_WARPS warps form G groups of T = 384 / G threads; group g takes the (tile, K chunk) items
+// g, g + G, ... of the CTA's sequence, so consecutive chunks are computed concurrently by different warps and every thread of
+// every warp has the same amount of work (first version: 2-row x 4-pixel tasks -- on the 5-row tiles a quarter of the producer
+// warps had no task and another quarter half a task, and the busy ones ran at 1 instruction per 10 cycles).
+// thread = (4-channel group c4, pair of output columns, R output rows): walks down its R + 2 input rows; per row 4 LDS.64 (a
+// half-warp reads one complete 128-byte pixel: conflict-free), bf16 -> f32 by shift / mask, packed FFMA2 into the (at most three)
+// output rows the input row feeds; every output accumulates bias, then its taps in row-major order (the order of the per-layer
+// kernel: bit-identical sums).  An output row is converted (cvt.rn.relu.bf16x2) and stored as soon as its last input row is
+// done -- 8 bytes per pixel into the K-major SWIZZLE_128B A stage -- so only three rows of accumulators are live.
+template <int R>
+__device__ __forceinline__ void producer_loop(const DwpParams& p, const ProdCtx& c) {
+  const int t_all = (int)threadIdx.x - 128;
+  const int T = (32 * PROD_WARPS) / p.G;
+  const int g = t_all / T, t = t_all - g * T;
+  const int lane = threadIdx.x & 31;
+  const int c4 = t & 15, task = t >> 4;
+  const int nxs = p.W >> 1;
+  const int rb = task / nxs, xs = task - rb * nxs;
+  const int r0 = rb * R, x0 = xs * 2;
+  const uint32_t row_pitch = (uint32_t)((p.W + 2) * 128);
+  const uint32_t in_off = (uint32_t)((r0 * (p.W + 2) + x0) * 128 + c4 * 8);
+  const uint32_t a_sw = (uint32_t)(c4 >> 1), a_lo = (uint32_t)((c4 & 1) * 8);
+  const int arow0 = r0 * p.W + x0;
+  const uint32_t wdw_u = c.wdw_u + (uint32_t)(c4 * 16);
+  int is = g % p.in_stages, as = g % p.ab_stages;
+  uint32_t ph_in = (uint32_t)((g / p.in_stages) & 1), ph_ab = (uint32_t)((g / p.ab_stages) & 1);
+  int kc = g;                       // K chunk of this group's current item (g < k_chunks: checked by the host)
+  for (int tile = blockIdx.x; tile < c.num_tiles;) {
+    tc::mbar_wait(c.in_full + 8u * (uint32_t)is, ph_in);
+    tc::mbar_wait(c.ab_empty + 8u * (uint32_t)as, ph_ab ^ 1);
+    const uint32_t wb = wdw_u + (uint32_t)(kc * WDW_CHUNK_FLOATS * 4);
+    uint64_t w[9][2], bv[2];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      const float4 w0 = tc::lds_f4(wb + (uint32_t)k * 256u);
+      w[k][0] = f32x2(w0.x, w0.y); w[k][1] = f32x2(w0.z, w0.w);
+    }
+    {
+      const float4 b0 = tc::lds_f4(wb + 9u * 256u);
+      bv[0] = f32x2(b0.x, b0.y); bv[1] = f32x2(b0.z, b0.w);
+    }
+    const uint32_t tile_u = c.in_u + (uint32_t)is * (uint32_t)p.in_stride + in_off;
+    const uint32_t sa = c.ab_u + (uint32_t)as * (uint32_t)A_BYTES;
+    uint64_t acc[R][2][2];
+#pragma unroll
+    for (int i = 0; i < R + 2; ++i) {
+      if (i < R) {
+#pragma unroll
+        for (int o = 0; o < 2; ++o) { acc[i][o][0] = bv[0]; acc[i][o][1] = bv[1]; }
+      }
+      const uint32_t row_u = tile_u + (uint32_t)i * row_pitch;
+      uint64_t v[4][2];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint32_t ux, uy;
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(ux), "=r"(uy) : "r"(row_u + (uint32_t)(j * 128)));
+        // bf16 pair -> packed f32 pair: low half << 16, high half masked
+        v[j][0] = f32x2(__uint_as_float(ux << 16), __uint_as_float(ux & 0xffff0000u));
+        v[j][1] = f32x2(__uint_as_float(uy << 16), __uint_as_float(uy & 0xffff0000u));
+      }
+      if (i == R + 1) {   // last input row is in registers: hand the input stage back before the remaining FMAs and stores
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(c.in_empty + 8u * (uint32_t)is);
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int ky = i - r;
+        if (ky >= 0 && ky <= 2) {
+#pragma unroll
+          for (int o = 0; o < 2; ++o)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+              acc[r][o][0] = fma_f32x2(v[o + kx][0], w[ky * 3 + kx][0], acc[r][o][0]);
+              acc[r][o][1] = fma_f32x2(v[o + kx][1], w[ky * 3 + kx][1], acc[r][o][1]);
+            }
+        }
+      }
+      if (i >= 2) {   // output row i - 2 has all its taps
+        const int r = i - 2;
+#pragma unroll
+        for (int o = 0; o < 2; ++o) {
+          const uint32_t row = (uint32_t)(arow0 + r * p.W + o);
+          const uint32_t off = row * 128u + ((a_sw ^ (row & 7u)) << 4) + a_lo;
+          asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(sa + off), "r"(dw::cvt_relu_bf16x2(acc[r][o][0])), "r"(dw::cvt_relu_bf16x2(acc[r][o][1])) : "memory");
+        }
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+    __syncwarp();                                                  // every lane has read its input pixels and stored its outputs
+    if (lane == 0) tc::mbar_arrive(c.ab_full + 8u * (uint32_t)as);
+    is += p.G;
+    while (is >= p.in_stages) { is -= p.in_stages; ph_in ^= 1; }
+    as += p.G;
+    while (as >= p.ab_stages) { as -= p.ab_stages; ph_ab ^= 1; }
+    kc += p.G;
+    while (kc >= p.k_chunks) { kc -= p.k_chunks; tile += gridDim.x; }
+  }
 }
 
 __global__ void __launch_bounds__(NT, 1)
@@ -93,10 +199,10 @@ dw_project_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < MAX_IN; ++i) {
       tc::mbar_init(tc::smem_u32(&in_full[i]), 1);
-      tc::mbar_init(tc::smem_u32(&in_empty[i]), PROD_WARPS);
+      tc::mbar_init(tc::smem_u32(&in_empty[i]), PROD_WARPS / p.G);
     }
     for (int i = 0; i < MAX_AB; ++i) {
-      tc::mbar_init(tc::smem_u32(&ab_full[i]), PROD_WARPS);       // one arrive per producer warp
+      tc::mbar_init(tc::smem_u32(&ab_full[i]), PROD_WARPS / p.G); // one arrive per producer warp of the group that owns the chunk
       tc::mbar_init(tc::smem_u32(&ab_empty[i]), 1);
     }
     for (int i = 0; i < MAX_W; ++i) {
@@ -118,6 +224,9 @@ dw_project_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   tc::tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
 
+  // register file per role (launch allocation 20 warps x 96): producers 12 x 120, epilogue 4 x 64, the warpgroup of the single-lane
+  // roles 4 x 40 (setmaxnreg is a warpgroup instruction: all four warps execute the same one)
+  if (warp < 4) fbt::reg_dec<40>();
   if (warp == 0) {
     // ===================== TMA: hidden-tensor boxes =====================
     if (lane == 0) {
@@ -188,108 +297,18 @@ dw_project_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     __syncwarp();
   } else if (warp >= 4 && warp < 4 + PROD_WARPS) {
     // ===================== depthwise producers =====================
-    // thread = (4-channel group c4 of the 64-channel chunk, run of 4 output pixels, pair of output rows): a half-warp reads /
-    // writes one complete 128-byte pixel per LDS.64 / STS.64 (conflict-free).  Two output rows per thread: 4 input rows are
-    // loaded and converted for 2 output rows (instead of 3 for 1) and the 9 weight vectors are loaded once for 8 outputs
-    // (ncu on the one-row version: as many bf16 -> f32 conversion instructions as FFMA2, FMA pipe 31 % busy at 45 % issue).
-    const int t = (int)threadIdx.x - 128;
-    const int c4 = t & 15, q = t >> 4;
-    const int nxs = p.W >> 2, nrp = (p.TH + 1) >> 1;
-    const bool has = q < nxs * nrp;
-    const int rp = q / nxs, xs = q - rp * nxs;
-    const int ry = 2 * rp;
-    const bool hasB = has && (ry + 1 < p.TH);
-    const uint32_t row_pitch = (uint32_t)((p.W + 2) * 128);
-    const uint32_t in_off = (uint32_t)((ry * (p.W + 2) + xs * 4) * 128 + c4 * 8);
-    const int row0 = ry * p.W + xs * 4;                 // first of this thread's four A-operand rows of output row ry (row ry + 1: + W)
-    uint32_t a_off[2][4];
-#pragma unroll
-    for (int r = 0; r < 2; ++r)
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int row = row0 + r * p.W + k;
-        a_off[r][k] = (uint32_t)(row * 128 + (((c4 >> 1) ^ (row & 7)) << 4) + (c4 & 1) * 8);
-      }
-    const uint32_t in_u = tc::smem_u32(in_s), ab_u = tc::smem_u32(ab_s), wdw_u = tc::smem_u32(wdw_s) + (uint32_t)(c4 * 16);
-    int is = 0, as = 0;
-    uint32_t ph_in = 0, ph_ab = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      for (int kc = 0; kc < p.k_chunks; ++kc) {
-        tc::mbar_wait(tc::smem_u32(&in_full[is]), ph_in);
-        uint32_t o[2][4][2];
-        if (has) {
-          const uint32_t wb = wdw_u + (uint32_t)(kc * WDW_CHUNK_FLOATS * 4);
-          uint64_t w[9][2];
-#pragma unroll
-          for (int k = 0; k < 9; ++k) {
-            const float4 w0 = tc::lds_f4(wb + (uint32_t)k * 256u);
-            w[k][0] = f32x2(w0.x, w0.y); w[k][1] = f32x2(w0.z, w0.w);
-          }
-          uint64_t acc[2][4][2];
-          {
-            const float4 b0 = tc::lds_f4(wb + 9u * 256u);
-            const uint64_t bv[2] = {f32x2(b0.x, b0.y), f32x2(b0.z, b0.w)};
-#pragma unroll
-            for (int r = 0; r < 2; ++r)
-#pragma unroll
-              for (int k = 0; k < 4; ++k) { acc[r][k][0] = bv[0]; acc[r][k][1] = bv[1]; }
-          }
-          const uint32_t tile_u = in_u + (uint32_t)is * (uint32_t)p.in_stride + in_off;
-          // input row i feeds output row ry with tap row ky = i and output row ry + 1 with ky = i - 1: every output still
-          // accumulates bias, then its taps in row-major order (the order of the per-layer kernel: bit-identical sums)
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            if (i < 3 || hasB) {
-              const uint32_t row_u = tile_u + (uint32_t)i * row_pitch;
-#pragma unroll
-              for (int j = 0; j < 6; ++j) {
-                uint32_t ux, uy;
-                asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(ux), "=r"(uy) : "r"(row_u + (uint32_t)(j * 128)));
-                // bf16 pair -> packed f32 pair: low half << 16, high half masked
-                const uint64_t v[2] = {f32x2(__uint_as_float(ux << 16), __uint_as_float(ux & 0xffff0000u)),
-                                       f32x2(__uint_as_float(uy << 16), __uint_as_float(uy & 0xffff0000u))};
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  const int kx = j - k;
-                  if (kx >= 0 && kx <= 2) {
-                    if (i < 3) {
-                      acc[0][k][0] = fma_f32x2(v[0], w[i * 3 + kx][0], acc[0][k][0]);
-                      acc[0][k][1] = fma_f32x2(v[1], w[i * 3 + kx][1], acc[0][k][1]);
-                    }
-                    if (i > 0) {
-                      acc[1][k][0] = fma_f32x2(v[0], w[(i - 1) * 3 + kx][0], acc[1][k][0]);
-                      acc[1][k][1] = fma_f32x2(v[1], w[(i - 1) * 3 + kx][1], acc[1][k][1]);
-                    }
-                  }
-                }
-              }
-            }
-          }
-#pragma unroll
-          for (int r = 0; r < 2; ++r)
-#pragma unroll
-            for (int k = 0; k < 4; ++k) { o[r][k][0] = dw::cvt_relu_bf16x2(acc[r][k][0]); o[r][k][1] = dw::cvt_relu_bf16x2(acc[r][k][1]); }
-        }
-        __syncwarp();                                   // every lane has read its input pixels
-        if (lane == 0) tc::mbar_arrive(tc::smem_u32(&in_empty[is]));
-        if (++is == p.in_stages) { is = 0; ph_in ^= 1; }
-        tc::mbar_wait(tc::smem_u32(&ab_empty[as]), ph_ab ^ 1);
-        if (has) {
-          const uint32_t sa = ab_u + (uint32_t)as * (uint32_t)abs_;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(sa + a_off[0][k]), "r"(o[0][k][0]), "r"(o[0][k][1]) : "memory");
-          if (hasB) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(sa + a_off[1][k]), "r"(o[1][k][0]), "r"(o[1][k][1]) : "memory");
-          }
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
-        __syncwarp();
-        if (lane == 0) tc::mbar_arrive(tc::smem_u32(&ab_full[as]));
-        if (++as == p.ab_stages) { as = 0; ph_ab ^= 1; }
-      }
+    fbt::reg_inc<120>();
+    const ProdCtx pc{tc::smem_u32(in_s), tc::smem_u32(ab_s), tc::smem_u32(wdw_s), tc::smem_u32(in_full), tc::smem_u32(in_empty),
+                     tc::smem_u32(ab_full), tc::smem_u32(ab_empty), num_tiles};
+    switch (p.R) {
+      case 5: producer_loop<5>(p, pc); break;
+      case 4: producer_loop<4>(p, pc); break;
+      case 3: producer_loop<3>(p, pc); break;
+      case 2: producer_loop<2>(p, pc); break;
+      default: producer_loop<1>(p, pc); break;
     }
   } else if (warp >= 4 + PROD_WARPS) {
+    fbt::reg_dec<64>();
     // ===================== epilogue =====================
     const int qd = warp & 3;                            // TMEM lane quarter this warp may read
     const int row = qd * 32 + lane;

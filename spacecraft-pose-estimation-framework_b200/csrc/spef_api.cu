@@ -698,15 +698,23 @@ static int plan_blocks_dp(spef_ctx* ctx) {
     for (int th = 128 / q.W; th >= 1 && !q.TH; --th)
       if (q.H % th == 0) q.TH = th;
     q.tiles_y = q.H / q.TH; q.n_px = q.TH * q.W; q.k_chunks = q.C / 64;
-    if ((q.W / 4) * ((q.TH + 1) / 2) * 16 > 32 * dwp::PROD_WARPS) continue;   // one (4 channels, 4 pixels, 2 rows) task per producer thread
+    // producer task = (4 channels, 2 columns, R rows): R the largest divisor of TH (<= 5) for which the tile's tasks fill a whole
+    // number G of equal producer groups (G * tasks * 16 threads = all producer threads); group g computes the K chunks g, g + G, ...
+    q.R = 0;
+    for (int r = 5; r >= 1 && !q.R; --r) {
+      if (q.TH % r != 0 || q.W % 2 != 0) continue;
+      const int threads = (q.W / 2) * (q.TH / r) * 16;
+      if (threads <= 32 * dwp::PROD_WARPS && threads % 32 == 0 && (32 * dwp::PROD_WARPS) % threads == 0) { q.R = r; q.G = 32 * dwp::PROD_WARPS / threads; }
+    }
+    if (!q.R || q.G > q.k_chunks || q.G > 2) continue;
     q.n_half = (q.N <= 256) ? 1 : 2; q.nh = q.N / q.n_half;
     if (q.nh > 256 || q.nh % 16 != 0 || q.N > 512) continue;
     q.acc_stride = q.N; q.acc_stages = (2 * q.N <= 512) ? 2 : 1;
     q.in_bytes = (q.TH + 2) * (q.W + 2) * 128; q.in_stride = ((q.in_bytes + 1023) / 1024) * 1024;
     bool found = false;
-    // {A stages, project-weight stages, input stages}: the weight ring is the deep one (its loads have the longest round trip: the
-    // MMA that frees a stage, then an L2 read that all CTAs issue for the same lines), three input boxes in flight, two or three A stages
-    const int opts[10][3] = {{3, 6, 4}, {3, 6, 3}, {3, 5, 3}, {3, 4, 3}, {2, 4, 3}, {2, 3, 3}, {2, 3, 2}, {2, 2, 3}, {2, 2, 2}, {1, 2, 2}};
+    // {A stages, project-weight stages, input stages}: a producer group holds its input stage for G chunk times, so four input boxes
+    // (two of them prefetched); the weight ring is decoupled from the A stages (a deeper one, up to 6, measured no faster)
+    const int opts[10][3] = {{4, 4, 4}, {3, 4, 4}, {3, 3, 4}, {3, 4, 3}, {2, 4, 3}, {2, 3, 3}, {2, 2, 4}, {2, 2, 3}, {2, 3, 2}, {2, 2, 2}};
     for (const auto& o : opts) {
       q.ab_stages = o[0]; q.w_stages = o[1]; q.in_stages = o[2];
       if (ctx->dwp_w_stages > 0 && q.w_stages > ctx->dwp_w_stages) continue;
