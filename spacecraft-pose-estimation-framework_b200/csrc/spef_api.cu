@@ -198,6 +198,13 @@ struct spef_ctx {
   TGraph tg_last{};                // signature of the previous direct (non-graph) call
   cudaStream_t cap_stream = nullptr;
   int temporal_graph = 1;          // SPEF_TEMPORAL_GRAPH=0 disables
+  // spef_eval_batch as a CUDA graph: the ~35 launches of a step replayed as one graph save the launch gaps (B = 256: 1.92 -> 1.87 ms
+  // per step, B = 64: 0.74 -> 0.69 ms).  One graph per call signature, captured when a signature comes back (the host-buffer
+  // routes call with the ctx's own one or two device buffers); SPEF_EVAL_GRAPH=0 disables
+  struct EGraph { const void *img, *qt, *tt, *per; int B; cudaGraphExec_t exec; int64_t launches; };
+  std::vector<EGraph> egraphs;
+  std::vector<EGraph> eg_seen;     // signatures of recent direct calls
+  int eval_graph = 1;
   int temporal_graph_max_streams = 8;
   // ingest plan (spef_resize_frames): taps of both axes for the last (src_h, src_w) seen, one device allocation
   int rz_fixed = 0, rz_gray = 0, rz_gray_off = 0;
@@ -319,6 +326,16 @@ static void* buf_ptr(spef_ctx* ctx, int id) {
 // ------------------------------------------------------------------------------------------------------
 // lifecycle
 // ------------------------------------------------------------------------------------------------------
+// instantiated graphs hold weight / table / state pointers and the kernel choice of the moment they were captured
+static void drop_graphs(spef_ctx* ctx) {
+  for (auto& g : ctx->tgraphs) cudaGraphExecDestroy(g.exec);
+  ctx->tgraphs.clear();
+  ctx->tg_last = spef_ctx::TGraph{};
+  for (auto& g : ctx->egraphs) cudaGraphExecDestroy(g.exec);
+  ctx->egraphs.clear();
+  ctx->eg_seen.clear();
+}
+
 extern "C" int spef_abi_version(void) { return SPEF_ABI_VERSION; }
 
 extern "C" const char* spef_last_error(const spef_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
@@ -362,6 +379,7 @@ extern "C" int spef_create(spef_ctx** out, const spef_config* cfg) {
   if (const char* e8 = getenv("SPEF_DWP")) ctx->dwp_enable = atoi(e8) ? 1 : 0;
   if (const char* e8 = getenv("SPEF_DWP_FORCE")) ctx->dwp_force = atoi(e8) ? 1 : 0;
   if (const char* e8 = getenv("SPEF_DWP_WST")) ctx->dwp_w_stages = atoi(e8);
+  if (const char* e8 = getenv("SPEF_EVAL_GRAPH")) ctx->eval_graph = atoi(e8) ? 1 : 0;
   if (const char* e9 = getenv("SPEF_FB_GW")) ctx->fb_gw = (atoi(e9) == 8) ? 8 : 4;
   if (const char* e11 = getenv("SPEF_FB_MAX_CIN")) ctx->fb_max_cin = atoi(e11);
   if (const char* e12 = getenv("SPEF_FB_VARIANT")) ctx->fb_variant = atoi(e12) ? 1 : 0;
@@ -447,7 +465,7 @@ extern "C" void spef_destroy(spef_ctx* ctx) {
     if (ctx->pipe_consumed[s]) cudaEventDestroy(ctx->pipe_consumed[s]);
   }
   if (ctx->pipe_copy_stream) cudaStreamDestroy(ctx->pipe_copy_stream);
-  for (auto& g : ctx->tgraphs) cudaGraphExecDestroy(g.exec);
+  drop_graphs(ctx);
   if (ctx->cap_stream) cudaStreamDestroy(ctx->cap_stream);
   delete ctx;
 }
@@ -891,9 +909,7 @@ extern "C" int spef_finalize_weights(spef_ctx* ctx) {
     CK(cudaFuncSetAttribute(dw::dwconv3x3_tma_kernel<2, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem));
     CK(cudaFuncSetAttribute(dw::dwconv3x3_tma_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem));
   }
-  for (auto& g : ctx->tgraphs) cudaGraphExecDestroy(g.exec);   // captured launches hold the old weight pointers
-  ctx->tgraphs.clear();
-  ctx->tg_last = spef_ctx::TGraph{};
+  drop_graphs(ctx);   // captured launches hold the old weight pointers
   ctx->host_tensors.clear();
   ctx->plan_batch = -1;
   for (Layer& l : ctx->layers) l.plan_batch = -1;
@@ -908,6 +924,7 @@ extern "C" int spef_set_ori_histogram(spef_ctx* ctx, const double* q, int32_t n)
   if (!ctx) return SPEF_ERR_INVALID;
   if (!q || n < 1) return fail(ctx, SPEF_ERR_INVALID, "spef_set_ori_histogram: bad argument");
   CK(cudaSetDevice(ctx->cfg.device));
+  drop_graphs(ctx);   // captured decode launches hold the old table pointers and sizes
   std::vector<float4> t(n);
   for (int i = 0; i < n; ++i) t[i] = make_float4((float)q[i * 4], (float)q[i * 4 + 1], (float)q[i * 4 + 2], (float)q[i * 4 + 3]);
   if (!upload(&ctx->ori_tab, t)) return fail(ctx, SPEF_ERR_CUDA, "spef_set_ori_histogram: upload failed");
@@ -925,6 +942,7 @@ extern "C" int spef_set_pos_histogram(spef_ctx* ctx, const double* x, int32_t n)
   if (!ctx) return SPEF_ERR_INVALID;
   if (!x || n < 1) return fail(ctx, SPEF_ERR_INVALID, "spef_set_pos_histogram: bad argument");
   CK(cudaSetDevice(ctx->cfg.device));
+  drop_graphs(ctx);
   std::vector<float4> t(n);
   for (int i = 0; i < n; ++i) t[i] = make_float4((float)x[i * 3], (float)x[i * 3 + 1], (float)x[i * 3 + 2], 0.f);
   if (!upload(&ctx->pos_tab, t)) return fail(ctx, SPEF_ERR_CUDA, "spef_set_pos_histogram: upload failed");
@@ -1372,6 +1390,7 @@ extern "C" int spef_set_image_dtype(spef_ctx* ctx, int32_t dt) {
   if (!ctx) return SPEF_ERR_INVALID;
   if (dt != SPEF_IMG_F32 && dt != SPEF_IMG_U8) return fail(ctx, SPEF_ERR_INVALID, "spef_set_image_dtype: unknown dtype %d", dt);
   if (dt == SPEF_IMG_U8 && ctx->cfg.precision != SPEF_BF16) return fail(ctx, SPEF_ERR_UNSUPPORTED, "uint8 images need the BF16 engine");
+  if (ctx->image_u8 != (dt == SPEF_IMG_U8)) drop_graphs(ctx);
   ctx->image_u8 = (dt == SPEF_IMG_U8);
   return SPEF_OK;
 }
@@ -1424,6 +1443,7 @@ extern "C" int spef_block_info(const spef_ctx* ctx, int32_t i, int32_t* first_la
 
 extern "C" int spef_set_fusion(spef_ctx* ctx, int32_t on) {
   if (!ctx) return SPEF_ERR_INVALID;
+  drop_graphs(ctx);
   ctx->fuse = on ? 1 : 0;
   return SPEF_OK;
 }
@@ -1807,10 +1827,60 @@ extern "C" int spef_eval_batch(spef_ctx* ctx, const float* images_dev, const flo
   if (!images_dev || !qt || !tt) return fail(ctx, SPEF_ERR_INVALID, "spef_eval_batch: NULL argument");
   CK(cudaSetDevice(ctx->cfg.device));
   cudaStream_t st = (cudaStream_t)stream;
-  rc = predict_internal(ctx, images_dev, B, nullptr, ctx->ws_quat, nullptr, ctx->ws_pos, nullptr, ctx->ws_flags, st);
-  if (rc) return rc;
-  // the decode guard flags of this batch are counted into sums[6] / sums[7] (the reference raises ValueError from decode())
-  return score_internal(ctx, ctx->ws_quat, ctx->ws_pos, qt, tt, B, ctx->eval_sums, per_image, ctx->ws_flags, stream);
+  auto run = [&](cudaStream_t s_) -> int {
+    int r = predict_internal(ctx, images_dev, B, nullptr, ctx->ws_quat, nullptr, ctx->ws_pos, nullptr, ctx->ws_flags, s_);
+    if (r) return r;
+    // the decode guard flags of this batch are counted into sums[6] / sums[7] (the reference raises ValueError from decode())
+    return score_internal(ctx, ctx->ws_quat, ctx->ws_pos, qt, tt, B, ctx->eval_sums, per_image, ctx->ws_flags, s_);
+  };
+  if (ctx->eval_graph) {
+    // same mechanism as spef_temporal_step: a signature that comes back is captured once (on an internal stream: the caller's may be
+    // the legacy default stream, which cannot capture) and replayed from then on; everything else the step touches is owned by the ctx
+    spef_ctx::EGraph sig{images_dev, qt, tt, per_image, B, nullptr, 0};
+    auto same = [&](const spef_ctx::EGraph& g) { return g.img == sig.img && g.qt == sig.qt && g.tt == sig.tt && g.per == sig.per && g.B == sig.B; };
+    for (auto& g : ctx->egraphs)
+      if (same(g)) {
+        CK(cudaGraphLaunch(g.exec, st));
+        ctx->launches += g.launches;
+        return SPEF_OK;
+      }
+    bool seen = false;
+    for (auto& g : ctx->eg_seen) seen = seen || same(g);
+    if (seen) {
+      if (!ctx->cap_stream) CK(cudaStreamCreateWithFlags(&ctx->cap_stream, cudaStreamNonBlocking));
+      const int64_t l0 = ctx->launches;
+      CK(cudaStreamBeginCapture(ctx->cap_stream, cudaStreamCaptureModeThreadLocal));
+      rc = run(ctx->cap_stream);
+      cudaGraph_t graph = nullptr;
+      const cudaError_t ce = cudaStreamEndCapture(ctx->cap_stream, &graph);
+      const int64_t n_launch = ctx->launches - l0;
+      ctx->launches = l0;   // nothing has run yet
+      if (rc || ce != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        ctx->eval_graph = 0;   // capture is not possible in this process: direct launches from now on
+        if (rc) return rc;
+      } else {
+        cudaGraphExec_t exec = nullptr;
+        const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ie == cudaSuccess) {
+          if (ctx->egraphs.size() >= 4) { cudaGraphExecDestroy(ctx->egraphs.front().exec); ctx->egraphs.erase(ctx->egraphs.begin()); }
+          sig.exec = exec; sig.launches = n_launch;
+          ctx->egraphs.push_back(sig);
+          CK(cudaGraphLaunch(exec, st));
+          ctx->launches += n_launch;
+          return SPEF_OK;
+        }
+        cudaGetLastError();
+        ctx->eval_graph = 0;
+      }
+    } else {
+      if (ctx->eg_seen.size() >= 4) ctx->eg_seen.erase(ctx->eg_seen.begin());
+      ctx->eg_seen.push_back(sig);
+    }
+  }
+  return run(st);
 }
 
 extern "C" int spef_eval_batch_host(spef_ctx* ctx, const float* images_host, const float* qt_h, const float* tt_h, int32_t B,
@@ -1988,8 +2058,7 @@ extern "C" int spef_temporal_reset(spef_ctx* ctx, int32_t S, void* stream) {
   CK(cudaSetDevice(ctx->cfg.device));
   cudaStream_t st = (cudaStream_t)stream;
   if (S != ctx->t_streams) {
-    for (auto& g : ctx->tgraphs) cudaGraphExecDestroy(g.exec);   // captured launches hold the old state pointers
-    ctx->tgraphs.clear();
+    drop_graphs(ctx);   // captured launches hold the old state pointers
     ctx->tg_last = spef_ctx::TGraph{};
     void** ptrs[] = {(void**)&ctx->t_ori_state, (void**)&ctx->t_pos_state, (void**)&ctx->t_has, (void**)&ctx->t_prev_still, (void**)&ctx->t_prev_video};
     for (void** p : ptrs) { if (*p) cudaFree(*p); *p = nullptr; }

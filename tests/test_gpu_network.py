@@ -455,3 +455,42 @@ def test_uint8_host_paths_and_decode_guards(sd):
                 yield {"torch": x}, targets
     with pytest.raises(ValueError, match="orientation decoding"):
         evaluation(spe, {"valid": NanLoader()}, su, ("valid",))
+
+
+def test_eval_step_graph_replay_equals_direct_launches(sd, images, monkeypatch):
+    """spef_eval_batch replays its ~35 launches as ONE CUDA graph once a call signature has come back (same device buffers, same
+    batch): per-image errors bit-identical to direct launches (SPEF_EVAL_GRAPH=0), accumulated sums equal, both host- and
+    device-buffer routes; changing the histogram afterwards drops the graphs (they hold table pointers)."""
+    tg = synthetic.synthetic_targets(4)
+    qt, tt = torch.as_tensor(tg["ori"]).float(), torch.as_tensor(tg["pos"]).float()
+    hist = O.ori_histogram(12)[0]
+    res = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("SPEF_EVAL_GRAPH", mode)
+        eng = _engine(sd, "bf16")
+        eng.set_ori_histogram(hist)
+        x, q, t = images.cuda(), qt.cuda(), tt.cuda()
+        eng.eval_reset()
+        l0 = eng.launch_count()
+        pers = [eng.eval_batch(x, q, t, want_per_image=False) for _ in range(2)]      # direct, direct (signature seen) ...
+        per_dev = [eng._empty(4, 2) for _ in range(1)][0]
+        from spef_b200._ffi import ptr
+        for _ in range(4):                                                               # ... seen, captured + replayed, replayed, replayed
+            eng._ck(eng.lib.spef_eval_batch(eng._h, ptr(x), ptr(q), ptr(t), 4, ptr(per_dev), None))
+        torch.cuda.synchronize()
+        n_launch = eng.launch_count() - l0
+        host = [eng.eval_batch(images, qt, tt, want_per_image=True) for _ in range(4)]  # host route: the ctx's own device buffers
+        sums = eng.eval_read()
+        res[mode] = (per_dev.cpu().numpy().copy(), [h.copy() for h in host], sums, n_launch)
+        if mode == "1":
+            eng.set_ori_histogram(O.ori_histogram(12)[0])                                # drops the graphs; the next calls run and re-capture
+            again = [eng.eval_batch(images, qt, tt, want_per_image=True) for _ in range(3)]
+            for a in again:
+                np.testing.assert_array_equal(a, host[0])
+        eng.close()
+    np.testing.assert_array_equal(res["0"][0], res["1"][0])
+    for a, b in zip(res["0"][1], res["1"][1]):
+        np.testing.assert_array_equal(a, b)
+    np.testing.assert_array_equal(res["1"][1][0], res["1"][1][3])
+    np.testing.assert_allclose(res["0"][2], res["1"][2], rtol=1e-12)
+    assert res["0"][2][3] == 40 and res["0"][3] == res["1"][3], (res["0"][2], res["0"][3], res["1"][3])   # 10 steps of 4 images; launch_count counts replayed launches
