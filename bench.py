@@ -52,6 +52,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
+    ap.add_argument("--lanes", type=int, default=2, help="device contexts / CUDA streams the steps are issued over round-robin (Engine.lanes); 1 = one stream")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--pw-impl", type=int, default=0, help="0 tcgen05 (default), 1 SIMT cross-check")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -439,6 +440,24 @@ def run_b200(args):
     images = host_images.to(dev)
     qt, tt = qt_h.to(dev), tt_h.to(dev)
     stream = torch.cuda.current_stream(dev)
+    # steps go round-robin over `lanes` device contexts with the same weights, one CUDA stream each (Engine.lanes, what evaluation()
+    # does with the batches of a phase): every step is still one full pass over one 256-image batch, consecutive steps overlap on
+    # the GPU (the partly filled last wave of one step's kernels next to the other step's kernels).  Each lane has its own batch.
+    lanes = eng.lanes(max(1, args.lanes))
+    lane_images = [images] + [images.clone() for _ in lanes[1:]]
+
+    def lanes_begin(ev):
+        for l in lanes:
+            l.side_stream.wait_event(ev)
+
+    def lanes_end():
+        for l in lanes:
+            stream.wait_stream(l.side_stream)
+
+    def step(i):
+        l = lanes[i % len(lanes)]
+        with torch.cuda.stream(l.side_stream):
+            l.eval_batch(lane_images[i % len(lanes)], qt, tt)
 
     def sync_all():
         torch.cuda.synchronize(dev)
@@ -447,9 +466,11 @@ def run_b200(args):
             torch.cuda.synchronize(dev)
 
     # ---- warm-up -------------------------------------------------------------------------------------
-    eng.eval_reset()
-    for _ in range(max(args.warmup, 3)):
-        eng.eval_batch(images, qt, tt)
+    for l in lanes:
+        l.eval_reset()
+    sync_all()
+    for i in range(max(args.warmup, 3) * len(lanes)):
+        step(i)
     sync_all()
 
     # ---- timed region: K steps, inputs resident in HBM, CUDA events on the launching stream ----------
@@ -458,24 +479,30 @@ def run_b200(args):
     sampler = ClockSampler(local)
     sampler.start()
     t_pre = time.perf_counter()
+    i_pre = 0
     while time.perf_counter() - t_pre < 0.4:
-        eng.eval_batch(images, qt, tt)
+        step(i_pre)
+        i_pre += 1
         torch.cuda.synchronize()
-    eng.eval_reset()
-    launches0 = eng.launch_count()
+    for l in lanes:
+        l.eval_reset()
+    launches0 = sum(l.launch_count() for l in lanes)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
     e0.record(stream)
-    for _ in range(args.steps):
-        eng.eval_batch(images, qt, tt)
-    sums = eng.eval_sums_tensor() if dist is None else None
-    if dist is not None:  # the path's one exchange step: SUM all-reduce of the 8 ESA accumulators over NVLink
-        sums = torch.from_numpy(eng.eval_read()).to(dev)
+    lanes_begin(e0)
+    for i in range(args.steps):
+        step(i)
+    lanes_end()
+    # the ESA accumulators are per context and linear: one vector per lane, added (and, at N > 1, all-reduced: the path's one
+    # exchange step, SUM of the 8 float64 accumulators over NVLink)
+    sums = torch.from_numpy(sum(l.eval_read() for l in lanes)).to(dev)
+    if dist is not None:
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)
     e1.record(stream)
     sync_all()
     ms_total = e0.elapsed_time(e1)
-    launches = eng.launch_count() - launches0
+    launches = sum(l.launch_count() for l in lanes) - launches0
     clocks = sampler.stop()
     if dist is not None:
         t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
@@ -489,44 +516,50 @@ def run_b200(args):
     # two pinned input batches alternate (a loader hands over a fresh buffer every step); the per-image results of every
     # step are read back into their own pinned buffer; spef_eval_submit_host overlaps the H2D of step i+1 with step i
     host_images2 = host_images.clone().pin_memory()
-    per_out = [torch.empty((B, 2), dtype=torch.float32).pin_memory() for _ in range(2)]
-    for i in range(2):
-        eng.eval_submit_host(host_images if i % 2 == 0 else host_images2, qt_h, tt_h, per_out[i % 2])
-    eng.eval_wait()
-    sync_all()
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        eng.eval_submit_host(host_images if i % 2 == 0 else host_images2, qt_h, tt_h, per_out[i % 2])
-    eng.eval_wait()
-    eng.eval_read()
-    sync_all()
-    e2e_s = time.perf_counter() - t0
-    if dist is not None:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
+    L = len(lanes)
+    per_out = [torch.empty((B, 2), dtype=torch.float32).pin_memory() for _ in range(2 * L)]
+
+    def e2e_loop(bufs):
+        """K pipelined host-buffer steps, round-robin over the lanes (each lane double-buffers its own H2D copies); wall clock
+        around submit ... wait + read of the sums, max over ranks."""
+        def submit(i):
+            l = lanes[i % L]
+            with torch.cuda.stream(l.side_stream):
+                l.eval_submit_host(bufs[(i // L) % 2], qt_h, tt_h, per_out[i % (2 * L)])
+
+        def drain():
+            for l in lanes:
+                with torch.cuda.stream(l.side_stream):
+                    l.eval_wait()
+        for i in range(2 * L):
+            submit(i)
+        drain()
+        sync_all()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            submit(i)
+        drain()
+        for l in lanes:
+            l.eval_read()
+        sync_all()
+        el = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([el], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            el = float(t.item())
+        return el
+
+    e2e_s = e2e_loop([host_images, host_images2])
     # same loop with uint8 pixels (the input side of the path: ToTensor's /255 moves into the stem; 4x fewer H2D bytes)
     e2e_u8 = None
     if args.precision == "bf16" and args.pw_impl == 0:
         u8a = (host_images * 255).round().to(torch.uint8).pin_memory()
         u8b = u8a.clone().pin_memory()
-        eng.set_image_dtype(torch.uint8)
-        for i in range(2):
-            eng.eval_submit_host(u8a if i % 2 == 0 else u8b, qt_h, tt_h, per_out[i % 2])
-        eng.eval_wait()
-        sync_all()
-        t0 = time.perf_counter()
-        for i in range(args.steps):
-            eng.eval_submit_host(u8a if i % 2 == 0 else u8b, qt_h, tt_h, per_out[i % 2])
-        eng.eval_wait()
-        eng.eval_read()
-        sync_all()
-        u8_s = time.perf_counter() - t0
-        eng.set_image_dtype(torch.float32)
-        if dist is not None:
-            t = torch.tensor([u8_s], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            u8_s = float(t.item())
+        for l in lanes:
+            l.set_image_dtype(torch.uint8)
+        u8_s = e2e_loop([u8a, u8b])
+        for l in lanes:
+            l.set_image_dtype(torch.float32)
         e2e_u8 = {"value": world * B * args.steps / u8_s, "unit": UNIT, "h2d_bytes_per_step": int(u8a.numel() + B * 28),
                   "d2h_bytes_per_step": int(B * 8), "note": "uint8 host images (spef_set_image_dtype(SPEF_IMG_U8)); results bit-identical to float images"}
     # the H2D roof this end-to-end number runs against: a plain cudaMemcpyAsync of the same pinned 283 MB buffer, rank 0 alone and
@@ -656,7 +689,11 @@ def run_b200(args):
                                + ("/[2]" if world > 1 else "") + ")",
                    "weights": "calibrated random init (seed 7)", "l2": "inputs larger than L2 (283 MB image batch, GB-scale activations)",
                    "parallelism": f"batch-sharded x{world}, one NCCL all-reduce of 8 f64 at the end" if world > 1 else "single GPU",
-                   "pw_impl": "tcgen05" if (args.precision == "bf16" and args.pw_impl == 0) else "simt"},
+                   "pw_impl": "tcgen05" if (args.precision == "bf16" and args.pw_impl == 0) else "simt",
+                   "lanes": len(lanes),
+                   "lanes_note": "the K timed steps (each one full pass over one batch, each replayed as one CUDA graph by the library) are issued "
+                                 "round-robin over this many device contexts / CUDA streams (Engine.lanes, as evaluation() issues the batches of a "
+                                 "phase), so consecutive steps overlap on the GPU; ms_per_step = timed region / K; --lanes 1 is one stream"},
         "e2e": e2e, "e2e_uint8_input": e2e_u8, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
         "step_roofline": {"algorithmic_bytes_per_step": shipped_bytes, "flops_per_step": tot_flops,
                           "achieved_GBps": shipped_bytes / (step_ms * 1e-3) / 1e9, "hbm_frac": shipped_bytes / (step_ms * 1e-3) / 1e9 / pk["hbm_gbs"],

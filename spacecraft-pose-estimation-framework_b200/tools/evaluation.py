@@ -104,33 +104,49 @@ def evaluation(
     for phase in split:
         if isinstance(spe_model, SPEB200):
             eng = spe_model.engine
-            eng.eval_reset()
+            # the batches of the phase go round-robin over the lanes (device contexts with the same weights, one CUDA stream each:
+            # Engine.lanes); the caller's stream only orders the loader's own device work before each batch
+            lanes = eng.lanes(getattr(spe_model, "lanes", 1))
+            main = torch.cuda.current_stream(eng.device)
+            for l in lanes:
+                l.side_stream.wait_stream(main)
+                with torch.cuda.stream(l.side_stream):
+                    l.eval_reset()
             per, keep = [], []
             dtype0 = eng.image_dtype
-            for images, targets in dataloader[phase]:
+            for i, (images, targets) in enumerate(dataloader[phase]):
+                l = lanes[i % len(lanes)]
                 x = images['torch']
                 # a loader that yields uint8 pixels (ToTensor not applied yet) takes the uint8 ingest route: a quarter of the
                 # H2D bytes, bit-identical results (the stem divides by 255 itself)
                 want = torch.uint8 if (x.dtype == torch.uint8 and eng.precision == "bf16") else torch.float32
-                if want != eng.image_dtype:
-                    eng.eval_wait()
-                    eng.set_image_dtype(want)
-                if x.device.type == "cpu":
-                    # pipelined: the H2D copy of this batch overlaps the kernels of the previous one; host buffers are kept
-                    # alive until the phase is drained
-                    x = eng._host_img(x)
-                    qt = torch.as_tensor(targets['ori']).detach().to("cpu", torch.float32).contiguous()
-                    tt = torch.as_tensor(targets['pos']).detach().to("cpu", torch.float32).contiguous()
-                    out = torch.empty((x.shape[0], 2), dtype=torch.float32, pin_memory=True)
-                    eng.eval_submit_host(x, qt, tt, out)
-                    keep.append((x, qt, tt))
-                    per.append(out)
-                else:
-                    per.append(eng.eval_batch(x, targets['ori'], targets['pos'], want_per_image=True))
-            eng.eval_wait()
-            sums = eng.eval_read()
-            if eng.image_dtype != dtype0:
-                eng.set_image_dtype(dtype0)
+                with torch.cuda.stream(l.side_stream):
+                    if want != l.image_dtype:
+                        l.eval_wait()
+                        l.set_image_dtype(want)
+                    if x.device.type == "cpu":
+                        # pipelined: the H2D copy of this batch overlaps the kernels of the previous one; host buffers are kept
+                        # alive until the phase is drained
+                        x = l._host_img(x)
+                        qt = torch.as_tensor(targets['ori']).detach().to("cpu", torch.float32).contiguous()
+                        tt = torch.as_tensor(targets['pos']).detach().to("cpu", torch.float32).contiguous()
+                        out = torch.empty((x.shape[0], 2), dtype=torch.float32, pin_memory=True)
+                        l.eval_submit_host(x, qt, tt, out)
+                        keep.append((x, qt, tt))
+                        per.append(out)
+                    else:
+                        l.side_stream.wait_stream(main)      # the loader produced this batch on the caller's stream
+                        x.record_stream(l.side_stream)
+                        per.append(l.eval_batch(x, targets['ori'], targets['pos'], want_per_image=True))
+                        keep.append(x)
+            sums = np.zeros(8, np.float64)
+            for l in lanes:
+                with torch.cuda.stream(l.side_stream):
+                    l.eval_wait()
+                    sums += l.eval_read()
+                    if l.image_dtype != dtype0:
+                        l.set_image_dtype(dtype0)
+                main.wait_stream(l.side_stream)
             per = [p.cpu().numpy() if isinstance(p, torch.Tensor) else p for p in per]
             del keep
             per_image = np.concatenate(per, axis=0) if per else np.zeros((0, 2), np.float32)

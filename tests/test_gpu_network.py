@@ -494,3 +494,50 @@ def test_eval_step_graph_replay_equals_direct_launches(sd, images, monkeypatch):
     np.testing.assert_array_equal(res["1"][1][0], res["1"][1][3])
     np.testing.assert_allclose(res["0"][2], res["1"][2], rtol=1e-12)
     assert res["0"][2][3] == 40 and res["0"][3] == res["1"][3], (res["0"][2], res["0"][3], res["1"][3])   # 10 steps of 4 images; launch_count counts replayed launches
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_evaluation_lanes_equal_single_stream(precision):
+    """evaluation() issues the batches of a phase round-robin over SPEB200.lanes device contexts / CUDA streams (Engine.lanes):
+    same rec_score / rec_error as one lane (the per-context float64 sums are added: linear), per-image statistics from the same
+    per-image rows; host batches, device-resident batches and uint8 host batches; a weight reload reaches the twin context."""
+    from spef_b200.modeling import import_model
+    from spef_b200.spe import SPEB200, SPEUtils
+    from spef_b200.tools import evaluation
+    su = SPEUtils(None, 'classification', 12, 3, False, 'regression', 10, 100, None)
+    loader = synthetic.SyntheticLoader(26, 4)        # 7 batches (the last one ragged): the lanes get 4 and 3
+
+    class DevLoader:
+        def __iter__(self):
+            for im, tg in loader:
+                yield {"torch": im["torch"].cuda()}, tg
+
+    class U8Loader:
+        def __iter__(self):
+            for im, tg in loader:
+                yield {"torch": (im["torch"] * 255).round().to(torch.uint8)}, tg
+
+    def run(lanes, sd):
+        model, _ = import_model({"valid": loader}, 'mobilenet_v2_pytorch', 'ursonet_pytorch', ori_mode='classification',
+                                n_ori_bins=su.orientation.n_bins, pos_mode='regression', precision=precision)
+        model.load_state_dict(sd)
+        spe = SPEB200(model, torch.device("cuda:0"), su, lanes=lanes)
+        out = [evaluation(spe, {"valid": ld}, su, ("valid",)) for ld in ([loader, DevLoader()] + ([U8Loader()] if precision == "bf16" else []))]
+        if lanes > 1:
+            assert len(spe.engine._twins) == lanes - 1
+            sd2 = {k: (v * 1.01 if k == "head.pos.0.bias" else v) for k, v in sd.items()}
+            model.load_state_dict(sd2)
+            spe.update_model(model, torch.device("cuda:0"))
+            out.append(evaluation(spe, {"valid": loader}, su, ("valid",)))
+        spe.delete_model()
+        return out
+    sd = synthetic.synthetic_state_dict(1728, 3)
+    one, two = run(1, sd), run(2, sd)
+    for (s1, e1), (s2, e2) in zip(one, two):
+        for k in ("ori", "pos", "esa"):
+            np.testing.assert_allclose(s2["valid"][k], s1["valid"][k], rtol=1e-12)
+        for k in ("ori", "pos", "ori_std", "pos_std", "ori_mad", "pos_mad"):
+            np.testing.assert_allclose(e2["valid"][k], e1["valid"][k], rtol=1e-12)
+    # host and device-resident loaders agree; the reloaded weights (position bias scaled) changed the position score on BOTH lanes
+    np.testing.assert_allclose(two[0][0]["valid"]["esa"], two[1][0]["valid"]["esa"], rtol=1e-12)
+    assert abs(two[-1][0]["valid"]["pos"][0] - two[0][0]["valid"]["pos"][0]) > 1e-6
