@@ -831,7 +831,7 @@ def temporal_numbers(n_frames_b1=200, n_steps_s64=50, cpu_frames=0):
         gbs = by / (np.median(lat) * 1e-3) / 1e9
         out[key] = {"p50_ms": float(np.percentile(lat, 50)), "p99_ms": float(np.percentile(lat, 99)),
                     "frames_per_s": float(S / (np.median(lat) * 1e-3)), "kernels_per_frame_step": eng.launch_count() - l0,
-                    "cuda_graph_inside_the_library": bool(S <= 8),
+                    "cuda_graph_inside_the_library": bool(S <= int(os.environ.get("SPEF_TEMPORAL_GRAPH_MAX", "256")) and os.environ.get("SPEF_TEMPORAL_GRAPH", "1") != "0"),
                     "roofline": {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"], "traffic": None,
                                  "note": "per-layer algorithmic bytes of one forward at this batch + the weights; batch 1 is latency-bound (one frame cannot fill 148 SMs)"}}
         eng.close()
