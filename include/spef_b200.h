@@ -137,6 +137,17 @@ int spef_block_info(const spef_ctx* ctx, int32_t block, int32_t* first_layer, in
 int spef_set_fusion(spef_ctx* ctx, int32_t on);
 int spef_block_forward(spef_ctx* ctx, int32_t block, const void* in_dev, void* out_dev, int32_t batch, void* stream);
 
+/* Stem fused into the first block (features[0] ConvBnAct(3 -> 32, k3, s2) + features[1], src/modeling/backbone/mobilenet_v2.py:252-262;
+ * BF16 tcgen05 path, both image dtypes): ONE kernel reads the image and writes the first block's output [B,H/2,W/2,16]; the stem's output
+ * (the largest tensor of the network) never reaches HBM and stays FP32 between the stem GEMM and the depthwise taps.  Default on
+ * (SPEF_STEM_FUSE=0 in the environment or spef_set_stem_fusion(ctx, 0): separate stem launch, the parity cross-check);
+ * spef_stem_fusion_active reports whether spef_forward takes that route in the current configuration (it needs the channel-lane
+ * kernel of block 0 and spef_set_fusion on); spef_stem_block_forward is the teacher-forced launch (images_dev as for spef_forward,
+ * out_dev NHWC bf16) and fails with SPEF_ERR_UNSUPPORTED when the route is not active. */
+int spef_set_stem_fusion(spef_ctx* ctx, int32_t on);
+int spef_stem_fusion_active(const spef_ctx* ctx);
+int spef_stem_block_forward(spef_ctx* ctx, const void* images_dev, void* out_dev, int32_t batch, void* stream);
+
 /* ---- encode (label side) and error statistics (8f #3) ----------------------------
  * spef_encode_ori replaces OrientationSoftClassification.encode for a batch of labels
  * (src/spe/classification_utils.py:85-111): k_b = exp(-((2 acos(min(1, |q . h_b|)) / pi)^2 / (2 variance))), bins with

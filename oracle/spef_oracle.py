@@ -163,7 +163,8 @@ def apply_layer(layer: dict, x: torch.Tensor, res: Optional[torch.Tensor], bf16:
 def forward_folded(sd, images: torch.Tensor, bf16: bool = False, return_layers: bool = False, fp32_hidden_blocks=()):
     """BN-folded forward; bf16=True reproduces the CUDA BF16 path's rounding points.  fp32_hidden_blocks: feature indices
     (1..17) of the InvertedResidual blocks that run as a channel-lane fused kernel, whose hidden tensor (expand output) stays
-    FP32 between the expand GEMM and the depthwise taps (Engine.fp32_hidden_blocks())."""
+    FP32 between the expand GEMM and the depthwise taps (Engine.fp32_hidden_blocks()); 0 stands for the stem fused into the first
+    block's kernel (its output, the hidden tensor of that kernel, is not rounded either)."""
     fp32_hidden_blocks = set(fp32_hidden_blocks)
     outs = []
     with torch.no_grad():
@@ -174,7 +175,8 @@ def forward_folded(sd, images: torch.Tensor, bf16: bool = False, return_layers: 
             if first_of_block:
                 block_in = x
             res = block_in if layer["residual"] else None
-            x = apply_layer(layer, x, res, bf16, round_out=not (layer["role"] == "expand" and layer["block"] in fp32_hidden_blocks))
+            keep_fp32 = (layer["role"] == "expand" and layer["block"] in fp32_hidden_blocks) or (layer["kind"] == "stem" and 0 in fp32_hidden_blocks)
+            x = apply_layer(layer, x, res, bf16, round_out=not keep_fp32)
             outs.append(x)
         f = x.mean([2, 3])
         wo, wp = sd["head.ori.1.weight"], sd["head.pos.0.weight"]

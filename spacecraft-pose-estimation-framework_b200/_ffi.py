@@ -57,6 +57,9 @@ SIGNATURES = {
     "spef_block_info": (C.c_int, [_vp, _i32] + [C.POINTER(_i32)] * 8),
     "spef_set_fusion": (C.c_int, [_vp, _i32]),
     "spef_block_forward": (C.c_int, [_vp, _i32, _vp, _vp, _i32, _vp]),
+    "spef_set_stem_fusion": (C.c_int, [_vp, _i32]),
+    "spef_stem_fusion_active": (C.c_int, [_vp]),
+    "spef_stem_block_forward": (C.c_int, [_vp, _vp, _vp, _i32, _vp]),
     "spef_decode_ori": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "spef_decode_pos": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "spef_score": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),

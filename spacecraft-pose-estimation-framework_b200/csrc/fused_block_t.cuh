@@ -84,19 +84,31 @@ struct FbtParams {
                        // of the weight stages, which then hold only Wp and the aux rows (we_bytes = 0): 16 KB less for three chunks,
                        // which is what lets a second x stage fit (one x stage left the expand issuer waiting ~3000 cycles per tile
                        // for the TMA load of the next tile: clock64 trace of block 3)
+  // Stem fused into the t = 1 block (STEM instantiation; reference: mobilenet_v2.py:252-262 -- features[0] ConvBnAct(3 -> 32, k3, s2) followed by
+  // the first InvertedResidual): the stem conv IS an expand conv with K = 27 taps (padded to 32) whose x tile is built on the SM.
+  // The TMA warp stages the image patch of a tile ({patch_w columns, 2 THI + 1 rows, 3 planes} of the NCHW image, zero fill outside the
+  // image = the stem's padding), four im2col warps (the second epilogue team's slot) write the K-major operand rows [27 taps | 0 x 5] of the
+  // four strips -- two strips share a 128-byte row (strip parity = which 64-byte half), so an x stage is 2 x n_px x 128 bytes --
+  // and the stem output (FP32, ReLU folded into the workers' max) never leaves the SM.
+  int stem;            // 1: STEM instantiation
+  int img_u8;          // image dtype of the patch (uint8: taps through the 256-entry table bf16(u8 / 255))
+  int patch_w;         // patch columns (104 f32 | 128 u8) and the patch column of input column 2 ox0 - 1 ... see the producer
+  int patch_x0;        // pixels between the patch origin and input column 2 * ox0 (4 f32 | 16 u8: the innermost TMA coordinate stays 16-byte aligned)
+  int patch_stages, patch_stride;
   long long* trace;
 };
 
 __host__ __device__ inline int w_stage_bytes(int we_bytes, int cpad) { return we_bytes + 2 * cpad * 128 + AUX_STRIDE; }
 __host__ __device__ inline int x_stage_bytes(int kc_in, int n_px) { return kc_in * n_px * 128; }
 inline size_t smem_bytes(const FbtParams& p, int ng) {
-  return 1024 + (size_t)p.x_stages * x_stage_bytes(p.kc_in, p.n_px) + (size_t)p.wz_bytes + (size_t)p.w_stages * w_stage_bytes(p.we_bytes, p.cpad) +
-         (size_t)ng * p.a2_bufs * A2_BYTES + 1024 /*bias: cpad <= 128 floats, padded*/ + 512 /*barriers*/;
+  return 1024 + (size_t)p.x_stages * x_stage_bytes(p.stem ? 2 : p.kc_in, p.n_px) + (size_t)p.patch_stages * p.patch_stride + (size_t)p.wz_bytes +
+         (size_t)p.w_stages * w_stage_bytes(p.we_bytes, p.cpad) +
+         (size_t)ng * p.a2_bufs * A2_BYTES + 1024 /*bias: cpad <= 128 floats, padded (STEM: + the uint8 table)*/ + 640 /*barriers*/;
 }
 // Register budget per role (setmaxnreg only moves registers inside the CTA's own launch allocation; every count is a multiple
 // of 8 and each role is a whole warpgroup of four warps).  Two worker groups + two epilogue teams + control = 20 warps x 96 at launch:
 //   8 * 160 + 8 * 56 + 4 * 40 = 1888 <= 1920.   (A first version that counted on the SM's unallocated registers deadlocked in setmaxnreg.inc.)
-template <int NG> struct RegPlan { static constexpr int WORKER = 160, EPI = 56, CTRL = 40; };
+template <int NG> struct RegPlan { static constexpr int WORKER = 160, EPI = 56, CTRL = 40, PROD = 64; };   // STEM: 8 * 160 + 4 * 56 + 4 * 64 + 4 * 40 = 1920
 template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 
@@ -213,7 +225,7 @@ __device__ __forceinline__ uint32_t bias_relu_bf16x2(uint32_t a0, uint32_t a1, u
 //     at 96 registers): block 2 288 -> 366 us, block 4 156 -> 190 us -- the extra halo rows, spills and issue contention cost more
 //     than the halved per-item latency gains.  The worker loop is not simply latency-bound per warp: ncu shows each worker warp
 //     issuing 26 % of the time with no dominant stall reason (wait 17 %, TMEM / barrier scoreboard 13 %, not selected 12 %).
-template <int S, int TH, int NG, bool EXP>
+template <int S, int TH, int NG, bool EXP, bool STEM = false>
 __global__ void __launch_bounds__(32 * (CTRL_WARPS + NG * GWT), 1)
 fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWe,
                      const __grid_constant__ CUtensorMap tmWp, const FbtParams p) {
@@ -223,10 +235,12 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   constexpr int TWI = (TW - 1) * S + 3;           // 14 | 13 input columns: one tcgen05.ld.x16 per pixel row
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const int xsb = x_stage_bytes(p.kc_in, p.n_px);
+  const int xsb = x_stage_bytes(STEM ? 2 : p.kc_in, p.n_px);
+  constexpr int TEAMS = STEM ? 1 : 2;             // epilogue teams (STEM: the second team's warps are the im2col producers)
   const int wsb = w_stage_bytes(p.we_bytes, p.cpad);
   uint8_t* x_s = smem;
-  uint8_t* wz_s = x_s + (size_t)p.x_stages * xsb;             // shared-zero expand weights (stack = 2), else empty
+  uint8_t* patch_s = x_s + (size_t)p.x_stages * xsb;          // STEM: image patch ring, else empty
+  uint8_t* wz_s = patch_s + (size_t)p.patch_stages * p.patch_stride;   // shared-zero expand weights (stack = 2), else empty
   uint8_t* w_s = wz_s + (size_t)p.wz_bytes;
   uint8_t* a2_s = w_s + (size_t)p.w_stages * wsb;             // [NG][a2_bufs][A2_BYTES]
   float* bp_s = reinterpret_cast<float*>(a2_s + (size_t)NG * p.a2_bufs * A2_BYTES);   // [256] (cpad <= 128)
@@ -246,6 +260,8 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   uint64_t* proj_full = a2_empty + 2 * MAX_NGT;   // [N_PFULL]
   uint64_t* proj_empty = proj_full + N_PFULL;     // [MAX_PROJ]
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(proj_empty + MAX_PROJ);
+  uint64_t* patch_full = reinterpret_cast<uint64_t*>(tmem_ptr_s + 2);   // [4]  STEM: TMA -> im2col producers
+  uint64_t* patch_empty = patch_full + 4;                               // [4]  STEM: im2col producers -> TMA
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -274,7 +290,14 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   itp.n_chunks = p.n_chunks; itp.x_stages = p.x_stages; itp.w_stages = p.w_stages; itp.resident = p.resident;
   itp.proj_stages = p.proj_stages; itp.n_acc = p.n_acc;
 
-  for (int i = threadIdx.x; i < 256; i += (int)blockDim.x) bp_s[i] = (i < p.cpad) ? p.bp[i] : 0.f;
+  for (int i = threadIdx.x; i < (STEM ? 128 : 256); i += (int)blockDim.x) bp_s[i] = (i < p.cpad) ? p.bp[i] : 0.f;
+  if (STEM) {   // uint8 images: pixel -> bf16(float(u8) / 255.0f), what rounding the reference's float tensor gives (the stem kernel's table)
+    uint16_t* lut = reinterpret_cast<uint16_t*>(bp_s + 128);
+    for (int i = threadIdx.x; i < 256; i += (int)blockDim.x) {
+      const bf16 h = __float2bfloat16_rn(__fdiv_rn((float)i, 255.0f));
+      lut[i] = *reinterpret_cast<const uint16_t*>(&h);
+    }
+  }
   if (warp == WARP_TMA && lane == 0) {
     tc::tma_prefetch_desc(&tmX);
     tc::tma_prefetch_desc(&tmWe);
@@ -282,11 +305,13 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   }
   if (warp == WARP_MMA && lane == 0) {
     for (int i = 0; i < 4; ++i) {
-      tc::mbar_init(tc::smem_u32(&x_full[i]), 1);
+      tc::mbar_init(tc::smem_u32(&x_full[i]), STEM ? 4 : 1);    // STEM: one arrival per im2col warp
       tc::mbar_init(tc::smem_u32(&x_empty[i]), 1);
+      tc::mbar_init(tc::smem_u32(&patch_full[i]), 1);
+      tc::mbar_init(tc::smem_u32(&patch_empty[i]), 4);
     }
     for (int i = 0; i < N_PFULL; ++i) tc::mbar_init(tc::smem_u32(&proj_full[i]), 1);
-    for (int i = 0; i < MAX_PROJ; ++i) tc::mbar_init(tc::smem_u32(&proj_empty[i]), ROT ? 1 : (p.stack > 1 ? 2 * N_EPI : N_EPI));
+    for (int i = 0; i < MAX_PROJ; ++i) tc::mbar_init(tc::smem_u32(&proj_empty[i]), ROT ? 1 : (p.stack > 1 ? TEAMS * N_EPI : N_EPI));
     for (int i = 0; i < MAX_W_STAGES; ++i) {
       tc::mbar_init(tc::smem_u32(&w_full[i]), 1);
       tc::mbar_init(tc::smem_u32(&w_empty[i]), 1);
@@ -345,8 +370,14 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       uint32_t xph = 0, wph = 0;
       for (int i = 0; i < my_tiles; ++i) {
         const int oy0 = ty * TH, ox0 = tx * TW * p.stack;
+        if (STEM) {
+          // image patch of the tile: hidden (= stem output) rows oy0 - 1 .. oy0 + TH read input rows 2 oy0 - 3 .. 2 oy0 + 2 TH + 1
+          mbar_wait_sleep(tc::smem_u32(&patch_empty[xs]), xph ^ 1u, 100);
+          const uint32_t fbar = tc::smem_u32(&patch_full[xs]);
+          tc::mbar_arrive_expect_tx(fbar, (uint32_t)(p.patch_w * (2 * THI + 1) * 3 * (p.img_u8 ? 1 : 4)));
+          tc::tma_load_3d_img(tc::smem_u32(patch_s + (size_t)xs * p.patch_stride), &tmX, 2 * ox0 - p.patch_x0, 2 * oy0 - 3, 3 * tb, fbar);
+        } else {
         mbar_wait_sleep(tc::smem_u32(&x_empty[xs]), xph ^ 1u, 100);
-        {
           const uint32_t fbar = tc::smem_u32(&x_full[xs]);
           tc::mbar_arrive_expect_tx(fbar, x_tx);
           for (int kc = 0; kc < p.kc_in; ++kc)
@@ -371,7 +402,7 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
             if (!p.resident && ++ws == p.w_stages) { ws = 0; wph ^= 1u; }
           }
         }
-        if (++xs == p.x_stages) { xs = 0; xph ^= 1u; }
+        if (++xs == (STEM ? p.patch_stages : p.x_stages)) { xs = 0; xph ^= 1u; }
         tx += dtx; ty += dty; tb += db;
         if (tx >= p.tiles_x) { tx -= p.tiles_x; ++ty; }
         if (ty >= p.tiles_y) { ty -= p.tiles_y; ++tb; }
@@ -410,7 +441,8 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
           const uint32_t a_off = (p.stack > 1) ? (uint32_t)(p.stack - 1 - kc) * ls_rows16 : (uint32_t)kc * (uint32_t)(CL * 128 >> 4);
           for (uint32_t ks = 0; ks < ksteps; ++ks)
             fb::mma_elect(d0, a0 + (uint64_t)(a_off + ks * 2u),
-                          b0 + (uint64_t)((uint32_t)kc * xk_step + ks * 2u), idesc_e, (kc > 0 || ks > 0) ? 1u : 0u);
+                          b0 + (uint64_t)((STEM ? ((uint32_t)kc >> 1) * xk_step + ((uint32_t)kc & 1u) * 4u : (uint32_t)kc * xk_step) + ks * 2u), idesc_e,
+                          (kc > 0 || ks > 0) ? 1u : 0u);
         }
         fb::commit_elect(tc::smem_u32(&acc_full[as]));
         if (lane == 0) FBT_TRACE(n, 2);
@@ -463,7 +495,7 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       fb::commit_elect(tc::smem_u32(&proj_full[i & (N_PFULL - 1)]));
       if (++ps == p.proj_stages) { ps = 0; pph ^= 1u; }
     }
-  } else if (warp >= FIRST_EPI_WARP && warp < FIRST_EPI_WARP + EPI_WARPS) {
+  } else if (warp >= FIRST_EPI_WARP && warp < FIRST_EPI_WARP + 4 * TEAMS) {
     // ===================== epilogue: project accumulator -> +bias (+x) -> bf16 -> global =====================
     // ncu (source page) and the clock64 traces showed this role, not the workers, pacing the kernel after the worker diet: one
     // warp per lane quarter ran ~150 dependent instructions per tile (strip) at ~8-10 cycles each, and for the 24-pixel stride-2
@@ -506,7 +538,7 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       // one strip and Cout <= 32: the accumulator row is a single tcgen05.ld -- hand the TMEM stage back as soon as it is in registers
       const bool early = (p.stack == 1 && p.Cout <= 32);
       const uint32_t t_tile = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(p.proj_col0 + ps * p.proj_stride);
-      for (int st = (p.stack > 1 ? team : 0); st < p.stack; st += (p.stack > 1 ? 2 : 1)) {
+      for (int st = (p.stack > 1 ? team : 0); st < p.stack; st += (p.stack > 1 ? TEAMS : 1)) {
         const bool valid = row_ok && (ox0 + st * TW + ox_l) < p.Wo;
         const long long off = (long long)(pix0 + st * TW) * p.Cout;
         bf16* yp = p.y + off;
@@ -565,6 +597,87 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       if (tx >= p.tiles_x) { tx -= p.tiles_x; ++ty; }
       if (ty >= p.tiles_y) { ty -= p.tiles_y; ++tb; }
     }
+    }
+  } else if (STEM && warp >= FIRST_EPI_WARP + 4 && warp < FIRST_EPI_WARP + 8) {
+    // ===================== STEM: im2col producers (four warps): image patch -> K-major expand operand of the four strips =====================
+    // Thread t < THI * TWI owns hidden pixel (r, j) = (t / TWI, t % TWI) of EVERY strip's haloed box: operand row t of the strip, 27 taps
+    // k = (ci * 3 + ky) * 3 + kx as bf16 + 5 zeros = 64 bytes = four 16-byte chunks at logical chunk (strip & 1) * 4 .. + 3 of row t in the
+    // 128-byte-swizzled K chunk (strip >> 1).  Tap (ci, ky, kx) of strip s is patch[ci][2 r + ky][24 s + 2 j + patch_x0 - 3 + kx]: hidden
+    // column ox0 + 12 s - 1 + j reads input columns 2 (ox0 + 12 s - 1 + j) - 1 + kx, and the patch starts at input column 2 ox0 - patch_x0.
+    // kx = 1, 2 are an aligned pair (patch_x0 is a multiple of 4).  A hidden pixel outside the stem's output gets whatever the taps give
+    // (zeros beyond the image): the workers overwrite the halo columns and drop the halo rows, exactly as for an expand conv.
+    reg_dec<RegPlan<NG>::PROD>();
+    const int t = (int)threadIdx.x - 32 * (FIRST_EPI_WARP + 4);
+    const bool act = t < THI * TWI;
+    const int tt = act ? t : 0;
+    const int r = tt / TWI, j = tt - r * TWI;
+    const int prow = p.patch_w * (p.img_u8 ? 1 : 4);                   // bytes per patch row
+    const uint32_t pplane = (uint32_t)(prow * (2 * THI + 1));           // bytes per colour plane
+    const uint32_t poff = (uint32_t)((2 * r) * prow + (2 * j + p.patch_x0 - 3) * (p.img_u8 ? 1 : 4));
+    const uint32_t patch_u = tc::smem_u32(patch_s) + poff;
+    const uint32_t xrow = tc::smem_u32(x_s) + (uint32_t)tt * 128u, swz = (uint32_t)tt & 7u;
+    const uint32_t lut_u = tc::smem_u32(bp_s + 128);
+    int ps = 0, xs = 0;
+    uint32_t pph = 0, xph = 0;
+    for (int i = 0; i < my_tiles; ++i) {
+      mbar_wait_hw(tc::smem_u32(&patch_full[ps]), pph);
+      mbar_wait_hw(tc::smem_u32(&x_empty[xs]), xph ^ 1u);
+      if (act) {
+        const uint32_t pb = patch_u + (uint32_t)ps * (uint32_t)p.patch_stride;
+        const uint32_t xb = xrow + (uint32_t)xs * (uint32_t)xsb;
+#pragma unroll 1
+        for (int st = 0; st < 4; ++st) {
+          uint32_t pk[16];
+          if (p.img_u8) {
+            uint32_t tap[28];
+#pragma unroll
+            for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+              for (int ky = 0; ky < 3; ++ky) {
+                const uint32_t a = pb + (uint32_t)ci * pplane + (uint32_t)(ky * prow) + (uint32_t)(st * 24);
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                  uint32_t px, h;
+                  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(px) : "r"(a + (uint32_t)kx));
+                  asm volatile("ld.shared.u16 %0, [%1];" : "=r"(h) : "r"(lut_u + px * 2u));
+                  tap[(ci * 3 + ky) * 3 + kx] = h;
+                }
+              }
+            tap[27] = 0u;
+#pragma unroll
+            for (int k = 0; k < 14; ++k) pk[k] = tap[2 * k] | (tap[2 * k + 1] << 16);
+          } else {
+            float f[28];
+#pragma unroll
+            for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+              for (int ky = 0; ky < 3; ++ky) {
+                const uint32_t a = pb + (uint32_t)ci * pplane + (uint32_t)(ky * prow) + (uint32_t)(st * 96);
+                float v0, v1, v2;
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v0) : "r"(a));
+                asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v1), "=f"(v2) : "r"(a + 4u));   // 8-byte aligned
+                f[(ci * 3 + ky) * 3 + 0] = v0; f[(ci * 3 + ky) * 3 + 1] = v1; f[(ci * 3 + ky) * 3 + 2] = v2;
+              }
+            f[27] = 0.f;
+#pragma unroll
+            for (int k = 0; k < 14; ++k) asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pk[k]) : "f"(f[2 * k + 1]), "f"(f[2 * k]));
+          }
+          pk[14] = 0u; pk[15] = 0u;
+          const uint32_t dst = xb + (uint32_t)(st >> 1) * (uint32_t)(p.n_px * 128);
+          const uint32_t cb = (uint32_t)(st & 1) * 4u;
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            tc::sts_u4(dst + (((cb + (uint32_t)c) ^ swz) << 4), make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]));
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+      __syncwarp();
+      if (lane == 0) {
+        tc::mbar_arrive(tc::smem_u32(&x_full[xs]));
+        tc::mbar_arrive(tc::smem_u32(&patch_empty[ps]));
+      }
+      if (++ps == p.patch_stages) { ps = 0; pph ^= 1u; }
+      if (++xs == p.x_stages) { xs = 0; xph ^= 1u; }
     }
   } else if (warp < NG * GW) {
     // ===================== workers: one hidden channel per thread, TMEM -> depthwise -> A2^T =====================

@@ -89,6 +89,16 @@ struct Block {
   bool t_tmW_ready = false;
   const void* t_tmX_ptr = nullptr;
   int t_tmX_batch = -1;
+  // stem fused into the t = 1 block (fused_block_t.cuh, STEM instantiation): block 0 only
+  bool s_ok = false;
+  fbt::FbtParams sprm;
+  size_t s_smem = 0;
+  bf16* s_we = nullptr;          // window matrix [224][64]: rows 96..127 = the stem's folded weights [32 ch][27 taps -> 32]
+  float* s_aux = nullptr;
+  CUtensorMap s_tmImg, s_tmWe, s_tmWp;
+  bool s_tmW_ready = false;
+  const void* s_img_ptr = nullptr;
+  int s_img_batch = -1, s_img_u8 = -1;
   // expand GEMM + fused depthwise -> project kernel (dw_project.cuh): the wide blocks that have no single-kernel plan
   bool dp_ok = false;
   dwp::DwpParams dprm;
@@ -119,6 +129,7 @@ struct spef_ctx {
   int stem_patch = 1;  // stem input patches staged by TMA (SPEF_STEM_PATCH=0: gather the 27 taps from global memory)
   int stem_prod = 2;   // im2col producer groups (128 threads each) of the tcgen05 stem (SPEF_STEM_PROD = 1 | 2)
   int fbt_a2_bufs = 2; // A2 buffers per worker group of the channel-lane kernel where shared memory allows (SPEF_FBT_A2 = 1 | 2)
+  int stem_fuse = 1;   // stem conv fused into the first InvertedResidual block's kernel (SPEF_STEM_FUSE=0: separate stem launch)
   int fbt_max_pstages = 4; // project accumulator stages of the channel-lane kernel, as many as TMEM has columns for (SPEF_FBT_PSTAGES)
   int fb_variant = 1;  // 1: channel-lane fused kernel where it applies, else the staged one; 0: staged kernel only (SPEF_FB_VARIANT)
   int fb_trace_block = -1;  // SPEF_FB_TRACE=<block index>: dump CTA-0 clock64 timestamps of that fused block to stderr
@@ -387,6 +398,7 @@ extern "C" int spef_create(spef_ctx** out, const spef_config* cfg) {
   if (const char* e15 = getenv("SPEF_STEM_PATCH")) ctx->stem_patch = atoi(e15) ? 1 : 0;
   if (const char* e14 = getenv("SPEF_STEM_PROD")) { int v = atoi(e14); ctx->stem_prod = (v == 1 || v == 4) ? v : 2; }
   if (const char* e16 = getenv("SPEF_FBT_A2")) ctx->fbt_a2_bufs = (atoi(e16) == 1) ? 1 : 2;
+  if (const char* e20 = getenv("SPEF_STEM_FUSE")) ctx->stem_fuse = atoi(e20) ? 1 : 0;
   if (const char* e19 = getenv("SPEF_FBT_PSTAGES")) { int v = atoi(e19); ctx->fbt_max_pstages = (v >= 1 && v <= fbt::MAX_PROJ) ? v : fbt::MAX_PROJ; }
   if (const char* e10 = getenv("SPEF_FB_TRACE")) { ctx->fb_trace_block = atoi(e10); if (!ctx->trace_dev) cudaMalloc((void**)&ctx->trace_dev, 256 * 16 * sizeof(long long)); }
   build_layers(ctx);
@@ -451,7 +463,7 @@ extern "C" void spef_destroy(spef_ctx* ctx) {
     cudaFree(l.w_bf16);
     cudaFree(l.bias);
   }
-  for (Block& b : ctx->blocks) { cudaFree(b.aux); cudaFree(b.t_we); cudaFree(b.t_wp); cudaFree(b.t_aux); cudaFree(b.dp_wdw); }
+  for (Block& b : ctx->blocks) { cudaFree(b.aux); cudaFree(b.t_we); cudaFree(b.t_wp); cudaFree(b.t_aux); cudaFree(b.dp_wdw); cudaFree(b.s_we); cudaFree(b.s_aux); }
   for (int i = 0; i < 4; ++i) cudaFree(ctx->act[i]);
   void* ptrs[] = {ctx->pooled, ctx->head_out, ctx->ori_tab64, ctx->pos_tab64, ctx->ori_tab, ctx->pos_tab, ctx->eval_sums, ctx->ws_images, ctx->ws_quat,
                   ctx->ws_pos, ctx->ws_qt, ctx->ws_tt, ctx->ws_soft, ctx->ws_soft2, ctx->ws_hinv, ctx->ws_per_image,
@@ -700,6 +712,49 @@ static int plan_blocks_t(spef_ctx* ctx) {
   return SPEF_OK;
 }
 
+// Stem fused into block 0 (the t = 1 block): the channel-lane plan of that block with the stem conv as its expand conv
+// (reference: mobilenet_v2.py:252-262).  Same tiles, strips, project weights and depthwise constants; the window matrix carries the
+// stem's folded BF16 weights instead of the identity, the aux rows the stem bias (fused_block_t.cuh: h' = max(acc, -be)).
+static int plan_stem_block(spef_ctx* ctx) {
+  if (ctx->blocks.empty() || ctx->layers.empty()) return SPEF_OK;
+  Block& b = ctx->blocks[0];
+  b.s_ok = false; b.s_tmW_ready = false; b.s_img_ptr = nullptr;
+  const Layer& s = ctx->layers[0];
+  if (!(b.t_ok && b.i_exp < 0 && b.first == 1 && b.tprm.stack == 4 && b.t_ng == 2 && b.tprm.TH == 6 && b.tprm.n_chunks == 1)) return SPEF_OK;
+  if (!(s.kind == K_STEM && s.cout == 32 && s.hin == 2 * s.hout && s.win == 2 * s.wout && s.win % 16 == 0 && s.h_wb.size() == 32 * 32)) return SPEF_OK;
+  const Layer& d = ctx->layers[b.i_dw];
+  fbt::FbtParams q = b.tprm;
+  q.stem = 1; q.x_stages = 2; q.a2_bufs = 1; q.kst_stack = 2;
+  q.patch_stride = ((104 * (2 * q.THI + 1) * 3 * 4 + 1023) / 1024) * 1024;   // sized for float images (uint8 patches are smaller)
+  q.patch_stages = 0;
+  for (int ps = 4; ps >= 2 && !q.patch_stages; --ps) {
+    q.patch_stages = ps;
+    if (fbt::smem_bytes(q, 2) > ctx->smem_optin) q.patch_stages = 0;
+  }
+  if (!q.patch_stages) return SPEF_OK;
+  const int we_rows = q.we_bytes >> 7;               // 224
+  std::vector<bf16> we((size_t)we_rows * 64, __float2bfloat16_rn(0.f));
+  std::vector<float> aux((size_t)fbt::AUX_ROWS * fbt::CL, 0.f);
+  const int Ch = 32, LS = 32;
+  for (int ch = 0; ch < Ch; ++ch) {
+    bf16* row = we.data() + ((size_t)(4 - 1) * LS + ch) * 64;
+    for (int k = 0; k < 27; ++k) row[k] = s.h_wb[(size_t)ch * 32 + k];
+    double wsum = 0.0;
+    for (int k = 0; k < 9; ++k) wsum += (double)d.h_wdw[(size_t)k * Ch + ch];
+    for (int st = 0; st < 4; ++st) {
+      const int slot = st * LS + ch;
+      aux[slot] = -s.h_bias[ch];
+      aux[fbt::CL + slot] = (float)((double)d.h_bias[ch] + (double)s.h_bias[ch] * wsum);
+      for (int k = 0; k < 9; ++k) aux[(2 + k) * fbt::CL + slot] = d.h_wdw[(size_t)k * Ch + ch];
+    }
+  }
+  if (!upload(&b.s_we, we) || !upload(&b.s_aux, aux)) return fail(ctx, SPEF_ERR_CUDA, "spef_finalize_weights: upload failed");
+  b.sprm = q;
+  b.s_smem = fbt::smem_bytes(q, 2);
+  b.s_ok = true;
+  return SPEF_OK;
+}
+
 // Depthwise -> project plan (dw_project.cuh): stride-1 blocks with an expand conv whose hidden width is a multiple of 64.
 static int plan_blocks_dp(spef_ctx* ctx) {
   std::vector<Layer>& L = ctx->layers;
@@ -803,6 +858,7 @@ extern "C" int spef_finalize_weights(spef_ctx* ctx) {
           }
         if (!upload(&l.w_bf16, wb)) return fail(ctx, SPEF_ERR_CUDA, "spef_finalize_weights: upload failed");
         l.tmW_ready = false;
+        l.h_wb = wb;
       }
       packed.resize(27 * 32);
       for (int co = 0; co < 32; ++co)
@@ -829,7 +885,7 @@ extern "C" int spef_finalize_weights(spef_ctx* ctx) {
       (void)N;
     }
     bias.resize(tc::bias_floats(l.n_pad), 0.f);
-    if (l.kind == K_PW || l.kind == K_DW) l.h_bias = bias;
+    if (l.kind == K_PW || l.kind == K_DW || l.kind == K_STEM) l.h_bias = bias;
     if (l.kind == K_DW) l.h_wdw = packed;
     if (!upload(&l.w_f32, packed) || !upload(&l.bias, bias)) return fail(ctx, SPEF_ERR_CUDA, "spef_finalize_weights: upload failed");
     if (l.kind == K_DW) {  // TMA tile plan (BF16 path)
@@ -877,6 +933,9 @@ extern "C" int spef_finalize_weights(spef_ctx* ctx) {
     if (rcb) return rcb;
     rcb = plan_blocks_dp(ctx);
     if (rcb) return rcb;
+    rcb = plan_stem_block(ctx);
+    if (rcb) return rcb;
+    CK(cudaFuncSetAttribute(fbt::fused_block_t_kernel<1, 6, 2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, so));
 #define SPEF_FBT_ATTR(S_, TH_) \
     CK(cudaFuncSetAttribute(fbt::fused_block_t_kernel<S_, TH_, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, so));
     SPEF_FBT_ATTR(1, 6) SPEF_FBT_ATTR(1, 5) SPEF_FBT_ATTR(2, 4)
@@ -1194,6 +1253,47 @@ static int launch_fused_block_t(spef_ctx* ctx, Block& b, const void* in, void* o
 
 static int run_layer(spef_ctx* ctx, Layer& l, const void* in, const void* res, void* out, int B, cudaStream_t st, bool cached_maps);
 
+// the stem conv and the first InvertedResidual block as ONE launch: images [B,3,H,W] (f32 or uint8) -> block output [B,H/2,W/2,16]
+static bool stem_block_fused(const spef_ctx* ctx) {
+  return ctx->stem_fuse && !ctx->stem_simt && !ctx->blocks.empty() && ctx->blocks[0].s_ok && block_variant(ctx, 0) == 2;
+}
+static int launch_stem_block(spef_ctx* ctx, const void* images, void* out, int B, cudaStream_t st) {
+  Block& b = ctx->blocks[0];
+  std::vector<Layer>& L = ctx->layers;
+  fbt::FbtParams& q = b.sprm;
+  const Layer& s = L[0];
+  if (((uintptr_t)images % 16) != 0) return fail(ctx, SPEF_ERR_INVALID, "fused stem: the image batch must be 16-byte aligned");
+  if (!b.s_tmW_ready) {
+    if (!tc::make_tmap_2d(ctx->encode, &b.s_tmWe, b.s_we, false, (long long)(q.we_bytes >> 7), 64, 64, q.we_bytes >> 7) ||
+        !tc::make_tmap_2d(ctx->encode, &b.s_tmWp, b.t_wp, false, q.Cout, (long long)q.n_chunks * fbt::CL, (long long)q.n_chunks * fbt::CL, q.cpad))
+      return fail(ctx, SPEF_ERR_CUDA, "cuTensorMapEncodeTiled(W') failed for the fused stem");
+    b.s_tmW_ready = true;
+  }
+  q.img_u8 = ctx->image_u8;
+  q.patch_w = ctx->image_u8 ? 128 : 104;       // >= patch_x0 + 2 * 48 + 1 columns; rows of a multiple of 16 bytes
+  q.patch_x0 = ctx->image_u8 ? 16 : 4;         // 16 bytes: the innermost TMA coordinate must be 16-byte aligned
+  if (b.s_img_ptr != images || b.s_img_batch != B || b.s_img_u8 != ctx->image_u8) {
+    const size_t esz = ctx->image_u8 ? 1 : 4;
+    const cuuint64_t gdim[3] = {(cuuint64_t)s.win, (cuuint64_t)s.hin, (cuuint64_t)3 * B};   // planes of all images: NCHW is [B*3][H][W]
+    const cuuint64_t gstride[2] = {(cuuint64_t)s.win * esz, (cuuint64_t)s.win * s.hin * esz};
+    const cuuint32_t box[3] = {(cuuint32_t)q.patch_w, (cuuint32_t)(2 * q.THI + 1), 3};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = ctx->encode(&b.s_tmImg, ctx->image_u8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(images),
+                             gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, SPEF_ERR_CUDA, "cuTensorMapEncodeTiled(image) failed for the fused stem");
+    b.s_img_ptr = images; b.s_img_batch = B; b.s_img_u8 = ctx->image_u8;
+  }
+  q.x = nullptr; q.y = (bf16*)out; q.B = B; q.aux = b.s_aux; q.bp = L[b.i_proj].bias; q.trace = nullptr;
+  const long long tiles = (long long)B * q.tiles_y * q.tiles_x;
+  if (tiles >= (1 << 22)) return fail(ctx, SPEF_ERR_UNSUPPORTED, "fused stem: %lld tiles exceed the 2^22 limit of the tile index arithmetic", tiles);
+  const int grid = (int)(tiles < ctx->num_sms ? tiles : ctx->num_sms);
+  const int nthr = 32 * (fbt::CTRL_WARPS + 2 * fbt::GWT);
+  fbt::fused_block_t_kernel<1, 6, 2, true, true><<<grid, nthr, b.s_smem, st>>>(b.s_tmImg, b.s_tmWe, b.s_tmWp, q);
+  CK_LAUNCH("fused_block_t_kernel<stem>");
+  return SPEF_OK;
+}
+
 // hidden: the expand conv's output [B,H,W,C]; res: the block input (skip connection) or nullptr
 static int launch_dw_project(spef_ctx* ctx, Block& b, const void* hidden, const void* res, void* out, int B, cudaStream_t st) {
   std::vector<Layer>& L = ctx->layers;
@@ -1316,6 +1416,16 @@ static int forward_internal(spef_ctx* ctx, const float* images, int B, cudaStrea
   for (int i = 0; i < nl; ++i) {
     Layer& l = ctx->layers[i];
     while (next_block < ctx->blocks.size() && ctx->blocks[next_block].first < i) ++next_block;
+    if (i == 0 && l.kind == K_STEM && stem_block_fused(ctx)) {
+      // stem + first block as one launch (its time is reported in the stem's slot)
+      Block& b = ctx->blocks[0];
+      int rc = launch_stem_block(ctx, images, buf_ptr(ctx, ctx->layers[b.i_proj].dst), B, st);
+      if (rc) return rc;
+      for (int j = 0; j <= b.n_layers; ++j)
+        if (ev) CK(cudaEventRecord(ev[j + 1], st));
+      i += b.n_layers;
+      continue;
+    }
     // the depthwise -> project kernel runs one CTA per (image, row tile): a few-image step (temporal streams) would leave most SMs
     // idle through its K-chunk loop, so small batches keep the per-layer kernels (batch 1: 0.37 ms per frame with it, 0.30 without)
     int variant = 0;
@@ -1447,6 +1557,24 @@ extern "C" int spef_set_fusion(spef_ctx* ctx, int32_t on) {
   drop_graphs(ctx);
   ctx->fuse = on ? 1 : 0;
   return SPEF_OK;
+}
+
+extern "C" int spef_set_stem_fusion(spef_ctx* ctx, int32_t on) {
+  if (!ctx) return SPEF_ERR_INVALID;
+  drop_graphs(ctx);
+  ctx->stem_fuse = on ? 1 : 0;
+  return SPEF_OK;
+}
+
+extern "C" int spef_stem_fusion_active(const spef_ctx* ctx) { return (ctx && ctx->finalized && stem_block_fused(ctx)) ? 1 : 0; }
+
+extern "C" int spef_stem_block_forward(spef_ctx* ctx, const void* images_dev, void* out_dev, int32_t B, void* stream) {
+  int rc = check_ready(ctx, B, "spef_stem_block_forward");
+  if (rc) return rc;
+  if (!images_dev || !out_dev) return fail(ctx, SPEF_ERR_INVALID, "spef_stem_block_forward: NULL argument");
+  if (!stem_block_fused(ctx)) return fail(ctx, SPEF_ERR_UNSUPPORTED, "spef_stem_block_forward: the stem is not fused into the first block in this configuration");
+  CK(cudaSetDevice(ctx->cfg.device));
+  return launch_stem_block(ctx, images_dev, out_dev, B, (cudaStream_t)stream);
 }
 
 extern "C" int spef_block_forward(spef_ctx* ctx, int32_t i, const void* in, void* out, int32_t B, void* stream) {

@@ -240,7 +240,27 @@ class Engine:
     def fp32_hidden_blocks(self):
         """Feature indices (1..17, the reference's `features.features.{i}`) of the blocks that run as a channel-lane fused kernel
         in the current configuration: their hidden tensor stays FP32 on the SM (a rounding point the oracle needs to know)."""
-        return {i + 1 for i in range(self.num_blocks()) if self.block_info(i)["fused"] == 2}
+        blocks = {i + 1 for i in range(self.num_blocks()) if self.block_info(i)["fused"] == 2}
+        if self.stem_fusion_active():
+            blocks.add(0)   # 0 = the stem: its output stays FP32 inside the stem + first-block kernel
+        return blocks
+
+    def stem_fusion_active(self) -> bool:
+        """True when the stem conv runs inside the first block's kernel (spef_stem_fusion_active)."""
+        return bool(self.lib.spef_stem_fusion_active(self._h))
+
+    def set_stem_fusion(self, on: bool):
+        """True (default): stem + first InvertedResidual block as one kernel; False: separate stem launch."""
+        self._ck(self.lib.spef_set_stem_fusion(self._h, 1 if on else 0))
+
+    def stem_block_forward(self, images: torch.Tensor) -> torch.Tensor:
+        """Teacher-forced stem + first block: images [B,3,H,W] (float32, or uint8 after set_image_dtype) -> NHWC bf16 block output."""
+        bi = self.block_info(0)
+        last = self.layer_info(bi["first_layer"] + bi["n_layers"] - 1)
+        images = images.to(self.device).contiguous()
+        out = self._empty(images.shape[0], last["hout"], last["wout"], last["cout"], dtype=torch.bfloat16)
+        self._ck(self.lib.spef_stem_block_forward(self._h, ptr(images), ptr(out), images.shape[0], _stream(self.device)))
+        return out
 
     def set_fusion(self, on: bool):
         """True (default): InvertedResidual blocks run as one fused kernel each; False: per-layer kernels."""

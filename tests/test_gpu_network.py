@@ -202,6 +202,81 @@ def test_fused_blocks_teacher_forced(sd, images):
     assert n[1] + n[2] + n[3] >= 16, f"only {n} of the 17 blocks run fused kernels"   # all but the stride-2 block 14 (576 -> 160)
 
 
+def _check_stem_block(sd, images, batch=3, pick=None, u8=False):
+    """Stem conv + first InvertedResidual block as ONE kernel (mobilenet_v2.py:252-262), teacher-forced on the image:
+      * against the oracle with the kernel's rounding points -- image taps and stem weights BF16, the stem output (the kernel's hidden tensor)
+        FP32, depthwise output BF16, block output BF16 -- at the gates of the fused blocks (32 floored BF16 ulp, < 1 % of the elements);
+      * against the separate stem launch followed by the block's own fused kernel (which rounds the stem output to BF16): reported, bounded.
+    uint8 images: the same pixels as bytes must give bit-identical results to their float32 values / 255."""
+    eng = _engine(sd, "bf16", 0, max_batch=max(8, batch))
+    assert eng.stem_fusion_active(), "the stem is not fused into the first block"
+    assert 0 in eng.fp32_hidden_blocks()
+    pick = list(range(batch)) if pick is None else pick
+    x = images[:len(pick)]
+    if u8:
+        xb = (x * 255.0).round().clamp(0, 255).to(torch.uint8)
+        x = xb.float() / 255.0
+    layers = O.folded_layers(sd)
+    info = eng.block_info(0)
+    first, last = info["first_layer"], info["first_layer"] + info["n_layers"] - 1
+    assert first == 1
+    stem_fp32 = O.apply_layer(layers[0], x, None, True, round_out=False)
+    want = _oracle_block(layers, first, last, stem_fp32, hidden_fp32=True).permute(0, 2, 3, 1).contiguous()
+    full = _spread(x, batch, pick)
+    if u8:
+        eng.set_image_dtype(torch.uint8)
+        got_full = eng.stem_block_forward(_spread(xb, batch, pick))
+        eng.set_image_dtype(torch.float32)
+        got_f32 = eng.stem_block_forward(full)
+        assert torch.equal(got_full, got_f32), "uint8 and float32 images differ through the fused stem"
+    else:
+        got_full = eng.stem_block_forward(full)
+    got = got_full[pick].float().cpu()
+    assert got.shape == want.shape
+    eng.set_stem_fusion(False)
+    assert not eng.stem_fusion_active() and 0 not in eng.fp32_hidden_blocks()
+    stem_out = eng.layer_forward(0, full.to(eng.device), None)
+    chain = eng.block_forward(0, stem_out)[pick].float().cpu()
+    eng.set_stem_fusion(True)
+    scale = float(want.abs().max())
+    err = (got - chain).abs()
+    print(f"stem + block 0: one kernel vs stem launch + block kernel (stem output FP32 vs BF16): max |diff| / scale {float(err.max()) / scale:.2e}, "
+          f"{float((err > 0).float().mean()):.3f} of the elements differ")
+    assert float(err.max()) <= 1e-2 * scale
+    err = (got - want).abs()
+    ulp = torch.maximum(want.abs(), torch.tensor(scale * 2 ** -8)) * 2 ** -7
+    worst, frac_off = float((err / ulp).max()), float((err > 0).float().mean())
+    print(f"stem + block 0: vs oracle max {worst:.2f} ulp, {frac_off:.4f} of the elements differ")
+    assert worst <= 32.0, f"stem + block 0 vs oracle: {worst:.2f} BF16 ulp"
+    assert frac_off < 0.01, f"stem + block 0 vs oracle: {frac_off:.4f} of the elements differ"
+    if batch != len(pick):
+        ref0 = got_full[pick[0]]
+        assert all(torch.equal(got_full[j], ref0) for j in range(batch) if j not in pick), "stem + block 0: batch slots differ"
+
+
+@pytest.mark.parametrize("u8", [False, True])
+def test_stem_block_teacher_forced(sd, images, u8):
+    _check_stem_block(sd, images, u8=u8)
+
+
+def test_stem_block_teacher_forced_full_batch(sd, images):
+    """Inside a B = 256 launch: slots 0, 127, 255 against the oracle, all other slots bit-identical copies."""
+    _check_stem_block(sd, images, batch=256, pick=[0, 127, 255])
+
+
+def test_stem_fusion_forward_equals_separate_stem(sd):
+    """End to end: logits with the stem inside the first block's kernel vs the separate stem launch (ragged batch)."""
+    eng = _engine(sd, "bf16", 0)
+    x = synthetic.synthetic_images(5, seed=11)
+    o_f, p_f = [t.cpu().numpy() for t in eng.forward(x)]
+    eng.set_stem_fusion(False)
+    o_l, p_l = [t.cpu().numpy() for t in eng.forward(x)]
+    eng.set_stem_fusion(True)
+    print(f"fused stem vs separate stem: logits {rel(o_f, o_l):.2e}, pos {rel(p_f, p_l):.2e}")
+    assert rel(o_f, o_l) < 3e-2 and rel(p_f, p_l) < 3e-2
+    assert (o_f.argmax(1) == o_l.argmax(1)).mean() >= 0.8
+
+
 def test_dw_project_kernel_on_every_shape_it_takes(sd, images, monkeypatch):
     """SPEF_DWP_FORCE=1 runs the expand GEMM + depthwise -> project kernel on every stride-1 block it has a plan for (hidden widths
     192 / 384 / 576 / 960, maps 30x48 ... 8x12, with and without skip connection, one- and two-half accumulators): bit-identical
