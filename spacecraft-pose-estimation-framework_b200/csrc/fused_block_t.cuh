@@ -108,7 +108,7 @@ inline size_t smem_bytes(const FbtParams& p, int ng) {
 // Register budget per role (setmaxnreg only moves registers inside the CTA's own launch allocation; every count is a multiple
 // of 8 and each role is a whole warpgroup of four warps).  Two worker groups + two epilogue teams + control = 20 warps x 96 at launch:
 //   8 * 160 + 8 * 56 + 4 * 40 = 1888 <= 1920.   (A first version that counted on the SM's unallocated registers deadlocked in setmaxnreg.inc.)
-template <int NG> struct RegPlan { static constexpr int WORKER = 160, EPI = 56, CTRL = 40, PROD = 64; };   // STEM: 8 * 160 + 4 * 56 + 4 * 64 + 4 * 40 = 1920
+template <int NG> struct RegPlan { static constexpr int WORKER = 160, EPI = 56, CTRL = 40, EPI_STEM = 64, PROD = 56; };   // STEM: 8 * 160 + 4 * 64 + 4 * 56 + 4 * 40 = 1920
 template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 
@@ -502,9 +502,74 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     // tiles only ONE of the four warps had pixels at all.  Now: eight warps in two teams; 24-pixel tiles rotate through the lane
     // quarters (ROT) so that every warp owns every eighth tile; larger tiles split their strips (stacked) or alternate (one
     // strip) between the teams; warps whose quarter holds no pixels leave at once; tile coordinates are carried, not divided.
-    reg_dec<RegPlan<NG>::EPI>();
     const int q = warp & 3;
     const int team = (warp - FIRST_EPI_WARP) >> 2;
+    if constexpr (STEM) {
+      // One team for four strips: ncu's wait sites showed it pacing the first version of the fused stem (project issuer 78 % of its time
+      // on proj_empty, the workers 52 % of theirs on a2_empty behind it) with the generic loop below at ~520 instructions per tile and
+      // warp.  Specialised: Cout = 16 (one tcgen05.ld.x16 per strip), no skip input, exact tiling in x; the four strip loads are
+      // software-pipelined through two landing buffers and the accumulator stage is handed back as soon as the last one is in registers.
+      reg_dec<RegPlan<NG>::EPI_STEM>();
+      if (q < N_EPI) {
+        const int o = q * 32 + lane;
+        const int oy_l = o / TW, ox_l = o - oy_l * TW;
+        const bool lane_ok = o < TH * TW;
+        int tb, ty, tx;
+        {
+          const int t0 = (int)blockIdx.x;
+          tb = t0 / tiles_per_img;
+          const int r = t0 - tb * tiles_per_img;
+          ty = r / p.tiles_x; tx = r - ty * p.tiles_x;
+        }
+        const int gstep = (int)gridDim.x;
+        const int db = gstep / tiles_per_img, dr = gstep - db * tiles_per_img, dty = dr / p.tiles_x, dtx = dr - dty * p.tiles_x;
+        const int row_px = p.Wo, img_px = p.Ho * p.Wo;
+        const uint32_t bias_u = tc::smem_u32(bp_s);
+        int ps = 0;
+        auto emit = [&](const uint32_t (&v)[16], bf16* yp, bool valid) {
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const float4 b0 = tc::lds_f4(bias_u + (uint32_t)j * 32u), b1 = tc::lds_f4(bias_u + (uint32_t)j * 32u + 16u);
+              float f[8] = {__uint_as_float(v[j * 8 + 0]) + b0.x, __uint_as_float(v[j * 8 + 1]) + b0.y,
+                            __uint_as_float(v[j * 8 + 2]) + b0.z, __uint_as_float(v[j * 8 + 3]) + b0.w,
+                            __uint_as_float(v[j * 8 + 4]) + b1.x, __uint_as_float(v[j * 8 + 5]) + b1.y,
+                            __uint_as_float(v[j * 8 + 6]) + b1.z, __uint_as_float(v[j * 8 + 7]) + b1.w};
+              Vec8<bf16>::store(yp + j * 8, f);
+            }
+          }
+        };
+        for (int i = 0; i < my_tiles; ++i) {
+          const int gy = ty * TH + oy_l;
+          const bool valid = lane_ok && gy < p.Ho;
+          bf16* yp = p.y + (long long)(tb * img_px + gy * row_px + tx * (TW * 4) + ox_l) * 16;   // strip st: + st * TW pixels
+          mbar_wait_hw(tc::smem_u32(&proj_full[i & (N_PFULL - 1)]), (uint32_t)((i >> 3) & 1));
+          tc::tcgen05_fence_after();
+          const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(p.proj_col0 + ps * p.proj_stride);
+          uint32_t va[16], vb[16];
+          tmem_ld_32x32b_x16(t_row, va);
+          tmem_ld_wait16(va);
+          tmem_ld_32x32b_x16(t_row + 16u, vb);
+          emit(va, yp, valid);
+          tmem_ld_wait16(vb);
+          tmem_ld_32x32b_x16(t_row + 32u, va);
+          emit(vb, yp + TW * 16, valid);
+          tmem_ld_wait16(va);
+          tmem_ld_32x32b_x16(t_row + 48u, vb);
+          emit(va, yp + 2 * TW * 16, valid);
+          tmem_ld_wait16(vb);
+          tc::tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(tc::smem_u32(&proj_empty[ps]));
+          emit(vb, yp + 3 * TW * 16, valid);
+          if (++ps == p.proj_stages) ps = 0;
+          tx += dtx; ty += dty; tb += db;
+          if (tx >= p.tiles_x) { tx -= p.tiles_x; ++ty; }
+          if (ty >= p.tiles_y) { ty -= p.tiles_y; ++tb; }
+        }
+      }
+    } else {
+    reg_dec<RegPlan<NG>::EPI>();
     if (ROT || q < N_EPI) {
     const int o = ROT ? lane : q * 32 + lane;     // output pixel of the tile held by this lane's accumulator row
     const int oy_l = o / TW, ox_l = o - oy_l * TW;
@@ -598,6 +663,7 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       if (ty >= p.tiles_y) { ty -= p.tiles_y; ++tb; }
     }
     }
+    }
   } else if (STEM && warp >= FIRST_EPI_WARP + 4 && warp < FIRST_EPI_WARP + 8) {
     // ===================== STEM: im2col producers (four warps): image patch -> K-major expand operand of the four strips =====================
     // Thread t < THI * TWI owns hidden pixel (r, j) = (t / TWI, t % TWI) of EVERY strip's haloed box: operand row t of the strip, 27 taps
@@ -647,6 +713,7 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
 #pragma unroll
             for (int k = 0; k < 14; ++k) pk[k] = tap[2 * k] | (tap[2 * k + 1] << 16);
           } else {
+            // taps in k order, converted as they arrive: k = 0..15 (ci 0, and ci 1 up to (ky 2, kx 0)) fill chunks 0 and 1
             float f[28];
 #pragma unroll
             for (int ci = 0; ci < 3; ++ci)
