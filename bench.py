@@ -343,6 +343,15 @@ def layer_table(eng, batch, ms):
         bi = eng.block_info(b)
         if bi["fused"]:
             fused_first[bi["first_layer"]] = bi
+    if eng.stem_fusion_active():
+        # stem conv + first block as ONE launch (timed in the stem's slot): reads the image once, writes the block output once
+        bi = eng.block_info(0)
+        grp = rows[0:1 + bi["n_layers"]]
+        skip.update(g["layer"] for g in grp)
+        merged.append({"layer": 0, "kernel": "fused_block_kernel", "cin": 3, "cout": grp[-1]["cout"], "hw": grp[-1]["hw"], "stride": 2,
+                       "bytes": grp[0]["ein"] * 4 + grp[-1]["eout"] * esz, "flops": sum(g["flops"] for g in grp),
+                       "ms": sum(g["ms"] for g in grp), "hidden": grp[0]["cout"], "tile": f"{bi['tile_h']}x{4 * bi['tile_w']}",
+                       "unfused_bytes": sum(g["bytes"] for g in grp), "stem_fused": True})
     for r in rows:
         if r["layer"] in skip:
             continue

@@ -23,6 +23,7 @@
 //     item is issued one and a half items ahead of its consumer.
 #pragma once
 #include <cuda.h>
+#include <type_traits>
 #include "common.cuh"
 #include "gemm_tcgen05.cuh"
 #include "gemm_tcgen05_v2.cuh"
@@ -677,75 +678,79 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     const bool act = t < THI * TWI;
     const int tt = act ? t : 0;
     const int r = tt / TWI, j = tt - r * TWI;
-    const int prow = p.patch_w * (p.img_u8 ? 1 : 4);                   // bytes per patch row
-    const uint32_t pplane = (uint32_t)(prow * (2 * THI + 1));           // bytes per colour plane
-    const uint32_t poff = (uint32_t)((2 * r) * prow + (2 * j + p.patch_x0 - 3) * (p.img_u8 ? 1 : 4));
-    const uint32_t patch_u = tc::smem_u32(patch_s) + poff;
-    const uint32_t xrow = tc::smem_u32(x_s) + (uint32_t)tt * 128u, swz = (uint32_t)tt & 7u;
+    const uint32_t xrow = tc::smem_u32(x_s) + (uint32_t)tt * 128u, swz = ((uint32_t)tt & 7u) << 4;
     const uint32_t lut_u = tc::smem_u32(bp_s + 128);
-    int ps = 0, xs = 0;
-    uint32_t pph = 0, xph = 0;
-    for (int i = 0; i < my_tiles; ++i) {
-      mbar_wait_hw(tc::smem_u32(&patch_full[ps]), pph);
-      mbar_wait_hw(tc::smem_u32(&x_empty[xs]), xph ^ 1u);
-      if (act) {
-        const uint32_t pb = patch_u + (uint32_t)ps * (uint32_t)p.patch_stride;
-        const uint32_t xb = xrow + (uint32_t)xs * (uint32_t)xsb;
-#pragma unroll 1
-        for (int st = 0; st < 4; ++st) {
-          uint32_t pk[16];
-          if (p.img_u8) {
-            uint32_t tap[28];
+    const uint32_t kc1 = (uint32_t)(p.n_px * 128);                      // second K chunk of an x stage (strips 2, 3)
+    // The patch geometry is a compile-time constant per image dtype (the host encodes the TMA box from the same numbers), so every
+    // tap load is [thread base + immediate]: the first version (run-time row / plane pitch, strip loop not unrolled) ran 318
+    // instructions per tile and warp and paced the kernel (ncu: the workers 35 % of their time on acc_full behind it).
+    auto run = [&](auto u8tag) {
+      constexpr bool U8 = decltype(u8tag)::value;
+      constexpr int ESZ = U8 ? 1 : 4, PW = U8 ? 128 : 104, PX0 = U8 ? 16 : 4;
+      constexpr int PROW = PW * ESZ, PPLANE = PROW * (2 * THI + 1), SSTEP = 2 * TW * ESZ;
+      const uint32_t patch_u = tc::smem_u32(patch_s) + (uint32_t)((2 * r) * PROW + (2 * j + PX0 - 3) * ESZ);
+      int ps = 0, xs = 0;
+      uint32_t pph = 0, xph = 0;
+      for (int i = 0; i < my_tiles; ++i) {
+        mbar_wait_hw(tc::smem_u32(&patch_full[ps]), pph);
+        mbar_wait_hw(tc::smem_u32(&x_empty[xs]), xph ^ 1u);
+        if (act) {
+          const uint32_t pb = patch_u + (uint32_t)ps * (uint32_t)p.patch_stride;
+          const uint32_t xb = xrow + (uint32_t)xs * (uint32_t)xsb;
 #pragma unroll
-            for (int ci = 0; ci < 3; ++ci)
+          for (int st = 0; st < 4; ++st) {
+            uint32_t pk[14];
+            if constexpr (U8) {
+              uint32_t tap[28];
 #pragma unroll
-              for (int ky = 0; ky < 3; ++ky) {
-                const uint32_t a = pb + (uint32_t)ci * pplane + (uint32_t)(ky * prow) + (uint32_t)(st * 24);
+              for (int ci = 0; ci < 3; ++ci)
 #pragma unroll
-                for (int kx = 0; kx < 3; ++kx) {
-                  uint32_t px, h;
-                  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(px) : "r"(a + (uint32_t)kx));
-                  asm volatile("ld.shared.u16 %0, [%1];" : "=r"(h) : "r"(lut_u + px * 2u));
-                  tap[(ci * 3 + ky) * 3 + kx] = h;
+                for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                  for (int kx = 0; kx < 3; ++kx) {
+                    uint32_t px, h;
+                    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(px) : "r"(pb + (uint32_t)(ci * PPLANE + ky * PROW + st * SSTEP + kx)));
+                    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(h) : "r"(lut_u + px * 2u));
+                    tap[(ci * 3 + ky) * 3 + kx] = h;
+                  }
+              tap[27] = 0u;
+#pragma unroll
+              for (int k = 0; k < 14; ++k) pk[k] = tap[2 * k] | (tap[2 * k + 1] << 16);
+            } else {
+              float f[28];
+#pragma unroll
+              for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky) {
+                  float v0, v1, v2;
+                  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v0) : "r"(pb + (uint32_t)(ci * PPLANE + ky * PROW + st * SSTEP)));
+                  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v1), "=f"(v2) : "r"(pb + (uint32_t)(ci * PPLANE + ky * PROW + st * SSTEP + 4)));   // 8-byte aligned
+                  f[(ci * 3 + ky) * 3 + 0] = v0; f[(ci * 3 + ky) * 3 + 1] = v1; f[(ci * 3 + ky) * 3 + 2] = v2;
                 }
-              }
-            tap[27] = 0u;
+              f[27] = 0.f;
 #pragma unroll
-            for (int k = 0; k < 14; ++k) pk[k] = tap[2 * k] | (tap[2 * k + 1] << 16);
-          } else {
-            // taps in k order, converted as they arrive: k = 0..15 (ci 0, and ci 1 up to (ky 2, kx 0)) fill chunks 0 and 1
-            float f[28];
-#pragma unroll
-            for (int ci = 0; ci < 3; ++ci)
-#pragma unroll
-              for (int ky = 0; ky < 3; ++ky) {
-                const uint32_t a = pb + (uint32_t)ci * pplane + (uint32_t)(ky * prow) + (uint32_t)(st * 96);
-                float v0, v1, v2;
-                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v0) : "r"(a));
-                asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v1), "=f"(v2) : "r"(a + 4u));   // 8-byte aligned
-                f[(ci * 3 + ky) * 3 + 0] = v0; f[(ci * 3 + ky) * 3 + 1] = v1; f[(ci * 3 + ky) * 3 + 2] = v2;
-              }
-            f[27] = 0.f;
-#pragma unroll
-            for (int k = 0; k < 14; ++k) asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pk[k]) : "f"(f[2 * k + 1]), "f"(f[2 * k]));
+              for (int k = 0; k < 14; ++k) asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pk[k]) : "f"(f[2 * k + 1]), "f"(f[2 * k]));
+            }
+            // logical chunk (st & 1) * 4 + c of row tt in K chunk (st >> 1): physical chunk = logical ^ (row & 7)
+            const uint32_t dst = xb + (uint32_t)(st >> 1) * kc1;
+            const uint32_t half = (uint32_t)(st & 1) << 6;
+            tc::sts_u4(dst + ((0u | half) ^ swz), make_uint4(pk[0], pk[1], pk[2], pk[3]));
+            tc::sts_u4(dst + ((16u | half) ^ swz), make_uint4(pk[4], pk[5], pk[6], pk[7]));
+            tc::sts_u4(dst + ((32u | half) ^ swz), make_uint4(pk[8], pk[9], pk[10], pk[11]));
+            tc::sts_u4(dst + ((48u | half) ^ swz), make_uint4(pk[12], pk[13], 0u, 0u));
           }
-          pk[14] = 0u; pk[15] = 0u;
-          const uint32_t dst = xb + (uint32_t)(st >> 1) * (uint32_t)(p.n_px * 128);
-          const uint32_t cb = (uint32_t)(st & 1) * 4u;
-#pragma unroll
-          for (int c = 0; c < 4; ++c)
-            tc::sts_u4(dst + (((cb + (uint32_t)c) ^ swz) << 4), make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]));
         }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+        __syncwarp();
+        if (lane == 0) {
+          tc::mbar_arrive(tc::smem_u32(&x_full[xs]));
+          tc::mbar_arrive(tc::smem_u32(&patch_empty[ps]));
+        }
+        if (++ps == p.patch_stages) { ps = 0; pph ^= 1u; }
+        if (++xs == p.x_stages) { xs = 0; xph ^= 1u; }
       }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
-      __syncwarp();
-      if (lane == 0) {
-        tc::mbar_arrive(tc::smem_u32(&x_full[xs]));
-        tc::mbar_arrive(tc::smem_u32(&patch_empty[ps]));
-      }
-      if (++ps == p.patch_stages) { ps = 0; pph ^= 1u; }
-      if (++xs == p.x_stages) { xs = 0; xph ^= 1u; }
-    }
+    };
+    if (p.img_u8) run(std::true_type{}); else run(std::false_type{});
   } else if (warp < NG * GW) {
     // ===================== workers: one hidden channel per thread, TMEM -> depthwise -> A2^T =====================
     // The hidden tensor stays FP32 between the expand GEMM and the depthwise taps (it never leaves the SM, so rounding it to BF16
