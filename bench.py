@@ -558,7 +558,18 @@ def run_b200(args):
             el = float(t.item())
         return el
 
+    pack_on, pack_threads = eng.host_pack_info()
     e2e_s = e2e_loop([host_images, host_images2])
+    # the same loop with the plain float copy (spef_set_host_pack(0)): what the packed upload is measured against
+    e2e_plain = None
+    if pack_on:
+        for l in lanes:
+            l.set_host_pack(False)
+        plain_s = e2e_loop([host_images, host_images2])
+        for l in lanes:
+            l.set_host_pack(True)
+        e2e_plain = {"value": world * B * args.steps / plain_s, "unit": UNIT, "h2d_bytes_per_step": int(host_images.numel() * 4 + B * 28),
+                     "d2h_bytes_per_step": int(B * 8), "note": "spef_set_host_pack(0): the float images cross the bus as they are"}
     # same loop with uint8 pixels (the input side of the path: ToTensor's /255 moves into the stem; 4x fewer H2D bytes)
     e2e_u8 = None
     if args.precision == "bf16" and args.pw_impl == 0:
@@ -574,14 +585,21 @@ def run_b200(args):
     # the H2D roof this end-to-end number runs against: a plain cudaMemcpyAsync of the same pinned 283 MB buffer, rank 0 alone and
     # all ranks at once (on a shared host the concurrent figure is what caps N-GPU end-to-end scaling, not the kernels)
     roof_alone, roof_conc = h2d_roof(host_images, dev, dist)
-    h2d_bytes = int(host_images.numel() * 4 + B * 28)
+    pack_f = eng.host_pack_stats()["packed_fraction"] if pack_on else 0.0     # of the last submit (the split follows the measured rates)
+    h2d_bytes = int(host_images.numel() * (4 - 2 * pack_f) + B * 28)
     e2e_val = world * B * args.steps / e2e_s
     e2e = {"value": e2e_val, "unit": UNIT,
            "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": int(B * 8),
            "h2d_roof_GBps": roof_conc, "h2d_roof_alone_GBps": roof_alone,
            "achieved_h2d_GBps_per_gpu": e2e_val / world / B * h2d_bytes / 1e9,
            "frac_of_h2d_roof": (e2e_val / world / B * h2d_bytes / 1e9) / roof_conc if roof_conc else None,
-           "bound": "host-to-device copy (PCIe): float images are 1.11 MB each; the device-timed `value` is what the kernels sustain",
+           "host_pack": ({"threads": pack_threads, "measured": eng.host_pack_stats(), "host_bytes_read_per_step": int(host_images.numel() * 4),
+                          "what": "the caller's float images (1.11 MB each) are rounded to BF16 by the library's host threads -- the stem's own first "
+                                  "step, bit-identical results -- and cross PCIe at half the bytes, chunk by chunk behind the conversion; the rest of the batch "
+                                  "crosses as float meanwhile; the split balances the measured conversion and copy rates"}
+                         if pack_on else None),
+           "bound": ("host side: the conversion threads and the PCIe copy share the host's memory bandwidth" if pack_on else
+                     "host-to-device copy (PCIe): float images are 1.11 MB each") + "; the device-timed `value` is what the kernels sustain",
            "numa": numa,
            "api": "spef_eval_submit_host / spef_eval_wait (pinned host images + targets in, per-image errors out every step; H2D of step i+1 overlaps the kernels of step i)"}
 
@@ -703,7 +721,7 @@ def run_b200(args):
                    "lanes_note": "the K timed steps (each one full pass over one batch, each replayed as one CUDA graph by the library) are issued "
                                  "round-robin over this many device contexts / CUDA streams (Engine.lanes, as evaluation() issues the batches of a "
                                  "phase), so consecutive steps overlap on the GPU; ms_per_step = timed region / K; --lanes 1 is one stream"},
-        "e2e": e2e, "e2e_uint8_input": e2e_u8, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+        "e2e": e2e, "e2e_plain_copy": e2e_plain, "e2e_uint8_input": e2e_u8, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
         "step_roofline": {"algorithmic_bytes_per_step": shipped_bytes, "flops_per_step": tot_flops,
                           "achieved_GBps": shipped_bytes / (step_ms * 1e-3) / 1e9, "hbm_frac": shipped_bytes / (step_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
                           "achieved_TFLOPs": tot_flops / (step_ms * 1e-3) / 1e12,

@@ -211,6 +211,19 @@ int spef_eval_batch_host(spef_ctx* ctx, const float* images_host, const float* q
 int spef_eval_submit_host(spef_ctx* ctx, const float* images_host, const float* quat_true_host,
                           const float* pos_true_host, int32_t batch, float* per_image_out_host, void* stream);
 int spef_eval_wait(spef_ctx* ctx, void* stream);
+/* Packed upload for spef_eval_submit_host (float images, BF16 engine; replaces the `.to(device)` of the float batch in
+ * SPETorch.predict, src/spe/spe_torch.py:57-61): the library's host threads round the pixels to BF16 -- the stem's own first step,
+ * same round-to-nearest-even -- chunk by chunk into pinned staging while the DMA engine moves the previous chunk, and a widening
+ * kernel restores the float tensor on the device: half the bytes on the bus, bit-identical results.  Default on for the BF16 engine
+ * (SPEF_HOST_PACK=0 or spef_set_host_pack(ctx, 0): plain copy; SPEF_PACK_THREADS: host threads, default min(16, cores / LOCAL_WORLD_SIZE)).
+ * A submit splits its batch: the tail crosses as float (the DMA engine starts on it at once), the head is packed; the split
+ * balances the host threads against the bus from rates the context measures while it runs (float bytes / s converted, bytes / s
+ * of the plain slice's copy).  spef_host_pack_info: whether the next submit packs, with how many host threads, and
+ * stats[3] = {packed fraction of the last submit, measured conversion rate, measured copy rate} (bytes / s). */
+int spef_set_host_pack(spef_ctx* ctx, int32_t on);
+/* the host half of the packed upload on its own (no GPU involved): dst[i] = bf16 bits of src[i], round to nearest even */
+int spef_pack_bf16_host(const float* src_host, uint16_t* dst_host, int64_t n);
+int spef_host_pack_info(const spef_ctx* ctx, int32_t* active, int32_t* threads, double* stats /*[3] or NULL*/);
 int spef_eval_batch(spef_ctx* ctx, const float* images_dev, const float* quat_true_dev,
                     const float* pos_true_dev, int32_t batch, float* per_image_out_dev, void* stream);
 int spef_eval_read(spef_ctx* ctx, double* sums_host /*[8]*/, void* stream);

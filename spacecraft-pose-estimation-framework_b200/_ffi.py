@@ -48,6 +48,9 @@ SIGNATURES = {
     "spef_set_ori_histogram": (C.c_int, [_vp, _vp, _i32]),
     "spef_set_pos_histogram": (C.c_int, [_vp, _vp, _i32]),
     "spef_set_image_dtype": (C.c_int, [_vp, _i32]),
+    "spef_set_host_pack": (C.c_int, [_vp, _i32]),
+    "spef_pack_bf16_host": (C.c_int, [_vp, _vp, _i64]),
+    "spef_host_pack_info": (C.c_int, [_vp, C.POINTER(_i32), C.POINTER(_i32), _vp]),
     "spef_resize_frames": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
     "spef_forward": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp]),
     "spef_num_layers": (C.c_int, [_vp]),

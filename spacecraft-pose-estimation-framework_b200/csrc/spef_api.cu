@@ -9,6 +9,7 @@
 #include <string.h>
 
 #include <cmath>
+#include <chrono>
 #include <map>
 #include <string>
 #include <vector>
@@ -181,6 +182,18 @@ struct spef_ctx {
   cudaEvent_t pipe_consumed[2] = {nullptr, nullptr}; // compute that read slot s complete
   int pipe_slot = 0;
   long long pipe_submitted = 0;
+  // packed upload of float images (host_pack.cpp): the host rounds the pixels to BF16 -- the stem's own first step -- chunk by chunk
+  // into a pinned staging slot, the chunks cross the bus at half the bytes and a widening kernel on the copy stream restores the
+  // float tensor the stem reads.  0: plain copy.  Default 1 on the BF16 tcgen05 engine (SPEF_HOST_PACK=0 / spef_set_host_pack).
+  int host_pack = 0;
+  uint16_t* pack_host[2] = {nullptr, nullptr};   // pinned, [max_batch * 3 * H * W] bf16
+  uint16_t* pack_dev[2] = {nullptr, nullptr};
+  cudaEvent_t pack_uploaded[2] = {nullptr, nullptr};   // the DMA engine is done reading pack_host[s]
+  cudaEvent_t pack_t0[2] = {nullptr, nullptr}, pack_t1[2] = {nullptr, nullptr};   // around the plain slice's copy (upload_packed)
+  size_t pack_plain_bytes[2] = {0, 0};
+  double pack_rc = 60e9, pack_rd = 50e9;   // measured while running: float bytes / s the host threads convert, bytes / s of a plain copy
+  double pack_frac = -1.0;                 // SPEF_PACK_FRAC (developer): fixed packed fraction instead of the balance
+  double pack_last_frac = 0.0;
   float* ws_quat = nullptr;     // [max_batch,4]
   float* ws_pos = nullptr;      // [max_batch,3]
   float* ws_qt = nullptr;       // [max_batch,4]
@@ -382,6 +395,9 @@ extern "C" int spef_create(spef_ctx** out, const spef_config* cfg) {
   if (const char* e5 = getenv("SPEF_STEM_SIMT")) ctx->stem_simt = atoi(e5) ? 1 : 0;
   if (const char* e5 = getenv("SPEF_FB_DEBUG_SKIP")) ctx->fb_debug_skip = atoi(e5);
   if (getenv("SPEF_FBT_NO_STACK")) ctx->fbt_no_stack = 1;
+  ctx->host_pack = (cfg->precision == SPEF_BF16 && cfg->pw_impl == 0) ? 1 : 0;
+  if (const char* e = getenv("SPEF_HOST_PACK")) ctx->host_pack = atoi(e) ? 1 : 0;
+  if (const char* e = getenv("SPEF_PACK_FRAC")) ctx->pack_frac = atof(e);
   if (getenv("SPEF_HEAD_WIDE")) ctx->head_wide = 1;
   if (const char* e5 = getenv("SPEF_TEMPORAL_GRAPH")) ctx->temporal_graph = atoi(e5) ? 1 : 0;
   if (const char* e5 = getenv("SPEF_TEMPORAL_GRAPH_MAX")) ctx->temporal_graph_max_streams = atoi(e5);
@@ -473,6 +489,11 @@ extern "C" void spef_destroy(spef_ctx* ctx) {
   for (int i = 0; i < 8; ++i) cudaFree(ctx->t_ws[i]);
   for (cudaEvent_t ev : ctx->events) cudaEventDestroy(ev);
   for (int s = 0; s < 2; ++s) {
+    if (ctx->pack_host[s]) cudaFreeHost(ctx->pack_host[s]);
+    cudaFree(ctx->pack_dev[s]);
+    if (ctx->pack_uploaded[s]) cudaEventDestroy(ctx->pack_uploaded[s]);
+    if (ctx->pack_t0[s]) cudaEventDestroy(ctx->pack_t0[s]);
+    if (ctx->pack_t1[s]) cudaEventDestroy(ctx->pack_t1[s]);
     cudaFree(ctx->pipe_images[s]); cudaFree(ctx->pipe_qt[s]); cudaFree(ctx->pipe_tt[s]); cudaFree(ctx->pipe_per[s]);
     if (ctx->pipe_copied[s]) cudaEventDestroy(ctx->pipe_copied[s]);
     if (ctx->pipe_consumed[s]) cudaEventDestroy(ctx->pipe_consumed[s]);
@@ -2032,6 +2053,97 @@ extern "C" int spef_eval_batch_host(spef_ctx* ctx, const float* images_host, con
   return SPEF_OK;
 }
 
+namespace spef_host {
+void pack_bf16(const float* src, uint16_t* dst, size_t n);
+int pack_threads();
+}
+
+// BF16 pixels -> the float tensor of the image contract (exact widening); 8 pixels per thread
+__global__ void __launch_bounds__(256) widen_bf16_kernel(const uint4* __restrict__ in, float4* __restrict__ out, size_t n8) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+    const uint4 v = in[i];
+    out[2 * i] = make_float4(__uint_as_float(v.x << 16), __uint_as_float(v.x & 0xffff0000u), __uint_as_float(v.y << 16), __uint_as_float(v.y & 0xffff0000u));
+    out[2 * i + 1] = make_float4(__uint_as_float(v.z << 16), __uint_as_float(v.z & 0xffff0000u), __uint_as_float(v.w << 16), __uint_as_float(v.w & 0xffff0000u));
+  }
+}
+
+static bool pack_applies(const spef_ctx* ctx) {
+  // only where the consumer's first step is the same rounding: the tcgen05 stem (GEMM or fused into block 1) of the BF16 engine
+  return ctx->host_pack && !ctx->image_u8 && ctx->cfg.precision == SPEF_BF16 && ctx->cfg.pw_impl == 0 && !ctx->stem_simt &&
+         ((size_t)3 * ctx->cfg.img_h * ctx->cfg.img_w) % 8 == 0;
+}
+
+static int ensure_pack(spef_ctx* ctx) {
+  if (ctx->pack_host[0]) return SPEF_OK;
+  const size_t n = (size_t)ctx->cfg.max_batch * 3 * ctx->cfg.img_h * ctx->cfg.img_w;
+  for (int s = 0; s < 2; ++s) {
+    CK(cudaHostAlloc((void**)&ctx->pack_host[s], n * 2, cudaHostAllocDefault));
+    CK(cudaMalloc((void**)&ctx->pack_dev[s], n * 2));
+    CK(cudaEventCreateWithFlags(&ctx->pack_uploaded[s], cudaEventDisableTiming));
+    CK(cudaEventCreate(&ctx->pack_t0[s]));
+    CK(cudaEventCreate(&ctx->pack_t1[s]));
+  }
+  return SPEF_OK;
+}
+
+// images_host (float) -> dst_dev (float) on `cs` through staging slot s.  The batch is split: the tail goes as it is (the DMA engine
+// needs no help with it and starts at once), the head is rounded to BF16 chunk by chunk on the host threads, each chunk handed to the DMA
+// engine while the next one converts, and widened on the device.  The split balances the two resources from what this context measures
+// while it runs -- r_c, the float bytes per second the host threads convert (host clock around the conversions, i.e. with the DMA traffic
+// competing for the same memory), and r_d, the bytes per second of the plain slice's copy (events around it):
+//   head fraction f:  f / r_c = (f / 2 + 1 - f) / r_d   ->   f = r_c / (r_d + r_c / 2),   capped at 15/16 (there is always a slice to time).
+static int upload_packed(spef_ctx* ctx, int s, const float* images_host, float* dst_dev, int B, cudaStream_t cs, cudaEvent_t dst_free) {
+  int rc = ensure_pack(ctx);
+  if (rc) return rc;
+  const size_t n = (size_t)B * 3 * ctx->cfg.img_h * ctx->cfg.img_w;
+  // the staging slot is free once the copies of its previous use have left the host (normally long ago: two submits back)
+  CK(cudaEventSynchronize(ctx->pack_uploaded[s]));
+  if (ctx->pack_plain_bytes[s] > 0) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ctx->pack_t0[s], ctx->pack_t1[s]) == cudaSuccess && ms > 0.f) {
+      const double obs = (double)ctx->pack_plain_bytes[s] / (ms * 1e-3);
+      ctx->pack_rd = obs > ctx->pack_rd * 0.95 ? obs : ctx->pack_rd * 0.95;   // the best recent rate: a copy that shared the engine with the other lane reads low
+    } else {
+      (void)cudaGetLastError();
+    }
+    ctx->pack_plain_bytes[s] = 0;
+  }
+  double f = ctx->pack_rc / (ctx->pack_rd + 0.5 * ctx->pack_rc);
+  if (ctx->pack_frac >= 0.0) f = ctx->pack_frac;
+  const size_t BLK = 65536;   // split and chunk boundaries: whole 64 K-pixel blocks (staging rows stay 64-byte aligned, n % 8 holds for the widening)
+  const size_t nblk = n / BLK;
+  size_t head_blk = (size_t)(f * (double)nblk + 0.5);
+  const size_t max_head = ctx->pack_frac >= 0.0 ? nblk : nblk - (nblk + 15) / 16;
+  if (head_blk > max_head) head_blk = max_head;
+  size_t head = head_blk * BLK;
+  if (nblk == 0 || ctx->pack_frac >= 1.0) head = n;             // a small batch (or a forced full pack): everything packed
+  if (dst_free) CK(cudaStreamWaitEvent(cs, dst_free, 0));
+  if (head < n) {
+    CK(cudaEventRecord(ctx->pack_t0[s], cs));
+    CK(cudaMemcpyAsync(dst_dev + head, images_host + head, (n - head) * 4, cudaMemcpyHostToDevice, cs));
+    CK(cudaEventRecord(ctx->pack_t1[s], cs));
+    ctx->pack_plain_bytes[s] = (n - head) * 4;
+  }
+  if (head > 0) {
+    size_t chunk = ((head / 8 + BLK - 1) / BLK) * BLK;   // ~8 chunks
+    if (chunk == 0) chunk = head;
+    const auto t0 = std::chrono::steady_clock::now();
+    for (size_t o = 0; o < head; o += chunk) {
+      const size_t len = (o + chunk <= head) ? chunk : head - o;
+      spef_host::pack_bf16(images_host + o, ctx->pack_host[s] + o, len);
+      CK(cudaMemcpyAsync(ctx->pack_dev[s] + o, ctx->pack_host[s] + o, len * 2, cudaMemcpyHostToDevice, cs));
+    }
+    const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (sec > 0 && head >= BLK) ctx->pack_rc = 0.5 * ctx->pack_rc + 0.5 * ((double)head * 4 / sec);
+    CK(cudaEventRecord(ctx->pack_uploaded[s], cs));
+    widen_bf16_kernel<<<ctx->num_sms * 4, 256, 0, cs>>>(reinterpret_cast<const uint4*>(ctx->pack_dev[s]), reinterpret_cast<float4*>(dst_dev), head / 8);
+    CK(cudaGetLastError());
+    ctx->launches++;
+  }
+  ctx->pack_last_frac = n ? (double)head / (double)n : 0.0;
+  return SPEF_OK;
+}
+
 static int ensure_pipe(spef_ctx* ctx) {
   if (ctx->pipe_copy_stream) return SPEF_OK;
   const size_t B = (size_t)ctx->cfg.max_batch;
@@ -2047,6 +2159,26 @@ static int ensure_pipe(spef_ctx* ctx) {
   return SPEF_OK;
 }
 
+extern "C" int spef_pack_bf16_host(const float* src_host, uint16_t* dst_host, int64_t n) {
+  if (!src_host || !dst_host || n < 0) return SPEF_ERR_INVALID;
+  spef_host::pack_bf16(src_host, dst_host, (size_t)n);
+  return SPEF_OK;
+}
+
+extern "C" int spef_set_host_pack(spef_ctx* ctx, int32_t on) {
+  if (!ctx) return SPEF_ERR_INVALID;
+  ctx->host_pack = on ? 1 : 0;
+  return SPEF_OK;
+}
+
+extern "C" int spef_host_pack_info(const spef_ctx* ctx, int32_t* active, int32_t* threads, double* stats) {
+  if (!ctx) return SPEF_ERR_INVALID;
+  if (active) *active = pack_applies(ctx) ? 1 : 0;
+  if (threads) *threads = pack_applies(ctx) ? spef_host::pack_threads() : 0;
+  if (stats) { stats[0] = ctx->pack_last_frac; stats[1] = ctx->pack_rc; stats[2] = ctx->pack_rd; }
+  return SPEF_OK;
+}
+
 extern "C" int spef_eval_submit_host(spef_ctx* ctx, const float* images_host, const float* qt_h, const float* tt_h, int32_t B,
                                      float* per_image_h, void* stream) {
   int rc = check_ready(ctx, B, "spef_eval_submit_host");
@@ -2057,8 +2189,12 @@ extern "C" int spef_eval_submit_host(spef_ctx* ctx, const float* images_host, co
   cudaStream_t st = (cudaStream_t)stream;
   const int s = ctx->pipe_slot;
   // the copy into slot s may start once the compute that last read slot s (two submits ago) has finished
-  if (ctx->pipe_submitted >= 2) CK(cudaStreamWaitEvent(ctx->pipe_copy_stream, ctx->pipe_consumed[s], 0));
-  CK(cudaMemcpyAsync(ctx->pipe_images[s], images_host, (size_t)B * 3 * ctx->cfg.img_h * ctx->cfg.img_w * (ctx->image_u8 ? 1 : sizeof(float)), cudaMemcpyHostToDevice, ctx->pipe_copy_stream));
+  if (pack_applies(ctx)) {
+    if ((rc = upload_packed(ctx, s, images_host, ctx->pipe_images[s], B, ctx->pipe_copy_stream, ctx->pipe_submitted >= 2 ? ctx->pipe_consumed[s] : nullptr))) return rc;
+  } else {
+    if (ctx->pipe_submitted >= 2) CK(cudaStreamWaitEvent(ctx->pipe_copy_stream, ctx->pipe_consumed[s], 0));
+    CK(cudaMemcpyAsync(ctx->pipe_images[s], images_host, (size_t)B * 3 * ctx->cfg.img_h * ctx->cfg.img_w * (ctx->image_u8 ? 1 : sizeof(float)), cudaMemcpyHostToDevice, ctx->pipe_copy_stream));
+  }
   CK(cudaMemcpyAsync(ctx->pipe_qt[s], qt_h, (size_t)B * 16, cudaMemcpyHostToDevice, ctx->pipe_copy_stream));
   CK(cudaMemcpyAsync(ctx->pipe_tt[s], tt_h, (size_t)B * 12, cudaMemcpyHostToDevice, ctx->pipe_copy_stream));
   CK(cudaEventRecord(ctx->pipe_copied[s], ctx->pipe_copy_stream));

@@ -616,3 +616,42 @@ def test_evaluation_lanes_equal_single_stream(precision):
     # host and device-resident loaders agree; the reloaded weights (position bias scaled) changed the position score on BOTH lanes
     np.testing.assert_allclose(two[0][0]["valid"]["esa"], two[1][0]["valid"]["esa"], rtol=1e-12)
     assert abs(two[-1][0]["valid"]["pos"][0] - two[0][0]["valid"]["pos"][0]) > 1e-6
+
+
+def test_packed_upload_is_bit_identical(sd):
+    """spef_eval_submit_host with the packed upload (host threads round the float pixels to BF16 -- the stem's first step -- and half
+    the bytes cross the bus; csrc/host_pack.cpp) against the plain float copy: per-image errors bit-identical, sums equal; full and
+    ragged batches, more submits than staging slots, a NaN pixel still reaches the decode guard; the FP32 engine never packs."""
+    hist = O.ori_histogram(12)[0]
+    imgs = [synthetic.synthetic_images(b, seed=40 + i).pin_memory() for i, b in enumerate((8, 5, 8, 1, 7))]
+    tgs = [synthetic.synthetic_targets(im.shape[0], seed=i) for i, im in enumerate(imgs)]
+    res = {}
+    for on in (False, True):
+        eng = _engine(sd, "bf16")
+        eng.set_ori_histogram(hist)
+        eng.set_host_pack(on)
+        active, threads = eng.host_pack_info()
+        assert active == on and (threads >= 1) == on
+        eng.eval_reset()
+        outs = []
+        for im, tg in zip(imgs, tgs):
+            per = torch.empty((im.shape[0], 2), dtype=torch.float32).pin_memory()
+            eng.eval_submit_host(im, torch.as_tensor(tg["ori"]).float(), torch.as_tensor(tg["pos"]).float(), per)
+            outs.append(per)
+        eng.eval_wait()
+        res[on] = ([o.numpy().copy() for o in outs], eng.eval_read())
+        if on:
+            bad = imgs[1].clone().pin_memory()
+            bad[2, 1, 100, 7] = float("nan")
+            eng.eval_reset()
+            eng.eval_submit_host(bad, torch.as_tensor(tgs[1]["ori"]).float(), torch.as_tensor(tgs[1]["pos"]).float(), None)
+            eng.eval_wait()
+            assert eng.eval_read()[6] >= 1          # the NaN image is counted by the orientation decode guard (sums[6]), as with the plain copy
+        eng.close()
+    for a, b in zip(res[False][0], res[True][0]):
+        np.testing.assert_array_equal(a, b)
+    np.testing.assert_array_equal(res[False][1], res[True][1])
+    assert res[True][1][3] == sum(im.shape[0] for im in imgs)
+    eng = _engine(sd, "fp32")
+    assert eng.host_pack_info() == (False, 0)
+    eng.close()

@@ -234,3 +234,26 @@ def test_running_average_and_mad():
     ra.update({"a": 5.0}, 1)
     assert ra.get("a") == 2.0 and ra.get_multiple(("a",)) == {"a": 2.0}
     assert mad([1.0, 2.0, 3.0, 4.0, 100.0]) == 1.0
+
+
+def test_host_pack_rounds_like_the_device():
+    """spef_pack_bf16_host (the host half of the packed image upload, csrc/host_pack.cpp) == round-to-nearest-even BF16 of every
+    float, the stem's own first step (cvt.rn.bf16.f32): ties, carries into the exponent, overflow to inf, denormals kept,
+    NaN stays NaN; unaligned heads / ragged tails of the vector code; several pool generations back to back."""
+    from spef_b200 import _ffi
+    lib = _ffi.lib()
+    g = torch.Generator().manual_seed(3)
+    special = torch.tensor([0.0, -0.0, 1.0, 1.00390625, 1.01171875, 0.999999, 3.3895314e38, 3.4028235e38, float("inf"), -float("inf"),
+                            1e-40, -1e-45, 1.1754944e-38, 0.5 + 2 ** -9, 0.5 + 2 ** -9 + 2 ** -20, float("nan")], dtype=torch.float32)
+    bits = torch.randint(-2 ** 31, 2 ** 31 - 1, (300000,), generator=g, dtype=torch.int64).to(torch.int32).view(torch.float32)
+    for n, off in ((16, 0), (special.numel(), 0), (1000, 3), (65536 * 3 + 77, 1), (300000, 0), (300000, 5)):
+        src = torch.cat([special, torch.rand(400000, generator=g), bits])[off:off + n].contiguous()
+        dst = torch.zeros(n + 64, dtype=torch.int16)
+        d = dst[off:off + n]
+        assert lib.spef_pack_bf16_host(src.data_ptr(), d.data_ptr(), n) == 0
+        want = src.to(torch.bfloat16)
+        got = d.view(torch.bfloat16)
+        nan = torch.isnan(src)
+        assert torch.equal(torch.isnan(got), nan)
+        assert torch.equal(got[~nan].view(torch.int16), want[~nan].view(torch.int16))
+        assert int(dst[:off].abs().sum()) == 0 and int(dst[off + n:].abs().sum()) == 0   # nothing written outside
