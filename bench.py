@@ -352,6 +352,14 @@ def layer_table(eng, batch, ms):
                        "bytes": grp[0]["ein"] * 4 + grp[-1]["eout"] * esz, "flops": sum(g["flops"] for g in grp),
                        "ms": sum(g["ms"] for g in grp), "hidden": grp[0]["cout"], "tile": f"{bi['tile_h']}x{4 * bi['tile_w']}",
                        "unfused_bytes": sum(g["bytes"] for g in grp), "stem_fused": True})
+    if eng.pool_fusion_active():
+        # last 1x1 conv + global average pool as ONE launch (timed in the conv's slot): reads x, writes the pooled vector
+        for r in rows:
+            if r["kernel"] == "global_mean_kernel" and r["layer"] > 0 and rows[r["layer"] - 1]["kernel"] == "pw_gemm":
+                cv = rows[r["layer"] - 1]
+                skip.add(r["layer"])
+                cv.update({"kernel": "conv_pool_kernel", "unfused_bytes": cv["bytes"] + r["bytes"], "bytes": (cv["ein"] + r["eout"]) * esz,
+                           "flops": cv["flops"] + r["flops"], "ms": cv["ms"] + r["ms"], "hw": r["hw"]})
     for r in rows:
         if r["layer"] in skip:
             continue

@@ -146,6 +146,10 @@ int spef_block_forward(spef_ctx* ctx, int32_t block, const void* in_dev, void* o
  * out_dev NHWC bf16) and fails with SPEF_ERR_UNSUPPORTED when the route is not active. */
 int spef_set_stem_fusion(spef_ctx* ctx, int32_t on);
 int spef_stem_fusion_active(const spef_ctx* ctx);
+/* Last 1x1 conv of the backbone (mobilenet_v2.py:264) + the global average pool in front of the heads (`x.mean([2, 3])`) as ONE
+ * kernel on the BF16 tcgen05 path (csrc/conv_pool.cuh; bit-identical to the two launches; SPEF_POOL_FUSE=0 or spef_set_fusion(ctx, 0):
+ * two launches).  Reports whether spef_forward takes that route in the current configuration. */
+int spef_pool_fusion_active(const spef_ctx* ctx);
 int spef_stem_block_forward(spef_ctx* ctx, const void* images_dev, void* out_dev, int32_t batch, void* stream);
 
 /* ---- encode (label side) and error statistics (8f #3) ----------------------------
@@ -218,8 +222,10 @@ int spef_eval_wait(spef_ctx* ctx, void* stream);
  * (SPEF_HOST_PACK=0 or spef_set_host_pack(ctx, 0): plain copy; SPEF_PACK_THREADS: host threads, default min(16, cores / LOCAL_WORLD_SIZE)).
  * A submit splits its batch: the tail crosses as float (the DMA engine starts on it at once), the head is packed; the split
  * balances the host threads against the bus from rates the context measures while it runs (float bytes / s converted, bytes / s
- * of the plain slice's copy).  spef_host_pack_info: whether the next submit packs, with how many host threads, and
- * stats[3] = {packed fraction of the last submit, measured conversion rate, measured copy rate} (bytes / s). */
+ * of the plain slice's copy); when the conversion rate is below half the copy rate (many ranks sharing a small host: the
+ * copies are then limited by the host's memory system, which the conversion would load further) the batch goes as it is and only a
+ * small probe slice is packed now and then.  spef_host_pack_info: whether packing is enabled, with how many host threads, and
+ * stats[3] = {packed fraction of the recent submits, measured conversion rate, measured copy rate} (bytes / s). */
 int spef_set_host_pack(spef_ctx* ctx, int32_t on);
 /* the host half of the packed upload on its own (no GPU involved): dst[i] = bf16 bits of src[i], round to nearest even */
 int spef_pack_bf16_host(const float* src_host, uint16_t* dst_host, int64_t n);

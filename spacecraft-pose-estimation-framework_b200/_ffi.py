@@ -62,6 +62,7 @@ SIGNATURES = {
     "spef_block_forward": (C.c_int, [_vp, _i32, _vp, _vp, _i32, _vp]),
     "spef_set_stem_fusion": (C.c_int, [_vp, _i32]),
     "spef_stem_fusion_active": (C.c_int, [_vp]),
+    "spef_pool_fusion_active": (C.c_int, [_vp]),
     "spef_stem_block_forward": (C.c_int, [_vp, _vp, _vp, _i32, _vp]),
     "spef_decode_ori": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "spef_decode_pos": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),

@@ -7,7 +7,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libspef_b200.so")
 SOURCES = ["spef_api.cu", "host_pack.cpp"]
-HEADERS = ["common.cuh", "kernels_conv.cuh", "kernels_post.cuh", "kernels_ingest.cuh", "decode_stream.cuh", "gemm_tcgen05.cuh", "gemm_tcgen05_v2.cuh", "dwconv_tma.cuh", "fused_block.cuh", "fused_block_t.cuh", "dw_project.cuh"]
+HEADERS = ["common.cuh", "kernels_conv.cuh", "kernels_post.cuh", "kernels_ingest.cuh", "decode_stream.cuh", "gemm_tcgen05.cuh", "gemm_tcgen05_v2.cuh", "dwconv_tma.cuh", "fused_block.cuh", "fused_block_t.cuh", "dw_project.cuh", "conv_pool.cuh"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-shared", "-Xcompiler", "-fPIC,-pthread",

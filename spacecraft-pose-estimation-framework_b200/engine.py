@@ -270,6 +270,10 @@ class Engine:
         """True when the stem conv runs inside the first block's kernel (spef_stem_fusion_active)."""
         return bool(self.lib.spef_stem_fusion_active(self._h))
 
+    def pool_fusion_active(self) -> bool:
+        """True when the last 1x1 conv and the global average pool run as one kernel (spef_pool_fusion_active)."""
+        return bool(self.lib.spef_pool_fusion_active(self._h))
+
     def set_stem_fusion(self, on: bool):
         """True (default): stem + first InvertedResidual block as one kernel; False: separate stem launch."""
         self._ck(self.lib.spef_set_stem_fusion(self._h, 1 if on else 0))

@@ -655,3 +655,26 @@ def test_packed_upload_is_bit_identical(sd):
     eng = _engine(sd, "fp32")
     assert eng.host_pack_info() == (False, 0)
     eng.close()
+
+
+def test_conv_pool_kernel_is_bit_identical_to_two_launches(sd, monkeypatch):
+    """The last 1x1 conv (320 -> 1280 @8x12) and the global average pool as ONE kernel (csrc/conv_pool.cuh: transposed GEMM, a thread
+    owns a channel, the pool is a sum over its registers in the pool kernel's order) against the GEMM + global_mean_kernel launches
+    (SPEF_POOL_FUSE=0; each of them is teacher-forced against the oracle above): logits and positions bit-identical for odd, single
+    and full batches (the odd image of a pair, CTAs without work, every CTA looping over several image pairs)."""
+    outs = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("SPEF_POOL_FUSE", mode)
+        eng = _engine(sd, "bf16", max_batch=256)
+        l0 = eng.launch_count()
+        res = []
+        for b, seed in ((5, 11), (1, 12), (256, 13)):
+            x = synthetic.synthetic_images(min(b, 16), seed=seed)
+            x = x.repeat((b + x.shape[0] - 1) // x.shape[0], 1, 1, 1)[:b].contiguous()
+            res.append([t.cpu().numpy() for t in eng.forward(x)])
+        outs[mode] = (res, eng.launch_count() - l0)
+        eng.close()
+    for (o1, p1), (o0, p0) in zip(outs["1"][0], outs["0"][0]):
+        np.testing.assert_array_equal(o1, o0)
+        np.testing.assert_array_equal(p1, p0)
+    assert outs["0"][1] - outs["1"][1] == 3, outs      # one launch fewer per forward
