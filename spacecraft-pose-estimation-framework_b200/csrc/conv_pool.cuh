@@ -14,14 +14,16 @@
 //   grid = n_ct x cpc CTAs: CTA (ct, j) keeps the K chunks of channel tile ct resident in shared memory (80 KB at K = 320) and walks
 //   over the image groups j, j + cpc, ...; the X tiles stream through a TMA ring (they are read by the n_ct CTAs of a group: from L2).
 //   warp 0  TMA producer          warp 1  tcgen05.mma issuer (elected lane of the converged warp)      warp 2  TMEM allocation
-//   warps 4-7  epilogue: tcgen05.ld of the image's HW columns -> + bias -> BF16 -> ReLU -> FP32 partial sums -> mean -> BF16 store
+//   warps 4-11 epilogue (two teams, one image of the pair each): tcgen05.ld of the image's HW columns -> + bias -> BF16 -> ReLU -> FP32
+//              partial sums -> mean -> BF16 store
 #pragma once
 #include "gemm_tcgen05_v2.cuh"
 
 namespace spef {
 namespace cpool {
 
-constexpr int NT = 256;
+constexpr int EPI_TEAMS = 2;                 // epilogue teams of four warps (one warp per TMEM lane quarter); team t takes the images t, t + 2, ... of an item
+constexpr int NT = 128 + 128 * EPI_TEAMS;
 constexpr int MAX_X_STAGES = 8;
 constexpr int ACC_STAGES = 2, ACC_STRIDE = 256;
 
@@ -64,7 +66,7 @@ conv_pool_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmW); tma_prefetch_desc(&tmX); }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < p.x_stages; ++i) { mbar_init(smem_u32(&x_full[i]), 1); mbar_init(smem_u32(&x_empty[i]), 1); }
-    for (int i = 0; i < ACC_STAGES; ++i) { mbar_init(smem_u32(&acc_full[i]), 1); mbar_init(smem_u32(&acc_empty[i]), 4); }
+    for (int i = 0; i < ACC_STAGES; ++i) { mbar_init(smem_u32(&acc_full[i]), 1); mbar_init(smem_u32(&acc_empty[i]), 4 * EPI_TEAMS); }
     mbar_init(smem_u32(w_bar), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -129,38 +131,61 @@ conv_pool_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
     __syncwarp();
   } else if (warp >= 4) {
     // ===================== epilogue: one output channel per thread =====================
+    // (first version: one team, a tcgen05.wait::ld after each of the six loads of an item, scalar adds -- ncu: the MMA issuer polled
+    //  acc_empty 12x per item, tensor pipe 50 %: the epilogue paced the kernel.  Now two teams take one image of the pair each, the three
+    //  loads of an image are in flight together and the bias add / partial sums are packed f32x2 operations.)
     const int q = warp & 3;                       // TMEM lane quarter this warp may read
+    const int team = (warp - 4) >> 2;
     const int ch = ct * 128 + q * 32 + lane;
     const float bias = p.bias[ch];
-    const float inv_div = (float)p.HW;
+    const uint64_t bias2 = pack_f32x2(__float_as_uint(bias), __float_as_uint(bias));
+    const float divisor = (float)p.HW;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int it = j0; it < n_items; it += p.cpc) {
       mbar_wait(smem_u32(&acc_full[acc]), acc_phase);
       tcgen05_fence_after();
       const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_STRIDE);
-      for (int im = 0; im < p.ipt; ++im) {
-        float part[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        // the pixels of image `im` are columns [im * HW, (im + 1) * HW): 32 at a time (HW is a multiple of 32: checked by the host)
-        for (int c0 = 0; c0 < p.HW; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(t0 + (uint32_t)(im * p.HW + c0), v);
-          tmem_ld_wait();
+      for (int im = team; im < p.ipt; im += EPI_TEAMS) {
+        // partial sums of the pool kernel: part[w] takes the pixels p = w (mod 8) in increasing order; pairs (part[2j], part[2j + 1]) are packed
+        uint64_t part2[4] = {0ull, 0ull, 0ull, 0ull};
+        auto fold = [&](const uint32_t (&v)[32]) {
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
             // the per-layer epilogue: acc + bias in FP32, one rounding to BF16, ReLU on the BF16 pair (NaN-propagating)
-            uint32_t pk;
-            asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pk) : "f"(__fadd_rn(__uint_as_float(v[i + 1]), bias)), "f"(__fadd_rn(__uint_as_float(v[i]), bias)));
+            uint32_t pk = cvt_bf16x2(add_f32x2(pack_f32x2(v[i], v[i + 1]), bias2));
             if (p.relu) pk = relu_bf16x2(pk);
-            part[i & 7] += __uint_as_float(pk << 16);
-            part[(i + 1) & 7] += __uint_as_float(pk & 0xffff0000u);
+            part2[(i >> 1) & 3] = add_f32x2(part2[(i >> 1) & 3], pack_f32x2(pk << 16, pk & 0xffff0000u));
           }
+        };
+        const uint32_t tc0 = t0 + (uint32_t)(im * p.HW);
+        int c0 = 0;
+        for (; c0 + 96 <= p.HW; c0 += 96) {       // three loads in flight (HW = 96: the whole image)
+          uint32_t v0[32], v1[32], v2[32];
+          tmem_ld_32x32b_x32(tc0 + (uint32_t)c0, v0);
+          tmem_ld_32x32b_x32(tc0 + (uint32_t)(c0 + 32), v1);
+          tmem_ld_32x32b_x32(tc0 + (uint32_t)(c0 + 64), v2);
+          tmem_ld_wait();
+          fold(v0); fold(v1); fold(v2);
+        }
+        for (; c0 < p.HW; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tc0 + (uint32_t)c0, v);
+          tmem_ld_wait();
+          fold(v);
+        }
+        float part[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          uint32_t lo, hi;
+          asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(part2[k]));
+          part[2 * k] = __uint_as_float(lo); part[2 * k + 1] = __uint_as_float(hi);
         }
         float t = part[0];
 #pragma unroll
         for (int k = 1; k < 8; ++k) t += part[k];
         const int b = it * p.ipt + im;
-        if (b < p.B) p.out[(size_t)b * p.C + ch] = __float2bfloat16_rn(t / inv_div);
+        if (b < p.B) p.out[(size_t)b * p.C + ch] = __float2bfloat16_rn(t / divisor);
       }
       tcgen05_fence_before();
       __syncwarp();
