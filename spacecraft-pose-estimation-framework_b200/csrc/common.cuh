@@ -52,6 +52,13 @@ template <> struct Vec8<float> {
   }
 };
 
+// Programmatic dependent launch (the forward chain is launched with cudaLaunchAttributeProgrammaticStreamSerialization, spef_api.cu):
+// a kernel lets its successor start launching at once and does its own set-up (barrier init, TMEM allocation, tensor-map prefetch,
+// bias staging -- nothing that depends on the predecessor's output) before it waits for the predecessor grid to have completed and
+// flushed.  Both instructions are no-ops in a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 template <typename T> __device__ __forceinline__ float to_f32(T x);
 template <> __device__ __forceinline__ float to_f32<float>(float x) { return x; }
 template <> __device__ __forceinline__ float to_f32<bf16>(bf16 x) { return __bfloat162float(x); }

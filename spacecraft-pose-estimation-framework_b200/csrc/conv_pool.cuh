@@ -44,6 +44,7 @@ inline size_t smem_bytes(const ConvPoolParams& p) { return 1024 + (size_t)w_byte
 __global__ void __launch_bounds__(NT, 1)
 conv_pool_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX, const ConvPoolParams p) {
   using namespace tc;
+  pdl_launch_dependents();   // the next kernel of the chain may start its own set-up (common.cuh)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int k_chunks = (p.K + 63) / 64;
@@ -78,6 +79,7 @@ conv_pool_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
+  pdl_wait();   // everything above is independent of the previous kernel's output (common.cuh)
 
   if (warp == 0) {
     // ===================== TMA producer =====================

@@ -160,6 +160,7 @@ __device__ __forceinline__ void producer_loop(const DwpParams& p, const ProdCtx&
 
 __global__ void __launch_bounds__(NT, 1)
 dw_project_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const DwpParams p) {
+  pdl_launch_dependents();   // the next kernel of the chain may start its own set-up (common.cuh)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int abs_ = A_BYTES, ws_ = w_stride(p);
@@ -223,6 +224,7 @@ dw_project_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   __syncthreads();
   tc::tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
+  pdl_wait();   // everything above is independent of the previous kernel's output (common.cuh)
 
   // register file per role (launch allocation 20 warps x 96): producers 12 x 120, epilogue 4 x 64, the warpgroup of the single-lane
   // roles 4 x 40 (setmaxnreg is a warpgroup instruction: all four warps execute the same one)

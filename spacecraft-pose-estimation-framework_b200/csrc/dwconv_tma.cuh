@@ -56,6 +56,7 @@ dwconv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmX, const float* __res
                      bf16* __restrict__ out, const DwParams p) {
   constexpr int NT = 32 * CV;
   constexpr int NCOLS = (TX - 1) * S + 3;
+  pdl_launch_dependents();   // the next kernel of the chain may start its own set-up (common.cuh)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
   const int tile_bytes = p.THI * p.TWI * CV * 16;               // TMA transaction size (full box, OOB included)
@@ -82,6 +83,7 @@ dwconv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmX, const float* __res
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  pdl_wait();   // everything above is independent of the previous kernel's output (common.cuh)
 
   auto issue = [&](long long sp, int stage) {
     long long r = sp;

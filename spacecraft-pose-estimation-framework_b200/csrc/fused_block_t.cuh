@@ -234,6 +234,7 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   constexpr int GT = 32 * GW;
   constexpr int TW = (S == 1) ? 12 : 6;           // output columns of a tile
   constexpr int TWI = (TW - 1) * S + 3;           // 14 | 13 input columns: one tcgen05.ld.x16 per pixel row
+  pdl_launch_dependents();   // the next kernel of the chain may start its own set-up (common.cuh)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int xsb = x_stage_bytes(STEM ? 2 : p.kc_in, p.n_px);
@@ -335,6 +336,7 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   __syncthreads();
   tc::tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
+  pdl_wait();   // everything above is independent of the previous kernel's output (common.cuh)
 
   const float rcp_tpi = 1.0f / (float)tiles_per_img, rcp_tx = 1.0f / (float)p.tiles_x;
   auto tile_coords = [&](int i, int& b, int& oy0, int& ox0) {

@@ -13,6 +13,7 @@
 #include <map>
 #include <string>
 #include <vector>
+#include <utility>
 
 #include "../../include/spef_b200.h"
 #include "common.cuh"
@@ -146,6 +147,11 @@ struct spef_ctx {
   int fb_debug_skip = 0;   // SPEF_FB_DEBUG_SKIP: timing experiments of the staged fused kernel (wrong results)
   int fbt_no_stack = 0;    // SPEF_FBT_NO_STACK=1: no strip stacking in the channel-lane plan
   int head_wide = 0;       // SPEF_HEAD_WIDE=1: 256-column tiles for the head GEMM
+  // Programmatic dependent launch along the forward chain (common.cuh), for batches that leave SMs idle (SPEF_PDL=0: never; SPEF_PDL_MAX_BATCH).
+  // Measured: one stream of single frames 0.292 -> 0.280 ms, 64 streams 88.9 k -> 93.9 k frames/s; at batch 256 the waiting successor
+  // takes the SMs the other lane's kernel would have filled the tail with: 166.8 k -> 164.8 k images/s, hence the batch limit.
+  int pdl = 1, pdl_max_batch = 96;
+  bool pdl_on = false;     // this call's launches (set per entry point from the batch)
   int pool_fuse = 1;       // last 1x1 conv + global average pool as one kernel (conv_pool.cuh); SPEF_POOL_FUSE=0: two launches
   CUtensorMap cp_tmW, cp_tmX;
   bool cp_w_ready = false;
@@ -271,6 +277,21 @@ static int fail(spef_ctx* c, int code, const char* fmt, ...) {
     if (e_ != cudaSuccess) return fail(ctx, SPEF_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(e_)); \
     ctx->launches++;                                                                                    \
   } while (0)
+
+
+// Launch with programmatic stream serialization (PDL): the kernel may begin while its predecessor in the stream is still draining; it
+// calls griddepcontrol.wait before touching anything the predecessor wrote (common.cuh).  Only kernels that do so are launched this way.
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_chain(bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
 
 // ------------------------------------------------------------------------------------------------------
 // topology
@@ -408,6 +429,8 @@ extern "C" int spef_create(spef_ctx** out, const spef_config* cfg) {
   if (const char* e = getenv("SPEF_PACK_FRAC")) ctx->pack_frac = atof(e);
   if (getenv("SPEF_HEAD_WIDE")) ctx->head_wide = 1;
   if (const char* e = getenv("SPEF_POOL_FUSE")) ctx->pool_fuse = atoi(e) ? 1 : 0;
+  if (const char* e = getenv("SPEF_PDL")) ctx->pdl = atoi(e) ? 1 : 0;
+  if (const char* e = getenv("SPEF_PDL_MAX_BATCH")) ctx->pdl_max_batch = atoi(e);
   if (const char* e5 = getenv("SPEF_TEMPORAL_GRAPH")) ctx->temporal_graph = atoi(e5) ? 1 : 0;
   if (const char* e5 = getenv("SPEF_TEMPORAL_GRAPH_MAX")) ctx->temporal_graph_max_streams = atoi(e5);
   if (const char* e7 = getenv("SPEF_GEMM_NDG")) ctx->gemm_ndg = (atoi(e7) == 1) ? 1 : 2;
@@ -1082,8 +1105,8 @@ static int launch_cuda_core_layer(spef_ctx* ctx, const Layer& l, const void* in,
 }
 
 template <int S, int CV, int TX = 4>
-static void launch_dw_inst(const CUtensorMap& tm, const Layer& l, bf16* out, int grid, size_t smem, cudaStream_t st) {
-  dw::dwconv3x3_tma_kernel<S, CV, TX><<<grid, 32 * CV, smem, st>>>(tm, l.w_f32, l.bias, out, l.dwp);
+static void launch_dw_inst(bool pdl, const CUtensorMap& tm, const Layer& l, bf16* out, int grid, size_t smem, cudaStream_t st) {
+  launch_chain(pdl, dw::dwconv3x3_tma_kernel<S, CV, TX>, dim3(grid), dim3(32 * CV), smem, st, tm, (const float*)l.w_f32, (const float*)l.bias, out, l.dwp);
 }
 
 static int launch_dw_tma_layer(spef_ctx* ctx, Layer& l, const void* in, void* out, int B, cudaStream_t st, bool cached_maps) {
@@ -1106,15 +1129,15 @@ static int launch_dw_tma_layer(spef_ctx* ctx, Layer& l, const void* in, void* ou
   const size_t smem = dw::smem_bytes(l.dwp, l.dw_cv);
   bf16* o = (bf16*)out;
   if (l.stride == 1) {
-    if (l.dw_cv == 8 && l.dw_tx == 3) launch_dw_inst<1, 8, 3>(*tm, l, o, grid, smem, st);
-    else if (l.dw_cv == 8) launch_dw_inst<1, 8>(*tm, l, o, grid, smem, st);
-    else if (l.dw_cv == 6) launch_dw_inst<1, 6>(*tm, l, o, grid, smem, st);
-    else launch_dw_inst<1, 4>(*tm, l, o, grid, smem, st);
+    if (l.dw_cv == 8 && l.dw_tx == 3) launch_dw_inst<1, 8, 3>(ctx->pdl_on, *tm, l, o, grid, smem, st);
+    else if (l.dw_cv == 8) launch_dw_inst<1, 8>(ctx->pdl_on, *tm, l, o, grid, smem, st);
+    else if (l.dw_cv == 6) launch_dw_inst<1, 6>(ctx->pdl_on, *tm, l, o, grid, smem, st);
+    else launch_dw_inst<1, 4>(ctx->pdl_on, *tm, l, o, grid, smem, st);
   } else {
-    if (l.dw_cv == 8 && l.dw_tx == 3) launch_dw_inst<2, 8, 3>(*tm, l, o, grid, smem, st);
-    else if (l.dw_cv == 8) launch_dw_inst<2, 8>(*tm, l, o, grid, smem, st);
-    else if (l.dw_cv == 6) launch_dw_inst<2, 6>(*tm, l, o, grid, smem, st);
-    else launch_dw_inst<2, 4>(*tm, l, o, grid, smem, st);
+    if (l.dw_cv == 8 && l.dw_tx == 3) launch_dw_inst<2, 8, 3>(ctx->pdl_on, *tm, l, o, grid, smem, st);
+    else if (l.dw_cv == 8) launch_dw_inst<2, 8>(ctx->pdl_on, *tm, l, o, grid, smem, st);
+    else if (l.dw_cv == 6) launch_dw_inst<2, 6>(ctx->pdl_on, *tm, l, o, grid, smem, st);
+    else launch_dw_inst<2, 4>(ctx->pdl_on, *tm, l, o, grid, smem, st);
   }
   CK_LAUNCH("dwconv3x3_tma_kernel");
   return SPEF_OK;
@@ -1184,7 +1207,7 @@ static int launch_tcgen05_layer(spef_ctx* ctx, Layer& l, const void* in, const v
   const int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
   {
     const int nsw = ctx->gemm_nsw, ndg = ctx->gemm_ndg, nt2 = 128 + 128 * ndg + 32 * nsw;
-#define SPEF_V2_LAUNCH(F32, NDG_, NSW_) tc::pw_gemm_tcgen05_v2_kernel<F32, NDG_, NSW_, 0><<<grid, nt2, l.smem, st>>>(*tA, l.tmW, p)
+#define SPEF_V2_LAUNCH(F32, NDG_, NSW_) launch_chain(ctx->pdl_on, tc::pw_gemm_tcgen05_v2_kernel<F32, NDG_, NSW_, 0>, dim3(grid), dim3(nt2), l.smem, st, *tA, l.tmW, p)
     if (f32out) {
       if (ndg == 2) SPEF_V2_LAUNCH(true, 2, 4); else if (nsw == 8) SPEF_V2_LAUNCH(true, 1, 8); else SPEF_V2_LAUNCH(true, 1, 4);
     } else {
@@ -1249,11 +1272,11 @@ static int launch_fused_block_t(spef_ctx* ctx, Block& b, const void* in, void* o
   if ((long long)B * q.Ho * q.Wo >= (1LL << 31)) return fail(ctx, SPEF_ERR_UNSUPPORTED, "fused block: %lld output pixels exceed the 32-bit pixel offsets of the epilogue", (long long)B * q.Ho * q.Wo);
   const int grid = (int)(tiles < ctx->num_sms ? tiles : ctx->num_sms);
   const int nthr = 32 * (fbt::CTRL_WARPS + b.t_ng * fbt::GWT);
-#define SPEF_FBT_LAUNCH(S_, TH_) fbt::fused_block_t_kernel<S_, TH_, 2, true><<<grid, nthr, b.t_smem, st>>>(b.t_tmX, b.t_tmWe, b.t_tmWp, q)
+#define SPEF_FBT_LAUNCH(S_, TH_) launch_chain(ctx->pdl_on, fbt::fused_block_t_kernel<S_, TH_, 2, true>, dim3(grid), dim3(nthr), b.t_smem, st, b.t_tmX, b.t_tmWe, b.t_tmWp, q)
   const int S = L[b.i_dw].stride;
   if (b.i_exp < 0) {   // t = 1 block: no expand conv (strip-stacked four ways, two worker groups)
     if (!(S == 1 && q.TH == 6 && b.t_ng == 2)) return fail(ctx, SPEF_ERR_UNSUPPORTED, "fused block: no kernel instance for the t = 1 block with tile height %d", q.TH);
-    fbt::fused_block_t_kernel<1, 6, 2, false><<<grid, nthr, b.t_smem, st>>>(b.t_tmX, b.t_tmWe, b.t_tmWp, q);
+    launch_chain(ctx->pdl_on, fbt::fused_block_t_kernel<1, 6, 2, false>, dim3(grid), dim3(nthr), b.t_smem, st, b.t_tmX, b.t_tmWe, b.t_tmWp, q);
   }
   else if (S == 1 && q.TH == 6) SPEF_FBT_LAUNCH(1, 6);
   else if (S == 1 && q.TH == 5) SPEF_FBT_LAUNCH(1, 5);
@@ -1320,7 +1343,7 @@ static int launch_stem_block(spef_ctx* ctx, const void* images, void* out, int B
   if (tiles >= (1 << 22)) return fail(ctx, SPEF_ERR_UNSUPPORTED, "fused stem: %lld tiles exceed the 2^22 limit of the tile index arithmetic", tiles);
   const int grid = (int)(tiles < ctx->num_sms ? tiles : ctx->num_sms);
   const int nthr = 32 * (fbt::CTRL_WARPS + 2 * fbt::GWT);
-  fbt::fused_block_t_kernel<1, 6, 2, true, true><<<grid, nthr, b.s_smem, st>>>(b.s_tmImg, b.s_tmWe, b.s_tmWp, q);
+  launch_chain(ctx->pdl_on, fbt::fused_block_t_kernel<1, 6, 2, true, true>, dim3(grid), dim3(nthr), b.s_smem, st, b.s_tmImg, b.s_tmWe, b.s_tmWp, q);
   CK_LAUNCH("fused_block_t_kernel<stem>");
   return SPEF_OK;
 }
@@ -1343,7 +1366,7 @@ static int launch_dw_project(spef_ctx* ctx, Block& b, const void* hidden, const 
   q.B = B; q.wdw = b.dp_wdw; q.bias = pj.bias; q.residual = pj.residual ? (const bf16*)res : nullptr; q.out = (bf16*)out;
   const long long tiles = (long long)B * q.tiles_y;
   const int grid = (int)(tiles < ctx->num_sms ? tiles : ctx->num_sms);
-  dwp::dw_project_kernel<<<grid, dwp::NT, b.dp_smem, st>>>(b.dp_tmX, b.dp_tmW, q);
+  launch_chain(ctx->pdl_on, dwp::dw_project_kernel, dim3(grid), dim3(dwp::NT), b.dp_smem, st, b.dp_tmX, b.dp_tmW, q);
   CK_LAUNCH("dw_project_kernel");
   return SPEF_OK;
 }
@@ -1428,6 +1451,7 @@ static int check_ready(spef_ctx* ctx, int B, const char* who) {
   if (!ctx) return SPEF_ERR_INVALID;
   if (!ctx->finalized) return fail(ctx, SPEF_ERR_STATE, "%s: weights not finalised (spef_load_tensor + spef_finalize_weights first)", who);
   if (B < 1 || B > ctx->cfg.max_batch) return fail(ctx, SPEF_ERR_INVALID, "%s: batch %d outside [1, max_batch=%d]", who, B, ctx->cfg.max_batch);
+  ctx->pdl_on = false;   // single-launch entry points: plain stream order (forward_internal decides for the chain)
   return SPEF_OK;
 }
 
@@ -1470,12 +1494,13 @@ static int launch_conv_pool(spef_ctx* ctx, Layer& l, const void* in, void* poole
     if (!tc::make_tmap_2d(ctx->encode, &ctx->cp_tmX, in, false, (long long)B * p.HW, l.cin, l.cin, p.ipt * p.HW)) return fail(ctx, SPEF_ERR_CUDA, "cuTensorMapEncodeTiled(X) failed for the conv + pool kernel");
     ctx->cp_x_ptr = in; ctx->cp_x_batch = B;
   }
-  cpool::conv_pool_kernel<<<p.n_ct * p.cpc, cpool::NT, smem, st>>>(ctx->cp_tmW, ctx->cp_tmX, p);
+  launch_chain(ctx->pdl_on, cpool::conv_pool_kernel, dim3(p.n_ct * p.cpc), dim3(cpool::NT), smem, st, ctx->cp_tmW, ctx->cp_tmX, p);
   CK_LAUNCH("conv_pool_kernel");
   return SPEF_OK;
 }
 
 static int forward_internal(spef_ctx* ctx, const float* images, int B, cudaStream_t st, float* layer_ms) {
+  ctx->pdl_on = ctx->pdl && B <= ctx->pdl_max_batch;
   cudaEvent_t* ev = nullptr;
   const int nl = (int)ctx->layers.size();
   if (layer_ms) {

@@ -678,3 +678,27 @@ def test_conv_pool_kernel_is_bit_identical_to_two_launches(sd, monkeypatch):
         np.testing.assert_array_equal(o1, o0)
         np.testing.assert_array_equal(p1, p0)
     assert outs["0"][1] - outs["1"][1] == 3, outs      # one launch fewer per forward
+
+
+def test_programmatic_dependent_launch_changes_no_bit(sd, monkeypatch):
+    """Small batches launch the forward chain with programmatic stream serialization (every tcgen05 / TMA kernel does its set-up, then
+    griddepcontrol.wait before it touches the previous kernel's output; csrc/common.cuh): logits bit-identical to plain stream order
+    (SPEF_PDL=0), directly and through the replayed evaluation graph, repeated to give a missing wait a chance to show."""
+    x = synthetic.synthetic_images(5, seed=21)
+    tg = synthetic.synthetic_targets(5)
+    qt, tt = torch.as_tensor(tg["ori"]).float().cuda(), torch.as_tensor(tg["pos"]).float().cuda()
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("SPEF_PDL", mode)
+        eng = _engine(sd, "bf16")
+        eng.set_ori_histogram(O.ori_histogram(12)[0])
+        outs = [[t.cpu().numpy() for t in eng.forward(x)] for _ in range(6)]
+        xd = x.cuda()
+        pers = [eng.eval_batch(xd, qt, tt, want_per_image=True).cpu().numpy() for _ in range(6)]   # direct, then captured + replayed
+        res[mode] = (outs, pers)
+        eng.close()
+    for a, b in zip(res["1"][0], res["0"][0]):
+        np.testing.assert_array_equal(a[0], b[0])
+        np.testing.assert_array_equal(a[1], b[1])
+    for a, b in zip(res["1"][1], res["0"][1]):
+        np.testing.assert_array_equal(a, b)
