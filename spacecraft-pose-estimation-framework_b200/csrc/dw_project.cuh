@@ -1,4 +1,4 @@
-// Depthwise 3x3 (stride 1, BN folded, ReLU) fused into the project 1x1 conv of an InvertedResidual block:
+// Depthwise 3x3 (stride 1, or 2 for the one stride-2 block that needs it; BN folded, ReLU) fused into the project 1x1 conv of an InvertedResidual block:
 //   y = [x +] Wp * relu(dw3x3(h) + bd) + bp        (reference: src/modeling/common/pytorch_layers.py:82-98)
 // for the wide blocks (hidden width 576 / 960) whose weights do not fit next to the tiles of the single-kernel block
 // (fused_block_t.cuh).  Per-layer kernels move the depthwise output through HBM twice (write + read, 2 x 106 MB at
@@ -34,7 +34,9 @@ constexpr int A_BYTES = 128 * 128;          // one K chunk of the A operand: 128
 constexpr int WDW_CHUNK_FLOATS = 10 * 64;   // per K chunk: 9 taps + bias, 64 channels each
 
 struct DwpParams {
-  int B, H, W, C, N;            // hidden map (= output map, stride 1), hidden channels (GEMM K), project outputs
+  int B, H, W, C, N;            // OUTPUT map (= the hidden map when S = 1), hidden channels (GEMM K), project outputs
+  int S;                        // depthwise stride 1 | 2 (the hidden map is S*H - (S-1)... x S*W: see the host plan)
+  int WB;                       // pixels per row of the input box: W + 2 (S = 1) | 2 W + 1 (S = 2); box rows: TH + 2 | 2 TH + 1
   int TH, tiles_y, n_px;        // tile = TH full-width rows; n_px = TH * W <= 128
   int k_chunks;                 // C / 64
   int in_stages, ab_stages, w_stages, acc_stages, acc_stride;   // ab_stages: A-operand stages; w_stages: project-weight chunk stages
@@ -59,6 +61,14 @@ struct ProdCtx {
   int num_tiles;
 };
 
+// INVARIANT (host plan): in_stages is a multiple of G, so an input stage always belongs to the same producer group.  A parity wait
+// cannot tell phase n from phase n + 2: with three input stages and two groups a group waited for item k on a stage whose previous
+// item k - 3 belonged to the OTHER group -- TMA loads complete out of order (an L2 hit overtakes a DRAM miss), so with fast producers
+// (the small stride-2 tiles at batch 256, hidden tensor larger than the L2) the wait could pass before item k - 3 had even landed: the
+// group read a stale stage and released it early (sporadic wrong tiles, then a fault; found when the stride-2 plan was added, latent in
+// the 960-channel plan, which had three input stages).  (Waiting for the previous phase first does not work either: when the item has
+// already landed that wait is for the NEXT phase -- a deadlock, tried.)  The A / weight / accumulator rings are safe: their consumer
+// sees every completion, or the previous phase was awaited by the writer itself.
 // Depthwise producers.  The PROD_WARPS warps form G groups of T = 384 / G threads; group g takes the (tile, K chunk) items
 // g, g + G, ... of the CTA's sequence, so consecutive chunks are computed concurrently by different warps and every thread of
 // every warp has the same amount of work (first version: 2-row x 4-pixel tasks -- on the 5-row tiles a quarter of the producer
@@ -78,8 +88,8 @@ __device__ __forceinline__ void producer_loop(const DwpParams& p, const ProdCtx&
   const int nxs = p.W >> 1;
   const int rb = task / nxs, xs = task - rb * nxs;
   const int r0 = rb * R, x0 = xs * 2;
-  const uint32_t row_pitch = (uint32_t)((p.W + 2) * 128);
-  const uint32_t in_off = (uint32_t)((r0 * (p.W + 2) + x0) * 128 + c4 * 8);
+  const uint32_t row_pitch = (uint32_t)(p.WB * 128);
+  const uint32_t in_off = (uint32_t)((r0 * p.WB + x0) * 128 + c4 * 8);
   const uint32_t a_sw = (uint32_t)(c4 >> 1), a_lo = (uint32_t)((c4 & 1) * 8);
   const int arow0 = r0 * p.W + x0;
   const uint32_t wdw_u = c.wdw_u + (uint32_t)(c4 * 16);
@@ -148,6 +158,101 @@ __device__ __forceinline__ void producer_loop(const DwpParams& p, const ProdCtx&
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
     __syncwarp();                                                  // every lane has read its input pixels and stored its outputs
+    if (lane == 0) tc::mbar_arrive(c.ab_full + 8u * (uint32_t)as);
+    is += p.G;
+    while (is >= p.in_stages) { is -= p.in_stages; ph_in ^= 1; }
+    as += p.G;
+    while (as >= p.ab_stages) { as -= p.ab_stages; ph_ab ^= 1; }
+    kc += p.G;
+    while (kc >= p.k_chunks) { kc -= p.k_chunks; tile += gridDim.x; }
+  }
+}
+
+// Stride-2 producers (the one stride-2 block without a single-kernel plan: 576 channels, 15x24 -> 8x12).  Same task shape and the same
+// hand-offs as above; box row 0 is hidden row 2 oy0 - 1 and box column 0 hidden column -1 (TMA zero fill = the conv's padding), so
+// output (r, x) reads box rows 2r .. 2r + 2 and box columns 2x .. 2x + 2: a thread walks down 2R + 1 input rows of five pixels; an
+// even row feeds two output rows (ky = 0 of row r, ky = 2 of row r - 1), an odd one only ky = 1 of row r.  Bias first, taps in
+// row-major order like the per-layer kernel: bit-identical sums.
+template <int R>
+__device__ __forceinline__ void producer_loop_s2(const DwpParams& p, const ProdCtx& c) {
+  const int t_all = (int)threadIdx.x - 128;
+  const int T = (32 * PROD_WARPS) / p.G;
+  const int g = t_all / T, t = t_all - g * T;
+  const int lane = threadIdx.x & 31;
+  const int c4 = t & 15, task = t >> 4;
+  const int nxs = p.W >> 1;
+  const int rb = task / nxs, xs = task - rb * nxs;
+  const int r0 = rb * R, x0 = xs * 2;
+  const uint32_t row_pitch = (uint32_t)(p.WB * 128);
+  const uint32_t in_off = (uint32_t)((2 * r0 * p.WB + 2 * x0) * 128 + c4 * 8);
+  const uint32_t a_sw = (uint32_t)(c4 >> 1), a_lo = (uint32_t)((c4 & 1) * 8);
+  const int arow0 = r0 * p.W + x0;
+  const uint32_t wdw_u = c.wdw_u + (uint32_t)(c4 * 16);
+  int is = g % p.in_stages, as = g % p.ab_stages;
+  uint32_t ph_in = (uint32_t)((g / p.in_stages) & 1), ph_ab = (uint32_t)((g / p.ab_stages) & 1);
+  int kc = g;
+  for (int tile = blockIdx.x; tile < c.num_tiles;) {
+    tc::mbar_wait(c.in_full + 8u * (uint32_t)is, ph_in);
+    tc::mbar_wait(c.ab_empty + 8u * (uint32_t)as, ph_ab ^ 1);
+    const uint32_t wb = wdw_u + (uint32_t)(kc * WDW_CHUNK_FLOATS * 4);
+    uint64_t w[9][2], bv[2];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      const float4 w0 = tc::lds_f4(wb + (uint32_t)k * 256u);
+      w[k][0] = f32x2(w0.x, w0.y); w[k][1] = f32x2(w0.z, w0.w);
+    }
+    {
+      const float4 b0 = tc::lds_f4(wb + 9u * 256u);
+      bv[0] = f32x2(b0.x, b0.y); bv[1] = f32x2(b0.z, b0.w);
+    }
+    const uint32_t tile_u = c.in_u + (uint32_t)is * (uint32_t)p.in_stride + in_off;
+    const uint32_t sa = c.ab_u + (uint32_t)as * (uint32_t)A_BYTES;
+    uint64_t acc[R][2][2];
+#pragma unroll
+    for (int i = 0; i < 2 * R + 1; ++i) {
+      if ((i & 1) == 0 && (i >> 1) < R) {
+#pragma unroll
+        for (int o = 0; o < 2; ++o) { acc[i >> 1][o][0] = bv[0]; acc[i >> 1][o][1] = bv[1]; }
+      }
+      const uint32_t row_u = tile_u + (uint32_t)i * row_pitch;
+      uint64_t v[5][2];
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        uint32_t ux, uy;
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(ux), "=r"(uy) : "r"(row_u + (uint32_t)(j * 128)));
+        v[j][0] = f32x2(__uint_as_float(ux << 16), __uint_as_float(ux & 0xffff0000u));
+        v[j][1] = f32x2(__uint_as_float(uy << 16), __uint_as_float(uy & 0xffff0000u));
+      }
+      if (i == 2 * R) {   // last input row is in registers: hand the input stage back before the remaining FMAs and stores
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(c.in_empty + 8u * (uint32_t)is);
+      }
+      // ky = 2 of the row above first (its last taps), then ky = 0 / 1 of the row this input row starts or continues
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int ky = i - 2 * r;
+        if (ky >= 0 && ky <= 2) {
+#pragma unroll
+          for (int o = 0; o < 2; ++o)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+              acc[r][o][0] = fma_f32x2(v[2 * o + kx][0], w[ky * 3 + kx][0], acc[r][o][0]);
+              acc[r][o][1] = fma_f32x2(v[2 * o + kx][1], w[ky * 3 + kx][1], acc[r][o][1]);
+            }
+        }
+      }
+      if (i >= 2 && (i & 1) == 0) {   // output row i / 2 - 1 has all its taps
+        const int r = (i >> 1) - 1;
+#pragma unroll
+        for (int o = 0; o < 2; ++o) {
+          const uint32_t row = (uint32_t)(arow0 + r * p.W + o);
+          const uint32_t off = row * 128u + ((a_sw ^ (row & 7u)) << 4) + a_lo;
+          asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(sa + off), "r"(dw::cvt_relu_bf16x2(acc[r][o][0])), "r"(dw::cvt_relu_bf16x2(acc[r][o][1])) : "memory");
+        }
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
     if (lane == 0) tc::mbar_arrive(c.ab_full + 8u * (uint32_t)as);
     is += p.G;
     while (is >= p.in_stages) { is -= p.in_stages; ph_in ^= 1; }
@@ -241,7 +346,7 @@ dw_project_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           tc::mbar_wait(tc::smem_u32(&in_empty[is]), ph ^ 1);
           const uint32_t fb = tc::smem_u32(&in_full[is]);
           tc::mbar_arrive_expect_tx(fb, (uint32_t)p.in_bytes);
-          dw::tma_load_4d(tc::smem_u32(in_s + (size_t)is * p.in_stride), &tmX, kc * 64, -1, ty * p.TH - 1, b, fb);
+          dw::tma_load_4d(tc::smem_u32(in_s + (size_t)is * p.in_stride), &tmX, kc * 64, -1, ty * p.TH * p.S - 1, b, fb);
           if (++is == p.in_stages) { is = 0; ph ^= 1; }
         }
         b += db; ty += dty;
@@ -302,7 +407,13 @@ dw_project_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     fbt::reg_inc<120>();
     const ProdCtx pc{tc::smem_u32(in_s), tc::smem_u32(ab_s), tc::smem_u32(wdw_s), tc::smem_u32(in_full), tc::smem_u32(in_empty),
                      tc::smem_u32(ab_full), tc::smem_u32(ab_empty), num_tiles};
-    switch (p.R) {
+    if (p.S == 2) {
+      switch (p.R) {
+        case 4: producer_loop_s2<4>(p, pc); break;
+        case 2: producer_loop_s2<2>(p, pc); break;
+        default: producer_loop_s2<1>(p, pc); break;
+      }
+    } else switch (p.R) {
       case 5: producer_loop<5>(p, pc); break;
       case 4: producer_loop<4>(p, pc); break;
       case 3: producer_loop<3>(p, pc); break;

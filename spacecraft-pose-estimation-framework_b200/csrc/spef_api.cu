@@ -127,6 +127,8 @@ struct spef_ctx {
   int fb_gw = 4;       // warps per worker group of the fused kernel (SPEF_FB_GW = 4 | 8; 4 measured faster: more registers per thread)
   int dwp_enable = 1;  // SPEF_DWP=0: per-layer kernels for the blocks without a single-kernel plan
   int dwp_w_stages = 0; // SPEF_DWP_WST (developer A/B): cap on the project-weight ring depth of the depthwise -> project kernel
+  int dwp_opt_skip = 0;
+  int dwp_s2_box_kb = 60;  // stride-2 depthwise -> project: largest input box (SPEF_DWP_S2_BOX_KB)
   int dwp_force = 0;   // SPEF_DWP_FORCE=1 (tests): expand GEMM + depthwise->project kernel for every block it can run, ahead of the single-kernel plans
   int fb_max_cin = 64; // fuse blocks with Cin <= this (SPEF_FB_MAX_CIN); wider blocks measured faster as three kernels
   int stem_patch = 1;  // stem input patches staged by TMA (SPEF_STEM_PATCH=0: gather the 27 taps from global memory)
@@ -430,6 +432,8 @@ extern "C" int spef_create(spef_ctx** out, const spef_config* cfg) {
   if (getenv("SPEF_HEAD_WIDE")) ctx->head_wide = 1;
   if (const char* e = getenv("SPEF_POOL_FUSE")) ctx->pool_fuse = atoi(e) ? 1 : 0;
   if (const char* e = getenv("SPEF_PDL")) ctx->pdl = atoi(e) ? 1 : 0;
+  if (const char* e = getenv("SPEF_DWP_OPT_SKIP")) ctx->dwp_opt_skip = atoi(e);
+  if (const char* e = getenv("SPEF_DWP_S2_BOX_KB")) ctx->dwp_s2_box_kb = atoi(e);
   if (const char* e = getenv("SPEF_PDL_MAX_BATCH")) ctx->pdl_max_batch = atoi(e);
   if (const char* e5 = getenv("SPEF_TEMPORAL_GRAPH")) ctx->temporal_graph = atoi(e5) ? 1 : 0;
   if (const char* e5 = getenv("SPEF_TEMPORAL_GRAPH_MAX")) ctx->temporal_graph_max_streams = atoi(e5);
@@ -808,7 +812,8 @@ static int plan_stem_block(spef_ctx* ctx) {
   return SPEF_OK;
 }
 
-// Depthwise -> project plan (dw_project.cuh): stride-1 blocks with an expand conv whose hidden width is a multiple of 64.
+// Depthwise -> project plan (dw_project.cuh): blocks with an expand conv whose hidden width is a multiple of 64 (stride 1, and stride 2
+// without a skip connection).
 static int plan_blocks_dp(spef_ctx* ctx) {
   std::vector<Layer>& L = ctx->layers;
   for (Block& b : ctx->blocks) {
@@ -818,32 +823,41 @@ static int plan_blocks_dp(spef_ctx* ctx) {
     if (b.i_exp < 0) continue;
     const Layer& d = L[b.i_dw];
     const Layer& pj = L[b.i_proj];
-    if (d.stride != 1 || d.cin % 64 != 0 || pj.cout % 32 != 0 || d.wout % 4 != 0 || d.wout > 128) continue;
+    if ((d.stride != 1 && d.stride != 2) || d.cin % 64 != 0 || pj.cout % 32 != 0 || d.wout % 4 != 0 || d.wout > 128) continue;
+    if (d.stride == 2 && (pj.residual || d.hout != (d.hin + 1) / 2 || d.wout != (d.win + 1) / 2)) continue;
     dwp::DwpParams& q = b.dprm;
     memset(&q, 0, sizeof(q));
-    q.H = d.hin; q.W = d.win; q.C = d.cin; q.N = pj.cout;
+    q.S = d.stride;
+    q.H = d.hout; q.W = d.wout; q.C = d.cin; q.N = pj.cout;
+    q.WB = (q.S == 1) ? q.W + 2 : 2 * q.W + 1;
+    // tile = TH full-width output rows, at most 128 pixels; stride 2: the input box (2 TH + 1 rows of 2 W + 1 pixels) also has to stay
+    // small enough for three stages next to the operand rings
     for (int th = 128 / q.W; th >= 1 && !q.TH; --th)
-      if (q.H % th == 0) q.TH = th;
+      if (q.H % th == 0 && (q.S == 1 || (2 * th + 1) * q.WB * 128 <= ctx->dwp_s2_box_kb * 1024 || th == 1)) q.TH = th;
     q.tiles_y = q.H / q.TH; q.n_px = q.TH * q.W; q.k_chunks = q.C / 64;
     // producer task = (4 channels, 2 columns, R rows): R the largest divisor of TH (<= 5) for which the tile's tasks fill a whole
     // number G of equal producer groups (G * tasks * 16 threads = all producer threads); group g computes the K chunks g, g + G, ...
     q.R = 0;
     for (int r = 5; r >= 1 && !q.R; --r) {
-      if (q.TH % r != 0 || q.W % 2 != 0) continue;
+      if (q.TH % r != 0 || q.W % 2 != 0 || (q.S == 2 && r != 4 && r != 2 && r != 1)) continue;
       const int threads = (q.W / 2) * (q.TH / r) * 16;
-      if (threads <= 32 * dwp::PROD_WARPS && threads % 32 == 0 && (32 * dwp::PROD_WARPS) % threads == 0) { q.R = r; q.G = 32 * dwp::PROD_WARPS / threads; }
+      if (threads <= 32 * dwp::PROD_WARPS && threads % 32 == 0 && (32 * dwp::PROD_WARPS) % threads == 0 && 32 * dwp::PROD_WARPS / threads <= 2) { q.R = r; q.G = 32 * dwp::PROD_WARPS / threads; }
     }
     if (!q.R || q.G > q.k_chunks || q.G > 2) continue;
     q.n_half = (q.N <= 256) ? 1 : 2; q.nh = q.N / q.n_half;
     if (q.nh > 256 || q.nh % 16 != 0 || q.N > 512) continue;
     q.acc_stride = q.N; q.acc_stages = (2 * q.N <= 512) ? 2 : 1;
-    q.in_bytes = (q.TH + 2) * (q.W + 2) * 128; q.in_stride = ((q.in_bytes + 1023) / 1024) * 1024;
+    q.in_bytes = ((q.S == 1) ? q.TH + 2 : 2 * q.TH + 1) * q.WB * 128; q.in_stride = ((q.in_bytes + 1023) / 1024) * 1024;
     bool found = false;
     // {A stages, project-weight stages, input stages}: a producer group holds its input stage for G chunk times, so four input boxes
     // (two of them prefetched); the weight ring is decoupled from the A stages (a deeper one, up to 6, measured no faster)
-    const int opts[10][3] = {{4, 4, 4}, {3, 4, 4}, {3, 4, 3}, {3, 3, 4}, {2, 4, 3}, {2, 3, 3}, {2, 2, 4}, {2, 2, 3}, {2, 3, 2}, {2, 2, 2}};
+    const int opts[12][3] = {{4, 4, 4}, {3, 4, 4}, {3, 4, 3}, {3, 3, 4}, {3, 3, 3}, {2, 4, 4}, {2, 4, 3}, {2, 3, 3}, {2, 2, 4}, {2, 2, 3}, {2, 3, 2}, {2, 2, 2}};
+    const int opt_skip = ctx->dwp_opt_skip;   // SPEF_DWP_OPT_SKIP (developer): skip the first n candidates
+    int oi = 0;
     for (const auto& o : opts) {
+      if (oi++ < opt_skip) continue;
       q.ab_stages = o[0]; q.w_stages = o[1]; q.in_stages = o[2];
+      if (q.in_stages % q.G != 0) continue;   // an input stage must always belong to the same producer group (dw_project.cuh: parity aliasing)
       if (ctx->dwp_w_stages > 0 && q.w_stages > ctx->dwp_w_stages) continue;
       if (dwp::smem_bytes(q) <= ctx->smem_optin) { found = true; break; }
     }
@@ -1359,7 +1373,8 @@ static int launch_dw_project(spef_ctx* ctx, Block& b, const void* hidden, const 
     b.dp_tmW_ready = true;
   }
   if (b.dp_tmX_ptr != hidden || b.dp_tmX_batch != B) {
-    if (!dw::make_tmap_nhwc(ctx->encode, &b.dp_tmX, hidden, B, q.H, q.W, q.C, 8, q.W + 2, q.TH + 2))
+    const Layer& dl = L[b.i_dw];
+    if (!dw::make_tmap_nhwc(ctx->encode, &b.dp_tmX, hidden, B, dl.hin, dl.win, q.C, 8, q.WB, (q.S == 1) ? q.TH + 2 : 2 * q.TH + 1))
       return fail(ctx, SPEF_ERR_CUDA, "cuTensorMapEncodeTiled(X) failed for the depthwise-project kernel at layer %d", b.i_dw);
     b.dp_tmX_ptr = hidden; b.dp_tmX_batch = B;
   }
