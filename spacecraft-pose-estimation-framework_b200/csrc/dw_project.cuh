@@ -39,6 +39,7 @@ struct DwpParams {
   int WB;                       // pixels per row of the input box: W + 2 (S = 1) | 2 W + 1 (S = 2); box rows: TH + 2 | 2 TH + 1
   int TH, tiles_y, n_px;        // tile = TH full-width rows; n_px = TH * W <= 128
   int k_chunks;                 // C / 64
+  int in_period;                // own items after which a producer group meets the same input stage again: in_stages / gcd(in_stages, G)
   int in_stages, ab_stages, w_stages, acc_stages, acc_stride;   // ab_stages: A-operand stages; w_stages: project-weight chunk stages
   int n_half, nh;               // N = n_half * nh: one MMA per half (nh <= 256, multiple of 16)
   int R, G;                     // producer task: R output rows x 2 columns x 4 channels; G producer groups take alternate K chunks
@@ -61,14 +62,16 @@ struct ProdCtx {
   int num_tiles;
 };
 
-// INVARIANT (host plan): in_stages is a multiple of G, so an input stage always belongs to the same producer group.  A parity wait
-// cannot tell phase n from phase n + 2: with three input stages and two groups a group waited for item k on a stage whose previous
-// item k - 3 belonged to the OTHER group -- TMA loads complete out of order (an L2 hit overtakes a DRAM miss), so with fast producers
-// (the small stride-2 tiles at batch 256, hidden tensor larger than the L2) the wait could pass before item k - 3 had even landed: the
-// group read a stale stage and released it early (sporadic wrong tiles, then a fault; found when the stride-2 plan was added, latent in
-// the 960-channel plan, which had three input stages).  (Waiting for the previous phase first does not work either: when the item has
-// already landed that wait is for the NEXT phase -- a deadlock, tried.)  The A / weight / accumulator rings are safe: their consumer
-// sees every completion, or the previous phase was awaited by the writer itself.
+// IN_FULL.  A parity wait cannot tell phase n from phase n + 2.  With ONE in_full barrier per input stage, three stages and two producer
+// groups, a group waited for item k on a stage whose previous item k - 3 belonged to the OTHER group; TMA loads complete out of order
+// (an L2 hit overtakes a DRAM miss), so with fast producers (the small stride-2 tiles at batch 256, hidden tensor larger than the L2)
+// the wait could pass before item k - 3 had even landed: the group read a stale stage and released it early (sporadic wrong tiles,
+// then a fault; found when the stride-2 plan was added, latent in the 960-channel plan with its three input stages).  Waiting for the
+// previous phase first is no fix (when the item has already landed that wait is for the NEXT phase: deadlock, tried).  Each group
+// therefore has its OWN in_full barrier per stage -- the TMA warp arms the barrier of the group the item goes to -- so a group sees
+// every completion of the barriers it waits on; its phase flips every in_period = in_stages / gcd(in_stages, G) own items (the period
+// after which it meets the same stage again).  The A / weight / accumulator rings are safe: their consumer sees every completion, or
+// the previous phase was awaited by the writer itself.
 // Depthwise producers.  The PROD_WARPS warps form G groups of T = 384 / G threads; group g takes the (tile, K chunk) items
 // g, g + G, ... of the CTA's sequence, so consecutive chunks are computed concurrently by different warps and every thread of
 // every warp has the same amount of work (first version: 2-row x 4-pixel tasks -- on the 5-row tiles a quarter of the producer
@@ -94,10 +97,12 @@ __device__ __forceinline__ void producer_loop(const DwpParams& p, const ProdCtx&
   const int arow0 = r0 * p.W + x0;
   const uint32_t wdw_u = c.wdw_u + (uint32_t)(c4 * 16);
   int is = g % p.in_stages, as = g % p.ab_stages;
-  uint32_t ph_in = (uint32_t)((g / p.in_stages) & 1), ph_ab = (uint32_t)((g / p.ab_stages) & 1);
+  uint32_t ph_in = 0, ph_ab = (uint32_t)((g / p.ab_stages) & 1);
+  int pn = 0;                       // own items since the group's phase of its in_full barriers last flipped (see IN_FULL below)
+  const uint32_t in_full_g = c.in_full + 8u * (uint32_t)(g * MAX_IN);
   int kc = g;                       // K chunk of this group's current item (g < k_chunks: checked by the host)
   for (int tile = blockIdx.x; tile < c.num_tiles;) {
-    tc::mbar_wait(c.in_full + 8u * (uint32_t)is, ph_in);
+    tc::mbar_wait(in_full_g + 8u * (uint32_t)is, ph_in);
     tc::mbar_wait(c.ab_empty + 8u * (uint32_t)as, ph_ab ^ 1);
     const uint32_t wb = wdw_u + (uint32_t)(kc * WDW_CHUNK_FLOATS * 4);
     uint64_t w[9][2], bv[2];
@@ -160,7 +165,8 @@ __device__ __forceinline__ void producer_loop(const DwpParams& p, const ProdCtx&
     __syncwarp();                                                  // every lane has read its input pixels and stored its outputs
     if (lane == 0) tc::mbar_arrive(c.ab_full + 8u * (uint32_t)as);
     is += p.G;
-    while (is >= p.in_stages) { is -= p.in_stages; ph_in ^= 1; }
+    while (is >= p.in_stages) is -= p.in_stages;
+    if (++pn == p.in_period) { pn = 0; ph_in ^= 1; }
     as += p.G;
     while (as >= p.ab_stages) { as -= p.ab_stages; ph_ab ^= 1; }
     kc += p.G;
@@ -189,10 +195,12 @@ __device__ __forceinline__ void producer_loop_s2(const DwpParams& p, const ProdC
   const int arow0 = r0 * p.W + x0;
   const uint32_t wdw_u = c.wdw_u + (uint32_t)(c4 * 16);
   int is = g % p.in_stages, as = g % p.ab_stages;
-  uint32_t ph_in = (uint32_t)((g / p.in_stages) & 1), ph_ab = (uint32_t)((g / p.ab_stages) & 1);
+  uint32_t ph_in = 0, ph_ab = (uint32_t)((g / p.ab_stages) & 1);
+  int pn = 0;                       // own items since the group's phase of its in_full barriers last flipped (see IN_FULL below)
+  const uint32_t in_full_g = c.in_full + 8u * (uint32_t)(g * MAX_IN);
   int kc = g;
   for (int tile = blockIdx.x; tile < c.num_tiles;) {
-    tc::mbar_wait(c.in_full + 8u * (uint32_t)is, ph_in);
+    tc::mbar_wait(in_full_g + 8u * (uint32_t)is, ph_in);
     tc::mbar_wait(c.ab_empty + 8u * (uint32_t)as, ph_ab ^ 1);
     const uint32_t wb = wdw_u + (uint32_t)(kc * WDW_CHUNK_FLOATS * 4);
     uint64_t w[9][2], bv[2];
@@ -255,7 +263,8 @@ __device__ __forceinline__ void producer_loop_s2(const DwpParams& p, const ProdC
     __syncwarp();
     if (lane == 0) tc::mbar_arrive(c.ab_full + 8u * (uint32_t)as);
     is += p.G;
-    while (is >= p.in_stages) { is -= p.in_stages; ph_in ^= 1; }
+    while (is >= p.in_stages) is -= p.in_stages;
+    if (++pn == p.in_period) { pn = 0; ph_in ^= 1; }
     as += p.G;
     while (as >= p.ab_stages) { as -= p.ab_stages; ph_ab ^= 1; }
     kc += p.G;
@@ -275,8 +284,8 @@ dw_project_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   float* wdw_s = reinterpret_cast<float*>(in_s + (size_t)p.in_stages * p.in_stride);
   float* bias_s = wdw_s + (size_t)p.k_chunks * WDW_CHUNK_FLOATS;
   uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + p.N);
-  uint64_t* in_full = bars;                 // [MAX_IN]   TMA -> producers
-  uint64_t* in_empty = in_full + MAX_IN;    // [MAX_IN]   producers -> TMA
+  uint64_t* in_full = bars;                 // [2][MAX_IN] TMA -> producers, one set per producer group (IN_FULL below)
+  uint64_t* in_empty = in_full + 2 * MAX_IN; // [MAX_IN]   producers -> TMA
   uint64_t* ab_full = in_empty + MAX_IN;    // [MAX_AB]   producers (A) -> MMA
   uint64_t* ab_empty = ab_full + MAX_AB;    // [MAX_AB]   MMA -> producers
   uint64_t* w_full = ab_empty + MAX_AB;     // [MAX_W]    TMA (Wp chunk) -> MMA
@@ -305,6 +314,7 @@ dw_project_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < MAX_IN; ++i) {
       tc::mbar_init(tc::smem_u32(&in_full[i]), 1);
+      tc::mbar_init(tc::smem_u32(&in_full[MAX_IN + i]), 1);
       tc::mbar_init(tc::smem_u32(&in_empty[i]), PROD_WARPS / p.G);
     }
     for (int i = 0; i < MAX_AB; ++i) {
@@ -337,17 +347,18 @@ dw_project_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   if (warp == 0) {
     // ===================== TMA: hidden-tensor boxes =====================
     if (lane == 0) {
-      int is = 0;
+      int is = 0, grp = 0;            // grp: the producer group that takes this item (items alternate between the G groups)
       uint32_t ph = 0;
       int b = (int)blockIdx.x / p.tiles_y, ty = (int)blockIdx.x % p.tiles_y;
       const int db = (int)gridDim.x / p.tiles_y, dty = (int)gridDim.x % p.tiles_y;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         for (int kc = 0; kc < p.k_chunks; ++kc) {
           tc::mbar_wait(tc::smem_u32(&in_empty[is]), ph ^ 1);
-          const uint32_t fb = tc::smem_u32(&in_full[is]);
+          const uint32_t fb = tc::smem_u32(&in_full[grp * MAX_IN + is]);
           tc::mbar_arrive_expect_tx(fb, (uint32_t)p.in_bytes);
           dw::tma_load_4d(tc::smem_u32(in_s + (size_t)is * p.in_stride), &tmX, kc * 64, -1, ty * p.TH * p.S - 1, b, fb);
           if (++is == p.in_stages) { is = 0; ph ^= 1; }
+          if (++grp == p.G) grp = 0;
         }
         b += db; ty += dty;
         if (ty >= p.tiles_y) { ty -= p.tiles_y; ++b; }

@@ -857,11 +857,15 @@ static int plan_blocks_dp(spef_ctx* ctx) {
     for (const auto& o : opts) {
       if (oi++ < opt_skip) continue;
       q.ab_stages = o[0]; q.w_stages = o[1]; q.in_stages = o[2];
-      if (q.in_stages % q.G != 0) continue;   // an input stage must always belong to the same producer group (dw_project.cuh: parity aliasing)
       if (ctx->dwp_w_stages > 0 && q.w_stages > ctx->dwp_w_stages) continue;
       if (dwp::smem_bytes(q) <= ctx->smem_optin) { found = true; break; }
     }
     if (!found) continue;
+    {
+      int a = q.in_stages, g2 = q.G;
+      while (g2) { const int t = a % g2; a = g2; g2 = t; }   // gcd(in_stages, G)
+      q.in_period = q.in_stages / a;
+    }
     b.dp_smem = dwp::smem_bytes(q);
     std::vector<float> w((size_t)q.k_chunks * dwp::WDW_CHUNK_FLOATS);
     for (int ch = 0; ch < q.C; ++ch) {
