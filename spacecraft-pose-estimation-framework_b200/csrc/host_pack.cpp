@@ -44,23 +44,28 @@ SPEF_AVX512 static inline __m512i cvt16(__m512i u) {
   const __mmask16 nan = _mm512_cmpgt_epu32_mask(_mm512_and_si512(u, _mm512_set1_epi32(0x7fffffff)), _mm512_set1_epi32(0x7f800000));
   return _mm512_mask_mov_epi32(r, nan, _mm512_or_si512(hi, _mm512_set1_epi32(0x0040)));
 }
-SPEF_AVX512 static void pack_avx512(const float* src, uint16_t* dst, size_t n) {
+template <bool NT>
+SPEF_AVX512 static void pack_avx512_t(const float* src, uint16_t* dst, size_t n) {
   size_t i = 0;
   // head: up to a 64-byte aligned destination (streaming stores need it)
   while (i < n && (reinterpret_cast<uintptr_t>(dst + i) & 63u)) { dst[i] = f2bf(reinterpret_cast<const uint32_t*>(src)[i]); ++i; }
   for (; i + 32 <= n; i += 32) {
     const __m256i lo = _mm512_cvtepi32_epi16(cvt16(_mm512_loadu_si512(src + i))), up = _mm512_cvtepi32_epi16(cvt16(_mm512_loadu_si512(src + i + 16)));
-    _mm512_stream_si512(reinterpret_cast<__m512i*>(dst + i), _mm512_inserti64x4(_mm512_castsi256_si512(lo), up, 1));
+    const __m512i v = _mm512_inserti64x4(_mm512_castsi256_si512(lo), up, 1);
+    if (NT) _mm512_stream_si512(reinterpret_cast<__m512i*>(dst + i), v); else _mm512_store_si512(reinterpret_cast<__m512i*>(dst + i), v);
   }
-  _mm_sfence();
+  if (NT) _mm_sfence();
   for (; i < n; ++i) dst[i] = f2bf(reinterpret_cast<const uint32_t*>(src)[i]);
 }
+SPEF_AVX512 static void pack_avx512(const float* src, uint16_t* dst, size_t n) { pack_avx512_t<true>(src, dst, n); }
+SPEF_AVX512 static void pack_avx512_cached(const float* src, uint16_t* dst, size_t n) { pack_avx512_t<false>(src, dst, n); }
 #endif
 
 using PackFn = void (*)(const float*, uint16_t*, size_t);
 static PackFn pick_pack() {
 #if defined(__x86_64__)
-  if (__builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw") && !getenv("SPEF_PACK_SCALAR")) return pack_avx512;
+  if (__builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw") && !getenv("SPEF_PACK_SCALAR"))
+    return getenv("SPEF_PACK_CACHED") ? pack_avx512_cached : pack_avx512;   // SPEF_PACK_CACHED (developer): plain stores instead of streaming ones
 #endif
   return pack_scalar;
 }
