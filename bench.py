@@ -536,6 +536,8 @@ def run_b200(args):
     L = len(lanes)
     per_out = [torch.empty((B, 2), dtype=torch.float32).pin_memory() for _ in range(2 * L)]
 
+    e2e_sums = []     # the accumulated sums of every e2e_loop call, in call order (packed, plain, uint8): they must be identical
+
     def e2e_loop(bufs):
         """K pipelined host-buffer steps, round-robin over the lanes (each lane double-buffers its own H2D copies); wall clock
         around submit ... wait + read of the sums, max over ranks."""
@@ -551,19 +553,22 @@ def run_b200(args):
         for i in range(2 * L):
             submit(i)
         drain()
+        for l in lanes:
+            with torch.cuda.stream(l.side_stream):
+                l.eval_reset()
         sync_all()
         t0 = time.perf_counter()
         for i in range(args.steps):
             submit(i)
         drain()
-        for l in lanes:
-            l.eval_read()
+        sums = sum(l.eval_read() for l in lanes)     # float64 accumulators of the K timed steps (the read is part of the timed region)
         sync_all()
         el = time.perf_counter() - t0
         if dist is not None:
             t = torch.tensor([el], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             el = float(t.item())
+        e2e_sums.append(sums)
         return el
 
     pack_on, pack_threads = eng.host_pack_info()
@@ -577,7 +582,8 @@ def run_b200(args):
         for l in lanes:
             l.set_host_pack(True)
         e2e_plain = {"value": world * B * args.steps / plain_s, "unit": UNIT, "h2d_bytes_per_step": int(host_images.numel() * 4 + B * 28),
-                     "d2h_bytes_per_step": int(B * 8), "note": "spef_set_host_pack(0): the float images cross the bus as they are"}
+                     "d2h_bytes_per_step": int(B * 8), "note": "spef_set_host_pack(0): the float images cross the bus as they are",
+                     "sums_equal_packed": bool(np.array_equal(e2e_sums[0], e2e_sums[1]))}
     # same loop with uint8 pixels (the input side of the path: ToTensor's /255 moves into the stem; 4x fewer H2D bytes)
     e2e_u8 = None
     if args.precision == "bf16" and args.pw_impl == 0:
@@ -589,7 +595,7 @@ def run_b200(args):
         for l in lanes:
             l.set_image_dtype(torch.float32)
         e2e_u8 = {"value": world * B * args.steps / u8_s, "unit": UNIT, "h2d_bytes_per_step": int(u8a.numel() + B * 28),
-                  "d2h_bytes_per_step": int(B * 8), "note": "uint8 host images (spef_set_image_dtype(SPEF_IMG_U8)); results bit-identical to float images"}
+                  "d2h_bytes_per_step": int(B * 8), "note": "uint8 host images (spef_set_image_dtype(SPEF_IMG_U8)); results bit-identical to float images of the same pixels"}
     # the H2D roof this end-to-end number runs against: a plain cudaMemcpyAsync of the same pinned 283 MB buffer, rank 0 alone and
     # all ranks at once (on a shared host the concurrent figure is what caps N-GPU end-to-end scaling, not the kernels)
     roof_alone, roof_conc = h2d_roof(host_images, dev, dist)
