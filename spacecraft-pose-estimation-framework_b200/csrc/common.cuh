@@ -55,7 +55,11 @@ template <> struct Vec8<float> {
 // Programmatic dependent launch (the forward chain is launched with cudaLaunchAttributeProgrammaticStreamSerialization, spef_api.cu):
 // a kernel lets its successor start launching at once and does its own set-up (barrier init, TMEM allocation, tensor-map prefetch,
 // bias staging -- nothing that depends on the predecessor's output) before it waits for the predecessor grid to have completed and
-// flushed.  Both instructions are no-ops in a kernel launched without the attribute.
+// flushed.  Both instructions are no-ops in a kernel launched without the attribute.  The explicit trigger is a per-launch choice
+// (`pdl_early` in every kernel's parameter block): with it the successor's CTAs take every SM a finished CTA leaves and wait there --
+// right for a few-image step whose grids leave SMs idle anyway, wrong at batch 256 where the other lane's kernel would have filled
+// that tail (measured -1.8 %); without it the successor is released when the last CTA exits, which still hides its launch latency
+// (+1.4 % at batch 256 over plain stream order).
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 

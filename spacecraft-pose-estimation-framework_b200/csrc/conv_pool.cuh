@@ -35,6 +35,7 @@ struct ConvPoolParams {
   int n_ct, cpc;       // channel tiles (C / 128), CTAs per channel tile
   int x_stages;
   int relu;
+  int pdl_early;       // trigger the dependent launch at once (common.cuh)
 };
 
 __host__ __device__ inline int w_bytes(int K) { return ((K + 63) / 64) * 128 * 128; }
@@ -44,7 +45,7 @@ inline size_t smem_bytes(const ConvPoolParams& p) { return 1024 + (size_t)w_byte
 __global__ void __launch_bounds__(NT, 1)
 conv_pool_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX, const ConvPoolParams p) {
   using namespace tc;
-  pdl_launch_dependents();   // the next kernel of the chain may start its own set-up (common.cuh)
+  if (p.pdl_early) pdl_launch_dependents();   // the next kernel of the chain may start its own set-up now (common.cuh)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int k_chunks = (p.K + 63) / 64;

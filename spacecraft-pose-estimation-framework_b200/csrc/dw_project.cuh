@@ -39,6 +39,7 @@ struct DwpParams {
   int WB;                       // pixels per row of the input box: W + 2 (S = 1) | 2 W + 1 (S = 2); box rows: TH + 2 | 2 TH + 1
   int TH, tiles_y, n_px;        // tile = TH full-width rows; n_px = TH * W <= 128
   int k_chunks;                 // C / 64
+  int pdl_early;                // trigger the dependent launch at once (common.cuh)
   int in_period;                // own items after which a producer group meets the same input stage again: in_stages / gcd(in_stages, G)
   int in_stages, ab_stages, w_stages, acc_stages, acc_stride;   // ab_stages: A-operand stages; w_stages: project-weight chunk stages
   int n_half, nh;               // N = n_half * nh: one MMA per half (nh <= 256, multiple of 16)
@@ -274,7 +275,7 @@ __device__ __forceinline__ void producer_loop_s2(const DwpParams& p, const ProdC
 
 __global__ void __launch_bounds__(NT, 1)
 dw_project_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const DwpParams p) {
-  pdl_launch_dependents();   // the next kernel of the chain may start its own set-up (common.cuh)
+  if (p.pdl_early) pdl_launch_dependents();   // the next kernel of the chain may start its own set-up now (common.cuh)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int abs_ = A_BYTES, ws_ = w_stride(p);

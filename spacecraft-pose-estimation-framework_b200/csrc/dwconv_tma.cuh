@@ -23,6 +23,7 @@ struct DwParams {
   int THI, TWI;      // input box rows / cols = (T-1)*S + 3
   int tiles_y, tiles_x, nchunks;
   int relu;
+  int pdl_early;     // trigger the dependent launch at once (common.cuh)
 };
 
 __device__ __forceinline__ void tma_load_4d(uint32_t smem_dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar) {
@@ -56,7 +57,7 @@ dwconv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmX, const float* __res
                      bf16* __restrict__ out, const DwParams p) {
   constexpr int NT = 32 * CV;
   constexpr int NCOLS = (TX - 1) * S + 3;
-  pdl_launch_dependents();   // the next kernel of the chain may start its own set-up (common.cuh)
+  if (p.pdl_early) pdl_launch_dependents();   // the next kernel of the chain may start its own set-up now (common.cuh)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
   const int tile_bytes = p.THI * p.TWI * CV * 16;               // TMA transaction size (full box, OOB included)

@@ -96,6 +96,7 @@ struct FbtParams {
   int patch_w;         // patch columns (104 f32 | 128 u8) and the patch column of input column 2 ox0 - 1 ... see the producer
   int patch_x0;        // pixels between the patch origin and input column 2 * ox0 (4 f32 | 16 u8: the innermost TMA coordinate stays 16-byte aligned)
   int patch_stages, patch_stride;
+  int pdl_early;       // trigger the dependent launch at once (common.cuh)
   long long* trace;
 };
 
@@ -234,7 +235,7 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   constexpr int GT = 32 * GW;
   constexpr int TW = (S == 1) ? 12 : 6;           // output columns of a tile
   constexpr int TWI = (TW - 1) * S + 3;           // 14 | 13 input columns: one tcgen05.ld.x16 per pixel row
-  pdl_launch_dependents();   // the next kernel of the chain may start its own set-up (common.cuh)
+  if (p.pdl_early) pdl_launch_dependents();   // the next kernel of the chain may start its own set-up now (common.cuh)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int xsb = x_stage_bytes(STEM ? 2 : p.kc_in, p.n_px);

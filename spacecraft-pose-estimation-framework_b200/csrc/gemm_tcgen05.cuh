@@ -37,6 +37,7 @@ struct GemmParams {
   int store_mode;      // 0: padded smem staging + coalesced st.global by the epilogue threads; 1: swizzled staging + TMA store
   void* out;           // D (copy-out mode)
   int ldd;             // row pitch of D in elements
+  int pdl_early;       // trigger the dependent launch at once (common.cuh)
   long long* trace;    // debug: clock64 timestamps of CTA 0 (nullptr in production)
   // im2col producer (stem as an implicit GEMM): image [B,3,H,W] f32 NCHW, output pixels [B,Ho,Wo]
   const float* img;

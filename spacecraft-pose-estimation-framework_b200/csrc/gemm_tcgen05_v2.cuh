@@ -102,7 +102,7 @@ __device__ __forceinline__ uint32_t relu_bf16x2(uint32_t v) {
 template <bool OUT_F32, int NDG, int NSW, int PROD>
 __global__ void __launch_bounds__(128 + 128 * PROD + 128 * NDG + 32 * NSW, 1)
 pw_gemm_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmParams p) {
-  pdl_launch_dependents();   // the next kernel of the chain may start its own set-up (common.cuh)
+  if (p.pdl_early) pdl_launch_dependents();   // the next kernel of the chain may start its own set-up now (common.cuh)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int block_n = p.block_n;

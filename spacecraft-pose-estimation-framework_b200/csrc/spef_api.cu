@@ -149,11 +149,12 @@ struct spef_ctx {
   int fb_debug_skip = 0;   // SPEF_FB_DEBUG_SKIP: timing experiments of the staged fused kernel (wrong results)
   int fbt_no_stack = 0;    // SPEF_FBT_NO_STACK=1: no strip stacking in the channel-lane plan
   int head_wide = 0;       // SPEF_HEAD_WIDE=1: 256-column tiles for the head GEMM
-  // Programmatic dependent launch along the forward chain (common.cuh), for batches that leave SMs idle (SPEF_PDL=0: never; SPEF_PDL_MAX_BATCH).
-  // Measured: one stream of single frames 0.292 -> 0.280 ms, 64 streams 88.9 k -> 93.9 k frames/s; at batch 256 the waiting successor
-  // takes the SMs the other lane's kernel would have filled the tail with: 166.8 k -> 164.8 k images/s, hence the batch limit.
+  // Programmatic dependent launch along the forward chain (common.cuh; SPEF_PDL=0: plain stream order).  The kernels trigger their
+  // successor at once only for batches that leave SMs idle (SPEF_PDL_MAX_BATCH).  Measured: one stream of single frames 0.292 -> 0.278 ms,
+  // 64 streams 88.5 k -> 94.6 k frames/s; at batch 256 the early trigger costs 1.8 % (the waiting successor takes the SMs the other
+  // lane's kernel would have filled the tail with) while the attribute alone gains 1.4 % (166.5 k -> 168.8 k images/s).
   int pdl = 1, pdl_max_batch = 96;
-  bool pdl_on = false;     // this call's launches (set per entry point from the batch)
+  bool pdl_on = false, pdl_early = false;   // this call's launches: attribute / explicit early trigger (set per entry point from the batch)
   int pool_fuse = 1;       // last 1x1 conv + global average pool as one kernel (conv_pool.cuh); SPEF_POOL_FUSE=0: two launches
   CUtensorMap cp_tmW, cp_tmX;
   bool cp_w_ready = false;
@@ -1123,8 +1124,10 @@ static int launch_cuda_core_layer(spef_ctx* ctx, const Layer& l, const void* in,
 }
 
 template <int S, int CV, int TX = 4>
-static void launch_dw_inst(bool pdl, const CUtensorMap& tm, const Layer& l, bf16* out, int grid, size_t smem, cudaStream_t st) {
-  launch_chain(pdl, dw::dwconv3x3_tma_kernel<S, CV, TX>, dim3(grid), dim3(32 * CV), smem, st, tm, (const float*)l.w_f32, (const float*)l.bias, out, l.dwp);
+static void launch_dw_inst(bool pdl, bool pdl_early, const CUtensorMap& tm, const Layer& l, bf16* out, int grid, size_t smem, cudaStream_t st) {
+  dw::DwParams q = l.dwp;
+  q.pdl_early = pdl_early ? 1 : 0;
+  launch_chain(pdl, dw::dwconv3x3_tma_kernel<S, CV, TX>, dim3(grid), dim3(32 * CV), smem, st, tm, (const float*)l.w_f32, (const float*)l.bias, out, q);
 }
 
 static int launch_dw_tma_layer(spef_ctx* ctx, Layer& l, const void* in, void* out, int B, cudaStream_t st, bool cached_maps) {
@@ -1147,15 +1150,15 @@ static int launch_dw_tma_layer(spef_ctx* ctx, Layer& l, const void* in, void* ou
   const size_t smem = dw::smem_bytes(l.dwp, l.dw_cv);
   bf16* o = (bf16*)out;
   if (l.stride == 1) {
-    if (l.dw_cv == 8 && l.dw_tx == 3) launch_dw_inst<1, 8, 3>(ctx->pdl_on, *tm, l, o, grid, smem, st);
-    else if (l.dw_cv == 8) launch_dw_inst<1, 8>(ctx->pdl_on, *tm, l, o, grid, smem, st);
-    else if (l.dw_cv == 6) launch_dw_inst<1, 6>(ctx->pdl_on, *tm, l, o, grid, smem, st);
-    else launch_dw_inst<1, 4>(ctx->pdl_on, *tm, l, o, grid, smem, st);
+    if (l.dw_cv == 8 && l.dw_tx == 3) launch_dw_inst<1, 8, 3>(ctx->pdl_on, ctx->pdl_early, *tm, l, o, grid, smem, st);
+    else if (l.dw_cv == 8) launch_dw_inst<1, 8>(ctx->pdl_on, ctx->pdl_early, *tm, l, o, grid, smem, st);
+    else if (l.dw_cv == 6) launch_dw_inst<1, 6>(ctx->pdl_on, ctx->pdl_early, *tm, l, o, grid, smem, st);
+    else launch_dw_inst<1, 4>(ctx->pdl_on, ctx->pdl_early, *tm, l, o, grid, smem, st);
   } else {
-    if (l.dw_cv == 8 && l.dw_tx == 3) launch_dw_inst<2, 8, 3>(ctx->pdl_on, *tm, l, o, grid, smem, st);
-    else if (l.dw_cv == 8) launch_dw_inst<2, 8>(ctx->pdl_on, *tm, l, o, grid, smem, st);
-    else if (l.dw_cv == 6) launch_dw_inst<2, 6>(ctx->pdl_on, *tm, l, o, grid, smem, st);
-    else launch_dw_inst<2, 4>(ctx->pdl_on, *tm, l, o, grid, smem, st);
+    if (l.dw_cv == 8 && l.dw_tx == 3) launch_dw_inst<2, 8, 3>(ctx->pdl_on, ctx->pdl_early, *tm, l, o, grid, smem, st);
+    else if (l.dw_cv == 8) launch_dw_inst<2, 8>(ctx->pdl_on, ctx->pdl_early, *tm, l, o, grid, smem, st);
+    else if (l.dw_cv == 6) launch_dw_inst<2, 6>(ctx->pdl_on, ctx->pdl_early, *tm, l, o, grid, smem, st);
+    else launch_dw_inst<2, 4>(ctx->pdl_on, ctx->pdl_early, *tm, l, o, grid, smem, st);
   }
   CK_LAUNCH("dwconv3x3_tma_kernel");
   return SPEF_OK;
@@ -1169,7 +1172,7 @@ static int launch_stem_tcgen05(spef_ctx* ctx, Layer& l, const void* images, void
   tc::GemmParams p;
   memset(&p, 0, sizeof(p));
   p.bias = l.bias; p.residual = nullptr; p.M = B * l.hout * l.wout; p.N = 32; p.K = 32; p.block_n = 32; p.num_stages = l.stages; p.relu = 1;
-  p.store_mode = 0; p.out = out; p.ldd = 32; p.trace = nullptr;
+  p.store_mode = 0; p.out = out; p.ldd = 32; p.trace = nullptr; p.pdl_early = 0;
   p.img_u8 = ctx->image_u8;
   p.img = (const float*)images; p.img_h = l.hin; p.img_w = l.win; p.out_h = l.hout; p.out_w = l.wout;
   // patch mode: 2 x 64 output-pixel tiles whose input patch is staged by TMA (needs exact tiling and 16-byte image rows)
@@ -1216,7 +1219,7 @@ static int launch_tcgen05_layer(spef_ctx* ctx, Layer& l, const void* in, const v
   tc::GemmParams p;
   memset(&p, 0, sizeof(p));
   p.bias = l.bias; p.residual = (const bf16*)res; p.M = M; p.N = N; p.K = K; p.block_n = l.block_n; p.num_stages = l.stages; p.relu = l.relu;
-  p.store_mode = 0; p.out = out; p.ldd = N;
+  p.store_mode = 0; p.out = out; p.ldd = N; p.pdl_early = ctx->pdl_early ? 1 : 0;
   p.img = nullptr; p.img_h = p.img_w = p.out_h = p.out_w = 0; p.img_u8 = 0;
   const bool trace = ctx->trace_dev && (&l == &ctx->layers[ctx->trace_layer < (int)ctx->layers.size() && ctx->trace_layer >= 0 ? ctx->trace_layer : 0]) && ctx->trace_layer >= 0;
   p.trace = nullptr;
@@ -1284,6 +1287,7 @@ static int launch_fused_block_t(spef_ctx* ctx, Block& b, const void* in, void* o
   q.x = (const bf16*)in; q.y = (bf16*)out; q.B = B; q.aux = b.t_aux; q.bp = L[b.i_proj].bias;
   const bool trace = ctx->trace_dev && ctx->fb_trace_block >= 0 && &b == &ctx->blocks[ctx->fb_trace_block < (int)ctx->blocks.size() ? ctx->fb_trace_block : 0];
   q.trace = trace ? ctx->trace_dev : nullptr;
+  q.pdl_early = ctx->pdl_early ? 1 : 0;
   if (trace) cudaMemsetAsync(ctx->trace_dev, 0, 256 * 16 * sizeof(long long), st);
   const long long tiles = (long long)B * q.tiles_y * q.tiles_x;
   if (tiles >= (1 << 22)) return fail(ctx, SPEF_ERR_UNSUPPORTED, "fused block: %lld tiles exceed the 2^22 limit of the tile index arithmetic", tiles);
@@ -1357,6 +1361,7 @@ static int launch_stem_block(spef_ctx* ctx, const void* images, void* out, int B
     b.s_img_ptr = images; b.s_img_batch = B; b.s_img_u8 = ctx->image_u8;
   }
   q.x = nullptr; q.y = (bf16*)out; q.B = B; q.aux = b.s_aux; q.bp = L[b.i_proj].bias; q.trace = nullptr;
+  q.pdl_early = ctx->pdl_early ? 1 : 0;
   const long long tiles = (long long)B * q.tiles_y * q.tiles_x;
   if (tiles >= (1 << 22)) return fail(ctx, SPEF_ERR_UNSUPPORTED, "fused stem: %lld tiles exceed the 2^22 limit of the tile index arithmetic", tiles);
   const int grid = (int)(tiles < ctx->num_sms ? tiles : ctx->num_sms);
@@ -1382,6 +1387,7 @@ static int launch_dw_project(spef_ctx* ctx, Block& b, const void* hidden, const 
       return fail(ctx, SPEF_ERR_CUDA, "cuTensorMapEncodeTiled(X) failed for the depthwise-project kernel at layer %d", b.i_dw);
     b.dp_tmX_ptr = hidden; b.dp_tmX_batch = B;
   }
+  q.pdl_early = ctx->pdl_early ? 1 : 0;
   q.B = B; q.wdw = b.dp_wdw; q.bias = pj.bias; q.residual = pj.residual ? (const bf16*)res : nullptr; q.out = (bf16*)out;
   const long long tiles = (long long)B * q.tiles_y;
   const int grid = (int)(tiles < ctx->num_sms ? tiles : ctx->num_sms);
@@ -1470,7 +1476,7 @@ static int check_ready(spef_ctx* ctx, int B, const char* who) {
   if (!ctx) return SPEF_ERR_INVALID;
   if (!ctx->finalized) return fail(ctx, SPEF_ERR_STATE, "%s: weights not finalised (spef_load_tensor + spef_finalize_weights first)", who);
   if (B < 1 || B > ctx->cfg.max_batch) return fail(ctx, SPEF_ERR_INVALID, "%s: batch %d outside [1, max_batch=%d]", who, B, ctx->cfg.max_batch);
-  ctx->pdl_on = false;   // single-launch entry points: plain stream order (forward_internal decides for the chain)
+  ctx->pdl_on = false; ctx->pdl_early = false;   // single-launch entry points: plain stream order (forward_internal decides for the chain)
   return SPEF_OK;
 }
 
@@ -1493,6 +1499,7 @@ static bool conv_pool_ok(const spef_ctx* ctx, int i) {
 static int launch_conv_pool(spef_ctx* ctx, Layer& l, const void* in, void* pooled, int B, cudaStream_t st) {
   cpool::ConvPoolParams p;
   memset(&p, 0, sizeof(p));
+  p.pdl_early = ctx->pdl_early ? 1 : 0;
   p.bias = l.bias; p.out = (bf16*)pooled; p.B = B; p.HW = l.hout * l.wout; p.K = l.cin; p.C = l.cout; p.relu = l.relu;
   p.ipt = conv_pool_ipt(l);
   p.n_ct = l.cout / 128;
@@ -1519,7 +1526,8 @@ static int launch_conv_pool(spef_ctx* ctx, Layer& l, const void* in, void* poole
 }
 
 static int forward_internal(spef_ctx* ctx, const float* images, int B, cudaStream_t st, float* layer_ms) {
-  ctx->pdl_on = ctx->pdl && B <= ctx->pdl_max_batch;
+  ctx->pdl_on = ctx->pdl != 0;
+  ctx->pdl_early = ctx->pdl && B <= ctx->pdl_max_batch;
   cudaEvent_t* ev = nullptr;
   const int nl = (int)ctx->layers.size();
   if (layer_ms) {

@@ -681,24 +681,28 @@ def test_conv_pool_kernel_is_bit_identical_to_two_launches(sd, monkeypatch):
 
 
 def test_programmatic_dependent_launch_changes_no_bit(sd, monkeypatch):
-    """Small batches launch the forward chain with programmatic stream serialization (every tcgen05 / TMA kernel does its set-up, then
-    griddepcontrol.wait before it touches the previous kernel's output; csrc/common.cuh): logits bit-identical to plain stream order
+    """The forward chain is launched with programmatic stream serialization (every tcgen05 / TMA kernel does its set-up, then
+    griddepcontrol.wait before it touches the previous kernel's output; csrc/common.cuh) -- with the early trigger for small batches
+    (B = 5) and without it for batches that fill the GPU (B = 128 > SPEF_PDL_MAX_BATCH): logits bit-identical to plain stream order
     (SPEF_PDL=0), directly and through the replayed evaluation graph, repeated to give a missing wait a chance to show."""
-    x = synthetic.synthetic_images(5, seed=21)
-    tg = synthetic.synthetic_targets(5)
-    qt, tt = torch.as_tensor(tg["ori"]).float().cuda(), torch.as_tensor(tg["pos"]).float().cuda()
     res = {}
     for mode in ("1", "0"):
         monkeypatch.setenv("SPEF_PDL", mode)
-        eng = _engine(sd, "bf16")
+        eng = _engine(sd, "bf16", max_batch=128)
         eng.set_ori_histogram(O.ori_histogram(12)[0])
-        outs = [[t.cpu().numpy() for t in eng.forward(x)] for _ in range(6)]
-        xd = x.cuda()
-        pers = [eng.eval_batch(xd, qt, tt, want_per_image=True).cpu().numpy() for _ in range(6)]   # direct, then captured + replayed
-        res[mode] = (outs, pers)
+        res[mode] = []
+        for B in (5, 128):
+            x = synthetic.synthetic_images(min(B, 8), seed=21).repeat((B + 7) // 8, 1, 1, 1)[:B].contiguous()
+            tg = synthetic.synthetic_targets(B)
+            qt, tt = torch.as_tensor(tg["ori"]).float().cuda(), torch.as_tensor(tg["pos"]).float().cuda()
+            outs = [[t.cpu().numpy() for t in eng.forward(x)] for _ in range(4)]
+            xd = x.cuda()
+            pers = [eng.eval_batch(xd, qt, tt, want_per_image=True).cpu().numpy() for _ in range(5)]   # direct, then captured + replayed
+            res[mode].append((outs, pers))
         eng.close()
-    for a, b in zip(res["1"][0], res["0"][0]):
-        np.testing.assert_array_equal(a[0], b[0])
-        np.testing.assert_array_equal(a[1], b[1])
-    for a, b in zip(res["1"][1], res["0"][1]):
-        np.testing.assert_array_equal(a, b)
+    for (o1, p1), (o0, p0) in zip(res["1"], res["0"]):
+        for a, b in zip(o1, o0):
+            np.testing.assert_array_equal(a[0], b[0])
+            np.testing.assert_array_equal(a[1], b[1])
+        for a, b in zip(p1, p0):
+            np.testing.assert_array_equal(a, b)
