@@ -5,6 +5,6 @@ set -e
 cd "$(dirname "$0")/.."
 name=$1; shift
 mkdir -p build/var
-/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -shared -Xcompiler -fPIC "$@" \
-  -o build/var/libspef_$name.so spacecraft-pose-estimation-framework_b200/csrc/spef_api.cu
+/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -shared -Xcompiler -fPIC,-pthread "$@" \
+  -o build/var/libspef_$name.so spacecraft-pose-estimation-framework_b200/csrc/spef_api.cu spacecraft-pose-estimation-framework_b200/csrc/host_pack.cpp
 echo build/var/libspef_$name.so
