@@ -302,6 +302,7 @@ __global__ void __launch_bounds__(NW * 32, 1) decode_ori_stream_kernel(const flo
                                                                        float* __restrict__ soft_out, float* __restrict__ quat_out,
                                                                        float* __restrict__ hinv_out, int* __restrict__ argmax_out,
                                                                        uint32_t* __restrict__ flags) {
+  pdl_wait();   // launched with programmatic stream serialization (common.cuh): nothing of the previous kernel is read before this
   extern __shared__ __align__(128) unsigned char dsm[];
   float* stab = reinterpret_cast<float*>(dsm);                                            // [4][TC]
   float* ring = stab + 4 * TC;                                                            // [NW][RING][SUB]
@@ -569,6 +570,7 @@ template <bool LOGITS>
 __global__ void __launch_bounds__(HNW * 32, 1) decode_ori_half_kernel(const float* __restrict__ in, int ld, int B, int n,
                                                                       const float* __restrict__ tab, int tab_ld,
                                                                       float* __restrict__ quat_out, uint32_t* __restrict__ flags) {
+  pdl_wait();   // launched with programmatic stream serialization (common.cuh): nothing of the previous kernel is read before this
   extern __shared__ __align__(128) unsigned char dsm[];
   float* stab = reinterpret_cast<float*>(dsm);                                   // [4][HN]
   float* ring = stab + 4 * HN;                                                   // [HNW][HRING][2][HN]

@@ -151,6 +151,7 @@ __global__ void __launch_bounds__(128) decode_ori_kernel(const float* __restrict
                                                          const float4* __restrict__ qtab, float* __restrict__ soft_out,
                                                          float* __restrict__ quat_out, float* __restrict__ hinv_out,
                                                          int* __restrict__ argmax_out, uint32_t* __restrict__ flags) {
+  pdl_wait();   // launched with programmatic stream serialization (common.cuh): nothing of the previous kernel is read before this
   const int lane = threadIdx.x & 31;
   const int img0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * G;
   if (img0 >= B) return;
@@ -266,6 +267,7 @@ __global__ void __launch_bounds__(128) decode_ori_kernel(const float* __restrict
 __global__ void __launch_bounds__(128) decode_pos_kernel(const float* __restrict__ in, int ld, int B, int n, int is_logits,
                                                          const float4* __restrict__ ptab, float* __restrict__ soft_out,
                                                          float* __restrict__ pos_out, uint32_t* __restrict__ flags) {
+  pdl_wait();   // launched with programmatic stream serialization (common.cuh): nothing of the previous kernel is read before this
   const int lane = threadIdx.x & 31;
   const int img = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (img >= B) return;
@@ -327,6 +329,7 @@ __global__ void __launch_bounds__(256) score_kernel(const float* __restrict__ qp
                                                     const float* __restrict__ qt, const float* __restrict__ tt, int B,
                                                     double* __restrict__ sums, float* __restrict__ per_image,
                                                     const uint32_t* __restrict__ flags) {
+  pdl_wait();   // launched with programmatic stream serialization (common.cuh): nothing of the previous kernel is read before this
   double s[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B; i += gridDim.x * blockDim.x) {
     const float dx = __fsub_rn(tt[i * 3 + 0], tp[i * 3 + 0]);
@@ -400,6 +403,7 @@ __device__ __forceinline__ double block_sum_256(double v, double* red) {
 __global__ void __launch_bounds__(256) temporal_filter_kernel(const float* __restrict__ cur, int n, float* __restrict__ state,
                                                               int* __restrict__ has_state, float n_coef, float alpha,
                                                               float* __restrict__ out, float* __restrict__ distance) {
+  pdl_wait();   // launched with programmatic stream serialization (common.cuh): nothing of the previous kernel is read before this
   __shared__ double red[8];
   const int s = blockIdx.x;
   const float* c = cur + (size_t)s * n;
@@ -458,6 +462,7 @@ __global__ void __launch_bounds__(256) temporal_filter_kernel(const float* __res
 
 // Quaternion sign continuity (inference.py:136-144, 173-180): one thread per stream.
 __global__ void quat_continuity_kernel(float* __restrict__ quat, float* __restrict__ prev, int* __restrict__ has_prev, int S) {
+  pdl_wait();   // launched with programmatic stream serialization (common.cuh): nothing of the previous kernel is read before this
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= S) return;
   float4 q = reinterpret_cast<float4*>(quat)[s];

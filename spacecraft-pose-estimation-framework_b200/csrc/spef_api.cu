@@ -1875,7 +1875,7 @@ static int launch_decode_stream_cfg(spef_ctx* ctx, const float* in, int ld, int 
   const int grid = std::min(cdiv(B, NW), ctx->num_sms);
   auto kern = is_logits ? decode_stream_pick<NW, RING, PF, true>(amax != nullptr, hinv != nullptr)
                         : decode_stream_pick<NW, RING, PF, false>(amax != nullptr, hinv != nullptr);
-  kern<<<grid, NW * 32, smem, st>>>(in, ld, B, n, ctx->ori_tab_soa, ctx->ori_tab_ld, soft, quat, hinv, amax, flags);
+  launch_chain(ctx->pdl_on, kern, dim3(grid), dim3(NW * 32), smem, st, in, ld, B, n, (const float*)ctx->ori_tab_soa, ctx->ori_tab_ld, soft, quat, hinv, (int*)amax, flags);
   CK_LAUNCH("decode_ori_stream_kernel");
   return SPEF_OK;
 }
@@ -1891,8 +1891,8 @@ static int launch_decode_stream(spef_ctx* ctx, const float* in, int ld, int B, i
   if ((cfg == 2 || ctx->decode_cfg == 3) && ctx->decode_cfg != 2 && n <= dstream::HN && ctx->ori_tab_ld <= 2 * dstream::HN && !soft && !hinv && !amax) {
     const int pairs = (B + 1) / 2;
     const int grid = std::min(cdiv(pairs, dstream::HNW), ctx->num_sms);
-    if (is_logits) dstream::decode_ori_half_kernel<true><<<grid, dstream::HNW * 32, dstream::half_smem_bytes(), st>>>(in, ld, B, n, ctx->ori_tab_soa, ctx->ori_tab_ld, quat, flags);
-    else dstream::decode_ori_half_kernel<false><<<grid, dstream::HNW * 32, dstream::half_smem_bytes(), st>>>(in, ld, B, n, ctx->ori_tab_soa, ctx->ori_tab_ld, quat, flags);
+    if (is_logits) launch_chain(ctx->pdl_on, dstream::decode_ori_half_kernel<true>, dim3(grid), dim3(dstream::HNW * 32), dstream::half_smem_bytes(), st, in, ld, B, n, (const float*)ctx->ori_tab_soa, ctx->ori_tab_ld, quat, flags);
+    else launch_chain(ctx->pdl_on, dstream::decode_ori_half_kernel<false>, dim3(grid), dim3(dstream::HNW * 32), dstream::half_smem_bytes(), st, in, ld, B, n, (const float*)ctx->ori_tab_soa, ctx->ori_tab_ld, quat, flags);
     CK_LAUNCH("decode_ori_half_kernel");
     return SPEF_OK;
   }
@@ -1913,9 +1913,9 @@ static int decode_ori_ld(spef_ctx* ctx, const float* in, int ld, int B, int n, i
   if (vec_ok && ctx->decode_stream != 0) {
     return launch_decode_stream(ctx, in, ld, B, n, is_logits, soft, quat, hinv, amax, flags, st);
   }
-  if ((long long)B >= 32 * fill) decode_ori_kernel<32><<<cdiv(cdiv(B, 32), 4), 128, 0, st>>>(in, ld, B, n, is_logits, ctx->ori_tab, soft, quat, hinv, amax, flags);
-  else if ((long long)B >= 8 * fill) decode_ori_kernel<8><<<cdiv(cdiv(B, 8), 4), 128, 0, st>>>(in, ld, B, n, is_logits, ctx->ori_tab, soft, quat, hinv, amax, flags);
-  else decode_ori_kernel<1><<<cdiv(B, 4), 128, 0, st>>>(in, ld, B, n, is_logits, ctx->ori_tab, soft, quat, hinv, amax, flags);
+  if ((long long)B >= 32 * fill) launch_chain(ctx->pdl_on, decode_ori_kernel<32>, dim3(cdiv(cdiv(B, 32), 4)), dim3(128), 0, st, in, ld, B, n, is_logits, (const float4*)ctx->ori_tab, soft, quat, hinv, (int*)amax, flags);
+  else if ((long long)B >= 8 * fill) launch_chain(ctx->pdl_on, decode_ori_kernel<8>, dim3(cdiv(cdiv(B, 8), 4)), dim3(128), 0, st, in, ld, B, n, is_logits, (const float4*)ctx->ori_tab, soft, quat, hinv, (int*)amax, flags);
+  else launch_chain(ctx->pdl_on, decode_ori_kernel<1>, dim3(cdiv(B, 4)), dim3(128), 0, st, in, ld, B, n, is_logits, (const float4*)ctx->ori_tab, soft, quat, hinv, (int*)amax, flags);
   CK_LAUNCH("decode_ori_kernel");
   return SPEF_OK;
 }
@@ -1924,7 +1924,7 @@ static int decode_pos_ld(spef_ctx* ctx, const float* in, int ld, int B, int n, i
   if (!ctx->pos_tab) return fail(ctx, SPEF_ERR_STATE, "decode_pos: position histogram not set (spef_set_pos_histogram)");
   if (n != ctx->pos_n) return fail(ctx, SPEF_ERR_INVALID, "decode_pos: n = %d but the histogram has %d bins", n, ctx->pos_n);
   if (!in || !pos || B < 1) return fail(ctx, SPEF_ERR_INVALID, "decode_pos: bad argument");
-  decode_pos_kernel<<<cdiv(B, 4), 128, 0, st>>>(in, ld, B, n, is_logits, ctx->pos_tab, soft, pos, flags);
+  launch_chain(ctx->pdl_on, decode_pos_kernel, dim3(cdiv(B, 4)), dim3(128), 0, st, in, ld, B, n, is_logits, (const float4*)ctx->pos_tab, soft, pos, flags);
   CK_LAUNCH("decode_pos_kernel");
   return SPEF_OK;
 }
@@ -1993,7 +1993,7 @@ static int score_internal(spef_ctx* ctx, const float* qp, const float* tp, const
   CK(cudaSetDevice(ctx->cfg.device));
   int grid = cdiv(B, 256);
   if (grid > 4 * ctx->num_sms) grid = 4 * ctx->num_sms;
-  score_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(qp, tp, qt, tt, B, sums, per_image, flags);
+  launch_chain(ctx->pdl_on, score_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, qp, tp, qt, tt, B, sums, per_image, (const uint32_t*)flags);
   CK_LAUNCH("score_kernel");
   return SPEF_OK;
 }
@@ -2496,18 +2496,18 @@ static int temporal_from_logits(spef_ctx* ctx, const float* ori_logits, int ld_o
   // still pose: softmax + decode (inference.py:131-133 -> spe_torch.py:75-76)
   if ((rc = decode_ori_ld(ctx, ori_logits, ld_o, S, no, 1, still_os, still_q, nullptr, nullptr, z.flags, st))) return rc;
   if ((rc = decode_pos_ld(ctx, pos_logits, ld_p, S, np, 1, still_ps, still_p, z.flags, st))) return rc;
-  quat_continuity_kernel<<<cdiv(S, 128), 128, 0, st>>>(still_q, ctx->t_prev_still, has + 2 * S, S);  // inference.py:136-144
+  launch_chain(ctx->pdl_on, quat_continuity_kernel, dim3(cdiv(S, 128)), dim3(128), 0, st, still_q, ctx->t_prev_still, has + 2 * S, S);  // inference.py:136-144
   CK_LAUNCH("quat_continuity_kernel");
   if (!apply_filter) return SPEF_OK;
   // adaptive pdf filters (inference.py:38-39, 164-165)
-  temporal_filter_kernel<<<S, 256, 0, st>>>(still_os, no, ctx->t_ori_state, has, 0.8f, 16.49f, vid_os, d_o);
+  launch_chain(ctx->pdl_on, temporal_filter_kernel, dim3(S), dim3(256), 0, st, (const float*)still_os, no, ctx->t_ori_state, has, 0.8f, 16.49f, vid_os, d_o);
   CK_LAUNCH("temporal_filter_kernel");
-  temporal_filter_kernel<<<S, 256, 0, st>>>(still_ps, np, ctx->t_pos_state, has + S, 0.5f, 48.64f, vid_ps, d_p);
+  launch_chain(ctx->pdl_on, temporal_filter_kernel, dim3(S), dim3(256), 0, st, (const float*)still_ps, np, ctx->t_pos_state, has + S, 0.5f, 48.64f, vid_ps, d_p);
   CK_LAUNCH("temporal_filter_kernel");
   // decode of the filtered pdfs (inference.py:167-168)
   if ((rc = decode_ori_ld(ctx, vid_os, no, S, no, 0, nullptr, vid_q, nullptr, nullptr, z.flags, st))) return rc;
   if ((rc = decode_pos_ld(ctx, vid_ps, np, S, np, 0, nullptr, vid_p, z.flags, st))) return rc;
-  quat_continuity_kernel<<<cdiv(S, 128), 128, 0, st>>>(vid_q, ctx->t_prev_video, has + 3 * S, S);  // inference.py:173-180
+  launch_chain(ctx->pdl_on, quat_continuity_kernel, dim3(cdiv(S, 128)), dim3(128), 0, st, vid_q, ctx->t_prev_video, has + 3 * S, S);  // inference.py:173-180
   CK_LAUNCH("quat_continuity_kernel");
   return SPEF_OK;
 }
