@@ -128,6 +128,7 @@ struct spef_ctx {
   int dwp_enable = 1;  // SPEF_DWP=0: per-layer kernels for the blocks without a single-kernel plan
   int dwp_w_stages = 0; // SPEF_DWP_WST (developer A/B): cap on the project-weight ring depth of the depthwise -> project kernel
   int dwp_opt_skip = 0;
+  int dwp_min_tiles = 37;  // fewer row tiles than this (a few-image step): per-layer kernels instead of the depthwise -> project kernel (SPEF_DWP_MIN_TILES)
   int dwp_s2_box_kb = 60;  // stride-2 depthwise -> project: largest input box (SPEF_DWP_S2_BOX_KB)
   int dwp_force = 0;   // SPEF_DWP_FORCE=1 (tests): expand GEMM + depthwise->project kernel for every block it can run, ahead of the single-kernel plans
   int fb_max_cin = 64; // fuse blocks with Cin <= this (SPEF_FB_MAX_CIN); wider blocks measured faster as three kernels
@@ -434,6 +435,7 @@ extern "C" int spef_create(spef_ctx** out, const spef_config* cfg) {
   if (const char* e = getenv("SPEF_POOL_FUSE")) ctx->pool_fuse = atoi(e) ? 1 : 0;
   if (const char* e = getenv("SPEF_PDL")) ctx->pdl = atoi(e) ? 1 : 0;
   if (const char* e = getenv("SPEF_DWP_OPT_SKIP")) ctx->dwp_opt_skip = atoi(e);
+  if (const char* e = getenv("SPEF_DWP_MIN_TILES")) ctx->dwp_min_tiles = atoi(e);
   if (const char* e = getenv("SPEF_DWP_S2_BOX_KB")) ctx->dwp_s2_box_kb = atoi(e);
   if (const char* e = getenv("SPEF_PDL_MAX_BATCH")) ctx->pdl_max_batch = atoi(e);
   if (const char* e5 = getenv("SPEF_TEMPORAL_GRAPH")) ctx->temporal_graph = atoi(e5) ? 1 : 0;
@@ -1558,7 +1560,7 @@ static int forward_internal(spef_ctx* ctx, const float* images, int B, cudaStrea
     int variant = 0;
     if (next_block < ctx->blocks.size() && ctx->blocks[next_block].first == i) {
       variant = block_variant(ctx, (int)next_block);
-      if (variant == 3 && !ctx->dwp_force && (long long)B * ctx->blocks[next_block].dprm.tiles_y < ctx->num_sms / 4) variant = 0;
+      if (variant == 3 && !ctx->dwp_force && (long long)B * ctx->blocks[next_block].dprm.tiles_y < ctx->dwp_min_tiles) variant = 0;
     }
     if (variant == 3) {
       // expand conv as a GEMM, then depthwise + project in one kernel (its time is reported in the slot of the depthwise layer)
