@@ -431,6 +431,9 @@ extern "C" int spef_create(spef_ctx** out, const spef_config* cfg) {
   ctx->host_pack = (cfg->precision == SPEF_BF16 && cfg->pw_impl == 0) ? 1 : 0;
   if (const char* e = getenv("SPEF_HOST_PACK")) ctx->host_pack = atoi(e) ? 1 : 0;
   if (const char* e = getenv("SPEF_PACK_FRAC")) ctx->pack_frac = atof(e);
+  // first guess of the conversion rate: the host's threads are shared by the ranks of the node (torchrun sets LOCAL_WORLD_SIZE), so eight
+  // ranks start with the packed upload off and let the probe slices decide, one or two ranks start with it on
+  if (const char* e = getenv("LOCAL_WORLD_SIZE")) { const int r = atoi(e); if (r > 1) ctx->pack_rc /= (double)r; }
   if (getenv("SPEF_HEAD_WIDE")) ctx->head_wide = 1;
   if (const char* e = getenv("SPEF_POOL_FUSE")) ctx->pool_fuse = atoi(e) ? 1 : 0;
   if (const char* e = getenv("SPEF_PDL")) ctx->pdl = atoi(e) ? 1 : 0;
@@ -2240,11 +2243,11 @@ static int upload_packed(spef_ctx* ctx, int s, const float* images_host, float* 
   // The balance assumes two independent resources; they are not when the host's memory system is what limits the copies (8 ranks on
   // one 32-core host: the plain copies already run at the concurrent H2D roof, the conversion threads crawl at 3 GB/s and packing a
   // tenth of the batch cost 12 % end to end).  The model's own gain, 1 + r_c / (2 r_d), is the test: below 1.25 the batch goes
-  // as it is, and every eighth submit packs a small probe slice so that r_c keeps being measured.
+  // as it is, and every sixteenth submit packs a small probe slice so that r_c keeps being measured.
   if (ctx->pack_frac < 0.0) {
     const bool worth = ctx->pack_rc >= (ctx->pack_on ? 0.5 : 0.6) * ctx->pack_rd;
     ctx->pack_on = worth ? 1 : 0;
-    if (!worth) head_blk = ((ctx->pack_calls & 7) == 0 && nblk >= 64) ? 16 : 0;
+    if (!worth) head_blk = ((ctx->pack_calls & 15) == 0 && nblk >= 64) ? 8 : 0;
   }
   ctx->pack_calls++;
   size_t head = head_blk * BLK;
