@@ -682,7 +682,6 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     const int tt = act ? t : 0;
     const int r = tt / TWI, j = tt - r * TWI;
     const uint32_t xrow = tc::smem_u32(x_s) + (uint32_t)tt * 128u, swz = ((uint32_t)tt & 7u) << 4;
-    const uint32_t lut_u = tc::smem_u32(bp_s + 128);
     const uint32_t kc1 = (uint32_t)(p.n_px * 128);                      // second K chunk of an x stage (strips 2, 3)
     // The patch geometry is a compile-time constant per image dtype (the host encodes the TMA box from the same numbers), so every
     // tap load is [thread base + immediate]: the first version (run-time row / plane pitch, strip loop not unrolled) ran 318
@@ -704,21 +703,27 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
           for (int st = 0; st < 4; ++st) {
             uint32_t pk[14];
             if constexpr (U8) {
-              uint32_t tap[28];
+              // bf16(u8 / 255.0f) without the table: u8 -> float exactly (0x4B000000 | u8 is 2^23 + u8), times float(1 / 255), rounded to
+              // BF16 -- equal to the table entry bf16(float(u8) / 255.0f) for all 256 values (the two float32 values differ for 126 of
+              // them, never after the rounding to BF16: enumerated in tests/test_host.py).  The table cost a second shared-memory load
+              // per tap with random bank conflicts: the uint8 stem took 297 us against 192 us with float pixels.
+              float f[28];
 #pragma unroll
               for (int ci = 0; ci < 3; ++ci)
 #pragma unroll
-                for (int ky = 0; ky < 3; ++ky)
+                for (int ky = 0; ky < 3; ++ky) {
+                  // kx = 0 sits at an odd byte, kx = 1, 2 are an aligned pair (PX0 - 3 is odd, every pitch even): two loads per row of taps
+                  uint32_t p0, p12;
+                  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(p0) : "r"(pb + (uint32_t)(ci * PPLANE + ky * PROW + st * SSTEP)));
+                  asm volatile("ld.shared.u16 %0, [%1];" : "=r"(p12) : "r"(pb + (uint32_t)(ci * PPLANE + ky * PROW + st * SSTEP + 1)));
+                  const uint32_t px[3] = {p0, p12 & 0xffu, p12 >> 8};
 #pragma unroll
-                  for (int kx = 0; kx < 3; ++kx) {
-                    uint32_t px, h;
-                    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(px) : "r"(pb + (uint32_t)(ci * PPLANE + ky * PROW + st * SSTEP + kx)));
-                    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(h) : "r"(lut_u + px * 2u));
-                    tap[(ci * 3 + ky) * 3 + kx] = h;
-                  }
-              tap[27] = 0u;
+                  for (int kx = 0; kx < 3; ++kx)
+                    f[(ci * 3 + ky) * 3 + kx] = __fmul_rn(__fsub_rn(__uint_as_float(0x4B000000u | px[kx]), 8388608.0f), 1.0f / 255.0f);
+                }
+              f[27] = 0.f;
 #pragma unroll
-              for (int k = 0; k < 14; ++k) pk[k] = tap[2 * k] | (tap[2 * k + 1] << 16);
+              for (int k = 0; k < 14; ++k) asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pk[k]) : "f"(f[2 * k + 1]), "f"(f[2 * k]));
             } else {
               float f[28];
 #pragma unroll

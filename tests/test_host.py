@@ -257,3 +257,15 @@ def test_host_pack_rounds_like_the_device():
         assert torch.equal(torch.isnan(got), nan)
         assert torch.equal(got[~nan].view(torch.int16), want[~nan].view(torch.int16))
         assert int(dst[:off].abs().sum()) == 0 and int(dst[off + n:].abs().sum()) == 0   # nothing written outside
+
+
+def test_uint8_pixel_to_bf16_without_the_table():
+    """The fused stem turns a uint8 pixel into its BF16 operand as bf16(float(u8) * float(1 / 255)) (csrc/fused_block_t.cuh); the
+    reference tensor is float(u8) / 255 (ToTensor), whose BF16 rounding the table-based paths store: equal for all 256 values,
+    although the two float32 values differ for about half of them; and the u8 -> float trick (2^23 + u8) - 2^23 is exact."""
+    u = np.arange(256, dtype=np.float32)
+    ref = torch.from_numpy((u / np.float32(255)).astype(np.float32)).to(torch.bfloat16).view(torch.int16)
+    mul = torch.from_numpy((u * np.float32(1.0 / 255.0)).astype(np.float32)).to(torch.bfloat16).view(torch.int16)
+    assert torch.equal(ref, mul)
+    magic = (np.arange(256, dtype=np.uint32) | np.uint32(0x4B000000)).view(np.float32) - np.float32(8388608.0)
+    assert np.array_equal(magic, u)
