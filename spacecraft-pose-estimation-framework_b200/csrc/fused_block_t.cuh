@@ -703,7 +703,7 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
           for (int st = 0; st < 4; ++st) {
             uint32_t pk[14];
             if constexpr (U8) {
-              // bf16(u8 / 255.0f) without the table: u8 -> float exactly (0x4B000000 | u8 is 2^23 + u8), times float(1 / 255), rounded to
+              // bf16(u8 / 255.0f) without the table: u8 -> float exactly (0x4B0000xx is 2^23 + u8), times float(1 / 255), rounded to
               // BF16 -- equal to the table entry bf16(float(u8) / 255.0f) for all 256 values (the two float32 values differ for 126 of
               // them, never after the rounding to BF16: enumerated in tests/test_host.py).  The table cost a second shared-memory load
               // per tap with random bank conflicts: the uint8 stem took 297 us against 192 us with float pixels.
@@ -716,10 +716,12 @@ fused_block_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
                   uint32_t p0, p12;
                   asm volatile("ld.shared.u8 %0, [%1];" : "=r"(p0) : "r"(pb + (uint32_t)(ci * PPLANE + ky * PROW + st * SSTEP)));
                   asm volatile("ld.shared.u16 %0, [%1];" : "=r"(p12) : "r"(pb + (uint32_t)(ci * PPLANE + ky * PROW + st * SSTEP + 1)));
-                  const uint32_t px[3] = {p0, p12 & 0xffu, p12 >> 8};
+                  // one PRMT builds the float 2^23 + u8 (0x4B0000xx), one FMA takes 2^23 * c off again: fma(2^23 + u8, c, -(2^23 * c)) rounds
+                  // u8 * c once (2^23 * c is exact), i.e. it IS the product
+                  constexpr float C255 = 1.0f / 255.0f, OFF = -8388608.0f * C255;
+                  const uint32_t m[3] = {__byte_perm(p0, 0x4B000000u, 0x7440), __byte_perm(p12, 0x4B000000u, 0x7440), __byte_perm(p12, 0x4B000000u, 0x7441)};
 #pragma unroll
-                  for (int kx = 0; kx < 3; ++kx)
-                    f[(ci * 3 + ky) * 3 + kx] = __fmul_rn(__fsub_rn(__uint_as_float(0x4B000000u | px[kx]), 8388608.0f), 1.0f / 255.0f);
+                  for (int kx = 0; kx < 3; ++kx) f[(ci * 3 + ky) * 3 + kx] = __fmaf_rn(__uint_as_float(m[kx]), C255, OFF);
                 }
               f[27] = 0.f;
 #pragma unroll

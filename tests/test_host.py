@@ -267,5 +267,11 @@ def test_uint8_pixel_to_bf16_without_the_table():
     ref = torch.from_numpy((u / np.float32(255)).astype(np.float32)).to(torch.bfloat16).view(torch.int16)
     mul = torch.from_numpy((u * np.float32(1.0 / 255.0)).astype(np.float32)).to(torch.bfloat16).view(torch.int16)
     assert torch.equal(ref, mul)
-    magic = (np.arange(256, dtype=np.uint32) | np.uint32(0x4B000000)).view(np.float32) - np.float32(8388608.0)
-    assert np.array_equal(magic, u)
+    magic = (np.arange(256, dtype=np.uint32) | np.uint32(0x4B000000)).view(np.float32)
+    assert np.array_equal(magic - np.float32(8388608.0), u)
+    # the kernel's single FMA: fma(2^23 + u8, c, -(2^23 * c)) -- exact in float64 (24 x 24 bit product), rounded once to float32
+    c = np.float32(1.0 / 255.0)
+    off = np.float32(-8388608.0) * c
+    assert np.float64(off) == -8388608.0 * np.float64(c)                      # 2^23 * c is exact
+    fma = (magic.astype(np.float64) * np.float64(c) + np.float64(off)).astype(np.float32)
+    assert np.array_equal(fma, (u * c).astype(np.float32))
